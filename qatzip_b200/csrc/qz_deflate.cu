@@ -1,0 +1,547 @@
+/* qz_deflate.cu -- sm_100a DEFLATE compressor: one warp per piece, everything the warp touches
+ * lives in its private slice of shared memory (input piece, hash table, histograms), so HBM
+ * sees each input byte once and each output byte once.
+ *
+ * This kernel is the replacement for the QAT compress request submitted at reference
+ * src/qatzip.c:1542 (cpaDcCompressData2, stateless deflate, CPA_DC_FLUSH_FINAL / _FULL) with the
+ * session set-up of reference src/qatzip_utils.c:264-341 (dynamic or static Huffman, stored
+ * fallback, CRC-32 of the input returned in res.checksum).
+ *
+ * Per piece the warp runs four phases, all warp-synchronous (no CTA barrier):
+ *   1 load    global -> shared, 16 B per lane, then CRC-32 over right-aligned per-lane strips
+ *   2 match   32 positions per step: 4-byte hash probe of a u16 table, verify + extend,
+ *             ballot-driven greedy selection, tokens to an L2-resident scratch, histograms
+ *   3 code    sort by frequency (warp bitonic), in-place length assignment, canonical codes,
+ *             dynamic header; cheapest of stored / fixed / dynamic is kept
+ *   4 emit    32 tokens per step: code lookup, warp scan of bit lengths, OR into a staging
+ *             window, full words flushed coalesced to the piece's slot
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qz_kernels.cuh"
+#include "qz_huffman.h"
+#include "qz_crc32.h"
+
+#define FULL 0xffffffffu
+#define QZ_NONE16 0xffffu
+#define QZ_LANE_CAP 36          /* in-lane match extension cap; longer matches are finished by the warp */
+#define QZ_MAX_MATCH 258
+#define QZ_STAGE_WORDS 64
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+/* unaligned 32-bit read from a 4-byte aligned shared byte array */
+__device__ __forceinline__ uint32_t ld32u(const uint8_t *base, uint32_t off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+
+template <int N>
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t *a, uint32_t lane)
+{
+#pragma unroll 1
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < N; i += 32) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+__device__ __forceinline__ void warp_sort_keys(uint32_t *keys, int n, uint32_t lane)
+{
+    int N = 32; while (N < n) N <<= 1;
+    for (int i = n + lane; i < N; i += 32) keys[i] = 0xffffffffu;
+    __syncwarp();
+    switch (N) {
+    case 32: warp_bitonic_sort<32>(keys, lane); break;
+    case 64: warp_bitonic_sort<64>(keys, lane); break;
+    case 128: warp_bitonic_sort<128>(keys, lane); break;
+    case 256: warp_bitonic_sort<256>(keys, lane); break;
+    default: warp_bitonic_sort<512>(keys, lane); break;
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+/* scratch carved out of the (dead after phase 2) hash-table region */
+struct CodeScratch {
+    uint32_t keys[512];                 /* sort keys; later the bit staging window */
+    uint16_t ids[QZ_NUM_LL + 2];
+    uint8_t ll_len[288];
+    uint8_t d_len[32];
+    QzDynHeader hdr;
+};
+
+template <int PIECE_LOG2, int HB>
+struct WarpSmem {
+    static constexpr int PIECE = 1 << PIECE_LOG2;
+    uint8_t piece[PIECE + 32];              /* +32: zero pad so unaligned reads past n are defined */
+    union {
+        uint16_t table[1 << HB];
+        CodeScratch cs;
+    } u;
+    uint32_t hist[QZ_NUM_LL + 2 + QZ_NUM_D + 2]; /* [0,286) lit/len, [288,318) dist; later the code tables */
+};
+#define QZ_DOFF 288
+
+template <int PIECE_LOG2, int HB>
+__global__ void __launch_bounds__(512) qzb_deflate_pieces_kernel(QzbCompressJob job)
+{
+    constexpr int PIECE = 1 << PIECE_LOG2;
+    typedef WarpSmem<PIECE_LOG2, HB> WS;
+    static_assert(sizeof(CodeScratch) <= (sizeof(uint16_t) << HB), "code scratch must fit in the hash table");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_crc_tab[256];
+    __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
+    constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
+
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
+    if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
+    __syncthreads();
+
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint32_t *toks = job.tok_scratch + (size_t)gwarp * PIECE;
+
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(job.ticket, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= job.npieces) break;
+
+        /* ---- which bytes ---- */
+        const uint32_t chunk = g / job.pieces_per_chunk, k = g - chunk * job.pieces_per_chunk;
+        const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
+        const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
+        const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+        const uint32_t p_off = k << PIECE_LOG2;
+        const uint32_t n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u;
+        const bool last_piece = (p_off + n == chunk_len);
+        const bool bfinal = last_piece && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
+        const uint8_t *src = job.src + chunk_off + p_off;
+        uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
+        uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
+
+        /* ---- phase 1: load + CRC ---- */
+        {
+            uint4 *d4 = reinterpret_cast<uint4 *>(ws.piece);
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+                uint32_t nv = n >> 4;
+                for (uint32_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+                for (uint32_t i = (nv << 4) + lane; i < n; i += 32) ws.piece[i] = src[i];
+            } else {
+                for (uint32_t i = lane; i < n; i += 32) ws.piece[i] = src[i];
+            }
+            if (lane < 32) ws.piece[n + lane] = 0;          /* zero pad */
+            for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
+            for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
+            __syncwarp();
+            /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
+            int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
+            if (lo < 0) lo = 0;
+            uint32_t c = 0xffffffffu;
+            for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ ws.piece[i]) & 0xff] ^ (c >> 8);
+            c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
+                if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
+            }
+            if (lane == 0) job.piece_crc[g] = c;
+        }
+
+        /* ---- phase 2: match + select + tokens ---- */
+        uint32_t ntok = 0, extra_acc = 0;
+        {
+            uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t p = base + lane;
+                const uint32_t v = ld32u(ws.piece, p);
+                const bool can = p + 4 <= n;
+                const uint32_t h = (v * 2654435761u) >> (32 - HB);
+                uint32_t cand = can ? ws.u.table[h] : QZ_NONE16;
+                __syncwarp();
+                if (can) ws.u.table[h] = (uint16_t)p;
+                __syncwarp();
+                uint32_t L = 0;
+                const uint32_t maxl = min((uint32_t)QZ_MAX_MATCH, n - min(p, n));
+                if (cand != QZ_NONE16 && ld32u(ws.piece, cand) == v) {
+                    uint32_t l = 4;
+                    while (l < QZ_LANE_CAP) {
+                        uint32_t x = ld32u(ws.piece, p + l) ^ ld32u(ws.piece, cand + l);
+                        if (x) { l += (__ffs(x) - 1) >> 3; break; }
+                        l += 4;
+                    }
+                    L = min(l, maxl);
+                }
+                const uint32_t valid = __ballot_sync(FULL, p < n);
+                const uint32_t M = __ballot_sync(FULL, L >= 4);
+                uint32_t tokmask = 0, matchmask = 0, cur = entry;
+                if (cur >= 32) { entry = cur - 32; continue; }
+                for (;;) {
+                    uint32_t rest = M & (FULL << cur);
+                    if (!rest) { tokmask |= (FULL << cur); cur = 32; break; }
+                    uint32_t m = __ffs(rest) - 1;
+                    tokmask |= (FULL << cur) & ~(FULL << m);      /* literals cur..m-1 */
+                    tokmask |= 1u << m; matchmask |= 1u << m;
+                    uint32_t Lm = __shfl_sync(FULL, L, m);
+                    if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
+                        const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
+                        const uint32_t mx = min((uint32_t)QZ_MAX_MATCH, n - pm);
+                        Lm = QZ_LANE_CAP;
+                        while (Lm < mx) {
+                            uint32_t kk = Lm + lane;
+                            bool eq = kk < mx && ws.piece[pm + kk] == ws.piece[cm + kk];
+                            uint32_t bal = __ballot_sync(FULL, eq);
+                            if (bal == FULL) { Lm += 32; continue; }
+                            Lm += __ffs(~bal) - 1; break;
+                        }
+                        Lm = min(Lm, mx);
+                        if (lane == m) L = Lm;
+                    }
+                    cur = m + Lm;
+                    if (cur >= 32) break;
+                }
+                entry = cur - 32;
+                tokmask &= valid;
+                const bool is_tok = (tokmask >> lane) & 1, is_match = (matchmask >> lane) & 1;
+                if (is_tok) {
+                    uint32_t t;
+                    if (is_match) {
+                        const uint32_t dist = p - cand;
+                        uint32_t ls, le, lv, ds, de, dv;
+                        qz_len_code(L, &ls, &le, &lv);
+                        qz_dist_code(dist, &ds, &de, &dv);
+                        atomicAdd(&ws.hist[ls], 1u);
+                        atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
+                        extra_acc += le + de;
+                        t = 0x80000000u | ((L - 3) << 16) | (dist - 1);
+                    } else {
+                        t = v & 0xff;
+                        atomicAdd(&ws.hist[t], 1u);
+                    }
+                    toks[ntok + __popc(tokmask & lanemask_lt())] = t;
+                }
+                ntok += __popc(tokmask);
+            }
+        }
+        __syncwarp();
+        const uint32_t extra_total = warp_sum(extra_acc);
+
+        /* ---- phase 3: code construction ---- */
+        CodeScratch &cs = ws.u.cs;
+        uint32_t out_bytes = 0;
+        int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
+        {
+            if (lane == 0) {
+                ws.hist[256] = 1;
+                qz_huff_force_two(ws.hist, QZ_NUM_LL);
+                qz_huff_force_two(ws.hist + QZ_DOFF, QZ_NUM_D);
+            }
+            for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
+            cs.d_len[lane] = 0;
+            __syncwarp();
+            /* literal/length alphabet */
+            int nk = 0;
+            for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
+                uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.hist[s] : 0;
+                uint32_t bal = __ballot_sync(FULL, f != 0);
+                if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
+                nk += __popc(bal);
+            }
+            __syncwarp();
+            warp_sort_keys(cs.keys, nk, lane);
+            if (lane == 0) qz_huff_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len);
+            __syncwarp();
+            /* distance alphabet */
+            {
+                uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
+                uint32_t bal = __ballot_sync(FULL, f != 0);
+                if (f) cs.keys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
+                nk = __popc(bal);
+                __syncwarp();
+                warp_sort_keys(cs.keys, nk, lane);
+                if (lane == 0) qz_huff_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len);
+                __syncwarp();
+            }
+            /* cost of each block type */
+            uint32_t dynb = 0, fixb = 0;
+            for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
+            if (lane < QZ_NUM_D) { uint32_t f = ws.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
+            dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
+            /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
+            if (lane == 0) qz_dyn_header_plan(cs.ll_len, cs.d_len, &cs.hdr);
+            __syncwarp();
+            dynb += cs.hdr.bits;
+            const uint32_t storedb = (5 + n) * 8;
+            if (job.static_huffman) dynb = 0xffffffffu;
+            btype = (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
+            if (n == 0) btype = 1;
+        }
+
+        if (btype == 0) {
+            /* stored block: the piece starts byte-aligned, so the 3 header bits + pad are one byte */
+            if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
+            for (uint32_t i = lane; i < n; i += 32) slot[5 + i] = ws.piece[i];
+            out_bytes = 5 + n;
+        } else {
+            /* code tables go where the histograms were: code | len << 16 */
+            QzBitWriter bw;
+            uint32_t bitpos = 0, flushed = 0;
+            if (lane == 0) {
+                if (btype == 1) {
+                    for (int s = 0; s < 288; s++) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
+                    for (int s = 0; s < 32; s++) cs.d_len[s] = 5;
+                }
+                qz_huff_codes(cs.ll_len, 288, ws.hist);
+                qz_huff_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF);
+                qz_bw_init(&bw, slotw);
+                if (btype == 2) qz_dyn_header_write(&bw, &cs.hdr, bfinal);
+                else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
+                bitpos = qz_bw_bitpos(&bw); flushed = bw.wpos;
+            }
+            bitpos = __shfl_sync(FULL, bitpos, 0); flushed = __shfl_sync(FULL, flushed, 0);
+            uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
+            uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
+            for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+            __syncwarp();
+            if (lane == 0) st[0] = pend;
+            __syncwarp();
+
+            /* ---- phase 4: emit ---- */
+            for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
+                uint64_t bits = 0; uint32_t nb = 0;
+                if (t0 + lane < ntok) {
+                    const uint32_t t = __ldcg(toks + t0 + lane);
+                    if (t & 0x80000000u) {
+                        uint32_t ls, le, lv, ds, de, dv;
+                        qz_len_code(((t >> 16) & 0xff) + 3, &ls, &le, &lv);
+                        qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
+                        const uint32_t lc = ws.hist[ls], dc = ws.hist[QZ_DOFF + ds];
+                        bits = lc & 0xffff; nb = lc >> 16;
+                        bits |= (uint64_t)lv << nb; nb += le;
+                        bits |= (uint64_t)(dc & 0xffff) << nb; nb += dc >> 16;
+                        bits |= (uint64_t)dv << nb; nb += de;
+                    } else {
+                        const uint32_t c = ws.hist[t];
+                        bits = c & 0xffff; nb = c >> 16;
+                    }
+                }
+                uint32_t incl = nb;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                if (nb) {
+                    const uint32_t pos = bitpos + incl - nb - (flushed << 5);
+                    const uint32_t w = pos >> 5, sh = pos & 31;
+                    const uint64_t lo = bits << sh;
+                    const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
+                    if ((uint32_t)lo) atomicOr(&st[w], (uint32_t)lo);
+                    if ((uint32_t)(lo >> 32)) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
+                    if (hi) atomicOr(&st[w + 2], hi);
+                }
+                __syncwarp();
+                bitpos += total;
+                const uint32_t nfull = (bitpos >> 5) - flushed;
+                for (uint32_t i = lane; i < nfull; i += 32) slotw[flushed + i] = st[i];
+                const uint32_t carry = st[nfull];
+                __syncwarp();
+                for (uint32_t i = lane; i <= nfull + 2 && i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+                __syncwarp();
+                if (lane == 0) st[0] = carry;
+                __syncwarp();
+                flushed += nfull;
+            }
+            /* end-of-block, then byte alignment: final blocks pad, others append an empty stored block */
+            if (lane == 0) {
+                bw.words = slotw; bw.wpos = flushed; bw.acc = st[0]; bw.nacc = bitpos & 31;
+                const uint32_t eob = ws.hist[256];
+                qz_bw_put(&bw, eob & 0xffff, eob >> 16);
+                if (!bfinal) {
+                    qz_bw_put(&bw, 0, 3);
+                    qz_bw_align_byte(&bw);
+                    qz_bw_put(&bw, 0x0000u, 16);
+                    qz_bw_put(&bw, 0xffffu, 16);
+                }
+                out_bytes = qz_bw_finish(&bw);
+            }
+            out_bytes = __shfl_sync(FULL, out_bytes, 0);
+        }
+        if (lane == 0) job.piece_len[g] = out_bytes;
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Framing: sizes -> exclusive scan -> headers, payload gather, footers.
+ * Replaces doCompressOut's per-chunk header gen / payload memcpy / crc32_combine / footer gen
+ * (reference src/qatzip.c:1699-1716, src/qatzip_gzip.c:98-143,228-237, src/qatzip_lz4.c:104-143). */
+
+__device__ __forceinline__ uint32_t qzb_hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : 0u; }
+__device__ __forceinline__ uint32_t qzb_ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : 0u; }
+
+__global__ void qzb_chunk_sizes_kernel(QzbCompressJob job)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= job.nchunks) return;
+    uint32_t g0 = c * job.pieces_per_chunk, g1 = min(g0 + job.pieces_per_chunk, job.npieces), payload = 0;
+    for (uint32_t g = g0; g < g1; g++) payload += job.piece_len[g];
+    job.chunk_total[c] = qzb_hdr_sz(job.fmt) + payload + qzb_ftr_sz(job.fmt);
+}
+
+/* single-CTA exclusive scan of chunk_total into chunk_off[0..nchunks] */
+__global__ void __launch_bounds__(1024) qzb_scan_kernel(const uint32_t *in, uint64_t *out, uint32_t n)
+{
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? in[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(FULL, wi, o); if (lane >= (uint32_t)o) wi += y; }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        uint64_t excl = s_carry + s_warp[warp] + incl - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+#include "qz_xxh32.h"
+__device__ __forceinline__ void st32le(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+/* one CTA (128 threads) per chunk */
+__global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
+{
+    const uint32_t c = blockIdx.x;
+    const uint64_t off = job.chunk_off[c];
+    const uint32_t total = job.chunk_total[c];
+    if (off + total > job.dst_cap) return;             /* host reports QZ_BUF_ERROR for this and later chunks */
+    const uint32_t g0 = c * job.pieces_per_chunk, g1 = min(g0 + job.pieces_per_chunk, job.npieces);
+    const uint64_t chunk_in = (uint64_t)c * job.chunk_sz;
+    const uint64_t rem = job.src_len > chunk_in ? job.src_len - chunk_in : 0;
+    const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+    const uint32_t hs = qzb_hdr_sz(job.fmt), fs = qzb_ftr_sz(job.fmt), payload = total - hs - fs;
+    const uint32_t PIECE = 1u << job.piece_log2;
+    uint8_t *d = job.dst + off;
+    __shared__ uint32_t s_cksum;
+    if (threadIdx.x == 0) {
+        uint32_t ck;
+        if (job.fmt == QZB_FMT_LZ4) ck = job.chunk_cksum[c];      /* XXH32 written by the xxh kernel */
+        else {
+            ck = 0;
+            for (uint32_t g = g0; g < g1; g++) {
+                uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE);
+                ck = (g == g0) ? job.piece_crc[g] : qz_crc32_combine(ck, job.piece_crc[g], pn);
+            }
+            job.chunk_cksum[c] = ck;
+        }
+        s_cksum = ck;
+        switch (job.fmt) {
+        case QZB_FMT_GZIP_EXT:
+            d[10] = 12; d[11] = 0; d[12] = 'Q'; d[13] = 'Z'; d[14] = 8; d[15] = 0;
+            st32le(d + 16, chunk_len); st32le(d + 20, payload);
+            /* fall through */
+        case QZB_FMT_GZIP:
+            d[0] = 0x1f; d[1] = 0x8b; d[2] = 8; d[3] = (job.fmt == QZB_FMT_GZIP_EXT) ? 4 : 0;
+            d[4] = d[5] = d[6] = d[7] = 0; d[8] = 0; d[9] = 0xff;
+            break;
+        case QZB_FMT_4B: st32le(d, payload); break;
+        case QZB_FMT_LZ4:
+            st32le(d, 0x184D2204u); d[4] = 0x4C; d[5] = 0x40; st32le(d + 6, chunk_len); st32le(d + 10, 0);
+            d[14] = (uint8_t)(qz_xxh32(d + 4, 10, 0) >> 8);
+            break;
+        default: break;
+        }
+    }
+    /* payload gather: pieces are contiguous runs; copy byte-wise with 4-byte fast path when aligned */
+    uint32_t o = hs;
+    for (uint32_t g = g0; g < g1; g++) {
+        const uint32_t len = job.piece_len[g];
+        const uint8_t *s = job.slots + (size_t)g * job.slot_stride;
+        uint8_t *dd = d + o;
+        const uint32_t mis = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
+        const uint32_t head = min(mis, len);
+        if (threadIdx.x < head) dd[threadIdx.x] = s[threadIdx.x];
+        const uint32_t nw = (len - head) >> 2;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dd + head);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(s);     /* slot is 16-byte aligned */
+        const uint32_t sh = head * 8;
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x)
+            dw[i] = sh ? __funnelshift_r(sw[i], sw[i + 1], sh) : sw[i];
+        for (uint32_t i = head + (nw << 2) + threadIdx.x; i < len; i += blockDim.x) dd[i] = s[i];
+        o += len;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && fs) {
+        uint8_t *f = d + hs + payload;
+        if (job.fmt == QZB_FMT_LZ4) { st32le(f, 0); st32le(f + 4, s_cksum); }
+        else { st32le(f, s_cksum); st32le(f + 4, chunk_len); }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps)
+{
+    size_t per = (piece_log2 == 13 && hb == 11) ? sizeof(WarpSmem<13, 11>) :
+                 (piece_log2 == 13 && hb == 12) ? sizeof(WarpSmem<13, 12>) :
+                 (piece_log2 == 14 && hb == 12) ? sizeof(WarpSmem<14, 12>) : sizeof(WarpSmem<14, 13>);
+    return per * (size_t)warps;
+}
+
+template <int P, int H>
+static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps, cudaStream_t st)
+{
+    size_t smem = sizeof(WarpSmem<P, H>) * (size_t)warps;
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_pieces_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qzb_deflate_pieces_kernel<P, H><<<grid, warps * 32, smem, st>>>(job);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, cudaStream_t st)
+{
+    if (job->piece_log2 == 13 && hb == 11) return launch_deflate<13, 11>(*job, grid, warps, st);
+    if (job->piece_log2 == 13 && hb == 12) return launch_deflate<13, 12>(*job, grid, warps, st);
+    if (job->piece_log2 == 14 && hb == 12) return launch_deflate<14, 12>(*job, grid, warps, st);
+    if (job->piece_log2 == 14 && hb == 13) return launch_deflate<14, 13>(*job, grid, warps, st);
+    return cudaErrorInvalidValue;
+}
+
+extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)
+{
+    qzb_chunk_sizes_kernel<<<(job->nchunks + 255) / 256, 256, 0, st>>>(*job);
+    qzb_scan_kernel<<<1, 1024, 0, st>>>(job->chunk_total, job->chunk_off, job->nchunks);
+    qzb_frame_kernel<<<job->nchunks, 128, 0, st>>>(*job);
+    return cudaGetLastError();
+}

@@ -1,0 +1,630 @@
+/* qz_engine.cu -- host-side chunk engine (see qz_engine.h).
+ *
+ * Reference loops replaced here:
+ *   compress    doCompressIn  (src/qatzip.c:1483-1604)  chunk loop, staging copy, submit
+ *               doCompressOut (src/qatzip.c:1610-1764)  poll, dest-space check, stitch, CRC combine
+ *   decompress  doDecompressIn/Out (src/qatzip.c:2103-2404) + checkHeader (src/qatzip_utils.c:1232)
+ * QAT's DMA rings become: pinned pages + cudaMemcpyAsync on per-slot streams, two slots in
+ * flight so the H2D of batch k+1 and the D2H of batch k-1 overlap the kernels of batch k.
+ * There is no polling thread and no sleep/back-off: completion is a CUDA event.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include "qz_engine.h"
+#include "qz_kernels.cuh"
+#include "qz_crc32.h"
+#include "qz_xxh32.h"
+
+extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
+extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps);
+extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
+
+/* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
+enum { RC_OK = 0, RC_PARAMS = -1, RC_FAIL = -2, RC_BUF_ERROR = -3, RC_DATA_ERROR = -4 };
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qzb_log_cuda(#call, e_, __LINE__); return RC_FAIL; } } while (0)
+static void qzb_log_cuda(const char *what, cudaError_t e, int line)
+{
+    if (getenv("QZB200_DEBUG")) fprintf(stderr, "[qatzip_b200] %s failed at qz_engine.cu:%d: %s\n", what, line, cudaGetErrorString(e));
+}
+
+/* ------------------------------------------------------------------ runtime + tuning */
+static std::once_flag g_rt_once;
+static int g_ndev = 0;
+extern "C" int qzb_runtime_devices(void)
+{
+    std::call_once(g_rt_once, [] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+        g_ndev = n;
+    });
+    return g_ndev;
+}
+static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+extern "C" int qzb_runtime_default_device(void)
+{
+    int n = qzb_runtime_devices();
+    if (n <= 0) return -1;
+    int d = env_int("QZB200_DEVICE", -1);
+    if (d < 0) d = env_int("LOCAL_RANK", 0);
+    return d % n;
+}
+extern "C" void qzb_get_tuning(QzbTuning *t)
+{
+    t->piece_log2 = env_int("QZB200_PIECE_LOG2", 13);
+    if (t->piece_log2 != 13 && t->piece_log2 != 14) t->piece_log2 = 13;
+    t->hash_bits = env_int("QZB200_HASH_BITS", t->piece_log2 == 13 ? 11 : 12);
+    if (t->piece_log2 == 13 && t->hash_bits != 11 && t->hash_bits != 12) t->hash_bits = 11;
+    if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
+    t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = as many as shared memory allows */
+    int mb = env_int("QZB200_BATCH_MB", 64);
+    if (mb < 1) mb = 1;
+    if (mb > 1024) mb = 1024;
+    t->batch_bytes = (size_t)mb << 20;
+}
+
+/* ------------------------------------------------------------------ pinned registry */
+static std::mutex g_pin_lock;
+static std::map<uintptr_t, size_t> g_pinned;
+extern "C" void *qzb_pinned_alloc(size_t sz)
+{
+    if (qzb_runtime_devices() <= 0) return NULL;
+    void *p = NULL;
+    if (cudaHostAlloc(&p, sz ? sz : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+    std::lock_guard<std::mutex> g(g_pin_lock);
+    g_pinned[(uintptr_t)p] = sz ? sz : 1;
+    return p;
+}
+extern "C" int qzb_pinned_free(void *p)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pin_lock);
+        auto it = g_pinned.find((uintptr_t)p);
+        if (it == g_pinned.end()) return 0;
+        g_pinned.erase(it);
+    }
+    cudaFreeHost(p);
+    return 1;
+}
+extern "C" int qzb_pinned_contains(const void *p, size_t len)
+{
+    std::lock_guard<std::mutex> g(g_pin_lock);
+    auto it = g_pinned.upper_bound((uintptr_t)p);
+    if (it == g_pinned.begin()) return 0;
+    --it;
+    return (uintptr_t)p >= it->first && (uintptr_t)p + (len ? len : 1) <= it->first + it->second;
+}
+
+/* ------------------------------------------------------------------ buffers */
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return RC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + (n >> 3) + 4096;
+        if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); if (cudaMalloc(&p, n) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return RC_FAIL; } want = n; }
+        cap = want; return RC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return RC_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + (n >> 3) + 4096;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; return RC_FAIL; }
+        cap = want; return RC_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr;
+    DevBuf d_in, d_slots, d_out, d_meta, d_tok, d_members, d_results;
+    HostBuf h_meta, h_in, h_out, h_members, h_results;
+    /* bookkeeping of the batch currently in flight */
+    bool busy = false;
+    uint64_t in_off = 0, in_len = 0;
+    uint32_t nchunks = 0;
+    size_t first_member = 0, nmembers = 0;
+    uint64_t span_src = 0, span_len = 0, out_base = 0, out_len = 0;
+};
+
+struct QzbEngine {
+    int device = 0;
+    int sm_count = 148;
+    QzbTuning tune;
+    Slot slot[2];
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" QzbEngine *qzb_engine_create(int device)
+{
+    if (device < 0 || device >= qzb_runtime_devices()) return NULL;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+    QzbEngine *e = new QzbEngine();
+    e->device = device;
+    qzb_get_tuning(&e->tune);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    for (auto &s : e->slot) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NULL; }
+        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_k1);
+        cudaEventCreateWithFlags(&s.ev_meta, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
+    }
+    return e;
+}
+extern "C" void qzb_engine_destroy(QzbEngine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (auto &s : e->slot) {
+        if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.ev_meta) cudaEventDestroy(s.ev_meta);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        s.d_in.release(); s.d_slots.release(); s.d_out.release(); s.d_meta.release(); s.d_tok.release();
+        s.d_members.release(); s.d_results.release();
+        s.h_meta.release(); s.h_in.release(); s.h_out.release(); s.h_members.release(); s.h_results.release();
+    }
+    delete e;
+}
+
+/* ------------------------------------------------------------------ compress */
+static uint32_t hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : 0u; }
+static uint32_t ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : 0u; }
+
+struct MetaLayout { size_t piece_len, piece_crc, chunk_total, chunk_cksum, chunk_off, ticket, total; };
+static MetaLayout meta_layout(uint32_t npieces, uint32_t nchunks)
+{
+    MetaLayout m; size_t o = 0;
+    m.chunk_off = o; o += align_up((size_t)(nchunks + 1) * 8, 16);
+    m.chunk_cksum = o; o += align_up((size_t)nchunks * 4, 16);
+    m.chunk_total = o; o += align_up((size_t)nchunks * 4, 16);
+    m.piece_len = o; o += align_up((size_t)npieces * 4, 16);
+    m.piece_crc = o; o += align_up((size_t)npieces * 4, 16);
+    m.ticket = o; o += 16;
+    m.total = o;
+    return m;
+}
+
+/* Enqueue one batch on a slot's stream: kernels + D2H of the per-chunk offsets and checksums.
+ * d_src/d_dst are device pointers (the slot's own buffers, or the caller's for device-resident calls). */
+static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, const uint8_t *d_src, uint64_t len,
+                            uint8_t *d_dst, uint64_t d_dst_cap, int last, uint64_t *launches)
+{
+    const QzbTuning &t = e->tune;
+    const uint32_t PIECE = 1u << t.piece_log2;
+    QzbCompressJob job; memset(&job, 0, sizeof job);
+    job.src = d_src; job.src_len = len; job.chunk_sz = c->chunk_sz; job.piece_log2 = (uint32_t)t.piece_log2;
+    job.pieces_per_chunk = (c->chunk_sz + PIECE - 1) / PIECE;
+    job.nchunks = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
+    const uint64_t last_len = len - (uint64_t)(job.nchunks - 1) * c->chunk_sz;
+    const uint32_t last_pieces = last_len ? (uint32_t)((last_len + PIECE - 1) / PIECE) : 1u;
+    job.npieces = (job.nchunks - 1) * job.pieces_per_chunk + last_pieces;
+    job.fmt = c->fmt; job.last = last; job.static_huffman = c->static_huffman;
+    job.slot_stride = PIECE + 64;
+    /* launch geometry: fill the SMs with as many warps as shared memory allows */
+    int warps = t.warps_per_cta, ctas_per_sm = 1;
+    const size_t smem_cap = 227 * 1024;
+    const bool lz4 = (c->fmt == QZB_FMT_LZ4);
+    auto smem_for = [&](int w) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w); };
+    if (warps <= 0) { warps = 16; while (warps > 1 && smem_for(warps) + 2048 > smem_cap) warps--; }
+    while (warps > 1 && smem_for(warps) + 2048 > smem_cap) warps--;
+    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps) + 3072));
+    if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
+    int grid = e->sm_count * ctas_per_sm;
+    const int need = (int)((job.npieces + warps - 1) / warps);
+    if (grid > need) grid = std::max(1, need);
+
+    if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
+    MetaLayout ml = meta_layout(job.npieces, job.nchunks);
+    if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((size_t)grid * warps * PIECE * 4) != RC_OK) return RC_FAIL;
+    uint8_t *dm = (uint8_t *)s.d_meta.p;
+    job.slots = (uint8_t *)s.d_slots.p;
+    job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
+    job.chunk_total = (uint32_t *)(dm + ml.chunk_total); job.chunk_cksum = (uint32_t *)(dm + ml.chunk_cksum);
+    job.chunk_off = (uint64_t *)(dm + ml.chunk_off); job.ticket = (uint32_t *)(dm + ml.ticket);
+    job.tok_scratch = (uint32_t *)s.d_tok.p;
+    job.dst = d_dst; job.dst_cap = d_dst_cap;
+
+    CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
+    CK(cudaEventRecord(s.ev_k0, s.st));
+    if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
+    else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, s.st));
+    CK(qzb_launch_frame(&job, s.st));
+    CK(cudaEventRecord(s.ev_k1, s.st));
+    *launches += lz4 ? 5 : 4;
+    /* chunk_off + chunk_cksum are adjacent at the start of the meta block */
+    CK(cudaMemcpyAsync(s.h_meta.p, dm, ml.chunk_total, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaEventRecord(s.ev_meta, s.st));
+    s.nchunks = job.nchunks;
+    return RC_OK;
+}
+
+extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCompressOut *o)
+{
+    memset(o, 0, sizeof *o);
+    if (!e || !c || c->chunk_sz < 1024 || (c->chunk_sz & (c->chunk_sz - 1))) return RC_PARAMS;
+    CK(cudaSetDevice(e->device));
+    uint32_t crc = c->crc_in;
+    const uint64_t per_chunk_out = (uint64_t)c->chunk_sz + (c->chunk_sz >> 7) + 256;   /* worst case incl. framing */
+
+    if (c->src_device && c->dst_device) {
+        /* device-resident: one launch per <= 1 GiB slab so piece counts stay 32-bit and scratch bounded */
+        const uint64_t slab = ((uint64_t)1 << 30) / c->chunk_sz * c->chunk_sz;
+        uint64_t in = 0, out = 0; int rc = RC_OK;
+        Slot &s = e->slot[0];
+        do {
+            const uint64_t len = std::min<uint64_t>(slab, c->src_len - in);
+            const int last = (in + len == c->src_len) ? c->last : 0;
+            if (enqueue_compress(e, s, c, c->src + in, len, c->dst + out, c->dst_cap - out, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
+            CK(cudaEventSynchronize(s.ev_meta));
+            float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+            const uint64_t *off = (const uint64_t *)s.h_meta.p;
+            const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
+            uint32_t fit = 0;
+            while (fit < s.nchunks && off[fit + 1] <= c->dst_cap - out) fit++;
+            for (uint32_t i = 0; i < fit; i++) {
+                const uint64_t clen = std::min<uint64_t>(c->chunk_sz, len - (uint64_t)i * c->chunk_sz);
+                if (c->fmt != QZB_FMT_LZ4) crc = (crc == 0) ? ck[i] : qz_crc32_combine(crc, ck[i], clen);
+            }
+            o->nchunks += fit;
+            out += off[fit];
+            if (fit < s.nchunks) { in += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; break; }
+            in += len;
+        } while (in < c->src_len);
+        o->consumed = in; o->produced = out; o->crc = crc;
+        return rc;
+    }
+    if (c->src_device || c->dst_device) return RC_PARAMS;      /* mixed residency is not offered */
+
+    /* host buffers: batches through two slots */
+    const uint64_t batch = std::max<uint64_t>(c->chunk_sz, e->tune.batch_bytes / c->chunk_sz * c->chunk_sz);
+    const uint64_t nb = c->src_len ? (c->src_len + batch - 1) / batch : 1;
+    uint64_t out = 0, consumed = 0; int rc = RC_OK; bool stop = false;
+
+    auto drain = [&](Slot &s) -> int {
+        if (!s.busy) return RC_OK;
+        s.busy = false;
+        CK(cudaEventSynchronize(s.ev_meta));
+        if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
+        float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+        const uint64_t *off = (const uint64_t *)s.h_meta.p;
+        const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
+        uint32_t fit = 0;
+        while (fit < s.nchunks && off[fit + 1] <= c->dst_cap - out) fit++;
+        const uint64_t bytes = off[fit];
+        if (bytes) {
+            if (c->dst_pinned) CK(cudaMemcpyAsync(c->dst + out, s.d_out.p, bytes, cudaMemcpyDeviceToHost, s.st));
+            else {
+                if (s.h_out.ensure(bytes) != RC_OK) return RC_FAIL;
+                CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, bytes, cudaMemcpyDeviceToHost, s.st));
+            }
+        }
+        for (uint32_t i = 0; i < fit; i++) {
+            const uint64_t clen = std::min<uint64_t>(c->chunk_sz, s.in_len - (uint64_t)i * c->chunk_sz);
+            if (c->fmt != QZB_FMT_LZ4) crc = (crc == 0) ? ck[i] : qz_crc32_combine(crc, ck[i], clen);
+        }
+        CK(cudaStreamSynchronize(s.st));
+        if (bytes && !c->dst_pinned) memcpy(c->dst + out, s.h_out.p, bytes);
+        out += bytes; o->nchunks += fit;
+        if (fit < s.nchunks) { consumed += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; stop = true; }
+        else consumed += s.in_len;
+        return RC_OK;
+    };
+
+    for (uint64_t b = 0; b < nb && !stop; b++) {
+        Slot &s = e->slot[b & 1];
+        if (drain(s) != RC_OK) return RC_FAIL;
+        if (stop) break;
+        const uint64_t in_off = b * batch, len = std::min<uint64_t>(batch, c->src_len - in_off);
+        const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
+        if (s.d_in.ensure(len + 64) != RC_OK || s.d_out.ensure((uint64_t)nch * per_chunk_out) != RC_OK) return RC_FAIL;
+        if (len) {
+            if (c->src_pinned) CK(cudaMemcpyAsync(s.d_in.p, c->src + in_off, len, cudaMemcpyHostToDevice, s.st));
+            else {
+                if (s.h_in.ensure(len) != RC_OK) return RC_FAIL;
+                memcpy(s.h_in.p, c->src + in_off, len);
+                CK(cudaMemcpyAsync(s.d_in.p, s.h_in.p, len, cudaMemcpyHostToDevice, s.st));
+            }
+        }
+        const int last = (in_off + len == c->src_len) ? c->last : 0;
+        if (enqueue_compress(e, s, c, (const uint8_t *)s.d_in.p, len, (uint8_t *)s.d_out.p, s.d_out.cap, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
+        s.busy = true; s.in_off = in_off; s.in_len = len;
+        /* drain the other slot while this one runs */
+        if (b > 0 && drain(e->slot[(b + 1) & 1]) != RC_OK) return RC_FAIL;
+    }
+    /* drain in issue order */
+    const uint64_t issued_last = nb ? (nb - 1) & 1 : 0;
+    if (drain(e->slot[issued_last ^ 1]) != RC_OK) return RC_FAIL;
+    if (drain(e->slot[issued_last]) != RC_OK) return RC_FAIL;
+    o->consumed = consumed; o->produced = out; o->crc = crc;
+    return rc;
+}
+
+/* ------------------------------------------------------------------ decompress */
+static inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+
+struct ParsedMember {
+    QzbMember m;
+    uint64_t unit_start;       /* offset of the member/frame header in the call's src */
+    uint32_t hdr_len, ftr_len;
+    bool sized;                /* payload length and output size known up front */
+};
+
+/* RFC 1952 header walk.  Returns header length, 0 if more bytes are needed, -1 if not gzip. */
+static long gzip_header_len(const uint8_t *p, uint64_t avail, bool *has_qz, uint32_t *qz_src, uint32_t *qz_dst)
+{
+    *has_qz = false;
+    if (avail < 10) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8) return -1;
+    const uint8_t flg = p[3]; uint64_t h = 10;
+    if (flg & 0xe0) return -1;
+    if (flg & 4) {
+        if (avail < h + 2) return 0;
+        const uint32_t xlen = p[h] | (uint32_t)p[h + 1] << 8;
+        if (avail < h + 2 + xlen) return 0;
+        /* the fixed-shape 'QZ' sub-field: reference src/qatzip_gzip.c:200-226 */
+        if (xlen == 12 && p[h + 2] == 'Q' && p[h + 3] == 'Z' && p[h + 4] == 8 && p[h + 5] == 0) { *has_qz = true; *qz_src = rd32(p + h + 6); *qz_dst = rd32(p + h + 10); }
+        h += 2 + xlen;
+    }
+    if (flg & 8) { while (h < avail && p[h]) h++; if (h >= avail) return 0; h++; }
+    if (flg & 16) { while (h < avail && p[h]) h++; if (h >= avail) return 0; h++; }
+    if (flg & 2) h += 2;
+    if (h > avail) return 0;
+    return (long)h;
+}
+
+extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, QzbDecompressOut *o)
+{
+    memset(o, 0, sizeof *o);
+    if (!e || !c) return RC_PARAMS;
+    CK(cudaSetDevice(e->device));
+    const uint8_t *hsrc = c->src_device ? c->src_host_view : c->src;
+    if (!hsrc) return RC_PARAMS;
+    if (c->src_device != c->dst_device) return RC_PARAMS;
+    const bool lz4 = (c->fmt == QZB_FMT_LZ4);
+    int rc = RC_OK;
+    uint64_t in = 0, out = 0;
+
+    /* ---- pass 1 (host): walk the units, like checkHeader does per request ---- */
+    std::vector<ParsedMember> units;
+    bool unsized_tail = false;
+    while (in < c->src_len) {
+        const uint8_t *p = hsrc + in; const uint64_t avail = c->src_len - in;
+        ParsedMember u; memset(&u, 0, sizeof u); u.unit_start = in;
+        if (c->fmt == QZB_FMT_GZIP || c->fmt == QZB_FMT_GZIP_EXT) {
+            bool has_qz; uint32_t qsrc = 0, qdst = 0;
+            long h = gzip_header_len(p, avail, &has_qz, &qsrc, &qdst);
+            if (h < 0) { rc = RC_FAIL; break; }
+            if (h == 0) { rc = RC_DATA_ERROR; break; }
+            u.hdr_len = (uint32_t)h; u.ftr_len = 8;
+            uint64_t payload;
+            if (has_qz) payload = qdst;
+            else {
+                /* next member by magic scan, footer sits right before it: reference src/qatzip_gzip.c:244-261 */
+                uint64_t q = (uint64_t)h + 8; bool found = false;
+                while (q + 4 <= avail) {
+                    const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, avail - q - 3);
+                    if (!f) break;
+                    q = (uint64_t)(f - p);
+                    if (p[q + 1] == 0x8b && p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0) { found = true; break; }
+                    q++;
+                }
+                const uint64_t end = found ? q : avail;
+                if (end < (uint64_t)h + 8) { rc = RC_DATA_ERROR; break; }
+                payload = end - h - 8;
+            }
+            if ((uint64_t)h + payload + 8 > avail) { rc = RC_DATA_ERROR; break; }
+            const uint8_t *ftr = p + h + payload;
+            const uint32_t isize = has_qz ? qsrc : rd32(ftr + 4);
+            if ((uint64_t)isize > c->dst_cap - out) { rc = RC_BUF_ERROR; break; }
+            u.m.src_off = in + h; u.m.src_len = (uint32_t)payload; u.m.exact_len = 1;
+            u.m.dst_off = out; u.m.dst_cap = isize; u.m.exact_out = 1;
+            u.m.expect_cksum = rd32(ftr); u.m.check_cksum = 1; u.sized = true;
+            if (payload > 0xfffffff0ull) { rc = RC_FAIL; break; }
+            in += h + payload + 8; out += isize;
+        } else if (c->fmt == QZB_FMT_4B) {
+            if (avail < 4) { rc = RC_DATA_ERROR; break; }
+            const uint32_t blk = rd32(p);
+            if (4 + (uint64_t)blk > avail) { rc = RC_DATA_ERROR; break; }
+            u.hdr_len = 4; u.m.src_off = in + 4; u.m.src_len = blk; u.m.exact_len = 1;
+            u.m.dst_cap = c->chunk_sz; u.m.exact_out = 0; u.sized = false;
+            in += 4 + (uint64_t)blk;
+        } else if (c->fmt == QZB_FMT_RAW) {
+            if (avail > 0xfffffff0ull) { rc = RC_FAIL; break; }
+            u.m.src_off = in; u.m.src_len = (uint32_t)avail; u.m.exact_len = 0;
+            /* deflate cannot expand more than 1032:1, which bounds the staging a raw stream needs */
+            u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, avail * 1032 + 64), 0xfffffff0ull); u.sized = false;
+            in += avail; unsized_tail = true;
+        } else if (lz4) {
+            /* frame header: reference src/qatzip_lz4.c:62-102 (verify), :145-173 (walk blocks to EndMark) */
+            if (avail < 7) { rc = RC_DATA_ERROR; break; }
+            if (rd32(p) != 0x184D2204u) { rc = RC_FAIL; break; }
+            const uint8_t flg = p[4];
+            if ((flg >> 6) != 1) { rc = RC_FAIL; break; }
+            uint64_t h = 6 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
+            if (avail < h + 4) { rc = RC_DATA_ERROR; break; }
+            if (p[h - 1] != (uint8_t)(qz_xxh32(p + 4, (size_t)(h - 5), 0) >> 8)) { rc = RC_DATA_ERROR; break; }
+            uint64_t q = h; bool ok = false;
+            while (q + 4 <= avail) {
+                const uint32_t bh = rd32(p + q);
+                if (bh == 0) { ok = true; break; }
+                q += 4 + (uint64_t)(bh & 0x7fffffffu) + ((flg & 0x10) ? 4 : 0);
+            }
+            if (!ok) { rc = RC_DATA_ERROR; break; }
+            const uint32_t ftr = 4 + ((flg & 4) ? 4 : 0);
+            if (q + ftr > avail) { rc = RC_DATA_ERROR; break; }
+            u.hdr_len = (uint32_t)h; u.ftr_len = ftr;
+            u.m.src_off = in + h; u.m.src_len = (uint32_t)(q - h); u.m.exact_len = 1;
+            u.m.check_cksum = (flg & 4) ? 1 : 0; u.m.expect_cksum = (flg & 4) ? rd32(p + q + 4) : 0;
+            /* flags the kernel needs ride in the upper bits of exact_len */
+            u.m.exact_len |= ((flg & 0x10) ? 2u : 0u) | ((flg & 0x20) ? 4u : 0u);
+            if (flg & 8) {
+                const uint64_t cs = (uint64_t)rd32(p + 6) | (uint64_t)rd32(p + 10) << 32;
+                if (cs > c->dst_cap - out) { rc = RC_BUF_ERROR; break; }
+                if (cs > 0xfffffff0ull) { rc = RC_FAIL; break; }
+                u.m.dst_off = out; u.m.dst_cap = (uint32_t)cs; u.m.exact_out = 1; u.sized = true; out += cs;
+            } else { u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, (q - h) * 255 + 64), 0xfffffff0ull); u.sized = false; }
+            in += q + ftr;
+        } else return RC_PARAMS;
+        units.push_back(u);
+        if (c->stop_at_first) break;
+        if (!u.sized && (lz4 || c->fmt == QZB_FMT_RAW)) break;      /* output position of what follows is unknown */
+    }
+    (void)unsized_tail;
+    if (units.empty()) { o->consumed = 0; o->produced = 0; return rc; }
+
+    /* ---- pass 2 (device) ---- */
+    const bool all_sized = std::all_of(units.begin(), units.end(), [](const ParsedMember &u) { return u.sized; });
+    uint64_t done_in = 0, done_out = 0; int rc2 = RC_OK;
+    const int grid_cap = e->sm_count * 6;
+
+    auto run = [&](Slot &s, size_t first, size_t count, uint64_t span_src, uint64_t span_len, uint64_t out_base, uint64_t out_len,
+                   bool staged_out) -> int {
+        /* staged_out: members decode into private regions of the slot's d_out (stride chunk_sz) */
+        const uint8_t *d_src; uint8_t *d_dst;
+        if (c->src_device) { d_src = c->src + span_src; d_dst = staged_out ? nullptr : c->dst + out_base; }
+        else {
+            if (s.d_in.ensure(span_len + 64) != RC_OK) return RC_FAIL;
+            if (c->src_pinned) CK(cudaMemcpyAsync(s.d_in.p, c->src + span_src, span_len, cudaMemcpyHostToDevice, s.st));
+            else { if (s.h_in.ensure(span_len) != RC_OK) return RC_FAIL; memcpy(s.h_in.p, c->src + span_src, span_len);
+                   CK(cudaMemcpyAsync(s.d_in.p, s.h_in.p, span_len, cudaMemcpyHostToDevice, s.st)); }
+            d_src = (const uint8_t *)s.d_in.p; d_dst = nullptr;
+        }
+        if (!d_dst) { if (s.d_out.ensure(out_len + 64) != RC_OK) return RC_FAIL; d_dst = (uint8_t *)s.d_out.p; }
+        if (s.h_members.ensure(count * sizeof(QzbMember)) != RC_OK || s.d_members.ensure(count * sizeof(QzbMember)) != RC_OK) return RC_FAIL;
+        if (s.h_results.ensure(count * sizeof(QzbMemberResult)) != RC_OK || s.d_results.ensure(count * sizeof(QzbMemberResult) + 16) != RC_OK) return RC_FAIL;
+        QzbMember *hm = (QzbMember *)s.h_members.p;
+        uint64_t stage_off = 0;
+        for (size_t i = 0; i < count; i++) {
+            hm[i] = units[first + i].m;
+            hm[i].src_off -= span_src;
+            if (staged_out) { hm[i].dst_off = stage_off; stage_off += align_up(hm[i].dst_cap, 16); }
+            else hm[i].dst_off -= out_base;
+        }
+        CK(cudaMemcpyAsync(s.d_members.p, hm, count * sizeof(QzbMember), cudaMemcpyHostToDevice, s.st));
+        uint32_t *ticket = (uint32_t *)((uint8_t *)s.d_results.p + count * sizeof(QzbMemberResult));
+        CK(cudaMemsetAsync(ticket, 0, 16, s.st));
+        QzbDecompressJob job; memset(&job, 0, sizeof job);
+        job.src = d_src; job.dst = d_dst; job.members = (const QzbMember *)s.d_members.p; job.results = (QzbMemberResult *)s.d_results.p;
+        job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket;
+        const int grid = (int)std::min<size_t>((count + 7) / 8, (size_t)grid_cap);
+        CK(cudaEventRecord(s.ev_k0, s.st));
+        if (lz4) CK(qzb_launch_lz4_decompress(&job, grid, s.st)); else CK(qzb_launch_inflate(&job, grid, s.st));
+        CK(cudaEventRecord(s.ev_k1, s.st));
+        o->kernel_launches += 1;
+        CK(cudaMemcpyAsync(s.h_results.p, s.d_results.p, count * sizeof(QzbMemberResult), cudaMemcpyDeviceToHost, s.st));
+        CK(cudaEventRecord(s.ev_meta, s.st));
+        s.busy = true; s.first_member = first; s.nmembers = count; s.span_src = span_src; s.span_len = span_len; s.out_base = out_base; s.out_len = out_len;
+        return RC_OK;
+    };
+
+    auto status_rc = [&](const QzbMemberResult &r, bool sized) -> int {
+        switch (r.status) {
+        case QZB_ST_OK: return RC_OK;
+        case QZB_ST_OUT_FULL: return sized ? RC_DATA_ERROR : RC_BUF_ERROR;
+        default: return RC_DATA_ERROR;
+        }
+    };
+
+    if (all_sized) {
+        /* members know where they go: batch them, two slots in flight */
+        const uint64_t bin = e->tune.batch_bytes, bout = e->tune.batch_bytes * 4;
+        size_t i = 0, issued = 0; bool stop = false;
+        auto drain = [&](Slot &s) -> int {
+            if (!s.busy) return RC_OK;
+            s.busy = false;
+            CK(cudaEventSynchronize(s.ev_meta));
+            if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
+            float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+            const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
+            size_t good = 0;
+            while (good < s.nmembers && r[good].status == QZB_ST_OK) good++;
+            uint64_t obytes = 0;
+            if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; obytes = lu.m.dst_off + lu.m.dst_cap - s.out_base; }
+            if (!c->dst_device && obytes) {
+                if (c->dst_pinned) CK(cudaMemcpyAsync(c->dst + s.out_base, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st));
+                else { if (s.h_out.ensure(obytes) != RC_OK) return RC_FAIL; CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st)); }
+                CK(cudaStreamSynchronize(s.st));
+                if (!c->dst_pinned) memcpy(c->dst + s.out_base, s.h_out.p, obytes);
+            }
+            if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; done_in = lu.unit_start + lu.hdr_len + lu.m.src_len + lu.ftr_len; done_out = s.out_base + obytes; o->nmembers += (uint32_t)good; }
+            if (good < s.nmembers) { rc2 = status_rc(r[good], true); stop = true; }
+            return RC_OK;
+        };
+        while (i < units.size() && !stop) {
+            size_t j = i; uint64_t sin = 0, sout = 0;
+            while (j < units.size()) {
+                const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
+                if (j > i && (sin + ulen > bin || sout + units[j].m.dst_cap > bout)) break;
+                sin += ulen; sout += units[j].m.dst_cap; j++;
+            }
+            Slot &s = e->slot[issued & 1];
+            if (drain(s) != RC_OK) return RC_FAIL;
+            if (stop) break;
+            if (run(s, i, j - i, units[i].unit_start, sin, units[i].m.dst_off, sout, false) != RC_OK) return RC_FAIL;
+            if (issued > 0 && drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL;
+            issued++; i = j;
+        }
+        if (issued) { if (drain(e->slot[issued & 1]) != RC_OK) return RC_FAIL; if (drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL; }
+    } else {
+        /* 4B / RAW / unsized frames: output sizes come back from the device.  Decode into
+         * private staging regions, then place results one after another. */
+        Slot &s = e->slot[0];
+        size_t i = 0; done_out = 0;
+        const uint64_t bin = e->tune.batch_bytes;
+        while (i < units.size() && rc2 == RC_OK) {
+            size_t j = i; uint64_t sin = 0, sout = 0;
+            while (j < units.size()) {
+                const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
+                if (j > i && (sin + ulen > bin || sout > (e->tune.batch_bytes << 2))) break;
+                sin += ulen; sout += align_up(units[j].m.dst_cap, 16); j++;
+            }
+            if (run(s, i, j - i, units[i].unit_start, sin, 0, sout, true) != RC_OK) return RC_FAIL;
+            s.busy = false;
+            CK(cudaEventSynchronize(s.ev_meta));
+            float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+            const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
+            const QzbMember *hm = (const QzbMember *)s.h_members.p;
+            for (size_t k = 0; k < j - i; k++) {
+                const ParsedMember &u = units[i + k];
+                int st = status_rc(r[k], false);
+                if (st == RC_OK && r[k].produced > c->dst_cap - done_out) st = RC_BUF_ERROR;
+                if (st != RC_OK) { rc2 = st; break; }
+                if (r[k].produced) {
+                    const uint8_t *from = (const uint8_t *)s.d_out.p + hm[k].dst_off;
+                    CK(cudaMemcpyAsync(c->dst + done_out, from, r[k].produced, c->dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.st));
+                }
+                done_out += r[k].produced;
+                done_in = u.unit_start + u.hdr_len + (u.m.exact_len & 1 ? u.m.src_len : r[k].consumed) + u.ftr_len;
+                o->nmembers++;
+            }
+            CK(cudaStreamSynchronize(s.st));
+            i = j;
+        }
+    }
+    o->consumed = done_in; o->produced = done_out;
+    o->end_of_stream = (rc2 == RC_OK && o->nmembers > 0) ? 1 : 0;
+    if (rc2 != RC_OK) return rc2;
+    return rc;
+}

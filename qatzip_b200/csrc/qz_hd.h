@@ -1,0 +1,22 @@
+/* qz_hd.h -- macros that let the scalar pieces of the codec (tables, Huffman construction,
+ * header coding, inflate decode loop, CRC-32, xxHash32) compile both as CUDA device code and
+ * as plain host C++ (for CPU unit tests of the exact same source). */
+#ifndef QZ_HD_H
+#define QZ_HD_H
+#include <stdint.h>
+#include <stddef.h>
+#if defined(__CUDACC__)
+#define QZ_HD __host__ __device__ __forceinline__
+#define QZ_HDN __host__ __device__
+#else
+#define QZ_HD static inline
+#define QZ_HDN
+#endif
+
+/* wire/data formats handled by the kernels (superset of QzDataFormat_T: LZ4 is a session type) */
+enum QzbFormat { QZB_FMT_4B = 0, QZB_FMT_GZIP = 1, QZB_FMT_GZIP_EXT = 2, QZB_FMT_RAW = 3, QZB_FMT_LZ4 = 4 };
+
+/* per-unit status words written by kernels */
+enum QzbStatus { QZB_ST_OK = 0, QZB_ST_DATA_ERROR = 1, QZB_ST_OUT_FULL = 2, QZB_ST_IN_TRUNC = 3, QZB_ST_CKSUM = 4, QZB_ST_SIZE = 5 };
+
+#endif

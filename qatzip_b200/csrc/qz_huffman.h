@@ -1,0 +1,190 @@
+/* qz_huffman.h -- Huffman code construction and deflate dynamic-block header coding, written as
+ * scalar host+device code: on the GPU one lane of the piece's warp runs it on shared-memory
+ * arrays; on the CPU the unit tests run the very same source against zlib's inflate.
+ *
+ * Replaces: the dynamic-Huffman tree generation inside the QAT deflate engine (reference
+ * src/qatzip_utils.c:270-275 only *selects* CPA_DC_HT_FULL_DYNAMIC / CPA_DC_HT_STATIC and
+ * auto-select-best; the construction itself is device firmware and is not in the reference). */
+#ifndef QZ_HUFFMAN_H
+#define QZ_HUFFMAN_H
+#include "qz_hd.h"
+#include "qz_deflate_tables.h"
+
+#define QZ_NUM_LL 286
+#define QZ_NUM_D 30
+#define QZ_NUM_CL 19
+#define QZ_HUFF_KEY(freq, sym) (((uint32_t)(freq) << 9) | (uint32_t)(sym))
+
+/* LSB-first bit writer over 32-bit words (slot buffers are 4-byte aligned). */
+struct QzBitWriter {
+    uint32_t *words;
+    uint64_t acc;
+    uint32_t nacc;     /* valid bits in acc, always < 32 between calls */
+    uint32_t wpos;     /* next word index */
+};
+QZ_HD void qz_bw_init(QzBitWriter *bw, uint32_t *words) { bw->words = words; bw->acc = 0; bw->nacc = 0; bw->wpos = 0; }
+QZ_HD void qz_bw_put(QzBitWriter *bw, uint32_t bits, uint32_t n)   /* n <= 32 */
+{
+    bw->acc |= (uint64_t)bits << bw->nacc;
+    bw->nacc += n;
+    if (bw->nacc >= 32) { bw->words[bw->wpos++] = (uint32_t)bw->acc; bw->acc >>= 32; bw->nacc -= 32; }
+}
+QZ_HD uint32_t qz_bw_bitpos(const QzBitWriter *bw) { return bw->wpos * 32 + bw->nacc; }
+/* zero-pad to the next byte boundary */
+QZ_HD void qz_bw_align_byte(QzBitWriter *bw) { uint32_t r = bw->nacc & 7; if (r) qz_bw_put(bw, 0, 8 - r); }
+/* write out the (<32) pending bits as a final partial word; returns total length in bytes */
+QZ_HD uint32_t qz_bw_finish(QzBitWriter *bw)
+{
+    uint32_t bytes = bw->wpos * 4 + ((bw->nacc + 7) >> 3);
+    if (bw->nacc) bw->words[bw->wpos] = (uint32_t)bw->acc;
+    return bytes;
+}
+
+/* deflate requires every alphabet to carry at least two codes (zlib's inflate rejects a
+ * one-code code-length alphabet): give unused low symbols a count of 1 until two are in use. */
+QZ_HD void qz_huff_force_two(uint32_t *freq, int n)
+{
+    int used = 0;
+    for (int i = 0; i < n && used < 2; i++) used += freq[i] != 0;
+    for (int i = 0; used < 2 && i < n; i++) if (freq[i] == 0) { freq[i] = 1; used++; }
+}
+
+/* In-place minimum-redundancy code lengths (Moffat & Katajainen, 1995) over frequencies sorted
+ * ascending in A[0..n), n >= 2.  On return A[i] is the code length of the i-th sorted symbol
+ * (non-increasing in i). */
+QZ_HD void qz_huff_inplace_lengths(uint32_t *A, int n)
+{
+    int root, leaf, next;
+    A[0] += A[1]; root = 0; leaf = 2;
+    for (next = 1; next < n - 1; next++) {
+        if (leaf >= n || A[root] < A[leaf]) { A[next] = A[root]; A[root++] = (uint32_t)next; }
+        else A[next] = A[leaf++];
+        if (leaf >= n || (root < next && A[root] < A[leaf])) { A[next] += A[root]; A[root++] = (uint32_t)next; }
+        else A[next] += A[leaf++];
+    }
+    A[n - 2] = 0;
+    for (next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
+    int avbl = 1, used = 0, dpth = 0;
+    root = n - 2; next = n - 1;
+    while (avbl > 0) {
+        while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
+        while (avbl > used) { A[next--] = (uint32_t)dpth; avbl--; }
+        avbl = 2 * used; dpth++; used = 0;
+    }
+}
+
+/* Sorted keys (QZ_HUFF_KEY(freq, sym), ascending, all freq > 0, n_used >= 2) -> per-symbol code
+ * lengths capped at maxbits.  keys[] is clobbered, ids[] is scratch for n_used entries.
+ * len_by_sym[] must be zero for symbols that do not occur. */
+QZ_HD void qz_huff_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n_used, int maxbits, uint8_t *len_by_sym)
+{
+    for (int i = 0; i < n_used; i++) { ids[i] = (uint16_t)(keys[i] & 511u); keys[i] >>= 9; }
+    qz_huff_inplace_lengths(keys, n_used);
+    if ((int)keys[0] > maxbits) {
+        /* Fold over-long codes to maxbits, then restore the Kraft equality by repeatedly turning
+         * the deepest leaf above the cap into an internal node that adopts one folded leaf. */
+        uint32_t cnt[16];
+        for (int l = 0; l < 16; l++) cnt[l] = 0;
+        for (int i = 0; i < n_used; i++) cnt[(int)keys[i] > maxbits ? maxbits : (int)keys[i]]++;
+        uint32_t kraft = 0;
+        for (int l = 1; l <= maxbits; l++) kraft += cnt[l] << (maxbits - l);
+        while (kraft > (1u << maxbits)) {
+            int b = maxbits - 1;
+            while (cnt[b] == 0) b--;
+            cnt[b]--; cnt[b + 1] += 2; cnt[maxbits]--;
+            kraft--;
+        }
+        int i = 0;
+        for (int l = maxbits; l >= 1; l--) for (uint32_t c = cnt[l]; c; c--) keys[i++] = (uint32_t)l;
+    }
+    for (int i = 0; i < n_used; i++) len_by_sym[ids[i]] = (uint8_t)keys[i];
+}
+
+/* Canonical codes, already bit-reversed for LSB-first emission: out[s] = code | len << 16. */
+QZ_HD void qz_huff_codes(const uint8_t *len, int n, uint32_t *out)
+{
+    uint32_t cnt[16], next[17];
+    for (int l = 0; l < 16; l++) cnt[l] = 0;
+    for (int s = 0; s < n; s++) cnt[len[s]]++;
+    cnt[0] = 0; next[0] = 0; next[1] = 0;
+    for (int l = 1; l < 16; l++) next[l + 1] = (next[l] + cnt[l]) << 1;
+    for (int s = 0; s < n; s++) {
+        uint32_t l = len[s];
+        out[s] = l ? (qz_bitrev(next[l]++, l) | (l << 16)) : 0u;
+    }
+}
+
+/* ---- dynamic block header (RFC 1951 3.2.7) ---- */
+struct QzDynHeader {
+    uint16_t items[QZ_NUM_LL + QZ_NUM_D];   /* sym | extra_value << 5 | extra_bits_count << 12 */
+    uint32_t nitems;
+    uint32_t hlit, hdist, hclen;
+    uint8_t cl_len[QZ_NUM_CL];
+    uint32_t bits;                          /* total header bits including the 3-bit block header */
+};
+
+QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return (uint16_t)(sym | (eval << 5) | (ebits << 12)); }
+
+/* Run-length code the two length arrays into code-length symbols and size the header. */
+QZ_HD void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len, QzDynHeader *h)
+{
+    uint32_t hlit = QZ_NUM_LL, hdist = QZ_NUM_D;
+    while (hlit > 257 && ll_len[hlit - 1] == 0) hlit--;
+    while (hdist > 1 && d_len[hdist - 1] == 0) hdist--;
+    h->hlit = hlit; h->hdist = hdist;
+    uint32_t total = hlit + hdist, i = 0, n = 0, cf[QZ_NUM_CL];
+    for (int k = 0; k < QZ_NUM_CL; k++) cf[k] = 0;
+    while (i < total) {
+        uint32_t v = i < hlit ? ll_len[i] : d_len[i - hlit], j = i + 1;
+        while (j < total && (j < hlit ? ll_len[j] : d_len[j - hlit]) == v) j++;
+        uint32_t run = j - i;
+        if (v == 0) {
+            while (run >= 11) { uint32_t r = run > 138 ? 138 : run; h->items[n++] = qz_cl_item(18, r - 11, 7); cf[18]++; run -= r; }
+            if (run >= 3) { h->items[n++] = qz_cl_item(17, run - 3, 3); cf[17]++; run = 0; }
+            while (run) { h->items[n++] = qz_cl_item(0, 0, 0); cf[0]++; run--; }
+        } else {
+            h->items[n++] = qz_cl_item(v, 0, 0); cf[v]++; run--;
+            while (run >= 3) { uint32_t r = run > 6 ? 6 : run; h->items[n++] = qz_cl_item(16, r - 3, 2); cf[16]++; run -= r; }
+            while (run) { h->items[n++] = qz_cl_item(v, 0, 0); cf[v]++; run--; }
+        }
+        i = j;
+    }
+    h->nitems = n;
+    /* code-length alphabet: <= 19 symbols, 7-bit cap; tiny insertion sort */
+    qz_huff_force_two(cf, QZ_NUM_CL);
+    uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
+    for (int k = 0; k < QZ_NUM_CL; k++) {
+        h->cl_len[k] = 0;
+        if (cf[k]) {
+            uint32_t key = QZ_HUFF_KEY(cf[k], k); int p = nu++;
+            while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; p--; }
+            keys[p] = key;
+        }
+    }
+    qz_huff_lengths_from_sorted(keys, ids, nu, 7, h->cl_len);
+    const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+    uint32_t hclen = QZ_NUM_CL;
+    while (hclen > 4 && h->cl_len[ORDER[hclen - 1]] == 0) hclen--;
+    h->hclen = hclen;
+    uint32_t bits = 3 + 5 + 5 + 4 + 3 * hclen;
+    for (uint32_t k = 0; k < n; k++) bits += h->cl_len[h->items[k] & 31] + (h->items[k] >> 12);
+    h->bits = bits;
+}
+
+QZ_HD void qz_dyn_header_write(QzBitWriter *bw, const QzDynHeader *h, int bfinal)
+{
+    const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+    uint32_t cl_code[QZ_NUM_CL];
+    qz_huff_codes(h->cl_len, QZ_NUM_CL, cl_code);
+    qz_bw_put(bw, (uint32_t)(bfinal ? 1 : 0) | (2u << 1), 3);
+    qz_bw_put(bw, h->hlit - 257, 5);
+    qz_bw_put(bw, h->hdist - 1, 5);
+    qz_bw_put(bw, h->hclen - 4, 4);
+    for (uint32_t k = 0; k < h->hclen; k++) qz_bw_put(bw, h->cl_len[ORDER[k]], 3);
+    for (uint32_t k = 0; k < h->nitems; k++) {
+        uint32_t it = h->items[k], c = cl_code[it & 31];
+        qz_bw_put(bw, c & 0xffff, c >> 16);
+        if (it >> 12) qz_bw_put(bw, (it >> 5) & 127, it >> 12);
+    }
+}
+#endif

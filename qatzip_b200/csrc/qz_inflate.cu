@@ -1,0 +1,160 @@
+/* qz_inflate.cu -- sm_100a DEFLATE decoder: one warp per member.
+ *
+ * Replaces the QAT decompress request at reference src/qatzip.c:2191 (cpaDcDecompressData,
+ * stateless, FLUSH_FINAL) and folds in the checks doDecompressOut performs afterwards
+ * (reference src/qatzip_utils.c:1483-1532 decompOutCheckSum: checksum vs footer, produced vs
+ * ISIZE).  Lane 0 is the bit-serial Huffman decoder (tables in the warp's shared-memory
+ * slice, built by all lanes); literals are stored as they are decoded and every
+ * back-reference / stored block is copied by the whole warp.  Output and history live in
+ * the caller's destination buffer (HBM / L2), so there is no separate window. */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "qz_kernels.cuh"
+#include "qz_inflate.h"
+#include "qz_crc32.h"
+
+#define FULL 0xffffffffu
+
+struct InflWarpSmem {
+    QzInflTables t;
+    uint16_t code_of[320];
+};
+
+__device__ __forceinline__ uint32_t bcast(uint32_t v) { return __shfl_sync(FULL, v, 0); }
+
+/* CRC-32 of dst[0..n) by the whole warp (right-aligned strips + GF(2) tree). */
+__device__ uint32_t warp_crc32_global(const uint8_t *p, uint32_t n, const uint32_t *crc_tab, uint32_t lane)
+{
+    if (n == 0) return 0;
+    const uint32_t S = (n + 31) / 32;
+    int hi = (int)n - (int)((31 - lane) * S), lo = hi - (int)S;
+    if (lo < 0) lo = 0;
+    uint32_t c = 0xffffffffu;
+    for (int i = lo; i < hi; i++) c = crc_tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    c = (hi > lo) ? ~c : 0u;
+    uint32_t xs = lane < 5 ? qz_crc_xpow8((uint64_t)S << lane) : 0;
+#pragma unroll
+    for (int lv = 0; lv < 5; lv++) {
+        uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);
+        uint32_t x = __shfl_sync(FULL, xs, lv);
+        if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, x) ^ other;
+    }
+    return __shfl_sync(FULL, c, 0);
+}
+
+__global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
+{
+    __shared__ InflWarpSmem s_w[8];
+    __shared__ uint32_t s_crc_tab[256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
+    __syncthreads();
+    InflWarpSmem &ws = s_w[warp];
+    QzInflTables &T = ws.t;
+
+    for (;;) {
+        uint32_t mi = 0;
+        if (lane == 0) mi = atomicAdd(job.ticket, 1u);
+        mi = bcast(mi);
+        if (mi >= job.nmembers) break;
+        const QzbMember m = job.members[mi];
+        const uint8_t *src = job.src + m.src_off;
+        uint8_t *dst = job.dst + m.dst_off;
+        const uint32_t cap = m.dst_cap;
+        QzBitReader br;
+        qz_br_init(&br, src, m.src_len);
+        uint32_t out = 0, status = QZB_ST_OK, bfinal = 0;
+
+        while (!bfinal && status == QZB_ST_OK) {
+            uint32_t type = 0;
+            if (lane == 0) {
+                qz_br_refill(&br);
+                /* QZ_DEFLATE_RAW chunks that are not the last of the stream end without BFINAL:
+                 * stop cleanly when nothing but padding is left */
+                if (job.fmt == QZB_FMT_RAW && qz_br_consumed(&br) >= br.n && br.phantom * 8 >= br.nacc) type = 4;
+                else { bfinal = qz_br_bits(&br, 1); type = qz_br_bits(&br, 2); }
+            }
+            type = bcast(type); bfinal = bcast(bfinal);
+            if (type == 4) break;
+            if (type == 3) { status = QZB_ST_DATA_ERROR; break; }
+            if (type == 0) {
+                uint32_t len = 0, start = 0, st = QZB_ST_OK;
+                if (lane == 0) {
+                    uint32_t drop = br.nacc & 7; br.acc >>= drop; br.nacc -= drop;
+                    qz_br_refill(&br);
+                    len = qz_br_bits(&br, 16);
+                    uint32_t nlen = qz_br_bits(&br, 16);
+                    start = qz_br_consumed(&br);
+                    if ((len ^ 0xffffu) != nlen) st = QZB_ST_DATA_ERROR;
+                    else if (start + len > br.n) st = QZB_ST_IN_TRUNC;
+                    else if (out + len > cap) st = QZB_ST_OUT_FULL;
+                    else { br.pos = start + len; br.acc = 0; br.nacc = 0; br.phantom = 0; }
+                }
+                st = bcast(st); len = bcast(len); start = bcast(start);
+                if (st != QZB_ST_OK) { status = st; break; }
+                for (uint32_t i = lane; i < len; i += 32) dst[out + i] = src[start + i];
+                out += len;
+                __syncwarp();
+                continue;
+            }
+            /* Huffman block: lane 0 reads the code lengths, the warp builds the tables */
+            uint32_t st = QZB_ST_OK, hlit = 288, hdist = 30;
+            if (lane == 0) {
+                if (type == 1) qz_inflate_fixed_lens(&T);
+                else if (qz_inflate_read_dynamic(&br, &T, &hlit, &hdist) != 0) st = QZB_ST_DATA_ERROR;
+                if (st == QZB_ST_OK) {
+                    if (qz_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_sorted, ws.code_of) < 0) st = QZB_ST_DATA_ERROR;
+                    else if (qz_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_sorted, ws.code_of + 288) < 0) st = QZB_ST_DATA_ERROR;
+                }
+            }
+            st = bcast(st); hlit = bcast(hlit); hdist = bcast(hdist);
+            if (st != QZB_ST_OK) { status = st; break; }
+            for (uint32_t i = lane; i < (1u << QZ_LL_LUT_BITS); i += 32) T.ll_lut[i] = 0;
+            for (uint32_t i = lane; i < (1u << QZ_D_LUT_BITS); i += 32) T.d_lut[i] = 0;
+            __syncwarp();
+            qz_infl_fill_lut(T.lens, ws.code_of, (int)hlit, T.ll_lut, QZ_LL_LUT_BITS, (int)lane, 32);
+            qz_infl_fill_lut(T.lens + hlit, ws.code_of + 288, (int)hdist, T.d_lut, QZ_D_LUT_BITS, (int)lane, 32);
+            __syncwarp();
+            for (;;) {
+                int ev = 0; uint32_t mlen = 0, mdist = 0;
+                if (lane == 0) ev = qz_inflate_run(&br, &T, dst, &out, cap, &mlen, &mdist);
+                __syncwarp();
+                ev = (int)bcast((uint32_t)ev); out = bcast(out);
+                if (ev == QZI_END_BLOCK) break;
+                if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; break; }
+                if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; break; }
+                mlen = bcast(mlen); mdist = bcast(mdist);
+                const uint8_t *from = dst + out - mdist;
+                if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) dst[out + k] = from[k]; }
+                else { for (uint32_t k = lane; k < mlen; k += 32) dst[out + k] = from[k % mdist]; }
+                out += mlen;
+                __syncwarp();
+            }
+        }
+        /* verdict */
+        uint32_t consumed = bcast(lane == 0 ? qz_br_consumed(&br) : 0u);
+        uint32_t over = bcast(lane == 0 ? (uint32_t)qz_br_overrun(&br) : 0u);
+        if (status == QZB_ST_OK && over) status = QZB_ST_IN_TRUNC;
+        if (status == QZB_ST_OK && m.exact_len && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
+        if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
+        uint32_t crc = 0;
+        if (status == QZB_ST_OK) {
+            __syncwarp();
+            crc = warp_crc32_global(dst, out, s_crc_tab, lane);
+            if (m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
+        }
+        if (lane == 0) {
+            QzbMemberResult r;
+            r.status = status; r.consumed = consumed; r.produced = out; r.cksum = crc; r.saw_final = bfinal;
+            r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            job.results[mi] = r;
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st)
+{
+    qzb_inflate_kernel<<<grid, 256, 0, st>>>(*job);
+    return cudaGetLastError();
+}

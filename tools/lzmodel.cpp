@@ -1,0 +1,211 @@
+// tools/lzmodel.cpp -- design-space model (NOT product, NOT oracle): estimates the compressed size a
+// GPU-shaped LZ77+Huffman scheme would reach, to pick parameters before writing the kernel.
+// Build: g++ -O2 -o /tmp/lzmodel tools/lzmodel.cpp -lz
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <vector>
+#include <algorithm>
+#include <queue>
+#include <string>
+#include <zlib.h>
+#include <dlfcn.h>
+
+struct Params {
+    int piece = 65536;     // window reset granularity
+    int sub = 16384;       // deflate block granularity (own huffman tables)
+    int W = 1024;          // positions looked up before any of them is inserted
+    int hb = 14;           // hash bits
+    int hbytes = 4;        // bytes hashed
+    int minm = 4;          // min match
+    int capA = 258;        // cap on extension in parallel phase (model: final len anyway)
+    int S = 1024;          // super-tile: matches truncated at S boundaries (0 = off)
+    int rle = 1;           // also try distance 1
+    int warp = 1;          // intra-warp same-hash candidate (match_any)
+    int winner = 1;        // 1: highest p in window wins table slot, 0: lowest
+    int lazy = 0;
+    int ways = 1;          // bucket ways
+};
+
+static const uint16_t LBASE[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+static const uint8_t LEXT[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+static const uint16_t DBASE[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+static const uint8_t DEXT[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+static int lsym(int len) { int s = 28; while (LBASE[s] > len) s--; return s; }
+static int dsym(int d) { int s = 29; while (DBASE[s] > d) s--; return s; }
+
+// optimal length-limited code lengths (simple: huffman then zlib-like fix-up by Kraft repair)
+static void huff_lengths(const uint32_t *freq, int n, int maxbits, uint8_t *len)
+{
+    struct Node { uint64_t f; int l, r; };
+    std::vector<Node> nodes; std::vector<int> alive;
+    typedef std::pair<uint64_t, int> PI;
+    std::priority_queue<PI, std::vector<PI>, std::greater<PI>> pq;
+    for (int i = 0; i < n; i++) { len[i] = 0; if (freq[i]) { nodes.push_back({freq[i], -1 - i, 0}); pq.push({freq[i], (int)nodes.size() - 1}); } }
+    if (nodes.empty()) return;
+    if (nodes.size() == 1) { len[-1 - nodes[0].l] = 1; return; }
+    while (pq.size() > 1) {
+        PI a = pq.top(); pq.pop(); PI b = pq.top(); pq.pop();
+        nodes.push_back({a.first + b.first, a.second, b.second}); pq.push({a.first + b.first, (int)nodes.size() - 1});
+    }
+    // depths
+    std::vector<int> depth(nodes.size(), 0);
+    for (int i = (int)nodes.size() - 1; i >= 0; i--) {
+        if (nodes[i].l >= 0 || nodes[i].r > 0 || (nodes[i].l >= 0)) {}
+        if (nodes[i].l >= 0 || nodes[i].l < 0) {
+            if (!(nodes[i].l < 0 && nodes[i].r == 0)) { depth[nodes[i].l] = depth[i] + 1; depth[nodes[i].r] = depth[i] + 1; }
+        }
+    }
+    for (size_t i = 0; i < nodes.size(); i++) if (nodes[i].l < 0 && nodes[i].r == 0) len[-1 - nodes[i].l] = (uint8_t)depth[i];
+    // limit
+    int over = 0; for (int i = 0; i < n; i++) if (len[i] > maxbits) { len[i] = (uint8_t)maxbits; over = 1; }
+    if (over) {
+        // Kraft repair: K = sum 2^(maxbits-len) must be <= 2^maxbits
+        long K = 0; for (int i = 0; i < n; i++) if (len[i]) K += 1L << (maxbits - len[i]);
+        while (K > (1L << maxbits)) {
+            // lengthen the least frequent symbol with len < maxbits
+            int best = -1; for (int i = 0; i < n; i++) if (len[i] && len[i] < maxbits && (best < 0 || freq[i] < freq[best] || (freq[i] == freq[best] && len[i] > len[best]))) best = i;
+            K -= 1L << (maxbits - len[best] - 1); len[best]++;
+        }
+    }
+}
+
+static long dyn_header_bits(const uint8_t *ll, const uint8_t *dl, int *out_hlit = 0)
+{
+    int hlit = 286; while (hlit > 257 && ll[hlit - 1] == 0) hlit--;
+    int hdist = 30; while (hdist > 1 && dl[hdist - 1] == 0) hdist--;
+    std::vector<uint8_t> seq(ll, ll + hlit); seq.insert(seq.end(), dl, dl + hdist);
+    uint32_t cf[19] = {0}; std::vector<std::pair<int,int>> items; // sym, extra bits count
+    size_t i = 0;
+    while (i < seq.size()) {
+        size_t j = i; while (j < seq.size() && seq[j] == seq[i]) j++;
+        size_t run = j - i; int v = seq[i];
+        if (v == 0) {
+            while (run >= 11) { size_t r = std::min<size_t>(run, 138); cf[18]++; items.push_back({18,7}); run -= r; }
+            if (run >= 3) { cf[17]++; items.push_back({17,3}); run = 0; }
+            while (run--) { cf[0]++; items.push_back({0,0}); }
+        } else {
+            cf[v]++; items.push_back({v,0}); run--;
+            while (run >= 3) { size_t r = std::min<size_t>(run, 6); cf[16]++; items.push_back({16,2}); run -= r; }
+            while (run--) { cf[v]++; items.push_back({v,0}); }
+        }
+        i = j;
+    }
+    uint8_t cl[19]; huff_lengths(cf, 19, 7, cl);
+    static const uint8_t ORDER[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+    int hclen = 19; while (hclen > 4 && cl[ORDER[hclen - 1]] == 0) hclen--;
+    long bits = 5 + 5 + 4 + 3 * hclen;
+    for (auto &it : items) bits += cl[it.first] + it.second;
+    return bits;
+}
+
+struct Tok { int len, dist; uint8_t lit; };
+
+static long encode_block_bits(const std::vector<Tok> &toks, int nbytes, long *dynb = 0, long *fixb = 0)
+{
+    uint32_t lf[286] = {0}, df[30] = {0};
+    long extra = 0;
+    for (auto &t : toks) {
+        if (t.len == 0) lf[t.lit]++;
+        else { int ls = lsym(t.len), ds = dsym(t.dist); lf[257 + ls]++; df[ds]++; extra += LEXT[ls] + DEXT[ds]; }
+    }
+    lf[256] = 1;
+    uint8_t ll[286], dl[30]; huff_lengths(lf, 286, 15, ll); huff_lengths(df, 30, 15, dl);
+    long dyn = 3 + dyn_header_bits(ll, dl) + extra;
+    for (int i = 0; i < 286; i++) dyn += (long)lf[i] * ll[i];
+    for (int i = 0; i < 30; i++) dyn += (long)df[i] * dl[i];
+    long fix = 3 + extra;
+    for (int i = 0; i < 286; i++) fix += (long)lf[i] * (i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+    for (int i = 0; i < 30; i++) fix += (long)df[i] * 5;
+    long stored = 3 + 7 + 32 + 8L * nbytes;   // approx (alignment up to 7)
+    if (dynb) *dynb = dyn; if (fixb) *fixb = fix;
+    return std::min(dyn, std::min(fix, stored));
+}
+
+static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint32_t hashf(const uint8_t *p, const Params &P)
+{
+    uint32_t v = rd32(p); if (P.hbytes == 3) v &= 0xffffff;
+    return (v * 2654435761u) >> (32 - P.hb);
+}
+static inline int mlen(const uint8_t *a, const uint8_t *b, int maxl) { int l = 0; while (l < maxl && a[l] == b[l]) l++; return l; }
+
+// returns total bits for the piece (excluding final-block padding)
+static long model_piece(const uint8_t *src, int n, const Params &P, long *ntok_out)
+{
+    std::vector<int> L(n, 0), D(n, 0);
+    std::vector<int32_t> T((size_t)P.ways << P.hb, -1);
+    for (int w0 = 0; w0 < n; w0 += P.W) {
+        int w1 = std::min(n, w0 + P.W);
+        for (int p = w0; p < w1; p++) {
+            int maxl = std::min(258, n - p); int bl = 0, bd = 0;
+            if (maxl >= P.minm && p + 4 <= n) {
+                uint32_t h = hashf(src + p, P);
+                for (int wy = 0; wy < P.ways; wy++) {
+                    int c = T[(size_t)h * P.ways + wy];
+                    if (c >= 0 && p - c <= 32768) { int l = mlen(src + c, src + p, maxl); if (l >= P.minm && l > bl) { bl = l; bd = p - c; } }
+                }
+                if (P.warp) {   // nearest lower lane in same warp with same hash
+                    int base = p & ~31;
+                    for (int q = p - 1; q >= base && q >= w0; q--) if (q + 4 <= n && hashf(src + q, P) == h) {
+                        int l = mlen(src + q, src + p, maxl); if (l >= P.minm && l > bl) { bl = l; bd = p - q; } break; }
+                }
+            }
+            if (P.rle && p >= 1 && maxl >= 3) { int l = mlen(src + p - 1, src + p, maxl); if (l >= 3 && l > bl) { bl = l; bd = 1; } }
+            L[p] = bl; D[p] = bd;
+        }
+        // insert
+        if (P.winner) { for (int p = w0; p < w1; p++) if (p + 4 <= n) { uint32_t h = hashf(src + p, P); if (P.ways > 1) { for (int wy = P.ways - 1; wy > 0; wy--) T[(size_t)h * P.ways + wy] = T[(size_t)h * P.ways + wy - 1]; } T[(size_t)h * P.ways] = p; } }
+        else { for (int p = w1 - 1; p >= w0; p--) if (p + 4 <= n) T[(size_t)hashf(src + p, P) * P.ways] = p; }
+    }
+    long bits = 0, ntok = 0;
+    for (int b0 = 0; b0 < n; b0 += P.sub) {
+        int b1 = std::min(n, b0 + P.sub);
+        std::vector<Tok> toks;
+        int p = b0;
+        while (p < b1) {
+            int l = L[p];
+            int lim = b1 - p; if (P.S) lim = std::min(lim, P.S - (p % P.S));
+            if (l > lim) l = lim;
+            if (P.lazy && l >= P.minm && l < 32 && p + 1 < b1) { int l2 = std::min(L[p + 1], lim - 1); if (l2 > l) l = 0; }
+            if (l >= std::max(3, (D[p] == 1 ? 3 : P.minm)) ) { toks.push_back({l, D[p], 0}); p += l; }
+            else { toks.push_back({0, 0, src[p]}); p++; }
+        }
+        ntok += toks.size();
+        bits += encode_block_bits(toks, b1 - b0);
+    }
+    if (ntok_out) *ntok_out += ntok;
+    return bits;
+}
+
+int main(int argc, char **argv)
+{
+    Params P; size_t total = 24u << 20; int kind = 1; const char *only = 0;
+    for (int i = 1; i < argc; i++) {
+        auto eq = strchr(argv[i], '='); if (!eq) continue; int v = atoi(eq + 1); std::string k(argv[i], eq - argv[i]);
+        if (k == "piece") P.piece = v; else if (k == "sub") P.sub = v; else if (k == "W") P.W = v; else if (k == "hb") P.hb = v;
+        else if (k == "hbytes") P.hbytes = v; else if (k == "minm") P.minm = v; else if (k == "S") P.S = v; else if (k == "rle") P.rle = v;
+        else if (k == "warp") P.warp = v; else if (k == "winner") P.winner = v; else if (k == "mb") total = (size_t)v << 20; else if (k == "kind") kind = v;
+        else if (k == "lazy") P.lazy = v; else if (k == "ways") P.ways = v; else if (k == "only") only = eq + 1;
+    }
+    void *h = dlopen("harness/libqzcorpus.so", RTLD_NOW); if (!h) { fprintf(stderr, "no corpus lib\n"); return 1; }
+    auto fill = (int (*)(int, uint64_t, uint64_t, uint8_t *, size_t, int))dlsym(h, "qzcorpus_fill");
+    std::vector<uint8_t> buf(total); fill(kind, kind ? 0x51CE51A : 1, 0, buf.data(), total, 8);
+    const char *CYC = "TXBETXBTZTXR";
+    long zl_tot = 0, my_tot = 0; long zl_c[256] = {0}, my_c[256] = {0}, nb_c[256] = {0}, ntok = 0;
+    std::vector<uint8_t> tmp(80000);
+    for (size_t off = 0; off < total; off += 65536) {
+        int n = (int)std::min<size_t>(65536, total - off); char cls = kind ? CYC[(off >> 20) % 12] : 'r';
+        if (only && !strchr(only, cls)) continue;
+        z_stream z; memset(&z, 0, sizeof z); deflateInit2(&z, 1, Z_DEFLATED, -15, 9, 0);
+        z.next_in = buf.data() + off; z.avail_in = n; z.next_out = tmp.data(); z.avail_out = tmp.size(); deflate(&z, Z_FINISH);
+        long zb = z.total_out; deflateEnd(&z);
+        long mb = 0;
+        for (int q = 0; q < n; q += P.piece) mb += (model_piece(buf.data() + off + q, std::min(P.piece, n - q), P, &ntok) + 7) / 8 + (q + P.piece < n ? 5 : 0);
+        zl_tot += zb; my_tot += mb; zl_c[(int)cls] += zb; my_c[(int)cls] += mb; nb_c[(int)cls] += n;
+    }
+    for (int c = 0; c < 256; c++) if (nb_c[c]) printf("  %c zlib %.4f model %.4f  rel %+.2f%%\n", c, (double)zl_c[c] / nb_c[c], (double)my_c[c] / nb_c[c], 100.0 * ((double)my_c[c] / zl_c[c] - 1));
+    printf("TOTAL zlib %ld model %ld rel %+.2f%%  tokens/byte %.3f\n", zl_tot, my_tot, 100.0 * ((double)my_tot / zl_tot - 1), (double)ntok / total);
+    return 0;
+}
