@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json: qzCompress GB/s of input at 64 KiB chunks).
+
+A "step" is one pass of the hot path over the whole per-GPU workload:
+    qzCompress, QZ_DEFLATE_GZIP_EXT, level 1, hw_buff_sz 64 KiB, 4 GiB SILESIA-LIKE synthetic,
+    issued as 8 calls of 512 MiB (the API's lengths are 32-bit), BASELINE.json configs[1].
+Every rank owns one GPU and its own 4 GiB shard (weak scaling, no data-path collective).
+
+  value      input bytes / second with the input already resident in HBM (device-resident entry
+             point qzb200CompressDevice -> same kernels), all ranks summed, max-over-ranks time.
+  e2e        the same pass through the reference-facing C ABI: qzCompress() with HOST buffers
+             from qzMalloc(PINNED), host->device and device->host copies inside the timed region.
+  roofline   (bytes in + bytes out) of one deflate-kernel launch / its CUDA-event duration,
+             against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's own software path (oracle/_ref: src/qatzip_sw.c + zlib) on the
+             host cores of this box, a bounded sample of the same bytes, same parameters.
+
+`--impl reference` times only that CPU path (all host threads) and prints the same JSON shape.
+Inputs are larger than L2 (4 GiB >> 126 MB), so no explicit flush is needed between steps.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from harness import qzapi as q  # noqa: E402
+
+GB = 1e9
+CALL_BYTES = 512 << 20
+CHUNK = 65536
+
+
+def env_int(name, d):
+    v = os.environ.get(name)
+    return int(v) if v else d
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_pass(lib_path, host_addr, nbytes, threads):
+    """The reference's software path over host_addr[0:nbytes): one session per thread, contiguous
+    slices, simultaneous start (pattern of reference test/main.c:2175-2202).  Returns (seconds, out_bytes)."""
+    ref = q.QzLib(lib_path)
+    per = (nbytes // threads) // CHUNK * CHUNK
+    per = max(per, CHUNK)
+    threads = max(1, min(threads, nbytes // per))
+    outs, barrier = [0] * threads, threading.Barrier(threads + 1)
+
+    def work(t):
+        sess = ref.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=CHUNK)
+        lo, hi = t * per, (t + 1) * per if t + 1 < threads else nbytes
+        cap = ref.lib.qzMaxCompressedLength(min(hi - lo, CALL_BYTES), None)
+        dst = (C.c_ubyte * cap)()
+        barrier.wait()
+        made_total = 0
+        for off in range(lo, hi, CALL_BYTES):
+            n = min(CALL_BYTES, hi - off)
+            rc, used, made = ref.compress_call(sess, host_addr + off, n, C.addressof(dst), cap)
+            assert rc == q.QZ_OK and used == n, (rc, used, n)
+            made_total += made
+        outs[t] = made_total
+        barrier.wait()
+        ref.end_session(sess)
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    barrier.wait(); t0 = time.perf_counter()
+    barrier.wait(); dt = time.perf_counter() - t0
+    [t.join() for t in ths]
+    return dt, sum(outs), threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gib", type=float, default=float(os.environ.get("QZ_BENCH_GIB", "4")), help="per-GPU workload (GiB); 4 = BASELINE config")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    nbytes = int(args.gib * (1 << 30)) // CALL_BYTES * CALL_BYTES or CALL_BYTES
+    ncores = os.cpu_count() or 1
+    ref_lib = q.REF_SO if os.path.exists(q.REF_SO) else None
+    workload = f"qzCompress QZ_DEFLATE_GZIP_EXT L1 hw_buff_sz=64KiB, {nbytes / (1 << 30):g} GiB SILESIA-LIKE per GPU in 512 MiB calls"
+
+    import __graft_entry__ as ge
+    if not (os.path.exists(q.CORPUS_SO) and os.path.exists(q.PORT_SO)):
+        ge.build_checkers()
+    cor = q.Corpus()
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = min(nbytes, max(1 << 30, ncores * (32 << 20)))
+        buf = (C.c_ubyte * sample)()
+        cor.fill(q.Corpus.SILESIA_LIKE, C.addressof(buf), sample, threads=min(64, ncores))
+        lib = ref_lib or None
+        assert lib, "oracle/_ref missing (build it where /root/reference exists)"
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt, out, thr = cpu_reference_pass(lib, C.addressof(buf), sample, ncores)
+            if i >= args.warmup:
+                times.append(dt)
+        dt = sum(times) / len(times)
+        v = sample / dt / GB
+        print(json.dumps({"impl": "reference", "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(v, 4), "unit": "GB/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": workload, "l2": "inputs larger than L2"},
+                          "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": thr, "kind": "reference",
+                                           "sample": f"{sample >> 20} MiB of the workload per step, one slice per thread"},
+                          "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "ratio": round(out / sample, 4)}))
+        return 0
+
+    # ---------------------------------------------------------------- our arm (GPU)
+    os.environ.setdefault("QZB200_DEVICE", str(local))
+    prod = q.QzLib(q.PRODUCT_SO)
+    L = prod.lib
+    assert L.qzb200DeviceCount() > 0, "no CUDA device: libqatzip.so has no CPU path"
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def allmax(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def allsum(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
+    sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=CHUNK)
+    # host input: pinned pages from qzMalloc, filled with this rank's shard of the corpus
+    h_in = L.qzMalloc(nbytes, 0, q.PINNED_MEM)
+    assert h_in, "qzMalloc(PINNED) failed"
+    segs_per_rank = nbytes >> 20
+    cor.fill(q.Corpus.SILESIA_LIKE, h_in, nbytes, first_seg=rank * segs_per_rank, threads=max(1, min(64, ncores // max(1, world))))
+    out_cap_call = L.qzMaxCompressedLength(CALL_BYTES, None)
+    h_out = L.qzMalloc(out_cap_call, 0, q.PINNED_MEM)
+    d_in = L.qzb200DeviceAlloc(nbytes)
+    d_out = L.qzb200DeviceAlloc(out_cap_call)
+    assert h_out and d_in and d_out
+    assert L.qzb200CopyToDevice(d_in, h_in, nbytes) == 0
+    ncalls = nbytes // CALL_BYTES
+
+    def device_pass():
+        made_total, codec_ms, codec_launches, launches = 0, 0.0, 0, 0
+        for i in range(ncalls):
+            rc, used, made, _ = prod.compress_device(sess, d_in + i * CALL_BYTES, CALL_BYTES, d_out, out_cap_call, 1)
+            assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
+            st = prod.stats(sess)
+            made_total += made; codec_ms += st.codec_ms; codec_launches += st.codec_launches; launches += st.kernel_launches
+        return made_total, codec_ms, codec_launches, launches
+
+    def host_pass():
+        made_total = 0
+        for i in range(ncalls):
+            rc, used, made = prod.compress_call(sess, h_in + i * CALL_BYTES, CALL_BYTES, h_out, out_cap_call, 1)
+            assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
+            made_total += made
+        return made_total
+
+    for _ in range(args.warmup):
+        device_pass()
+    clocks = ClockSampler(local)
+    barrier(); clocks.start(); t0 = time.perf_counter()
+    made = codec_ms = 0.0; codec_launches = launches = 0
+    for _ in range(args.steps):
+        m, cm, cl, ln = device_pass()
+        made, codec_ms, codec_launches, launches = m, codec_ms + cm, codec_launches + cl, launches + ln
+    barrier(); dt = allmax(time.perf_counter() - t0)
+    clk = clocks.stop()
+    ms_per_step = dt / args.steps * 1e3
+    total_in = allsum(float(nbytes))
+    value = total_in / (dt / args.steps) / GB
+
+    # end to end through qzCompress with host buffers
+    for _ in range(min(args.warmup, 2)):
+        host_pass()
+    barrier(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        made_h = host_pass()
+    barrier(); dt_e = allmax(time.perf_counter() - t0)
+    e2e = total_in / (dt_e / args.steps) / GB
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        per_launch_bytes = (nbytes + made) / (codec_launches / args.steps)
+        per_launch_s = codec_ms / 1e3 / codec_launches
+        achieved = per_launch_bytes / per_launch_s / GB
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("deflate_pieces_dram_bytes_per_launch")
+        # CPU baseline: bounded sample of the same bytes through the reference's software path
+        cpu = None
+        if ref_lib and not os.environ.get("QZ_BENCH_NOCPU"):
+            sample = min(nbytes, max(256 << 20, ncores * (16 << 20)))
+            dtc, outc, thr = cpu_reference_pass(ref_lib, h_in, sample, ncores)
+            cpu = {"value": round(sample / dtc / GB, 4), "unit": "GB/s", "cores": thr, "kind": "reference",
+                   "sample": f"first {sample >> 20} MiB of rank 0's shard, one pass, {thr} threads", "ratio": round(outc / sample, 4)}
+        st = prod.stats(sess)
+        print(json.dumps({
+            "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
+                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
+            "ratio": round(made / nbytes, 4),
+            "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
+                    "api": "qzCompress(host pinned -> host pinned), 512 MiB per call"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": int(per_launch_bytes), "ms_per_launch": round(per_launch_s * 1e3, 4)},
+            "cpu_baseline": cpu, "clocks": clk}))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

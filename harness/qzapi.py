@@ -72,6 +72,12 @@ class QzStream(C.Structure):  # reference include/qatzip.h:2358-2379
                 ("crc_32", C.c_uint), ("reserved", C.c_ulonglong), ("opaque", C.c_void_p)]
 
 
+class QzB200Stats(C.Structure):  # include/qatzip_b200.h
+    _fields_ = [("kernel_ms", C.c_double), ("codec_ms", C.c_double), ("codec_launches", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("units", C.c_uint64), ("device", C.c_int),
+                ("piece_log2", C.c_int), ("hash_bits", C.c_int)]
+
+
 def _addr(buf):
     """Address of a bytes / bytearray / numpy array / int without copying."""
     if isinstance(buf, int):
@@ -122,6 +128,17 @@ class QzLib:
         L.qzEndStream.argtypes = [S, P(QzStream)]
         L.qzGetDeflateEndOfStream.argtypes = [S, P(C.c_ubyte)]
         L.qzSetLogLevel.argtypes = [C.c_int]
+        if hasattr(L, "qzb200DeviceCount"):   # product-only extensions (include/qatzip_b200.h)
+            U64P = P(C.c_uint64)
+            L.qzb200CompressDevice.argtypes = [S, V, C.c_uint64, V, C.c_uint64, C.c_uint, U64P, U64P, P(C.c_ulong)]
+            L.qzb200DecompressDevice.argtypes = [S, V, V, C.c_uint64, V, C.c_uint64, U64P, U64P]
+            L.qzb200GetStats.argtypes = [S, P(QzB200Stats)]
+            L.qzb200DeviceAlloc.argtypes = [C.c_uint64]
+            L.qzb200DeviceAlloc.restype = V
+            L.qzb200DeviceFree.argtypes = [V]
+            L.qzb200DeviceFree.restype = None
+            L.qzb200CopyToDevice.argtypes = [V, V, C.c_uint64]
+            L.qzb200CopyToHost.argtypes = [V, V, C.c_uint64]
         if not os.environ.get("QZ_HARNESS_VERBOSE"):
             L.qzSetLogLevel(0)  # LOG_NONE: the CPU reference logs an error per qzInit without QAT hardware
 
@@ -156,6 +173,22 @@ class QzLib:
 
     def end_session(self, sess):
         self.lib.qzTeardownSession(C.byref(sess))
+
+    def stats(self, sess):
+        st = QzB200Stats()
+        rc = self.lib.qzb200GetStats(C.byref(sess), C.byref(st))
+        assert rc == QZ_OK
+        return st
+
+    def compress_device(self, sess, d_src, n, d_dst, cap, last=1):
+        used, made, crc = C.c_uint64(0), C.c_uint64(0), C.c_ulong(0)
+        rc = self.lib.qzb200CompressDevice(C.byref(sess), d_src, n, d_dst, cap, last, C.byref(used), C.byref(made), C.byref(crc))
+        return rc, used.value, made.value, crc.value & 0xFFFFFFFF
+
+    def decompress_device(self, sess, d_src, h_view, n, d_dst, cap):
+        used, made = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.qzb200DecompressDevice(C.byref(sess), d_src, _addr(h_view), n, d_dst, cap, C.byref(used), C.byref(made))
+        return rc, used.value, made.value
 
     # ---- one-shot helpers -----------------------------------------------------------------
     def compress_call(self, sess, src, src_len, dst, dst_cap, last=1, crc=None):

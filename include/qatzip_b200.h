@@ -12,7 +12,9 @@ extern "C" {
 #endif
 
 typedef struct QzB200Stats_S {
-    double kernel_ms;            /* device time of the codec kernels of the last call (CUDA events) */
+    double kernel_ms;            /* device time of all kernels of the last call (CUDA events on the launch stream) */
+    double codec_ms;             /* of which: the piece kernel (deflate / LZ4 compress), summed over its launches */
+    uint64_t codec_launches;     /* launches of the piece kernel in the last call */
     uint64_t kernel_launches;    /* kernels launched by the last call */
     uint64_t units;              /* chunks compressed / members decoded by the last call */
     int device;                  /* CUDA device ordinal the session runs on */
@@ -31,6 +33,12 @@ int qzb200DecompressDevice(QzSession_T *sess, const void *d_src, const void *h_s
 int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *stats);
 /* number of CUDA devices the library can use, and the one this process would pick
  * (QZB200_DEVICE, else LOCAL_RANK, else 0) */
+/* plain device-memory helpers (cudaMalloc / cudaFree / cudaMemcpy on the session's GPU) so that a
+ * C caller or a ctypes harness can stage data in HBM without linking the CUDA runtime itself */
+void *qzb200DeviceAlloc(uint64_t bytes);
+void qzb200DeviceFree(void *d_ptr);
+int qzb200CopyToDevice(void *d_dst, const void *h_src, uint64_t bytes);
+int qzb200CopyToHost(void *h_dst, const void *d_src, uint64_t bytes);
 int qzb200DeviceCount(void);
 int qzb200DefaultDevice(void);
 

@@ -376,7 +376,7 @@ extern "C" int qzCompressCrcExt(QzSession_T *sess, const unsigned char *src, uns
         c.src_pinned = qzb_pinned_contains(src, *src_len); c.dst_pinned = qzb_pinned_contains(dest, *dest_len);
         c.want_crc = crc != NULL; c.crc_in = crc ? (uint32_t)*crc : 0;
         rc = qzb_engine_compress(s->engine, &c, &o);
-        s->stats.kernel_ms = o.kernel_ms; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nchunks;
+        s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.codec_ms; s->stats.codec_launches = o.codec_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nchunks;
         if (rc != QZ_OK && rc != QZ_BUF_ERROR) goto err;
         if (crc && c.fmt != QZB_FMT_INTERNAL_LZ4) *crc = o.crc;       /* reference src/qatzip.c:1707-1714 */
         *src_len = (unsigned int)o.consumed; *dest_len = (unsigned int)o.produced;
@@ -419,7 +419,7 @@ extern "C" int qzDecompressCrcExt(QzSession_T *sess, const unsigned char *src, u
         c.stop_at_first = s->p.stop_decompression_stream_end;
         s->end_of_stream = 0;
         rc = qzb_engine_decompress(s->engine, &c, &o);
-        s->stats.kernel_ms = o.kernel_ms; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
+        s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.kernel_ms; s->stats.codec_launches = o.kernel_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
         if (rc != QZ_OK && rc != QZ_BUF_ERROR && rc != QZ_DATA_ERROR) goto err;
         if (rc == QZ_DATA_ERROR && o.consumed == 0) goto err;
         if (o.nmembers > 0) s->end_of_stream = 1;                        /* reference src/qatzip_utils.c:1534-1554 */
@@ -495,6 +495,7 @@ struct QzbStreamBuf {
     unsigned int in_cap, out_cap;          /* staging capacity (may grow beyond strm_buff_sz on decode) */
     unsigned int in_off, out_off;          /* consumed prefix of in_buf / delivered prefix of out_buf */
     unsigned int flush_more;
+    unsigned int finished;                 /* a call with last==1 has already been coded */
 };
 static int stream_init(QzSession_T *sess, QzStream_T *strm, QzbSess **sp)
 {
@@ -554,7 +555,7 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
         if (strm->in) consumed += stream_copy_in(strm, b, strm->in + consumed);
         const bool input_done = (strm->in_sz == 0);
         if (strm->pending_in < b->in_cap - b->in_off && !(last && input_done)) break;
-        if (strm->pending_in == 0 && !(last && input_done)) break;
+        if (strm->pending_in == 0 && (!(last && input_done) || b->finished)) break;
         /* 3. one engine call over the staged bytes */
         unsigned int in_len = strm->pending_in, out_len = b->out_cap;
         unsigned int need = qzMaxCompressedLength(in_len ? in_len : 1, sess);
@@ -564,6 +565,7 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
         rc = qzCompressCrc(sess, b->in_buf + b->in_off, &in_len, b->out_buf, &out_len, strm_last, &crc);
         if (rc != QZ_OK) { rc = QZ_FAIL; break; }
         strm->crc_32 = (unsigned int)crc;
+        if (strm_last) b->finished = 1;
         strm->pending_in -= in_len; b->in_off += in_len;
         if (strm->pending_in == 0) b->in_off = 0;
         strm->pending_out = out_len; b->out_off = 0;
@@ -660,7 +662,7 @@ extern "C" int qzb200CompressDevice(QzSession_T *sess, const void *d_src, uint64
     c.src = (const uint8_t *)d_src; c.src_len = src_len; c.dst = (uint8_t *)d_dest; c.dst_cap = dest_cap;
     c.src_device = 1; c.dst_device = 1; c.want_crc = crc != NULL; c.crc_in = crc ? (uint32_t)*crc : 0;
     rc = qzb_engine_compress(s->engine, &c, &o);
-    s->stats.kernel_ms = o.kernel_ms; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nchunks;
+    s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.codec_ms; s->stats.codec_launches = o.codec_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nchunks;
     *consumed = o.consumed; *produced = o.produced;
     if (crc && c.fmt != QZB_FMT_INTERNAL_LZ4 && (rc == QZ_OK || rc == QZ_BUF_ERROR)) *crc = o.crc;
     if (rc == QZ_OK || rc == QZ_BUF_ERROR) { sess->total_in += o.consumed; sess->total_out += o.produced; }
@@ -680,7 +682,7 @@ extern "C" int qzb200DecompressDevice(QzSession_T *sess, const void *d_src, cons
     c.dst = (uint8_t *)d_dest; c.dst_cap = dest_cap; c.src_device = 1; c.dst_device = 1;
     c.stop_at_first = s->p.stop_decompression_stream_end;
     rc = qzb_engine_decompress(s->engine, &c, &o);
-    s->stats.kernel_ms = o.kernel_ms; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
+    s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.kernel_ms; s->stats.codec_launches = o.kernel_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
     *consumed = o.consumed; *produced = o.produced;
     return rc;
 }
@@ -692,6 +694,10 @@ extern "C" int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *st)
     *st = s->stats; st->device = qzb_runtime_default_device(); st->piece_log2 = t.piece_log2; st->hash_bits = t.hash_bits;
     return QZ_OK;
 }
+extern "C" void *qzb200DeviceAlloc(uint64_t n) { int d = qzb_runtime_default_device(); return d < 0 ? NULL : qzb_device_alloc(d, (size_t)n); }
+extern "C" void qzb200DeviceFree(void *p) { int d = qzb_runtime_default_device(); if (d >= 0) qzb_device_free(d, p); }
+extern "C" int qzb200CopyToDevice(void *d, const void *h, uint64_t n) { int dv = qzb_runtime_default_device(); return dv < 0 ? QZ_NOSW_NO_HW : qzb_device_copy(dv, d, h, (size_t)n, 1); }
+extern "C" int qzb200CopyToHost(void *h, const void *d, uint64_t n) { int dv = qzb_runtime_default_device(); return dv < 0 ? QZ_NOSW_NO_HW : qzb_device_copy(dv, h, d, (size_t)n, 0); }
 extern "C" int qzb200DeviceCount(void) { return qzb_runtime_devices(); }
 extern "C" int qzb200DefaultDevice(void) { return qzb_runtime_default_device(); }
 

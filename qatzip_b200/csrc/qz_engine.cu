@@ -105,6 +105,19 @@ extern "C" int qzb_pinned_contains(const void *p, size_t len)
     return (uintptr_t)p >= it->first && (uintptr_t)p + (len ? len : 1) <= it->first + it->second;
 }
 
+extern "C" void *qzb_device_alloc(int device, size_t n)
+{
+    void *p = NULL;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, n ? n : 1) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+    return p;
+}
+extern "C" void qzb_device_free(int device, void *p) { if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p); }
+extern "C" int qzb_device_copy(int device, void *dst, const void *src, size_t n, int to_device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return RC_FAIL;
+    return cudaMemcpy(dst, src, n, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost) == cudaSuccess ? RC_OK : RC_FAIL;
+}
+
 /* ------------------------------------------------------------------ buffers */
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -133,7 +146,7 @@ struct HostBuf {
 
 struct Slot {
     cudaStream_t st = nullptr;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr;
     DevBuf d_in, d_slots, d_out, d_meta, d_tok, d_members, d_results;
     HostBuf h_meta, h_in, h_out, h_members, h_results;
     /* bookkeeping of the batch currently in flight */
@@ -164,7 +177,7 @@ extern "C" QzbEngine *qzb_engine_create(int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     for (auto &s : e->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NULL; }
-        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_k1);
+        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1);
         cudaEventCreateWithFlags(&s.ev_meta, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
     }
@@ -177,6 +190,7 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
     for (auto &s : e->slot) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_km) cudaEventDestroy(s.ev_km);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_meta) cudaEventDestroy(s.ev_meta);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -250,6 +264,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, s.st));
+    CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));
     CK(cudaEventRecord(s.ev_k1, s.st));
     *launches += lz4 ? 5 : 4;
@@ -279,6 +294,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
             if (enqueue_compress(e, s, c, c->src + in, len, c->dst + out, c->dst_cap - out, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
             CK(cudaEventSynchronize(s.ev_meta));
             float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+            cudaEventElapsedTime(&ms, s.ev_k0, s.ev_km); o->codec_ms += ms; o->codec_launches++;
             const uint64_t *off = (const uint64_t *)s.h_meta.p;
             const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
             uint32_t fit = 0;
@@ -308,6 +324,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         CK(cudaEventSynchronize(s.ev_meta));
         if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
         float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+        cudaEventElapsedTime(&ms, s.ev_k0, s.ev_km); o->codec_ms += ms; o->codec_launches++;
         const uint64_t *off = (const uint64_t *)s.h_meta.p;
         const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
         uint32_t fit = 0;
@@ -369,6 +386,7 @@ struct ParsedMember {
     uint64_t unit_start;       /* offset of the member/frame header in the call's src */
     uint32_t hdr_len, ftr_len;
     bool sized;                /* payload length and output size known up front */
+    bool speculative;          /* extent guessed by the gzip magic scan: verified by the decode */
 };
 
 /* RFC 1952 header walk.  Returns header length, 0 if more bytes are needed, -1 if not gzip. */
@@ -403,113 +421,22 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
     if (!hsrc) return RC_PARAMS;
     if (c->src_device != c->dst_device) return RC_PARAMS;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
-    int rc = RC_OK;
-    uint64_t in = 0, out = 0;
-
-    /* ---- pass 1 (host): walk the units, like checkHeader does per request ---- */
-    std::vector<ParsedMember> units;
-    bool unsized_tail = false;
-    while (in < c->src_len) {
-        const uint8_t *p = hsrc + in; const uint64_t avail = c->src_len - in;
-        ParsedMember u; memset(&u, 0, sizeof u); u.unit_start = in;
-        if (c->fmt == QZB_FMT_GZIP || c->fmt == QZB_FMT_GZIP_EXT) {
-            bool has_qz; uint32_t qsrc = 0, qdst = 0;
-            long h = gzip_header_len(p, avail, &has_qz, &qsrc, &qdst);
-            if (h < 0) { rc = RC_FAIL; break; }
-            if (h == 0) { rc = RC_DATA_ERROR; break; }
-            u.hdr_len = (uint32_t)h; u.ftr_len = 8;
-            uint64_t payload;
-            if (has_qz) payload = qdst;
-            else {
-                /* next member by magic scan, footer sits right before it: reference src/qatzip_gzip.c:244-261 */
-                uint64_t q = (uint64_t)h + 8; bool found = false;
-                while (q + 4 <= avail) {
-                    const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, avail - q - 3);
-                    if (!f) break;
-                    q = (uint64_t)(f - p);
-                    if (p[q + 1] == 0x8b && p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0) { found = true; break; }
-                    q++;
-                }
-                const uint64_t end = found ? q : avail;
-                if (end < (uint64_t)h + 8) { rc = RC_DATA_ERROR; break; }
-                payload = end - h - 8;
-            }
-            if ((uint64_t)h + payload + 8 > avail) { rc = RC_DATA_ERROR; break; }
-            const uint8_t *ftr = p + h + payload;
-            const uint32_t isize = has_qz ? qsrc : rd32(ftr + 4);
-            if ((uint64_t)isize > c->dst_cap - out) { rc = RC_BUF_ERROR; break; }
-            u.m.src_off = in + h; u.m.src_len = (uint32_t)payload; u.m.exact_len = 1;
-            u.m.dst_off = out; u.m.dst_cap = isize; u.m.exact_out = 1;
-            u.m.expect_cksum = rd32(ftr); u.m.check_cksum = 1; u.sized = true;
-            if (payload > 0xfffffff0ull) { rc = RC_FAIL; break; }
-            in += h + payload + 8; out += isize;
-        } else if (c->fmt == QZB_FMT_4B) {
-            if (avail < 4) { rc = RC_DATA_ERROR; break; }
-            const uint32_t blk = rd32(p);
-            if (4 + (uint64_t)blk > avail) { rc = RC_DATA_ERROR; break; }
-            u.hdr_len = 4; u.m.src_off = in + 4; u.m.src_len = blk; u.m.exact_len = 1;
-            u.m.dst_cap = c->chunk_sz; u.m.exact_out = 0; u.sized = false;
-            in += 4 + (uint64_t)blk;
-        } else if (c->fmt == QZB_FMT_RAW) {
-            if (avail > 0xfffffff0ull) { rc = RC_FAIL; break; }
-            u.m.src_off = in; u.m.src_len = (uint32_t)avail; u.m.exact_len = 0;
-            /* deflate cannot expand more than 1032:1, which bounds the staging a raw stream needs */
-            u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, avail * 1032 + 64), 0xfffffff0ull); u.sized = false;
-            in += avail; unsized_tail = true;
-        } else if (lz4) {
-            /* frame header: reference src/qatzip_lz4.c:62-102 (verify), :145-173 (walk blocks to EndMark) */
-            if (avail < 7) { rc = RC_DATA_ERROR; break; }
-            if (rd32(p) != 0x184D2204u) { rc = RC_FAIL; break; }
-            const uint8_t flg = p[4];
-            if ((flg >> 6) != 1) { rc = RC_FAIL; break; }
-            uint64_t h = 6 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
-            if (avail < h + 4) { rc = RC_DATA_ERROR; break; }
-            if (p[h - 1] != (uint8_t)(qz_xxh32(p + 4, (size_t)(h - 5), 0) >> 8)) { rc = RC_DATA_ERROR; break; }
-            uint64_t q = h; bool ok = false;
-            while (q + 4 <= avail) {
-                const uint32_t bh = rd32(p + q);
-                if (bh == 0) { ok = true; break; }
-                q += 4 + (uint64_t)(bh & 0x7fffffffu) + ((flg & 0x10) ? 4 : 0);
-            }
-            if (!ok) { rc = RC_DATA_ERROR; break; }
-            const uint32_t ftr = 4 + ((flg & 4) ? 4 : 0);
-            if (q + ftr > avail) { rc = RC_DATA_ERROR; break; }
-            u.hdr_len = (uint32_t)h; u.ftr_len = ftr;
-            u.m.src_off = in + h; u.m.src_len = (uint32_t)(q - h); u.m.exact_len = 1;
-            u.m.check_cksum = (flg & 4) ? 1 : 0; u.m.expect_cksum = (flg & 4) ? rd32(p + q + 4) : 0;
-            /* flags the kernel needs ride in the upper bits of exact_len */
-            u.m.exact_len |= ((flg & 0x10) ? 2u : 0u) | ((flg & 0x20) ? 4u : 0u);
-            if (flg & 8) {
-                const uint64_t cs = (uint64_t)rd32(p + 6) | (uint64_t)rd32(p + 10) << 32;
-                if (cs > c->dst_cap - out) { rc = RC_BUF_ERROR; break; }
-                if (cs > 0xfffffff0ull) { rc = RC_FAIL; break; }
-                u.m.dst_off = out; u.m.dst_cap = (uint32_t)cs; u.m.exact_out = 1; u.sized = true; out += cs;
-            } else { u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, (q - h) * 255 + 64), 0xfffffff0ull); u.sized = false; }
-            in += q + ftr;
-        } else return RC_PARAMS;
-        units.push_back(u);
-        if (c->stop_at_first) break;
-        if (!u.sized && (lz4 || c->fmt == QZB_FMT_RAW)) break;      /* output position of what follows is unknown */
-    }
-    (void)unsized_tail;
-    if (units.empty()) { o->consumed = 0; o->produced = 0; return rc; }
-
-    /* ---- pass 2 (device) ---- */
-    const bool all_sized = std::all_of(units.begin(), units.end(), [](const ParsedMember &u) { return u.sized; });
-    uint64_t done_in = 0, done_out = 0; int rc2 = RC_OK;
     const int grid_cap = e->sm_count * 6;
+    uint64_t cur_in = 0, cur_out = 0;      /* everything before these offsets is decoded and delivered */
 
+    /* one kernel launch over units[first, first+count); outputs either at their final offsets
+     * (relative to out_base) or, when staged, in private regions of the slot's d_out */
+    std::vector<ParsedMember> units;
     auto run = [&](Slot &s, size_t first, size_t count, uint64_t span_src, uint64_t span_len, uint64_t out_base, uint64_t out_len,
                    bool staged_out) -> int {
-        /* staged_out: members decode into private regions of the slot's d_out (stride chunk_sz) */
-        const uint8_t *d_src; uint8_t *d_dst;
-        if (c->src_device) { d_src = c->src + span_src; d_dst = staged_out ? nullptr : c->dst + out_base; }
+        const uint8_t *d_src; uint8_t *d_dst = nullptr;
+        if (c->src_device) { d_src = c->src + span_src; if (!staged_out) d_dst = c->dst + out_base; }
         else {
             if (s.d_in.ensure(span_len + 64) != RC_OK) return RC_FAIL;
             if (c->src_pinned) CK(cudaMemcpyAsync(s.d_in.p, c->src + span_src, span_len, cudaMemcpyHostToDevice, s.st));
             else { if (s.h_in.ensure(span_len) != RC_OK) return RC_FAIL; memcpy(s.h_in.p, c->src + span_src, span_len);
                    CK(cudaMemcpyAsync(s.d_in.p, s.h_in.p, span_len, cudaMemcpyHostToDevice, s.st)); }
-            d_src = (const uint8_t *)s.d_in.p; d_dst = nullptr;
+            d_src = (const uint8_t *)s.d_in.p;
         }
         if (!d_dst) { if (s.d_out.ensure(out_len + 64) != RC_OK) return RC_FAIL; d_dst = (uint8_t *)s.d_out.p; }
         if (s.h_members.ensure(count * sizeof(QzbMember)) != RC_OK || s.d_members.ensure(count * sizeof(QzbMember)) != RC_OK) return RC_FAIL;
@@ -538,93 +465,248 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         s.busy = true; s.first_member = first; s.nmembers = count; s.span_src = span_src; s.span_len = span_len; s.out_base = out_base; s.out_len = out_len;
         return RC_OK;
     };
-
     auto status_rc = [&](const QzbMemberResult &r, bool sized) -> int {
-        switch (r.status) {
-        case QZB_ST_OK: return RC_OK;
-        case QZB_ST_OUT_FULL: return sized ? RC_DATA_ERROR : RC_BUF_ERROR;
-        default: return RC_DATA_ERROR;
-        }
+        if (r.status == QZB_ST_OK) return RC_OK;
+        if (r.status == QZB_ST_OUT_FULL) return sized ? RC_DATA_ERROR : RC_BUF_ERROR;
+        return RC_DATA_ERROR;
+    };
+    /* decode ONE unit whose extent is not trusted / not known: payload = everything that is left,
+     * output into staging; the device reports how much it really used and made */
+    auto run_single = [&](ParsedMember u, uint32_t src_len, uint32_t cap, QzbMemberResult *res, const uint8_t **staged) -> int {
+        Slot &s = e->slot[0];
+        units.assign(1, u);
+        units[0].m.src_len = src_len; units[0].m.exact_len &= ~1u; units[0].m.dst_cap = cap; units[0].m.exact_out = 0; units[0].m.check_cksum = 0;
+        if (run(s, 0, 1, u.m.src_off, src_len, 0, align_up(cap, 16), true) != RC_OK) return RC_FAIL;
+        s.busy = false;
+        CK(cudaEventSynchronize(s.ev_meta));
+        float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+        *res = *(const QzbMemberResult *)s.h_results.p;
+        *staged = (const uint8_t *)s.d_out.p;
+        return RC_OK;
+    };
+    auto deliver = [&](const uint8_t *staged, uint64_t nbytes) -> int {
+        if (!nbytes) return RC_OK;
+        Slot &s = e->slot[0];
+        CK(cudaMemcpyAsync(c->dst + cur_out, staged, nbytes, c->dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.st));
+        CK(cudaStreamSynchronize(s.st));
+        return RC_OK;
     };
 
-    if (all_sized) {
-        /* members know where they go: batch them, two slots in flight */
-        const uint64_t bin = e->tune.batch_bytes, bout = e->tune.batch_bytes * 4;
-        size_t i = 0, issued = 0; bool stop = false;
-        auto drain = [&](Slot &s) -> int {
-            if (!s.busy) return RC_OK;
-            s.busy = false;
-            CK(cudaEventSynchronize(s.ev_meta));
-            if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
-            float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
-            const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
-            size_t good = 0;
-            while (good < s.nmembers && r[good].status == QZB_ST_OK) good++;
-            uint64_t obytes = 0;
-            if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; obytes = lu.m.dst_off + lu.m.dst_cap - s.out_base; }
-            if (!c->dst_device && obytes) {
-                if (c->dst_pinned) CK(cudaMemcpyAsync(c->dst + s.out_base, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st));
-                else { if (s.h_out.ensure(obytes) != RC_OK) return RC_FAIL; CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st)); }
-                CK(cudaStreamSynchronize(s.st));
-                if (!c->dst_pinned) memcpy(c->dst + s.out_base, s.h_out.p, obytes);
-            }
-            if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; done_in = lu.unit_start + lu.hdr_len + lu.m.src_len + lu.ftr_len; done_out = s.out_base + obytes; o->nmembers += (uint32_t)good; }
-            if (good < s.nmembers) { rc2 = status_rc(r[good], true); stop = true; }
-            return RC_OK;
-        };
-        while (i < units.size() && !stop) {
-            size_t j = i; uint64_t sin = 0, sout = 0;
-            while (j < units.size()) {
-                const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
-                if (j > i && (sin + ulen > bin || sout + units[j].m.dst_cap > bout)) break;
-                sin += ulen; sout += units[j].m.dst_cap; j++;
-            }
-            Slot &s = e->slot[issued & 1];
-            if (drain(s) != RC_OK) return RC_FAIL;
-            if (stop) break;
-            if (run(s, i, j - i, units[i].unit_start, sin, units[i].m.dst_off, sout, false) != RC_OK) return RC_FAIL;
-            if (issued > 0 && drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL;
-            issued++; i = j;
-        }
-        if (issued) { if (drain(e->slot[issued & 1]) != RC_OK) return RC_FAIL; if (drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL; }
-    } else {
-        /* 4B / RAW / unsized frames: output sizes come back from the device.  Decode into
-         * private staging regions, then place results one after another. */
-        Slot &s = e->slot[0];
-        size_t i = 0; done_out = 0;
-        const uint64_t bin = e->tune.batch_bytes;
-        while (i < units.size() && rc2 == RC_OK) {
-            size_t j = i; uint64_t sin = 0, sout = 0;
-            while (j < units.size()) {
-                const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
-                if (j > i && (sin + ulen > bin || sout > (e->tune.batch_bytes << 2))) break;
-                sin += ulen; sout += align_up(units[j].m.dst_cap, 16); j++;
-            }
-            if (run(s, i, j - i, units[i].unit_start, sin, 0, sout, true) != RC_OK) return RC_FAIL;
-            s.busy = false;
-            CK(cudaEventSynchronize(s.ev_meta));
-            float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
-            const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
-            const QzbMember *hm = (const QzbMember *)s.h_members.p;
-            for (size_t k = 0; k < j - i; k++) {
-                const ParsedMember &u = units[i + k];
-                int st = status_rc(r[k], false);
-                if (st == RC_OK && r[k].produced > c->dst_cap - done_out) st = RC_BUF_ERROR;
-                if (st != RC_OK) { rc2 = st; break; }
-                if (r[k].produced) {
-                    const uint8_t *from = (const uint8_t *)s.d_out.p + hm[k].dst_off;
-                    CK(cudaMemcpyAsync(c->dst + done_out, from, r[k].produced, c->dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s.st));
+    int final_rc = RC_OK;
+    while (cur_in < c->src_len) {
+        /* ---- pass 1 (host): walk unit headers from cur_in, like checkHeader does per request ---- */
+        units.clear();
+        int parse_rc = RC_OK;
+        uint64_t in = cur_in, out = cur_out;
+        while (in < c->src_len) {
+            const uint8_t *p = hsrc + in; const uint64_t avail = c->src_len - in;
+            ParsedMember u; memset(&u, 0, sizeof u); u.unit_start = in;
+            if (c->fmt == QZB_FMT_GZIP || c->fmt == QZB_FMT_GZIP_EXT) {
+                bool has_qz; uint32_t qsrc = 0, qdst = 0;
+                long h = gzip_header_len(p, avail, &has_qz, &qsrc, &qdst);
+                if (h < 0) { parse_rc = RC_FAIL; break; }
+                if (h == 0) { parse_rc = RC_DATA_ERROR; break; }
+                u.hdr_len = (uint32_t)h; u.ftr_len = 8;
+                uint64_t payload;
+                if (has_qz) payload = qdst;
+                else {
+                    /* next member by magic scan, footer right before it: reference src/qatzip_gzip.c:244-261.
+                     * The guess is verified by the decode (exact length, ISIZE, CRC) and replaced by a
+                     * sequential decode of this member if it does not hold. */
+                    uint64_t q = (uint64_t)h + 8; bool found = false;
+                    while (q + 4 <= avail) {
+                        const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, avail - q - 3);
+                        if (!f) break;
+                        q = (uint64_t)(f - p);
+                        if (p[q + 1] == 0x8b && p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0) { found = true; break; }
+                        q++;
+                    }
+                    const uint64_t end = found ? q : avail;
+                    if (end < (uint64_t)h + 8) { parse_rc = RC_DATA_ERROR; break; }
+                    payload = end - h - 8;
+                    u.speculative = true;
                 }
-                done_out += r[k].produced;
-                done_in = u.unit_start + u.hdr_len + (u.m.exact_len & 1 ? u.m.src_len : r[k].consumed) + u.ftr_len;
-                o->nmembers++;
-            }
-            CK(cudaStreamSynchronize(s.st));
-            i = j;
+                if ((uint64_t)h + payload + 8 > avail) { parse_rc = RC_DATA_ERROR; break; }
+                if (payload > 0xfffffff0ull) { parse_rc = RC_FAIL; break; }
+                const uint8_t *ftr = p + h + payload;
+                const uint32_t isize = has_qz ? qsrc : rd32(ftr + 4);
+                if ((uint64_t)isize > c->dst_cap - out) { parse_rc = RC_BUF_ERROR; break; }
+                u.m.src_off = in + h; u.m.src_len = (uint32_t)payload; u.m.exact_len = 1;
+                u.m.dst_off = out; u.m.dst_cap = isize; u.m.exact_out = 1;
+                u.m.expect_cksum = rd32(ftr); u.m.check_cksum = 1; u.sized = true;
+                in += h + payload + 8; out += isize;
+            } else if (c->fmt == QZB_FMT_4B) {
+                if (avail < 4) { parse_rc = RC_DATA_ERROR; break; }
+                const uint32_t blk = rd32(p);
+                if (4 + (uint64_t)blk > avail) { parse_rc = RC_DATA_ERROR; break; }
+                u.hdr_len = 4; u.m.src_off = in + 4; u.m.src_len = blk; u.m.exact_len = 1;
+                u.m.dst_cap = c->chunk_sz; u.m.exact_out = 0; u.sized = false;
+                in += 4 + (uint64_t)blk;
+            } else if (c->fmt == QZB_FMT_RAW) {
+                if (avail > 0xfffffff0ull) { parse_rc = RC_FAIL; break; }
+                u.m.src_off = in; u.m.src_len = (uint32_t)avail; u.m.exact_len = 0;
+                /* deflate cannot expand more than 1032:1, which bounds the staging a raw stream needs */
+                u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, avail * 1032 + 64), 0xfffffff0ull); u.sized = false;
+                in += avail;
+            } else if (lz4) {
+                /* frame header: reference src/qatzip_lz4.c:62-102 (verify), :145-173 (walk blocks to EndMark) */
+                if (avail < 7) { parse_rc = RC_DATA_ERROR; break; }
+                if (rd32(p) != 0x184D2204u) { parse_rc = RC_FAIL; break; }
+                const uint8_t flg = p[4];
+                if ((flg >> 6) != 1) { parse_rc = RC_FAIL; break; }
+                uint64_t h = 6 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
+                if (avail < h + 4) { parse_rc = RC_DATA_ERROR; break; }
+                if (p[h - 1] != (uint8_t)(qz_xxh32(p + 4, (size_t)(h - 5), 0) >> 8)) { parse_rc = RC_DATA_ERROR; break; }
+                uint64_t q = h; bool ok = false;
+                while (q + 4 <= avail) {
+                    const uint32_t bh = rd32(p + q);
+                    if (bh == 0) { ok = true; break; }
+                    q += 4 + (uint64_t)(bh & 0x7fffffffu) + ((flg & 0x10) ? 4 : 0);
+                }
+                if (!ok) { parse_rc = RC_DATA_ERROR; break; }
+                const uint32_t ftr = 4 + ((flg & 4) ? 4 : 0);
+                if (q + ftr > avail) { parse_rc = RC_DATA_ERROR; break; }
+                if (q - h > 0xfffffff0ull) { parse_rc = RC_FAIL; break; }
+                u.hdr_len = (uint32_t)h; u.ftr_len = ftr;
+                u.m.src_off = in + h; u.m.src_len = (uint32_t)(q - h);
+                /* bit 0: payload length is exact; bit 1: per-block checksums present (kernel skips them) */
+                u.m.exact_len = 1u | ((flg & 0x10) ? 2u : 0u);
+                u.m.check_cksum = (flg & 4) ? 1 : 0; u.m.expect_cksum = (flg & 4) ? rd32(p + q + 4) : 0;
+                if (flg & 8) {
+                    const uint64_t cs = (uint64_t)rd32(p + 6) | (uint64_t)rd32(p + 10) << 32;
+                    if (cs > c->dst_cap - out) { parse_rc = RC_BUF_ERROR; break; }
+                    if (cs > 0xfffffff0ull) { parse_rc = RC_FAIL; break; }
+                    u.m.dst_off = out; u.m.dst_cap = (uint32_t)cs; u.m.exact_out = 1; u.sized = true; out += cs;
+                } else { u.m.dst_cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - out, (q - h) * 255 + 64), 0xfffffff0ull); u.sized = false; }
+                in += q + ftr;
+            } else return RC_PARAMS;
+            units.push_back(u);
+            if (c->stop_at_first) break;
+            if (!u.sized && c->fmt != QZB_FMT_4B) break;     /* where the next unit's output starts is not known yet */
         }
+        if (units.empty()) { final_rc = parse_rc; break; }
+
+        /* ---- pass 2 (device) ---- */
+        const bool all_sized = std::all_of(units.begin(), units.end(), [](const ParsedMember &u) { return u.sized; });
+        int rc2 = RC_OK; long failed_unit = -1;
+        if (all_sized) {
+            /* members know where they go: batch them, two slots in flight */
+            const uint64_t bin = e->tune.batch_bytes, bout = e->tune.batch_bytes * 4;
+            size_t i = 0, issued = 0; bool stop = false;
+            auto drain = [&](Slot &s) -> int {
+                if (!s.busy) return RC_OK;
+                s.busy = false;
+                CK(cudaEventSynchronize(s.ev_meta));
+                if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
+                float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+                const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
+                size_t good = 0;
+                while (good < s.nmembers && r[good].status == QZB_ST_OK) good++;
+                uint64_t obytes = 0;
+                if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; obytes = lu.m.dst_off + lu.m.dst_cap - s.out_base; }
+                if (!c->dst_device && obytes) {
+                    if (c->dst_pinned) CK(cudaMemcpyAsync(c->dst + s.out_base, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st));
+                    else { if (s.h_out.ensure(obytes) != RC_OK) return RC_FAIL; CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, obytes, cudaMemcpyDeviceToHost, s.st)); }
+                    CK(cudaStreamSynchronize(s.st));
+                    if (!c->dst_pinned) memcpy(c->dst + s.out_base, s.h_out.p, obytes);
+                }
+                if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; cur_in = lu.unit_start + lu.hdr_len + lu.m.src_len + lu.ftr_len; cur_out = s.out_base + obytes; o->nmembers += (uint32_t)good; }
+                if (good < s.nmembers) { rc2 = status_rc(r[good], true); failed_unit = (long)(s.first_member + good); stop = true; }
+                return RC_OK;
+            };
+            while (i < units.size() && !stop) {
+                size_t j = i; uint64_t sin = 0, sout = 0;
+                while (j < units.size()) {
+                    const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
+                    if (j > i && (sin + ulen > bin || sout + units[j].m.dst_cap > bout)) break;
+                    sin += ulen; sout += units[j].m.dst_cap; j++;
+                }
+                Slot &s = e->slot[issued & 1];
+                if (drain(s) != RC_OK) return RC_FAIL;
+                if (stop) break;
+                if (run(s, i, j - i, units[i].unit_start, sin, units[i].m.dst_off, sout, false) != RC_OK) return RC_FAIL;
+                if (issued > 0 && drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL;
+                issued++; i = j;
+            }
+            if (issued) { if (drain(e->slot[issued & 1]) != RC_OK) return RC_FAIL; if (drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL; }
+            if (failed_unit >= 0 && units[(size_t)failed_unit].speculative) {
+                /* the magic-scan boundary was wrong (or the member is corrupt): decode it alone,
+                 * let the device find its end, check the footer found there, then resume parsing */
+                ParsedMember u = units[(size_t)failed_unit];
+                const uint64_t rest = c->src_len - u.m.src_off;
+                const uint64_t capl = std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - cur_out, rest * 1032 + 64), 0xfffffff0ull);
+                QzbMemberResult r; const uint8_t *staged = nullptr;
+                if (rest > 0xfffffff0ull) return RC_FAIL;
+                if (run_single(u, (uint32_t)rest, (uint32_t)capl, &r, &staged) != RC_OK) return RC_FAIL;
+                int st = status_rc(r, false);
+                if (st == RC_OK && !r.saw_final) st = RC_DATA_ERROR;
+                if (st == RC_OK && (uint64_t)r.consumed + 8 > rest) st = RC_DATA_ERROR;
+                if (st == RC_OK) {
+                    const uint8_t *ftr = hsrc + u.m.src_off + r.consumed;
+                    if (rd32(ftr) != r.cksum || rd32(ftr + 4) != r.produced) st = RC_DATA_ERROR;
+                }
+                if (st != RC_OK) { final_rc = st; break; }
+                if (deliver(staged, r.produced) != RC_OK) return RC_FAIL;
+                cur_in = u.m.src_off + r.consumed + 8; cur_out += r.produced; o->nmembers++;
+                if (c->stop_at_first) break;
+                continue;                                    /* re-parse from the corrected position */
+            }
+            if (rc2 != RC_OK) { final_rc = rc2; break; }
+        } else {
+            /* 4B / RAW / unsized frames: output sizes come back from the device.  Decode into
+             * private staging regions, then place the results one after another. */
+            Slot &s = e->slot[0];
+            size_t i = 0;
+            const uint64_t bin = e->tune.batch_bytes;
+            while (i < units.size() && rc2 == RC_OK) {
+                size_t j = i; uint64_t sin = 0, sout = 0;
+                while (j < units.size()) {
+                    const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
+                    if (j > i && (sin + ulen > bin || sout > (e->tune.batch_bytes << 2))) break;
+                    sin += ulen; sout += align_up(units[j].m.dst_cap, 16); j++;
+                }
+                if (run(s, i, j - i, units[i].unit_start, sin, 0, sout, true) != RC_OK) return RC_FAIL;
+                s.busy = false;
+                CK(cudaEventSynchronize(s.ev_meta));
+                float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+                std::vector<QzbMemberResult> res((const QzbMemberResult *)s.h_results.p, (const QzbMemberResult *)s.h_results.p + (j - i));
+                std::vector<QzbMember> hm((const QzbMember *)s.h_members.p, (const QzbMember *)s.h_members.p + (j - i));
+                const std::vector<ParsedMember> saved(units.begin() + (long)i, units.begin() + (long)j);
+                for (size_t k = 0; k < saved.size(); k++) {
+                    const ParsedMember &u = saved[k];
+                    const uint8_t *from = (const uint8_t *)s.d_out.p + hm[k].dst_off;
+                    QzbMemberResult r = res[k];
+                    int st = status_rc(r, false);
+                    if (st == RC_BUF_ERROR && (uint64_t)u.m.dst_cap < c->dst_cap - cur_out && c->fmt == QZB_FMT_4B) {
+                        /* a block larger than hw_buff_sz (the reference hands these to zlib): retry it alone with room */
+                        const uint64_t capl = std::min<uint64_t>(std::min<uint64_t>(c->dst_cap - cur_out, (uint64_t)u.m.src_len * 1032 + 64), 0xfffffff0ull);
+                        const uint8_t *staged = nullptr;
+                        if (run_single(u, u.m.src_len, (uint32_t)capl, &r, &staged) != RC_OK) return RC_FAIL;
+                        units = saved;                      /* run_single reused the vector */
+                        from = staged; st = status_rc(r, false);
+                        if (st == RC_OK) {
+                            if (deliver(from, r.produced) != RC_OK) return RC_FAIL;
+                            cur_out += r.produced; cur_in = u.unit_start + u.hdr_len + u.m.src_len + u.ftr_len; o->nmembers++;
+                            /* staging of the batch is gone: re-parse what follows */
+                            rc2 = RC_OK; i = units.size(); j = i; goto reparse;
+                        }
+                    }
+                    if (st == RC_OK && r.produced > c->dst_cap - cur_out) st = RC_BUF_ERROR;
+                    if (st != RC_OK) { rc2 = st; break; }
+                    if (deliver(from, r.produced) != RC_OK) return RC_FAIL;
+                    cur_out += r.produced;
+                    cur_in = u.unit_start + u.hdr_len + ((u.m.exact_len & 1) ? u.m.src_len : r.consumed) + u.ftr_len;
+                    o->nmembers++;
+                }
+                i = j;
+            }
+            if (rc2 != RC_OK) { final_rc = rc2; break; }
+        }
+        if (c->stop_at_first) break;
+        if (parse_rc != RC_OK) { final_rc = parse_rc; break; }
+reparse:;
     }
-    o->consumed = done_in; o->produced = done_out;
-    o->end_of_stream = (rc2 == RC_OK && o->nmembers > 0) ? 1 : 0;
-    if (rc2 != RC_OK) return rc2;
-    return rc;
+    o->consumed = cur_in; o->produced = cur_out;
+    o->end_of_stream = (o->nmembers > 0) ? 1 : 0;
+    return final_rc;
 }

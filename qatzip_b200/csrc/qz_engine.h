@@ -39,7 +39,9 @@ typedef struct QzbCompressOut {
     uint64_t consumed, produced;
     uint32_t crc;
     uint32_t nchunks;
-    double kernel_ms;               /* device time of the codec kernels (CUDA events), all batches */
+    double kernel_ms;               /* device time of codec + framing kernels (CUDA events), all batches */
+    double codec_ms;                /* device time of the piece kernel alone (deflate / lz4) */
+    uint64_t codec_launches;        /* how many times the piece kernel was launched */
     uint64_t kernel_launches;
 } QzbCompressOut;
 /* returns a qatzip.h return code (QZ_OK, QZ_BUF_ERROR with partial progress, QZ_FAIL) */
@@ -71,6 +73,11 @@ int qzb_pinned_contains(const void *p, size_t len);
 /* tuning knobs (environment: QZB200_PIECE_LOG2, QZB200_HASH_BITS, QZB200_BATCH_MB, QZB200_WARPS) */
 typedef struct QzbTuning { int piece_log2, hash_bits, warps_per_cta; size_t batch_bytes; } QzbTuning;
 void qzb_get_tuning(QzbTuning *t);
+
+/* raw device memory helpers for callers that keep data in HBM (bench, tests) */
+void *qzb_device_alloc(int device, size_t n);
+void qzb_device_free(int device, void *p);
+int qzb_device_copy(int device, void *dst, const void *src, size_t n, int to_device);
 
 #ifdef __cplusplus
 }
