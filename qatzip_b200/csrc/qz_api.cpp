@@ -608,8 +608,8 @@ extern "C" int qzDecompressStream(QzSession_T *sess, QzStream_T *strm, unsigned 
             produced += stream_copy_out(strm, b, strm->out + produced);
             if (strm->pending_out) break;
             if (input_done && strm->pending_in == 0) break;
-            if (input_done && !full) { if (last) { rc = QZ_DATA_ERROR; } break; }
-            continue;
+            if (input_done && !last && strm->pending_in < b->in_cap) break;     /* wait for more input */
+            continue;                                                            /* more whole members may be staged */
         }
         if (in_len == 0 && (rc == QZ_BUF_ERROR || rc == QZ_DATA_ERROR || rc == QZ_PARAMS)) {
             /* no progress: the staged bytes do not hold one whole member, or its output does not
