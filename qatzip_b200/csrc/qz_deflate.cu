@@ -24,7 +24,7 @@
 
 #define FULL 0xffffffffu
 #define QZ_NONE16 0xffffu
-#define QZ_LANE_CAP 36          /* in-lane match extension cap; longer matches are finished by the warp */
+#define QZ_LANE_CAP 12          /* in-lane match extension cap; longer matches are finished by the warp */
 #define QZ_MAX_MATCH 258
 #define QZ_STAGE_WORDS 64
 
@@ -76,6 +76,43 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+
+/* sorted keys -> code lengths per symbol: split and scatter run across the warp, only the
+ * in-place tree pass and the (rare) length cap run on lane 0 */
+__device__ __forceinline__ void warp_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n, int maxbits, uint8_t *len_by_sym, uint32_t lane)
+{
+    for (int i = lane; i < n; i += 32) { uint32_t k = keys[i]; ids[i] = (uint16_t)(k & 511u); keys[i] = k >> 9; }
+    __syncwarp();
+    if (lane == 0) { qz_huff_inplace_lengths(keys, n); qz_huff_limit_sorted(keys, n, maxbits); }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) len_by_sym[ids[i]] = (uint8_t)keys[i];
+    __syncwarp();
+}
+
+/* canonical codes for len[0..n) -> out[s] = bit-reversed code | len << 16, in symbol order.
+ * Symbols are taken 32 at a time; lanes holding equal lengths find each other with match.any
+ * and take consecutive codes.  scratch = 32 words. */
+__device__ __forceinline__ void warp_assign_codes(const uint8_t *len, int n, uint32_t *out, uint32_t *scratch, uint32_t lane)
+{
+    uint32_t *cnt = scratch, *next = scratch + 16;
+    if (lane < 16) cnt[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) { uint32_t l = len[s]; if (l) atomicAdd(&cnt[l], 1u); }
+    __syncwarp();
+    if (lane == 0) { uint32_t code = 0; for (int l = 1; l < 16; l++) { next[l] = code; code = (code + cnt[l]) << 1; } next[0] = 0; }
+    __syncwarp();
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + (int)lane;
+        const uint32_t l = s < n ? len[s] : 0u;
+        const uint32_t same = __match_any_sync(FULL, l);
+        const uint32_t rank = __popc(same & lanemask_lt());
+        const uint32_t base = next[l];
+        __syncwarp();
+        if (l && rank == 0) next[l] = base + __popc(same);
+        if (s < n) out[s] = l ? ((__brev(base + rank) >> (32 - l)) | (l << 16)) : 0u;
+        __syncwarp();
+    }
 }
 
 /* scratch carved out of the (dead after phase 2) hash-table region */
@@ -268,8 +305,7 @@ __global__ void __launch_bounds__(512) qzb_deflate_pieces_kernel(QzbCompressJob 
             }
             __syncwarp();
             warp_sort_keys(cs.keys, nk, lane);
-            if (lane == 0) qz_huff_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len);
-            __syncwarp();
+            warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len, lane);
             /* distance alphabet */
             {
                 uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
@@ -278,8 +314,7 @@ __global__ void __launch_bounds__(512) qzb_deflate_pieces_kernel(QzbCompressJob 
                 nk = __popc(bal);
                 __syncwarp();
                 warp_sort_keys(cs.keys, nk, lane);
-                if (lane == 0) qz_huff_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len);
-                __syncwarp();
+                warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len, lane);
             }
             /* cost of each block type */
             uint32_t dynb = 0, fixb = 0;
@@ -305,13 +340,14 @@ __global__ void __launch_bounds__(512) qzb_deflate_pieces_kernel(QzbCompressJob 
             /* code tables go where the histograms were: code | len << 16 */
             QzBitWriter bw;
             uint32_t bitpos = 0, flushed = 0;
+            if (btype == 1) {
+                for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
+                cs.d_len[lane] = 5;
+                __syncwarp();
+            }
+            warp_assign_codes(cs.ll_len, 288, ws.hist, cs.keys, lane);
+            warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF, cs.keys, lane);
             if (lane == 0) {
-                if (btype == 1) {
-                    for (int s = 0; s < 288; s++) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
-                    for (int s = 0; s < 32; s++) cs.d_len[s] = 5;
-                }
-                qz_huff_codes(cs.ll_len, 288, ws.hist);
-                qz_huff_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF);
                 qz_bw_init(&bw, slotw);
                 if (btype == 2) qz_dyn_header_write(&bw, &cs.hdr, bfinal);
                 else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);

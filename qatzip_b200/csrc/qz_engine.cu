@@ -275,12 +275,26 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     return RC_OK;
 }
 
+/* running CRC over `fit` consecutive chunks: crc(A||B) = crc(A)*x^(8|B|) + crc(B) with the
+ * multiplier of a full chunk computed once per call (reference does one zlib crc32_combine per
+ * chunk, src/qatzip.c:1707-1714, including its "0 restarts" rule) */
+static uint32_t fold_chunk_crcs(uint32_t crc, const uint32_t *ck, uint32_t fit, uint32_t chunk_sz, uint64_t batch_len, uint32_t xchunk)
+{
+    for (uint32_t i = 0; i < fit; i++) {
+        const uint64_t clen = std::min<uint64_t>(chunk_sz, batch_len - (uint64_t)i * chunk_sz);
+        if (crc == 0) crc = ck[i];
+        else crc = (clen == chunk_sz ? qz_gf2_mul(crc, xchunk) : qz_gf2_mul(crc, qz_crc_xpow8(clen))) ^ ck[i];
+    }
+    return crc;
+}
+
 extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCompressOut *o)
 {
     memset(o, 0, sizeof *o);
     if (!e || !c || c->chunk_sz < 1024 || (c->chunk_sz & (c->chunk_sz - 1))) return RC_PARAMS;
     CK(cudaSetDevice(e->device));
     uint32_t crc = c->crc_in;
+    const uint32_t xchunk = c->want_crc ? qz_crc_xpow8(c->chunk_sz) : 0;
     const uint64_t per_chunk_out = (uint64_t)c->chunk_sz + (c->chunk_sz >> 7) + 256;   /* worst case incl. framing */
 
     if (c->src_device && c->dst_device) {
@@ -299,10 +313,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
             const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
             uint32_t fit = 0;
             while (fit < s.nchunks && off[fit + 1] <= c->dst_cap - out) fit++;
-            for (uint32_t i = 0; i < fit; i++) {
-                const uint64_t clen = std::min<uint64_t>(c->chunk_sz, len - (uint64_t)i * c->chunk_sz);
-                if (c->fmt != QZB_FMT_LZ4) crc = (crc == 0) ? ck[i] : qz_crc32_combine(crc, ck[i], clen);
-            }
+            if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(crc, ck, fit, c->chunk_sz, len, xchunk);
             o->nchunks += fit;
             out += off[fit];
             if (fit < s.nchunks) { in += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; break; }
@@ -337,10 +348,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
                 CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, bytes, cudaMemcpyDeviceToHost, s.st));
             }
         }
-        for (uint32_t i = 0; i < fit; i++) {
-            const uint64_t clen = std::min<uint64_t>(c->chunk_sz, s.in_len - (uint64_t)i * c->chunk_sz);
-            if (c->fmt != QZB_FMT_LZ4) crc = (crc == 0) ? ck[i] : qz_crc32_combine(crc, ck[i], clen);
-        }
+        if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
         CK(cudaStreamSynchronize(s.st));
         if (bytes && !c->dst_pinned) memcpy(c->dst + out, s.h_out.p, bytes);
         out += bytes; o->nchunks += fit;

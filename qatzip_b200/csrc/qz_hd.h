@@ -7,10 +7,10 @@
 #include <stddef.h>
 #if defined(__CUDACC__)
 #define QZ_HD __host__ __device__ __forceinline__
-#define QZ_HDN __host__ __device__
+#define QZ_HD_SERIAL static __host__ __device__ __noinline__   /* long single-lane routines: one copy, out of the hot I-cache path */
 #else
 #define QZ_HD static inline
-#define QZ_HDN
+#define QZ_HD_SERIAL static
 #endif
 
 /* wire/data formats handled by the kernels (superset of QzDataFormat_T: LZ4 is a session type) */

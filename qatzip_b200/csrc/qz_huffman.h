@@ -52,7 +52,7 @@ QZ_HD void qz_huff_force_two(uint32_t *freq, int n)
 /* In-place minimum-redundancy code lengths (Moffat & Katajainen, 1995) over frequencies sorted
  * ascending in A[0..n), n >= 2.  On return A[i] is the code length of the i-th sorted symbol
  * (non-increasing in i). */
-QZ_HD void qz_huff_inplace_lengths(uint32_t *A, int n)
+QZ_HD_SERIAL void qz_huff_inplace_lengths(uint32_t *A, int n)
 {
     int root, leaf, next;
     A[0] += A[1]; root = 0; leaf = 2;
@@ -73,35 +73,42 @@ QZ_HD void qz_huff_inplace_lengths(uint32_t *A, int n)
     }
 }
 
+/* Cap the (sorted, non-increasing) code lengths in len[0..n) at maxbits, keeping the Kraft sum
+ * exact: fold over-long codes to maxbits, then repeatedly turn the deepest leaf above the cap
+ * into an internal node that adopts one folded leaf; finally hand lengths back out longest
+ * first (= least frequent first). */
+QZ_HD_SERIAL void qz_huff_limit_sorted(uint32_t *len, int n, int maxbits)
+{
+    if ((int)len[0] <= maxbits) return;
+    uint32_t cnt[16];
+    for (int l = 0; l < 16; l++) cnt[l] = 0;
+    for (int i = 0; i < n; i++) cnt[(int)len[i] > maxbits ? maxbits : (int)len[i]]++;
+    uint32_t kraft = 0;
+    for (int l = 1; l <= maxbits; l++) kraft += cnt[l] << (maxbits - l);
+    while (kraft > (1u << maxbits)) {
+        int b = maxbits - 1;
+        while (cnt[b] == 0) b--;
+        cnt[b]--; cnt[b + 1] += 2; cnt[maxbits]--;
+        kraft--;
+    }
+    int i = 0;
+    for (int l = maxbits; l >= 1; l--) for (uint32_t c = cnt[l]; c; c--) len[i++] = (uint32_t)l;
+}
+
 /* Sorted keys (QZ_HUFF_KEY(freq, sym), ascending, all freq > 0, n_used >= 2) -> per-symbol code
  * lengths capped at maxbits.  keys[] is clobbered, ids[] is scratch for n_used entries.
- * len_by_sym[] must be zero for symbols that do not occur. */
-QZ_HD void qz_huff_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n_used, int maxbits, uint8_t *len_by_sym)
+ * len_by_sym[] must be zero for symbols that do not occur.  (The kernel runs the first and the
+ * last loop across the warp and only the two calls in between on one lane.) */
+QZ_HD_SERIAL void qz_huff_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n_used, int maxbits, uint8_t *len_by_sym)
 {
     for (int i = 0; i < n_used; i++) { ids[i] = (uint16_t)(keys[i] & 511u); keys[i] >>= 9; }
     qz_huff_inplace_lengths(keys, n_used);
-    if ((int)keys[0] > maxbits) {
-        /* Fold over-long codes to maxbits, then restore the Kraft equality by repeatedly turning
-         * the deepest leaf above the cap into an internal node that adopts one folded leaf. */
-        uint32_t cnt[16];
-        for (int l = 0; l < 16; l++) cnt[l] = 0;
-        for (int i = 0; i < n_used; i++) cnt[(int)keys[i] > maxbits ? maxbits : (int)keys[i]]++;
-        uint32_t kraft = 0;
-        for (int l = 1; l <= maxbits; l++) kraft += cnt[l] << (maxbits - l);
-        while (kraft > (1u << maxbits)) {
-            int b = maxbits - 1;
-            while (cnt[b] == 0) b--;
-            cnt[b]--; cnt[b + 1] += 2; cnt[maxbits]--;
-            kraft--;
-        }
-        int i = 0;
-        for (int l = maxbits; l >= 1; l--) for (uint32_t c = cnt[l]; c; c--) keys[i++] = (uint32_t)l;
-    }
+    qz_huff_limit_sorted(keys, n_used, maxbits);
     for (int i = 0; i < n_used; i++) len_by_sym[ids[i]] = (uint8_t)keys[i];
 }
 
 /* Canonical codes, already bit-reversed for LSB-first emission: out[s] = code | len << 16. */
-QZ_HD void qz_huff_codes(const uint8_t *len, int n, uint32_t *out)
+QZ_HD_SERIAL void qz_huff_codes(const uint8_t *len, int n, uint32_t *out)
 {
     uint32_t cnt[16], next[17];
     for (int l = 0; l < 16; l++) cnt[l] = 0;
@@ -117,6 +124,7 @@ QZ_HD void qz_huff_codes(const uint8_t *len, int n, uint32_t *out)
 /* ---- dynamic block header (RFC 1951 3.2.7) ---- */
 struct QzDynHeader {
     uint16_t items[QZ_NUM_LL + QZ_NUM_D];   /* sym | extra_value << 5 | extra_bits_count << 12 */
+    uint8_t seq[QZ_NUM_LL + QZ_NUM_D + 4];  /* scratch: the code lengths being run-length coded */
     uint32_t nitems;
     uint32_t hlit, hdist, hclen;
     uint8_t cl_len[QZ_NUM_CL];
@@ -126,17 +134,22 @@ struct QzDynHeader {
 QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return (uint16_t)(sym | (eval << 5) | (ebits << 12)); }
 
 /* Run-length code the two length arrays into code-length symbols and size the header. */
-QZ_HD void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len, QzDynHeader *h)
+QZ_HD_SERIAL void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len, QzDynHeader *h)
 {
     uint32_t hlit = QZ_NUM_LL, hdist = QZ_NUM_D;
     while (hlit > 257 && ll_len[hlit - 1] == 0) hlit--;
     while (hdist > 1 && d_len[hdist - 1] == 0) hdist--;
     h->hlit = hlit; h->hdist = hdist;
+    /* the two length arrays back to back, so the run-length scan below walks one plain array */
+    uint8_t *seq = h->seq;
+    for (uint32_t k = 0; k < hlit; k++) seq[k] = ll_len[k];
+    for (uint32_t k = 0; k < hdist; k++) seq[hlit + k] = d_len[k];
     uint32_t total = hlit + hdist, i = 0, n = 0, cf[QZ_NUM_CL];
     for (int k = 0; k < QZ_NUM_CL; k++) cf[k] = 0;
     while (i < total) {
-        uint32_t v = i < hlit ? ll_len[i] : d_len[i - hlit], j = i + 1;
-        while (j < total && (j < hlit ? ll_len[j] : d_len[j - hlit]) == v) j++;
+        const uint32_t v = seq[i];
+        uint32_t j = i + 1;
+        while (j < total && seq[j] == v) j++;
         uint32_t run = j - i;
         if (v == 0) {
             while (run >= 11) { uint32_t r = run > 138 ? 138 : run; h->items[n++] = qz_cl_item(18, r - 11, 7); cf[18]++; run -= r; }
@@ -171,7 +184,7 @@ QZ_HD void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len, QzDyn
     h->bits = bits;
 }
 
-QZ_HD void qz_dyn_header_write(QzBitWriter *bw, const QzDynHeader *h, int bfinal)
+QZ_HD_SERIAL void qz_dyn_header_write(QzBitWriter *bw, const QzDynHeader *h, int bfinal)
 {
     const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
     uint32_t cl_code[QZ_NUM_CL];
