@@ -124,304 +124,371 @@ struct CodeScratch {
     QzDynHeader hdr;
 };
 
-template <int PIECE_LOG2, int HB>
-struct WarpSmem {
-    static constexpr int PIECE = 1 << PIECE_LOG2;
-    uint8_t piece[PIECE + 32];              /* +32: zero pad so unaligned reads past n are defined */
+/* Shared-memory plan.  Two warps form a PAIR that shares one piece buffer: while one warp of
+ * the pair runs phases 1-2 (the only phases that read the piece), its partner runs phases 3-4
+ * of the piece it matched in the previous interval; a named barrier swaps the roles.  The
+ * buffer is the scarce resource (8 KiB of a 227 KiB budget), so halving it per warp lifts
+ * residency from 16 to 24 warps per SM. */
+template <int HB>
+struct WarpPriv {
     union {
         uint16_t table[1 << HB];
         CodeScratch cs;
     } u;
     uint32_t hist[QZ_NUM_LL + 2 + QZ_NUM_D + 2]; /* [0,286) lit/len, [288,318) dist; later the code tables */
 };
+template <int PIECE_LOG2, int HB>
+struct PairSmem {
+    static constexpr int PIECE = 1 << PIECE_LOG2;
+    uint8_t piece[PIECE + 32];              /* +32: zero pad so unaligned reads past n are defined */
+    WarpPriv<HB> w[2];
+    uint32_t got[2];                        /* did warp i obtain a piece on its last turn */
+    uint32_t pad[2];
+};
 #define QZ_DOFF 288
 
+/* what phases 3-4 need to know about the piece phases 1-2 just finished */
+struct PieceState {
+    uint32_t g, n, ntok, extra_total;
+    bool bfinal;
+    const uint8_t *src;
+};
+
 template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(512) qzb_deflate_pieces_kernel(QzbCompressJob job)
+__device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, WarpPriv<HB> &ws, uint32_t *toks,
+                                        const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    typedef WarpSmem<PIECE_LOG2, HB> WS;
+    constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
+    /* ---- which bytes ---- */
+    const uint32_t chunk = g / job.pieces_per_chunk, k = g - chunk * job.pieces_per_chunk;
+    const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
+    const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
+    const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+    const uint32_t p_off = k << PIECE_LOG2;
+    const uint32_t n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u;
+    const bool last_piece = (p_off + n == chunk_len);
+    ps.g = g; ps.n = n;
+    ps.bfinal = last_piece && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
+    const uint8_t *src = job.src + chunk_off + p_off;
+    ps.src = src;
+
+    /* ---- phase 1: load + CRC ---- */
+    {
+        uint4 *d4 = reinterpret_cast<uint4 *>(piece);
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            uint32_t nv = n >> 4;
+            for (uint32_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+            for (uint32_t i = (nv << 4) + lane; i < n; i += 32) piece[i] = src[i];
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) piece[i] = src[i];
+        }
+        piece[n + lane] = 0;          /* zero pad */
+        for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
+        for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
+        __syncwarp();
+        /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
+        int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
+        if (lo < 0) lo = 0;
+        uint32_t c = 0xffffffffu;
+        for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ piece[i]) & 0xff] ^ (c >> 8);
+        c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
+#pragma unroll
+        for (int lv = 0; lv < 5; lv++) {
+            uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
+            if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
+        }
+        if (lane == 0) job.piece_crc[g] = c;
+    }
+
+    /* ---- phase 2: match + select + tokens ---- */
+    uint32_t ntok = 0, extra_acc = 0;
+    {
+        uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t p = base + lane;
+            const uint32_t v = ld32u(piece, p);
+            const bool can = p + 4 <= n;
+            const uint32_t h = (v * 2654435761u) >> (32 - HB);
+            uint32_t cand = can ? ws.u.table[h] : QZ_NONE16;
+            __syncwarp();
+            if (can) ws.u.table[h] = (uint16_t)p;
+            __syncwarp();
+            uint32_t L = 0;
+            const uint32_t maxl = min((uint32_t)QZ_MAX_MATCH, n - min(p, n));
+            if (cand != QZ_NONE16 && ld32u(piece, cand) == v) {
+                uint32_t l = 4;
+                while (l < QZ_LANE_CAP) {
+                    uint32_t x = ld32u(piece, p + l) ^ ld32u(piece, cand + l);
+                    if (x) { l += (__ffs(x) - 1) >> 3; break; }
+                    l += 4;
+                }
+                L = min(l, maxl);
+            }
+            const uint32_t valid = __ballot_sync(FULL, p < n);
+            const uint32_t M = __ballot_sync(FULL, L >= 4);
+            uint32_t tokmask = 0, matchmask = 0, cur = entry;
+            if (cur >= 32) { entry = cur - 32; continue; }
+            for (;;) {
+                uint32_t rest = M & (FULL << cur);
+                if (!rest) { tokmask |= (FULL << cur); cur = 32; break; }
+                uint32_t m = __ffs(rest) - 1;
+                tokmask |= (FULL << cur) & ~(FULL << m);      /* literals cur..m-1 */
+                tokmask |= 1u << m; matchmask |= 1u << m;
+                uint32_t Lm = __shfl_sync(FULL, L, m);
+                if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
+                    const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
+                    const uint32_t mx = min((uint32_t)QZ_MAX_MATCH, n - pm);
+                    Lm = QZ_LANE_CAP;
+                    while (Lm < mx) {
+                        uint32_t kk = Lm + lane;
+                        bool eq = kk < mx && piece[pm + kk] == piece[cm + kk];
+                        uint32_t bal = __ballot_sync(FULL, eq);
+                        if (bal == FULL) { Lm += 32; continue; }
+                        Lm += __ffs(~bal) - 1; break;
+                    }
+                    Lm = min(Lm, mx);
+                    if (lane == m) L = Lm;
+                }
+                cur = m + Lm;
+                if (cur >= 32) break;
+            }
+            entry = cur - 32;
+            tokmask &= valid;
+            const bool is_tok = (tokmask >> lane) & 1, is_match = (matchmask >> lane) & 1;
+            if (is_tok) {
+                uint32_t t;
+                if (is_match) {
+                    const uint32_t dist = p - cand;
+                    uint32_t ls, le, lv, ds, de, dv;
+                    qz_len_code(L, &ls, &le, &lv);
+                    qz_dist_code(dist, &ds, &de, &dv);
+                    atomicAdd(&ws.hist[ls], 1u);
+                    atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
+                    extra_acc += le + de;
+                    t = 0x80000000u | ((L - 3) << 16) | (dist - 1);
+                } else {
+                    t = v & 0xff;
+                    atomicAdd(&ws.hist[t], 1u);
+                }
+                toks[ntok + __popc(tokmask & lanemask_lt())] = t;
+            }
+            ntok += __popc(tokmask);
+        }
+    }
+    __syncwarp();
+    ps.ntok = ntok;
+    ps.extra_total = warp_sum(extra_acc);
+}
+
+template <int HB>
+__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, const uint32_t *toks, uint32_t lane, const PieceState &ps)
+{
+    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok, extra_total = ps.extra_total;
+    const bool bfinal = ps.bfinal;
+    uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
+    uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
+
+    /* ---- phase 3: code construction ---- */
+    CodeScratch &cs = ws.u.cs;
+    uint32_t out_bytes = 0;
+    int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
+    {
+        if (lane == 0) {
+            ws.hist[256] = 1;
+            qz_huff_force_two(ws.hist, QZ_NUM_LL);
+            qz_huff_force_two(ws.hist + QZ_DOFF, QZ_NUM_D);
+        }
+        for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
+        cs.d_len[lane] = 0;
+        __syncwarp();
+        /* literal/length alphabet */
+        int nk = 0;
+        for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
+            uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.hist[s] : 0;
+            uint32_t bal = __ballot_sync(FULL, f != 0);
+            if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
+            nk += __popc(bal);
+        }
+        __syncwarp();
+        warp_sort_keys(cs.keys, nk, lane);
+        warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len, lane);
+        /* distance alphabet */
+        {
+            uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
+            uint32_t bal = __ballot_sync(FULL, f != 0);
+            if (f) cs.keys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
+            nk = __popc(bal);
+            __syncwarp();
+            warp_sort_keys(cs.keys, nk, lane);
+            warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len, lane);
+        }
+        /* cost of each block type */
+        uint32_t dynb = 0, fixb = 0;
+        for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
+        if (lane < QZ_NUM_D) { uint32_t f = ws.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
+        dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
+        /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
+        if (lane == 0) qz_dyn_header_plan(cs.ll_len, cs.d_len, &cs.hdr);
+        __syncwarp();
+        dynb += cs.hdr.bits;
+        const uint32_t storedb = (5 + n) * 8;
+        if (job.static_huffman) dynb = 0xffffffffu;
+        btype = (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
+        if (n == 0) btype = 1;
+    }
+
+    if (btype == 0) {
+        /* stored block: the piece starts byte-aligned, so the 3 header bits + pad are one byte.
+         * The bytes come from global memory again (the shared piece buffer already belongs to the
+         * partner warp); incompressible pieces are the only ones that pay this second read. */
+        if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
+        for (uint32_t i = lane; i < n; i += 32) slot[5 + i] = ps.src[i];
+        out_bytes = 5 + n;
+    } else {
+        /* code tables go where the histograms were: code | len << 16 */
+        QzBitWriter bw;
+        uint32_t bitpos = 0, flushed = 0;
+        if (btype == 1) {
+            for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
+            cs.d_len[lane] = 5;
+            __syncwarp();
+        }
+        warp_assign_codes(cs.ll_len, 288, ws.hist, cs.keys, lane);
+        warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF, cs.keys, lane);
+        if (lane == 0) {
+            qz_bw_init(&bw, slotw);
+            if (btype == 2) qz_dyn_header_write(&bw, &cs.hdr, bfinal);
+            else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
+            bitpos = qz_bw_bitpos(&bw); flushed = bw.wpos;
+        }
+        bitpos = __shfl_sync(FULL, bitpos, 0); flushed = __shfl_sync(FULL, flushed, 0);
+        uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
+        uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
+        for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+        __syncwarp();
+        if (lane == 0) st[0] = pend;
+        __syncwarp();
+
+        /* ---- phase 4: emit ---- */
+        for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
+            uint64_t bits = 0; uint32_t nb = 0;
+            if (t0 + lane < ntok) {
+                const uint32_t t = __ldcg(toks + t0 + lane);
+                if (t & 0x80000000u) {
+                    uint32_t ls, le, lv, ds, de, dv;
+                    qz_len_code(((t >> 16) & 0xff) + 3, &ls, &le, &lv);
+                    qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
+                    const uint32_t lc = ws.hist[ls], dc = ws.hist[QZ_DOFF + ds];
+                    bits = lc & 0xffff; nb = lc >> 16;
+                    bits |= (uint64_t)lv << nb; nb += le;
+                    bits |= (uint64_t)(dc & 0xffff) << nb; nb += dc >> 16;
+                    bits |= (uint64_t)dv << nb; nb += de;
+                } else {
+                    const uint32_t c = ws.hist[t];
+                    bits = c & 0xffff; nb = c >> 16;
+                }
+            }
+            uint32_t incl = nb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            if (nb) {
+                const uint32_t pos = bitpos + incl - nb - (flushed << 5);
+                const uint32_t w = pos >> 5, sh = pos & 31;
+                const uint64_t lo = bits << sh;
+                const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
+                if ((uint32_t)lo) atomicOr(&st[w], (uint32_t)lo);
+                if ((uint32_t)(lo >> 32)) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
+                if (hi) atomicOr(&st[w + 2], hi);
+            }
+            __syncwarp();
+            bitpos += total;
+            const uint32_t nfull = (bitpos >> 5) - flushed;
+            for (uint32_t i = lane; i < nfull; i += 32) slotw[flushed + i] = st[i];
+            const uint32_t carry = st[nfull];
+            __syncwarp();
+            for (uint32_t i = lane; i <= nfull + 2 && i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+            __syncwarp();
+            if (lane == 0) st[0] = carry;
+            __syncwarp();
+            flushed += nfull;
+        }
+        /* end-of-block, then byte alignment: final blocks pad, others append an empty stored block */
+        if (lane == 0) {
+            bw.words = slotw; bw.wpos = flushed; bw.acc = st[0]; bw.nacc = bitpos & 31;
+            const uint32_t eob = ws.hist[256];
+            qz_bw_put(&bw, eob & 0xffff, eob >> 16);
+            if (!bfinal) {
+                qz_bw_put(&bw, 0, 3);
+                qz_bw_align_byte(&bw);
+                qz_bw_put(&bw, 0x0000u, 16);
+                qz_bw_put(&bw, 0xffffu, 16);
+            }
+            out_bytes = qz_bw_finish(&bw);
+        }
+        out_bytes = __shfl_sync(FULL, out_bytes, 0);
+    }
+    if (lane == 0) job.piece_len[g] = out_bytes;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void pair_barrier(uint32_t pair)
+{
+    asm volatile("bar.sync %0, 64;" :: "r"(pair + 1) : "memory");
+}
+
+template <int PIECE_LOG2, int HB>
+__global__ void __launch_bounds__(960) qzb_deflate_pieces_kernel(QzbCompressJob job)
+{
+    constexpr int PIECE = 1 << PIECE_LOG2;
+    typedef PairSmem<PIECE_LOG2, HB> PS;
     static_assert(sizeof(CodeScratch) <= (sizeof(uint16_t) << HB), "code scratch must fit in the hash table");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
-    constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
+    constexpr uint32_t STRIP = PIECE / 32 + 4;
 
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, pair = warp >> 1, side = warp & 1;
+    PS &ps = reinterpret_cast<PS *>(smem_raw)[pair];
+    WarpPriv<HB> &ws = ps.w[side];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
+    if (lane < 2) ps.got[lane] = 1;
     __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     uint32_t *toks = job.tok_scratch + (size_t)gwarp * PIECE;
 
-    for (;;) {
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(job.ticket, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= job.npieces) break;
-
-        /* ---- which bytes ---- */
-        const uint32_t chunk = g / job.pieces_per_chunk, k = g - chunk * job.pieces_per_chunk;
-        const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
-        const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
-        const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
-        const uint32_t p_off = k << PIECE_LOG2;
-        const uint32_t n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u;
-        const bool last_piece = (p_off + n == chunk_len);
-        const bool bfinal = last_piece && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
-        const uint8_t *src = job.src + chunk_off + p_off;
-        uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
-        uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
-
-        /* ---- phase 1: load + CRC ---- */
-        {
-            uint4 *d4 = reinterpret_cast<uint4 *>(ws.piece);
-            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-                uint32_t nv = n >> 4;
-                for (uint32_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
-                for (uint32_t i = (nv << 4) + lane; i < n; i += 32) ws.piece[i] = src[i];
-            } else {
-                for (uint32_t i = lane; i < n; i += 32) ws.piece[i] = src[i];
-            }
-            if (lane < 32) ws.piece[n + lane] = 0;          /* zero pad */
-            for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
-            for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
-            __syncwarp();
-            /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
-            int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
-            if (lo < 0) lo = 0;
-            uint32_t c = 0xffffffffu;
-            for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ ws.piece[i]) & 0xff] ^ (c >> 8);
-            c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
-#pragma unroll
-            for (int lv = 0; lv < 5; lv++) {
-                uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
-                if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
-            }
-            if (lane == 0) job.piece_crc[g] = c;
-        }
-
-        /* ---- phase 2: match + select + tokens ---- */
-        uint32_t ntok = 0, extra_acc = 0;
-        {
-            uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t p = base + lane;
-                const uint32_t v = ld32u(ws.piece, p);
-                const bool can = p + 4 <= n;
-                const uint32_t h = (v * 2654435761u) >> (32 - HB);
-                uint32_t cand = can ? ws.u.table[h] : QZ_NONE16;
-                __syncwarp();
-                if (can) ws.u.table[h] = (uint16_t)p;
-                __syncwarp();
-                uint32_t L = 0;
-                const uint32_t maxl = min((uint32_t)QZ_MAX_MATCH, n - min(p, n));
-                if (cand != QZ_NONE16 && ld32u(ws.piece, cand) == v) {
-                    uint32_t l = 4;
-                    while (l < QZ_LANE_CAP) {
-                        uint32_t x = ld32u(ws.piece, p + l) ^ ld32u(ws.piece, cand + l);
-                        if (x) { l += (__ffs(x) - 1) >> 3; break; }
-                        l += 4;
-                    }
-                    L = min(l, maxl);
-                }
-                const uint32_t valid = __ballot_sync(FULL, p < n);
-                const uint32_t M = __ballot_sync(FULL, L >= 4);
-                uint32_t tokmask = 0, matchmask = 0, cur = entry;
-                if (cur >= 32) { entry = cur - 32; continue; }
-                for (;;) {
-                    uint32_t rest = M & (FULL << cur);
-                    if (!rest) { tokmask |= (FULL << cur); cur = 32; break; }
-                    uint32_t m = __ffs(rest) - 1;
-                    tokmask |= (FULL << cur) & ~(FULL << m);      /* literals cur..m-1 */
-                    tokmask |= 1u << m; matchmask |= 1u << m;
-                    uint32_t Lm = __shfl_sync(FULL, L, m);
-                    if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
-                        const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
-                        const uint32_t mx = min((uint32_t)QZ_MAX_MATCH, n - pm);
-                        Lm = QZ_LANE_CAP;
-                        while (Lm < mx) {
-                            uint32_t kk = Lm + lane;
-                            bool eq = kk < mx && ws.piece[pm + kk] == ws.piece[cm + kk];
-                            uint32_t bal = __ballot_sync(FULL, eq);
-                            if (bal == FULL) { Lm += 32; continue; }
-                            Lm += __ffs(~bal) - 1; break;
-                        }
-                        Lm = min(Lm, mx);
-                        if (lane == m) L = Lm;
-                    }
-                    cur = m + Lm;
-                    if (cur >= 32) break;
-                }
-                entry = cur - 32;
-                tokmask &= valid;
-                const bool is_tok = (tokmask >> lane) & 1, is_match = (matchmask >> lane) & 1;
-                if (is_tok) {
-                    uint32_t t;
-                    if (is_match) {
-                        const uint32_t dist = p - cand;
-                        uint32_t ls, le, lv, ds, de, dv;
-                        qz_len_code(L, &ls, &le, &lv);
-                        qz_dist_code(dist, &ds, &de, &dv);
-                        atomicAdd(&ws.hist[ls], 1u);
-                        atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
-                        extra_acc += le + de;
-                        t = 0x80000000u | ((L - 3) << 16) | (dist - 1);
-                    } else {
-                        t = v & 0xff;
-                        atomicAdd(&ws.hist[t], 1u);
-                    }
-                    toks[ntok + __popc(tokmask & lanemask_lt())] = t;
-                }
-                ntok += __popc(tokmask);
-            }
+    /* Interval `iter` belongs to the warp with side == iter & 1: it draws a ticket and runs phases
+     * 1-2 on the shared piece buffer while its partner runs phases 3-4 of the piece it matched in
+     * the previous interval.  Tickets only grow, so once both warps have drawn a blank in their
+     * latest turns the pair is finished.  Each side's latest outcome travels through got[side]:
+     * written before the barrier by the turn holder, read after the barrier by the partner, and
+     * not written again until two barriers later. */
+    PieceState cur, nxt;
+    bool have_cur = false, my_got = true, partner_got = true;
+    for (uint32_t iter = 0;; iter++) {
+        const bool my_turn = ((iter & 1u) == side);
+        bool have_new = false;
+        if (my_turn) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(job.ticket, 1u);
+            g = __shfl_sync(FULL, g, 0);
+            have_new = g < job.npieces;
+            if (have_new) phase12<PIECE_LOG2, HB>(job, ps.piece, ws, toks, s_crc_tab, s_xstrip, g, lane, nxt);
+            if (lane == 0) ps.got[side] = have_new ? 1u : 0u;
+            my_got = have_new;
+        } else if (have_cur) {
+            phase34<HB>(job, ws, toks, lane, cur);
+            have_cur = false;
         }
         __syncwarp();
-        const uint32_t extra_total = warp_sum(extra_acc);
-
-        /* ---- phase 3: code construction ---- */
-        CodeScratch &cs = ws.u.cs;
-        uint32_t out_bytes = 0;
-        int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
-        {
-            if (lane == 0) {
-                ws.hist[256] = 1;
-                qz_huff_force_two(ws.hist, QZ_NUM_LL);
-                qz_huff_force_two(ws.hist + QZ_DOFF, QZ_NUM_D);
-            }
-            for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
-            cs.d_len[lane] = 0;
-            __syncwarp();
-            /* literal/length alphabet */
-            int nk = 0;
-            for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
-                uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.hist[s] : 0;
-                uint32_t bal = __ballot_sync(FULL, f != 0);
-                if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
-                nk += __popc(bal);
-            }
-            __syncwarp();
-            warp_sort_keys(cs.keys, nk, lane);
-            warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len, lane);
-            /* distance alphabet */
-            {
-                uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
-                uint32_t bal = __ballot_sync(FULL, f != 0);
-                if (f) cs.keys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
-                nk = __popc(bal);
-                __syncwarp();
-                warp_sort_keys(cs.keys, nk, lane);
-                warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len, lane);
-            }
-            /* cost of each block type */
-            uint32_t dynb = 0, fixb = 0;
-            for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
-            if (lane < QZ_NUM_D) { uint32_t f = ws.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
-            dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
-            /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
-            if (lane == 0) qz_dyn_header_plan(cs.ll_len, cs.d_len, &cs.hdr);
-            __syncwarp();
-            dynb += cs.hdr.bits;
-            const uint32_t storedb = (5 + n) * 8;
-            if (job.static_huffman) dynb = 0xffffffffu;
-            btype = (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
-            if (n == 0) btype = 1;
-        }
-
-        if (btype == 0) {
-            /* stored block: the piece starts byte-aligned, so the 3 header bits + pad are one byte */
-            if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
-            for (uint32_t i = lane; i < n; i += 32) slot[5 + i] = ws.piece[i];
-            out_bytes = 5 + n;
-        } else {
-            /* code tables go where the histograms were: code | len << 16 */
-            QzBitWriter bw;
-            uint32_t bitpos = 0, flushed = 0;
-            if (btype == 1) {
-                for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
-                cs.d_len[lane] = 5;
-                __syncwarp();
-            }
-            warp_assign_codes(cs.ll_len, 288, ws.hist, cs.keys, lane);
-            warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF, cs.keys, lane);
-            if (lane == 0) {
-                qz_bw_init(&bw, slotw);
-                if (btype == 2) qz_dyn_header_write(&bw, &cs.hdr, bfinal);
-                else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
-                bitpos = qz_bw_bitpos(&bw); flushed = bw.wpos;
-            }
-            bitpos = __shfl_sync(FULL, bitpos, 0); flushed = __shfl_sync(FULL, flushed, 0);
-            uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
-            uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
-            for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
-            __syncwarp();
-            if (lane == 0) st[0] = pend;
-            __syncwarp();
-
-            /* ---- phase 4: emit ---- */
-            for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
-                uint64_t bits = 0; uint32_t nb = 0;
-                if (t0 + lane < ntok) {
-                    const uint32_t t = __ldcg(toks + t0 + lane);
-                    if (t & 0x80000000u) {
-                        uint32_t ls, le, lv, ds, de, dv;
-                        qz_len_code(((t >> 16) & 0xff) + 3, &ls, &le, &lv);
-                        qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
-                        const uint32_t lc = ws.hist[ls], dc = ws.hist[QZ_DOFF + ds];
-                        bits = lc & 0xffff; nb = lc >> 16;
-                        bits |= (uint64_t)lv << nb; nb += le;
-                        bits |= (uint64_t)(dc & 0xffff) << nb; nb += dc >> 16;
-                        bits |= (uint64_t)dv << nb; nb += de;
-                    } else {
-                        const uint32_t c = ws.hist[t];
-                        bits = c & 0xffff; nb = c >> 16;
-                    }
-                }
-                uint32_t incl = nb;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-                const uint32_t total = __shfl_sync(FULL, incl, 31);
-                if (nb) {
-                    const uint32_t pos = bitpos + incl - nb - (flushed << 5);
-                    const uint32_t w = pos >> 5, sh = pos & 31;
-                    const uint64_t lo = bits << sh;
-                    const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
-                    if ((uint32_t)lo) atomicOr(&st[w], (uint32_t)lo);
-                    if ((uint32_t)(lo >> 32)) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
-                    if (hi) atomicOr(&st[w + 2], hi);
-                }
-                __syncwarp();
-                bitpos += total;
-                const uint32_t nfull = (bitpos >> 5) - flushed;
-                for (uint32_t i = lane; i < nfull; i += 32) slotw[flushed + i] = st[i];
-                const uint32_t carry = st[nfull];
-                __syncwarp();
-                for (uint32_t i = lane; i <= nfull + 2 && i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
-                __syncwarp();
-                if (lane == 0) st[0] = carry;
-                __syncwarp();
-                flushed += nfull;
-            }
-            /* end-of-block, then byte alignment: final blocks pad, others append an empty stored block */
-            if (lane == 0) {
-                bw.words = slotw; bw.wpos = flushed; bw.acc = st[0]; bw.nacc = bitpos & 31;
-                const uint32_t eob = ws.hist[256];
-                qz_bw_put(&bw, eob & 0xffff, eob >> 16);
-                if (!bfinal) {
-                    qz_bw_put(&bw, 0, 3);
-                    qz_bw_align_byte(&bw);
-                    qz_bw_put(&bw, 0x0000u, 16);
-                    qz_bw_put(&bw, 0xffffu, 16);
-                }
-                out_bytes = qz_bw_finish(&bw);
-            }
-            out_bytes = __shfl_sync(FULL, out_bytes, 0);
-        }
-        if (lane == 0) job.piece_len[g] = out_bytes;
-        __syncwarp();
+        pair_barrier(pair);
+        if (my_turn) { if (have_new) { cur = nxt; have_cur = true; } }
+        else partner_got = ps.got[side ^ 1u] != 0;
+        if (!my_got && !partner_got) break;
     }
 }
 
@@ -547,18 +614,19 @@ __global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* shared memory for `warps` warps (an even number: warps work in pairs) */
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps)
 {
-    size_t per = (piece_log2 == 13 && hb == 11) ? sizeof(WarpSmem<13, 11>) :
-                 (piece_log2 == 13 && hb == 12) ? sizeof(WarpSmem<13, 12>) :
-                 (piece_log2 == 14 && hb == 12) ? sizeof(WarpSmem<14, 12>) : sizeof(WarpSmem<14, 13>);
-    return per * (size_t)warps;
+    size_t per = (piece_log2 == 13 && hb == 11) ? sizeof(PairSmem<13, 11>) :
+                 (piece_log2 == 13 && hb == 12) ? sizeof(PairSmem<13, 12>) :
+                 (piece_log2 == 14 && hb == 12) ? sizeof(PairSmem<14, 12>) : sizeof(PairSmem<14, 13>);
+    return per * (size_t)((warps + 1) / 2);
 }
 
 template <int P, int H>
 static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps, cudaStream_t st)
 {
-    size_t smem = sizeof(WarpSmem<P, H>) * (size_t)warps;
+    size_t smem = sizeof(PairSmem<P, H>) * (size_t)(warps / 2);
     cudaError_t e = cudaFuncSetAttribute(qzb_deflate_pieces_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     qzb_deflate_pieces_kernel<P, H><<<grid, warps * 32, smem, st>>>(job);

@@ -161,7 +161,8 @@ struct QzbEngine {
     int device = 0;
     int sm_count = 148;
     QzbTuning tune;
-    Slot slot[2];
+    static constexpr int NSLOT = 3;       /* batches in flight: copy-in, compute, copy-out */
+    Slot slot[NSLOT];
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -240,8 +241,12 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     auto smem_for = [&](int w) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w); };
-    if (warps <= 0) { warps = 16; while (warps > 1 && smem_for(warps) + 2048 > smem_cap) warps--; }
-    while (warps > 1 && smem_for(warps) + 2048 > smem_cap) warps--;
+    /* deflate warps work in pairs (15 named barriers -> at most 30 warps per CTA); LZ4 warps are independent */
+    const int wmax = lz4 ? 16 : 30, wstep = lz4 ? 1 : 2;
+    if (warps <= 0 || warps > wmax) warps = wmax;
+    if (!lz4) warps &= ~1;
+    if (warps < wstep) warps = wstep;
+    while (warps > wstep && smem_for(warps) + 2048 > smem_cap) warps -= wstep;
     ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps) + 3072));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
@@ -357,9 +362,14 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         return RC_OK;
     };
 
+    /* Ring of NSLOT slots.  Batch b is issued on slot b % NSLOT as soon as that slot's previous
+     * tenant (batch b - NSLOT) has been drained; after issuing b the oldest undrained batch is
+     * drained, so that while the host waits for it two younger batches are already queued. */
+    constexpr int NS = QzbEngine::NSLOT;
+    uint64_t next_drain = 0;
     for (uint64_t b = 0; b < nb && !stop; b++) {
-        Slot &s = e->slot[b & 1];
-        if (drain(s) != RC_OK) return RC_FAIL;
+        Slot &s = e->slot[b % NS];
+        while (next_drain + NS <= b) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
         if (stop) break;
         const uint64_t in_off = b * batch, len = std::min<uint64_t>(batch, c->src_len - in_off);
         const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
@@ -375,13 +385,11 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         const int last = (in_off + len == c->src_len) ? c->last : 0;
         if (enqueue_compress(e, s, c, (const uint8_t *)s.d_in.p, len, (uint8_t *)s.d_out.p, s.d_out.cap, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
         s.busy = true; s.in_off = in_off; s.in_len = len;
-        /* drain the other slot while this one runs */
-        if (b > 0 && drain(e->slot[(b + 1) & 1]) != RC_OK) return RC_FAIL;
+        if (b + 1 - next_drain >= (uint64_t)NS) {       /* ring full: retire the oldest while NS-1 younger ones are queued */
+            if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++;
+        }
     }
-    /* drain in issue order */
-    const uint64_t issued_last = nb ? (nb - 1) & 1 : 0;
-    if (drain(e->slot[issued_last ^ 1]) != RC_OK) return RC_FAIL;
-    if (drain(e->slot[issued_last]) != RC_OK) return RC_FAIL;
+    for (int k = 0; k < NS; k++, next_drain++) if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL;
     o->consumed = consumed; o->produced = out; o->crc = crc;
     return rc;
 }
@@ -622,6 +630,8 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                 if (good < s.nmembers) { rc2 = status_rc(r[good], true); failed_unit = (long)(s.first_member + good); stop = true; }
                 return RC_OK;
             };
+            constexpr int NS = QzbEngine::NSLOT;
+            size_t next_drain = 0;
             while (i < units.size() && !stop) {
                 size_t j = i; uint64_t sin = 0, sout = 0;
                 while (j < units.size()) {
@@ -629,14 +639,14 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     if (j > i && (sin + ulen > bin || sout + units[j].m.dst_cap > bout)) break;
                     sin += ulen; sout += units[j].m.dst_cap; j++;
                 }
-                Slot &s = e->slot[issued & 1];
-                if (drain(s) != RC_OK) return RC_FAIL;
+                while (next_drain + NS <= issued) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
                 if (stop) break;
+                Slot &s = e->slot[issued % NS];
                 if (run(s, i, j - i, units[i].unit_start, sin, units[i].m.dst_off, sout, false) != RC_OK) return RC_FAIL;
-                if (issued > 0 && drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL;
                 issued++; i = j;
+                if (issued - next_drain >= (size_t)NS) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
             }
-            if (issued) { if (drain(e->slot[issued & 1]) != RC_OK) return RC_FAIL; if (drain(e->slot[(issued + 1) & 1]) != RC_OK) return RC_FAIL; }
+            for (int k = 0; k < NS; k++, next_drain++) if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL;
             if (failed_unit >= 0 && units[(size_t)failed_unit].speculative) {
                 /* the magic-scan boundary was wrong (or the member is corrupt): decode it alone,
                  * let the device find its end, check the footer found there, then resume parsing */

@@ -11,6 +11,7 @@ fmts = [int(x) for x in os.environ.get("DIAG_FMTS", "2,1,0,3").split(",")]
 data_all = cor.make(q.Corpus.SILESIA_LIKE, 12 << 20)
 
 def check_members(blob, data, fmt, hw):
+    if fmt != q.QZ_DEFLATE_GZIP_EXT: return -1, '', b''
     """walk gzip-ext members with python zlib; return index of first bad chunk or -1"""
     off = 0; i = 0; pos = 0
     while off < len(blob):
@@ -32,8 +33,8 @@ def check_members(blob, data, fmt, hw):
     return -1, "", b""
 
 for fmt in fmts:
-    for n in (0, 1, 100, 4096, 8191, 8192, 8193, 65536, 65537, 1 << 20, 12 << 20):
-        for seg in (0, 2, 8, 11):
+    for n in ((0, 100, 8193, 65537, 300000) if os.environ.get('DIAG_QUICK') else (0, 1, 100, 4096, 8191, 8192, 8193, 65536, 65537, 1 << 20, 12 << 20)):
+        for seg in ((0, 8) if os.environ.get('DIAG_QUICK') else (0, 2, 8, 11)):
             if n > (1 << 20) and seg: continue
             data = data_all[seg << 20:(seg << 20) + n] if n <= (1 << 20) else data_all[:n]
             tag = f"fmt={q.FMT_NAMES[fmt]} n={n} seg={seg}"

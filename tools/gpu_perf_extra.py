@@ -1,0 +1,70 @@
+"""Secondary measurements on the GPU box (not the headline): decompress, LZ4, stream API.
+Prints one JSON object; device-resident numbers use CUDA-event kernel time from qzb200GetStats."""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from harness import qzapi as q
+
+prod, cor = q.QzLib(q.PRODUCT_SO), q.Corpus()
+L = prod.lib
+N = int(os.environ.get("EXTRA_MIB", "1024")) << 20
+CALL = 512 << 20
+h_in = L.qzMalloc(N, 0, q.PINNED_MEM); cor.fill(q.Corpus.SILESIA_LIKE, h_in, N)
+cap = L.qzMaxCompressedLength(CALL, None)
+h_out = L.qzMalloc(cap * (N // CALL), 0, q.PINNED_MEM); h_back = L.qzMalloc(N, 0, q.PINNED_MEM)
+d_in, d_out, d_back = L.qzb200DeviceAlloc(N), L.qzb200DeviceAlloc(cap * (N // CALL)), L.qzb200DeviceAlloc(N)
+L.qzb200CopyToDevice(d_in, h_in, N)
+res = {}
+for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4)):
+    sess = prod.new_session(fmt=fmt)
+    # compress each 512 MiB call into consecutive regions; remember sizes
+    sizes, kms = [], 0.0
+    for rep in range(2):
+        sizes, kms, off = [], 0.0, 0
+        t0 = time.perf_counter()
+        for i in range(N // CALL):
+            rc, used, made, _ = prod.compress_device(sess, d_in + i * CALL, CALL, d_out + off, cap, 1)
+            assert rc == 0 and used == CALL
+            kms += prod.stats(sess).kernel_ms; sizes.append(made); off += made
+        wall = time.perf_counter() - t0
+    total_c = sum(sizes)
+    res[name + "_compress"] = {"GBps_wall": round(N / wall / 1e9, 2), "GBps_kernels": round(N / (kms / 1e3) / 1e9, 2), "ratio": round(total_c / N, 4)}
+    # host copy of the compressed stream for header walking, then device-resident decompress
+    L.qzb200CopyToHost(h_out, d_out, total_c)
+    for rep in range(2):
+        kms, off, ooff = 0.0, 0, 0
+        t0 = time.perf_counter()
+        for i, sz in enumerate(sizes):
+            used, made = C.c_uint64(0), C.c_uint64(0)
+            rc = L.qzb200DecompressDevice(C.byref(sess), d_out + off, h_out + off, sz, d_back + ooff, CALL, C.byref(used), C.byref(made))
+            assert rc == 0 and used.value == sz and made.value == CALL, (rc, used.value, sz, made.value)
+            kms += prod.stats(sess).kernel_ms; off += sz; ooff += CALL
+        wall = time.perf_counter() - t0
+    res[name + "_decompress"] = {"GBps_out_wall": round(N / wall / 1e9, 2), "GBps_out_kernels": round(N / (kms / 1e3) / 1e9, 2),
+                                 "GBps_in_plus_out_kernels": round((N + total_c) / (kms / 1e3) / 1e9, 2)}
+    L.qzb200CopyToHost(h_back, d_back, N)
+    assert C.string_at(h_back, 1 << 20) == C.string_at(h_in, 1 << 20) and C.string_at(h_back + N - 4096, 4096) == C.string_at(h_in + N - 4096, 4096)
+    # host path decompress (pinned -> pinned)
+    t0 = time.perf_counter(); off = ooff = 0
+    for sz in sizes:
+        rc, used, made = prod.decompress_call(sess, h_out + off, sz, h_back + ooff, CALL)
+        assert rc == 0 and made == CALL
+        off += sz; ooff += CALL
+    res[name + "_decompress"]["GBps_out_e2e_host"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
+    prod.end_session(sess)
+# stream API, BASELINE config 5: RAW, 4 KiB submissions (a slice of the 1 GiB stream)
+SN = int(os.environ.get("EXTRA_STREAM_MIB", "64")) << 20
+for sb in (65536, 2 * 1024 * 1024 - 5 * 1024):
+    sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW, strm_buff_sz=sb)
+    st = q.QzStream(); ocap = 4 << 20; obuf = (C.c_ubyte * ocap)()
+    consumed = outb = calls = 0
+    t0 = time.perf_counter()
+    while True:
+        left = SN - consumed; n = min(4096, left); last = 1 if left - n == 0 else 0
+        st.in_ = h_in + consumed; st.in_sz = n; st.out = C.addressof(obuf); st.out_sz = ocap
+        rc = L.qzCompressStream(C.byref(sess), C.byref(st), last); assert rc == 0, rc
+        consumed += st.in_sz; outb += st.out_sz; calls += 1
+        if last and st.pending_in == 0 and st.pending_out == 0 and consumed == SN: break
+    dt = time.perf_counter() - t0
+    L.qzEndStream(C.byref(sess), C.byref(st)); prod.end_session(sess)
+    res[f"stream_raw_4KiB_strmbuf_{sb}"] = {"MBps": round(SN / dt / 1e6, 1), "calls": calls, "ratio": round(outb / SN, 4), "stream_MiB": SN >> 20}
+print(json.dumps(res))
