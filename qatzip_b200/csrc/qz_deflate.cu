@@ -186,7 +186,6 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         }
         piece[n + lane] = 0;          /* zero pad */
         for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
-        for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
         __syncwarp();
         /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
         int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
@@ -203,10 +202,11 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
     }
 
     /* ---- phase 2: match + select + tokens ---- */
-    uint32_t ntok = 0, extra_acc = 0;
+    uint32_t ntok = 0;
     {
         uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
         for (uint32_t base = 0; base < n; base += 32) {
+            if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
             const uint32_t p = base + lane;
             const uint32_t v = ld32u(piece, p);
             const bool can = p + 4 <= n;
@@ -229,7 +229,6 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
             const uint32_t valid = __ballot_sync(FULL, p < n);
             const uint32_t M = __ballot_sync(FULL, L >= 4);
             uint32_t tokmask = 0, matchmask = 0, cur = entry;
-            if (cur >= 32) { entry = cur - 32; continue; }
             for (;;) {
                 uint32_t rest = M & (FULL << cur);
                 if (!rest) { tokmask |= (FULL << cur); cur = 32; break; }
@@ -256,22 +255,10 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
             }
             entry = cur - 32;
             tokmask &= valid;
-            const bool is_tok = (tokmask >> lane) & 1, is_match = (matchmask >> lane) & 1;
-            if (is_tok) {
-                uint32_t t;
-                if (is_match) {
-                    const uint32_t dist = p - cand;
-                    uint32_t ls, le, lv, ds, de, dv;
-                    qz_len_code(L, &ls, &le, &lv);
-                    qz_dist_code(dist, &ds, &de, &dv);
-                    atomicAdd(&ws.hist[ls], 1u);
-                    atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
-                    extra_acc += le + de;
-                    t = 0x80000000u | ((L - 3) << 16) | (dist - 1);
-                } else {
-                    t = v & 0xff;
-                    atomicAdd(&ws.hist[t], 1u);
-                }
+            if ((tokmask >> lane) & 1) {
+                /* raw token: literal byte, or match flag | (len - 3) << 16 | (dist - 1); symbols and
+                 * histograms are derived in phase 3, off the piece buffer's critical path */
+                const uint32_t t = ((matchmask >> lane) & 1) ? (0x80000000u | ((L - 3) << 16) | (p - cand - 1)) : (v & 0xff);
                 toks[ntok + __popc(tokmask & lanemask_lt())] = t;
             }
             ntok += __popc(tokmask);
@@ -279,19 +266,154 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
     }
     __syncwarp();
     ps.ntok = ntok;
-    ps.extra_total = warp_sum(extra_acc);
+    ps.extra_total = 0;
+}
+
+/* ---- bit emission: 32 variable-length fields per call --------------------------------------
+ * Each lane contributes `nb` bits (<= 48).  A warp scan gives every field its bit offset, the
+ * fields are OR-ed into a zeroed shared staging window, and every word that became complete is
+ * stored (coalesced) to the slot.  st[0] always holds the pending partial word. */
+struct EmitState { uint32_t bitpos, flushed; };
+
+__device__ __forceinline__ void emit_group(uint32_t *st, uint32_t *slotw, EmitState &es, uint64_t bits, uint32_t nb, uint32_t lane)
+{
+    uint32_t incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (nb) {
+        const uint32_t pos = es.bitpos + incl - nb - (es.flushed << 5);
+        const uint32_t w = pos >> 5, sh = pos & 31;
+        const uint64_t lo = bits << sh;
+        const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
+        if ((uint32_t)lo) atomicOr(&st[w], (uint32_t)lo);
+        if ((uint32_t)(lo >> 32)) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
+        if (hi) atomicOr(&st[w + 2], hi);
+    }
+    __syncwarp();
+    es.bitpos += total;
+    const uint32_t nfull = (es.bitpos >> 5) - es.flushed;
+    for (uint32_t i = lane; i < nfull; i += 32) slotw[es.flushed + i] = st[i];
+    const uint32_t carry = st[nfull];
+    __syncwarp();
+    for (uint32_t i = lane; i <= nfull + 2 && i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+    __syncwarp();
+    if (lane == 0) st[0] = carry;
+    __syncwarp();
+    es.flushed += nfull;
+}
+
+/* length 3..258 -> symbol index 0..28 | extra-bit count << 5 | (base - 3) << 8, filled once per CTA */
+__device__ __forceinline__ uint16_t len_table_entry(uint32_t l /* len - 3 */)
+{
+    uint32_t sym, eb, ev;
+    qz_len_code(l + 3, &sym, &eb, &ev);
+    return (uint16_t)((sym - 257) | (eb << 5) | ((l - ev) << 8));
+}
+
+/* Warp-parallel version of qz_dyn_header_plan's run-length pass (RFC 1951 3.2.7): every run of
+ * equal code lengths is handled by the lane sitting on its first element. */
+__device__ __forceinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 19 counters + 12 words */, uint32_t lane)
+{
+    QzDynHeader &h = cs.hdr;
+    uint32_t bal = __ballot_sync(FULL, lane < 29 && cs.ll_len[257 + lane] != 0);
+    const uint32_t hlit = 257 + (bal ? 32 - __clz(bal) : 0);
+    bal = __ballot_sync(FULL, lane < QZ_NUM_D && cs.d_len[lane] != 0);
+    const uint32_t hdist = bal ? 32 - __clz(bal) : 1;
+    const uint32_t total = hlit + hdist, ngroups = (total + 31) >> 5;
+    uint8_t *seq = h.seq;
+    uint32_t *heads = cf + 20;                    /* one head mask per group of 32 positions */
+    if (lane < QZ_NUM_CL) cf[lane] = 0;
+    for (uint32_t i = lane; i < total; i += 32) seq[i] = i < hlit ? cs.ll_len[i] : cs.d_len[i - hlit];
+    __syncwarp();
+    for (uint32_t g = 0; g < ngroups; g++) {
+        const uint32_t i = (g << 5) + lane;
+        const bool head = i < total && (i == 0 || seq[i] != seq[i - 1]);
+        const uint32_t m = __ballot_sync(FULL, head);
+        if (lane == 0) heads[g] = m;
+    }
+    __syncwarp();
+    uint32_t nitems = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+        const uint32_t i = (g << 5) + lane, hm = heads[g];
+        const bool head = (hm >> lane) & 1;
+        uint32_t cnt = 0, v = 0, run = 0;
+        if (head) {
+            v = seq[i];
+            uint32_t nxt = total, m = lane < 31 ? hm & (FULL << (lane + 1)) : 0u;
+            if (m) nxt = (g << 5) + __ffs(m) - 1;
+            else for (uint32_t g2 = g + 1; g2 < ngroups; g2++) { uint32_t m2 = heads[g2]; if (m2) { nxt = (g2 << 5) + __ffs(m2) - 1; break; } }
+            run = nxt - i;
+            if (v == 0) {
+                const uint32_t full = run / 138, rem = run - full * 138;
+                cnt = full + (rem >= 11 ? 1 : rem >= 3 ? 1 : rem);
+            } else {
+                const uint32_t r1 = run - 1, full = r1 / 6, rem = r1 - full * 6;
+                cnt = 1 + full + (rem >= 3 ? 1 : rem);
+            }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        if (head) {
+            uint16_t *it = h.items + nitems + incl - cnt;
+            if (v == 0) {
+                uint32_t r = run;
+                while (r >= 11) { const uint32_t t = r > 138 ? 138 : r; *it++ = qz_cl_item(18, t - 11, 7); atomicAdd(&cf[18], 1u); r -= t; }
+                if (r >= 3) { *it++ = qz_cl_item(17, r - 3, 3); atomicAdd(&cf[17], 1u); r = 0; }
+                if (r) { atomicAdd(&cf[0], r); while (r--) *it++ = qz_cl_item(0, 0, 0); }
+            } else {
+                uint32_t r = run - 1, lits = 1;
+                *it++ = qz_cl_item(v, 0, 0);
+                while (r >= 3) { const uint32_t t = r > 6 ? 6 : r; *it++ = qz_cl_item(16, t - 3, 2); atomicAdd(&cf[16], 1u); r -= t; }
+                lits += r;
+                while (r--) *it++ = qz_cl_item(v, 0, 0);
+                atomicAdd(&cf[v], lits);
+            }
+        }
+        nitems += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    if (lane == 0) { h.hlit = hlit; h.hdist = hdist; h.nitems = nitems; qz_cl_build(cf, &h); }
+    __syncwarp();
 }
 
 template <int HB>
-__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, const uint32_t *toks, uint32_t lane, const PieceState &ps)
+__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, const uint16_t *s_lentab,
+                                        uint32_t lane, const PieceState &ps)
 {
-    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok, extra_total = ps.extra_total;
+    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
     const bool bfinal = ps.bfinal;
     uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
     uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
-
-    /* ---- phase 3: code construction ---- */
     CodeScratch &cs = ws.u.cs;
+
+    /* ---- phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
+     *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13) */
+    for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
+    for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
+    cs.d_len[lane] = 0;
+    __syncwarp();
+    uint32_t extra_acc = 0;
+    for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
+        if (t0 + lane < ntok) {
+            uint32_t t = __ldcg(toks + t0 + lane);
+            if (t & 0x80000000u) {
+                const uint32_t le = s_lentab[(t >> 16) & 0xff];
+                const uint32_t ls = le & 31, leb = (le >> 5) & 7, lev = ((t >> 16) & 0xff) - (le >> 8);
+                uint32_t ds, de, dv;
+                qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
+                atomicAdd(&ws.hist[257 + ls], 1u);
+                atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
+                extra_acc += leb + de;
+                __stcg(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv);
+            } else atomicAdd(&ws.hist[t], 1u);
+        }
+    }
+    __syncwarp();
+    const uint32_t extra_total = warp_sum(extra_acc);
+
+    /* ---- phase 3b: code construction ---- */
     uint32_t out_bytes = 0;
     int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
     {
@@ -300,8 +422,6 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             qz_huff_force_two(ws.hist, QZ_NUM_LL);
             qz_huff_force_two(ws.hist + QZ_DOFF, QZ_NUM_D);
         }
-        for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
-        cs.d_len[lane] = 0;
         __syncwarp();
         /* literal/length alphabet */
         int nk = 0;
@@ -330,8 +450,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         if (lane < QZ_NUM_D) { uint32_t f = ws.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
         dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
         /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
-        if (lane == 0) qz_dyn_header_plan(cs.ll_len, cs.d_len, &cs.hdr);
-        __syncwarp();
+        warp_plan_header(cs, cs.keys, lane);
         dynb += cs.hdr.bits;
         const uint32_t storedb = (5 + n) * 8;
         if (job.static_huffman) dynb = 0xffffffffu;
@@ -349,7 +468,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     } else {
         /* code tables go where the histograms were: code | len << 16 */
         QzBitWriter bw;
-        uint32_t bitpos = 0, flushed = 0;
+        EmitState es; es.bitpos = 0; es.flushed = 0;
         if (btype == 1) {
             for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
             cs.d_len[lane] = 5;
@@ -357,19 +476,36 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         }
         warp_assign_codes(cs.ll_len, 288, ws.hist, cs.keys, lane);
         warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF, cs.keys, lane);
+        uint32_t *clc = cs.keys + 40;                 /* code-length alphabet codes, 19 words */
+        if (btype == 2) warp_assign_codes(cs.hdr.cl_len, QZ_NUM_CL, clc, cs.keys, lane);
         if (lane == 0) {
             qz_bw_init(&bw, slotw);
-            if (btype == 2) qz_dyn_header_write(&bw, &cs.hdr, bfinal);
+            if (btype == 2) qz_dyn_header_write_prefix(&bw, &cs.hdr, bfinal);
             else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
-            bitpos = qz_bw_bitpos(&bw); flushed = bw.wpos;
+            es.bitpos = qz_bw_bitpos(&bw); es.flushed = bw.wpos;
         }
-        bitpos = __shfl_sync(FULL, bitpos, 0); flushed = __shfl_sync(FULL, flushed, 0);
-        uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
+        es.bitpos = __shfl_sync(FULL, es.bitpos, 0); es.flushed = __shfl_sync(FULL, es.flushed, 0);
+        const uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
+        /* the cl codes must survive the staging window being cleared: keep them in registers */
+        const uint32_t my_clc = (btype == 2 && lane < QZ_NUM_CL) ? clc[lane] : 0u;
+        __syncwarp();
         uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
         for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
         __syncwarp();
         if (lane == 0) st[0] = pend;
         __syncwarp();
+
+        /* run-length coded code lengths of a dynamic header go through the same emitter */
+        if (btype == 2) {
+            const uint32_t nitems = cs.hdr.nitems;
+            for (uint32_t k0 = 0; k0 < nitems; k0 += 32) {
+                uint64_t bits = 0; uint32_t nb = 0;
+                const uint32_t it = k0 + lane < nitems ? cs.hdr.items[k0 + lane] : 0xffffffffu;
+                const uint32_t c = __shfl_sync(FULL, my_clc, it & 31);
+                if (it != 0xffffffffu) { bits = c & 0xffff; nb = c >> 16; bits |= (uint64_t)((it >> 5) & 127) << nb; nb += (it >> 12) & 15; }
+                emit_group(st, slotw, es, bits, nb, lane);
+            }
+        }
 
         /* ---- phase 4: emit ---- */
         for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
@@ -377,10 +513,9 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             if (t0 + lane < ntok) {
                 const uint32_t t = __ldcg(toks + t0 + lane);
                 if (t & 0x80000000u) {
-                    uint32_t ls, le, lv, ds, de, dv;
-                    qz_len_code(((t >> 16) & 0xff) + 3, &ls, &le, &lv);
-                    qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
-                    const uint32_t lc = ws.hist[ls], dc = ws.hist[QZ_DOFF + ds];
+                    const uint32_t ls = (t >> 26) & 31, lv = (t >> 21) & 31, ds = (t >> 16) & 31, dv = t & 0x1fff;
+                    const uint32_t le = (ls < 8 || ls == 28) ? 0u : (ls - 4) >> 2, de = ds < 4 ? 0u : (ds >> 1) - 1;
+                    const uint32_t lc = ws.hist[257 + ls], dc = ws.hist[QZ_DOFF + ds];
                     bits = lc & 0xffff; nb = lc >> 16;
                     bits |= (uint64_t)lv << nb; nb += le;
                     bits |= (uint64_t)(dc & 0xffff) << nb; nb += dc >> 16;
@@ -390,34 +525,11 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
                     bits = c & 0xffff; nb = c >> 16;
                 }
             }
-            uint32_t incl = nb;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            if (nb) {
-                const uint32_t pos = bitpos + incl - nb - (flushed << 5);
-                const uint32_t w = pos >> 5, sh = pos & 31;
-                const uint64_t lo = bits << sh;
-                const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
-                if ((uint32_t)lo) atomicOr(&st[w], (uint32_t)lo);
-                if ((uint32_t)(lo >> 32)) atomicOr(&st[w + 1], (uint32_t)(lo >> 32));
-                if (hi) atomicOr(&st[w + 2], hi);
-            }
-            __syncwarp();
-            bitpos += total;
-            const uint32_t nfull = (bitpos >> 5) - flushed;
-            for (uint32_t i = lane; i < nfull; i += 32) slotw[flushed + i] = st[i];
-            const uint32_t carry = st[nfull];
-            __syncwarp();
-            for (uint32_t i = lane; i <= nfull + 2 && i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
-            __syncwarp();
-            if (lane == 0) st[0] = carry;
-            __syncwarp();
-            flushed += nfull;
+            emit_group(st, slotw, es, bits, nb, lane);
         }
         /* end-of-block, then byte alignment: final blocks pad, others append an empty stored block */
         if (lane == 0) {
-            bw.words = slotw; bw.wpos = flushed; bw.acc = st[0]; bw.nacc = bitpos & 31;
+            bw.words = slotw; bw.wpos = es.flushed; bw.acc = st[0]; bw.nacc = es.bitpos & 31;
             const uint32_t eob = ws.hist[256];
             qz_bw_put(&bw, eob & 0xffff, eob >> 16);
             if (!bfinal) {
@@ -448,12 +560,13 @@ __global__ void __launch_bounds__(960) qzb_deflate_pieces_kernel(QzbCompressJob 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
+    __shared__ uint16_t s_lentab[256];
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, pair = warp >> 1, side = warp & 1;
     PS &ps = reinterpret_cast<PS *>(smem_raw)[pair];
     WarpPriv<HB> &ws = ps.w[side];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
     if (lane < 2) ps.got[lane] = 1;
     __syncthreads();
@@ -481,7 +594,7 @@ __global__ void __launch_bounds__(960) qzb_deflate_pieces_kernel(QzbCompressJob 
             if (lane == 0) ps.got[side] = have_new ? 1u : 0u;
             my_got = have_new;
         } else if (have_cur) {
-            phase34<HB>(job, ws, toks, lane, cur);
+            phase34<HB>(job, ws, toks, s_lentab, lane, cur);
             have_cur = false;
         }
         __syncwarp();

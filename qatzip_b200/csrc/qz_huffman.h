@@ -133,6 +133,30 @@ struct QzDynHeader {
 
 QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return (uint16_t)(sym | (eval << 5) | (ebits << 12)); }
 
+/* Code-length alphabet (<= 19 symbols, 7-bit cap) from its frequencies cf[]; sizes the header.
+ * h->items / h->nitems / h->hlit / h->hdist must already be set. */
+QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
+{
+    qz_huff_force_two(cf, QZ_NUM_CL);
+    uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
+    for (int k = 0; k < QZ_NUM_CL; k++) {
+        h->cl_len[k] = 0;
+        if (cf[k]) {
+            uint32_t key = QZ_HUFF_KEY(cf[k], k); int p = nu++;
+            while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; p--; }
+            keys[p] = key;
+        }
+    }
+    qz_huff_lengths_from_sorted(keys, ids, nu, 7, h->cl_len);
+    const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+    uint32_t hclen = QZ_NUM_CL;
+    while (hclen > 4 && h->cl_len[ORDER[hclen - 1]] == 0) hclen--;
+    h->hclen = hclen;
+    uint32_t bits = 3 + 5 + 5 + 4 + 3 * hclen;
+    for (uint32_t k = 0; k < h->nitems; k++) bits += h->cl_len[h->items[k] & 31] + (h->items[k] >> 12);
+    h->bits = bits;
+}
+
 /* Run-length code the two length arrays into code-length symbols and size the header. */
 QZ_HD_SERIAL void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len, QzDynHeader *h)
 {
@@ -163,25 +187,18 @@ QZ_HD_SERIAL void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len
         i = j;
     }
     h->nitems = n;
-    /* code-length alphabet: <= 19 symbols, 7-bit cap; tiny insertion sort */
-    qz_huff_force_two(cf, QZ_NUM_CL);
-    uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
-    for (int k = 0; k < QZ_NUM_CL; k++) {
-        h->cl_len[k] = 0;
-        if (cf[k]) {
-            uint32_t key = QZ_HUFF_KEY(cf[k], k); int p = nu++;
-            while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; p--; }
-            keys[p] = key;
-        }
-    }
-    qz_huff_lengths_from_sorted(keys, ids, nu, 7, h->cl_len);
+    qz_cl_build(cf, h);
+}
+
+/* the fixed part of a dynamic block header: BFINAL/BTYPE, HLIT, HDIST, HCLEN and the 3-bit lengths */
+QZ_HD_SERIAL void qz_dyn_header_write_prefix(QzBitWriter *bw, const QzDynHeader *h, int bfinal)
+{
     const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
-    uint32_t hclen = QZ_NUM_CL;
-    while (hclen > 4 && h->cl_len[ORDER[hclen - 1]] == 0) hclen--;
-    h->hclen = hclen;
-    uint32_t bits = 3 + 5 + 5 + 4 + 3 * hclen;
-    for (uint32_t k = 0; k < n; k++) bits += h->cl_len[h->items[k] & 31] + (h->items[k] >> 12);
-    h->bits = bits;
+    qz_bw_put(bw, (uint32_t)(bfinal ? 1 : 0) | (2u << 1), 3);
+    qz_bw_put(bw, h->hlit - 257, 5);
+    qz_bw_put(bw, h->hdist - 1, 5);
+    qz_bw_put(bw, h->hclen - 4, 4);
+    for (uint32_t k = 0; k < h->hclen; k++) qz_bw_put(bw, h->cl_len[ORDER[k]], 3);
 }
 
 QZ_HD_SERIAL void qz_dyn_header_write(QzBitWriter *bw, const QzDynHeader *h, int bfinal)

@@ -15,9 +15,11 @@
 
 #define FULL 0xffffffffu
 
+#define QZ_INFL_BATCH 32
 struct InflWarpSmem {
     QzInflTables t;
     uint16_t code_of[320];
+    uint32_t tok[QZ_INFL_BATCH];     /* one decoded batch: lane 0 fills it, every lane places one token */
 };
 
 __device__ __forceinline__ uint32_t bcast(uint32_t v) { return __shfl_sync(FULL, v, 0); }
@@ -115,20 +117,47 @@ __global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
             qz_infl_fill_lut(T.lens, ws.code_of, (int)hlit, T.ll_lut, QZ_LL_LUT_BITS, (int)lane, 32);
             qz_infl_fill_lut(T.lens + hlit, ws.code_of + 288, (int)hdist, T.d_lut, QZ_D_LUT_BITS, (int)lane, 32);
             __syncwarp();
+            /* lane 0 decodes a batch of tokens (no output touched); then every lane places one:
+             * literals and matches whose source lies wholly before the batch go out at once, matches
+             * that read bytes produced inside the batch follow in order, copied by the whole warp */
             for (;;) {
-                int ev = 0; uint32_t mlen = 0, mdist = 0;
-                if (lane == 0) ev = qz_inflate_run(&br, &T, dst, &out, cap, &mlen, &mdist);
+                int ev = 0; uint32_t ntk = 0, pos = out;
+                if (lane == 0) ev = qz_inflate_tokens(&br, &T, ws.tok, QZ_INFL_BATCH, &ntk, &pos, cap);
                 __syncwarp();
-                ev = (int)bcast((uint32_t)ev); out = bcast(out);
+                ev = (int)bcast((uint32_t)ev); ntk = bcast(ntk);
+                const uint32_t t = lane < ntk ? ws.tok[lane] : 0u;
+                const bool is_match = lane < ntk && (t >> 31);
+                const uint32_t len = lane < ntk ? (is_match ? ((t >> 16) & 0xff) + 3 : 1u) : 0u;
+                const uint32_t dist = (t & 0x7fff) + 1;
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+                const uint32_t o = out + incl - len;                       /* where this lane's token lands */
+                const uint32_t span = dist < len ? dist : len;               /* distinct source bytes actually read */
+                const bool dep = is_match && (o - dist + span > out);        /* reads output of this very batch */
+                if (lane < ntk) {
+                    if (!is_match) dst[o] = (uint8_t)t;
+                    else if (!dep) {
+                        const uint8_t *from = dst + o - dist;
+                        if (dist >= len) { for (uint32_t k = 0; k < len; k++) dst[o + k] = __ldcg(from + k); }
+                        else { for (uint32_t k = 0; k < len; k++) dst[o + k] = __ldcg(from + k % dist); }
+                    }
+                }
+                uint32_t depmask = __ballot_sync(FULL, dep);
+                __syncwarp();
+                while (depmask) {
+                    const uint32_t j = __ffs(depmask) - 1; depmask &= depmask - 1;
+                    const uint32_t oj = __shfl_sync(FULL, o, j), lj = __shfl_sync(FULL, len, j), dj = __shfl_sync(FULL, dist, j);
+                    const uint8_t *from = dst + oj - dj;
+                    /* dj < lj: every output byte repeats one of the dj bytes before oj, all already final */
+                    if (dj >= lj) { for (uint32_t k = lane; k < lj; k += 32) dst[oj + k] = __ldcg(from + k); }
+                    else { for (uint32_t k = lane; k < lj; k += 32) dst[oj + k] = __ldcg(from + k % dj); }
+                    __syncwarp();
+                }
+                out += __shfl_sync(FULL, incl, 31);
                 if (ev == QZI_END_BLOCK) break;
                 if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; break; }
                 if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; break; }
-                mlen = bcast(mlen); mdist = bcast(mdist);
-                const uint8_t *from = dst + out - mdist;
-                if (mdist >= mlen) { for (uint32_t k = lane; k < mlen; k += 32) dst[out + k] = from[k]; }
-                else { for (uint32_t k = lane; k < mlen; k += 32) dst[out + k] = from[k % mdist]; }
-                out += mlen;
-                __syncwarp();
             }
         }
         /* verdict */

@@ -34,10 +34,17 @@ struct QzBitReader {
 QZ_HD void qz_br_init(QzBitReader *b, const uint8_t *p, uint32_t n) { b->p = p; b->n = n; b->pos = 0; b->acc = 0; b->nacc = 0; b->phantom = 0; }
 QZ_HD void qz_br_refill(QzBitReader *b)
 {
-    /* fast path: 4 aligned bytes at once */
-    if (b->nacc <= 32 && b->pos + 4 <= b->n && (((uintptr_t)(b->p + b->pos)) & 3) == 0) {
-        b->acc |= (uint64_t)(*(const uint32_t *)(b->p + b->pos)) << b->nacc; b->pos += 4; b->nacc += 32;
+    /* Top up only when half empty, and then with ONE aligned 32-bit load: the decode loop calls this
+     * per symbol, so the common case must be a compare and nothing else.  Byte loads happen only
+     * to reach 4-byte alignment at the start and in the last <4 bytes (then zero "phantom" bytes). */
+    if (b->nacc > 32) return;
+    while (b->nacc <= 56 && (((uintptr_t)(b->p + b->pos)) & 3) != 0) {
+        if (b->pos < b->n) b->acc |= (uint64_t)b->p[b->pos++] << b->nacc;
+        else b->phantom++;
+        b->nacc += 8;
     }
+    if (b->nacc > 32) return;
+    if (b->pos + 4 <= b->n) { b->acc |= (uint64_t)(*(const uint32_t *)(b->p + b->pos)) << b->nacc; b->pos += 4; b->nacc += 32; return; }
     while (b->nacc <= 56) {
         if (b->pos < b->n) b->acc |= (uint64_t)b->p[b->pos++] << b->nacc;
         else b->phantom++;
@@ -133,6 +140,48 @@ QZ_HD int qz_inflate_run(QzBitReader *b, const QzInflTables *t, uint8_t *dst, ui
         *mlen = len; *mdist = dist;
         return QZI_MATCH;
     }
+}
+
+/* Batch form of the decode loop: turn the next symbols of the current Huffman block into at most
+ * `max_tok` tokens (literal byte, or 1<<31 | (len-3) << 16 | (dist-1)) WITHOUT touching the
+ * output; *pos is the output position before the batch and is advanced by the bytes the tokens
+ * stand for.  Returns QZI_MATCH (= 0: buffer full, more to come), QZI_END_BLOCK, or an error. */
+QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
+                            uint32_t *pos, uint32_t cap)
+{
+    uint32_t n = 0, o = *pos;
+    int ev = QZI_MATCH;
+    while (n < max_tok) {
+        qz_br_refill(b);
+        uint32_t e = t->ll_lut[b->acc & ((1u << QZ_LL_LUT_BITS) - 1)];
+        int sym;
+        if (e) { sym = (int)(e >> 4); b->acc >>= (e & 15); b->nacc -= (e & 15); }
+        else { sym = qz_infl_slow(b, t->ll_count, t->ll_sorted); if (sym < 0) { ev = QZI_ERR_DATA; break; } }
+        if (sym < 256) {
+            if (o >= cap) { ev = QZI_ERR_FULL; break; }
+            tok[n++] = (uint32_t)sym; o++;
+            continue;
+        }
+        if (sym == 256) { ev = QZI_END_BLOCK; break; }
+        sym -= 257;
+        if (sym >= 29) { ev = QZI_ERR_DATA; break; }
+        uint32_t eb, len = qz_len_base((uint32_t)sym, &eb);
+        if (b->nacc < 48) qz_br_refill(b);
+        len += qz_br_bits(b, eb);
+        uint32_t de = t->d_lut[b->acc & ((1u << QZ_D_LUT_BITS) - 1)];
+        int ds;
+        if (de) { ds = (int)(de >> 4); b->acc >>= (de & 15); b->nacc -= (de & 15); }
+        else { ds = qz_infl_slow(b, t->d_count, t->d_sorted); if (ds < 0) { ev = QZI_ERR_DATA; break; } }
+        if (ds >= 30) { ev = QZI_ERR_DATA; break; }
+        uint32_t dist = qz_dist_base((uint32_t)ds, &eb);
+        dist += qz_br_bits(b, eb);
+        if (dist > o) { ev = QZI_ERR_DATA; break; }
+        if (o + len > cap) { ev = QZI_ERR_FULL; break; }
+        tok[n++] = 0x80000000u | ((len - 3) << 16) | (dist - 1);
+        o += len;
+    }
+    *ntok = n; *pos = o;
+    return ev;
 }
 
 /* Read the code lengths of a dynamic block header into t->lens (hlit lengths then hdist).

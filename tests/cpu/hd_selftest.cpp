@@ -133,13 +133,18 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
             qz_infl_fill_lut(T.lens, code_of, hlit, T.ll_lut, QZ_LL_LUT_BITS, lane, 32);
             qz_infl_fill_lut(T.lens + hlit, code_of + 288, hdist, T.d_lut, QZ_D_LUT_BITS, lane, 32);
         }
-        for (;;) {
-            uint32_t ml = 0, md = 0; int ev = qz_inflate_run(&br, &T, dst.data(), &out, cap, &ml, &md);
+        for (;;) {   // the kernel's batch loop: 32 tokens decoded without touching the output, then placed
+            uint32_t tok[32], ntk = 0, pos = out;
+            int ev = qz_inflate_tokens(&br, &T, tok, 32, &ntk, &pos, cap);
+            for (uint32_t k = 0; k < ntk; k++) {
+                if (tok[k] >> 31) { uint32_t ml = ((tok[k] >> 16) & 0xff) + 3, md = (tok[k] & 0x7fff) + 1;
+                    for (uint32_t q = 0; q < ml; q++) dst[out + q] = dst[out - md + (md >= ml ? q : q % md)]; out += ml; }
+                else dst[out++] = (uint8_t)tok[k];
+            }
+            if (out != pos) return -9;
             if (ev == QZI_END_BLOCK) break;
             if (ev == QZI_ERR_DATA) return -1;
             if (ev == QZI_ERR_FULL) return -2;
-            for (uint32_t k = 0; k < ml; k++) dst[out + k] = dst[out - md + (md >= ml ? k : k % md)];
-            out += ml;
         }
     }
     if (qz_br_overrun(&br)) return -3;
