@@ -201,12 +201,18 @@ def main():
             made_total += made; codec_ms += st.codec_ms; codec_launches += st.codec_launches; launches += st.kernel_launches
         return made_total, codec_ms, codec_launches, launches
 
+    host_break = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0}
+
     def host_pass():
         made_total = 0
+        for k in host_break:
+            host_break[k] = 0.0
         for i in range(ncalls):
             rc, used, made = prod.compress_call(sess, h_in + i * CALL_BYTES, CALL_BYTES, h_out, out_cap_call, 1)
             assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
             made_total += made
+            st = prod.stats(sess)
+            host_break["h2d_ms"] += st.h2d_ms; host_break["kernel_ms"] += st.kernel_ms; host_break["d2h_ms"] += st.d2h_ms
         return made_total
 
     for _ in range(args.warmup):
@@ -261,7 +267,8 @@ def main():
                        "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
             "ratio": round(made / nbytes, 4),
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
-                    "api": "qzCompress(host pinned -> host pinned), 512 MiB per call"},
+                    "api": "qzCompress(host pinned -> host pinned), 512 MiB per call", "ms_per_step": round(dt_e / args.steps * 1e3, 3),
+                    "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in host_break.items()}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,

@@ -19,6 +19,7 @@ typedef struct QzB200Stats_S {
     uint64_t units;              /* chunks compressed / members decoded by the last call */
     int device;                  /* CUDA device ordinal the session runs on */
     int piece_log2, hash_bits;   /* compressor geometry in use */
+    double h2d_ms, d2h_ms;       /* host-buffer compress calls: summed copy times of the last call (overlapping the kernels) */
 } QzB200Stats_T;
 
 /* qzCompress / qzDecompress with src and dest in device memory of the session's GPU.

@@ -377,6 +377,7 @@ extern "C" int qzCompressCrcExt(QzSession_T *sess, const unsigned char *src, uns
         c.want_crc = crc != NULL; c.crc_in = crc ? (uint32_t)*crc : 0;
         rc = qzb_engine_compress(s->engine, &c, &o);
         s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.codec_ms; s->stats.codec_launches = o.codec_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nchunks;
+        s->stats.h2d_ms = o.h2d_ms; s->stats.d2h_ms = o.d2h_ms;
         if (rc != QZ_OK && rc != QZ_BUF_ERROR) goto err;
         if (crc && c.fmt != QZB_FMT_INTERNAL_LZ4) *crc = o.crc;       /* reference src/qatzip.c:1707-1714 */
         *src_len = (unsigned int)o.consumed; *dest_len = (unsigned int)o.produced;

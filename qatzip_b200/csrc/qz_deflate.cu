@@ -124,11 +124,11 @@ struct CodeScratch {
     QzDynHeader hdr;
 };
 
-/* Shared-memory plan.  Two warps form a PAIR that shares one piece buffer: while one warp of
- * the pair runs phases 1-2 (the only phases that read the piece), its partner runs phases 3-4
- * of the piece it matched in the previous interval; a named barrier swaps the roles.  The
- * buffer is the scarce resource (8 KiB of a 227 KiB budget), so halving it per warp lifts
- * residency from 16 to 24 warps per SM. */
+/* Shared-memory plan.  The piece buffer (8 KiB) is needed only by phases 1-2; phases 3-4 work
+ * from the token scratch and the warp's private tables.  So a CTA owns NB piece buffers and
+ * NW > NB warps: a warp draws a ticket, takes any free buffer, runs phases 1-2, hands the buffer
+ * back and finishes phases 3-4 without it.  With phases 1-2 about half of a piece's time,
+ * NW = 2 * NB keeps every buffer busy and lifts residency from 16 to 24 warps per SM. */
 template <int HB>
 struct WarpPriv {
     union {
@@ -137,13 +137,9 @@ struct WarpPriv {
     } u;
     uint32_t hist[QZ_NUM_LL + 2 + QZ_NUM_D + 2]; /* [0,286) lit/len, [288,318) dist; later the code tables */
 };
-template <int PIECE_LOG2, int HB>
-struct PairSmem {
-    static constexpr int PIECE = 1 << PIECE_LOG2;
-    uint8_t piece[PIECE + 32];              /* +32: zero pad so unaligned reads past n are defined */
-    WarpPriv<HB> w[2];
-    uint32_t got[2];                        /* did warp i obtain a piece on its last turn */
-    uint32_t pad[2];
+template <int PIECE_LOG2>
+struct PieceBuf {
+    uint8_t bytes[(1 << PIECE_LOG2) + 32];  /* +32: zero pad so unaligned reads past n are defined */
 };
 #define QZ_DOFF 288
 
@@ -546,62 +542,51 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     __syncwarp();
 }
 
-__device__ __forceinline__ void pair_barrier(uint32_t pair)
-{
-    asm volatile("bar.sync %0, 64;" :: "r"(pair + 1) : "memory");
-}
-
 template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(960) qzb_deflate_pieces_kernel(QzbCompressJob job)
+__global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    typedef PairSmem<PIECE_LOG2, HB> PS;
     static_assert(sizeof(CodeScratch) <= (sizeof(uint16_t) << HB), "code scratch must fit in the hash table");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
     __shared__ uint16_t s_lentab[256];
+    __shared__ uint32_t s_busy[32];         /* one flag per piece buffer */
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, pair = warp >> 1, side = warp & 1;
-    PS &ps = reinterpret_cast<PS *>(smem_raw)[pair];
-    WarpPriv<HB> &ws = ps.w[side];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    PieceBuf<PIECE_LOG2> *bufs = reinterpret_cast<PieceBuf<PIECE_LOG2> *>(smem_raw);
+    WarpPriv<HB> &ws = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>))[warp];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (lane < 2) ps.got[lane] = 1;
+    if (threadIdx.x < 32) s_busy[threadIdx.x] = 0;
     __syncthreads();
 
-    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    const uint32_t gwarp = blockIdx.x * nwarps + warp;
     uint32_t *toks = job.tok_scratch + (size_t)gwarp * PIECE;
 
-    /* Interval `iter` belongs to the warp with side == iter & 1: it draws a ticket and runs phases
-     * 1-2 on the shared piece buffer while its partner runs phases 3-4 of the piece it matched in
-     * the previous interval.  Tickets only grow, so once both warps have drawn a blank in their
-     * latest turns the pair is finished.  Each side's latest outcome travels through got[side]:
-     * written before the barrier by the turn holder, read after the barrier by the partner, and
-     * not written again until two barriers later. */
-    PieceState cur, nxt;
-    bool have_cur = false, my_got = true, partner_got = true;
-    for (uint32_t iter = 0;; iter++) {
-        const bool my_turn = ((iter & 1u) == side);
-        bool have_new = false;
-        if (my_turn) {
-            uint32_t g = 0;
-            if (lane == 0) g = atomicAdd(job.ticket, 1u);
-            g = __shfl_sync(FULL, g, 0);
-            have_new = g < job.npieces;
-            if (have_new) phase12<PIECE_LOG2, HB>(job, ps.piece, ws, toks, s_crc_tab, s_xstrip, g, lane, nxt);
-            if (lane == 0) ps.got[side] = have_new ? 1u : 0u;
-            my_got = have_new;
-        } else if (have_cur) {
-            phase34<HB>(job, ws, toks, s_lentab, lane, cur);
-            have_cur = false;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(job.ticket, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= job.npieces) break;
+        /* take a free piece buffer (lane 0 probes, starting at a warp-specific slot) */
+        uint32_t b = 0;
+        if (lane == 0) {
+            b = warp % (uint32_t)nbuf;
+            for (uint32_t tries = 0;; tries++) {
+                if (atomicCAS(&s_busy[b], 0u, 1u) == 0u) break;
+                if (++b == (uint32_t)nbuf) b = 0;
+                if ((tries % (uint32_t)nbuf) == (uint32_t)nbuf - 1) __nanosleep(200);
+            }
+            __threadfence_block();
         }
+        b = __shfl_sync(FULL, b, 0);
+        PieceState ps;
+        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps);
         __syncwarp();
-        pair_barrier(pair);
-        if (my_turn) { if (have_new) { cur = nxt; have_cur = true; } }
-        else partner_got = ps.got[side ^ 1u] != 0;
-        if (!my_got && !partner_got) break;
+        if (lane == 0) { __threadfence_block(); atomicExch(&s_busy[b], 0u); }
+        phase34<HB>(job, ws, toks, s_lentab, lane, ps);
     }
 }
 
@@ -727,31 +712,31 @@ __global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* shared memory for `warps` warps (an even number: warps work in pairs) */
-extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps)
+/* shared memory for `warps` warps sharing `nbuf` piece buffers */
+extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf)
 {
-    size_t per = (piece_log2 == 13 && hb == 11) ? sizeof(PairSmem<13, 11>) :
-                 (piece_log2 == 13 && hb == 12) ? sizeof(PairSmem<13, 12>) :
-                 (piece_log2 == 14 && hb == 12) ? sizeof(PairSmem<14, 12>) : sizeof(PairSmem<14, 13>);
-    return per * (size_t)((warps + 1) / 2);
+    size_t priv = hb == 11 ? sizeof(WarpPriv<11>) : hb == 12 ? sizeof(WarpPriv<12>) : sizeof(WarpPriv<13>);
+    size_t buf = piece_log2 == 13 ? sizeof(PieceBuf<13>) : sizeof(PieceBuf<14>);
+    return priv * (size_t)warps + buf * (size_t)nbuf;
 }
 
 template <int P, int H>
-static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps, cudaStream_t st)
+static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    size_t smem = sizeof(PairSmem<P, H>) * (size_t)(warps / 2);
+    size_t smem = sizeof(WarpPriv<H>) * (size_t)warps + sizeof(PieceBuf<P>) * (size_t)nbuf;
     cudaError_t e = cudaFuncSetAttribute(qzb_deflate_pieces_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_pieces_kernel<P, H><<<grid, warps * 32, smem, st>>>(job);
+    qzb_deflate_pieces_kernel<P, H><<<grid, warps * 32, smem, st>>>(job, nbuf);
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, cudaStream_t st)
+extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    if (job->piece_log2 == 13 && hb == 11) return launch_deflate<13, 11>(*job, grid, warps, st);
-    if (job->piece_log2 == 13 && hb == 12) return launch_deflate<13, 12>(*job, grid, warps, st);
-    if (job->piece_log2 == 14 && hb == 12) return launch_deflate<14, 12>(*job, grid, warps, st);
-    if (job->piece_log2 == 14 && hb == 13) return launch_deflate<14, 13>(*job, grid, warps, st);
+    if (nbuf < 1 || nbuf > 32 || warps < 1 || warps > 32) return cudaErrorInvalidValue;
+    if (job->piece_log2 == 13 && hb == 11) return launch_deflate<13, 11>(*job, grid, warps, nbuf, st);
+    if (job->piece_log2 == 13 && hb == 12) return launch_deflate<13, 12>(*job, grid, warps, nbuf, st);
+    if (job->piece_log2 == 14 && hb == 12) return launch_deflate<14, 12>(*job, grid, warps, nbuf, st);
+    if (job->piece_log2 == 14 && hb == 13) return launch_deflate<14, 13>(*job, grid, warps, nbuf, st);
     return cudaErrorInvalidValue;
 }
 

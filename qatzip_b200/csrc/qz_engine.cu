@@ -21,12 +21,12 @@
 #include "qz_crc32.h"
 #include "qz_xxh32.h"
 
-extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
-extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps);
+extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -66,7 +66,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->hash_bits = env_int("QZB200_HASH_BITS", t->piece_log2 == 13 ? 11 : 12);
     if (t->piece_log2 == 13 && t->hash_bits != 11 && t->hash_bits != 12) t->hash_bits = 11;
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
-    t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = as many as shared memory allows */
+    t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
+    t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);   /* deflate: piece buffers per CTA, 0 = warps / 2 */
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
@@ -146,7 +147,7 @@ struct HostBuf {
 
 struct Slot {
     cudaStream_t st = nullptr;
-    cudaEvent_t ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr, ev_h0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf d_in, d_slots, d_out, d_meta, d_tok, d_members, d_results;
     HostBuf h_meta, h_in, h_out, h_members, h_results;
     /* bookkeeping of the batch currently in flight */
@@ -178,7 +179,7 @@ extern "C" QzbEngine *qzb_engine_create(int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     for (auto &s : e->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NULL; }
-        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1);
+        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1); cudaEventCreate(&s.ev_h0); cudaEventCreate(&s.ev_d0); cudaEventCreate(&s.ev_d1);
         cudaEventCreateWithFlags(&s.ev_meta, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
     }
@@ -192,6 +193,9 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_km) cudaEventDestroy(s.ev_km);
+        if (s.ev_h0) cudaEventDestroy(s.ev_h0);
+        if (s.ev_d0) cudaEventDestroy(s.ev_d0);
+        if (s.ev_d1) cudaEventDestroy(s.ev_d1);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_meta) cudaEventDestroy(s.ev_meta);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -240,14 +244,19 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     int warps = t.warps_per_cta, ctas_per_sm = 1;
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
-    auto smem_for = [&](int w) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w); };
-    /* deflate warps work in pairs (15 named barriers -> at most 30 warps per CTA); LZ4 warps are independent */
-    const int wmax = lz4 ? 16 : 30, wstep = lz4 ? 1 : 2;
-    if (warps <= 0 || warps > wmax) warps = wmax;
-    if (!lz4) warps &= ~1;
-    if (warps < wstep) warps = wstep;
-    while (warps > wstep && smem_for(warps) + 2048 > smem_cap) warps -= wstep;
-    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps) + 3072));
+    /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
+    int nbuf = t.buffers_per_cta;
+    auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
+    if (lz4) {
+        if (warps <= 0 || warps > 16) warps = 16;
+        while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
+        nbuf = 0;
+    } else {
+        if (warps <= 0 || warps > 32) warps = 24;
+        if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
+        while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
+    }
+    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps, nbuf) + 3328));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
     const int need = (int)((job.npieces + warps - 1) / warps);
@@ -268,7 +277,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, s.st));
+    else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));
     CK(cudaEventRecord(s.ev_k1, s.st));
@@ -346,6 +355,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         uint32_t fit = 0;
         while (fit < s.nchunks && off[fit + 1] <= c->dst_cap - out) fit++;
         const uint64_t bytes = off[fit];
+        CK(cudaEventRecord(s.ev_d0, s.st));
         if (bytes) {
             if (c->dst_pinned) CK(cudaMemcpyAsync(c->dst + out, s.d_out.p, bytes, cudaMemcpyDeviceToHost, s.st));
             else {
@@ -353,8 +363,10 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
                 CK(cudaMemcpyAsync(s.h_out.p, s.d_out.p, bytes, cudaMemcpyDeviceToHost, s.st));
             }
         }
+        CK(cudaEventRecord(s.ev_d1, s.st));
         if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
         CK(cudaStreamSynchronize(s.st));
+        { float t = 0; cudaEventElapsedTime(&t, s.ev_h0, s.ev_k0); o->h2d_ms += t; cudaEventElapsedTime(&t, s.ev_d0, s.ev_d1); o->d2h_ms += t; }
         if (bytes && !c->dst_pinned) memcpy(c->dst + out, s.h_out.p, bytes);
         out += bytes; o->nchunks += fit;
         if (fit < s.nchunks) { consumed += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; stop = true; }
@@ -374,6 +386,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         const uint64_t in_off = b * batch, len = std::min<uint64_t>(batch, c->src_len - in_off);
         const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
         if (s.d_in.ensure(len + 64) != RC_OK || s.d_out.ensure((uint64_t)nch * per_chunk_out) != RC_OK) return RC_FAIL;
+        CK(cudaEventRecord(s.ev_h0, s.st));
         if (len) {
             if (c->src_pinned) CK(cudaMemcpyAsync(s.d_in.p, c->src + in_off, len, cudaMemcpyHostToDevice, s.st));
             else {
@@ -437,7 +450,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
     if (!hsrc) return RC_PARAMS;
     if (c->src_device != c->dst_device) return RC_PARAMS;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
-    const int grid_cap = e->sm_count * 6;
+    const int grid_cap = e->sm_count * 8;
     uint64_t cur_in = 0, cur_out = 0;      /* everything before these offsets is decoded and delivered */
 
     /* one kernel launch over units[first, first+count); outputs either at their final offsets
@@ -607,7 +620,9 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         int rc2 = RC_OK; long failed_unit = -1;
         if (all_sized) {
             /* members know where they go: batch them, two slots in flight */
-            const uint64_t bin = e->tune.batch_bytes, bout = e->tune.batch_bytes * 4;
+            /* one warp per member: a launch needs ~7000 members in flight to fill 148 SMs, so batches are
+             * cut by member count first and by bytes second */
+            const uint64_t bin = std::max<uint64_t>(e->tune.batch_bytes, (uint64_t)256 << 20), bout = bin * 4;
             size_t i = 0, issued = 0; bool stop = false;
             auto drain = [&](Slot &s) -> int {
                 if (!s.busy) return RC_OK;

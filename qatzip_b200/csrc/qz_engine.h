@@ -43,6 +43,7 @@ typedef struct QzbCompressOut {
     double codec_ms;                /* device time of the piece kernel alone (deflate / lz4) */
     uint64_t codec_launches;        /* how many times the piece kernel was launched */
     uint64_t kernel_launches;
+    double h2d_ms, d2h_ms;          /* host-buffer calls: summed copy times (CUDA events), they overlap with kernels */
 } QzbCompressOut;
 /* returns a qatzip.h return code (QZ_OK, QZ_BUF_ERROR with partial progress, QZ_FAIL) */
 int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCompressOut *o);
@@ -71,7 +72,7 @@ int qzb_pinned_free(void *p);          /* 1 if p was one of ours */
 int qzb_pinned_contains(const void *p, size_t len);
 
 /* tuning knobs (environment: QZB200_PIECE_LOG2, QZB200_HASH_BITS, QZB200_BATCH_MB, QZB200_WARPS) */
-typedef struct QzbTuning { int piece_log2, hash_bits, warps_per_cta; size_t batch_bytes; } QzbTuning;
+typedef struct QzbTuning { int piece_log2, hash_bits, warps_per_cta, buffers_per_cta; size_t batch_bytes; } QzbTuning;
 void qzb_get_tuning(QzbTuning *t);
 
 /* raw device memory helpers for callers that keep data in HBM (bench, tests) */

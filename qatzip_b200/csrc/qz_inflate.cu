@@ -44,7 +44,7 @@ __device__ uint32_t warp_crc32_global(const uint8_t *p, uint32_t n, const uint32
     return __shfl_sync(FULL, c, 0);
 }
 
-__global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
+__global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob job)
 {
     __shared__ InflWarpSmem s_w[8];
     __shared__ uint32_t s_crc_tab[256];

@@ -382,3 +382,37 @@ def test_stream_rejects_other_formats(prod):
     st.in_ = C.addressof(buf); st.in_sz = 4096; st.out = C.addressof(buf); st.out_sz = 4096
     assert prod.lib.qzCompressStream(C.byref(sess), C.byref(st), 1) == q.QZ_PARAMS     # reference src/qatzip_stream.c:478-484
     prod.end_session(sess)
+
+
+# ---------------------------------------------------------------------------- member discovery robustness
+def test_gzip_magic_inside_payload(prod, ref):
+    """Plain gzip members carry no size: like the reference (src/qatzip_gzip.c:244-261) the next member is
+    found by scanning for 1f 8b 08 00.  Payloads that contain those bytes (stored blocks of random
+    data) make the scan guess wrong; the engine must notice (length/CRC/ISIZE) and recover."""
+    import random
+    rnd = random.Random(7)
+    chunk = bytearray(rnd.getrandbits(8) for _ in range(150000))
+    for pos in (100, 5000, 70000, 70100, 140000):
+        chunk[pos:pos + 10] = bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff])
+    d = bytes(chunk)
+    for maker in (prod, ref):
+        blob = maker.compress(d, fmt=q.QZ_DEFLATE_GZIP)
+        assert blob.count(bytes([0x1f, 0x8b, 8, 0])) > 3
+        assert prod.decompress(blob, len(d) + 8, fmt=q.QZ_DEFLATE_GZIP) == d
+    two = prod.compress(d, fmt=q.QZ_DEFLATE_GZIP) + ref.compress(d[:70000], fmt=q.QZ_DEFLATE_GZIP)
+    assert prod.decompress(two, len(d) + 70000 + 8, fmt=q.QZ_DEFLATE_GZIP) == d + d[:70000]
+
+
+def test_mixed_member_sizes_like_config3(prod, ref, corpus):
+    """BASELINE configs[2] in small: gzip members made by the reference software path with uncompressed
+    sizes drawn from {4..256} KiB, decoded in one call with hw_buff_sz = 256 KiB."""
+    data = corpus.make(q.Corpus.SILESIA_LIKE, 8 << 20, first_seg=40)
+    sizes, state, pos, blob, want = [4, 8, 16, 32, 64, 128, 256], 3, 0, b"", b""
+    while pos + (256 << 10) <= len(data):
+        state = (state * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+        n = sizes[(state >> 33) % 7] << 10
+        piece = data[pos:pos + n]
+        blob += ref.compress(piece, fmt=q.QZ_DEFLATE_GZIP, hw_buff_sz=262144)
+        want += piece
+        pos += n
+    assert prod.decompress(blob, len(want) + 8, fmt=q.QZ_DEFLATE_GZIP, hw_buff_sz=262144) == want
