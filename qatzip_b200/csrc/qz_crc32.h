@@ -10,6 +10,9 @@
 QZ_HD uint32_t qz_gf2_mul(uint32_t a, uint32_t b)
 {
     uint32_t p = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1          /* rarely executed: keep it small in the instruction cache */
+#endif
     for (int i = 0; i < 32; i++) {
         p ^= (0u - (a >> 31)) & b;
         a <<= 1;

@@ -45,6 +45,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint32_t *a, uint32_t lane)
     for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = lane; i < N; i += 32) {
                 int ixj = i ^ j;
                 if (ixj > i) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint32_t *a, uint32_t lane)
         }
     }
 }
-__device__ __forceinline__ void warp_sort_keys(uint32_t *keys, int n, uint32_t lane)
+__device__ __noinline__ void warp_sort_keys(uint32_t *keys, int n, uint32_t lane)
 {
     int N = 32; while (N < n) N <<= 1;
     for (int i = n + lane; i < N; i += 32) keys[i] = 0xffffffffu;
@@ -80,7 +81,7 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 
 /* sorted keys -> code lengths per symbol: split and scatter run across the warp, only the
  * in-place tree pass and the (rare) length cap run on lane 0 */
-__device__ __forceinline__ void warp_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n, int maxbits, uint8_t *len_by_sym, uint32_t lane)
+__device__ __noinline__ void warp_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n, int maxbits, uint8_t *len_by_sym, uint32_t lane)
 {
     for (int i = lane; i < n; i += 32) { uint32_t k = keys[i]; ids[i] = (uint16_t)(k & 511u); keys[i] = k >> 9; }
     __syncwarp();
@@ -93,7 +94,7 @@ __device__ __forceinline__ void warp_lengths_from_sorted(uint32_t *keys, uint16_
 /* canonical codes for len[0..n) -> out[s] = bit-reversed code | len << 16, in symbol order.
  * Symbols are taken 32 at a time; lanes holding equal lengths find each other with match.any
  * and take consecutive codes.  scratch = 32 words. */
-__device__ __forceinline__ void warp_assign_codes(const uint8_t *len, int n, uint32_t *out, uint32_t *scratch, uint32_t lane)
+__device__ __noinline__ void warp_assign_codes(const uint8_t *len, int n, uint32_t *out, uint32_t *scratch, uint32_t lane)
 {
     uint32_t *cnt = scratch, *next = scratch + 16;
     if (lane < 16) cnt[lane] = 0;
@@ -309,7 +310,7 @@ __device__ __forceinline__ uint16_t len_table_entry(uint32_t l /* len - 3 */)
 
 /* Warp-parallel version of qz_dyn_header_plan's run-length pass (RFC 1951 3.2.7): every run of
  * equal code lengths is handled by the lane sitting on its first element. */
-__device__ __forceinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 19 counters + 12 words */, uint32_t lane)
+__device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 19 counters + 12 words */, uint32_t lane)
 {
     QzDynHeader &h = cs.hdr;
     uint32_t bal = __ballot_sync(FULL, lane < 29 && cs.ll_len[257 + lane] != 0);
@@ -391,9 +392,11 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     cs.d_len[lane] = 0;
     __syncwarp();
     uint32_t extra_acc = 0;
+    uint32_t tnext = lane < ntok ? __ldcg(toks + lane) : 0u;          /* one group ahead: hides the L2 round trip */
     for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
+        const uint32_t t = tnext;
+        if (t0 + 32 + lane < ntok) tnext = __ldcg(toks + t0 + 32 + lane);
         if (t0 + lane < ntok) {
-            uint32_t t = __ldcg(toks + t0 + lane);
             if (t & 0x80000000u) {
                 const uint32_t le = s_lentab[(t >> 16) & 0xff];
                 const uint32_t ls = le & 31, leb = (le >> 5) & 7, lev = ((t >> 16) & 0xff) - (le >> 8);
@@ -504,10 +507,12 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         }
 
         /* ---- phase 4: emit ---- */
+        uint32_t tnext = lane < ntok ? __ldcg(toks + lane) : 0u;
         for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
             uint64_t bits = 0; uint32_t nb = 0;
+            const uint32_t t = tnext;
+            if (t0 + 32 + lane < ntok) tnext = __ldcg(toks + t0 + 32 + lane);
             if (t0 + lane < ntok) {
-                const uint32_t t = __ldcg(toks + t0 + lane);
                 if (t & 0x80000000u) {
                     const uint32_t ls = (t >> 26) & 31, lv = (t >> 21) & 31, ds = (t >> 16) & 31, dv = t & 0x1fff;
                     const uint32_t le = (ls < 8 || ls == 28) ? 0u : (ls - 4) >> 2, de = ds < 4 ? 0u : (ds >> 1) - 1;

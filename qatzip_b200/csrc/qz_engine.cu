@@ -68,7 +68,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);   /* deflate: piece buffers per CTA, 0 = warps / 2 */
-    int mb = env_int("QZB200_BATCH_MB", 64);
+    int mb = env_int("QZB200_BATCH_MB", 128);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
@@ -162,7 +162,7 @@ struct QzbEngine {
     int device = 0;
     int sm_count = 148;
     QzbTuning tune;
-    static constexpr int NSLOT = 3;       /* batches in flight: copy-in, compute, copy-out */
+    static constexpr int NSLOT = 4;       /* batches in flight: copy-in queued, copy-in, compute, copy-out */
     Slot slot[NSLOT];
 };
 
@@ -252,7 +252,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
     } else {
-        if (warps <= 0 || warps > 32) warps = 24;
+        if (warps <= 0 || warps > 32) { warps = 22; if (nbuf <= 0) nbuf = 13; }    /* measured best split of the 227 KB */
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
@@ -622,7 +622,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             /* members know where they go: batch them, two slots in flight */
             /* one warp per member: a launch needs ~7000 members in flight to fill 148 SMs, so batches are
              * cut by member count first and by bytes second */
-            const uint64_t bin = std::max<uint64_t>(e->tune.batch_bytes, (uint64_t)256 << 20), bout = bin * 4;
+            const uint64_t bin = e->tune.batch_bytes, bout = bin * 4;
             size_t i = 0, issued = 0; bool stop = false;
             auto drain = [&](Slot &s) -> int {
                 if (!s.busy) return RC_OK;

@@ -36,7 +36,8 @@ def test_cli_roundtrip(tmp_path, corpus, port, fmt, ext):
     data = corpus.make(q.Corpus.SILESIA_LIKE, 5 << 20, first_seg=3)[: (5 << 20) - 12345]
     src = tmp_path / "sample.bin"
     src.write_bytes(data)
-    run("-k", "-O", fmt, str(src), cwd=tmp_path)
+    # the CLI copies -A into comp_algorithm and qzSetupSessionLZ4 insists on QZ_LZ4 (reference utils/qzip.c:471)
+    run("-k", *(("-A", "lz4") if fmt == "lz4" else ()), "-O", fmt, str(src), cwd=tmp_path)
     comp = tmp_path / ("sample.bin" + ext)
     blob = comp.read_bytes()
     assert 0 < len(blob) < len(data)
@@ -45,7 +46,7 @@ def test_cli_roundtrip(tmp_path, corpus, port, fmt, ext):
     else:
         assert port.decompress(blob, q.FMT_LZ4, len(data) + 8) == data
     src.unlink()
-    run("-d", "-k", str(comp), cwd=tmp_path)
+    run("-d", "-k", *(("-A", "lz4") if fmt == "lz4" else ()), str(comp), cwd=tmp_path)
     assert src.read_bytes() == data
 
 
