@@ -68,7 +68,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);   /* deflate: piece buffers per CTA, 0 = warps / 2 */
-    int mb = env_int("QZB200_BATCH_MB", 128);
+    int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
@@ -379,11 +379,16 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
      * drained, so that while the host waits for it two younger batches are already queued. */
     constexpr int NS = QzbEngine::NSLOT;
     uint64_t next_drain = 0;
-    for (uint64_t b = 0; b < nb && !stop; b++) {
+    /* batch sizes ramp up 16, 32, 64 ... MiB: the first kernel starts after a short copy, and a call's
+     * unavoidable fill/drain tail (calls are synchronous) stays small against its steady state */
+    uint64_t in_off_next = 0;
+    for (uint64_t b = 0; (in_off_next < c->src_len || b == 0) && !stop; b++) {
         Slot &s = e->slot[b % NS];
         while (next_drain + NS <= b) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
         if (stop) break;
-        const uint64_t in_off = b * batch, len = std::min<uint64_t>(batch, c->src_len - in_off);
+        const uint64_t ramp = std::max<uint64_t>(c->chunk_sz, (((uint64_t)16 << 20) << std::min<uint64_t>(b, 8)) / c->chunk_sz * c->chunk_sz);
+        const uint64_t in_off = in_off_next, len = std::min<uint64_t>(std::min(batch, ramp), c->src_len - in_off);
+        in_off_next = in_off + len;
         const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
         if (s.d_in.ensure(len + 64) != RC_OK || s.d_out.ensure((uint64_t)nch * per_chunk_out) != RC_OK) return RC_FAIL;
         CK(cudaEventRecord(s.ev_h0, s.st));
@@ -416,6 +421,7 @@ struct ParsedMember {
     uint32_t hdr_len, ftr_len;
     bool sized;                /* payload length and output size known up front */
     bool speculative;          /* extent guessed by the gzip magic scan: verified by the decode */
+    bool force_seq;            /* guessed extent is implausible: decode alone, device finds the end */
 };
 
 /* RFC 1952 header walk.  Returns header length, 0 if more bytes are needed, -1 if not gzip. */
@@ -559,7 +565,14 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                 if (payload > 0xfffffff0ull) { parse_rc = RC_FAIL; break; }
                 const uint8_t *ftr = p + h + payload;
                 const uint32_t isize = has_qz ? qsrc : rd32(ftr + 4);
-                if ((uint64_t)isize > c->dst_cap - out) { parse_rc = RC_BUF_ERROR; break; }
+                if ((uint64_t)isize > c->dst_cap - out) {
+                    if (!u.speculative) { parse_rc = RC_BUF_ERROR; break; }
+                    /* the size came from a guessed footer position: do not trust it, let the device find the end */
+                    u.m.src_off = in + h; u.m.src_len = (uint32_t)payload; u.m.exact_len = 1; u.m.dst_off = out; u.m.dst_cap = 0;
+                    u.sized = true; u.force_seq = true;
+                    units.push_back(u);
+                    break;
+                }
                 u.m.src_off = in + h; u.m.src_len = (uint32_t)payload; u.m.exact_len = 1;
                 u.m.dst_off = out; u.m.dst_cap = isize; u.m.exact_out = 1;
                 u.m.expect_cksum = rd32(ftr); u.m.check_cksum = 1; u.sized = true;
@@ -624,6 +637,9 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
              * cut by member count first and by bytes second */
             const uint64_t bin = e->tune.batch_bytes, bout = bin * 4;
             size_t i = 0, issued = 0; bool stop = false;
+            long seq_unit = -1;
+            size_t nsized = units.size();
+            if (units.back().force_seq) { seq_unit = (long)units.size() - 1; nsized--; }
             auto drain = [&](Slot &s) -> int {
                 if (!s.busy) return RC_OK;
                 s.busy = false;
@@ -647,9 +663,9 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             };
             constexpr int NS = QzbEngine::NSLOT;
             size_t next_drain = 0;
-            while (i < units.size() && !stop) {
+            while (i < nsized && !stop) {
                 size_t j = i; uint64_t sin = 0, sout = 0;
-                while (j < units.size()) {
+                while (j < nsized) {
                     const uint64_t ulen = units[j].hdr_len + (uint64_t)units[j].m.src_len + units[j].ftr_len;
                     if (j > i && (sin + ulen > bin || sout + units[j].m.dst_cap > bout)) break;
                     sin += ulen; sout += units[j].m.dst_cap; j++;
@@ -662,6 +678,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                 if (issued - next_drain >= (size_t)NS) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
             }
             for (int k = 0; k < NS; k++, next_drain++) if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL;
+            if (failed_unit < 0 && rc2 == RC_OK && seq_unit >= 0) failed_unit = seq_unit;
             if (failed_unit >= 0 && units[(size_t)failed_unit].speculative) {
                 /* the magic-scan boundary was wrong (or the member is corrupt): decode it alone,
                  * let the device find its end, check the footer found there, then resume parsing */
