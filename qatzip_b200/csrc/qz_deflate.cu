@@ -31,6 +31,27 @@
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
+/* L2 residency control.  The token scratch is written once and read twice by the same SM within
+ * microseconds, while the input streams through exactly once: tokens ask L2 to keep them
+ * (evict_last), input lines are marked evict_first and skip L1, so the stream does not push the
+ * tokens out to HBM.  .cg keeps token accesses coherent at L2 between lanes. */
+__device__ __forceinline__ uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint32_t tok_ld(const uint32_t *a, uint64_t pol)
+{
+    uint32_t v; asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ void tok_st(uint32_t *a, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint4 stream_ld16(const uint4 *a, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+
 /* unaligned 32-bit read from a 4-byte aligned shared byte array */
 __device__ __forceinline__ uint32_t ld32u(const uint8_t *base, uint32_t off)
 {
@@ -176,7 +197,8 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
             const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
             uint32_t nv = n >> 4;
-            for (uint32_t i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+            const uint64_t pstream = l2_policy_stream();
+            for (uint32_t i = lane; i < nv; i += 32) d4[i] = stream_ld16(s4 + i, pstream);
             for (uint32_t i = (nv << 4) + lane; i < n; i += 32) piece[i] = src[i];
         } else {
             for (uint32_t i = lane; i < n; i += 32) piece[i] = src[i];
@@ -200,6 +222,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
 
     /* ---- phase 2: match + select + tokens ---- */
     uint32_t ntok = 0;
+    const uint64_t pkeep = l2_policy_keep();
     {
         uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
         for (uint32_t base = 0; base < n; base += 32) {
@@ -256,7 +279,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
                 /* raw token: literal byte, or match flag | (len - 3) << 16 | (dist - 1); symbols and
                  * histograms are derived in phase 3, off the piece buffer's critical path */
                 const uint32_t t = ((matchmask >> lane) & 1) ? (0x80000000u | ((L - 3) << 16) | (p - cand - 1)) : (v & 0xff);
-                toks[ntok + __popc(tokmask & lanemask_lt())] = t;
+                tok_st(toks + ntok + __popc(tokmask & lanemask_lt()), t, pkeep);
             }
             ntok += __popc(tokmask);
         }
@@ -391,11 +414,12 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
     cs.d_len[lane] = 0;
     __syncwarp();
+    const uint64_t pkeep = l2_policy_keep();
     uint32_t extra_acc = 0;
-    uint32_t tnext = lane < ntok ? __ldcg(toks + lane) : 0u;          /* one group ahead: hides the L2 round trip */
+    uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;          /* one group ahead: hides the L2 round trip */
     for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
         const uint32_t t = tnext;
-        if (t0 + 32 + lane < ntok) tnext = __ldcg(toks + t0 + 32 + lane);
+        if (t0 + 32 + lane < ntok) tnext = tok_ld(toks + t0 + 32 + lane, pkeep);
         if (t0 + lane < ntok) {
             if (t & 0x80000000u) {
                 const uint32_t le = s_lentab[(t >> 16) & 0xff];
@@ -405,7 +429,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
                 atomicAdd(&ws.hist[257 + ls], 1u);
                 atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
                 extra_acc += leb + de;
-                __stcg(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv);
+                tok_st(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv, pkeep);
             } else atomicAdd(&ws.hist[t], 1u);
         }
     }
@@ -507,11 +531,11 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         }
 
         /* ---- phase 4: emit ---- */
-        uint32_t tnext = lane < ntok ? __ldcg(toks + lane) : 0u;
+        uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;
         for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
             uint64_t bits = 0; uint32_t nb = 0;
             const uint32_t t = tnext;
-            if (t0 + 32 + lane < ntok) tnext = __ldcg(toks + t0 + 32 + lane);
+            if (t0 + 32 + lane < ntok) tnext = tok_ld(toks + t0 + 32 + lane, pkeep);
             if (t0 + lane < ntok) {
                 if (t & 0x80000000u) {
                     const uint32_t ls = (t >> 26) & 31, lv = (t >> 21) & 31, ds = (t >> 16) & 31, dv = t & 0x1fff;

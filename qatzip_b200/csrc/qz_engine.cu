@@ -635,7 +635,8 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             /* members know where they go: batch them, two slots in flight */
             /* one warp per member: a launch needs ~7000 members in flight to fill 148 SMs, so batches are
              * cut by member count first and by bytes second */
-            const uint64_t bin = e->tune.batch_bytes, bout = bin * 4;
+            /* host buffers: batches small enough to pipeline copies; device-resident: one launch as wide as possible */
+            const uint64_t bin = c->src_device ? ((uint64_t)1 << 30) : e->tune.batch_bytes, bout = bin * 4;
             size_t i = 0, issued = 0; bool stop = false;
             long seq_unit = -1;
             size_t nsized = units.size();

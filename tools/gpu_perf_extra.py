@@ -47,13 +47,44 @@ for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4)):
     L.qzb200CopyToHost(h_back, d_back, N)
     assert C.string_at(h_back, 1 << 20) == C.string_at(h_in, 1 << 20) and C.string_at(h_back + N - 4096, 4096) == C.string_at(h_in + N - 4096, 4096)
     # host path decompress (pinned -> pinned)
-    t0 = time.perf_counter(); off = ooff = 0
-    for sz in sizes:
-        rc, used, made = prod.decompress_call(sess, h_out + off, sz, h_back + ooff, CALL)
-        assert rc == 0 and made == CALL
-        off += sz; ooff += CALL
-    res[name + "_decompress"]["GBps_out_e2e_host"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
+    for rep in range(2):      # first pass allocates the engine's device/pinned buffers
+        t0 = time.perf_counter(); off = ooff = 0
+        for sz in sizes:
+            rc, used, made = prod.decompress_call(sess, h_out + off, sz, h_back + ooff, CALL)
+            assert rc == 0 and made == CALL
+            off += sz; ooff += CALL
+        res[name + "_decompress"]["GBps_out_e2e_host"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
     prod.end_session(sess)
+# the reference's software inflate on all host threads over the same gzip-ext members (CPU baseline of decompress)
+if os.path.exists(q.REF_SO) and not os.environ.get("EXTRA_NOCPU"):
+    import threading
+    ref = q.QzLib(q.REF_SO)
+    sess0 = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT)
+    rc, used, made, _ = prod.compress_device(sess0, d_in, CALL, d_out, cap, 1)
+    L.qzb200CopyToHost(h_out, d_out, made)
+    blob = C.string_at(h_out, made)
+    prod.end_session(sess0)
+    # member boundaries via the QZ extra field
+    offs, o = [], 0
+    while o < len(blob):
+        csz = int.from_bytes(blob[o + 20:o + 24], "little"); offs.append((o, 24 + csz + 8)); o += 24 + csz + 8
+    T = os.cpu_count() or 1
+    per = (len(offs) + T - 1) // T
+    bar = threading.Barrier(T + 1)
+    def work(t):
+        mine = offs[t * per:(t + 1) * per]
+        sess = ref.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT)
+        dst = (C.c_ubyte * (65536 * max(1, len(mine))))()
+        bar.wait()
+        if mine:
+            lo, hi = mine[0][0], mine[-1][0] + mine[-1][1]
+            rc, used, made = ref.decompress_call(sess, h_out + lo, hi - lo, C.addressof(dst), len(dst))
+            assert rc == 0 and made == 65536 * len(mine), (rc, made)
+        bar.wait()
+        ref.end_session(sess)
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    [t.start() for t in ths]; bar.wait(); t0 = time.perf_counter(); bar.wait(); dt = time.perf_counter() - t0; [t.join() for t in ths]
+    res["cpu_reference_decompress"] = {"GBps_out": round(CALL / dt / 1e9, 2), "threads": T, "sample_MiB_out": CALL >> 20}
 # stream API, BASELINE config 5: RAW, 4 KiB submissions (a slice of the 1 GiB stream)
 SN = int(os.environ.get("EXTRA_STREAM_MIB", "64")) << 20
 for sb in (65536, 2 * 1024 * 1024 - 5 * 1024):
