@@ -182,6 +182,145 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Lane-per-member decoder.  Huffman decoding is serial inside a member, so the warp-per-member
+ * kernel above keeps 31 of 32 lanes idle while lane 0 decodes.  When a batch holds many members
+ * whose output positions are known (gzip / gzip-ext), each LANE takes its own member instead:
+ * private bit reader in registers, private decode tables in shared memory (odd word stride, so
+ * the 32 lanes of a warp start in 32 different banks), literals stored directly, matches copied
+ * 8 bytes per L2 round trip.  The same host+device decode routines are used (qz_inflate.h).
+ * CRC-32 verification runs afterwards in qzb_crc_verify_kernel with a whole warp per member. */
+struct InflLaneSmem {
+    QzInflTables t;
+    uint16_t code_of[320];
+    uint32_t pad;                /* sizeof % 8 == 4: consecutive lanes' tables start one bank apart */
+};
+static_assert((sizeof(InflLaneSmem) / 4) % 2 == 1, "lane table stride must be an odd number of words");
+
+__device__ __forceinline__ void lane_copy_match(uint8_t *dst, uint32_t out, uint32_t len, uint32_t dist)
+{
+    const uint8_t *from = dst + out - dist;
+    if (dist >= 8) {
+        /* 8 independent loads, then 8 stores: one L2 round trip per 8 bytes */
+        for (uint32_t k = 0; k < len; k += 8) {
+            uint8_t b[8];
+            const uint32_t m = len - k < 8 ? len - k : 8;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) b[j] = j < m ? __ldcg(from + k + j) : (uint8_t)0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) if (j < m) dst[out + k + j] = b[j];
+        }
+    } else {
+        /* short period: read the pattern once, then repeat it */
+        uint8_t b[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) b[j] = j < dist ? __ldcg(from + j) : (uint8_t)0;
+        uint32_t ph = 0;
+        for (uint32_t k = 0; k < len; k++) {
+            uint8_t v = b[0];
+#pragma unroll
+            for (uint32_t j = 1; j < 8; j++) v = ph == j ? b[j] : v;
+            dst[out + k] = v;
+            ph = ph + 1 == dist ? 0 : ph + 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) qzb_inflate_lanes_kernel(QzbDecompressJob job)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    InflLaneSmem &ws = reinterpret_cast<InflLaneSmem *>(smem_raw)[threadIdx.x];
+    QzInflTables &T = ws.t;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t mi = blockIdx.x * blockDim.x + threadIdx.x; mi < job.nmembers; mi += stride) {
+        const QzbMember m = job.members[mi];
+        const uint8_t *src = job.src + m.src_off;
+        uint8_t *dst = job.dst + m.dst_off;
+        const uint32_t cap = m.dst_cap;
+        QzBitReader br;
+        qz_br_init(&br, src, m.src_len);
+        uint32_t out = 0, status = QZB_ST_OK, bfinal = 0;
+        while (!bfinal && status == QZB_ST_OK) {
+            qz_br_refill(&br);
+            bfinal = qz_br_bits(&br, 1);
+            const uint32_t type = qz_br_bits(&br, 2);
+            if (type == 3) { status = QZB_ST_DATA_ERROR; break; }
+            if (type == 0) {
+                const uint32_t drop = br.nacc & 7; br.acc >>= drop; br.nacc -= drop;
+                qz_br_refill(&br);
+                const uint32_t len = qz_br_bits(&br, 16), nlen = qz_br_bits(&br, 16), start = qz_br_consumed(&br);
+                if ((len ^ 0xffffu) != nlen) { status = QZB_ST_DATA_ERROR; break; }
+                if (start + len > br.n) { status = QZB_ST_IN_TRUNC; break; }
+                if (out + len > cap) { status = QZB_ST_OUT_FULL; break; }
+                for (uint32_t i = 0; i < len; i++) dst[out + i] = src[start + i];
+                out += len;
+                br.pos = start + len; br.acc = 0; br.nacc = 0; br.phantom = 0;
+                continue;
+            }
+            uint32_t hlit = 288, hdist = 30;
+            if (type == 1) qz_inflate_fixed_lens(&T);
+            else if (qz_inflate_read_dynamic(&br, &T, &hlit, &hdist) != 0) { status = QZB_ST_DATA_ERROR; break; }
+            if (qz_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_sorted, ws.code_of) < 0 ||
+                qz_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_sorted, ws.code_of + 288) < 0) { status = QZB_ST_DATA_ERROR; break; }
+            for (uint32_t i = 0; i < (1u << QZ_LL_LUT_BITS); i++) T.ll_lut[i] = 0;
+            for (uint32_t i = 0; i < (1u << QZ_D_LUT_BITS); i++) T.d_lut[i] = 0;
+            qz_infl_fill_lut(T.lens, ws.code_of, (int)hlit, T.ll_lut, QZ_LL_LUT_BITS, 0, 1);
+            qz_infl_fill_lut(T.lens + hlit, ws.code_of + 288, (int)hdist, T.d_lut, QZ_D_LUT_BITS, 0, 1);
+            for (;;) {
+                uint32_t mlen = 0, mdist = 0;
+                const int ev = qz_inflate_run(&br, &T, dst, &out, cap, &mlen, &mdist);
+                if (ev == QZI_MATCH) { lane_copy_match(dst, out, mlen, mdist); out += mlen; continue; }
+                if (ev == QZI_ERR_DATA) status = QZB_ST_DATA_ERROR;
+                else if (ev == QZI_ERR_FULL) status = QZB_ST_OUT_FULL;
+                break;
+            }
+        }
+        const uint32_t consumed = qz_br_consumed(&br);
+        if (status == QZB_ST_OK && qz_br_overrun(&br)) status = QZB_ST_IN_TRUNC;
+        if (status == QZB_ST_OK && (m.exact_len & 1) && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
+        if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
+        QzbMemberResult r;
+        r.status = status; r.consumed = consumed; r.produced = out; r.cksum = 0; r.saw_final = bfinal;
+        r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        job.results[mi] = r;
+    }
+}
+
+/* one warp per member: CRC-32 of what the lane decoder produced, compared with the footer */
+__global__ void __launch_bounds__(256) qzb_crc_verify_kernel(QzbDecompressJob job)
+{
+    __shared__ uint32_t s_crc_tab[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; mi < job.nmembers; mi += nw) {
+        const QzbMember m = job.members[mi];
+        QzbMemberResult r = job.results[mi];
+        if (r.status != QZB_ST_OK) continue;
+        const uint32_t crc = warp_crc32_global(job.dst + m.dst_off, r.produced, s_crc_tab, lane);
+        if (lane == 0) {
+            r.cksum = crc;
+            if (m.check_cksum && crc != m.expect_cksum) r.status = QZB_ST_CKSUM;
+            job.results[mi] = r;
+        }
+    }
+}
+
+extern "C" cudaError_t qzb_launch_inflate_lanes(const QzbDecompressJob *job, int sm_count, cudaStream_t st)
+{
+    const int threads = 64;
+    const size_t smem = sizeof(InflLaneSmem) * threads;
+    cudaError_t e = cudaFuncSetAttribute(qzb_inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int grid = (int)((job->nmembers + threads - 1) / threads);
+    if (grid > sm_count * 2) grid = sm_count * 2;
+    qzb_inflate_lanes_kernel<<<grid, threads, smem, st>>>(*job);
+    int cgrid = (int)((job->nmembers + 7) / 8);
+    if (cgrid > sm_count * 8) cgrid = sm_count * 8;
+    qzb_crc_verify_kernel<<<cgrid, 256, 0, st>>>(*job);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st)
 {
     qzb_inflate_kernel<<<grid, 256, 0, st>>>(*job);

@@ -11,8 +11,8 @@
 #include "qz_hd.h"
 #include "qz_deflate_tables.h"
 
-#define QZ_LL_LUT_BITS 10
-#define QZ_D_LUT_BITS 8
+#define QZ_LL_LUT_BITS 9     /* 1 KiB: small enough that 64 members per SM can keep private tables in shared memory */
+#define QZ_D_LUT_BITS 7
 
 struct QzInflTables {
     uint16_t ll_lut[1 << QZ_LL_LUT_BITS];   /* (sym << 4) | len ; 0 = code longer than the LUT / unused */
