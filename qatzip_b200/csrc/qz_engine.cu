@@ -69,7 +69,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
-    t->inflate_lane_min = env_int("QZB200_INFLATE_LANE_MIN", 64);   /* batches with at least this many sized members decode one member per lane */   /* deflate: piece buffers per CTA, 0 = warps / 2 */
+    t->inflate_lane_min = env_int("QZB200_INFLATE_LANE_MIN", 1 << 30);   /* lane-per-member decoder: off by default (measured slower than warp-per-member so far) */   /* deflate: piece buffers per CTA, 0 = warps / 2 */
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
