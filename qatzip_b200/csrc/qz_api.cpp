@@ -15,6 +15,9 @@
 #include <stdarg.h>
 #include <time.h>
 #include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 #include "../../include/qatzip.h"
 #include "../../include/qatzip_b200.h"
 #include "qz_engine.h"
@@ -50,11 +53,23 @@ struct QzbParams {
     QzPollingMode_T polling_mode; unsigned int is_sensitive_mode;
     unsigned char stop_decompression_stream_end, zlib_format;
 };
+/* asynchronous requests (qzCompress2 / qzDecompress2 with a callback): one completion thread per
+ * session consumes them in submission order and runs the ordinary synchronous engine, so a session
+ * is still only ever driven by one thread at a time (reference: ring + AsyncReqConsumeJob,
+ * src/qatzip.c:3854; lock-free ring src/qatzip_utils.c:1673-1823) */
+struct QzbAsyncReq { int decompress; const unsigned char *src; unsigned char *dest; qzAsyncCallbackFn cb; QzResult_T *res; };
+struct QzbAsync {
+    std::mutex m; std::condition_variable cv, idle;
+    std::deque<QzbAsyncReq> q;
+    std::thread worker;
+    bool stop = false, busy = false;
+};
 struct QzbSess {
     QzbParams p;
     QzbEngine *engine;
     unsigned char end_of_stream;
     QzB200Stats_T stats;
+    QzbAsync *async;
 };
 
 static std::mutex g_lock;                     /* reference src/qatzip.c:124 g_lock */
@@ -307,6 +322,12 @@ extern "C" int qzTeardownSession(QzSession_T *sess)
     if (!sess) return QZ_PARAMS;
     if (sess->internal) {
         QzbSess *s = (QzbSess *)sess->internal;
+        if (s->async) {
+            { std::unique_lock<std::mutex> lk(s->async->m); s->async->idle.wait(lk, [&] { return s->async->q.empty() && !s->async->busy; }); s->async->stop = true; }
+            s->async->cv.notify_all();
+            s->async->worker.join();
+            delete s->async;
+        }
         if (s->engine) qzb_engine_destroy(s->engine);
         free(s);
         sess->internal = NULL;
@@ -444,19 +465,49 @@ extern "C" int qzDecompress(QzSession_T *sess, const unsigned char *src, unsigne
                             unsigned int *dest_len)
 { return qzDecompressCrcExt(sess, src, src_len, dest, dest_len, NULL, NULL); }
 
-/* async entry points: with a NULL callback the reference runs the synchronous engine
- * (reference src/qatzip.c:4122-4133); the callback mode is a "next" row */
+/* async entry points.  NULL callback = the synchronous engine (reference src/qatzip.c:4122-4133);
+ * with a callback the request is queued and the call returns QZ_OK at once; the callback later
+ * receives the same QzResult_T with status / src_len (consumed) / dest_len (produced) filled in. */
+static void async_worker(QzSession_T *sess, QzbAsync *a)
+{
+    for (;;) {
+        QzbAsyncReq r;
+        {
+            std::unique_lock<std::mutex> lk(a->m);
+            a->cv.wait(lk, [&] { return a->stop || !a->q.empty(); });
+            if (a->q.empty()) return;
+            r = a->q.front(); a->q.pop_front(); a->busy = true;
+        }
+        if (r.decompress) r.res->status = qzDecompressCrcExt(sess, r.src, &r.res->src_len, r.dest, &r.res->dest_len, NULL, &r.res->ext_rc);
+        else r.res->status = qzCompressCrcExt(sess, r.src, &r.res->src_len, r.dest, &r.res->dest_len, 1, NULL, &r.res->ext_rc);
+        r.cb(r.res);
+        { std::lock_guard<std::mutex> lk(a->m); a->busy = false; }
+        a->idle.notify_all();
+    }
+}
+static int async_submit(QzSession_T *sess, int decompress, const unsigned char *src, unsigned char *dest, qzAsyncCallbackFn cb, QzResult_T *r)
+{
+    QzbSess *s = NULL;
+    int rc = ready_session(sess, &s);
+    if (rc != QZ_OK) { r->src_len = 0; r->dest_len = 0; return rc; }
+    if (!s->async) { s->async = new QzbAsync(); s->async->worker = std::thread(async_worker, sess, s->async); }
+    { std::lock_guard<std::mutex> lk(s->async->m); s->async->q.push_back(QzbAsyncReq{ decompress, src, dest, cb, r }); }
+    s->async->cv.notify_one();
+    return QZ_OK;
+}
 extern "C" int qzCompress2(QzSession_T *sess, const unsigned char *src, unsigned char *dest, qzAsyncCallbackFn cb, QzResult_T *r)
 {
-    if (!sess || !src || !dest || !r) return QZ_PARAMS;
-    if (cb) return QZ_NOT_SUPPORTED;
+    if (!r) return QZ_PARAMS;
+    if (!sess || !src || !dest) { r->src_len = 0; r->dest_len = 0; return QZ_PARAMS; }
+    if (cb) return async_submit(sess, 0, src, dest, cb, r);
     r->status = qzCompressCrcExt(sess, src, &r->src_len, dest, &r->dest_len, 1, NULL, &r->ext_rc);
     return r->status;
 }
 extern "C" int qzDecompress2(QzSession_T *sess, const unsigned char *src, unsigned char *dest, qzAsyncCallbackFn cb, QzResult_T *r)
 {
-    if (!sess || !src || !dest || !r) return QZ_PARAMS;
-    if (cb) return QZ_NOT_SUPPORTED;
+    if (!r) return QZ_PARAMS;
+    if (!sess || !src || !dest) { r->src_len = 0; r->dest_len = 0; return QZ_PARAMS; }
+    if (cb) return async_submit(sess, 1, src, dest, cb, r);
     r->status = qzDecompressCrcExt(sess, src, &r->src_len, dest, &r->dest_len, NULL, &r->ext_rc);
     return r->status;
 }

@@ -197,34 +197,10 @@ struct InflLaneSmem {
 };
 static_assert((sizeof(InflLaneSmem) / 4) % 2 == 1, "lane table stride must be an odd number of words");
 
-__device__ __forceinline__ void lane_copy_match(uint8_t *dst, uint32_t out, uint32_t len, uint32_t dist)
-{
-    const uint8_t *from = dst + out - dist;
-    if (dist >= 8) {
-        /* 8 independent loads, then 8 stores: one L2 round trip per 8 bytes */
-        for (uint32_t k = 0; k < len; k += 8) {
-            uint8_t b[8];
-            const uint32_t m = len - k < 8 ? len - k : 8;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) b[j] = j < m ? __ldcg(from + k + j) : (uint8_t)0;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) if (j < m) dst[out + k + j] = b[j];
-        }
-    } else {
-        /* short period: read the pattern once, then repeat it */
-        uint8_t b[8];
-#pragma unroll
-        for (uint32_t j = 0; j < 8; j++) b[j] = j < dist ? __ldcg(from + j) : (uint8_t)0;
-        uint32_t ph = 0;
-        for (uint32_t k = 0; k < len; k++) {
-            uint8_t v = b[0];
-#pragma unroll
-            for (uint32_t j = 1; j < 8; j++) v = ph == j ? b[j] : v;
-            dst[out + k] = v;
-            ph = ph + 1 == dist ? 0 : ph + 1;
-        }
-    }
-}
+/* Every lane runs this flat state machine; one trip through the loop does a bounded amount of work
+ * (one symbol, or 8 bytes of a match, or 16 bytes of a stored block), so no lane ever waits for
+ * another lane's long inner loop -- the only long state is the (rare) block header. */
+enum { LS_FETCH = 0, LS_HEADER, LS_DECODE, LS_COPY, LS_STORED, LS_FINISH, LS_EXIT };
 
 __global__ void __launch_bounds__(64) qzb_inflate_lanes_kernel(QzbDecompressJob job)
 {
@@ -232,57 +208,131 @@ __global__ void __launch_bounds__(64) qzb_inflate_lanes_kernel(QzbDecompressJob 
     InflLaneSmem &ws = reinterpret_cast<InflLaneSmem *>(smem_raw)[threadIdx.x];
     QzInflTables &T = ws.t;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t mi = blockIdx.x * blockDim.x + threadIdx.x; mi < job.nmembers; mi += stride) {
-        const QzbMember m = job.members[mi];
-        const uint8_t *src = job.src + m.src_off;
-        uint8_t *dst = job.dst + m.dst_off;
-        const uint32_t cap = m.dst_cap;
-        QzBitReader br;
-        qz_br_init(&br, src, m.src_len);
-        uint32_t out = 0, status = QZB_ST_OK, bfinal = 0;
-        while (!bfinal && status == QZB_ST_OK) {
+    uint32_t mi = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t state = LS_FETCH, status = QZB_ST_OK, bfinal = 0, out = 0, cap = 0, mlen = 0, mdist = 0, s_src = 0, s_rem = 0;
+    uint32_t exact_len = 0, exact_out = 0, src_len = 0;
+    const uint8_t *src = nullptr; uint8_t *dst = nullptr;
+    QzBitReader br; qz_br_init(&br, nullptr, 0);
+
+    /* all lanes stay in the loop until the whole warp is done and re-converge after every trip:
+     * without the explicit __syncwarp the 32 lanes drift apart and run one after another */
+    while (__any_sync(0xffffffffu, state != LS_EXIT)) {
+        if (state == LS_EXIT) { /* idle */ }
+        else if (state == LS_DECODE) {
+            qz_br_refill(&br);
+            const uint32_t e = T.ll_lut[br.acc & ((1u << QZ_LL_LUT_BITS) - 1)];
+            int sym;
+            if (e) { sym = (int)(e >> 4); br.acc >>= (e & 15); br.nacc -= (e & 15); }
+            else sym = qz_infl_slow(&br, T.ll_count, T.ll_sorted);
+            if (sym < 0) { status = QZB_ST_DATA_ERROR; state = LS_FINISH; }
+            else if (sym < 256) {
+                if (out >= cap) { status = QZB_ST_OUT_FULL; state = LS_FINISH; }
+                else dst[out++] = (uint8_t)sym;
+            } else if (sym == 256) state = bfinal ? LS_FINISH : LS_HEADER;
+            else {
+                sym -= 257;
+                uint32_t eb = 0, len = sym < 29 ? qz_len_base((uint32_t)sym, &eb) : 0;
+                if (br.nacc < 48) qz_br_refill(&br);
+                len += qz_br_bits(&br, eb);
+                const uint32_t de = T.d_lut[br.acc & ((1u << QZ_D_LUT_BITS) - 1)];
+                int ds;
+                if (de) { ds = (int)(de >> 4); br.acc >>= (de & 15); br.nacc -= (de & 15); }
+                else ds = qz_infl_slow(&br, T.d_count, T.d_sorted);
+                uint32_t dist = 0;
+                if (ds >= 0 && ds < 30) { dist = qz_dist_base((uint32_t)ds, &eb); dist += qz_br_bits(&br, eb); }
+                if (sym >= 29 || dist == 0 || dist > out) { status = QZB_ST_DATA_ERROR; state = LS_FINISH; }
+                else if (out + len > cap) { status = QZB_ST_OUT_FULL; state = LS_FINISH; }
+                else { mlen = len; mdist = dist; state = LS_COPY; }
+            }
+        } else if (state == LS_COPY) {
+            /* dst[out + j] = dst[out + j - mdist] for up to 8 bytes; all loads first (one L2 round trip) */
+            const uint8_t *from = dst + out - mdist;
+            const uint32_t m = mlen < 8 ? mlen : 8, span = mdist < 8 ? mdist : 8;
+            uint8_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, b6 = 0, b7 = 0;
+            if (0 < span) b0 = __ldcg(from + 0);
+            if (1 < span) b1 = __ldcg(from + 1);
+            if (2 < span) b2 = __ldcg(from + 2);
+            if (3 < span) b3 = __ldcg(from + 3);
+            if (4 < span) b4 = __ldcg(from + 4);
+            if (5 < span) b5 = __ldcg(from + 5);
+            if (6 < span) b6 = __ldcg(from + 6);
+            if (7 < span) b7 = __ldcg(from + 7);
+            if (mdist < 8) {      /* short period: later bytes repeat earlier ones */
+                if (mdist == 1) { b1 = b0; b2 = b0; b3 = b0; b4 = b0; b5 = b0; b6 = b0; b7 = b0; }
+                else if (mdist == 2) { b2 = b0; b3 = b1; b4 = b0; b5 = b1; b6 = b0; b7 = b1; }
+                else if (mdist == 3) { b3 = b0; b4 = b1; b5 = b2; b6 = b0; b7 = b1; }
+                else if (mdist == 4) { b4 = b0; b5 = b1; b6 = b2; b7 = b3; }
+                else if (mdist == 5) { b5 = b0; b6 = b1; b7 = b2; }
+                else if (mdist == 6) { b6 = b0; b7 = b1; }
+                else { b7 = b0; }
+            }
+            uint8_t *o = dst + out;
+            if (0 < m) o[0] = b0;
+            if (1 < m) o[1] = b1;
+            if (2 < m) o[2] = b2;
+            if (3 < m) o[3] = b3;
+            if (4 < m) o[4] = b4;
+            if (5 < m) o[5] = b5;
+            if (6 < m) o[6] = b6;
+            if (7 < m) o[7] = b7;
+            out += m; mlen -= m;
+            if (mlen == 0) state = LS_DECODE;
+        } else if (state == LS_STORED) {
+            const uint32_t m = s_rem < 16 ? s_rem : 16;
+            for (uint32_t j = 0; j < m; j++) dst[out + j] = src[s_src + j];
+            out += m; s_src += m; s_rem -= m;
+            if (s_rem == 0) { br.pos = s_src; br.acc = 0; br.nacc = 0; br.phantom = 0; state = bfinal ? LS_FINISH : LS_HEADER; }
+        } else if (state == LS_HEADER) {
             qz_br_refill(&br);
             bfinal = qz_br_bits(&br, 1);
             const uint32_t type = qz_br_bits(&br, 2);
-            if (type == 3) { status = QZB_ST_DATA_ERROR; break; }
-            if (type == 0) {
+            if (type == 3) { status = QZB_ST_DATA_ERROR; state = LS_FINISH; }
+            else if (type == 0) {
                 const uint32_t drop = br.nacc & 7; br.acc >>= drop; br.nacc -= drop;
                 qz_br_refill(&br);
                 const uint32_t len = qz_br_bits(&br, 16), nlen = qz_br_bits(&br, 16), start = qz_br_consumed(&br);
-                if ((len ^ 0xffffu) != nlen) { status = QZB_ST_DATA_ERROR; break; }
-                if (start + len > br.n) { status = QZB_ST_IN_TRUNC; break; }
-                if (out + len > cap) { status = QZB_ST_OUT_FULL; break; }
-                for (uint32_t i = 0; i < len; i++) dst[out + i] = src[start + i];
-                out += len;
-                br.pos = start + len; br.acc = 0; br.nacc = 0; br.phantom = 0;
-                continue;
+                if ((len ^ 0xffffu) != nlen) { status = QZB_ST_DATA_ERROR; state = LS_FINISH; }
+                else if (start + len > br.n) { status = QZB_ST_IN_TRUNC; state = LS_FINISH; }
+                else if (out + len > cap) { status = QZB_ST_OUT_FULL; state = LS_FINISH; }
+                else if (len == 0) { br.pos = start; br.acc = 0; br.nacc = 0; br.phantom = 0; state = bfinal ? LS_FINISH : LS_HEADER; }
+                else { s_src = start; s_rem = len; state = LS_STORED; }
+            } else {
+                uint32_t hlit = 288, hdist = 30; bool ok = true;
+                if (type == 1) qz_inflate_fixed_lens(&T);
+                else ok = qz_inflate_read_dynamic(&br, &T, &hlit, &hdist) == 0;
+                ok = ok && qz_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_sorted, ws.code_of) >= 0
+                        && qz_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_sorted, ws.code_of + 288) >= 0;
+                if (!ok) { status = QZB_ST_DATA_ERROR; state = LS_FINISH; }
+                else {
+                    for (uint32_t i = 0; i < (1u << QZ_LL_LUT_BITS); i++) T.ll_lut[i] = 0;
+                    for (uint32_t i = 0; i < (1u << QZ_D_LUT_BITS); i++) T.d_lut[i] = 0;
+                    qz_infl_fill_lut(T.lens, ws.code_of, (int)hlit, T.ll_lut, QZ_LL_LUT_BITS, 0, 1);
+                    qz_infl_fill_lut(T.lens + hlit, ws.code_of + 288, (int)hdist, T.d_lut, QZ_D_LUT_BITS, 0, 1);
+                    state = LS_DECODE;
+                }
             }
-            uint32_t hlit = 288, hdist = 30;
-            if (type == 1) qz_inflate_fixed_lens(&T);
-            else if (qz_inflate_read_dynamic(&br, &T, &hlit, &hdist) != 0) { status = QZB_ST_DATA_ERROR; break; }
-            if (qz_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_sorted, ws.code_of) < 0 ||
-                qz_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_sorted, ws.code_of + 288) < 0) { status = QZB_ST_DATA_ERROR; break; }
-            for (uint32_t i = 0; i < (1u << QZ_LL_LUT_BITS); i++) T.ll_lut[i] = 0;
-            for (uint32_t i = 0; i < (1u << QZ_D_LUT_BITS); i++) T.d_lut[i] = 0;
-            qz_infl_fill_lut(T.lens, ws.code_of, (int)hlit, T.ll_lut, QZ_LL_LUT_BITS, 0, 1);
-            qz_infl_fill_lut(T.lens + hlit, ws.code_of + 288, (int)hdist, T.d_lut, QZ_D_LUT_BITS, 0, 1);
-            for (;;) {
-                uint32_t mlen = 0, mdist = 0;
-                const int ev = qz_inflate_run(&br, &T, dst, &out, cap, &mlen, &mdist);
-                if (ev == QZI_MATCH) { lane_copy_match(dst, out, mlen, mdist); out += mlen; continue; }
-                if (ev == QZI_ERR_DATA) status = QZB_ST_DATA_ERROR;
-                else if (ev == QZI_ERR_FULL) status = QZB_ST_OUT_FULL;
-                break;
+        } else if (state == LS_FINISH) {
+            const uint32_t consumed = qz_br_consumed(&br);
+            if (status == QZB_ST_OK && qz_br_overrun(&br)) status = QZB_ST_IN_TRUNC;
+            if (status == QZB_ST_OK && (exact_len & 1) && consumed != src_len) status = QZB_ST_DATA_ERROR;
+            if (status == QZB_ST_OK && exact_out && out != cap) status = QZB_ST_SIZE;
+            QzbMemberResult r;
+            r.status = status; r.consumed = consumed; r.produced = out; r.cksum = 0; r.saw_final = bfinal;
+            r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            job.results[mi] = r;
+            mi += stride;
+            state = LS_FETCH;
+        } else {   /* LS_FETCH */
+            if (mi >= job.nmembers) state = LS_EXIT;
+            else {
+                const QzbMember m = job.members[mi];
+                src = job.src + m.src_off; dst = job.dst + m.dst_off; cap = m.dst_cap; src_len = m.src_len;
+                exact_len = m.exact_len; exact_out = m.exact_out;
+                qz_br_init(&br, src, m.src_len);
+                out = 0; status = QZB_ST_OK; bfinal = 0; state = LS_HEADER;
             }
         }
-        const uint32_t consumed = qz_br_consumed(&br);
-        if (status == QZB_ST_OK && qz_br_overrun(&br)) status = QZB_ST_IN_TRUNC;
-        if (status == QZB_ST_OK && (m.exact_len & 1) && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
-        if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
-        QzbMemberResult r;
-        r.status = status; r.consumed = consumed; r.produced = out; r.cksum = 0; r.saw_final = bfinal;
-        r.pad[0] = r.pad[1] = r.pad[2] = 0;
-        job.results[mi] = r;
+        __syncwarp();
     }
 }
 

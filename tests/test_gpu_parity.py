@@ -416,3 +416,68 @@ def test_mixed_member_sizes_like_config3(prod, ref, corpus):
         want += piece
         pos += n
     assert prod.decompress(blob, len(want) + 8, fmt=q.QZ_DEFLATE_GZIP, hw_buff_sz=262144) == want
+
+
+# ---------------------------------------------------------------------------- threads and the async entry points
+def test_concurrent_sessions(prod, port, data):
+    """API contract: thread-safe across sessions (reference run_perf_test.sh runs one session per thread)."""
+    import threading
+    errs = []
+
+    def work(t):
+        try:
+            fmt = ALL_FMTS[t % len(ALL_FMTS)]
+            d = pick(data, 700000 + 4099 * t, t)
+            for _ in range(3):
+                blob = prod.compress(d, fmt=fmt)
+                assert port.decompress(blob, fmt, len(d) + 8) == d
+                assert prod.decompress(blob, len(d) + 8, fmt=fmt) == d
+        except Exception as e:      # noqa: BLE001
+            errs.append((t, repr(e)))
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert not errs, errs
+
+
+class QzResult(C.Structure):   # reference include/qatzip.h QzResult_T
+    _fields_ = [("status", C.c_int), ("cb_tag", C.c_void_p), ("src_len", C.c_uint), ("dest_len", C.c_uint),
+                ("ext_rc", C.c_uint64), ("crc", C.c_void_p), ("extension_result", C.c_void_p)]
+
+
+def test_async_callbacks(prod, port, data):
+    """qzCompress2 / qzDecompress2 with a callback (reference test modes 28/29): requests complete in order,
+    the callback sees status and the consumed / produced lengths; NULL callback = synchronous call."""
+    import threading
+    CB = C.CFUNCTYPE(C.c_int, C.POINTER(QzResult))
+    L = prod.lib
+    L.qzCompress2.argtypes = [C.POINTER(q.QzSession), C.c_void_p, C.c_void_p, CB, C.POINTER(QzResult)]
+    L.qzDecompress2.argtypes = [C.POINTER(q.QzSession), C.c_void_p, C.c_void_p, CB, C.POINTER(QzResult)]
+    sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT)
+    done, order = threading.Semaphore(0), []
+
+    def on_done(res):
+        order.append(res.contents.cb_tag); done.release(); return 0
+    cb = CB(on_done)
+    n, reqs = 400000, []
+    for i in range(4):
+        d = pick(data, n, 31 * i)
+        src, dst, r = C.create_string_buffer(d, n), C.create_string_buffer(n + 65536), QzResult()
+        r.src_len, r.dest_len, r.cb_tag = n, n + 65536, i + 1
+        assert L.qzCompress2(C.byref(sess), src, dst, cb, C.byref(r)) == q.QZ_OK
+        reqs.append((d, src, dst, r))
+    for _ in reqs:
+        assert done.acquire(timeout=60)
+    assert order == [1, 2, 3, 4]
+    for d, src, dst, r in reqs:
+        assert r.status == q.QZ_OK and r.src_len == n
+        assert port.decompress(dst.raw[:r.dest_len], q.QZ_DEFLATE_GZIP_EXT, n + 8) == d
+    # async decompress of the first result, then the synchronous form (callback NULL)
+    d, src, dst, r = reqs[0]
+    back, r2 = C.create_string_buffer(n + 8), QzResult()
+    r2.src_len, r2.dest_len, r2.cb_tag = r.dest_len, n + 8, 9
+    assert L.qzDecompress2(C.byref(sess), dst, back, cb, C.byref(r2)) == q.QZ_OK
+    assert done.acquire(timeout=60) and r2.status == q.QZ_OK and back.raw[:r2.dest_len] == d
+    r3 = QzResult(); r3.src_len, r3.dest_len = n, n + 65536
+    assert L.qzCompress2(C.byref(sess), src, dst, CB(), C.byref(r3)) == q.QZ_OK and r3.status == q.QZ_OK and r3.src_len == n
+    assert L.qzCompress2(C.byref(sess), src, dst, cb, None) == q.QZ_PARAMS
+    prod.end_session(sess)          # drains and stops the completion thread
