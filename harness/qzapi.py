@@ -23,13 +23,14 @@ QZ_NO_HW, QZ_NOSW_NO_HW, QZ_NOT_SUPPORTED = 11, -101, -200
 # QzDataFormat_T (reference include/qatzip.h:235-245)
 QZ_DEFLATE_4B, QZ_DEFLATE_GZIP, QZ_DEFLATE_GZIP_EXT, QZ_DEFLATE_RAW = 0, 1, 2, 3
 FMT_LZ4 = 4  # harness-only tag: LZ4 is selected by the session type, not by data_fmt
+FMT_ZLIB = 5  # harness-only tag: zlib wire format = qzSetupSessionDeflateExt with zlib_format=1
 QZ_DEFLATE, QZ_LZ4 = 8, ord("4")
 QZ_DYNAMIC_HDR, QZ_STATIC_HDR = 0, 1
 QZ_DIR_COMPRESS, QZ_DIR_DECOMPRESS, QZ_DIR_BOTH = 0, 1, 2
 COMMON_MEM, PINNED_MEM = 0, 1
 
 FMT_NAMES = {QZ_DEFLATE_4B: "4B", QZ_DEFLATE_GZIP: "GZIP", QZ_DEFLATE_GZIP_EXT: "GZIP_EXT",
-             QZ_DEFLATE_RAW: "RAW", FMT_LZ4: "LZ4"}
+             QZ_DEFLATE_RAW: "RAW", FMT_LZ4: "LZ4", FMT_ZLIB: "ZLIB"}
 
 
 class QzSession(C.Structure):  # reference include/qatzip.h:676-687
@@ -145,8 +146,10 @@ class QzLib:
     # ---- sessions -------------------------------------------------------------------------
     def new_session(self, fmt=QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536, huffman=QZ_DYNAMIC_HDR,
                     sw_backup=1, strm_buff_sz=65536, input_sz_thrshold=1024, direction=QZ_DIR_BOTH,
-                    expect=QZ_OK, init=True):
+                    expect=QZ_OK, init=True, zlib_format=0, stop_at_stream_end=0):
         """qzInit + qzSetupSessionDeflate / qzSetupSessionLZ4 the way reference utils/qzip.c:449-477 does."""
+        if fmt == FMT_ZLIB:
+            fmt, zlib_format = QZ_DEFLATE_GZIP_EXT, 1
         sess = QzSession()
         if init:
             rc = self.lib.qzInit(C.byref(sess), sw_backup)
@@ -167,6 +170,15 @@ class QzLib:
         cp.sw_backup = sw_backup
         cp.input_sz_thrshold = input_sz_thrshold
         cp.direction = direction
+        if fmt != FMT_LZ4 and (zlib_format or stop_at_stream_end):
+            # reference include/qatzip.h:565-569: the Ext struct selects the zlib wire format / stop-at-stream-end
+            px = QzSessionParamsDeflateExt()
+            px.deflate_params = p
+            px.stop_decompression_stream_end = stop_at_stream_end
+            px.zlib_format = zlib_format
+            rc = self.lib.qzSetupSessionDeflateExt(C.byref(sess), C.byref(px))
+            assert rc == expect, f"qzSetupSessionDeflateExt rc={rc} expected {expect}"
+            return sess
         rc = (self.lib.qzSetupSessionLZ4 if fmt == FMT_LZ4 else self.lib.qzSetupSessionDeflate)(C.byref(sess), C.byref(p))
         assert rc == expect, f"qzSetupSession rc={rc} expected {expect}"
         return sess
@@ -243,6 +255,8 @@ class OraclePort:
         L.qzo_crc32_combine.restype = C.c_uint32
         L.qzo_xxh32.argtypes = [V, C.c_size_t, C.c_uint32]
         L.qzo_xxh32.restype = C.c_uint32
+        L.qzo_adler32.argtypes = [C.c_uint32, V, C.c_size_t]
+        L.qzo_adler32.restype = C.c_uint32
         L.qzo_compress.argtypes = [C.c_int, C.c_int, C.c_uint32, V, SP, V, SP, C.c_int, C.POINTER(C.c_uint32)]
         L.qzo_decompress.argtypes = [C.c_int, V, SP, V, SP]
         L.qzo_inflate_raw.argtypes = [V, C.c_size_t, V, C.c_size_t, SP, SP, C.c_int, C.POINTER(C.c_int)]
@@ -261,6 +275,10 @@ class OraclePort:
     def xxh32(self, data, seed=0):
         data = bytes(data)
         return self.lib.qzo_xxh32(data, len(data), seed)
+
+    def adler32(self, data, adler=1):
+        data = bytes(data)
+        return self.lib.qzo_adler32(adler, data, len(data))
 
     def compress(self, data, fmt, level=1, hw_buff_sz=65536, last=1, cap=None, want_crc=False):
         data = bytes(data)

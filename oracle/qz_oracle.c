@@ -37,7 +37,7 @@
 #define QZ_BUF_ERROR (-3)
 #define QZ_DATA_ERROR (-4)
 
-enum { FMT_4B = 0, FMT_GZIP = 1, FMT_GZIP_EXT = 2, FMT_RAW = 3, FMT_LZ4 = 4 };
+enum { FMT_4B = 0, FMT_GZIP = 1, FMT_GZIP_EXT = 2, FMT_RAW = 3, FMT_LZ4 = 4, FMT_ZLIB = 5 };
 
 static inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 static inline void wr32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
@@ -293,8 +293,20 @@ long qzo_lz4_block_decompress(const uint8_t *src, size_t n, uint8_t *dst, size_t
 }
 
 /* ------------------------------------------------------------------ framing (hardware-path layout) */
-static size_t hdr_sz(int fmt) { return fmt == FMT_GZIP_EXT ? 24 : fmt == FMT_GZIP ? 10 : fmt == FMT_4B ? 4 : fmt == FMT_LZ4 ? 15 : 0; }
-static size_t ftr_sz(int fmt) { return (fmt == FMT_GZIP_EXT || fmt == FMT_GZIP || fmt == FMT_LZ4) ? 8 : 0; }
+static size_t hdr_sz(int fmt) { return fmt == FMT_GZIP_EXT ? 24 : fmt == FMT_GZIP ? 10 : fmt == FMT_4B ? 4 : fmt == FMT_LZ4 ? 15 : fmt == FMT_ZLIB ? 2 : 0; }
+static size_t ftr_sz(int fmt) { return (fmt == FMT_GZIP_EXT || fmt == FMT_GZIP || fmt == FMT_LZ4) ? 8 : fmt == FMT_ZLIB ? 4 : 0; }
+
+/* Adler-32 (RFC 1950), the checksum of zlib-format sessions: reference src/qatzip_utils.c:277-283 */
+uint32_t qzo_adler32(uint32_t adler, const uint8_t *p, size_t n)
+{
+    uint32_t a = adler & 0xffff, b = adler >> 16;
+    while (n) {
+        size_t k = n < 5552 ? n : 5552; n -= k;
+        while (k--) { a += *p++; b += a; }
+        a %= 65521u; b %= 65521u;
+    }
+    return b << 16 | a;
+}
 
 /* reference src/qatzip_gzip.c:98-143 (gzip-ext / gzip / 4B), src/qatzip_lz4.c:104-132 (LZ4 frame) */
 static void gen_header(int fmt, uint8_t *p, uint32_t consumed, uint32_t produced)
@@ -306,6 +318,7 @@ static void gen_header(int fmt, uint8_t *p, uint32_t consumed, uint32_t produced
         memcpy(p, std, 10); p[3] = 4; p[10] = 12; p[11] = 0; p[12] = 'Q'; p[13] = 'Z'; p[14] = 8; p[15] = 0;
         wr32(p + 16, consumed); wr32(p + 20, produced); break;
     case FMT_4B: wr32(p, produced); break;
+    case FMT_ZLIB: p[0] = 0x78; p[1] = 0x9C; break;                /* reference src/qatzip_gzip.c:263-271 */
     case FMT_LZ4:
         wr32(p, 0x184D2204u); p[4] = 0x4C; p[5] = 0x40; wr32(p + 6, consumed); wr32(p + 10, 0);
         p[14] = (uint8_t)(qzo_xxh32(p + 4, 10, 0) >> 8); break;
@@ -317,6 +330,7 @@ static void gen_footer(int fmt, uint8_t *p, uint32_t checksum, uint32_t consumed
 {
     if (fmt == FMT_GZIP || fmt == FMT_GZIP_EXT) { wr32(p, checksum); wr32(p + 4, consumed); }
     else if (fmt == FMT_LZ4) { wr32(p, 0); wr32(p + 4, checksum); }
+    else if (fmt == FMT_ZLIB) { p[0] = (uint8_t)(checksum >> 24); p[1] = (uint8_t)(checksum >> 16); p[2] = (uint8_t)(checksum >> 8); p[3] = (uint8_t)checksum; }   /* htonl: src/qatzip_gzip.c:273-281 */
 }
 
 /* DEST_SZ: reference src/qatzip_internal.h:99 */
@@ -344,7 +358,7 @@ int qzo_compress(int fmt, int level, uint32_t hw_buff_sz, const uint8_t *src, si
                  size_t *dst_len, int last, uint32_t *crc)
 {
     size_t in = 0, out = 0, n = *src_len, cap = *dst_len; int rc = QZ_OK;
-    if (fmt < 0 || fmt > FMT_LZ4 || hw_buff_sz < 1024 || (hw_buff_sz & (hw_buff_sz - 1))) return QZ_PARAMS;
+    if (fmt < 0 || fmt > FMT_ZLIB || hw_buff_sz < 1024 || (hw_buff_sz & (hw_buff_sz - 1))) return QZ_PARAMS;
     uint8_t *tmp = (uint8_t *)malloc(dest_sz(hw_buff_sz) + 64);
     if (!tmp) return QZ_FAIL;
     do {
@@ -360,13 +374,13 @@ int qzo_compress(int fmt, int level, uint32_t hw_buff_sz, const uint8_t *src, si
             int final = (fmt != FMT_RAW) || (is_last_chunk && last);
             rc = deflate_chunk(src + in, send, tmp, dest_sz(hw_buff_sz), level, final, &produced);
             if (rc != QZ_OK) break;
-            cks = qzo_crc32(0, src + in, send);
+            cks = (fmt == FMT_ZLIB) ? qzo_adler32(1, src + in, send) : qzo_crc32(0, src + in, send);
         }
         if (out + hdr_sz(fmt) + produced + ftr_sz(fmt) > cap) { rc = QZ_BUF_ERROR; break; }
         gen_header(fmt, dst + out, (uint32_t)send, (uint32_t)produced); out += hdr_sz(fmt);
         memcpy(dst + out, tmp, produced); out += produced;
         gen_footer(fmt, dst + out, cks, (uint32_t)send); out += ftr_sz(fmt);
-        if (crc && fmt != FMT_LZ4) *crc = (*crc == 0) ? cks : qzo_crc32_combine(*crc, cks, send);
+        if (crc && fmt != FMT_LZ4 && fmt != FMT_ZLIB) *crc = (*crc == 0) ? cks : qzo_crc32_combine(*crc, cks, send);
         in += send;
     } while (in < n);
     free(tmp);
@@ -399,6 +413,16 @@ int qzo_decompress(int fmt, const uint8_t *src, size_t *src_len, uint8_t *dst, s
             if (h + consumed + 8 > avail) { rc = QZ_DATA_ERROR; break; }
             if (rd32(p + h + consumed) != qzo_crc32(0, dst + out, produced) || rd32(p + h + consumed + 4) != (uint32_t)produced) { rc = QZ_DATA_ERROR; break; }
             in += h + consumed + 8; out += produced;
+        } else if (fmt == FMT_ZLIB) {
+            /* header test: reference src/qatzip_gzip.c:283-306; trailer: big-endian Adler-32 */
+            if ((p[0] & 0x0f) != 8 || (p[0] >> 4) > 7 || (p[1] & 0x20) || ((unsigned)p[0] * 256 + p[1]) % 31) { rc = QZ_FAIL; break; }
+            r = qzo_inflate_raw(p + 2, avail - 2, dst + out, cap - out, &consumed, &produced, 0, &fin);
+            if (r == -2) { rc = QZ_BUF_ERROR; break; }
+            if (r) { rc = QZ_DATA_ERROR; break; }
+            if (2 + consumed + 4 > avail) { rc = QZ_DATA_ERROR; break; }
+            const uint8_t *f = p + 2 + consumed;
+            if (((uint32_t)f[0] << 24 | (uint32_t)f[1] << 16 | (uint32_t)f[2] << 8 | f[3]) != qzo_adler32(1, dst + out, produced)) { rc = QZ_DATA_ERROR; break; }
+            in += 2 + consumed + 4; out += produced;
         } else if (fmt == FMT_4B) {
             uint32_t blk = rd32(p);
             if (4 + (size_t)blk > avail) { rc = QZ_DATA_ERROR; break; }

@@ -24,6 +24,7 @@
 
 #define QZB_NUM_BUFF 32                 /* reference src/qatzip_internal.h:65 (req_cnt_thrshold ceiling) */
 #define QZB_FMT_INTERNAL_LZ4 4          /* internal data_fmt value for LZ4 frames (QzbFormat) */
+#define QZB_FMT_INTERNAL_ZLIB 5         /* DEFLATE_ZLIB: zlib_format=1 sessions (reference src/qatzip_internal.h:251) */
 
 /* ------------------------------------------------------------------ logging */
 static QzLogLevel_T g_log_level = LOG_WARNING;
@@ -197,10 +198,12 @@ extern "C" int qzGetDefaultsDeflateExt(QzSessionParamsDeflateExt_T *d)
 extern "C" int qzSetDefaultsDeflateExt(QzSessionParamsDeflateExt_T *d)
 {
     if (!d || check_params_deflate(&d->deflate_params) != QZ_OK) return QZ_PARAMS;
-    if (d->zlib_format) return QZ_PARAMS;       /* DEFLATE_ZLIB is outside this build's scope */
+    if (d->zlib_format > 1) return QZ_PARAMS;
     int rc = qzSetDefaultsDeflate(&d->deflate_params);
     std::lock_guard<std::mutex> g(g_defaults_lock);
     g_defaults.stop_decompression_stream_end = d->stop_decompression_stream_end;
+    /* reference src/qatzip_utils.c:725-728: zlib_format turns the internal format into DEFLATE_ZLIB */
+    g_defaults.zlib_format = d->zlib_format; if (d->zlib_format) g_defaults.data_fmt = QZB_FMT_INTERNAL_ZLIB;
     return rc;
 }
 extern "C" int qzGetDefaultsLZ4(QzSessionParamsLZ4_T *d)
@@ -292,11 +295,12 @@ extern "C" int qzSetupSessionDeflateExt(QzSession_T *sess, QzSessionParamsDeflat
     QzSessionParamsDeflateExt_T tmp;
     if (!params) { qzGetDefaultsDeflateExt(&tmp); params = &tmp; }
     if (check_params_deflate(&params->deflate_params) != QZ_OK) return QZ_PARAMS;
-    if (params->zlib_format) return QZ_UNSUPPORTED_FMT;                /* not in this build's scope */
+    if (params->zlib_format > 1) return QZ_PARAMS;
     QzbParams p = g_defaults;
     internal_from_common(&p, &params->deflate_params.common_params);
     p.huffman_hdr = params->deflate_params.huffman_hdr; p.data_fmt = fmt_to_internal(params->deflate_params.data_fmt);
-    p.stop_decompression_stream_end = params->stop_decompression_stream_end; p.zlib_format = 0;
+    p.stop_decompression_stream_end = params->stop_decompression_stream_end; p.zlib_format = params->zlib_format;
+    if (params->zlib_format) p.data_fmt = QZB_FMT_INTERNAL_ZLIB;       /* reference src/qatzip_utils.c:725-728 */
     return attach_session(sess, &p);
 }
 extern "C" int qzSetupSessionLZ4(QzSession_T *sess, QzSessionParamsLZ4_T *params)
@@ -367,7 +371,8 @@ static int ready_session(QzSession_T *sess, QzbSess **out)
     if (!sess->internal || sess->hw_session_stat == QZ_NONE) {
         int fmt;
         { std::lock_guard<std::mutex> g(g_defaults_lock); fmt = g_defaults.data_fmt; }
-        rc = (fmt == QZB_FMT_INTERNAL_LZ4) ? qzSetupSessionLZ4(sess, NULL) : qzSetupSessionDeflate(sess, NULL);
+        rc = (fmt == QZB_FMT_INTERNAL_LZ4) ? qzSetupSessionLZ4(sess, NULL)
+           : (fmt == QZB_FMT_INTERNAL_ZLIB) ? qzSetupSessionDeflateExt(sess, NULL) : qzSetupSessionDeflate(sess, NULL);
         if (rc != QZ_OK && rc != QZ_DUPLICATE) return rc;
     }
     QzbSess *s = (QzbSess *)sess->internal;

@@ -21,6 +21,7 @@
 #include "qz_kernels.cuh"
 #include "qz_huffman.h"
 #include "qz_crc32.h"
+#include "qz_adler32.h"
 
 #define FULL 0xffffffffu
 #define QZ_NONE16 0xffffu
@@ -100,15 +101,23 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
     return v;
 }
 
-/* sorted keys -> code lengths per symbol: split and scatter run across the warp, only the
- * in-place tree pass and the (rare) length cap run on lane 0 */
-__device__ __noinline__ void warp_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n, int maxbits, uint8_t *len_by_sym, uint32_t lane)
+/* sorted keys -> code lengths per symbol, for the literal/length and the distance alphabet at once:
+ * split and scatter run across the warp; the in-place tree pass and the (rare) length cap are serial,
+ * so lane 0 walks the literal/length tree while lane 1 walks the distance tree in lockstep */
+__device__ __noinline__ void warp_lengths_pair(uint32_t *keys, uint16_t *ids, int n, uint8_t *ll_len,
+                                               uint32_t *dkeys, uint16_t *dids, int nd, uint8_t *d_len, uint32_t lane)
 {
     for (int i = lane; i < n; i += 32) { uint32_t k = keys[i]; ids[i] = (uint16_t)(k & 511u); keys[i] = k >> 9; }
+    if ((int)lane < nd) { uint32_t k = dkeys[lane]; dids[lane] = (uint16_t)(k & 511u); dkeys[lane] = k >> 9; }
     __syncwarp();
-    if (lane == 0) { qz_huff_inplace_lengths(keys, n); qz_huff_limit_sorted(keys, n, maxbits); }
+    if (lane < 2) {
+        uint32_t *A = lane ? dkeys : keys; const int m = lane ? nd : n;
+        qz_huff_inplace_lengths(A, m);
+        qz_huff_limit_sorted(A, m, 15);
+    }
     __syncwarp();
-    for (int i = lane; i < n; i += 32) len_by_sym[ids[i]] = (uint8_t)keys[i];
+    for (int i = lane; i < n; i += 32) ll_len[ids[i]] = (uint8_t)keys[i];
+    if ((int)lane < nd) d_len[dids[lane]] = (uint8_t)dkeys[lane];
     __syncwarp();
 }
 
@@ -209,13 +218,27 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
         int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
         if (lo < 0) lo = 0;
-        uint32_t c = 0xffffffffu;
-        for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ piece[i]) & 0xff] ^ (c >> 8);
-        c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
+        uint32_t c;
+        if (job.fmt == QZB_FMT_ZLIB) {
+            /* Adler-32 sums of the strip (STRIP < NMAX: no reduction inside), joined up the same tree */
+            uint32_t s1 = 0, s2 = 0;
+            for (int i = lo; i < hi; i++) { s1 += piece[i]; s2 += s1; }
+            s2 %= QZ_ADLER_P;
+#pragma unroll 1
+            for (int lv = 0; lv < 5; lv++) {
+                const uint32_t o1 = __shfl_down_sync(FULL, s1, 1u << lv), o2 = __shfl_down_sync(FULL, s2, 1u << lv);
+                if ((lane & ((2u << lv) - 1)) == 0) qz_adler_join(&s1, &s2, o1, o2, (uint64_t)STRIP << lv);
+            }
+            c = qz_adler_pack(s1, s2);
+        } else {
+            c = 0xffffffffu;
+            for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ piece[i]) & 0xff] ^ (c >> 8);
+            c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
 #pragma unroll
-        for (int lv = 0; lv < 5; lv++) {
-            uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
-            if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
+            for (int lv = 0; lv < 5; lv++) {
+                uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
+                if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
+            }
         }
         if (lane == 0) job.piece_crc[g] = c;
     }
@@ -456,16 +479,17 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         }
         __syncwarp();
         warp_sort_keys(cs.keys, nk, lane);
-        warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.ll_len, lane);
-        /* distance alphabet */
+        /* distance alphabet: its 30 keys and ids borrow the (not yet planned) header area */
         {
+            uint32_t *dkeys = reinterpret_cast<uint32_t *>(cs.hdr.items);
+            uint16_t *dids = reinterpret_cast<uint16_t *>(cs.hdr.seq);
             uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
             uint32_t bal = __ballot_sync(FULL, f != 0);
-            if (f) cs.keys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
-            nk = __popc(bal);
+            if (f) dkeys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
+            const int nd = __popc(bal);
             __syncwarp();
-            warp_sort_keys(cs.keys, nk, lane);
-            warp_lengths_from_sorted(cs.keys, cs.ids, nk, 15, cs.d_len, lane);
+            warp_sort_keys(dkeys, nd, lane);
+            warp_lengths_pair(cs.keys, cs.ids, nk, cs.ll_len, dkeys, dids, nd, cs.d_len, lane);
         }
         /* cost of each block type */
         uint32_t dynb = 0, fixb = 0;
@@ -624,8 +648,8 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
  * Replaces doCompressOut's per-chunk header gen / payload memcpy / crc32_combine / footer gen
  * (reference src/qatzip.c:1699-1716, src/qatzip_gzip.c:98-143,228-237, src/qatzip_lz4.c:104-143). */
 
-__device__ __forceinline__ uint32_t qzb_hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : 0u; }
-__device__ __forceinline__ uint32_t qzb_ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : 0u; }
+__device__ __forceinline__ uint32_t qzb_hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : fmt == QZB_FMT_ZLIB ? 2u : 0u; }
+__device__ __forceinline__ uint32_t qzb_ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : fmt == QZB_FMT_ZLIB ? 4u : 0u; }
 
 __global__ void qzb_chunk_sizes_kernel(QzbCompressJob job)
 {
@@ -688,7 +712,16 @@ __global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
     if (threadIdx.x == 0) {
         uint32_t ck;
         if (job.fmt == QZB_FMT_LZ4) ck = job.chunk_cksum[c];      /* XXH32 written by the xxh kernel */
-        else {
+        else if (job.fmt == QZB_FMT_ZLIB) {
+            /* per-piece Adler sums -> chunk Adler-32 (reference footer: src/qatzip_gzip.c:273-281) */
+            uint32_t s1 = 0, s2 = 0;
+            for (uint32_t g = g0; g < g1; g++) {
+                const uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE), w = job.piece_crc[g];
+                qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, pn);
+            }
+            ck = qz_adler_finish(s1, s2, chunk_len);
+            job.chunk_cksum[c] = ck;
+        } else {
             ck = 0;
             for (uint32_t g = g0; g < g1; g++) {
                 uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE);
@@ -707,6 +740,7 @@ __global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
             d[4] = d[5] = d[6] = d[7] = 0; d[8] = 0; d[9] = 0xff;
             break;
         case QZB_FMT_4B: st32le(d, payload); break;
+        case QZB_FMT_ZLIB: d[0] = 0x78; d[1] = 0x9C; break;           /* reference src/qatzip_gzip.c:263-271 */
         case QZB_FMT_LZ4:
             st32le(d, 0x184D2204u); d[4] = 0x4C; d[5] = 0x40; st32le(d + 6, chunk_len); st32le(d + 10, 0);
             d[14] = (uint8_t)(qz_xxh32(d + 4, 10, 0) >> 8);
@@ -736,6 +770,7 @@ __global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
     if (threadIdx.x == 0 && fs) {
         uint8_t *f = d + hs + payload;
         if (job.fmt == QZB_FMT_LZ4) { st32le(f, 0); st32le(f + 4, s_cksum); }
+        else if (job.fmt == QZB_FMT_ZLIB) { f[0] = (uint8_t)(s_cksum >> 24); f[1] = (uint8_t)(s_cksum >> 16); f[2] = (uint8_t)(s_cksum >> 8); f[3] = (uint8_t)s_cksum; }
         else { st32le(f, s_cksum); st32le(f + 4, chunk_len); }
     }
 }

@@ -19,6 +19,7 @@
 #include "qz_engine.h"
 #include "qz_kernels.cuh"
 #include "qz_crc32.h"
+#include "qz_adler32.h"
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
@@ -74,6 +75,11 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
+    int fmb = env_int("QZB200_FIRST_MB", 4);
+    if (fmb < 1) fmb = 1;
+    if (fmb > mb) fmb = mb;
+    t->first_batch_bytes = (size_t)fmb << 20;
+    t->taper = env_int("QZB200_TAPER", 1);
 }
 
 /* ------------------------------------------------------------------ pinned registry */
@@ -209,8 +215,8 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
 }
 
 /* ------------------------------------------------------------------ compress */
-static uint32_t hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : 0u; }
-static uint32_t ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : 0u; }
+static uint32_t hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : fmt == QZB_FMT_ZLIB ? 2u : 0u; }
+static uint32_t ftr_sz(int fmt) { return (fmt == QZB_FMT_GZIP_EXT || fmt == QZB_FMT_GZIP || fmt == QZB_FMT_LZ4) ? 8u : fmt == QZB_FMT_ZLIB ? 4u : 0u; }
 
 struct MetaLayout { size_t piece_len, piece_crc, chunk_total, chunk_cksum, chunk_off, ticket, total; };
 static MetaLayout meta_layout(uint32_t npieces, uint32_t nchunks)
@@ -294,8 +300,18 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
 /* running CRC over `fit` consecutive chunks: crc(A||B) = crc(A)*x^(8|B|) + crc(B) with the
  * multiplier of a full chunk computed once per call (reference does one zlib crc32_combine per
  * chunk, src/qatzip.c:1707-1714, including its "0 restarts" rule) */
-static uint32_t fold_chunk_crcs(uint32_t crc, const uint32_t *ck, uint32_t fit, uint32_t chunk_sz, uint64_t batch_len, uint32_t xchunk)
+static uint32_t fold_chunk_crcs(int fmt, uint32_t crc, const uint32_t *ck, uint32_t fit, uint32_t chunk_sz, uint64_t batch_len, uint32_t xchunk)
 {
+    if (fmt == QZB_FMT_ZLIB) {
+        /* zlib sessions carry Adler-32 per chunk; the running value is the Adler-32 of everything
+         * consumed (the reference pushes Adler values through crc32_combine here, which is not a
+         * checksum of anything -- DESIGN.md section 4) */
+        for (uint32_t i = 0; i < fit; i++) {
+            const uint64_t clen = std::min<uint64_t>(chunk_sz, batch_len - (uint64_t)i * chunk_sz);
+            crc = (crc == 0) ? ck[i] : qz_adler32_combine(crc, ck[i], clen);
+        }
+        return crc;
+    }
     for (uint32_t i = 0; i < fit; i++) {
         const uint64_t clen = std::min<uint64_t>(chunk_sz, batch_len - (uint64_t)i * chunk_sz);
         if (crc == 0) crc = ck[i];
@@ -329,7 +345,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
             const uint32_t *ck = (const uint32_t *)((const uint8_t *)s.h_meta.p + align_up((size_t)(s.nchunks + 1) * 8, 16));
             uint32_t fit = 0;
             while (fit < s.nchunks && off[fit + 1] <= c->dst_cap - out) fit++;
-            if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(crc, ck, fit, c->chunk_sz, len, xchunk);
+            if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(c->fmt, crc, ck, fit, c->chunk_sz, len, xchunk);
             o->nchunks += fit;
             out += off[fit];
             if (fit < s.nchunks) { in += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; break; }
@@ -366,7 +382,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
             }
         }
         CK(cudaEventRecord(s.ev_d1, s.st));
-        if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
+        if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(c->fmt, crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
         CK(cudaStreamSynchronize(s.st));
         { float t = 0; cudaEventElapsedTime(&t, s.ev_h0, s.ev_k0); o->h2d_ms += t; cudaEventElapsedTime(&t, s.ev_d0, s.ev_d1); o->d2h_ms += t; }
         if (bytes && !c->dst_pinned) memcpy(c->dst + out, s.h_out.p, bytes);
@@ -381,15 +397,20 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
      * drained, so that while the host waits for it two younger batches are already queued. */
     constexpr int NS = QzbEngine::NSLOT;
     uint64_t next_drain = 0;
-    /* batch sizes ramp up 16, 32, 64 ... MiB: the first kernel starts after a short copy, and a call's
+    /* batch sizes ramp up 4, 8, 16 ... MiB: the first kernel starts after a short copy, and a call's
      * unavoidable fill/drain tail (calls are synchronous) stays small against its steady state */
     uint64_t in_off_next = 0;
     for (uint64_t b = 0; (in_off_next < c->src_len || b == 0) && !stop; b++) {
         Slot &s = e->slot[b % NS];
         while (next_drain + NS <= b) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
         if (stop) break;
-        const uint64_t ramp = std::max<uint64_t>(c->chunk_sz, (((uint64_t)16 << 20) << std::min<uint64_t>(b, 8)) / c->chunk_sz * c->chunk_sz);
-        const uint64_t in_off = in_off_next, len = std::min<uint64_t>(std::min(batch, ramp), c->src_len - in_off);
+        const uint64_t first = std::max<uint64_t>(c->chunk_sz, e->tune.first_batch_bytes / c->chunk_sz * c->chunk_sz);
+        const uint64_t ramp = first << std::min<uint64_t>(b, 10);
+        const uint64_t in_off = in_off_next, left = c->src_len - in_off;
+        uint64_t len = std::min<uint64_t>(std::min(batch, ramp), left);
+        /* ... and taper off again: no batch takes more than half of what is left, so the last kernel and
+         * the last copy back (nothing overlaps them) are short */
+        if (e->tune.taper && left > first) len = std::min<uint64_t>(len, std::max<uint64_t>(first, left / 2 / c->chunk_sz * c->chunk_sz));
         in_off_next = in_off + len;
         const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
         if (s.d_in.ensure(len + 64) != RC_OK || s.d_out.ensure((uint64_t)nch * per_chunk_out) != RC_OK) return RC_FAIL;
@@ -460,10 +481,12 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     const int grid_cap = e->sm_count * 8;
     uint64_t cur_in = 0, cur_out = 0;      /* everything before these offsets is decoded and delivered */
+    uint64_t zlib_window = std::max<uint64_t>(e->tune.batch_bytes * 2, (uint64_t)4 << 20);   /* span searched for zlib stream starts per round */
 
     /* one kernel launch over units[first, first+count); outputs either at their final offsets
      * (relative to out_base) or, when staged, in private regions of the slot's d_out */
     std::vector<ParsedMember> units;
+    bool size_only = false;                /* zlib member discovery: lengths only, nothing written */
     auto run = [&](Slot &s, size_t first, size_t count, uint64_t span_src, uint64_t span_len, uint64_t out_base, uint64_t out_len,
                    bool staged_out) -> int {
         const uint8_t *d_src; uint8_t *d_dst = nullptr;
@@ -483,7 +506,8 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         for (size_t i = 0; i < count; i++) {
             hm[i] = units[first + i].m;
             hm[i].src_off -= span_src;
-            if (staged_out) { hm[i].dst_off = stage_off; stage_off += align_up(hm[i].dst_cap, 16); }
+            if (size_only) hm[i].dst_off = 0;
+            else if (staged_out) { hm[i].dst_off = stage_off; stage_off += align_up(hm[i].dst_cap, 16); }
             else hm[i].dst_off -= out_base;
         }
         CK(cudaMemcpyAsync(s.d_members.p, hm, count * sizeof(QzbMember), cudaMemcpyHostToDevice, s.st));
@@ -491,7 +515,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         CK(cudaMemsetAsync(ticket, 0, 16, s.st));
         QzbDecompressJob job; memset(&job, 0, sizeof job);
         job.src = d_src; job.dst = d_dst; job.members = (const QzbMember *)s.d_members.p; job.results = (QzbMemberResult *)s.d_results.p;
-        job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket;
+        job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket; job.size_only = size_only ? 1 : 0;
         const int grid = (int)std::min<size_t>((count + 7) / 8, (size_t)grid_cap);
         CK(cudaEventRecord(s.ev_k0, s.st));
         /* many sized gzip members: one LANE per member (32 decoders per warp); otherwise one warp per member */
@@ -539,6 +563,68 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         units.clear();
         int parse_rc = RC_OK;
         uint64_t in = cur_in, out = cur_out;
+        if (c->fmt == QZB_FMT_ZLIB) {
+            /* A zlib stream carries neither its compressed nor its uncompressed size (the reference
+             * submits "everything that is left" and reads `consumed` back, src/qatzip_utils.c:1309-1315,
+             * one stream at a time).  Here every offset that passes the header test
+             * (src/qatzip_gzip.c:283-306) is decoded for LENGTHS ONLY in one launch; walking the
+             * (consumed, produced) links from the first stream yields the real members, which then go
+             * through the ordinary sized path with exact lengths and their Adler-32. */
+            uint64_t win = std::min<uint64_t>(c->src_len - cur_in, c->src_device ? 0xfffffff0ull : zlib_window);
+            const uint8_t *p = hsrc + cur_in;
+            auto hdr_ok = [&](uint64_t q) { return (p[q] & 0x0f) == 8 && (p[q] >> 4) <= 7 && !(p[q + 1] & 0x20) && ((uint32_t)p[q] * 256u + p[q + 1]) % 31u == 0; };
+            std::vector<uint64_t> cand;
+            if (win >= 2 && hdr_ok(0)) {
+                cand.push_back(0);
+                if (!c->stop_at_first) for (uint64_t q = 1; q + 6 <= win; q++) if (hdr_ok(q)) cand.push_back(q);
+            }
+            if (cand.empty()) { final_rc = (win < 2) ? RC_DATA_ERROR : RC_FAIL; break; }
+            for (uint64_t q : cand) {
+                ParsedMember u; memset(&u, 0, sizeof u);
+                u.unit_start = cur_in + q; u.m.src_off = cur_in + q + 2; u.m.src_len = (uint32_t)(win - q - 2); u.m.dst_cap = 0xfffffff0u;
+                units.push_back(u);
+            }
+            Slot &s0 = e->slot[0];
+            size_only = true;
+            const int rr = run(s0, 0, units.size(), cur_in, win, 0, 0, true);
+            size_only = false;
+            if (rr != RC_OK) return RC_FAIL;
+            s0.busy = false;
+            CK(cudaEventSynchronize(s0.ev_meta));
+            { float ms = 0; cudaEventElapsedTime(&ms, s0.ev_k0, s0.ev_k1); o->kernel_ms += ms; }
+            const QzbMemberResult *res = (const QzbMemberResult *)s0.h_results.p;
+            std::vector<ParsedMember> chain;
+            uint64_t pos = 0; bool need_more = false;
+            while (pos < win) {
+                auto it = std::lower_bound(cand.begin(), cand.end(), pos);
+                if (it == cand.end() || *it != pos) { if (win - pos < 2 || !hdr_ok(pos)) parse_rc = (win - pos < 2) ? RC_DATA_ERROR : RC_FAIL; else need_more = true; break; }
+                const QzbMemberResult &r = res[it - cand.begin()];
+                /* ran off the end of the window (the reader feeds zero bits there, so this can also surface as a data error) */
+                const uint64_t avail = win - pos - 2;
+                const bool cut = (r.status == QZB_ST_IN_TRUNC) || (r.status != QZB_ST_OK && r.status != QZB_ST_OUT_FULL && (uint64_t)r.consumed + 4 >= avail) ||
+                                 (r.status == QZB_ST_OK && (!r.saw_final || (uint64_t)r.consumed + 4 > avail));
+                if (cut) { if (cur_in + win < c->src_len) need_more = true; else parse_rc = RC_DATA_ERROR; break; }
+                if (r.status != QZB_ST_OK) { parse_rc = RC_DATA_ERROR; break; }
+                if ((uint64_t)r.produced > c->dst_cap - out) { parse_rc = RC_BUF_ERROR; break; }
+                const uint8_t *f = p + pos + 2 + r.consumed;
+                ParsedMember u; memset(&u, 0, sizeof u);
+                u.unit_start = cur_in + pos; u.hdr_len = 2; u.ftr_len = 4;
+                u.m.src_off = cur_in + pos + 2; u.m.src_len = r.consumed; u.m.exact_len = 1;
+                u.m.dst_off = out; u.m.dst_cap = r.produced; u.m.exact_out = 1;
+                u.m.expect_cksum = (uint32_t)f[0] << 24 | (uint32_t)f[1] << 16 | (uint32_t)f[2] << 8 | f[3]; u.m.check_cksum = 1; u.sized = true;
+                chain.push_back(u);
+                out += r.produced; pos += 2 + (uint64_t)r.consumed + 4;
+                if (c->stop_at_first) break;
+            }
+            if (chain.empty() && need_more) {
+                /* not even one whole stream inside the window: widen it */
+                if (c->src_device || zlib_window >= c->src_len - cur_in) { final_rc = RC_DATA_ERROR; break; }
+                zlib_window *= 4;
+                continue;
+            }
+            units.swap(chain);
+            in = c->src_len;                   /* skip the header walk below */
+        }
         while (in < c->src_len) {
             const uint8_t *p = hsrc + in; const uint64_t avail = c->src_len - in;
             ParsedMember u; memset(&u, 0, sizeof u); u.unit_start = in;

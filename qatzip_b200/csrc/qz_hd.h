@@ -14,7 +14,7 @@
 #endif
 
 /* wire/data formats handled by the kernels (superset of QzDataFormat_T: LZ4 is a session type) */
-enum QzbFormat { QZB_FMT_4B = 0, QZB_FMT_GZIP = 1, QZB_FMT_GZIP_EXT = 2, QZB_FMT_RAW = 3, QZB_FMT_LZ4 = 4 };
+enum QzbFormat { QZB_FMT_4B = 0, QZB_FMT_GZIP = 1, QZB_FMT_GZIP_EXT = 2, QZB_FMT_RAW = 3, QZB_FMT_LZ4 = 4, QZB_FMT_ZLIB = 5 };
 
 /* per-unit status words written by kernels */
 enum QzbStatus { QZB_ST_OK = 0, QZB_ST_DATA_ERROR = 1, QZB_ST_OUT_FULL = 2, QZB_ST_IN_TRUNC = 3, QZB_ST_CKSUM = 4, QZB_ST_SIZE = 5 };

@@ -137,6 +137,10 @@ QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return 
  * h->items / h->nitems / h->hlit / h->hdist must already be set. */
 QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
 {
+    /* every item costs its symbol's code plus that symbol's extra bits, so the header size follows from
+     * the counters alone (taken before two-code forcing adds symbols that are never written) */
+    uint32_t emitted[QZ_NUM_CL];
+    for (int k = 0; k < QZ_NUM_CL; k++) emitted[k] = cf[k];
     qz_huff_force_two(cf, QZ_NUM_CL);
     uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
     for (int k = 0; k < QZ_NUM_CL; k++) {
@@ -153,7 +157,7 @@ QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
     while (hclen > 4 && h->cl_len[ORDER[hclen - 1]] == 0) hclen--;
     h->hclen = hclen;
     uint32_t bits = 3 + 5 + 5 + 4 + 3 * hclen;
-    for (uint32_t k = 0; k < h->nitems; k++) bits += h->cl_len[h->items[k] & 31] + (h->items[k] >> 12);
+    for (int k = 0; k < QZ_NUM_CL; k++) bits += emitted[k] * (h->cl_len[k] + (k == 16 ? 2u : k == 17 ? 3u : k == 18 ? 7u : 0u));
     h->bits = bits;
 }
 

@@ -12,6 +12,7 @@
 #include "qz_kernels.cuh"
 #include "qz_inflate.h"
 #include "qz_crc32.h"
+#include "qz_adler32.h"
 
 #define FULL 0xffffffffu
 
@@ -44,6 +45,23 @@ __device__ uint32_t warp_crc32_global(const uint8_t *p, uint32_t n, const uint32
     return __shfl_sync(FULL, c, 0);
 }
 
+/* Adler-32 of dst[0..n) by the whole warp: same strips, sums joined as in qz_adler32.h */
+__device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t lane)
+{
+    const uint32_t S = n ? (n + 31) / 32 : 1;
+    int hi = (int)n - (int)((31 - lane) * S), lo = hi - (int)S;
+    if (lo < 0) lo = 0;
+    if (hi < lo) hi = lo;
+    uint32_t s1, s2;
+    qz_adler_block(p + lo, (uint32_t)(hi - lo), &s1, &s2);
+#pragma unroll 1
+    for (int lv = 0; lv < 5; lv++) {
+        const uint32_t o1 = __shfl_down_sync(FULL, s1, 1u << lv), o2 = __shfl_down_sync(FULL, s2, 1u << lv);
+        if ((lane & ((2u << lv) - 1)) == 0) qz_adler_join(&s1, &s2, o1, o2, (uint64_t)S << lv);
+    }
+    return __shfl_sync(FULL, qz_adler_finish(s1, s2, n), 0);
+}
+
 __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob job)
 {
     __shared__ InflWarpSmem s_w[8];
@@ -66,6 +84,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
         QzBitReader br;
         qz_br_init(&br, src, m.src_len);
         uint32_t out = 0, status = QZB_ST_OK, bfinal = 0;
+        const bool wr = !job.size_only;
 
         while (!bfinal && status == QZB_ST_OK) {
             uint32_t type = 0;
@@ -94,7 +113,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                 }
                 st = bcast(st); len = bcast(len); start = bcast(start);
                 if (st != QZB_ST_OK) { status = st; break; }
-                for (uint32_t i = lane; i < len; i += 32) dst[out + i] = src[start + i];
+                if (wr) for (uint32_t i = lane; i < len; i += 32) dst[out + i] = src[start + i];
                 out += len;
                 __syncwarp();
                 continue;
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                 const uint32_t o = out + incl - len;                       /* where this lane's token lands */
                 const uint32_t span = dist < len ? dist : len;               /* distinct source bytes actually read */
                 const bool dep = is_match && (o - dist + span > out);        /* reads output of this very batch */
-                if (lane < ntk) {
+                if (lane < ntk && wr) {
                     if (!is_match) dst[o] = (uint8_t)t;
                     else if (!dep) {
                         const uint8_t *from = dst + o - dist;
@@ -143,7 +162,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                         else { for (uint32_t k = 0; k < len; k++) dst[o + k] = __ldcg(from + k % dist); }
                     }
                 }
-                uint32_t depmask = __ballot_sync(FULL, dep);
+                uint32_t depmask = wr ? __ballot_sync(FULL, dep) : 0u;
                 __syncwarp();
                 while (depmask) {
                     const uint32_t j = __ffs(depmask) - 1; depmask &= depmask - 1;
@@ -167,9 +186,9 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
         if (status == QZB_ST_OK && m.exact_len && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
         if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
         uint32_t crc = 0;
-        if (status == QZB_ST_OK) {
+        if (status == QZB_ST_OK && wr) {
             __syncwarp();
-            crc = warp_crc32_global(dst, out, s_crc_tab, lane);
+            crc = (job.fmt == QZB_FMT_ZLIB) ? warp_adler32_global(dst, out, lane) : warp_crc32_global(dst, out, s_crc_tab, lane);
             if (m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
         }
         if (lane == 0) {

@@ -22,7 +22,7 @@ struct QzbCompressJob {
     uint8_t *slots;              /* npieces * slot_stride bytes, 16-byte aligned stride */
     uint32_t slot_stride;
     uint32_t *piece_len;         /* [npieces] bytes produced per piece */
-    uint32_t *piece_crc;         /* [npieces] CRC-32 (deflate formats) of the piece's input */
+    uint32_t *piece_crc;         /* [npieces] CRC-32 of the piece's input (zlib format: packed Adler sums) */
     uint32_t *tok_scratch;       /* [resident warps * PIECE] token scratch */
     uint32_t *ticket;            /* dynamic piece counter (zeroed before launch) */
     /* framing */
@@ -30,7 +30,7 @@ struct QzbCompressJob {
     uint64_t dst_cap;
     uint32_t *chunk_total;       /* [nchunks] header + payload + footer bytes */
     uint64_t *chunk_off;         /* [nchunks + 1] exclusive prefix of chunk_total */
-    uint32_t *chunk_cksum;       /* [nchunks] CRC-32 or XXH32 of the chunk's input */
+    uint32_t *chunk_cksum;       /* [nchunks] CRC-32, Adler-32 (zlib) or XXH32 of the chunk's input */
 };
 
 /* Decompress side: one unit = one gzip member / 4B block / raw stream / LZ4 frame. */
@@ -60,5 +60,6 @@ struct QzbDecompressJob {
     uint32_t nmembers;
     int32_t fmt;
     uint32_t *ticket;
+    int32_t size_only;           /* deflate: decode lengths only -- no output written, no checksum (member discovery) */
 };
 #endif

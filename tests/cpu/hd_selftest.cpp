@@ -13,6 +13,7 @@
 #include "../../qatzip_b200/csrc/qz_inflate.h"
 #include "../../qatzip_b200/csrc/qz_crc32.h"
 #include "../../qatzip_b200/csrc/qz_xxh32.h"
+#include "../../qatzip_b200/csrc/qz_adler32.h"
 
 static uint64_t rng_state = 88172645463325252ull;
 static uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (uint32_t)(rng_state >> 11); }
@@ -184,7 +185,18 @@ int main()
       for (int t = 0; t < 50; t++) { uint32_t cut = rnd() % d.size(); uint32_t a = crc32(0, d.data(), cut), b = crc32(0, d.data() + cut, d.size() - cut); CHECK(qz_crc32_combine(a, b, d.size() - cut) == c); }
       CHECK(qz_xxh32((const uint8_t *)"", 0, 0) == 0x02CC5D05u);
       CHECK(qz_xxh32((const uint8_t *)"a", 1, 0) == 0x550D7456u);
-      CHECK(qz_xxh32((const uint8_t *)"Nobody inspects the spammish repetition", 39, 0) == 0xE2293B2Fu); }
+      CHECK(qz_xxh32((const uint8_t *)"Nobody inspects the spammish repetition", 39, 0) == 0xE2293B2Fu);
+      // Adler-32: whole-buffer, pairwise combine, and the warp's right-aligned 32-strip tree
+      CHECK(qz_adler32(d.data(), 0) == 1u && qz_adler32(d.data(), d.size()) == adler32(1, d.data(), (uInt)d.size()));
+      for (int t = 0; t < 50; t++) { uint32_t cut = rnd() % d.size(); uint32_t a = adler32(1, d.data(), cut), b = adler32(1, d.data() + cut, (uInt)(d.size() - cut));
+                                     CHECK(qz_adler32_combine(a, b, d.size() - cut) == adler32(1, d.data(), (uInt)d.size())); }
+      for (uint32_t n : {0u, 1u, 31u, 32u, 33u, 259u, 8192u, 8191u, 65536u, 99999u}) {
+          const uint32_t S = n ? (n + 31) / 32 : 1; uint32_t s1[32], s2[32];
+          for (int lane = 0; lane < 32; lane++) { int hi = (int)n - (31 - lane) * (int)S, lo = hi - (int)S; if (lo < 0) lo = 0; if (hi < lo) hi = lo;
+                                                  qz_adler_block(d.data() + lo, (uint32_t)(hi - lo), &s1[lane], &s2[lane]); }
+          for (int lv = 0; lv < 5; lv++) for (int lane = 0; lane < 32; lane += (2 << lv)) qz_adler_join(&s1[lane], &s2[lane], s1[lane + (1 << lv)], s2[lane + (1 << lv)], (uint64_t)S << lv);
+          CHECK(qz_adler_finish(s1[0], s2[0], n) == adler32(1, d.data(), n));
+      } }
     // 3. huffman length limiting on adversarial (fibonacci) frequencies
     { uint32_t f[40]; f[0] = 1; f[1] = 1; for (int i = 2; i < 40; i++) f[i] = f[i - 1] + f[i - 2] > 30000 ? 30000 : f[i - 1] + f[i - 2];
       for (int n = 2; n <= 40; n++) { uint32_t keys[64]; uint16_t ids[64]; uint8_t len[64] = {0}; for (int i = 0; i < n; i++) keys[i] = QZ_HUFF_KEY(f[i], i); std::sort(keys, keys + n);

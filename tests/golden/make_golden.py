@@ -24,13 +24,13 @@ for name, data in inputs.items():
     open(os.path.join(HERE, name), "wb").write(data)
     lz = ref.compress(data, fmt=q.FMT_LZ4, hw_buff_sz=4096)
     xxh = int.from_bytes(lz[-4:], "little")          # content checksum written by liblz4 via the reference
-    for fmt in (q.QZ_DEFLATE_4B, q.QZ_DEFLATE_GZIP, q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW, q.FMT_LZ4):
+    for fmt in (q.QZ_DEFLATE_4B, q.QZ_DEFLATE_GZIP, q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW, q.FMT_LZ4, q.FMT_ZLIB):
         hw = 4096
         blob = ref.compress(data, fmt=fmt, hw_buff_sz=hw)
         sname = f"{name[:-4]}.{q.FMT_NAMES[fmt].lower()}"
         open(os.path.join(HERE, sname), "wb").write(blob)
         cases.append({"input": name, "stream": sname, "fmt": fmt, "hw_buff_sz": hw,
-                      "input_sha256": hashlib.sha256(data).hexdigest(), "crc32": zlib.crc32(data), "xxh32": xxh})
+                      "input_sha256": hashlib.sha256(data).hexdigest(), "crc32": zlib.crc32(data), "xxh32": xxh, "adler32": zlib.adler32(data)})
 json.dump({"generator": "tests/golden/make_golden.py", "reference": "intel/QATzip 1.3.1 software path (zlib 1.3, liblz4 1.9.4)",
            "cases": cases}, open(os.path.join(HERE, "manifest.json"), "w"), indent=1)
 print(len(cases), "cases")

@@ -22,7 +22,7 @@ from conftest import has_gpu
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")]
 
 DEFLATE_FMTS = [q.QZ_DEFLATE_4B, q.QZ_DEFLATE_GZIP, q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW]
-ALL_FMTS = DEFLATE_FMTS + [q.FMT_LZ4]
+ALL_FMTS = DEFLATE_FMTS + [q.FMT_LZ4, q.FMT_ZLIB]
 SIZES = [0, 1, 127, 1023, 1024, 4096, 8191, 8192, 8193, 65535, 65536, 65537, 524288, 1060921]
 
 
@@ -209,6 +209,71 @@ def test_stop_at_stream_end(prod, data):
     assert rc == q.QZ_OK and made == 65536 and bytes(out[:made]) == d[:65536]
     eos = C.c_ubyte(0)
     assert prod.lib.qzGetDeflateEndOfStream(C.byref(sess), C.byref(eos)) == q.QZ_OK and eos.value == 1
+    prod.end_session(sess)
+
+
+def test_zlib_format(prod, port, ref, data, monkeypatch):
+    """zlib_format=1 sessions (reference include/qatzip.h:565-569, src/qatzip_gzip.c:263-306): one RFC 1950
+    stream per chunk, readable by any zlib; decode finds the streams without size fields."""
+    d = pick(data, 3 * 1024 * 1024 + 777, 4)
+    blob = prod.compress(d, fmt=q.FMT_ZLIB)
+    out, rest, n = b"", blob, 0
+    while rest:
+        assert rest[:2] == b"\x78\x9c"
+        z = zlib.decompressobj()
+        out += z.decompress(rest)
+        assert z.eof
+        rest, n = z.unused_data, n + 1
+    assert out == d and n == (len(d) + 65535) // 65536
+    # running checksum of a zlib session is the Adler-32 of everything consumed
+    sess = prod.new_session(fmt=q.FMT_ZLIB)
+    dst = bytearray(len(d))
+    rc, used, made, ck = prod.compress_call(sess, d, len(d), dst, len(dst), crc=0)
+    assert rc == q.QZ_OK and ck == zlib.adler32(d)
+    prod.end_session(sess)
+    # streams made by zlib itself at other levels / window sizes, concatenated
+    parts = [pick(data, n, 7 * i) for i, n in enumerate((100000, 1, 70000, 300000))]
+    cat = b"".join(zlib.compress(p, lvl) for p, lvl in zip(parts, (1, 6, 9, 0)))
+    co = zlib.compressobj(6, zlib.DEFLATED, 9)
+    small = pick(data, 50000, 3)
+    cat += co.compress(small) + co.flush()
+    parts.append(small)
+    assert prod.decompress(cat, sum(map(len, parts)) + 8, fmt=q.FMT_ZLIB) == b"".join(parts)
+    # payload full of bytes that look like zlib headers: stored blocks of 78 9C 78 01 78 DA ...
+    noisy = (b"\x78\x9c\x78\x01\x78\xda\x78\x5e" * 8 + os.urandom(64)) * 4096
+    nb = prod.compress(noisy, fmt=q.FMT_ZLIB)
+    assert prod.decompress(nb, len(noisy) + 8, fmt=q.FMT_ZLIB) == noisy
+    assert ref.decompress(nb, len(noisy) + 8, fmt=q.FMT_ZLIB) == noisy
+    # several discovery windows (window follows the batch size) and a stream larger than one window
+    monkeypatch.setenv("QZB200_BATCH_MB", "1")
+    big = pick(data, 24 * 1024 * 1024, 1)
+    bb = prod.compress(big, fmt=q.FMT_ZLIB)
+    assert prod.decompress(bb, len(big) + 8, fmt=q.FMT_ZLIB) == big
+    one = zlib.compress(big, 1)                       # a single 10 MiB+ stream
+    assert prod.decompress(one + bb[:len(bb)], 2 * len(big) + 8, fmt=q.FMT_ZLIB) == big + big
+    monkeypatch.delenv("QZB200_BATCH_MB")
+    # errors: corrupted trailer, corrupted header, truncated tail (whole streams before it are delivered)
+    bad = bytearray(blob); bad[-1] ^= 0x55
+    sess = prod.new_session(fmt=q.FMT_ZLIB)
+    outb = bytearray(len(d) + 8)
+    rc, used, made = prod.decompress_call(sess, bytes(bad), len(bad), outb, len(outb))
+    assert rc == q.QZ_DATA_ERROR and made == (n - 1) * 65536 and bytes(outb[:made]) == d[:made]
+    bad = bytearray(blob); bad[0] = 0x79
+    rc, used, made = prod.decompress_call(sess, bytes(bad), len(bad), outb, len(outb))
+    assert rc == q.QZ_FAIL and used == 0 and made == 0
+    rc, used, made = prod.decompress_call(sess, blob[:-3], len(blob) - 3, outb, len(outb))
+    assert rc == q.QZ_DATA_ERROR and made == (n - 1) * 65536 and bytes(outb[:made]) == d[:made]
+    # too little room: whole streams that fit are delivered
+    rc, used, made = prod.decompress_call(sess, blob, len(blob), outb, 200000)
+    assert rc == q.QZ_BUF_ERROR and made == 3 * 65536 and bytes(outb[:made]) == d[:made]
+    prod.end_session(sess)
+    # stop_decompression_stream_end: one stream, end-of-stream flag set
+    sess = prod.new_session(fmt=q.FMT_ZLIB, stop_at_stream_end=1)
+    rc, used, made = prod.decompress_call(sess, blob, len(blob), outb, len(outb))
+    eos = C.c_ubyte(0)
+    assert rc == q.QZ_OK and made == 65536 and bytes(outb[:made]) == d[:65536]
+    assert prod.lib.qzGetDeflateEndOfStream(C.byref(sess), C.byref(eos)) == q.QZ_OK and eos.value == 1
+    assert blob[used:used + 2] == b"\x78\x9c"
     prod.end_session(sess)
 
 

@@ -16,7 +16,7 @@ from harness import qzapi as q
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SIZES = [0, 1, 127, 1023, 1024, 4096, 65535, 65536, 65537, 200001]
-FMTS = [q.QZ_DEFLATE_4B, q.QZ_DEFLATE_GZIP, q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW, q.FMT_LZ4]
+FMTS = [q.QZ_DEFLATE_4B, q.QZ_DEFLATE_GZIP, q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW, q.FMT_LZ4, q.FMT_ZLIB]
 
 
 def sample(corpus, n, kind=q.Corpus.SILESIA_LIKE, seg=0):
@@ -29,6 +29,23 @@ def test_crc32_and_combine(port, corpus):
     for cut in (0, 1, 1000, 65536, 299999, 300000):
         a, b = d[:cut], d[cut:]
         assert port.crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(d)
+
+
+def test_adler32_and_zlib_streams(port, corpus):
+    """zlib-format sessions: Adler-32 trailer, 78 9C header, one stream per chunk, and every stream is
+    what Python's zlib (RFC 1950) reads."""
+    d = sample(corpus, 300000)
+    assert port.adler32(b"") == 1 and port.adler32(d) == zlib.adler32(d)
+    blob = port.compress(d, q.FMT_ZLIB, hw_buff_sz=65536)
+    out, rest, n = b"", blob, 0
+    while rest:
+        assert rest[:2] == b"\x78\x9c"
+        z = zlib.decompressobj()
+        out += z.decompress(rest)
+        assert z.eof
+        rest = z.unused_data
+        n += 1
+    assert out == d and n == (len(d) + 65535) // 65536
 
 
 def test_xxh32_known_answers(port):
@@ -120,5 +137,5 @@ def test_golden_fixtures(port, ref):
         blob = open(os.path.join(GOLD, case["stream"]), "rb").read()
         assert hashlib.sha256(raw).hexdigest() == case["input_sha256"]
         assert port.decompress(blob, case["fmt"], len(raw) + 8) == raw
-        assert port.crc32(raw) == case["crc32"] and port.xxh32(raw) == case["xxh32"]
+        assert port.crc32(raw) == case["crc32"] and port.xxh32(raw) == case["xxh32"] and port.adler32(raw) == case["adler32"]
         assert ref.decompress(blob, len(raw) + 8, fmt=case["fmt"], hw_buff_sz=case["hw_buff_sz"]) == raw

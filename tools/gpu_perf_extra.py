@@ -17,7 +17,7 @@ res = {}
 # raw PCIe copy bandwidth with the same pinned pages (what bounds the end-to-end number)
 for nm, fn, a, b in (("h2d", L.qzb200CopyToDevice, d_in, h_in), ("d2h", L.qzb200CopyToHost, h_back, d_in)):
     fn(a, b, N); t0 = time.perf_counter(); fn(a, b, N); res["pcie_" + nm + "_GBps"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
-for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4)):
+for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4), ("zlib", q.FMT_ZLIB)):
     sess = prod.new_session(fmt=fmt)
     # compress each 512 MiB call into consecutive regions; remember sizes
     sizes, kms = [], 0.0
