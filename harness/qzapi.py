@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_SO = os.path.join(ROOT, "qatzip_b200", "libqatzip.so")
+PRODUCT_SO = os.environ.get("QZ_PRODUCT_SO") or os.path.join(ROOT, "qatzip_b200", "libqatzip.so")   # env: A/B builds on the GPU box
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "liboracle_qatzip.so")
 PORT_SO = os.path.join(ROOT, "oracle", "liboracle_port.so")
 CORPUS_SO = os.path.join(ROOT, "harness", "libqzcorpus.so")

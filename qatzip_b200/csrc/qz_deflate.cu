@@ -110,11 +110,15 @@ __device__ __noinline__ void warp_lengths_pair(uint32_t *keys, uint16_t *ids, in
     for (int i = lane; i < n; i += 32) { uint32_t k = keys[i]; ids[i] = (uint16_t)(k & 511u); keys[i] = k >> 9; }
     if ((int)lane < nd) { uint32_t k = dkeys[lane]; dids[lane] = (uint16_t)(k & 511u); dkeys[lane] = k >> 9; }
     __syncwarp();
+#ifdef QZ_MK_SERIAL      /* A/B switch: both trees on lane 0, one after the other */
+    if (lane == 0) { qz_huff_inplace_lengths(keys, n); qz_huff_limit_sorted(keys, n, 15); qz_huff_inplace_lengths(dkeys, nd); qz_huff_limit_sorted(dkeys, nd, 15); }
+#else
     if (lane < 2) {
         uint32_t *A = lane ? dkeys : keys; const int m = lane ? nd : n;
         qz_huff_inplace_lengths(A, m);
         qz_huff_limit_sorted(A, m, 15);
     }
+#endif
     __syncwarp();
     for (int i = lane; i < n; i += 32) ll_len[ids[i]] = (uint8_t)keys[i];
     if ((int)lane < nd) d_len[dids[lane]] = (uint8_t)dkeys[lane];

@@ -75,11 +75,15 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
-    int fmb = env_int("QZB200_FIRST_MB", 4);
+    int fmb = env_int("QZB200_FIRST_MB", 16);
     if (fmb < 1) fmb = 1;
     if (fmb > mb) fmb = mb;
     t->first_batch_bytes = (size_t)fmb << 20;
-    t->taper = env_int("QZB200_TAPER", 1);
+    t->taper = env_int("QZB200_TAPER", 0);
+    int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
+    if (wmb < 1) wmb = 1;
+    if (wmb > 2048) wmb = 2048;
+    t->zlib_window_bytes = (size_t)wmb << 20;
 }
 
 /* ------------------------------------------------------------------ pinned registry */
@@ -397,7 +401,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
      * drained, so that while the host waits for it two younger batches are already queued. */
     constexpr int NS = QzbEngine::NSLOT;
     uint64_t next_drain = 0;
-    /* batch sizes ramp up 4, 8, 16 ... MiB: the first kernel starts after a short copy, and a call's
+    /* batch sizes ramp up 16, 32, 64 ... MiB (QZB200_FIRST_MB, QZB200_BATCH_MB): the first kernel starts after a short copy, and a call's
      * unavoidable fill/drain tail (calls are synchronous) stays small against its steady state */
     uint64_t in_off_next = 0;
     for (uint64_t b = 0; (in_off_next < c->src_len || b == 0) && !stop; b++) {
@@ -408,8 +412,9 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         const uint64_t ramp = first << std::min<uint64_t>(b, 10);
         const uint64_t in_off = in_off_next, left = c->src_len - in_off;
         uint64_t len = std::min<uint64_t>(std::min(batch, ramp), left);
-        /* ... and taper off again: no batch takes more than half of what is left, so the last kernel and
-         * the last copy back (nothing overlaps them) are short */
+        /* optional taper (QZB200_TAPER=1): no batch takes more than half of what is left, so the last
+         * kernel and the last copy back are short.  Off by default: on B200 the extra batches cost more
+         * than the shorter tail saves (profiles/r01_e2e_batching.md) */
         if (e->tune.taper && left > first) len = std::min<uint64_t>(len, std::max<uint64_t>(first, left / 2 / c->chunk_sz * c->chunk_sz));
         in_off_next = in_off + len;
         const uint32_t nch = len ? (uint32_t)((len + c->chunk_sz - 1) / c->chunk_sz) : 1u;
@@ -481,7 +486,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     const int grid_cap = e->sm_count * 8;
     uint64_t cur_in = 0, cur_out = 0;      /* everything before these offsets is decoded and delivered */
-    uint64_t zlib_window = std::max<uint64_t>(e->tune.batch_bytes * 2, (uint64_t)4 << 20);   /* span searched for zlib stream starts per round */
+    uint64_t zlib_window = e->tune.zlib_window_bytes;       /* span searched for zlib stream starts per round */
 
     /* one kernel launch over units[first, first+count); outputs either at their final offsets
      * (relative to out_base) or, when staged, in private regions of the slot's d_out */
@@ -581,7 +586,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             if (cand.empty()) { final_rc = (win < 2) ? RC_DATA_ERROR : RC_FAIL; break; }
             for (uint64_t q : cand) {
                 ParsedMember u; memset(&u, 0, sizeof u);
-                u.unit_start = cur_in + q; u.m.src_off = cur_in + q + 2; u.m.src_len = (uint32_t)(win - q - 2); u.m.dst_cap = 0xfffffff0u;
+                u.unit_start = cur_in + q; u.m.src_off = cur_in + q + 2; u.m.src_len = (uint32_t)(win - q - 2); u.m.dst_cap = (uint32_t)std::min<uint64_t>(c->dst_cap - cur_out, 0xfffffff0ull);   /* more than fits cannot be delivered anyway */
                 units.push_back(u);
             }
             Slot &s0 = e->slot[0];
@@ -597,7 +602,15 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             uint64_t pos = 0; bool need_more = false;
             while (pos < win) {
                 auto it = std::lower_bound(cand.begin(), cand.end(), pos);
-                if (it == cand.end() || *it != pos) { if (win - pos < 2 || !hdr_ok(pos)) parse_rc = (win - pos < 2) ? RC_DATA_ERROR : RC_FAIL; else need_more = true; break; }
+                if (it == cand.end() || *it != pos) {
+                    /* too close to the window end to have been tried, or not a zlib header at all */
+                    const bool more_input = cur_in + win < c->src_len;
+                    if (win - pos < 2) { if (more_input) need_more = true; else parse_rc = RC_DATA_ERROR; }
+                    else if (!hdr_ok(pos)) parse_rc = RC_FAIL;
+                    else if (more_input) need_more = true;
+                    else parse_rc = RC_DATA_ERROR;
+                    break;
+                }
                 const QzbMemberResult &r = res[it - cand.begin()];
                 /* ran off the end of the window (the reader feeds zero bits there, so this can also surface as a data error) */
                 const uint64_t avail = win - pos - 2;
@@ -615,6 +628,14 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                 chain.push_back(u);
                 out += r.produced; pos += 2 + (uint64_t)r.consumed + 4;
                 if (c->stop_at_first) break;
+            }
+            if (getenv("QZB200_DEBUG")) {
+                const QzbMemberResult &r0 = res[0];
+                fprintf(stderr, "[qatzip_b200] zlib discovery at %llu: window %llu, %zu candidates, chain %zu, stopped at +%llu (need_more %d, rc %d); first: status %u consumed %u produced %u final %u\n",
+                        (unsigned long long)cur_in, (unsigned long long)win, cand.size(), chain.size(), (unsigned long long)pos, (int)need_more, parse_rc,
+                        r0.status, r0.consumed, r0.produced, r0.saw_final);
+                if (pos < win) { auto it = std::lower_bound(cand.begin(), cand.end(), pos); if (it != cand.end() && *it == pos) { const QzbMemberResult &r = res[it - cand.begin()];
+                    fprintf(stderr, "[qatzip_b200]   stopping candidate: status %u consumed %u produced %u final %u avail %llu\n", r.status, r.consumed, r.produced, r.saw_final, (unsigned long long)(win - pos - 2)); } }
             }
             if (chain.empty() && need_more) {
                 /* not even one whole stream inside the window: widen it */
@@ -751,7 +772,11 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     if (!c->dst_pinned) memcpy(c->dst + s.out_base, s.h_out.p, obytes);
                 }
                 if (good) { const ParsedMember &lu = units[s.first_member + good - 1]; cur_in = lu.unit_start + lu.hdr_len + lu.m.src_len + lu.ftr_len; cur_out = s.out_base + obytes; o->nmembers += (uint32_t)good; }
-                if (good < s.nmembers) { rc2 = status_rc(r[good], true); failed_unit = (long)(s.first_member + good); stop = true; }
+                if (good < s.nmembers) {
+                    rc2 = status_rc(r[good], true); failed_unit = (long)(s.first_member + good); stop = true;
+                    if (getenv("QZB200_DEBUG")) fprintf(stderr, "[qatzip_b200] member %ld failed: status %u consumed %u/%u produced %u/%u cksum %08x/%08x\n", failed_unit, r[good].status,
+                                                        r[good].consumed, units[(size_t)failed_unit].m.src_len, r[good].produced, units[(size_t)failed_unit].m.dst_cap, r[good].cksum, units[(size_t)failed_unit].m.expect_cksum);
+                }
                 return RC_OK;
             };
             constexpr int NS = QzbEngine::NSLOT;

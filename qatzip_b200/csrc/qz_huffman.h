@@ -139,8 +139,8 @@ QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
 {
     /* every item costs its symbol's code plus that symbol's extra bits, so the header size follows from
      * the counters alone (taken before two-code forcing adds symbols that are never written) */
-    uint32_t emitted[QZ_NUM_CL];
-    for (int k = 0; k < QZ_NUM_CL; k++) emitted[k] = cf[k];
+    uint32_t unused = 0;
+    for (int k = 0; k < QZ_NUM_CL; k++) unused |= (uint32_t)(cf[k] == 0) << k;
     qz_huff_force_two(cf, QZ_NUM_CL);
     uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
     for (int k = 0; k < QZ_NUM_CL; k++) {
@@ -157,7 +157,7 @@ QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
     while (hclen > 4 && h->cl_len[ORDER[hclen - 1]] == 0) hclen--;
     h->hclen = hclen;
     uint32_t bits = 3 + 5 + 5 + 4 + 3 * hclen;
-    for (int k = 0; k < QZ_NUM_CL; k++) bits += emitted[k] * (h->cl_len[k] + (k == 16 ? 2u : k == 17 ? 3u : k == 18 ? 7u : 0u));
+    for (int k = 0; k < QZ_NUM_CL; k++) if (!((unused >> k) & 1)) bits += cf[k] * (h->cl_len[k] + (k == 16 ? 2u : k == 17 ? 3u : k == 18 ? 7u : 0u));
     h->bits = bits;
 }
 

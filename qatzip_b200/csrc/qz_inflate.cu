@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                 if (ev == QZI_END_BLOCK) break;
                 if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; break; }
                 if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; break; }
+                if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; break; }
             }
         }
         /* verdict */

@@ -101,7 +101,7 @@ QZ_HD int qz_infl_slow(QzBitReader *b, const uint16_t *count, const uint16_t *so
 }
 
 /* events returned by qz_inflate_run */
-enum { QZI_MATCH = 0, QZI_END_BLOCK = 1, QZI_ERR_DATA = -1, QZI_ERR_FULL = -2 };
+enum { QZI_MATCH = 0, QZI_END_BLOCK = 1, QZI_ERR_DATA = -1, QZI_ERR_FULL = -2, QZI_ERR_TRUNC = -3 };
 
 /* Decode symbols of the current Huffman block: literals go straight to dst[*out], the loop
  * returns at the first back-reference (len/dist filled, NOT yet copied), at end-of-block, or
@@ -180,6 +180,9 @@ QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok
         tok[n++] = 0x80000000u | ((len - 3) << 16) | (dist - 1);
         o += len;
     }
+    /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
+     * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
+    if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
     *ntok = n; *pos = o;
     return ev;
 }

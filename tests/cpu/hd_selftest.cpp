@@ -146,6 +146,7 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
             if (ev == QZI_END_BLOCK) break;
             if (ev == QZI_ERR_DATA) return -1;
             if (ev == QZI_ERR_FULL) return -2;
+            if (ev == QZI_ERR_TRUNC) return -3;
         }
     }
     if (qz_br_overrun(&br)) return -3;

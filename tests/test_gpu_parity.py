@@ -244,14 +244,15 @@ def test_zlib_format(prod, port, ref, data, monkeypatch):
     nb = prod.compress(noisy, fmt=q.FMT_ZLIB)
     assert prod.decompress(nb, len(noisy) + 8, fmt=q.FMT_ZLIB) == noisy
     assert ref.decompress(nb, len(noisy) + 8, fmt=q.FMT_ZLIB) == noisy
-    # several discovery windows (window follows the batch size) and a stream larger than one window
-    monkeypatch.setenv("QZB200_BATCH_MB", "1")
-    big = pick(data, 24 * 1024 * 1024, 1)
+    # several discovery windows, a stream larger than one window, and streams cut by a window end
+    monkeypatch.setenv("QZB200_ZLIB_WINDOW_MB", "1")
+    big = pick(data, 6 * 1024 * 1024, 1)
     bb = prod.compress(big, fmt=q.FMT_ZLIB)
+    assert len(bb) > 2 << 20
     assert prod.decompress(bb, len(big) + 8, fmt=q.FMT_ZLIB) == big
-    one = zlib.compress(big, 1)                       # a single 10 MiB+ stream
-    assert prod.decompress(one + bb[:len(bb)], 2 * len(big) + 8, fmt=q.FMT_ZLIB) == big + big
-    monkeypatch.delenv("QZB200_BATCH_MB")
+    one = zlib.compress(big[:3 << 20], 0)             # one stream of stored blocks, three windows long
+    assert prod.decompress(bb[:len(bb)] + one + bb, 3 * len(big), fmt=q.FMT_ZLIB) == big + big[:3 << 20] + big
+    monkeypatch.delenv("QZB200_ZLIB_WINDOW_MB")
     # errors: corrupted trailer, corrupted header, truncated tail (whole streams before it are delivered)
     bad = bytearray(blob); bad[-1] ^= 0x55
     sess = prod.new_session(fmt=q.FMT_ZLIB)
