@@ -29,6 +29,25 @@
 #define QZ_MAX_MATCH 258
 #define QZ_STAGE_WORDS 64
 
+/* Per-phase cycle accounting for on-box diagnosis (A/B build only: make ab ABFLAGS=-DQZ_PHASE_CLOCKS).
+ * Lane 0 of every warp adds the cycles since its previous mark to a global counter per phase. */
+#ifdef QZ_PHASE_CLOCKS
+__device__ unsigned long long qz_phase_cycles[16];
+#define QZ_MARK(i) do { if (lane == 0) { long long now_ = clock64(); atomicAdd(&qz_phase_cycles[i], (unsigned long long)(now_ - tlast)); tlast = now_; } } while (0)
+#define QZ_TARG , long long &tlast
+#define QZ_TPASS , tlast
+extern "C" __attribute__((visibility("default"))) int qzb_phase_cycles_read(unsigned long long *out, int reset)
+{
+    if (cudaMemcpyFromSymbol(out, qz_phase_cycles, sizeof(qz_phase_cycles)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(qz_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define QZ_MARK(i) do { } while (0)
+#define QZ_TARG
+#define QZ_TPASS
+#endif
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -187,7 +206,7 @@ struct PieceState {
 
 template <int PIECE_LOG2, int HB>
 __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, WarpPriv<HB> &ws, uint32_t *toks,
-                                        const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps)
+                                        const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps QZ_TARG)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
@@ -246,6 +265,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         }
         if (lane == 0) job.piece_crc[g] = c;
     }
+    QZ_MARK(1);
 
     /* ---- phase 2: match + select + tokens ---- */
     uint32_t ntok = 0;
@@ -312,6 +332,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         }
     }
     __syncwarp();
+    QZ_MARK(2);
     ps.ntok = ntok;
     ps.extra_total = 0;
 }
@@ -427,7 +448,7 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
 
 template <int HB>
 __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, const uint16_t *s_lentab,
-                                        uint32_t lane, const PieceState &ps)
+                                        uint32_t lane, const PieceState &ps QZ_TARG)
 {
     const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
     const bool bfinal = ps.bfinal;
@@ -462,6 +483,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     }
     __syncwarp();
     const uint32_t extra_total = warp_sum(extra_acc);
+    QZ_MARK(3);
 
     /* ---- phase 3b: code construction ---- */
     uint32_t out_bytes = 0;
@@ -493,7 +515,9 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             const int nd = __popc(bal);
             __syncwarp();
             warp_sort_keys(dkeys, nd, lane);
+            QZ_MARK(4);
             warp_lengths_pair(cs.keys, cs.ids, nk, cs.ll_len, dkeys, dids, nd, cs.d_len, lane);
+            QZ_MARK(5);
         }
         /* cost of each block type */
         uint32_t dynb = 0, fixb = 0;
@@ -502,6 +526,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
         /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
         warp_plan_header(cs, cs.keys, lane);
+        QZ_MARK(6);
         dynb += cs.hdr.bits;
         const uint32_t storedb = (5 + n) * 8;
         if (job.static_huffman) dynb = 0xffffffffu;
@@ -546,6 +571,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         if (lane == 0) st[0] = pend;
         __syncwarp();
 
+        QZ_MARK(7);
         /* run-length coded code lengths of a dynamic header go through the same emitter */
         if (btype == 2) {
             const uint32_t nitems = cs.hdr.nitems;
@@ -597,6 +623,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     }
     if (lane == 0) job.piece_len[g] = out_bytes;
     __syncwarp();
+    QZ_MARK(8);
 }
 
 template <int PIECE_LOG2, int HB>
@@ -622,6 +649,9 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
     uint32_t *toks = job.tok_scratch + (size_t)gwarp * PIECE;
 
+#ifdef QZ_PHASE_CLOCKS
+    long long tlast = clock64();
+#endif
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(job.ticket, 1u);
@@ -639,11 +669,12 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
             __threadfence_block();
         }
         b = __shfl_sync(FULL, b, 0);
+        QZ_MARK(0);
         PieceState ps;
-        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps);
+        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicExch(&s_busy[b], 0u); }
-        phase34<HB>(job, ws, toks, s_lentab, lane, ps);
+        phase34<HB>(job, ws, toks, s_lentab, lane, ps QZ_TPASS);
     }
 }
 
