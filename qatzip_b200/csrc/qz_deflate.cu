@@ -272,36 +272,39 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
     const uint64_t pkeep = l2_policy_keep();
     {
         uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
+        const uint32_t sh = (lane & 3) * 8;  /* base is a multiple of 32: the byte phase of p is the lane's */
+        const uint32_t *piece_w = reinterpret_cast<const uint32_t *>(piece);
         for (uint32_t base = 0; base < n; base += 32) {
             if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
             const uint32_t p = base + lane;
-            const uint32_t v = ld32u(piece, p);
+            /* 12 bytes at p, straight-line: the three words every lane needs for verify + in-lane extension */
+            const uint32_t *pw = piece_w + (min(p, n) >> 2);
+            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2], w3 = pw[3];
+            const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
             const bool can = p + 4 <= n;
             const uint32_t h = (v * 2654435761u) >> (32 - HB);
             uint32_t cand = can ? ws.u.table[h] : QZ_NONE16;
             __syncwarp();
             if (can) ws.u.table[h] = (uint16_t)p;
             __syncwarp();
-            uint32_t L = 0;
-            const uint32_t maxl = min((uint32_t)QZ_MAX_MATCH, n - min(p, n));
-            if (cand != QZ_NONE16 && ld32u(piece, cand) == v) {
-                uint32_t l = 4;
-                while (l < QZ_LANE_CAP) {
-                    uint32_t x = ld32u(piece, p + l) ^ ld32u(piece, cand + l);
-                    if (x) { l += (__ffs(x) - 1) >> 3; break; }
-                    l += 4;
-                }
-                L = min(l, maxl);
-            }
+            /* candidate bytes are fetched unconditionally (slot 0 when there is none): no divergent
+             * verify/extend branches, all loads in flight together */
+            const bool has = cand != QZ_NONE16;
+            const uint32_t c = has ? cand : 0u, csh = (c & 3) * 8;
+            const uint32_t *cw = piece_w + (c >> 2);
+            const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
+            const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
+            uint32_t L = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : x2 ? 8 + ((__ffs(x2) - 1) >> 3) : (uint32_t)QZ_LANE_CAP;
+            L = min(L, min((uint32_t)QZ_MAX_MATCH, n - min(p, n)));
+            if (!has || x0) L = 0;
             const uint32_t valid = __ballot_sync(FULL, p < n);
             const uint32_t M = __ballot_sync(FULL, L >= 4);
-            uint32_t tokmask = 0, matchmask = 0, cur = entry;
+            uint32_t matchmask = 0, cur = entry;
             for (;;) {
-                uint32_t rest = M & (FULL << cur);
-                if (!rest) { tokmask |= (FULL << cur); cur = 32; break; }
-                uint32_t m = __ffs(rest) - 1;
-                tokmask |= (FULL << cur) & ~(FULL << m);      /* literals cur..m-1 */
-                tokmask |= 1u << m; matchmask |= 1u << m;
+                const uint32_t rest = M & (FULL << cur);
+                if (!rest) { cur = 32; break; }
+                const uint32_t m = __ffs(rest) - 1;
+                matchmask |= 1u << m;
                 uint32_t Lm = __shfl_sync(FULL, L, m);
                 if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
                     const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
@@ -320,12 +323,16 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
                 cur = m + Lm;
                 if (cur >= 32) break;
             }
+            /* positions covered by the match running in from the previous tile or by a selected match
+             * of this one carry no token: every selected lane marks (lane, lane + L), one warp OR joins them */
+            const bool sel = (matchmask >> lane) & 1;
+            const uint32_t mycov = sel ? (((FULL << lane) << 1) & ~(lane + L >= 32 ? 0u : FULL << (lane + L))) : 0u;
+            const uint32_t tokmask = ~(__reduce_or_sync(FULL, mycov) | ~(FULL << entry)) & valid;
             entry = cur - 32;
-            tokmask &= valid;
             if ((tokmask >> lane) & 1) {
                 /* raw token: literal byte, or match flag | (len - 3) << 16 | (dist - 1); symbols and
                  * histograms are derived in phase 3, off the piece buffer's critical path */
-                const uint32_t t = ((matchmask >> lane) & 1) ? (0x80000000u | ((L - 3) << 16) | (p - cand - 1)) : (v & 0xff);
+                const uint32_t t = sel ? (0x80000000u | ((L - 3) << 16) | (p - cand - 1)) : (v & 0xff);
                 tok_st(toks + ntok + __popc(tokmask & lanemask_lt()), t, pkeep);
             }
             ntok += __popc(tokmask);
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
     __shared__ uint16_t s_lentab[256];
-    __shared__ uint32_t s_busy[32];         /* one flag per piece buffer */
+    __shared__ uint32_t s_busy[1];          /* free mask of the piece buffers */
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
     WarpPriv<HB> &ws = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>))[warp];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (threadIdx.x < 32) s_busy[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;   /* bit b set = piece buffer b is free */
     __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
@@ -657,14 +664,20 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
         if (lane == 0) g = atomicAdd(job.ticket, 1u);
         g = __shfl_sync(FULL, g, 0);
         if (g >= job.npieces) break;
-        /* take a free piece buffer (lane 0 probes, starting at a warp-specific slot) */
+        /* take a free piece buffer: one bit per buffer in s_free; a warp that finds none sleeps with
+         * exponential back-off instead of spinning on the issue slots the working warps need */
         uint32_t b = 0;
         if (lane == 0) {
-            b = warp % (uint32_t)nbuf;
-            for (uint32_t tries = 0;; tries++) {
-                if (atomicCAS(&s_busy[b], 0u, 1u) == 0u) break;
-                if (++b == (uint32_t)nbuf) b = 0;
-                if ((tries % (uint32_t)nbuf) == (uint32_t)nbuf - 1) __nanosleep(200);
+            uint32_t ns = 128;
+            for (;;) {
+                const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&s_busy[0]);
+                if (m) {
+                    b = __ffs(m) - 1;
+                    if (atomicAnd(&s_busy[0], ~(1u << b)) & (1u << b)) break;
+                    continue;
+                }
+                __nanosleep(ns);
+                if (ns < 4096) ns <<= 1;
             }
             __threadfence_block();
         }
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
         PieceState ps;
         phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
         __syncwarp();
-        if (lane == 0) { __threadfence_block(); atomicExch(&s_busy[b], 0u); }
+        if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
         phase34<HB>(job, ws, toks, s_lentab, lane, ps QZ_TPASS);
     }
 }
