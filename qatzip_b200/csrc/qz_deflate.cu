@@ -61,6 +61,12 @@ __device__ __forceinline__ uint32_t tok_ld(const uint32_t *a, uint64_t pol)
 {
     uint32_t v; asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol) : "memory"); return v;
 }
+__device__ __forceinline__ uint4 tok_ld4(const uint32_t *a, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tok_st(uint32_t *a, uint32_t v, uint64_t pol)
 {
     asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
@@ -79,38 +85,52 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t *base, uint32_t off)
     return __funnelshift_r(w[0], w[1], (off & 3) * 8);
 }
 
-template <int N>
-__device__ __forceinline__ void warp_bitonic_sort(uint32_t *a, uint32_t lane)
+/* Warp bitonic sort of 32*K keys held K per lane (element e = lane * K + r): exchanges at distance
+ * >= K are shuffles, shorter ones stay inside the lane's registers. */
+template <int K>
+__device__ __forceinline__ void warp_sort_regs(uint32_t (&x)[K], uint32_t lane)
 {
 #pragma unroll 1
-    for (int k = 2; k <= N; k <<= 1) {
+    for (int k = 2; k <= 32 * K; k <<= 1) {
 #pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-            for (int i = lane; i < N; i += 32) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    uint32_t x = a[i], y = a[ixj];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        for (int j = k >> 1; j >= K; j >>= 1) {
+            const int m = j / K;
+            const bool lower = (lane & m) == 0;
+            const bool up = ((lane * K) & k) == 0;        /* j >= K => k > K: the direction bit lies in the lane part */
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                const uint32_t o = __shfl_xor_sync(FULL, x[r], m);
+                x[r] = (lower == up) ? min(x[r], o) : max(x[r], o);
+            }
+        }
+#pragma unroll
+        for (int j = K >> 1; j > 0; j >>= 1) {
+            if (j < k) {
+#pragma unroll
+                for (int r = 0; r < K; r++) {
+                    if ((r & j) == 0) {
+                        const bool up = (((lane * K + r) & k) == 0);
+                        const uint32_t a = x[r], c = x[r | j];
+                        const uint32_t mn = min(a, c), mx = max(a, c);
+                        x[r] = up ? mn : mx; x[r | j] = up ? mx : mn;
+                    }
                 }
             }
-            __syncwarp();
         }
     }
 }
-__device__ __noinline__ void warp_sort_keys(uint32_t *keys, int n, uint32_t lane)
+/* keys[0..n) (QZ_HUFF_KEY) -> ascending; written back split: freq[e] = frequency, ids[e] = symbol */
+template <int K>
+__device__ __noinline__ void warp_sort_split(const uint32_t *keys, int n, uint32_t *freq, uint16_t *ids, uint32_t lane)
 {
-    int N = 32; while (N < n) N <<= 1;
-    for (int i = n + lane; i < N; i += 32) keys[i] = 0xffffffffu;
+    uint32_t x[K];
+#pragma unroll
+    for (int r = 0; r < K; r++) { const int e = r * 32 + (int)lane; x[r] = e < n ? keys[e] : 0xffffffffu; }   /* any input order will do */
     __syncwarp();
-    switch (N) {
-    case 32: warp_bitonic_sort<32>(keys, lane); break;
-    case 64: warp_bitonic_sort<64>(keys, lane); break;
-    case 128: warp_bitonic_sort<128>(keys, lane); break;
-    case 256: warp_bitonic_sort<256>(keys, lane); break;
-    default: warp_bitonic_sort<512>(keys, lane); break;
-    }
+    warp_sort_regs<K>(x, lane);
+#pragma unroll
+    for (int r = 0; r < K; r++) { const int e = (int)lane * K + r; if (e < n) { freq[e] = x[r] >> 9; ids[e] = (uint16_t)(x[r] & 511u); } }
+    __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
@@ -120,24 +140,17 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
     return v;
 }
 
-/* sorted keys -> code lengths per symbol, for the literal/length and the distance alphabet at once:
- * split and scatter run across the warp; the in-place tree pass and the (rare) length cap are serial,
- * so lane 0 walks the literal/length tree while lane 1 walks the distance tree in lockstep */
-__device__ __noinline__ void warp_lengths_pair(uint32_t *keys, uint16_t *ids, int n, uint8_t *ll_len,
-                                               uint32_t *dkeys, uint16_t *dids, int nd, uint8_t *d_len, uint32_t lane)
+/* sorted frequencies -> code lengths per symbol, for the literal/length and the distance alphabet at once:
+ * the in-place tree pass and the (rare) length cap are serial, so lane 0 walks the literal/length tree
+ * while lane 1 walks the distance tree; the scatter back to symbol order runs across the warp */
+__device__ __noinline__ void warp_lengths_pair(uint32_t *keys, const uint16_t *ids, int n, uint8_t *ll_len,
+                                               uint32_t *dkeys, const uint16_t *dids, int nd, uint8_t *d_len, uint32_t lane)
 {
-    for (int i = lane; i < n; i += 32) { uint32_t k = keys[i]; ids[i] = (uint16_t)(k & 511u); keys[i] = k >> 9; }
-    if ((int)lane < nd) { uint32_t k = dkeys[lane]; dids[lane] = (uint16_t)(k & 511u); dkeys[lane] = k >> 9; }
-    __syncwarp();
-#ifdef QZ_MK_SERIAL      /* A/B switch: both trees on lane 0, one after the other */
-    if (lane == 0) { qz_huff_inplace_lengths(keys, n); qz_huff_limit_sorted(keys, n, 15); qz_huff_inplace_lengths(dkeys, nd); qz_huff_limit_sorted(dkeys, nd, 15); }
-#else
     if (lane < 2) {
         uint32_t *A = lane ? dkeys : keys; const int m = lane ? nd : n;
         qz_huff_inplace_lengths(A, m);
         qz_huff_limit_sorted(A, m, 15);
     }
-#endif
     __syncwarp();
     for (int i = lane; i < n; i += 32) ll_len[ids[i]] = (uint8_t)keys[i];
     if ((int)lane < nd) d_len[dids[lane]] = (uint8_t)dkeys[lane];
@@ -169,27 +182,29 @@ __device__ __noinline__ void warp_assign_codes(const uint8_t *len, int n, uint32
     }
 }
 
-/* scratch carved out of the (dead after phase 2) hash-table region */
+/* Everything phases 3-4 keep in shared memory lives where the hash table was (dead after phase 2):
+ * sort keys -> frequencies -> header-plan counters -> bit staging window, symbol ids, code lengths, the
+ * dynamic header, and the histograms that later become the code tables.  4000 B against the 4096 B
+ * of a 2^11-entry table, so a warp's private slice is exactly its hash table. */
 struct CodeScratch {
-    uint32_t keys[512];                 /* sort keys; later the bit staging window */
+    uint32_t keys[288];                 /* 286 sort keys at most; see above for its later lives */
     uint16_t ids[QZ_NUM_LL + 2];
     uint8_t ll_len[288];
     uint8_t d_len[32];
-    QzDynHeader hdr;
+    QzDynHeaderCore hdr;
 };
+#define QZ_HIST_WORDS (QZ_NUM_LL + 2 + QZ_NUM_D + 2)   /* [0,286) lit/len, [288,318) dist; later the code tables */
 
 /* Shared-memory plan.  The piece buffer (8 KiB) is needed only by phases 1-2; phases 3-4 work
  * from the token scratch and the warp's private tables.  So a CTA owns NB piece buffers and
  * NW > NB warps: a warp draws a ticket, takes any free buffer, runs phases 1-2, hands the buffer
- * back and finishes phases 3-4 without it.  With phases 1-2 about half of a piece's time,
- * NW = 2 * NB keeps every buffer busy and lifts residency from 16 to 24 warps per SM. */
+ * back and finishes phases 3-4 without it. */
 template <int HB>
 struct WarpPriv {
     union {
         uint16_t table[1 << HB];
-        CodeScratch cs;
+        struct { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; } b;
     } u;
-    uint32_t hist[QZ_NUM_LL + 2 + QZ_NUM_D + 2]; /* [0,286) lit/len, [288,318) dist; later the code tables */
 };
 template <int PIECE_LOG2>
 struct PieceBuf {
@@ -388,15 +403,15 @@ __device__ __forceinline__ uint16_t len_table_entry(uint32_t l /* len - 3 */)
 
 /* Warp-parallel version of qz_dyn_header_plan's run-length pass (RFC 1951 3.2.7): every run of
  * equal code lengths is handled by the lane sitting on its first element. */
-__device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 19 counters + 12 words */, uint32_t lane)
+__device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 19 counters + 12 words + 80 words of run-length scratch */, uint32_t lane)
 {
-    QzDynHeader &h = cs.hdr;
+    QzDynHeaderCore &h = cs.hdr;
     uint32_t bal = __ballot_sync(FULL, lane < 29 && cs.ll_len[257 + lane] != 0);
     const uint32_t hlit = 257 + (bal ? 32 - __clz(bal) : 0);
     bal = __ballot_sync(FULL, lane < QZ_NUM_D && cs.d_len[lane] != 0);
     const uint32_t hdist = bal ? 32 - __clz(bal) : 1;
     const uint32_t total = hlit + hdist, ngroups = (total + 31) >> 5;
-    uint8_t *seq = h.seq;
+    uint8_t *seq = reinterpret_cast<uint8_t *>(cf + 32);   /* 316 bytes of the dead sort-key space */
     uint32_t *heads = cf + 20;                    /* one head mask per group of 32 positions */
     if (lane < QZ_NUM_CL) cf[lane] = 0;
     for (uint32_t i = lane; i < total; i += 32) seq[i] = i < hlit ? cs.ll_len[i] : cs.d_len[i - hlit];
@@ -461,11 +476,11 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     const bool bfinal = ps.bfinal;
     uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
     uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
-    CodeScratch &cs = ws.u.cs;
+    CodeScratch &cs = ws.u.b.cs;
 
     /* ---- phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
      *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13) */
-    for (uint32_t i = lane; i < QZ_NUM_LL + 2 + QZ_NUM_D + 2; i += 32) ws.hist[i] = 0;
+    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) ws.u.b.hist[i] = 0;
     for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
     cs.d_len[lane] = 0;
     __syncwarp();
@@ -481,13 +496,14 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
                 const uint32_t ls = le & 31, leb = (le >> 5) & 7, lev = ((t >> 16) & 0xff) - (le >> 8);
                 uint32_t ds, de, dv;
                 qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
-                atomicAdd(&ws.hist[257 + ls], 1u);
-                atomicAdd(&ws.hist[QZ_DOFF + ds], 1u);
+                atomicAdd(&ws.u.b.hist[257 + ls], 1u);
+                atomicAdd(&ws.u.b.hist[QZ_DOFF + ds], 1u);
                 extra_acc += leb + de;
                 tok_st(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv, pkeep);
-            } else atomicAdd(&ws.hist[t], 1u);
+            } else atomicAdd(&ws.u.b.hist[t], 1u);
         }
     }
+    if (lane == 0) tok_st(toks + ntok, 256u, pkeep);      /* end-of-block rides along as the last token */
     __syncwarp();
     const uint32_t extra_total = warp_sum(extra_acc);
     QZ_MARK(3);
@@ -497,39 +513,42 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
     {
         if (lane == 0) {
-            ws.hist[256] = 1;
-            qz_huff_force_two(ws.hist, QZ_NUM_LL);
-            qz_huff_force_two(ws.hist + QZ_DOFF, QZ_NUM_D);
+            ws.u.b.hist[256] = 1;
+            qz_huff_force_two(ws.u.b.hist, QZ_NUM_LL);
+            qz_huff_force_two(ws.u.b.hist + QZ_DOFF, QZ_NUM_D);
         }
         __syncwarp();
         /* literal/length alphabet */
         int nk = 0;
         for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
-            uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.hist[s] : 0;
+            uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.u.b.hist[s] : 0;
             uint32_t bal = __ballot_sync(FULL, f != 0);
             if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
             nk += __popc(bal);
         }
         __syncwarp();
-        warp_sort_keys(cs.keys, nk, lane);
-        /* distance alphabet: its 30 keys and ids borrow the (not yet planned) header area */
+        /* sort in registers; frequencies land back in keys[], symbols in ids[] */
+        if (nk <= 128) warp_sort_split<4>(cs.keys, nk, cs.keys, cs.ids, lane);
+        else if (nk <= 256) warp_sort_split<8>(cs.keys, nk, cs.keys, cs.ids, lane);
+        else warp_sort_split<16>(cs.keys, nk, cs.keys, cs.ids, lane);
+        /* distance alphabet: one key per lane; its frequencies and ids borrow the (not yet planned) header area */
         {
             uint32_t *dkeys = reinterpret_cast<uint32_t *>(cs.hdr.items);
-            uint16_t *dids = reinterpret_cast<uint16_t *>(cs.hdr.seq);
-            uint32_t f = lane < QZ_NUM_D ? ws.hist[QZ_DOFF + lane] : 0;
-            uint32_t bal = __ballot_sync(FULL, f != 0);
-            if (f) dkeys[__popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, lane);
-            const int nd = __popc(bal);
+            uint16_t *dids = cs.hdr.items + 64;
+            const uint32_t f = lane < QZ_NUM_D ? ws.u.b.hist[QZ_DOFF + lane] : 0;
+            const int nd = __popc(__ballot_sync(FULL, f != 0));
+            uint32_t x[1] = { f ? QZ_HUFF_KEY(f, lane) : 0xffffffffu };
+            warp_sort_regs<1>(x, lane);
+            if ((int)lane < nd) { dkeys[lane] = x[0] >> 9; dids[lane] = (uint16_t)(x[0] & 511u); }
             __syncwarp();
-            warp_sort_keys(dkeys, nd, lane);
             QZ_MARK(4);
             warp_lengths_pair(cs.keys, cs.ids, nk, cs.ll_len, dkeys, dids, nd, cs.d_len, lane);
             QZ_MARK(5);
         }
         /* cost of each block type */
         uint32_t dynb = 0, fixb = 0;
-        for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
-        if (lane < QZ_NUM_D) { uint32_t f = ws.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
+        for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.u.b.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
+        if (lane < QZ_NUM_D) { uint32_t f = ws.u.b.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
         dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
         /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
         warp_plan_header(cs, cs.keys, lane);
@@ -546,7 +565,13 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
          * The bytes come from global memory again (the shared piece buffer already belongs to the
          * partner warp); incompressible pieces are the only ones that pay this second read. */
         if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
-        for (uint32_t i = lane; i < n; i += 32) slot[5 + i] = ps.src[i];
+        for (uint32_t i0 = lane; i0 < n; i0 += 256) {           /* eight loads in flight per lane */
+            uint8_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = i0 + 32 * k < n ? ps.src[i0 + 32 * k] : (uint8_t)0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (i0 + 32 * k < n) slot[5 + i0 + 32 * k] = v[k];
+        }
         out_bytes = 5 + n;
     } else {
         /* code tables go where the histograms were: code | len << 16 */
@@ -557,8 +582,8 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             cs.d_len[lane] = 5;
             __syncwarp();
         }
-        warp_assign_codes(cs.ll_len, 288, ws.hist, cs.keys, lane);
-        warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.hist + QZ_DOFF, cs.keys, lane);
+        warp_assign_codes(cs.ll_len, 288, ws.u.b.hist, cs.keys, lane);
+        warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.u.b.hist + QZ_DOFF, cs.keys, lane);
         uint32_t *clc = cs.keys + 40;                 /* code-length alphabet codes, 19 words */
         if (btype == 2) warp_assign_codes(cs.hdr.cl_len, QZ_NUM_CL, clc, cs.keys, lane);
         if (lane == 0) {
@@ -591,42 +616,84 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             }
         }
 
-        /* ---- phase 4: emit ---- */
-        uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;
-        for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
-            uint64_t bits = 0; uint32_t nb = 0;
-            const uint32_t t = tnext;
-            if (t0 + 32 + lane < ntok) tnext = tok_ld(toks + t0 + 32 + lane, pkeep);
-            if (t0 + lane < ntok) {
-                if (t & 0x80000000u) {
-                    const uint32_t ls = (t >> 26) & 31, lv = (t >> 21) & 31, ds = (t >> 16) & 31, dv = t & 0x1fff;
-                    const uint32_t le = (ls < 8 || ls == 28) ? 0u : (ls - 4) >> 2, de = ds < 4 ? 0u : (ds >> 1) - 1;
-                    const uint32_t lc = ws.hist[257 + ls], dc = ws.hist[QZ_DOFF + ds];
-                    bits = lc & 0xffff; nb = lc >> 16;
-                    bits |= (uint64_t)lv << nb; nb += le;
-                    bits |= (uint64_t)(dc & 0xffff) << nb; nb += dc >> 16;
-                    bits |= (uint64_t)dv << nb; nb += de;
-                } else {
-                    const uint32_t c = ws.hist[t];
-                    bits = c & 0xffff; nb = c >> 16;
+        /* ---- phase 4: emit ----
+         * Every lane codes a contiguous run of tokens: pass 1 adds up the run's bit length, a warp scan
+         * turns the lengths into bit offsets, pass 2 packs the run through a private 64-bit accumulator
+         * straight into the slot.  Words that hold a run boundary are zeroed first and receive their
+         * parts by atomic OR; every other word is written whole by exactly one lane.  The end-of-block
+         * code is the last token; the lane that owns it also appends the byte-alignment trailer. */
+        __syncwarp();
+        const uint32_t pend2 = st[0], hb = es.bitpos;
+        /* code table entries gain their extra-bit counts: code | len << 16 | extra << 24 */
+        if (lane < 29) ws.u.b.hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
+        if (lane < QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
+        if (lane >= QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
+        __syncwarp();
+        const uint32_t NT = ntok + 1;
+        const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
+        const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
+        uint32_t mybits = 0;
+        uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);   /* one group ahead: hides the L2 round trip */
+        for (uint32_t j = beg; j < end; j += 4) {
+            const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
+            if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (j + k < end) {
+                    const uint32_t t = tt[k];
+                    const bool isM = (t >> 31) != 0;
+                    const uint32_t c1 = ws.u.b.hist[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
+                    const uint32_t c2 = ws.u.b.hist[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
+                    mybits += ((c1 >> 16) & 0xff) + (c1 >> 24) + ((c2 >> 16) & 0xff) + (c2 >> 24);
                 }
             }
-            emit_group(st, slotw, es, bits, nb, lane);
         }
-        /* end-of-block, then byte alignment: final blocks pad, others append an empty stored block */
-        if (lane == 0) {
-            bw.words = slotw; bw.wpos = es.flushed; bw.acc = st[0]; bw.nacc = es.bitpos & 31;
-            const uint32_t eob = ws.hist[256];
-            qz_bw_put(&bw, eob & 0xffff, eob >> 16);
-            if (!bfinal) {
-                qz_bw_put(&bw, 0, 3);
-                qz_bw_align_byte(&bw);
-                qz_bw_put(&bw, 0x0000u, 16);
-                qz_bw_put(&bw, 0xffffu, 16);
+        uint32_t incl = mybits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        const uint32_t start = hb + incl - mybits;
+        const uint32_t end_bit = hb + __shfl_sync(FULL, incl, 31);
+        const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);                /* stored-block header + pad to a byte */
+        const uint32_t end_bit2 = bfinal ? end_bit : end_bit + nz + 32;
+        slotw[start >> 5] = 0;
+        if (lane == 31) slotw[end_bit2 >> 5] = 0;
+        __syncwarp();
+        {
+            uint64_t acc = lane == 0 ? (uint64_t)pend2 : 0ull;
+            uint32_t nacc = start & 31, wpos = start >> 5;
+            bool partial = lane != 0 && nacc != 0;
+#define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slotw[wpos] = (uint32_t)acc; \
+                                               acc >>= 32; nacc -= 32; wpos++; } } while (0)
+            qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);
+            for (uint32_t j = beg; j < end; j += 4) {
+                const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
+                if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (j + k < end) {
+                        const uint32_t t = tt[k];
+                        const bool isM = (t >> 31) != 0;
+                        const uint32_t c1 = ws.u.b.hist[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
+                        const uint32_t c2 = ws.u.b.hist[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
+                        const uint32_t l1 = (c1 >> 16) & 0xff, l2 = (c2 >> 16) & 0xff;
+                        const uint32_t lv = isM ? (t >> 21) & 31 : 0u, dv = isM ? t & 0x1fff : 0u;
+                        acc |= (uint64_t)((c1 & 0xffff) | (lv << l1)) << nacc; nacc += l1 + (c1 >> 24);
+                        QZ_EMIT_FLUSH();
+                        acc |= (uint64_t)((c2 & 0xffff) | (dv << l2)) << nacc; nacc += l2 + (c2 >> 24);
+                        QZ_EMIT_FLUSH();
+                    }
+                }
             }
-            out_bytes = qz_bw_finish(&bw);
+            if (!bfinal && beg < NT && end == NT) {          /* owner of the end-of-block token: empty stored block */
+                nacc += nz; QZ_EMIT_FLUSH();
+                nacc += 16; QZ_EMIT_FLUSH();
+                acc |= (uint64_t)0xffffu << nacc; nacc += 16; QZ_EMIT_FLUSH();
+            }
+            if ((uint32_t)acc) atomicOr(slotw + wpos, (uint32_t)acc);
+#undef QZ_EMIT_FLUSH
         }
-        out_bytes = __shfl_sync(FULL, out_bytes, 0);
+        out_bytes = (end_bit2 + 7) >> 3;
+        __syncwarp();
     }
     if (lane == 0) job.piece_len[g] = out_bytes;
     __syncwarp();
@@ -637,7 +704,7 @@ template <int PIECE_LOG2, int HB>
 __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    static_assert(sizeof(CodeScratch) <= (sizeof(uint16_t) << HB), "code scratch must fit in the hash table");
+    static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
@@ -654,7 +721,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
     __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint32_t *toks = job.tok_scratch + (size_t)gwarp * PIECE;
+    uint32_t *toks = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
 
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();

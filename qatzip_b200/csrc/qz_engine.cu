@@ -264,7 +264,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
     } else {
-        if (warps <= 0 || warps > 32) { warps = 22; if (nbuf <= 0) nbuf = 13; }    /* measured best split of the 227 KB */
+        if (warps <= 0 || warps > 32) { warps = 20; if (nbuf <= 0) nbuf = 17; }    /* measured best split of the 227 KB (tools/gpu_geom.py sweep) */
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
@@ -277,7 +277,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((size_t)grid * warps * PIECE * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((size_t)grid * warps * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);

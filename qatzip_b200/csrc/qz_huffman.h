@@ -122,20 +122,24 @@ QZ_HD_SERIAL void qz_huff_codes(const uint8_t *len, int n, uint32_t *out)
 }
 
 /* ---- dynamic block header (RFC 1951 3.2.7) ---- */
-struct QzDynHeader {
+struct QzDynHeaderCore {
     uint16_t items[QZ_NUM_LL + QZ_NUM_D];   /* sym | extra_value << 5 | extra_bits_count << 12 */
-    uint8_t seq[QZ_NUM_LL + QZ_NUM_D + 4];  /* scratch: the code lengths being run-length coded */
     uint32_t nitems;
     uint32_t hlit, hdist, hclen;
     uint8_t cl_len[QZ_NUM_CL];
     uint32_t bits;                          /* total header bits including the 3-bit block header */
+};
+/* the serial planner keeps its run-length scratch inside the header; the kernel's warp-parallel planner
+ * borrows (dead) sort-key space instead and only carries the core */
+struct QzDynHeader : QzDynHeaderCore {
+    uint8_t seq[QZ_NUM_LL + QZ_NUM_D + 4];  /* scratch: the code lengths being run-length coded */
 };
 
 QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return (uint16_t)(sym | (eval << 5) | (ebits << 12)); }
 
 /* Code-length alphabet (<= 19 symbols, 7-bit cap) from its frequencies cf[]; sizes the header.
  * h->items / h->nitems / h->hlit / h->hdist must already be set. */
-QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeader *h)
+QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeaderCore *h)
 {
     /* every item costs its symbol's code plus that symbol's extra bits, so the header size follows from
      * the counters alone (taken before two-code forcing adds symbols that are never written) */
@@ -195,7 +199,7 @@ QZ_HD_SERIAL void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len
 }
 
 /* the fixed part of a dynamic block header: BFINAL/BTYPE, HLIT, HDIST, HCLEN and the 3-bit lengths */
-QZ_HD_SERIAL void qz_dyn_header_write_prefix(QzBitWriter *bw, const QzDynHeader *h, int bfinal)
+QZ_HD_SERIAL void qz_dyn_header_write_prefix(QzBitWriter *bw, const QzDynHeaderCore *h, int bfinal)
 {
     const uint8_t ORDER[QZ_NUM_CL] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
     qz_bw_put(bw, (uint32_t)(bfinal ? 1 : 0) | (2u << 1), 3);

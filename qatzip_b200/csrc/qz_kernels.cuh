@@ -9,6 +9,10 @@
  * member / 4B block / LZ4 frame, reference src/qatzip.c:1513-1594).  A *piece* is the device's
  * unit: PIECE bytes of a chunk compressed by one warp into a byte-aligned run of deflate blocks
  * (or one LZ4 block).  Pieces of a chunk are laid end to end by the framing kernel. */
+/* words of token scratch per resident warp: one per input byte, the end-of-block token, and room for
+ * the 16-byte loads of the emit pass to run past the last token */
+#define QZB_TOK_STRIDE(piece) ((piece) + 32)
+
 struct QzbCompressJob {
     const uint8_t *src;          /* device, batch input */
     uint64_t src_len;
@@ -23,7 +27,7 @@ struct QzbCompressJob {
     uint32_t slot_stride;
     uint32_t *piece_len;         /* [npieces] bytes produced per piece */
     uint32_t *piece_crc;         /* [npieces] CRC-32 of the piece's input (zlib format: packed Adler sums) */
-    uint32_t *tok_scratch;       /* [resident warps * PIECE] token scratch */
+    uint32_t *tok_scratch;       /* [resident warps * QZB_TOK_STRIDE(PIECE)] token scratch */
     uint32_t *ticket;            /* dynamic piece counter (zeroed before launch) */
     /* framing */
     uint8_t *dst;                /* device, batch output */

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(512) qzb_lz4_pieces_kernel(QzbCompressJob job)
     WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
     /* match records: two words each (pos | len << 16, dist) */
-    uint32_t *recs = job.tok_scratch + (size_t)gwarp * PIECE;
+    uint32_t *recs = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
 
     for (;;) {
         uint32_t g = 0;
