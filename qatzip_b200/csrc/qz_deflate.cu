@@ -140,15 +140,51 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
     return v;
 }
 
+/* Pass 3 of the in-place Huffman construction across the warp.  A[0..n-1) holds the depths of the
+ * internal nodes, non-increasing with the index.  Lane d counts the internal nodes at depth d by two
+ * binary searches' worth of work (one, plus its neighbour's by shuffle); a level with I internal nodes
+ * offers 2 I places to the next one, and what the next level's internal nodes leave over are leaves.
+ * Leaves are handed out from the top of A (most frequent symbol, smallest depth) downwards.
+ * Returns false when the tree is deeper than 30 levels (caller falls back to the serial pass). */
+__device__ __forceinline__ bool warp_leaf_depths(uint32_t *A, int n, uint32_t lane)
+{
+    const int ni = n - 1;
+    /* c(d) = number of internal nodes with depth >= d = first index whose depth is < d */
+    int lo = 0, hi = ni;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (A[mid] >= lane) lo = mid + 1; else hi = mid; }
+    const int c_ge = lo;
+    const int c_next = __shfl_down_sync(FULL, c_ge, 1);
+    if (__shfl_sync(FULL, c_ge, 31) != 0) return false;
+    const int I = c_ge - (lane == 31 ? 0 : c_next);
+    const int Iprev = __shfl_up_sync(FULL, I, 1);
+    const int Lf = (lane == 0 ? 1 : 2 * Iprev) - I;                  /* leaves at depth = lane */
+    int incl = Lf;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+    __syncwarp();
+    uint32_t levels = __ballot_sync(FULL, Lf > 0);
+    while (levels) {
+        const int d = __ffs(levels) - 1; levels &= levels - 1;
+        const int cnt = __shfl_sync(FULL, Lf, d), top = n - (__shfl_sync(FULL, incl, d) - cnt);
+        for (int i = lane; i < cnt; i += 32) A[top - 1 - i] = (uint32_t)d;
+    }
+    __syncwarp();
+    return true;
+}
+
 /* sorted frequencies -> code lengths per symbol, for the literal/length and the distance alphabet at once:
- * the in-place tree pass and the (rare) length cap are serial, so lane 0 walks the literal/length tree
- * while lane 1 walks the distance tree; the scatter back to symbol order runs across the warp */
+ * the tree passes are serial, so lane 0 walks the literal/length tree while lane 1 walks the distance
+ * tree; leaf depths, and the scatter back to symbol order, run across the warp */
 __device__ __noinline__ void warp_lengths_pair(uint32_t *keys, const uint16_t *ids, int n, uint8_t *ll_len,
                                                uint32_t *dkeys, const uint16_t *dids, int nd, uint8_t *d_len, uint32_t lane)
 {
+    if (lane < 2) qz_huff_inplace_depths(lane ? dkeys : keys, lane ? nd : n);
+    __syncwarp();
+    const bool ok_ll = warp_leaf_depths(keys, n, lane);
+    const bool ok_d = warp_leaf_depths(dkeys, nd, lane);
     if (lane < 2) {
         uint32_t *A = lane ? dkeys : keys; const int m = lane ? nd : n;
-        qz_huff_inplace_lengths(A, m);
+        if (!(lane ? ok_d : ok_ll)) qz_huff_depths_to_lengths(A, m);
         qz_huff_limit_sorted(A, m, 15);
     }
     __syncwarp();

@@ -50,9 +50,11 @@ QZ_HD void qz_huff_force_two(uint32_t *freq, int n)
 }
 
 /* In-place minimum-redundancy code lengths (Moffat & Katajainen, 1995) over frequencies sorted
- * ascending in A[0..n), n >= 2.  On return A[i] is the code length of the i-th sorted symbol
- * (non-increasing in i). */
-QZ_HD_SERIAL void qz_huff_inplace_lengths(uint32_t *A, int n)
+ * ascending in A[0..n), n >= 2, in three passes.  Passes 1-2 (tree by two-queue merge, then depths of
+ * the n-1 internal nodes, root = node n-2 at depth 0, depths non-increasing with the index) are serial;
+ * pass 3 (internal depths -> leaf depths) has a serial form here and a warp-parallel one in the kernel.
+ * On return of the full routine A[i] is the code length of the i-th sorted symbol (non-increasing in i). */
+QZ_HD_SERIAL void qz_huff_inplace_depths(uint32_t *A, int n)
 {
     int root, leaf, next;
     A[0] += A[1]; root = 0; leaf = 2;
@@ -64,13 +66,20 @@ QZ_HD_SERIAL void qz_huff_inplace_lengths(uint32_t *A, int n)
     }
     A[n - 2] = 0;
     for (next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
-    int avbl = 1, used = 0, dpth = 0;
-    root = n - 2; next = n - 1;
+}
+QZ_HD_SERIAL void qz_huff_depths_to_lengths(uint32_t *A, int n)
+{
+    int avbl = 1, used = 0, dpth = 0, root = n - 2, next = n - 1;
     while (avbl > 0) {
         while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
         while (avbl > used) { A[next--] = (uint32_t)dpth; avbl--; }
         avbl = 2 * used; dpth++; used = 0;
     }
+}
+QZ_HD_SERIAL void qz_huff_inplace_lengths(uint32_t *A, int n)
+{
+    qz_huff_inplace_depths(A, n);
+    qz_huff_depths_to_lengths(A, n);
 }
 
 /* Cap the (sorted, non-increasing) code lengths in len[0..n) at maxbits, keeping the Kraft sum
