@@ -25,7 +25,6 @@
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_inflate_lanes(const QzbDecompressJob *job, int sm_count, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
@@ -70,7 +69,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
-    t->inflate_lane_min = env_int("QZB200_INFLATE_LANE_MIN", 1 << 30);   /* lane-per-member decoder: off by default (measured slower than warp-per-member so far) */   /* deflate: piece buffers per CTA, 0 = warps / 2 */
+    t->inflate_lane_min = 0;                              /* (unused: the lane-per-member decoder was measured slower and removed) */
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
@@ -523,13 +522,10 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket; job.size_only = size_only ? 1 : 0;
         const int grid = (int)std::min<size_t>((count + 7) / 8, (size_t)grid_cap);
         CK(cudaEventRecord(s.ev_k0, s.st));
-        /* many sized gzip members: one LANE per member (32 decoders per warp); otherwise one warp per member */
-        const bool lanes = !lz4 && !staged_out && count >= (size_t)e->tune.inflate_lane_min && (c->fmt == QZB_FMT_GZIP || c->fmt == QZB_FMT_GZIP_EXT);
         if (lz4) CK(qzb_launch_lz4_decompress(&job, grid, s.st));
-        else if (lanes) CK(qzb_launch_inflate_lanes(&job, e->sm_count, s.st));
         else CK(qzb_launch_inflate(&job, grid, s.st));
         CK(cudaEventRecord(s.ev_k1, s.st));
-        o->kernel_launches += lanes ? 2 : 1;
+        o->kernel_launches += 1;
         CK(cudaMemcpyAsync(s.h_results.p, s.d_results.p, count * sizeof(QzbMemberResult), cudaMemcpyDeviceToHost, s.st));
         CK(cudaEventRecord(s.ev_meta, s.st));
         s.busy = true; s.first_member = first; s.nmembers = count; s.span_src = span_src; s.span_len = span_len; s.out_base = out_base; s.out_len = out_len;

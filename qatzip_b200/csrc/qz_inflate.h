@@ -1,8 +1,9 @@
 /* qz_inflate.h -- RFC 1951 decoder core as scalar host+device code.
  *
- * On the GPU one warp owns one member: lane 0 runs qz_inflate_run() (table-driven symbol
- * decode, literals stored directly), and every back-reference / stored block is handed to the
- * whole warp for the copy.  The CPU unit tests drive the same functions serially.
+ * On the GPU one warp owns one member: lane 0 turns the bit stream into tokens with
+ * qz_inflate_tokens() (one table lookup per literal, two per match; bases and extra-bit counts come
+ * out of the table entry), the whole warp places them.  The CPU unit tests drive the same functions
+ * serially against zlib.
  *
  * Replaces the QAT stateless inflate request (reference src/qatzip.c:2191 cpaDcDecompressData
  * with CPA_DC_FLUSH_FINAL); the decoder itself lives in device firmware, not in the reference. */
@@ -11,175 +12,202 @@
 #include "qz_hd.h"
 #include "qz_deflate_tables.h"
 
-#define QZ_LL_LUT_BITS 9     /* 1 KiB: small enough that 64 members per SM can keep private tables in shared memory */
-#define QZ_D_LUT_BITS 7
+#define QZ_LL_LUT_BITS 10    /* 4 KiB of 32-bit entries per warp */
+#define QZ_D_LUT_BITS 8
+
+/* Decode-table entry:
+ *   bits 0..3   code length (1..15); an all-zero entry = code longer than the table, or unused
+ *   bits 4..7   number of extra bits that follow the code
+ *   bits 8..23  literal byte, or length base 3..258, or distance base 1..24577
+ *   bits 28..31 kind */
+#define QZE_LIT 0x80000000u
+#define QZE_LEN 0x40000000u      /* also marks a valid distance entry */
+#define QZE_EOB 0x20000000u
+#define QZE_BAD 0x10000000u      /* symbol that must not occur (lit/len 286, 287; distance 30, 31) */
 
 struct QzInflTables {
-    uint16_t ll_lut[1 << QZ_LL_LUT_BITS];   /* (sym << 4) | len ; 0 = code longer than the LUT / unused */
-    uint16_t d_lut[1 << QZ_D_LUT_BITS];
-    uint16_t ll_count[16], d_count[16];      /* codes per length (slow path, canonical decode) */
+    uint32_t ll_lut[1 << QZ_LL_LUT_BITS];
+    uint32_t d_lut[1 << QZ_D_LUT_BITS];
+    uint16_t ll_count[16], d_count[16];      /* codes per length */
+    uint16_t ll_first[16], d_first[16];      /* canonical first code of each length */
+    uint16_t ll_offs[16], d_offs[16];        /* index in sorted[] of the first symbol of each length */
     uint16_t ll_sorted[288], d_sorted[32];   /* symbols ordered by (length, symbol) */
-    uint8_t lens[320];                       /* scratch: code lengths while reading a dynamic header */
+    uint8_t lens[320];                       /* code lengths read from a dynamic header (hlit, then hdist) */
 };
 
-/* LSB-first bit reader over a byte buffer of length n.  Reads past the end yield zero bits and
- * are detected afterwards through qz_br_overrun(). */
+QZ_HD uint32_t qz_infl_ll_entry(uint32_t s, uint32_t l)
+{
+    if (s < 256) return QZE_LIT | (s << 8) | l;
+    if (s == 256) return QZE_EOB | l;
+    if (s > 285) return QZE_BAD | l;
+    uint32_t eb, base = qz_len_base(s - 257, &eb);
+    return QZE_LEN | (base << 8) | (eb << 4) | l;
+}
+QZ_HD uint32_t qz_infl_d_entry(uint32_t s, uint32_t l)
+{
+    if (s > 29) return QZE_BAD | l;
+    uint32_t eb, base = qz_dist_base(s, &eb);
+    return QZE_LEN | (base << 8) | (eb << 4) | l;
+}
+
+/* LSB-first bit reader.  Input is fetched as aligned 32-bit words, one word ahead of need (wnext),
+ * so the decode loop never waits for the load it has just issued.  Offsets are relative to the aligned
+ * address at or below the first byte; bytes past the end read as zero and are detected afterwards
+ * through qz_br_overrun(). */
 struct QzBitReader {
-    const uint8_t *p;
-    uint32_t n, pos;       /* pos = next byte to load */
+    const uint8_t *base;   /* p rounded down to 4 bytes */
+    uint32_t skew;         /* p - base */
+    uint32_t end;          /* skew + n */
+    uint32_t n;
+    uint32_t pos;          /* offset of wnext */
+    uint32_t wnext;
     uint64_t acc;
     uint32_t nacc;
-    uint32_t phantom;      /* zero bytes supplied beyond the end */
 };
-QZ_HD void qz_br_init(QzBitReader *b, const uint8_t *p, uint32_t n) { b->p = p; b->n = n; b->pos = 0; b->acc = 0; b->nacc = 0; b->phantom = 0; }
+QZ_HD uint32_t qz_br_word(const QzBitReader *b, uint32_t off)
+{
+    if (off + 4 <= b->end) return *(const uint32_t *)(b->base + off);
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < 4; k++) if (off + k < b->end) w |= (uint32_t)b->base[off + k] << (8 * k);
+    return w;
+}
+/* position the reader at byte `off` of the input */
+QZ_HD void qz_br_seek(QzBitReader *b, uint32_t off)
+{
+    const uint32_t a = off + b->skew, w = a & ~3u, sub = a & 3u;
+    b->acc = (uint64_t)(qz_br_word(b, w) >> (8 * sub));
+    b->nacc = 32 - 8 * sub;
+    b->pos = w + 4;
+    b->wnext = qz_br_word(b, b->pos);
+}
+QZ_HD void qz_br_init(QzBitReader *b, const uint8_t *p, uint32_t n)
+{
+    b->skew = (uint32_t)((uintptr_t)p & 3); b->base = p - b->skew; b->end = b->skew + n; b->n = n;
+    qz_br_seek(b, 0);
+}
+/* after this at least 33 bits are buffered */
 QZ_HD void qz_br_refill(QzBitReader *b)
 {
-    /* Top up only when half empty, and then with ONE aligned 32-bit load: the decode loop calls this
-     * per symbol, so the common case must be a compare and nothing else.  Byte loads happen only
-     * to reach 4-byte alignment at the start and in the last <4 bytes (then zero "phantom" bytes). */
     if (b->nacc > 32) return;
-    while (b->nacc <= 56 && (((uintptr_t)(b->p + b->pos)) & 3) != 0) {
-        if (b->pos < b->n) b->acc |= (uint64_t)b->p[b->pos++] << b->nacc;
-        else b->phantom++;
-        b->nacc += 8;
-    }
-    if (b->nacc > 32) return;
-    if (b->pos + 4 <= b->n) { b->acc |= (uint64_t)(*(const uint32_t *)(b->p + b->pos)) << b->nacc; b->pos += 4; b->nacc += 32; return; }
-    while (b->nacc <= 56) {
-        if (b->pos < b->n) b->acc |= (uint64_t)b->p[b->pos++] << b->nacc;
-        else b->phantom++;
-        b->nacc += 8;
-    }
+    b->acc |= (uint64_t)b->wnext << b->nacc;
+    b->nacc += 32;
+    b->pos += 4;
+    b->wnext = qz_br_word(b, b->pos);
 }
 QZ_HD uint32_t qz_br_bits(QzBitReader *b, uint32_t n)   /* n <= 32; caller keeps nacc >= n via refill */
 {
     uint32_t v = (uint32_t)(b->acc & ((1ull << n) - 1)); b->acc >>= n; b->nacc -= n; return v;
 }
-/* bytes of input actually consumed (whole bytes, bits still buffered are given back) */
-QZ_HD uint32_t qz_br_consumed(const QzBitReader *b) { return b->pos + b->phantom - (b->nacc >> 3); }
+/* bytes of input actually consumed (whole bytes; bits still buffered are given back) */
+QZ_HD uint32_t qz_br_consumed(const QzBitReader *b) { return b->pos - b->skew - (b->nacc >> 3); }
 QZ_HD int qz_br_overrun(const QzBitReader *b) { return qz_br_consumed(b) > b->n; }
+/* nothing but zero fill is left (QZ_DEFLATE_RAW chunks that end without BFINAL stop here) */
+QZ_HD int qz_br_exhausted(const QzBitReader *b) { return (uint64_t)(b->pos - b->skew) * 8 >= (uint64_t)b->n * 8 + b->nacc; }
 
-/* Build decode tables from code lengths.  Step 1 (serial): counts, canonical first codes, the
- * (length,symbol)-sorted symbol list; returns -1 for an over-subscribed set, 1 for an
- * incomplete one, 0 for a complete one.  code_of[] receives each symbol's canonical code. */
-QZ_HD int qz_infl_prepare(const uint8_t *len, int n, uint16_t *count, uint16_t *sorted, uint16_t *code_of)
+/* Build the canonical-code description of one alphabet from its code lengths (serial form; the
+ * kernel has a warp-parallel equivalent): counts, first codes, offsets, and the (length, symbol)-
+ * sorted symbol list.  Returns -1 for an over-subscribed set, 1 for an incomplete one, 0 otherwise. */
+QZ_HD int qz_infl_prepare(const uint8_t *len, int n, uint16_t *count, uint16_t *first, uint16_t *offs, uint16_t *sorted)
 {
-    uint16_t offs[16]; uint32_t next[16]; int left = 1;
-    for (int l = 0; l < 16; l++) count[l] = 0;
+    uint16_t fill[16]; int left = 1;
+    for (int l = 0; l < 16; l++) { count[l] = 0; first[l] = 0; offs[l] = 0; }
     for (int s = 0; s < n; s++) count[len[s]]++;
-    if (count[0] == n) return 1;
+    if (count[0] == n) { count[0] = 0; return 1; }
     for (int l = 1; l < 16; l++) { left <<= 1; left -= count[l]; if (left < 0) return -1; }
-    offs[1] = 0; next[0] = 0; next[1] = 0;
-    uint32_t code = 0;
-    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
-    for (int l = 1; l < 16; l++) { next[l] = code; code = (code + count[l]) << 1; }
-    for (int s = 0; s < n; s++) if (len[s]) { sorted[offs[len[s]]++] = (uint16_t)s; code_of[s] = (uint16_t)next[len[s]]++; }
+    uint32_t code = 0; offs[0] = 0; first[0] = 0; offs[1] = 0;
+    for (int l = 1; l < 16; l++) { first[l] = (uint16_t)code; code = (code + count[l]) << 1; if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + count[l]); }
+    for (int l = 0; l < 16; l++) fill[l] = offs[l];
+    for (int s = 0; s < n; s++) if (len[s]) sorted[fill[len[s]]++] = (uint16_t)s;
     return left > 0 ? 1 : 0;
 }
-/* Step 2 (parallel over symbols: call with lane/nlanes, or 0/1 on the host): fill the LUT. */
-QZ_HD void qz_infl_fill_lut(const uint8_t *len, const uint16_t *code_of, int n, uint16_t *lut, int lut_bits, int lane, int nlanes)
+/* Fill the lookup table (parallel over sorted symbols: call with lane/nlanes, or 0/1 on the host).
+ * The table must be zero beforehand. */
+QZ_HD void qz_infl_fill_lut(const uint8_t *len, const uint16_t *count, const uint16_t *first, const uint16_t *offs, const uint16_t *sorted,
+                            uint32_t *lut, int lut_bits, int is_dist, int lane, int nlanes)
 {
-    for (int s = lane; s < n; s += nlanes) {
-        uint32_t l = len[s];
-        if (l == 0 || l > (uint32_t)lut_bits) continue;
-        uint32_t r = qz_bitrev(code_of[s], l);
-        uint16_t e = (uint16_t)((s << 4) | l);
+    const int used = offs[15] + count[15];
+    for (int i = lane; i < used; i += nlanes) {
+        const uint32_t s = sorted[i], l = len[s];
+        if (l > (uint32_t)lut_bits) continue;
+        const uint32_t r = qz_bitrev((uint32_t)first[l] + (uint32_t)(i - offs[l]), l);
+        const uint32_t e = is_dist ? qz_infl_d_entry(s, l) : qz_infl_ll_entry(s, l);
         for (uint32_t k = r; k < (1u << lut_bits); k += (1u << l)) lut[k] = e;
     }
 }
-/* canonical bit-by-bit decode for codes longer than the LUT.  Returns symbol or -1. */
-QZ_HD int qz_infl_slow(QzBitReader *b, const uint16_t *count, const uint16_t *sorted)
+/* canonical bit-by-bit decode for codes longer than the table.  Returns the symbol and its code length
+ * in *len_out, or -1. */
+QZ_HD int qz_infl_slow(uint64_t acc, const uint16_t *count, const uint16_t *sorted, uint32_t *len_out)
 {
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; l++) {
-        code |= (int)(b->acc & 1); b->acc >>= 1; b->nacc--;
+        code |= (int)(acc & 1); acc >>= 1;
         int c = count[l];
-        if (code - c < first) return sorted[index + (code - first)];
+        if (code - c < first) { *len_out = (uint32_t)l; return sorted[index + (code - first)]; }
         index += c; first += c; first <<= 1; code <<= 1;
     }
     return -1;
 }
 
-/* events returned by qz_inflate_run */
+/* events returned by qz_inflate_tokens */
 enum { QZI_MATCH = 0, QZI_END_BLOCK = 1, QZI_ERR_DATA = -1, QZI_ERR_FULL = -2, QZI_ERR_TRUNC = -3 };
 
-/* Decode symbols of the current Huffman block: literals go straight to dst[*out], the loop
- * returns at the first back-reference (len/dist filled, NOT yet copied), at end-of-block, or
- * on error. */
-QZ_HD int qz_inflate_run(QzBitReader *b, const QzInflTables *t, uint8_t *dst, uint32_t *out, uint32_t cap,
-                         uint32_t *mlen, uint32_t *mdist)
-{
-    uint32_t o = *out;
-    for (;;) {
-        qz_br_refill(b);
-        uint32_t e = t->ll_lut[b->acc & ((1u << QZ_LL_LUT_BITS) - 1)];
-        int sym;
-        if (e) { sym = (int)(e >> 4); b->acc >>= (e & 15); b->nacc -= (e & 15); }
-        else { sym = qz_infl_slow(b, t->ll_count, t->ll_sorted); if (sym < 0) { *out = o; return QZI_ERR_DATA; } }
-        if (sym < 256) {
-            if (o >= cap) { *out = o; return QZI_ERR_FULL; }
-            dst[o++] = (uint8_t)sym;
-            continue;
-        }
-        *out = o;
-        if (sym == 256) return QZI_END_BLOCK;
-        sym -= 257;
-        if (sym >= 29) return QZI_ERR_DATA;
-        uint32_t eb, len = qz_len_base((uint32_t)sym, &eb);
-        if (b->nacc < 48) qz_br_refill(b);
-        len += qz_br_bits(b, eb);
-        uint32_t de = t->d_lut[b->acc & ((1u << QZ_D_LUT_BITS) - 1)];
-        int ds;
-        if (de) { ds = (int)(de >> 4); b->acc >>= (de & 15); b->nacc -= (de & 15); }
-        else { ds = qz_infl_slow(b, t->d_count, t->d_sorted); if (ds < 0) return QZI_ERR_DATA; }
-        if (ds >= 30) return QZI_ERR_DATA;
-        uint32_t dist = qz_dist_base((uint32_t)ds, &eb);
-        dist += qz_br_bits(b, eb);
-        if (dist > o) return QZI_ERR_DATA;
-        if (o + len > cap) return QZI_ERR_FULL;
-        *mlen = len; *mdist = dist;
-        return QZI_MATCH;
-    }
-}
-
-/* Batch form of the decode loop: turn the next symbols of the current Huffman block into at most
- * `max_tok` tokens (literal byte, or 1<<31 | (len-3) << 16 | (dist-1)) WITHOUT touching the
- * output; *pos is the output position before the batch and is advanced by the bytes the tokens
- * stand for.  Returns QZI_MATCH (= 0: buffer full, more to come), QZI_END_BLOCK, or an error. */
+/* Turn the next symbols of the current Huffman block into at most `max_tok` tokens (literal byte, or
+ * 1<<31 | (len-3) << 16 | (dist-1)) WITHOUT touching the output; *pos is the output position before
+ * the batch and is advanced by the bytes the tokens stand for.  Returns QZI_MATCH (= 0: buffer full,
+ * more to come), QZI_END_BLOCK, or an error. */
 QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
                             uint32_t *pos, uint32_t cap)
 {
     uint32_t n = 0, o = *pos;
     int ev = QZI_MATCH;
+    /* the reader's hot state lives in locals so that it stays in registers */
+    uint64_t acc = b->acc; uint32_t nacc = b->nacc, rp = b->pos, wnext = b->wnext;
+#define QZI_REFILL() do { if (nacc <= 32) { acc |= (uint64_t)wnext << nacc; nacc += 32; rp += 4; \
+                          if (rp + 4 <= b->end) wnext = *(const uint32_t *)(b->base + rp); else { b->pos = rp; wnext = qz_br_word(b, rp); } } } while (0)
     while (n < max_tok) {
-        qz_br_refill(b);
-        uint32_t e = t->ll_lut[b->acc & ((1u << QZ_LL_LUT_BITS) - 1)];
-        int sym;
-        if (e) { sym = (int)(e >> 4); b->acc >>= (e & 15); b->nacc -= (e & 15); }
-        else { sym = qz_infl_slow(b, t->ll_count, t->ll_sorted); if (sym < 0) { ev = QZI_ERR_DATA; break; } }
-        if (sym < 256) {
+        QZI_REFILL();
+        uint32_t e = t->ll_lut[(uint32_t)acc & ((1u << QZ_LL_LUT_BITS) - 1)];
+        if (e & QZE_LIT) {                                   /* the common case first */
             if (o >= cap) { ev = QZI_ERR_FULL; break; }
-            tok[n++] = (uint32_t)sym; o++;
+            acc >>= (e & 15); nacc -= (e & 15);
+            tok[n++] = (e >> 8) & 0xff; o++;
             continue;
         }
-        if (sym == 256) { ev = QZI_END_BLOCK; break; }
-        sym -= 257;
-        if (sym >= 29) { ev = QZI_ERR_DATA; break; }
-        uint32_t eb, len = qz_len_base((uint32_t)sym, &eb);
-        if (b->nacc < 48) qz_br_refill(b);
-        len += qz_br_bits(b, eb);
-        uint32_t de = t->d_lut[b->acc & ((1u << QZ_D_LUT_BITS) - 1)];
-        int ds;
-        if (de) { ds = (int)(de >> 4); b->acc >>= (de & 15); b->nacc -= (de & 15); }
-        else { ds = qz_infl_slow(b, t->d_count, t->d_sorted); if (ds < 0) { ev = QZI_ERR_DATA; break; } }
-        if (ds >= 30) { ev = QZI_ERR_DATA; break; }
-        uint32_t dist = qz_dist_base((uint32_t)ds, &eb);
-        dist += qz_br_bits(b, eb);
+        if (e == 0) {
+            uint32_t l; const int sym = qz_infl_slow(acc, t->ll_count, t->ll_sorted, &l);
+            if (sym < 0) { ev = QZI_ERR_DATA; break; }
+            e = qz_infl_ll_entry((uint32_t)sym, l);
+            if (e & QZE_LIT) {
+                if (o >= cap) { ev = QZI_ERR_FULL; break; }
+                acc >>= l; nacc -= l;
+                tok[n++] = (e >> 8) & 0xff; o++;
+                continue;
+            }
+        }
+        if (e & QZE_EOB) { acc >>= (e & 15); nacc -= (e & 15); ev = QZI_END_BLOCK; break; }
+        if (e & QZE_BAD) { ev = QZI_ERR_DATA; break; }
+        /* length: code + extra bits, at most 20 of the >= 33 buffered */
+        const uint32_t cl = e & 15, eb = (e >> 4) & 15;
+        const uint32_t len = ((e >> 8) & 0xffff) + (((uint32_t)(acc >> cl)) & ((1u << eb) - 1));
+        acc >>= (cl + eb); nacc -= (cl + eb);
+        QZI_REFILL();
+        uint32_t de = t->d_lut[(uint32_t)acc & ((1u << QZ_D_LUT_BITS) - 1)];
+        if (de == 0) {
+            uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_sorted, &l);
+            if (ds < 0) { ev = QZI_ERR_DATA; break; }
+            de = qz_infl_d_entry((uint32_t)ds, l);
+        }
+        if (de & QZE_BAD) { ev = QZI_ERR_DATA; break; }
+        const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
+        const uint32_t dist = ((de >> 8) & 0xffff) + (((uint32_t)(acc >> dcl)) & ((1u << deb) - 1));
+        acc >>= (dcl + deb); nacc -= (dcl + deb);
         if (dist > o) { ev = QZI_ERR_DATA; break; }
         if (o + len > cap) { ev = QZI_ERR_FULL; break; }
         tok[n++] = 0x80000000u | ((len - 3) << 16) | (dist - 1);
         o += len;
     }
+#undef QZI_REFILL
+    b->acc = acc; b->nacc = nacc; b->pos = rp; b->wnext = wnext;
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
     if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
@@ -187,26 +215,31 @@ QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok
     return ev;
 }
 
-/* Read the code lengths of a dynamic block header into t->lens (hlit lengths then hdist).
- * Returns 0 or QZI_ERR_DATA. */
+/* Read the code lengths of a dynamic block header into t->lens (hlit lengths then hdist).  The
+ * code-length alphabet's own tables borrow the (not yet built) distance table.  Returns 0 or QZI_ERR_DATA. */
 QZ_HD int qz_inflate_read_dynamic(QzBitReader *b, QzInflTables *t, uint32_t *hlit_out, uint32_t *hdist_out)
 {
     const uint8_t ORDER[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
     qz_br_refill(b);
     uint32_t hlit = qz_br_bits(b, 5) + 257, hdist = qz_br_bits(b, 5) + 1, hclen = qz_br_bits(b, 4) + 4;
     if (hlit > 286 || hdist > 30) return QZI_ERR_DATA;
-    uint8_t cl[19]; uint16_t code_of[19], cl_count[16], cl_sorted[19], cl_lut[128];
+    uint8_t cl[19]; uint16_t cl_count[16], cl_first[16], cl_offs[16], cl_sorted[19];
+    uint32_t *cl_lut = t->d_lut;                             /* 128 of its 256 entries */
     for (int i = 0; i < 19; i++) cl[i] = 0;
-    for (uint32_t i = 0; i < hclen; i++) { if (b->nacc < 3) qz_br_refill(b); cl[ORDER[i]] = (uint8_t)qz_br_bits(b, 3); }
-    if (qz_infl_prepare(cl, 19, cl_count, cl_sorted, code_of) != 0) return QZI_ERR_DATA;
+    for (uint32_t i = 0; i < hclen; i++) { qz_br_refill(b); cl[ORDER[i]] = (uint8_t)qz_br_bits(b, 3); }
+    if (qz_infl_prepare(cl, 19, cl_count, cl_first, cl_offs, cl_sorted) != 0) return QZI_ERR_DATA;
     for (int i = 0; i < 128; i++) cl_lut[i] = 0;
-    qz_infl_fill_lut(cl, code_of, 19, cl_lut, 7, 0, 1);
+    /* entries: symbol << 8 | length (QZE_LIT layout without the flag) */
+    { const int used = cl_offs[15] + cl_count[15];
+      for (int i = 0; i < used; i++) { const uint32_t s = cl_sorted[i], l = cl[s];
+          const uint32_t r = qz_bitrev((uint32_t)cl_first[l] + (uint32_t)(i - cl_offs[l]), l);
+          for (uint32_t k = r; k < 128; k += (1u << l)) cl_lut[k] = (s << 8) | l; } }
     uint32_t i = 0, total = hlit + hdist;
     while (i < total) {
         qz_br_refill(b);
-        uint32_t e = cl_lut[b->acc & 127];
+        const uint32_t e = cl_lut[b->acc & 127];
         if (!e) return QZI_ERR_DATA;
-        uint32_t s = e >> 4; b->acc >>= (e & 15); b->nacc -= (e & 15);
+        const uint32_t s = e >> 8; b->acc >>= (e & 15); b->nacc -= (e & 15);
         if (s < 16) { t->lens[i++] = (uint8_t)s; continue; }
         uint32_t rep; uint8_t v = 0;
         if (s == 16) { if (i == 0) return QZI_ERR_DATA; v = t->lens[i - 1]; rep = 3 + qz_br_bits(b, 2); }

@@ -106,13 +106,13 @@ static std::vector<uint8_t> compress_piece(const uint8_t *src, uint32_t n, bool 
 // ---- serial driver of the inflate core (what the warp does around lane 0) ----
 static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst, uint32_t cap, uint32_t *consumed, bool raw_stop)
 {
-    static QzInflTables T; static uint16_t code_of[320];
+    static QzInflTables T;
     QzBitReader br; qz_br_init(&br, src, n);
     dst.assign(cap + 1, 0);
     uint32_t out = 0, bfinal = 0;
     while (!bfinal) {
         qz_br_refill(&br);
-        if (raw_stop && qz_br_consumed(&br) >= br.n && br.phantom * 8 >= br.nacc) break;
+        if (raw_stop && qz_br_exhausted(&br)) break;
         bfinal = qz_br_bits(&br, 1); uint32_t type = qz_br_bits(&br, 2);
         if (type == 3) return -1;
         if (type == 0) {
@@ -122,17 +122,17 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
             if (start + len > br.n) return -3;
             if (out + len > cap) return -2;
             memcpy(&dst[out], src + start, len); out += len;
-            br.pos = start + len; br.acc = 0; br.nacc = 0; br.phantom = 0;
+            qz_br_seek(&br, start + len);
             continue;
         }
         uint32_t hlit = 288, hdist = 30;
         if (type == 1) qz_inflate_fixed_lens(&T); else if (qz_inflate_read_dynamic(&br, &T, &hlit, &hdist)) return -1;
-        if (qz_infl_prepare(T.lens, hlit, T.ll_count, T.ll_sorted, code_of) < 0) return -1;
-        if (qz_infl_prepare(T.lens + hlit, hdist, T.d_count, T.d_sorted, code_of + 288) < 0) return -1;
+        if (qz_infl_prepare(T.lens, hlit, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted) < 0) return -1;
+        if (qz_infl_prepare(T.lens + hlit, hdist, T.d_count, T.d_first, T.d_offs, T.d_sorted) < 0) return -1;
         memset(T.ll_lut, 0, sizeof T.ll_lut); memset(T.d_lut, 0, sizeof T.d_lut);
         for (int lane = 0; lane < 32; lane++) {   // emulate the 32-lane fill
-            qz_infl_fill_lut(T.lens, code_of, hlit, T.ll_lut, QZ_LL_LUT_BITS, lane, 32);
-            qz_infl_fill_lut(T.lens + hlit, code_of + 288, hdist, T.d_lut, QZ_D_LUT_BITS, lane, 32);
+            qz_infl_fill_lut(T.lens, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut, QZ_LL_LUT_BITS, 0, lane, 32);
+            qz_infl_fill_lut(T.lens + hlit, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut, QZ_D_LUT_BITS, 1, lane, 32);
         }
         for (;;) {   // the kernel's batch loop: 32 tokens decoded without touching the output, then placed
             uint32_t tok[32], ntk = 0, pos = out;
