@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                 __syncwarp();
                 ev = (int)bcast((uint32_t)ev); ntk = bcast(ntk);
                 const uint32_t t = lane < ntk ? ws.tok[lane] : 0u;
-                const bool is_match = lane < ntk && (t >> 31);
-                const uint32_t len = lane < ntk ? (is_match ? ((t >> 16) & 0xff) + 3 : 1u) : 0u;
-                const uint32_t dist = (t & 0x7fff) + 1;
+                const bool is_match = lane < ntk && !qz_tok_is_literal(t);
+                const uint32_t len = lane < ntk ? (is_match ? qz_tok_len(t) : 1u) : 0u;
+                const uint32_t dist = qz_tok_dist(t);
                 uint32_t incl = len;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
                  * all loads first (ordinary cached loads: what this warp wrote is in this SM's L1 or in L2) */
                 const bool lane_copy = is_match && !dep && len <= QZ_INFL_LANE_COPY && dist >= len;
                 if (lane < ntk && wr) {
-                    if (!is_match) dst[o] = (uint8_t)t;
+                    if (!is_match) dst[o] = (uint8_t)qz_tok_byte(t);
                     else if (lane_copy) {
                         const uint8_t *from = dst + o - dist;
                         uint8_t v[QZ_INFL_LANE_COPY];

@@ -151,67 +151,80 @@ QZ_HD int qz_infl_slow(uint64_t acc, const uint16_t *count, const uint16_t *sort
 /* events returned by qz_inflate_tokens */
 enum { QZI_MATCH = 0, QZI_END_BLOCK = 1, QZI_ERR_DATA = -1, QZI_ERR_FULL = -2, QZI_ERR_TRUNC = -3 };
 
-/* Turn the next symbols of the current Huffman block into at most `max_tok` tokens (literal byte, or
- * 1<<31 | (len-3) << 16 | (dist-1)) WITHOUT touching the output; *pos is the output position before
- * the batch and is advanced by the bytes the tokens stand for.  Returns QZI_MATCH (= 0: buffer full,
- * more to come), QZI_END_BLOCK, or an error. */
+/* Token produced by the decode loop: a literal is its table entry as is (QZE_LIT set, byte in bits 8..15),
+ * a match is (len - 3) << 16 | (dist - 1) with bit 31 clear. */
+QZ_HD int qz_tok_is_literal(uint32_t t) { return (t >> 31) != 0; }
+QZ_HD uint32_t qz_tok_byte(uint32_t t) { return (t >> 8) & 0xff; }
+QZ_HD uint32_t qz_tok_len(uint32_t t) { return ((t >> 16) & 0xff) + 3; }
+QZ_HD uint32_t qz_tok_dist(uint32_t t) { return (t & 0x7fff) + 1; }
+
+/* Turn the next symbols of the current Huffman block into at most `max_tok` tokens WITHOUT touching
+ * the output; *pos is the output position before the batch and is advanced by the bytes the tokens
+ * stand for.  Returns QZI_MATCH (= 0: buffer full, more to come), QZI_END_BLOCK, or an error.
+ * This loop is the serial heart of inflate (one lane per member runs it), so it is written for
+ * instruction count: reader state in locals, one pointer for input words and one for tokens, the
+ * literal case first and exits by goto. */
 QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
                             uint32_t *pos, uint32_t cap)
 {
-    uint32_t n = 0, o = *pos;
+    uint32_t o = *pos;
     int ev = QZI_MATCH;
-    /* the reader's hot state lives in locals so that it stays in registers */
-    uint64_t acc = b->acc; uint32_t nacc = b->nacc, rp = b->pos, wnext = b->wnext;
-#define QZI_REFILL() do { if (nacc <= 32) { acc |= (uint64_t)wnext << nacc; nacc += 32; rp += 4; \
-                          if (rp + 4 <= b->end) wnext = *(const uint32_t *)(b->base + rp); else { b->pos = rp; wnext = qz_br_word(b, rp); } } } while (0)
-    while (n < max_tok) {
+    uint64_t acc = b->acc; uint32_t nacc = b->nacc, wnext = b->wnext;
+    const uint32_t *wp = (const uint32_t *)(b->base + b->pos);              /* address wnext came from */
+    const uint32_t *const wlast = (const uint32_t *)(b->base + (b->end & ~3u)) - 1;   /* last word wholly inside the input */
+    uint32_t *tp = tok, *const tend = tok + max_tok;
+    const uint32_t *const ll_lut = t->ll_lut, *const d_lut = t->d_lut;
+#define QZI_REFILL() do { if (nacc <= 32) { acc |= (uint64_t)wnext << nacc; nacc += 32; wp++; \
+                          wnext = wp <= wlast ? *wp : qz_br_word(b, (uint32_t)((const uint8_t *)wp - b->base)); } } while (0)
+    while (tp != tend) {
         QZI_REFILL();
-        uint32_t e = t->ll_lut[(uint32_t)acc & ((1u << QZ_LL_LUT_BITS) - 1)];
-        if (e & QZE_LIT) {                                   /* the common case first */
-            if (o >= cap) { ev = QZI_ERR_FULL; break; }
+        uint32_t e = ll_lut[(uint32_t)acc & ((1u << QZ_LL_LUT_BITS) - 1)];
+        if ((int32_t)e < 0) {                                /* literal */
+lit:
+            if (o >= cap) { ev = QZI_ERR_FULL; goto done; }
             acc >>= (e & 15); nacc -= (e & 15);
-            tok[n++] = (e >> 8) & 0xff; o++;
+            *tp++ = e; o++;
             continue;
         }
         if (e == 0) {
             uint32_t l; const int sym = qz_infl_slow(acc, t->ll_count, t->ll_sorted, &l);
-            if (sym < 0) { ev = QZI_ERR_DATA; break; }
+            if (sym < 0) { ev = QZI_ERR_DATA; goto done; }
             e = qz_infl_ll_entry((uint32_t)sym, l);
-            if (e & QZE_LIT) {
-                if (o >= cap) { ev = QZI_ERR_FULL; break; }
-                acc >>= l; nacc -= l;
-                tok[n++] = (e >> 8) & 0xff; o++;
-                continue;
+            if ((int32_t)e < 0) goto lit;
+        }
+        if (!(e & QZE_LEN)) {
+            if (e & QZE_EOB) { acc >>= (e & 15); nacc -= (e & 15); ev = QZI_END_BLOCK; }
+            else ev = QZI_ERR_DATA;
+            goto done;
+        }
+        {   /* length: code + extra bits, at most 20 of the >= 33 buffered */
+            const uint32_t cl = e & 15, eb = (e >> 4) & 15;
+            const uint32_t len = ((e >> 8) & 0xffff) + (((uint32_t)(acc >> cl)) & ~(0xffffffffu << eb));
+            acc >>= (cl + eb); nacc -= (cl + eb);
+            QZI_REFILL();
+            uint32_t de = d_lut[(uint32_t)acc & ((1u << QZ_D_LUT_BITS) - 1)];
+            if (de == 0) {
+                uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_sorted, &l);
+                if (ds < 0) { ev = QZI_ERR_DATA; goto done; }
+                de = qz_infl_d_entry((uint32_t)ds, l);
             }
+            if (de & QZE_BAD) { ev = QZI_ERR_DATA; goto done; }
+            const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
+            const uint32_t dist = ((de >> 8) & 0xffff) + (((uint32_t)(acc >> dcl)) & ~(0xffffffffu << deb));
+            acc >>= (dcl + deb); nacc -= (dcl + deb);
+            if (dist > o) { ev = QZI_ERR_DATA; goto done; }
+            if (o + len > cap) { ev = QZI_ERR_FULL; goto done; }
+            *tp++ = ((len - 3) << 16) | (dist - 1);
+            o += len;
         }
-        if (e & QZE_EOB) { acc >>= (e & 15); nacc -= (e & 15); ev = QZI_END_BLOCK; break; }
-        if (e & QZE_BAD) { ev = QZI_ERR_DATA; break; }
-        /* length: code + extra bits, at most 20 of the >= 33 buffered */
-        const uint32_t cl = e & 15, eb = (e >> 4) & 15;
-        const uint32_t len = ((e >> 8) & 0xffff) + (((uint32_t)(acc >> cl)) & ((1u << eb) - 1));
-        acc >>= (cl + eb); nacc -= (cl + eb);
-        QZI_REFILL();
-        uint32_t de = t->d_lut[(uint32_t)acc & ((1u << QZ_D_LUT_BITS) - 1)];
-        if (de == 0) {
-            uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_sorted, &l);
-            if (ds < 0) { ev = QZI_ERR_DATA; break; }
-            de = qz_infl_d_entry((uint32_t)ds, l);
-        }
-        if (de & QZE_BAD) { ev = QZI_ERR_DATA; break; }
-        const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
-        const uint32_t dist = ((de >> 8) & 0xffff) + (((uint32_t)(acc >> dcl)) & ((1u << deb) - 1));
-        acc >>= (dcl + deb); nacc -= (dcl + deb);
-        if (dist > o) { ev = QZI_ERR_DATA; break; }
-        if (o + len > cap) { ev = QZI_ERR_FULL; break; }
-        tok[n++] = 0x80000000u | ((len - 3) << 16) | (dist - 1);
-        o += len;
     }
+done:
 #undef QZI_REFILL
-    b->acc = acc; b->nacc = nacc; b->pos = rp; b->wnext = wnext;
+    b->acc = acc; b->nacc = nacc; b->pos = (uint32_t)((const uint8_t *)wp - b->base); b->wnext = wnext;
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
     if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
-    *ntok = n; *pos = o;
+    *ntok = (uint32_t)(tp - tok); *pos = o;
     return ev;
 }
 

@@ -138,9 +138,9 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
             uint32_t tok[32], ntk = 0, pos = out;
             int ev = qz_inflate_tokens(&br, &T, tok, 32, &ntk, &pos, cap);
             for (uint32_t k = 0; k < ntk; k++) {
-                if (tok[k] >> 31) { uint32_t ml = ((tok[k] >> 16) & 0xff) + 3, md = (tok[k] & 0x7fff) + 1;
+                if (!qz_tok_is_literal(tok[k])) { uint32_t ml = qz_tok_len(tok[k]), md = qz_tok_dist(tok[k]);
                     for (uint32_t q = 0; q < ml; q++) dst[out + q] = dst[out - md + (md >= ml ? q : q % md)]; out += ml; }
-                else dst[out++] = (uint8_t)tok[k];
+                else dst[out++] = (uint8_t)qz_tok_byte(tok[k]);
             }
             if (out != pos) return -9;
             if (ev == QZI_END_BLOCK) break;
