@@ -553,6 +553,7 @@ struct QzbStreamBuf {
     unsigned int in_off, out_off;          /* consumed prefix of in_buf / delivered prefix of out_buf */
     unsigned int flush_more;
     unsigned int finished;                 /* a call with last==1 has already been coded */
+    unsigned int batched;                  /* compress: staging buffer already sized for batched engine calls */
 };
 static int stream_init(QzSession_T *sess, QzStream_T *strm, QzbSess **sp)
 {
@@ -585,7 +586,8 @@ static unsigned int stream_copy_out(QzStream_T *strm, QzbStreamBuf *b, unsigned 
 }
 static int grow(unsigned char **buf, unsigned int *cap, unsigned int keep_off, unsigned int keep_len, unsigned int want)
 {
-    unsigned char *n = (unsigned char *)qzMalloc(want, QZ_AUTO_SELECT_NUMA_NODE, COMMON_MEM);
+    unsigned char *n = (unsigned char *)qzMalloc(want, QZ_AUTO_SELECT_NUMA_NODE, want >= (1u << 20) ? PINNED_MEM : COMMON_MEM);
+    if (!n) n = (unsigned char *)qzMalloc(want, QZ_AUTO_SELECT_NUMA_NODE, COMMON_MEM);
     if (!n) return QZ_FAIL;
     if (keep_len) memcpy(n, *buf + keep_off, keep_len);
     qzFree(*buf); *buf = n; *cap = want;
@@ -602,13 +604,29 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
     if (s->p.data_fmt != QZ_DEFLATE_RAW && s->p.data_fmt != QZ_DEFLATE_GZIP_EXT) { strm->in_sz = 0; strm->out_sz = 0; return QZ_PARAMS; }
     QzbStreamBuf *b = (QzbStreamBuf *)strm->opaque;
     unsigned int consumed = 0, produced = 0; int rc = QZ_OK;
+    /* The reference submits one engine request per full strm_buff_sz buffer (src/qatzip_stream.c:514-560).
+     * A GPU launch costs about what 20 MiB of compression costs, so the staging buffer here is at least
+     * QZB200_STREAM_BATCH_KB (default 4 MiB, a whole number of chunks) of pinned memory: the stream is
+     * still cut into hw_buff_sz chunks, only fewer, larger engine calls carry them. */
+    if (!b->batched) {
+        b->batched = 1;
+        const char *ev = getenv("QZB200_STREAM_BATCH_KB");
+        unsigned long long want = (ev && *ev ? strtoull(ev, NULL, 10) : 4096ull) << 10;
+        const unsigned int hw = s->p.hw_buff_sz;
+        if (want > (64ull << 20)) want = 64ull << 20;
+        want = (want + hw - 1) / hw * hw;
+        if (want > b->in_cap && strm->pending_in == 0 && strm->pending_out == 0) {
+            unsigned char *ni = (unsigned char *)qzMalloc((size_t)want, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+            if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = (unsigned int)want; b->in_off = 0; }
+        }
+    }
     /* 1. hand over output left from an earlier call */
     if (strm->pending_out) {
         produced += stream_copy_out(strm, b, strm->out + produced);
         if (strm->pending_out) goto done;                 /* caller must make room first */
     }
     for (;;) {
-        /* 2. batch input up to strm_buff_sz; only a full buffer or `last` triggers the engine */
+        /* 2. batch input up to the staging capacity; only a full buffer or `last` triggers the engine */
         if (strm->in) consumed += stream_copy_in(strm, b, strm->in + consumed);
         const bool input_done = (strm->in_sz == 0);
         if (strm->pending_in < b->in_cap - b->in_off && !(last && input_done)) break;

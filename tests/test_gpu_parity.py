@@ -399,17 +399,26 @@ def stream_decompress(prod, sess, blob, slice_sz, out_sz):
     return bytes(out)
 
 
+@pytest.mark.parametrize("batch_kb", [None, "0"])
 @pytest.mark.parametrize("fmt", [q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW])
-def test_stream_compress_slices(prod, port, ref, data, fmt):
+def test_stream_compress_slices(prod, port, ref, data, fmt, batch_kb, monkeypatch):
+    """batch_kb None: default staging (4 MiB of chunks per engine call); "0": the reference's cadence,
+    one engine call per strm_buff_sz (src/qatzip_stream.c:514-560).  Same chunks, same bytes either way."""
+    if batch_kb is not None:
+        monkeypatch.setenv("QZB200_STREAM_BATCH_KB", batch_kb)
     d = pick(data, 1 << 20, 12)
     sess = prod.new_session(fmt=fmt)
+    blobs = []
     for slice_sz in (16384, 4096, 65536, 100000):            # hw_buff_sz/4 like mode 9, 4 KiB like BASELINE config 5
         blob, crc, calls, empties = stream_compress(prod, sess, d, slice_sz)
         assert crc == zlib.crc32(d)                          # strm.crc_32 = CRC-32 of all stream input (mode 11)
         assert port.decompress(blob, fmt, len(d) + 8) == d
         assert ref.decompress(blob, len(d) + 8, fmt=fmt) == d
+        blobs.append(blob)
         if slice_sz == 4096:
-            assert calls == 256 and empties == 240           # batched to strm_buff_sz: 16 flushes
+            # reference cadence: batched to strm_buff_sz, 16 flushes (SURVEY.md section 3.3); default: one flush
+            assert calls == 256 and empties == (240 if batch_kb == "0" else 255)
+    assert all(b == blobs[0] for b in blobs)                 # the stream does not depend on how the input was sliced
     # RAW stream wrapped by hand in a gzip header + {crc_32, in_sz} trailer (mode 11 :3045-3072)
     if fmt == q.QZ_DEFLATE_RAW:
         blob, crc, _, _ = stream_compress(prod, sess, d, 16384)

@@ -87,7 +87,9 @@ if os.path.exists(q.REF_SO) and not os.environ.get("EXTRA_NOCPU"):
     res["cpu_reference_decompress"] = {"GBps_out": round(CALL / dt / 1e9, 2), "threads": T, "sample_MiB_out": CALL >> 20}
 # stream API, BASELINE config 5: RAW, 4 KiB submissions (a slice of the 1 GiB stream)
 SN = int(os.environ.get("EXTRA_STREAM_MIB", "64")) << 20
-for sb in (65536, 2 * 1024 * 1024 - 5 * 1024):
+for sb, batch_kb in ((65536, None), (65536, "0"), (2 * 1024 * 1024 - 5 * 1024, "0")):
+    if batch_kb is None: os.environ.pop("QZB200_STREAM_BATCH_KB", None)
+    else: os.environ["QZB200_STREAM_BATCH_KB"] = batch_kb
     sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW, strm_buff_sz=sb)
     st = q.QzStream(); ocap = 4 << 20; obuf = (C.c_ubyte * ocap)()
     consumed = outb = calls = 0
@@ -100,5 +102,5 @@ for sb in (65536, 2 * 1024 * 1024 - 5 * 1024):
         if last and st.pending_in == 0 and st.pending_out == 0 and consumed == SN: break
     dt = time.perf_counter() - t0
     L.qzEndStream(C.byref(sess), C.byref(st)); prod.end_session(sess)
-    res[f"stream_raw_4KiB_strmbuf_{sb}"] = {"MBps": round(SN / dt / 1e6, 1), "calls": calls, "ratio": round(outb / SN, 4), "stream_MiB": SN >> 20}
+    res[f"stream_raw_4KiB_strmbuf_{sb}_{'batched4MiB' if batch_kb is None else 'per_strm_buff'}"] = {"MBps": round(SN / dt / 1e6, 1), "calls": calls, "ratio": round(outb / SN, 4), "stream_MiB": SN >> 20}
 print(json.dumps(res))
