@@ -15,6 +15,7 @@
 #include <map>
 #include <mutex>
 #include <vector>
+#include <thread>
 #include <algorithm>
 #include "qz_engine.h"
 #include "qz_kernels.cuh"
@@ -474,8 +475,42 @@ static long gzip_header_len(const uint8_t *p, uint64_t avail, bool *has_qz, uint
     return (long)h;
 }
 
+/* Positions in p[lo, hi) that look like the start of a gzip member: magic, method, reserved flag bits clear,
+ * XFL and OS values that exist (RFC 1952 2.3.1).  The reference finds member ends with one linear scan
+ * per member (src/qatzip_gzip.c:244-261); here the whole input is scanned once, sliced over host threads,
+ * and the member walk looks boundaries up in the sorted result. */
+static bool gzip_member_start(const uint8_t *p, uint64_t q, uint64_t n)
+{
+    return q + 10 <= n && p[q] == 0x1f && p[q + 1] == 0x8b && p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0 &&
+           (p[q + 8] == 0 || p[q + 8] == 2 || p[q + 8] == 4) && (p[q + 9] <= 13 || p[q + 9] == 255);
+}
+static void gzip_scan_candidates(const uint8_t *p, uint64_t lo, uint64_t n, std::vector<uint64_t> &out)
+{
+    out.clear();
+    if (n < lo + 10) return;
+    const uint64_t span = n - lo;
+    unsigned T = std::thread::hardware_concurrency(); if (T == 0) T = 4; if (T > 16) T = 16;
+    if (span < (8u << 20)) T = 1;
+    std::vector<std::vector<uint64_t>> part(T);
+    auto work = [&](unsigned t) {
+        const uint64_t a = lo + span * t / T, b = lo + span * (t + 1) / T;
+        uint64_t q = a;
+        while (q < b) {
+            const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, b - q);
+            if (!f) break;
+            q = (uint64_t)(f - p);
+            if (gzip_member_start(p, q, n)) part[t].push_back(q);
+            q++;
+        }
+    };
+    if (T == 1) work(0);
+    else { std::vector<std::thread> th; for (unsigned t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+    for (auto &v : part) out.insert(out.end(), v.begin(), v.end());
+}
+
 extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, QzbDecompressOut *o)
 {
+    std::vector<uint64_t> gz_cand; bool gz_scanned = false;       /* absolute offsets of plausible gzip member starts */
     memset(o, 0, sizeof *o);
     if (!e || !c) return RC_PARAMS;
     CK(cudaSetDevice(e->device));
@@ -657,13 +692,12 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     /* next member by magic scan, footer right before it: reference src/qatzip_gzip.c:244-261.
                      * The guess is verified by the decode (exact length, ISIZE, CRC) and replaced by a
                      * sequential decode of this member if it does not hold. */
-                    uint64_t q = (uint64_t)h + 8; bool found = false;
-                    while (q + 4 <= avail) {
-                        const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, avail - q - 3);
-                        if (!f) break;
-                        q = (uint64_t)(f - p);
-                        if (p[q + 1] == 0x8b && p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0) { found = true; break; }
-                        q++;
+                    if (!gz_scanned) { gzip_scan_candidates(hsrc, in, c->src_len, gz_cand); gz_scanned = true; }
+                    /* first candidate that leaves room for this member's footer and has a believable ISIZE in front */
+                    uint64_t q = 0; bool found = false;
+                    for (auto it = std::lower_bound(gz_cand.begin(), gz_cand.end(), in + (uint64_t)h + 8); it != gz_cand.end(); ++it) {
+                        q = *it - in;
+                        if ((uint64_t)rd32(p + q - 4) <= (q - h - 8) * 1032 + 64) { found = true; break; }
                     }
                     const uint64_t end = found ? q : avail;
                     if (end < (uint64_t)h + 8) { parse_rc = RC_DATA_ERROR; break; }

@@ -469,6 +469,8 @@ def test_gzip_magic_inside_payload(prod, ref):
     chunk = bytearray(rnd.getrandbits(8) for _ in range(150000))
     for pos in (100, 5000, 70000, 70100, 140000):
         chunk[pos:pos + 10] = bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff])
+        if pos in (5000, 70100):
+            chunk[pos - 4:pos] = (1000).to_bytes(4, "little")    # a believable ISIZE in front: passes the scan's plausibility filter
     d = bytes(chunk)
     for maker in (prod, ref):
         blob = maker.compress(d, fmt=q.QZ_DEFLATE_GZIP)
