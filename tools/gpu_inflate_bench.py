@@ -27,7 +27,7 @@ def decode(name, fmt, hw, total_c, n_out):
         st = prod.stats(sess)
         best = min(best, st.kernel_ms)
     L.qzb200CopyToHost(h_back, d_back, n_out)
-    ok = C.string_at(h_back, n_out) == C.string_at(h_in, n_out)
+    ok = all(C.string_at(h_back + o, min(256 << 20, n_out - o)) == C.string_at(h_in + o, min(256 << 20, n_out - o)) for o in range(0, n_out, 256 << 20))
     res[name] = {"GBps_out_kernels": round(n_out / (best / 1e3) / 1e9, 2), "kernel_ms": round(best, 3), "GBps_out_wall_last": round(n_out / wall / 1e9, 2),
                  "members": int(st.units), "launches": int(st.kernel_launches), "exact": ok, "MiB_out": n_out >> 20}
     prod.end_session(sess)
