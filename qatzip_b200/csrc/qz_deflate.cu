@@ -845,84 +845,106 @@ __global__ void __launch_bounds__(1024) qzb_scan_kernel(const uint32_t *in, uint
 #include "qz_xxh32.h"
 __device__ __forceinline__ void st32le(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 
-/* one CTA (128 threads) per chunk */
-__global__ void __launch_bounds__(128) qzb_frame_kernel(QzbCompressJob job)
+/* One CTA (8 warps) per chunk.  Warp 0 turns the pieces' lengths into offsets and, lane per piece, their
+ * checksums into the chunk's (every piece's CRC-32 times x^(8 * bytes after it), XOR-ed: the pieces' terms
+ * are independent); then every warp copies whole pieces, 4 bytes per lane with the loads of eight steps in
+ * flight, realigning through a funnel shift when the destination is not word-aligned. */
+#define QZ_FRAME_WARPS 8
+__global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompressJob job)
 {
-    const uint32_t c = blockIdx.x;
+    const uint32_t c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t off = job.chunk_off[c];
     const uint32_t total = job.chunk_total[c];
     if (off + total > job.dst_cap) return;             /* host reports QZ_BUF_ERROR for this and later chunks */
-    const uint32_t g0 = c * job.pieces_per_chunk, g1 = min(g0 + job.pieces_per_chunk, job.npieces);
+    const uint32_t g0 = c * job.pieces_per_chunk, g1 = min(g0 + job.pieces_per_chunk, job.npieces), np = g1 - g0;   /* np <= 64 */
     const uint64_t chunk_in = (uint64_t)c * job.chunk_sz;
     const uint64_t rem = job.src_len > chunk_in ? job.src_len - chunk_in : 0;
     const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
     const uint32_t hs = qzb_hdr_sz(job.fmt), fs = qzb_ftr_sz(job.fmt), payload = total - hs - fs;
     const uint32_t PIECE = 1u << job.piece_log2;
-    uint8_t *d = job.dst + off;
-    __shared__ uint32_t s_cksum;
-    if (threadIdx.x == 0) {
+    uint8_t *__restrict__ d = job.dst + off;
+    __shared__ uint32_t s_poff[65];                      /* exclusive prefix of the pieces' lengths */
+    if (warp == 0) {
+        /* lengths -> offsets: two pieces per lane */
+        const uint32_t l0 = lane < np ? job.piece_len[g0 + lane] : 0u, l1 = lane + 32 < np ? job.piece_len[g0 + 32 + lane] : 0u;
+        uint32_t i0 = l0, i1 = l1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y0 = __shfl_up_sync(FULL, i0, o), y1 = __shfl_up_sync(FULL, i1, o); if (lane >= (uint32_t)o) { i0 += y0; i1 += y1; } }
+        const uint32_t t0 = __shfl_sync(FULL, i0, 31);
+        s_poff[lane] = i0 - l0; s_poff[32 + lane] = t0 + i1 - l1;
+        if (lane == 31) s_poff[64] = t0 + i1;
+        /* checksum of the chunk */
         uint32_t ck;
         if (job.fmt == QZB_FMT_LZ4) ck = job.chunk_cksum[c];      /* XXH32 written by the xxh kernel */
         else if (job.fmt == QZB_FMT_ZLIB) {
             /* per-piece Adler sums -> chunk Adler-32 (reference footer: src/qatzip_gzip.c:273-281) */
-            uint32_t s1 = 0, s2 = 0;
-            for (uint32_t g = g0; g < g1; g++) {
-                const uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE), w = job.piece_crc[g];
-                qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, pn);
+            ck = 0;
+            if (lane == 0) {
+                uint32_t s1 = 0, s2 = 0;
+                for (uint32_t g = g0; g < g1; g++) {
+                    const uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE), w = job.piece_crc[g];
+                    qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, pn);
+                }
+                ck = qz_adler_finish(s1, s2, chunk_len);
             }
-            ck = qz_adler_finish(s1, s2, chunk_len);
-            job.chunk_cksum[c] = ck;
+            ck = __shfl_sync(FULL, ck, 0);
         } else {
             ck = 0;
-            for (uint32_t g = g0; g < g1; g++) {
-                uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE);
-                ck = (g == g0) ? job.piece_crc[g] : qz_crc32_combine(ck, job.piece_crc[g], pn);
+            for (uint32_t k = lane; k < np; k += 32) {
+                const uint32_t after = chunk_len - min(chunk_len, (k + 1) * PIECE);      /* input bytes behind piece k */
+                ck ^= qz_gf2_mul(job.piece_crc[g0 + k], qz_crc_xpow8(after));
             }
-            job.chunk_cksum[c] = ck;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
         }
-        s_cksum = ck;
-        switch (job.fmt) {
-        case QZB_FMT_GZIP_EXT:
-            d[10] = 12; d[11] = 0; d[12] = 'Q'; d[13] = 'Z'; d[14] = 8; d[15] = 0;
-            st32le(d + 16, chunk_len); st32le(d + 20, payload);
-            /* fall through */
-        case QZB_FMT_GZIP:
-            d[0] = 0x1f; d[1] = 0x8b; d[2] = 8; d[3] = (job.fmt == QZB_FMT_GZIP_EXT) ? 4 : 0;
-            d[4] = d[5] = d[6] = d[7] = 0; d[8] = 0; d[9] = 0xff;
-            break;
-        case QZB_FMT_4B: st32le(d, payload); break;
-        case QZB_FMT_ZLIB: d[0] = 0x78; d[1] = 0x9C; break;           /* reference src/qatzip_gzip.c:263-271 */
-        case QZB_FMT_LZ4:
-            st32le(d, 0x184D2204u); d[4] = 0x4C; d[5] = 0x40; st32le(d + 6, chunk_len); st32le(d + 10, 0);
-            d[14] = (uint8_t)(qz_xxh32(d + 4, 10, 0) >> 8);
-            break;
-        default: break;
+        if (lane == 0) {
+            if (job.fmt != QZB_FMT_LZ4) job.chunk_cksum[c] = ck;
+            switch (job.fmt) {
+            case QZB_FMT_GZIP_EXT:
+                d[10] = 12; d[11] = 0; d[12] = 'Q'; d[13] = 'Z'; d[14] = 8; d[15] = 0;
+                st32le(d + 16, chunk_len); st32le(d + 20, payload);
+                /* fall through */
+            case QZB_FMT_GZIP:
+                d[0] = 0x1f; d[1] = 0x8b; d[2] = 8; d[3] = (job.fmt == QZB_FMT_GZIP_EXT) ? 4 : 0;
+                d[4] = d[5] = d[6] = d[7] = 0; d[8] = 0; d[9] = 0xff;
+                break;
+            case QZB_FMT_4B: st32le(d, payload); break;
+            case QZB_FMT_ZLIB: d[0] = 0x78; d[1] = 0x9C; break;           /* reference src/qatzip_gzip.c:263-271 */
+            case QZB_FMT_LZ4:
+                st32le(d, 0x184D2204u); d[4] = 0x4C; d[5] = 0x40; st32le(d + 6, chunk_len); st32le(d + 10, 0);
+                d[14] = (uint8_t)(qz_xxh32(d + 4, 10, 0) >> 8);
+                break;
+            default: break;
+            }
+            if (fs) {
+                uint8_t *f = d + hs + payload;
+                if (job.fmt == QZB_FMT_LZ4) { st32le(f, 0); st32le(f + 4, ck); }
+                else if (job.fmt == QZB_FMT_ZLIB) { f[0] = (uint8_t)(ck >> 24); f[1] = (uint8_t)(ck >> 16); f[2] = (uint8_t)(ck >> 8); f[3] = (uint8_t)ck; }
+                else { st32le(f, ck); st32le(f + 4, chunk_len); }
+            }
         }
-    }
-    /* payload gather: pieces are contiguous runs; copy byte-wise with 4-byte fast path when aligned */
-    uint32_t o = hs;
-    for (uint32_t g = g0; g < g1; g++) {
-        const uint32_t len = job.piece_len[g];
-        const uint8_t *s = job.slots + (size_t)g * job.slot_stride;
-        uint8_t *dd = d + o;
-        const uint32_t mis = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
-        const uint32_t head = min(mis, len);
-        if (threadIdx.x < head) dd[threadIdx.x] = s[threadIdx.x];
-        const uint32_t nw = (len - head) >> 2;
-        uint32_t *dw = reinterpret_cast<uint32_t *>(dd + head);
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(s);     /* slot is 16-byte aligned */
-        const uint32_t sh = head * 8;
-        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x)
-            dw[i] = sh ? __funnelshift_r(sw[i], sw[i + 1], sh) : sw[i];
-        for (uint32_t i = head + (nw << 2) + threadIdx.x; i < len; i += blockDim.x) dd[i] = s[i];
-        o += len;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && fs) {
-        uint8_t *f = d + hs + payload;
-        if (job.fmt == QZB_FMT_LZ4) { st32le(f, 0); st32le(f + 4, s_cksum); }
-        else if (job.fmt == QZB_FMT_ZLIB) { f[0] = (uint8_t)(s_cksum >> 24); f[1] = (uint8_t)(s_cksum >> 16); f[2] = (uint8_t)(s_cksum >> 8); f[3] = (uint8_t)s_cksum; }
-        else { st32le(f, s_cksum); st32le(f + 4, chunk_len); }
+    /* payload gather: pieces are contiguous runs, one warp per piece */
+    for (uint32_t k = warp; k < np; k += QZ_FRAME_WARPS) {
+        const uint32_t len = s_poff[k + 1] - s_poff[k];
+        const uint8_t *__restrict__ s = job.slots + (size_t)(g0 + k) * job.slot_stride;
+        uint8_t *__restrict__ dd = d + hs + s_poff[k];
+        const uint32_t mis = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
+        const uint32_t head = min(mis, len);
+        if (lane < head) dd[lane] = s[lane];
+        const uint32_t nw = (len - head) >> 2;
+        uint32_t *__restrict__ dw = reinterpret_cast<uint32_t *>(dd + head);
+        const uint32_t *__restrict__ sw = reinterpret_cast<const uint32_t *>(s);     /* slot is 16-byte aligned */
+        const uint32_t sh = head * 8;
+        for (uint32_t i0 = lane; i0 < nw; i0 += 32 * 8) {
+            uint32_t a[8], b2[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; a[u] = i < nw ? sw[i] : 0u; b2[u] = (sh && i < nw) ? sw[i + 1] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; if (i < nw) dw[i] = sh ? __funnelshift_r(a[u], b2[u], sh) : a[u]; }
+        }
+        for (uint32_t i = head + (nw << 2) + lane; i < len; i += 32) dd[i] = s[i];
     }
 }
 
@@ -959,6 +981,6 @@ extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t 
 {
     qzb_chunk_sizes_kernel<<<(job->nchunks + 255) / 256, 256, 0, st>>>(*job);
     qzb_scan_kernel<<<1, 1024, 0, st>>>(job->chunk_total, job->chunk_off, job->nchunks);
-    qzb_frame_kernel<<<job->nchunks, 128, 0, st>>>(*job);
+    qzb_frame_kernel<<<job->nchunks, QZ_FRAME_WARPS * 32, 0, st>>>(*job);
     return cudaGetLastError();
 }
