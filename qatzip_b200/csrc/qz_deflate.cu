@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "qz_kernels.cuh"
+#include "qz_warp.cuh"
 #include "qz_huffman.h"
 #include "qz_crc32.h"
 #include "qz_adler32.h"
@@ -49,34 +50,7 @@ extern "C" __attribute__((visibility("default"))) int qzb_phase_cycles_read(unsi
 #endif
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-
-/* L2 residency control.  The token scratch is written once and read twice by the same SM within
- * microseconds, while the input streams through exactly once: tokens ask L2 to keep them
- * (evict_last), input lines are marked evict_first and skip L1, so the stream does not push the
- * tokens out to HBM.  .cg keeps token accesses coherent at L2 between lanes. */
-__device__ __forceinline__ uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ uint32_t tok_ld(const uint32_t *a, uint64_t pol)
-{
-    uint32_t v; asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol) : "memory"); return v;
-}
-__device__ __forceinline__ uint4 tok_ld4(const uint32_t *a, uint64_t pol)
-{
-    uint4 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ void tok_st(uint32_t *a, uint32_t v, uint64_t pol)
-{
-    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint4 stream_ld16(const uint4 *a, uint64_t pol)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
-    return v;
-}
+__device__ __forceinline__ uint32_t lanemask_lt() { return qz_lanemask_lt(); }
 
 /* unaligned 32-bit read from a 4-byte aligned shared byte array */
 __device__ __forceinline__ uint32_t ld32u(const uint8_t *base, uint32_t off)
@@ -594,6 +568,9 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         if (job.static_huffman) dynb = 0xffffffffu;
         btype = (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
         if (n == 0) btype = 1;
+#ifdef QZ_EMU_TRACE
+        if (lane == 0) fprintf(stderr, "piece %u ntok %u extra %u dynb %u fixb %u hdrbits %u nitems %u hlit %u hdist %u\n", g, ntok, extra_total, dynb, fixb, cs.hdr.bits, cs.hdr.nitems, cs.hdr.hlit, cs.hdr.hdist);
+#endif
     }
 
     if (btype == 0) {
@@ -741,7 +718,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
     __shared__ uint16_t s_lentab[256];
@@ -949,6 +926,7 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
 }
 
 /* ------------------------------------------------------------------------------------------ */
+#ifndef QZ_WARP_EMU
 /* shared memory for `warps` warps sharing `nbuf` piece buffers */
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf)
 {
@@ -984,3 +962,4 @@ extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t 
     qzb_frame_kernel<<<job->nchunks, QZ_FRAME_WARPS * 32, 0, st>>>(*job);
     return cudaGetLastError();
 }
+#endif

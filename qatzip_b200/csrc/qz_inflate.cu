@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "qz_kernels.cuh"
+#include "qz_warp.cuh"
 #include "qz_inflate.h"
 #include "qz_crc32.h"
 #include "qz_adler32.h"
@@ -24,7 +25,7 @@ struct InflWarpSmem {
 };
 
 __device__ __forceinline__ uint32_t bcast(uint32_t v) { return __shfl_sync(FULL, v, 0); }
-__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint32_t lanemask_lt() { return qz_lanemask_lt(); }
 
 /* Warp-parallel form of qz_infl_prepare: counts by shared atomics, first codes / offsets by lane 0
  * (15 steps), the (length, symbol) order by taking symbols 32 at a time -- lanes holding equal lengths
@@ -109,7 +110,7 @@ __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t l
 
 __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob job)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    QZ_DYN_SMEM(smem_raw);
     InflWarpSmem *s_w = reinterpret_cast<InflWarpSmem *>(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob jo
     }
 }
 
+#ifndef QZ_WARP_EMU
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st)
 {
     const size_t smem = sizeof(InflWarpSmem) * 8;          /* 8 warps per CTA, 4 CTAs per SM */
@@ -264,3 +266,4 @@ extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid,
     qzb_inflate_kernel<<<grid, 256, smem, st>>>(*job);
     return cudaGetLastError();
 }
+#endif

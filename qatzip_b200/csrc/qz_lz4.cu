@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "qz_kernels.cuh"
+#include "qz_warp.cuh"
 #include "qz_xxh32.h"
 
 #define FULL 0xffffffffu
@@ -20,7 +21,7 @@
 #define LZ4_LANE_CAP 36
 
 __device__ __forceinline__ uint32_t lz_lane() { return threadIdx.x & 31; }
-__device__ __forceinline__ uint32_t lz_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ uint32_t lz_lt() { return qz_lanemask_lt(); }
 __device__ __forceinline__ uint32_t lz_ld32u(const uint8_t *base, uint32_t off)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(base) + (off >> 2);
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(512) qzb_lz4_pieces_kernel(QzbCompressJob job)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     typedef Lz4WarpSmem<PIECE_LOG2> WS;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    QZ_DYN_SMEM(smem_raw);
     const uint32_t lane = lz_lane(), warp = threadIdx.x >> 5;
     WS &ws = reinterpret_cast<WS *>(smem_raw)[warp];
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(256) qzb_lz4_decompress_kernel(QzbDecompressJo
     }
 }
 
+#ifndef QZ_WARP_EMU
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps)
 {
     return (piece_log2 == 13 ? sizeof(Lz4WarpSmem<13>) : sizeof(Lz4WarpSmem<14>)) * (size_t)warps;
@@ -353,3 +355,4 @@ extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, in
     qzb_lz4_decompress_kernel<<<grid, 256, 0, st>>>(*job);
     return cudaGetLastError();
 }
+#endif

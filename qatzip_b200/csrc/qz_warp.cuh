@@ -1,0 +1,49 @@
+/* qz_warp.cuh -- the few PTX-level helpers the kernels share: lane masks, L2 residency hints, the
+ * dynamic shared-memory declaration.  Under QZ_WARP_EMU (tests/emu: the kernel sources compiled by g++
+ * against a SIMT emulator -- test infrastructure only, never linked into libqatzip.so) they reduce to
+ * plain loads and stores. */
+#ifndef QZ_WARP_CUH
+#define QZ_WARP_CUH
+#include <stdint.h>
+
+#ifdef QZ_WARP_EMU
+#define QZ_DYN_SMEM(name) QZ_EMU_DYN_SMEM(name)
+static inline uint32_t qz_lanemask_lt() { return (1u << emu::lane()) - 1u; }
+static inline uint64_t l2_policy_keep() { return 0; }
+static inline uint64_t l2_policy_stream() { return 0; }
+static inline uint32_t tok_ld(const uint32_t *a, uint64_t) { return *a; }
+static inline uint4 tok_ld4(const uint32_t *a, uint64_t) { return *reinterpret_cast<const uint4 *>(a); }
+static inline void tok_st(uint32_t *a, uint32_t v, uint64_t) { *a = v; }
+static inline uint4 stream_ld16(const uint4 *a, uint64_t) { return *a; }
+#else
+#define QZ_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+__device__ __forceinline__ uint32_t qz_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+/* L2 residency control.  The token scratch is written once and read twice by the same SM within
+ * microseconds, while the input streams through exactly once: tokens ask L2 to keep them
+ * (evict_last), input lines are marked evict_first and skip L1, so the stream does not push the
+ * tokens out to HBM.  .cg keeps token accesses coherent at L2 between lanes. */
+__device__ __forceinline__ uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint32_t tok_ld(const uint32_t *a, uint64_t pol)
+{
+    uint32_t v; asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol) : "memory"); return v;
+}
+__device__ __forceinline__ uint4 tok_ld4(const uint32_t *a, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tok_st(uint32_t *a, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint4 stream_ld16(const uint4 *a, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+#endif
+#endif

@@ -1,0 +1,15 @@
+/* emu_inflate.cpp -- TEST INFRASTRUCTURE: qzb_inflate_kernel (qatzip_b200/csrc/qz_inflate.cu) compiled by g++ against
+ * the SIMT emulator and launched over a caller-made member table, the way qz_engine.cu launches it.  Not part of libqatzip.so. */
+#include "warp_emu.h"
+#include "../../qatzip_b200/csrc/qz_inflate.cu"
+
+extern "C" int emu_inflate(int fmt, const uint8_t *src, uint8_t *dst, const QzbMember *members, QzbMemberResult *results, uint32_t nmembers,
+                           int size_only, int grid)
+{
+    uint32_t ticket[4] = { 0, 0, 0, 0 };
+    QzbDecompressJob job; memset(&job, 0, sizeof job);
+    job.src = src; job.dst = dst; job.members = members; job.results = results; job.nmembers = nmembers; job.fmt = fmt;
+    job.ticket = ticket; job.size_only = size_only;
+    emu::launch((unsigned)(grid < 1 ? 1 : grid), 256, sizeof(InflWarpSmem) * 8, [&] { qzb_inflate_kernel(job); });
+    return 0;
+}

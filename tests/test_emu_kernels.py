@@ -1,0 +1,318 @@
+"""CPU checks of the CUDA kernels' warp logic through the SIMT emulator (tests/emu, harness/qzemu.py).
+
+The kernel sources of qatzip_b200/csrc/*.cu are compiled by g++ against tests/emu/warp_emu.h and run here
+one CTA at a time: what these tests exercise is the very code the GPU runs (match selection, Huffman
+construction, bit emission, framing, the inflate and LZ4 decoders), checked against the oracle port and
+Python's zlib.  This is test infrastructure: the product has no CPU path, nothing here is timed, and the
+parity tests proper are the `-m gpu` ones that go through the C ABI on a B200.
+"""
+import struct
+import zlib
+
+import pytest
+
+from harness import qzemu as E
+from harness.qzapi import Corpus
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    E.build()
+    return E.Emu()
+
+
+def rle(n, seed=1):
+    return Corpus().make(Corpus.REF_RLE, n, seed=seed)
+
+
+def sil(n):
+    return Corpus().make(Corpus.SILESIA_LIKE, max(n, 1))[:n]
+
+
+def noise(n, seed=7):
+    x, out = seed or 1, bytearray()
+    while len(out) < n:
+        x = (x * 6364136223846793005 + 1442695040888963407) & (2 ** 64 - 1)
+        out += struct.pack("<Q", x)
+    return bytes(out[:n])
+
+
+def walk_gzip(blob, ext):
+    """-> [(payload_off, payload_len, crc, isize, hdr_src, hdr_dst)] for a run of members made by the framing kernel"""
+    out, p = [], 0
+    while p < len(blob):
+        assert blob[p:p + 3] == b"\x1f\x8b\x08"
+        if ext:
+            assert blob[p + 3] == 4 and blob[p + 10:p + 16] == b"\x0c\x00QZ\x08\x00" and blob[p + 9] == 0xff
+            src_sz, dst_sz = struct.unpack_from("<II", blob, p + 16)
+            h = 24
+        else:
+            assert blob[p + 3] == 0 and blob[p + 9] == 0xff
+            # plain gzip carries no size: find the end by inflating
+            d = zlib.decompressobj(-15)
+            d.decompress(blob[p + 10:])
+            dst_sz, src_sz, h = len(blob) - p - 10 - len(d.unused_data), None, 10
+        crc, isize = struct.unpack_from("<II", blob, p + h + dst_sz)
+        out.append((p + h, dst_sz, crc, isize, src_sz))
+        p += h + dst_sz + 8
+    assert p == len(blob)
+    return out
+
+
+def inflate_raw(b):
+    d = zlib.decompressobj(-15)
+    out = d.decompress(b) + d.flush()
+    return out, d.eof, len(b) - len(d.unused_data)
+
+
+SIZES = [0, 1, 31, 100, 4095, 8191, 8192, 8193, 20000, 65535, 65536, 65537, 150001]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_deflate_gzip_ext_sizes(emu, port, n):
+    data = sil(n)
+    blob, cks = emu.deflate(data, E.FMT_GZIP_EXT)
+    members = walk_gzip(blob, ext=True)
+    assert len(members) == max(1, (n + 65535) // 65536)
+    got = b""
+    for i, (off, ln, crc, isize, src_sz) in enumerate(members):
+        piece, eof, used = inflate_raw(blob[off:off + ln])
+        chunk = data[i * 65536:(i + 1) * 65536]
+        assert eof and used == ln and piece == chunk
+        assert crc == zlib.crc32(chunk) == cks[i] and isize == len(chunk) == src_sz
+        got += piece
+    assert got == data
+    if n == 0:
+        assert len(blob) == 34          # QZ_COMPRESSED_SZ_OF_EMPTY_FILE
+    # and the oracle's member walk + inflate restores it too
+    assert port.decompress(blob, E.FMT_GZIP_EXT, n + 16) == data
+
+
+@pytest.mark.parametrize("fmt", [E.FMT_4B, E.FMT_GZIP, E.FMT_GZIP_EXT, E.FMT_RAW, E.FMT_ZLIB])
+@pytest.mark.parametrize("make", [sil, rle, noise, lambda n: b"\0" * n, lambda n: (b"abcabcabd" * (n // 9 + 1))[:n]])
+def test_deflate_formats_and_corpora(emu, port, fmt, make):
+    data = make(70000)
+    blob, cks = emu.deflate(data, fmt, chunk=16384)
+    if fmt == E.FMT_ZLIB:
+        p, got = 0, b""
+        for i in range(len(cks)):
+            d = zlib.decompressobj(15)
+            got += d.decompress(blob[p:])
+            assert d.eof
+            p = len(blob) - len(d.unused_data)
+            assert cks[i] == zlib.adler32(data[i * 16384:(i + 1) * 16384])
+        assert p == len(blob) and got == data
+    else:
+        assert port.decompress(blob, fmt, len(data) + 16) == data
+        assert cks == [zlib.crc32(data[i:i + 16384]) for i in range(0, len(data), 16384)]
+    if fmt == E.FMT_RAW:        # one continuous raw stream: non-final chunks end on a flush, the last one carries BFINAL
+        out, eof, used = inflate_raw(blob)
+        assert out == data and eof and used == len(blob)
+    if fmt == E.FMT_4B:
+        p = 0
+        for i in range(len(cks)):
+            (ln,) = struct.unpack_from("<I", blob, p)
+            out, eof, used = inflate_raw(blob[p + 4:p + 4 + ln])
+            assert eof and used == ln and out == data[i * 16384:(i + 1) * 16384]
+            p += 4 + ln
+        assert p == len(blob)
+
+
+def test_deflate_raw_not_last_leaves_stream_open(emu):
+    data = sil(40000)
+    blob, _ = emu.deflate(data, E.FMT_RAW, chunk=16384, last=0)
+    out, eof, used = inflate_raw(blob)
+    assert out == data and not eof and used == len(blob)
+    assert blob[-5:] == b"\x00\x00\x00\xff\xff"            # ends like Z_FULL_FLUSH
+
+
+@pytest.mark.parametrize("geom", [dict(piece_log2=13, hb=11, warps=20, nbuf=17, grid=1), dict(piece_log2=13, hb=11, warps=3, nbuf=1, grid=3),
+                                  dict(piece_log2=13, hb=12, warps=4, nbuf=2, grid=2), dict(piece_log2=14, hb=12, warps=4, nbuf=3, grid=2),
+                                  dict(piece_log2=14, hb=13, warps=2, nbuf=2, grid=1), dict(piece_log2=13, hb=11, warps=10, nbuf=8, grid=2)])
+def test_deflate_geometries(emu, port, geom):
+    data = sil(300000)
+    blob, cks = emu.deflate(data, E.FMT_GZIP, chunk=65536, **geom)
+    assert port.decompress(blob, E.FMT_GZIP, len(data) + 16) == data
+    assert cks == [zlib.crc32(data[i:i + 65536]) for i in range(0, len(data), 65536)]
+
+
+def test_deflate_output_is_reproducible(emu, port):
+    """Same launch twice: same bytes.  Across geometries only the winner of equal-hash insertions inside one 32-position
+    tile may change (the kernel's one intended write/write race), i.e. a few bytes per piece."""
+    data = sil(200000)
+    a, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=4, nbuf=3, grid=2)
+    b, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=4, nbuf=3, grid=2)
+    c, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=7, nbuf=2, grid=1)
+    assert a == b
+    assert abs(len(a) - len(c)) <= len(a) // 500
+    assert port.decompress(c, E.FMT_GZIP_EXT, len(data) + 16) == data
+
+
+@pytest.mark.parametrize("chunk", [1024, 4096, 65536, 524288])
+def test_deflate_chunk_sizes(emu, port, chunk):
+    data = sil(3 * chunk // 2 + 77) if chunk <= 65536 else sil(chunk + 5000)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk)
+    assert port.decompress(blob, E.FMT_GZIP_EXT, len(data) + 16) == data
+
+
+def test_deflate_static_huffman_uses_fixed_or_stored_blocks(emu):
+    data = sil(30000)
+    blob, _ = emu.deflate(data, E.FMT_RAW, chunk=65536, static=1)
+    out, eof, used = inflate_raw(blob)
+    assert out == data and eof
+    assert (blob[0] >> 1) & 3 in (0, 1)             # first block: stored or fixed, never dynamic
+
+
+def test_deflate_ratio_near_zlib1(emu):
+    data = sil(1 << 20)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT)
+    ref = sum(len(zlib.compress(data[i:i + 65536], 1)) + 20 for i in range(0, len(data), 65536))
+    assert len(blob) <= 1.05 * ref, (len(blob), ref)
+
+
+def test_deflate_dest_too_small_keeps_whole_chunks(emu):
+    data = sil(200000)
+    full, _ = emu.deflate(data, E.FMT_GZIP_EXT)
+    members = walk_gzip(full, ext=True)
+    two = members[2][0] - 24                      # bytes of the first two members
+    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100)
+    assert part == full[:two]
+
+
+# ------------------------------------------------------------------ inflate
+
+def one_member(payload_len, out_len, crc, src_off=0, dst_off=0, exact_len=1, exact_out=1, check=1):
+    return dict(src_off=src_off, src_len=payload_len, exact_len=exact_len, dst_off=dst_off, dst_cap=out_len, exact_out=exact_out,
+                expect_cksum=crc, check_cksum=check)
+
+
+@pytest.mark.parametrize("level,strategy", [(0, 0), (1, 0), (6, 0), (9, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)])
+@pytest.mark.parametrize("make", [sil, rle, noise])
+def test_inflate_zlib_made_streams(emu, level, strategy, make):
+    data = make(100000)
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    raw = c.compress(data) + c.flush()
+    out, res = emu.decode(E.FMT_GZIP, raw, [one_member(len(raw), len(data), zlib.crc32(data))], len(data))
+    r = res[0]
+    assert (r.status, r.consumed, r.produced, r.cksum, r.saw_final) == (E.ST_OK, len(raw), len(data), zlib.crc32(data), 1)
+    assert out == data
+
+
+def test_inflate_many_members_mixed_sizes(emu):
+    sizes = [4096, 0, 262144, 1, 8192, 65536, 131072, 16384, 300]
+    datas = [sil(sum(sizes))[sum(sizes[:i]):sum(sizes[:i + 1])] for i in range(len(sizes))]
+    src, members, doff = b"", [], 0
+    for d in datas:
+        c = zlib.compressobj(1, zlib.DEFLATED, -15)
+        raw = c.compress(d) + c.flush()
+        members.append(one_member(len(raw), len(d), zlib.crc32(d), src_off=len(src), dst_off=doff))
+        src += raw + b"\x55" * 3            # unrelated bytes between payloads (footers/headers in a real stream)
+        doff += len(d)
+    out, res = emu.decode(E.FMT_GZIP, src, members, doff, grid=3)
+    assert all(r.status == E.ST_OK for r in res)
+    assert out == b"".join(datas)
+
+
+def test_inflate_our_own_streams(emu):
+    data = sil(200000)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT)
+    members = [one_member(ln, isize, crc, src_off=off, dst_off=i * 65536) for i, (off, ln, crc, isize, _) in enumerate(walk_gzip(blob, ext=True))]
+    out, res = emu.decode(E.FMT_GZIP_EXT, blob, members, len(data))
+    assert [r.status for r in res] == [E.ST_OK] * len(members) and out == data
+
+
+def test_inflate_zlib_format_checks_adler(emu):
+    data = sil(50000)
+    z = zlib.compress(data, 1)
+    m = one_member(len(z) - 6, len(data), zlib.adler32(data), src_off=2)
+    out, res = emu.decode(E.FMT_ZLIB, z, [m], len(data))
+    assert res[0].status == E.ST_OK and out == data
+    m["expect_cksum"] ^= 1
+    _, res = emu.decode(E.FMT_ZLIB, z, [m], len(data))
+    assert res[0].status == E.ST_CKSUM
+
+
+def test_inflate_errors(emu):
+    data = sil(60000)
+    c = zlib.compressobj(1, zlib.DEFLATED, -15)
+    raw = c.compress(data) + c.flush()
+    crc = zlib.crc32(data)
+    # wrong CRC, wrong ISIZE, output too small, truncated input, garbage, reserved block type
+    assert emu.decode(E.FMT_GZIP, raw, [one_member(len(raw), len(data), crc ^ 1)], len(data))[1][0].status == E.ST_CKSUM
+    assert emu.decode(E.FMT_GZIP, raw, [one_member(len(raw), len(data) + 1, crc)], len(data) + 1)[1][0].status == E.ST_SIZE
+    assert emu.decode(E.FMT_GZIP, raw, [one_member(len(raw), len(data) - 100, crc, exact_out=0)], len(data))[1][0].status == E.ST_OUT_FULL
+    assert emu.decode(E.FMT_GZIP, raw, [one_member(len(raw) // 2, len(data), crc)], len(data))[1][0].status in (E.ST_IN_TRUNC, E.ST_DATA_ERROR)
+    bad = bytearray(raw); bad[len(bad) // 2] ^= 0x5a
+    assert emu.decode(E.FMT_GZIP, bytes(bad), [one_member(len(raw), len(data), crc)], len(data))[1][0].status != E.ST_OK
+    assert emu.decode(E.FMT_GZIP, b"\x07" + raw, [one_member(len(raw) + 1, len(data), crc)], len(data))[1][0].status == E.ST_DATA_ERROR
+    # payload followed by extra bytes: exact_len catches it, without exact_len the decoder reports where it stopped
+    r = emu.decode(E.FMT_GZIP, raw + b"\0" * 9, [one_member(len(raw) + 9, len(data), crc)], len(data))[1][0]
+    assert r.status == E.ST_DATA_ERROR
+    r = emu.decode(E.FMT_GZIP, raw + b"\0" * 9, [one_member(len(raw) + 9, len(data), crc, exact_len=0)], len(data))[1][0]
+    assert r.status == E.ST_OK and r.consumed == len(raw)
+
+
+def test_inflate_size_only_mode_reports_lengths_without_writing(emu):
+    data = sil(50000)
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    raw = c.compress(data) + c.flush()
+    out, res = emu.decode(E.FMT_ZLIB, raw + b"tail", [one_member(len(raw) + 4, 1 << 20, 0, exact_len=0, exact_out=0, check=0)], 64, size_only=1)
+    assert (res[0].status, res[0].consumed, res[0].produced) == (E.ST_OK, len(raw), len(data))
+    assert out == b"\0" * 64
+
+
+def test_inflate_raw_chunk_without_bfinal(emu):
+    data = sil(30000)
+    c = zlib.compressobj(1, zlib.DEFLATED, -15)
+    raw = c.compress(data) + c.flush(zlib.Z_FULL_FLUSH)
+    out, res = emu.decode(E.FMT_RAW, raw, [one_member(len(raw), len(data), 0, exact_out=0, check=0)], len(data))
+    assert (res[0].status, res[0].produced, res[0].saw_final) == (E.ST_OK, len(data), 0) and out == data
+
+
+# ------------------------------------------------------------------ LZ4
+
+def walk_lz4(blob):
+    """-> [(payload_off, payload_len, content_size, xxh)] per frame written by the framing kernel"""
+    out, p = [], 0
+    while p < len(blob):
+        assert blob[p:p + 6] == b"\x04\x22\x4d\x18\x4c\x40"
+        (csize,) = struct.unpack_from("<Q", blob, p + 6)
+        q = p + 15
+        while True:
+            (bs,) = struct.unpack_from("<I", blob, q)
+            if bs == 0:
+                break
+            q += 4 + (bs & 0x7fffffff)
+        (xxh,) = struct.unpack_from("<I", blob, q + 4)
+        out.append((p + 15, q - p - 15, csize, xxh))
+        p = q + 8
+    assert p == len(blob)
+    return out
+
+
+@pytest.mark.parametrize("n", [0, 1, 12, 13, 100, 8192, 8193, 65536, 65537, 200000])
+@pytest.mark.parametrize("make", [sil, rle, noise])
+def test_lz4_round_trip(emu, port, n, make):
+    data = make(n)
+    blob, cks = emu.lz4(data)
+    assert port.decompress(blob, E.FMT_LZ4, n + 16) == data
+    frames = walk_lz4(blob)
+    assert [f[2] for f in frames] == [len(data[i:i + 65536]) for i in range(0, max(n, 1), 65536)]
+    assert [f[3] for f in frames] == cks == [port.xxh32(data[i:i + 65536]) for i in range(0, max(n, 1), 65536)]
+    members = [one_member(ln, cs, x, src_off=off, dst_off=i * 65536) for i, (off, ln, cs, x) in enumerate(frames)]
+    out, res = emu.decode(E.FMT_LZ4, blob, members, n)
+    assert [r.status for r in res] == [E.ST_OK] * len(frames) and out == data
+
+
+def test_lz4_decodes_oracle_frames_and_rejects_corruption(emu, port):
+    data = sil(150000)
+    blob = port.compress(data, E.FMT_LZ4)
+    frames = walk_lz4(blob)
+    members, doff = [], 0
+    for off, ln, cs, x in frames:
+        members.append(one_member(ln, cs, x, src_off=off, dst_off=doff)); doff += cs
+    out, res = emu.decode(E.FMT_LZ4, blob, members, len(data))
+    assert [r.status for r in res] == [E.ST_OK] * len(frames) and out == data
+    members[0]["expect_cksum"] ^= 4
+    _, res = emu.decode(E.FMT_LZ4, blob, members, len(data))
+    assert res[0].status == E.ST_CKSUM and res[1].status == E.ST_OK
