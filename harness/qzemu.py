@@ -37,20 +37,20 @@ class Emu:
         V = C.c_void_p
         L.emu_deflate_compress.restype = C.c_long
         L.emu_deflate_compress.argtypes = [C.c_int, V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                           V, C.c_uint64, V]
+                                           V, C.c_uint64, V, C.c_int]
         L.emu_lz4_compress.restype = C.c_long
         L.emu_lz4_compress.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_inflate.argtypes = [C.c_int, V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int, C.c_int]
         L.emu_lz4_decompress.argtypes = [V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int]
 
-    def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None):
+    def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None, group=0):
         """-> (stream bytes, [per-chunk checksum])"""
         data = bytes(data)
         nch = max(1, (len(data) + chunk - 1) // chunk)
         cap = cap if cap is not None else len(data) + len(data) // 8 + 512 * nch + 64
         dst = C.create_string_buffer(max(cap, 1))
         ck = (C.c_uint32 * nch)()
-        n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck)
+        n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck, group)
         assert n >= 0, "geometry not offered by the kernel"
         return dst.raw[:n], list(ck)
 

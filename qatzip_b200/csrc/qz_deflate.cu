@@ -29,6 +29,11 @@
 #define QZ_LANE_CAP 12          /* in-lane match extension cap; longer matches are finished by the warp */
 #define QZ_MAX_MATCH 258
 #define QZ_STAGE_WORDS 64
+/* most warps a CTA of the deflate kernels may have: shared memory admits 20-24, and the bound lets the compiler use
+ * up to 80 registers per thread instead of the 64 a 1024-thread bound would impose */
+#ifndef QZ_DEFLATE_MAX_WARPS
+#define QZ_DEFLATE_MAX_WARPS 24
+#endif
 
 /* Per-phase cycle accounting for on-box diagnosis (A/B build only: make ab ABFLAGS=-DQZ_PHASE_CLOCKS).
  * Lane 0 of every warp adds the cycles since its previous mark to a global counter per phase. */
@@ -478,23 +483,20 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
     __syncwarp();
 }
 
-template <int HB>
-__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, const uint16_t *s_lentab,
-                                        uint32_t lane, const PieceState &ps QZ_TARG)
-{
-    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
-    const bool bfinal = ps.bfinal;
-    uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
-    uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
-    CodeScratch &cs = ws.u.b.cs;
+/* ---- phases 3-4 as building blocks (the per-piece kernel strings them together for one piece; the group
+ * kernel runs the token pass and the emission per piece and the code construction once per group) ---- */
 
-    /* ---- phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
-     *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13) */
+/* phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
+ *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13)
+ * Returns the piece's total of extra bits. */
+template <int HB>
+__device__ __forceinline__ uint32_t token_pass(WarpPriv<HB> &ws, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep)
+{
+    CodeScratch &cs = ws.u.b.cs;
     for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) ws.u.b.hist[i] = 0;
     for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
     cs.d_len[lane] = 0;
     __syncwarp();
-    const uint64_t pkeep = l2_policy_keep();
     uint32_t extra_acc = 0;
     uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;          /* one group ahead: hides the L2 round trip */
     for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
@@ -513,154 +515,224 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
             } else atomicAdd(&ws.u.b.hist[t], 1u);
         }
     }
-    if (lane == 0) tok_st(toks + ntok, 256u, pkeep);      /* end-of-block rides along as the last token */
-    __syncwarp();
-    const uint32_t extra_total = warp_sum(extra_acc);
-    QZ_MARK(3);
+    return extra_acc;
+}
 
-    /* ---- phase 3b: code construction ---- */
-    uint32_t out_bytes = 0;
-    int btype;                          /* 0 stored, 1 fixed, 2 dynamic */
-    {
-        if (lane == 0) {
-            ws.u.b.hist[256] = 1;
-            qz_huff_force_two(ws.u.b.hist, QZ_NUM_LL);
-            qz_huff_force_two(ws.u.b.hist + QZ_DOFF, QZ_NUM_D);
-        }
-        __syncwarp();
-        /* literal/length alphabet */
-        int nk = 0;
-        for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
-            uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.u.b.hist[s] : 0;
-            uint32_t bal = __ballot_sync(FULL, f != 0);
-            if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
-            nk += __popc(bal);
-        }
-        __syncwarp();
-        /* sort in registers; frequencies land back in keys[], symbols in ids[] */
-        if (nk <= 128) warp_sort_split<4>(cs.keys, nk, cs.keys, cs.ids, lane);
-        else if (nk <= 256) warp_sort_split<8>(cs.keys, nk, cs.keys, cs.ids, lane);
-        else warp_sort_split<16>(cs.keys, nk, cs.keys, cs.ids, lane);
-        /* distance alphabet: one key per lane; its frequencies and ids borrow the (not yet planned) header area */
-        {
-            uint32_t *dkeys = reinterpret_cast<uint32_t *>(cs.hdr.items);
-            uint16_t *dids = cs.hdr.items + 64;
-            const uint32_t f = lane < QZ_NUM_D ? ws.u.b.hist[QZ_DOFF + lane] : 0;
-            const int nd = __popc(__ballot_sync(FULL, f != 0));
-            uint32_t x[1] = { f ? QZ_HUFF_KEY(f, lane) : 0xffffffffu };
-            warp_sort_regs<1>(x, lane);
-            if ((int)lane < nd) { dkeys[lane] = x[0] >> 9; dids[lane] = (uint16_t)(x[0] & 511u); }
-            __syncwarp();
-            QZ_MARK(4);
-            warp_lengths_pair(cs.keys, cs.ids, nk, cs.ll_len, dkeys, dids, nd, cs.d_len, lane);
-            QZ_MARK(5);
-        }
-        /* cost of each block type */
-        uint32_t dynb = 0, fixb = 0;
-        for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.u.b.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
-        if (lane < QZ_NUM_D) { uint32_t f = ws.u.b.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
-        dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
-        /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
-        warp_plan_header(cs, cs.keys, lane);
-        QZ_MARK(6);
-        dynb += cs.hdr.bits;
-        const uint32_t storedb = (5 + n) * 8;
-        if (job.static_huffman) dynb = 0xffffffffu;
-        btype = (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
-        if (n == 0) btype = 1;
-#ifdef QZ_EMU_TRACE
-        if (lane == 0) fprintf(stderr, "piece %u ntok %u extra %u dynb %u fixb %u hdrbits %u nitems %u hlit %u hdist %u\n", g, ntok, extra_total, dynb, fixb, cs.hdr.bits, cs.hdr.nitems, cs.hdr.hlit, cs.hdr.hdist);
-#endif
+/* phase 3b: code construction from the histograms in ws.u.b.hist -> code lengths in cs.ll_len / cs.d_len, the planned
+ * dynamic header in cs.hdr, and the cheapest block type for `storedb` bits of stored cost: 0 stored, 1 fixed, 2 dynamic */
+template <int HB>
+__device__ __forceinline__ int choose_block(WarpPriv<HB> &ws, uint32_t extra_total, uint32_t storedb, int static_huffman, uint32_t lane QZ_TARG)
+{
+    CodeScratch &cs = ws.u.b.cs;
+    if (lane == 0) {
+        ws.u.b.hist[256] = 1;
+        qz_huff_force_two(ws.u.b.hist, QZ_NUM_LL);
+        qz_huff_force_two(ws.u.b.hist + QZ_DOFF, QZ_NUM_D);
     }
+    __syncwarp();
+    /* literal/length alphabet */
+    int nk = 0;
+    for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
+        uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.u.b.hist[s] : 0;
+        uint32_t bal = __ballot_sync(FULL, f != 0);
+        if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
+        nk += __popc(bal);
+    }
+    __syncwarp();
+    /* sort in registers; frequencies land back in keys[], symbols in ids[] */
+    if (nk <= 128) warp_sort_split<4>(cs.keys, nk, cs.keys, cs.ids, lane);
+    else if (nk <= 256) warp_sort_split<8>(cs.keys, nk, cs.keys, cs.ids, lane);
+    else warp_sort_split<16>(cs.keys, nk, cs.keys, cs.ids, lane);
+    /* distance alphabet: one key per lane; its frequencies and ids borrow the (not yet planned) header area */
+    {
+        uint32_t *dkeys = reinterpret_cast<uint32_t *>(cs.hdr.items);
+        uint16_t *dids = cs.hdr.items + 64;
+        const uint32_t f = lane < QZ_NUM_D ? ws.u.b.hist[QZ_DOFF + lane] : 0;
+        const int nd = __popc(__ballot_sync(FULL, f != 0));
+        uint32_t x[1] = { f ? QZ_HUFF_KEY(f, lane) : 0xffffffffu };
+        warp_sort_regs<1>(x, lane);
+        if ((int)lane < nd) { dkeys[lane] = x[0] >> 9; dids[lane] = (uint16_t)(x[0] & 511u); }
+        __syncwarp();
+        QZ_MARK(4);
+        warp_lengths_pair(cs.keys, cs.ids, nk, cs.ll_len, dkeys, dids, nd, cs.d_len, lane);
+        QZ_MARK(5);
+    }
+    /* cost of each block type */
+    uint32_t dynb = 0, fixb = 0;
+    for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.u.b.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
+    if (lane < QZ_NUM_D) { uint32_t f = ws.u.b.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
+    dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
+    /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
+    warp_plan_header(cs, cs.keys, lane);
+    QZ_MARK(6);
+    dynb += cs.hdr.bits;
+    if (static_huffman) dynb = 0xffffffffu;
+    return (dynb <= fixb && dynb < storedb) ? 2 : (fixb < storedb ? 1 : 0);
+}
 
-    if (btype == 0) {
-        /* stored block: the piece starts byte-aligned, so the 3 header bits + pad are one byte.
-         * The bytes come from global memory again (the shared piece buffer already belongs to the
-         * partner warp); incompressible pieces are the only ones that pay this second read. */
-        if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
-        for (uint32_t i0 = lane; i0 < n; i0 += 256) {           /* eight loads in flight per lane */
-            uint8_t v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = i0 + 32 * k < n ? ps.src[i0 + 32 * k] : (uint8_t)0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (i0 + 32 * k < n) slot[5 + i0 + 32 * k] = v[k];
-        }
-        out_bytes = 5 + n;
-    } else {
-        /* code tables go where the histograms were: code | len << 16 */
-        QzBitWriter bw;
-        EmitState es; es.bitpos = 0; es.flushed = 0;
-        if (btype == 1) {
-            for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
-            cs.d_len[lane] = 5;
-            __syncwarp();
-        }
-        warp_assign_codes(cs.ll_len, 288, ws.u.b.hist, cs.keys, lane);
-        warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.u.b.hist + QZ_DOFF, cs.keys, lane);
-        uint32_t *clc = cs.keys + 40;                 /* code-length alphabet codes, 19 words */
-        if (btype == 2) warp_assign_codes(cs.hdr.cl_len, QZ_NUM_CL, clc, cs.keys, lane);
-        if (lane == 0) {
-            qz_bw_init(&bw, slotw);
-            if (btype == 2) qz_dyn_header_write_prefix(&bw, &cs.hdr, bfinal);
-            else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
-            es.bitpos = qz_bw_bitpos(&bw); es.flushed = bw.wpos;
-        }
-        es.bitpos = __shfl_sync(FULL, es.bitpos, 0); es.flushed = __shfl_sync(FULL, es.flushed, 0);
-        const uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
-        /* the cl codes must survive the staging window being cleared: keep them in registers */
-        const uint32_t my_clc = (btype == 2 && lane < QZ_NUM_CL) ? clc[lane] : 0u;
+/* phase 3c: open a fixed (btype 1) or dynamic (2) block at the start of slotw: code tables go where the histograms
+ * were (code | len << 16 | extra-bit count << 24), the block header is written; *hb = bits written so far, *pend = the
+ * partial word at that position (the first token run continues it) */
+template <int HB>
+__device__ __forceinline__ void open_block(WarpPriv<HB> &ws, int btype, bool bfinal, uint32_t *slotw, uint32_t lane, uint32_t *hb, uint32_t *pend_out QZ_TARG)
+{
+    CodeScratch &cs = ws.u.b.cs;
+    QzBitWriter bw;
+    EmitState es; es.bitpos = 0; es.flushed = 0;
+    if (btype == 1) {
+        for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
+        cs.d_len[lane] = 5;
         __syncwarp();
-        uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
-        for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
-        __syncwarp();
-        if (lane == 0) st[0] = pend;
-        __syncwarp();
+    }
+    warp_assign_codes(cs.ll_len, 288, ws.u.b.hist, cs.keys, lane);
+    warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.u.b.hist + QZ_DOFF, cs.keys, lane);
+    uint32_t *clc = cs.keys + 40;                 /* code-length alphabet codes, 19 words */
+    if (btype == 2) warp_assign_codes(cs.hdr.cl_len, QZ_NUM_CL, clc, cs.keys, lane);
+    if (lane == 0) {
+        qz_bw_init(&bw, slotw);
+        if (btype == 2) qz_dyn_header_write_prefix(&bw, &cs.hdr, bfinal);
+        else qz_bw_put(&bw, (bfinal ? 1u : 0u) | (1u << 1), 3);
+        es.bitpos = qz_bw_bitpos(&bw); es.flushed = bw.wpos;
+    }
+    es.bitpos = __shfl_sync(FULL, es.bitpos, 0); es.flushed = __shfl_sync(FULL, es.flushed, 0);
+    const uint32_t pend = __shfl_sync(FULL, (uint32_t)bw.acc, 0);
+    /* the cl codes must survive the staging window being cleared: keep them in registers */
+    const uint32_t my_clc = (btype == 2 && lane < QZ_NUM_CL) ? clc[lane] : 0u;
+    __syncwarp();
+    uint32_t *st = cs.keys;                      /* staging window, QZ_STAGE_WORDS words */
+    for (uint32_t i = lane; i < QZ_STAGE_WORDS; i += 32) st[i] = 0;
+    __syncwarp();
+    if (lane == 0) st[0] = pend;
+    __syncwarp();
 
-        QZ_MARK(7);
-        /* run-length coded code lengths of a dynamic header go through the same emitter */
-        if (btype == 2) {
-            const uint32_t nitems = cs.hdr.nitems;
-            for (uint32_t k0 = 0; k0 < nitems; k0 += 32) {
-                uint64_t bits = 0; uint32_t nb = 0;
-                const uint32_t it = k0 + lane < nitems ? cs.hdr.items[k0 + lane] : 0xffffffffu;
-                const uint32_t c = __shfl_sync(FULL, my_clc, it & 31);
-                if (it != 0xffffffffu) { bits = c & 0xffff; nb = c >> 16; bits |= (uint64_t)((it >> 5) & 127) << nb; nb += (it >> 12) & 15; }
-                emit_group(st, slotw, es, bits, nb, lane);
+    QZ_MARK(7);
+    /* run-length coded code lengths of a dynamic header go through the same emitter */
+    if (btype == 2) {
+        const uint32_t nitems = cs.hdr.nitems;
+        for (uint32_t k0 = 0; k0 < nitems; k0 += 32) {
+            uint64_t bits = 0; uint32_t nb = 0;
+            const uint32_t it = k0 + lane < nitems ? cs.hdr.items[k0 + lane] : 0xffffffffu;
+            const uint32_t c = __shfl_sync(FULL, my_clc, it & 31);
+            if (it != 0xffffffffu) { bits = c & 0xffff; nb = c >> 16; bits |= (uint64_t)((it >> 5) & 127) << nb; nb += (it >> 12) & 15; }
+            emit_group(st, slotw, es, bits, nb, lane);
+        }
+    }
+    __syncwarp();
+    *pend_out = st[0]; *hb = es.bitpos;
+    /* code table entries gain their extra-bit counts: code | len << 16 | extra << 24 */
+    if (lane < 29) ws.u.b.hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
+    if (lane < QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
+    if (lane >= QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
+    __syncwarp();
+}
+
+/* phase 4, pass 1: bits the tokens [beg, end) take under the code tables `tab` */
+__device__ __forceinline__ uint32_t count_run_bits(const uint32_t *tab, const uint32_t *toks, uint32_t beg, uint32_t end, uint64_t pkeep)
+{
+    uint32_t mybits = 0;
+    uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);   /* one group ahead: hides the L2 round trip */
+    for (uint32_t j = beg; j < end; j += 4) {
+        const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
+        if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (j + k < end) {
+                const uint32_t t = tt[k];
+                const bool isM = (t >> 31) != 0;
+                const uint32_t c1 = tab[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
+                const uint32_t c2 = tab[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
+                mybits += ((c1 >> 16) & 0xff) + (c1 >> 24) + ((c2 >> 16) & 0xff) + (c2 >> 24);
             }
         }
+    }
+    return mybits;
+}
 
+/* phase 4, pass 2: pack the tokens [beg, end) at bit `start` of slotw through a private 64-bit accumulator.  `acc0` is
+ * what already sits in the first word below the start bit and `owns_first` says this lane writes that word whole (it
+ * continues the block header); every other lane joins its first word by atomic OR when it starts inside one.  With
+ * `trailer` the lane appends the byte-aligning empty stored block (nz zero bits, 00 00 ff ff) after its last token. */
+__device__ __forceinline__ void emit_run(const uint32_t *tab, const uint32_t *toks, uint32_t beg, uint32_t end, uint32_t start, uint32_t acc0,
+                                         bool owns_first, bool trailer, uint32_t nz, uint32_t *slotw, uint64_t pkeep)
+{
+    uint64_t acc = owns_first ? (uint64_t)acc0 : 0ull;
+    uint32_t nacc = start & 31, wpos = start >> 5;
+    bool partial = !owns_first && nacc != 0;
+#define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slotw[wpos] = (uint32_t)acc; \
+                                               acc >>= 32; nacc -= 32; wpos++; } } while (0)
+    uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);
+    for (uint32_t j = beg; j < end; j += 4) {
+        const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
+        if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (j + k < end) {
+                const uint32_t t = tt[k];
+                const bool isM = (t >> 31) != 0;
+                const uint32_t c1 = tab[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
+                const uint32_t c2 = tab[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
+                const uint32_t l1 = (c1 >> 16) & 0xff, l2 = (c2 >> 16) & 0xff;
+                const uint32_t lv = isM ? (t >> 21) & 31 : 0u, dv = isM ? t & 0x1fff : 0u;
+                acc |= (uint64_t)((c1 & 0xffff) | (lv << l1)) << nacc; nacc += l1 + (c1 >> 24);
+                QZ_EMIT_FLUSH();
+                acc |= (uint64_t)((c2 & 0xffff) | (dv << l2)) << nacc; nacc += l2 + (c2 >> 24);
+                QZ_EMIT_FLUSH();
+            }
+        }
+    }
+    if (trailer) {          /* owner of the end-of-block token: empty stored block */
+        nacc += nz; QZ_EMIT_FLUSH();
+        nacc += 16; QZ_EMIT_FLUSH();
+        acc |= (uint64_t)0xffffu << nacc; nacc += 16; QZ_EMIT_FLUSH();
+    }
+    if ((uint32_t)acc) atomicOr(slotw + wpos, (uint32_t)acc);
+#undef QZ_EMIT_FLUSH
+}
+
+/* stored block for one piece: the piece starts byte-aligned, so the 3 header bits + pad are one byte.
+ * The bytes come from global memory again (the shared piece buffer already belongs to another warp);
+ * incompressible pieces are the only ones that pay this second read. */
+__device__ __forceinline__ uint32_t stored_piece(uint8_t *slot, const uint8_t *src, uint32_t n, bool bfinal, uint32_t lane)
+{
+    if (lane == 0) { slot[0] = bfinal ? 1 : 0; slot[1] = (uint8_t)n; slot[2] = (uint8_t)(n >> 8); slot[3] = (uint8_t)~n; slot[4] = (uint8_t)(~n >> 8); }
+    for (uint32_t i0 = lane; i0 < n; i0 += 256) {           /* eight loads in flight per lane */
+        uint8_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = i0 + 32 * k < n ? src[i0 + 32 * k] : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (i0 + 32 * k < n) slot[5 + i0 + 32 * k] = v[k];
+    }
+    return 5 + n;
+}
+
+/* one piece as its own block (or run of blocks): everything after the token pass */
+template <int HB>
+__device__ __forceinline__ void finish_piece(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, uint32_t lane, const PieceState &ps,
+                                             uint32_t extra_total, uint64_t pkeep QZ_TARG)
+{
+    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
+    const bool bfinal = ps.bfinal;
+    uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
+    uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
+
+    uint32_t out_bytes = 0;
+    int btype = choose_block<HB>(ws, extra_total, (5 + n) * 8, job.static_huffman, lane QZ_TPASS);
+    if (n == 0) btype = 1;
+
+    if (btype == 0) out_bytes = stored_piece(slot, ps.src, n, bfinal, lane);
+    else {
+        uint32_t hb, pend2;
+        open_block<HB>(ws, btype, bfinal, slotw, lane, &hb, &pend2 QZ_TPASS);
         /* ---- phase 4: emit ----
          * Every lane codes a contiguous run of tokens: pass 1 adds up the run's bit length, a warp scan
          * turns the lengths into bit offsets, pass 2 packs the run through a private 64-bit accumulator
          * straight into the slot.  Words that hold a run boundary are zeroed first and receive their
          * parts by atomic OR; every other word is written whole by exactly one lane.  The end-of-block
          * code is the last token; the lane that owns it also appends the byte-alignment trailer. */
-        __syncwarp();
-        const uint32_t pend2 = st[0], hb = es.bitpos;
-        /* code table entries gain their extra-bit counts: code | len << 16 | extra << 24 */
-        if (lane < 29) ws.u.b.hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
-        if (lane < QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
-        if (lane >= QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
-        __syncwarp();
         const uint32_t NT = ntok + 1;
         const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
         const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-        uint32_t mybits = 0;
-        uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);   /* one group ahead: hides the L2 round trip */
-        for (uint32_t j = beg; j < end; j += 4) {
-            const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
-            if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (j + k < end) {
-                    const uint32_t t = tt[k];
-                    const bool isM = (t >> 31) != 0;
-                    const uint32_t c1 = ws.u.b.hist[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
-                    const uint32_t c2 = ws.u.b.hist[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
-                    mybits += ((c1 >> 16) & 0xff) + (c1 >> 24) + ((c2 >> 16) & 0xff) + (c2 >> 24);
-                }
-            }
-        }
+        const uint32_t mybits = count_run_bits(ws.u.b.hist, toks, beg, end, pkeep);
         uint32_t incl = mybits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -671,40 +743,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
         slotw[start >> 5] = 0;
         if (lane == 31) slotw[end_bit2 >> 5] = 0;
         __syncwarp();
-        {
-            uint64_t acc = lane == 0 ? (uint64_t)pend2 : 0ull;
-            uint32_t nacc = start & 31, wpos = start >> 5;
-            bool partial = lane != 0 && nacc != 0;
-#define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slotw[wpos] = (uint32_t)acc; \
-                                               acc >>= 32; nacc -= 32; wpos++; } } while (0)
-            qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);
-            for (uint32_t j = beg; j < end; j += 4) {
-                const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
-                if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (j + k < end) {
-                        const uint32_t t = tt[k];
-                        const bool isM = (t >> 31) != 0;
-                        const uint32_t c1 = ws.u.b.hist[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
-                        const uint32_t c2 = ws.u.b.hist[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
-                        const uint32_t l1 = (c1 >> 16) & 0xff, l2 = (c2 >> 16) & 0xff;
-                        const uint32_t lv = isM ? (t >> 21) & 31 : 0u, dv = isM ? t & 0x1fff : 0u;
-                        acc |= (uint64_t)((c1 & 0xffff) | (lv << l1)) << nacc; nacc += l1 + (c1 >> 24);
-                        QZ_EMIT_FLUSH();
-                        acc |= (uint64_t)((c2 & 0xffff) | (dv << l2)) << nacc; nacc += l2 + (c2 >> 24);
-                        QZ_EMIT_FLUSH();
-                    }
-                }
-            }
-            if (!bfinal && beg < NT && end == NT) {          /* owner of the end-of-block token: empty stored block */
-                nacc += nz; QZ_EMIT_FLUSH();
-                nacc += 16; QZ_EMIT_FLUSH();
-                acc |= (uint64_t)0xffffu << nacc; nacc += 16; QZ_EMIT_FLUSH();
-            }
-            if ((uint32_t)acc) atomicOr(slotw + wpos, (uint32_t)acc);
-#undef QZ_EMIT_FLUSH
-        }
+        emit_run(ws.u.b.hist, toks, beg, end, start, pend2, lane == 0, !bfinal && beg < NT && end == NT, nz, slotw, pkeep);
         out_bytes = (end_bit2 + 7) >> 3;
         __syncwarp();
     }
@@ -713,8 +752,21 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
     QZ_MARK(8);
 }
 
+template <int HB>
+__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, const uint16_t *s_lentab,
+                                        uint32_t lane, const PieceState &ps QZ_TARG)
+{
+    const uint64_t pkeep = l2_policy_keep();
+    const uint32_t extra_acc = token_pass<HB>(ws, toks, ps.ntok, s_lentab, lane, pkeep);
+    if (lane == 0) tok_st(toks + ps.ntok, 256u, pkeep);      /* end-of-block rides along as the last token */
+    __syncwarp();
+    const uint32_t extra_total = warp_sum(extra_acc);
+    QZ_MARK(3);
+    finish_piece<HB>(job, ws, toks, lane, ps, extra_total, pkeep QZ_TPASS);
+}
+
 template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
+__global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
@@ -768,6 +820,183 @@ __global__ void __launch_bounds__(1024) qzb_deflate_pieces_kernel(QzbCompressJob
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
         phase34<HB>(job, ws, toks, s_lentab, lane, ps QZ_TPASS);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Group kernel: QZ_GROUP consecutive pieces of one chunk (64 KiB with 8 KiB pieces) become ONE deflate block.
+ * Eight warps take a group together.  Each runs phases 1-2 and the token pass on its own piece exactly as above
+ * (private window, private token scratch), then the group's leader adds up the eight histograms and does the
+ * serial work once -- sort, Huffman lengths, header plan, block type, canonical codes, block header -- and every
+ * warp packs its tokens with the shared code tables at its bit offset inside the group's output, which starts at the
+ * first piece's slot.  Against one block per piece this divides the per-block work (a quarter of a piece's time)
+ * and the per-block bytes (dynamic header, flush marker) by eight; the stream is what a zlib deflate with a
+ * Z_FULL_FLUSH per 64 KiB would look like.  Warps of a group meet at a named barrier (bar.sync id, 256); groups of
+ * one CTA are independent of each other.  Used when a chunk is a whole number of groups (hw_buff_sz >= 64 KiB). */
+#define QZ_GROUP 8
+struct GroupShared {
+    uint32_t ticket, bfinal, btype, hb, pend;
+    uint32_t nbytes[QZ_GROUP], ntok[QZ_GROUP], extra[QZ_GROUP], bits[QZ_GROUP];
+};
+#ifdef QZ_WARP_EMU
+static inline void group_bar(uint32_t id) { emu::named_barrier(id, QZ_GROUP * 32); }
+#else
+__device__ __forceinline__ void group_bar(uint32_t id) { __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(QZ_GROUP * 32) : "memory"); }
+#endif
+
+template <int PIECE_LOG2, int HB>
+__global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
+{
+    constexpr int PIECE = 1 << PIECE_LOG2;
+    static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
+    QZ_DYN_SMEM(smem_raw);
+    __shared__ uint32_t s_crc_tab[256];
+    __shared__ uint32_t s_xstrip[5];
+    __shared__ uint16_t s_lentab[256];
+    __shared__ uint32_t s_busy[1];
+    __shared__ GroupShared s_grp[QZ_DEFLATE_MAX_WARPS / QZ_GROUP];
+    constexpr uint32_t STRIP = PIECE / 32 + 4;
+
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    PieceBuf<PIECE_LOG2> *bufs = reinterpret_cast<PieceBuf<PIECE_LOG2> *>(smem_raw);
+    WarpPriv<HB> *wsv = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>));
+    WarpPriv<HB> &ws = wsv[warp];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
+    if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
+    if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;
+    __syncthreads();
+
+    const uint32_t grp = warp / QZ_GROUP, wg = warp % QZ_GROUP, bar = 1 + grp;
+    GroupShared &G = s_grp[grp];
+    WarpPriv<HB> &lead = wsv[grp * QZ_GROUP];                 /* the leader's slice: group histogram, then the code tables */
+    const uint32_t gwarp = blockIdx.x * nwarps + warp;
+    uint32_t *toks = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
+    const uint32_t gpc = job.pieces_per_chunk / QZ_GROUP;     /* groups per chunk */
+    const uint64_t pkeep = l2_policy_keep();
+#ifdef QZ_PHASE_CLOCKS
+    long long tlast = clock64();
+#endif
+    for (;;) {
+        if (wg == 0 && lane == 0) { G.ticket = atomicAdd(job.ticket, 1u); G.bfinal = 0; }
+        group_bar(bar);
+        const uint32_t gi = G.ticket;
+        if (gi >= job.ngroups) break;
+        const uint32_t chunk = gi / gpc, blk = gi - chunk * gpc;
+        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_GROUP, g = g0 + wg;
+        /* this warp's piece: n = 0 for pieces behind the end of a ragged last chunk */
+        PieceState ps;
+        bool chunk_end;
+        {
+            const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
+            const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
+            const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+            const uint32_t p_off = (blk * QZ_GROUP + wg) << PIECE_LOG2;
+            ps.g = g; ps.n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u; ps.ntok = 0; ps.extra_total = 0; ps.bfinal = false;
+            ps.src = job.src + chunk_off + p_off;
+            chunk_end = ps.n != 0 && p_off + ps.n == chunk_len;
+        }
+        if (ps.n) {
+            uint32_t b = 0;
+            if (lane == 0) {
+                uint32_t ns = 128;
+                for (;;) {
+                    const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&s_busy[0]);
+                    if (m) {
+                        b = __ffs(m) - 1;
+                        if (atomicAnd(&s_busy[0], ~(1u << b)) & (1u << b)) break;
+                        continue;
+                    }
+                    __nanosleep(ns);
+                    if (ns < 4096) ns <<= 1;
+                }
+                __threadfence_block();
+            }
+            b = __shfl_sync(FULL, b, 0);
+            QZ_MARK(0);
+            phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
+        }
+        /* token pass on the private histogram; the last piece of the block carries the end-of-block token */
+        const uint32_t extra = warp_sum(token_pass<HB>(ws, toks, ps.ntok, s_lentab, lane, pkeep));
+        const bool last_in_group = ps.n != 0 && (wg == QZ_GROUP - 1 || chunk_end);
+        if (lane == 0) {
+            if (last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
+            G.nbytes[wg] = ps.n; G.ntok[wg] = ps.ntok + (last_in_group ? 1u : 0u); G.extra[wg] = extra;
+            if (ps.bfinal) G.bfinal = 1;
+        }
+        QZ_MARK(3);
+        group_bar(bar);
+        /* A group that mixes incompressible pieces (close to one token per byte) with compressible ones is better off
+         * with a block per piece: one code table cannot serve both, and only whole blocks can fall back to stored. */
+        {
+            uint32_t hi = 0, lo = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < QZ_GROUP; i++) {
+                const uint32_t nb = G.nbytes[i];
+                if (nb) { const uint32_t r = (G.ntok[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
+            }
+            if (hi > 920u && lo < 768u) {
+                if (ps.n) {
+                    if (lane == 0 && !last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
+                    __syncwarp();
+                    finish_piece<HB>(job, ws, toks, lane, ps, extra, pkeep QZ_TPASS);
+                }
+                continue;
+            }
+        }
+        /* leader: one histogram, one set of codes, one block header for the group */
+        if (wg == 0) {
+            uint32_t extra_total = 0, nbytes = 0, npc = 0;
+            for (int i = 0; i < QZ_GROUP; i++) { extra_total += G.extra[i]; nbytes += G.nbytes[i]; npc += G.nbytes[i] ? 1u : 0u; }
+            for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) {
+                uint32_t f = ws.u.b.hist[s];
+#pragma unroll
+                for (int i = 1; i < QZ_GROUP; i++) f += wsv[grp * QZ_GROUP + i].u.b.hist[s];
+                ws.u.b.hist[s] = f;
+            }
+            __syncwarp();
+            const int btype = choose_block<HB>(ws, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
+            uint32_t hb = 0, pend = 0;
+            if (btype) open_block<HB>(ws, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
+            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
+        }
+        group_bar(bar);
+        const uint32_t btype = G.btype;
+        const bool gfinal = G.bfinal != 0;
+        if (btype == 0) {
+            /* incompressible group: every piece is its own stored block in its own slot, as in the per-piece kernel */
+            uint32_t out_bytes = 0;
+            if (ps.n) out_bytes = stored_piece(job.slots + (size_t)g * job.slot_stride, ps.src, ps.n, ps.bfinal, lane);
+            if (lane == 0 && ps.n) job.piece_len[g] = out_bytes;
+        } else {
+            uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
+            const uint32_t NT = G.ntok[wg];
+            const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
+            const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
+            const uint32_t mybits = count_run_bits(lead.u.b.hist, toks, beg, end, pkeep);
+            uint32_t incl = mybits;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+            if (lane == 31) G.bits[wg] = incl;
+            group_bar(bar);
+            uint32_t before = G.hb, total = G.hb;
+#pragma unroll
+            for (int i = 0; i < QZ_GROUP; i++) { const uint32_t bi = G.bits[i]; if (i < (int)wg) before += bi; total += bi; }
+            const uint32_t start = before + incl - mybits;
+            const uint32_t end_bit = total;
+            const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);
+            const uint32_t end_bit2 = gfinal ? end_bit : end_bit + nz + 32;
+            slotw[start >> 5] = 0;
+            if (wg == QZ_GROUP - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
+            group_bar(bar);
+            /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
+            const bool owns_eob = last_in_group && beg < NT && end == NT;
+            emit_run(lead.u.b.hist, toks, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
+            if (lane == 0 && ps.n) job.piece_len[g] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
+        }
+        __syncwarp();
+        QZ_MARK(8);
     }
 }
 
@@ -902,26 +1131,33 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
         }
     }
     __syncthreads();
-    /* payload gather: pieces are contiguous runs, one warp per piece */
-    for (uint32_t k = warp; k < np; k += QZ_FRAME_WARPS) {
-        const uint32_t len = s_poff[k + 1] - s_poff[k];
-        const uint8_t *__restrict__ s = job.slots + (size_t)(g0 + k) * job.slot_stride;
-        uint8_t *__restrict__ dd = d + hs + s_poff[k];
-        const uint32_t mis = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
-        const uint32_t head = min(mis, len);
-        if (lane < head) dd[lane] = s[lane];
-        const uint32_t nw = (len - head) >> 2;
-        uint32_t *__restrict__ dw = reinterpret_cast<uint32_t *>(dd + head);
-        const uint32_t *__restrict__ sw = reinterpret_cast<const uint32_t *>(s);     /* slot is 16-byte aligned */
-        const uint32_t sh = head * 8;
-        for (uint32_t i0 = lane; i0 < nw; i0 += 32 * 8) {
-            uint32_t a[8], b2[8];
+    /* payload gather: every piece's bytes (a group's block sits whole in its first piece's slot, the other seven are
+     * empty) are cut into runs of 4 KiB that are dealt to the warps in turn */
+    constexpr uint32_t SUB = 4096;
+    uint32_t item = 0;
+    for (uint32_t k = 0; k < np; k++) {
+        const uint32_t plen = s_poff[k + 1] - s_poff[k];
+        for (uint32_t o = 0; o < plen; o += SUB, item++) {
+            if (item % QZ_FRAME_WARPS != warp) continue;
+            const uint32_t len = min(SUB, plen - o);
+            const uint8_t *__restrict__ s = job.slots + (size_t)(g0 + k) * job.slot_stride + o;     /* slot and o are 16-byte aligned */
+            uint8_t *__restrict__ dd = d + hs + s_poff[k] + o;
+            const uint32_t mis = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dd) & 3)) & 3);
+            const uint32_t head = min(mis, len);
+            if (lane < head) dd[lane] = s[lane];
+            const uint32_t nw = (len - head) >> 2;
+            uint32_t *__restrict__ dw = reinterpret_cast<uint32_t *>(dd + head);
+            const uint32_t *__restrict__ sw = reinterpret_cast<const uint32_t *>(s);
+            const uint32_t sh = head * 8;
+            for (uint32_t i0 = lane; i0 < nw; i0 += 32 * 8) {
+                uint32_t a[8], b2[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; a[u] = i < nw ? sw[i] : 0u; b2[u] = (sh && i < nw) ? sw[i + 1] : 0u; }
+                for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; a[u] = i < nw ? sw[i] : 0u; b2[u] = (sh && i < nw) ? sw[i + 1] : 0u; }
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; if (i < nw) dw[i] = sh ? __funnelshift_r(a[u], b2[u], sh) : a[u]; }
+                for (int u = 0; u < 8; u++) { const uint32_t i = i0 + 32 * u; if (i < nw) dw[i] = sh ? __funnelshift_r(a[u], b2[u], sh) : a[u]; }
+            }
+            for (uint32_t i = head + (nw << 2) + lane; i < len; i += 32) dd[i] = s[i];
         }
-        for (uint32_t i = head + (nw << 2) + lane; i < len; i += 32) dd[i] = s[i];
     }
 }
 
@@ -947,11 +1183,30 @@ static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    if (nbuf < 1 || nbuf > 32 || warps < 1 || warps > 32) return cudaErrorInvalidValue;
+    if (nbuf < 1 || nbuf > 32 || warps < 1 || warps > QZ_DEFLATE_MAX_WARPS) return cudaErrorInvalidValue;
     if (job->piece_log2 == 13 && hb == 11) return launch_deflate<13, 11>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 12) return launch_deflate<13, 12>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 14 && hb == 12) return launch_deflate<14, 12>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 14 && hb == 13) return launch_deflate<14, 13>(*job, grid, warps, nbuf, st);
+    return cudaErrorInvalidValue;
+}
+
+template <int P, int H>
+static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, int warps, int nbuf, cudaStream_t st)
+{
+    size_t smem = sizeof(WarpPriv<H>) * (size_t)warps + sizeof(PieceBuf<P>) * (size_t)nbuf;
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_groups_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qzb_deflate_groups_kernel<P, H><<<grid, warps * 32, smem, st>>>(job, nbuf);
+    return cudaGetLastError();
+}
+
+/* group kernel (one deflate block per QZ_GROUP pieces): warps must be a multiple of QZ_GROUP, job->ngroups set */
+extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
+{
+    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups) return cudaErrorInvalidValue;
+    if (job->piece_log2 == 13 && hb == 11) return launch_deflate_groups<13, 11>(*job, grid, warps, nbuf, st);
+    if (job->piece_log2 == 13 && hb == 12) return launch_deflate_groups<13, 12>(*job, grid, warps, nbuf, st);
     return cudaErrorInvalidValue;
 }
 

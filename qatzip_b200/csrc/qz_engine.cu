@@ -24,6 +24,7 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
@@ -52,6 +53,9 @@ extern "C" int qzb_runtime_devices(void)
     });
     return g_ndev;
 }
+#ifndef QZB200_GROUP_DEFAULT
+#define QZB200_GROUP_DEFAULT 0
+#endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
 {
@@ -80,6 +84,9 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (fmb > mb) fmb = mb;
     t->first_batch_bytes = (size_t)fmb << 20;
     t->taper = env_int("QZB200_TAPER", 0);
+    /* deflate block granularity: 1 = one block per group of 8 pieces (group kernel, chunks that are a whole number of
+     * groups, i.e. hw_buff_sz >= 64 KiB with 8 KiB pieces), 0 = one block per piece everywhere */
+    t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -263,15 +270,22 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         if (warps <= 0 || warps > 16) warps = 16;
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
+    } else if (t.group && t.piece_log2 == 13 && len && job.pieces_per_chunk % 8 == 0) {
+        /* group kernel: CTAs of 2 or 3 groups of 8 warps */
+        const uint32_t gpc = job.pieces_per_chunk / 8;
+        job.ngroups = (job.nchunks - 1) * gpc + (last_pieces + 7) / 8;
+        if (warps != 8 && warps != 16 && warps != 24) { warps = 24; if (nbuf <= 0) nbuf = 15; }
+        if (nbuf <= 0 || nbuf > warps) nbuf = (warps * 5 + 7) / 8;
+        while (nbuf > 1 && smem_for(warps, nbuf) + 3328 > smem_cap) nbuf--;
     } else {
-        if (warps <= 0 || warps > 32) { warps = 20; if (nbuf <= 0) nbuf = 17; }    /* measured best split of the 227 KB (tools/gpu_geom.py sweep) */
+        if (warps <= 0 || warps > 24) { warps = 20; if (nbuf <= 0) nbuf = 17; }      /* 24 = QZ_DEFLATE_MAX_WARPS (qz_deflate.cu) */
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
     ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps, nbuf) + 3328));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
-    const int need = (int)((job.npieces + warps - 1) / warps);
+    const int need = job.ngroups ? (int)((job.ngroups + warps / 8 - 1) / (warps / 8)) : (int)((job.npieces + warps - 1) / warps);
     if (grid > need) grid = std::max(1, need);
 
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
@@ -289,6 +303,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_groups(&job, t.hash_bits, grid, warps, nbuf, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

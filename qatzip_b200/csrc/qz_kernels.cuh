@@ -35,6 +35,7 @@ struct QzbCompressJob {
     uint32_t *chunk_total;       /* [nchunks] header + payload + footer bytes */
     uint64_t *chunk_off;         /* [nchunks + 1] exclusive prefix of chunk_total */
     uint32_t *chunk_cksum;       /* [nchunks] CRC-32, Adler-32 (zlib) or XXH32 of the chunk's input */
+    uint32_t ngroups;            /* group kernel only: blocks of 8 pieces over all chunks (0 = per-piece kernel) */
 };
 
 /* Decompress side: one unit = one gzip member / 4B block / raw stream / LZ4 frame. */

@@ -45,6 +45,10 @@ extern "C" void emu_job_setup(QzbCompressJob *job, EmuCompressBuffers *b, int fm
     job->piece_len = (uint32_t *)(m + o_plen); job->piece_crc = (uint32_t *)(m + o_pcrc);
     job->chunk_total = (uint32_t *)(m + o_tot); job->chunk_cksum = (uint32_t *)(m + o_ck);
     job->chunk_off = (uint64_t *)(m + o_off); job->ticket = (uint32_t *)(m + o_ticket);
+    {   /* group kernel: blocks of QZ_GROUP pieces (set for every job; the per-piece kernel ignores it) */
+        const uint32_t gpc = job->pieces_per_chunk / QZ_GROUP;
+        job->ngroups = (job->pieces_per_chunk % QZ_GROUP == 0 && len) ? (job->nchunks - 1) * gpc + (last_pieces + QZ_GROUP - 1) / QZ_GROUP : 0u;
+    }
     b->tok.assign((size_t)resident_warps * QZB_TOK_STRIDE(PIECE), 0xEEEEEEEEu);
     job->tok_scratch = b->tok.data();
     job->dst = dst; job->dst_cap = cap;
@@ -64,15 +68,24 @@ extern "C" long emu_frame(const QzbCompressJob *jobp, uint32_t *chunk_cksum_out)
 }
 
 /* One batch through the deflate kernels.  Geometry (piece size, hash bits, warps and piece buffers per CTA, CTAs)
- * is the caller's.  Returns bytes produced, or -1 for an unsupported geometry. */
+ * is the caller's.  Returns bytes produced, or -1 for an unsupported geometry.
+ * group != 0: the group kernel (one deflate block per 8 pieces) instead of the per-piece kernel. */
 extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman,
-                                     int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out)
+                                     int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int group)
 {
     if (warps < 1 || warps > 32 || nbuf < 1 || nbuf > warps || grid < 1) return -1;
     QzbCompressJob job; EmuCompressBuffers b;
     emu_job_setup(&job, &b, fmt, src, len, chunk_sz, last, static_huffman, piece_log2, grid * warps, dst, cap);
     size_t smem;
     std::function<void()> body;
+    if (group) {
+        if (!job.ngroups || warps % QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || piece_log2 != 13) return -1;
+        if (hb == 11) { smem = sizeof(WarpPriv<11>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_groups_kernel<13, 11>(job, nbuf); }; }
+        else if (hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_groups_kernel<13, 12>(job, nbuf); }; }
+        else return -1;
+        emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
+        return emu_frame(&job, chunk_cksum_out);
+    }
     if (piece_log2 == 13 && hb == 11) { smem = sizeof(WarpPriv<11>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 11>(job, nbuf); }; }
     else if (piece_log2 == 13 && hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 12>(job, nbuf); }; }
     else if (piece_log2 == 14 && hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<14>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<14, 12>(job, nbuf); }; }

@@ -16,8 +16,8 @@ asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
 
 namespace emu {
 namespace {
-enum St { RUN, WAIT_WARP, WAIT_CTA, DONE };
-struct Fiber { void *sp; unsigned tid; St st; unsigned gen; void *site; };
+enum St { RUN, WAIT_WARP, WAIT_CTA, WAIT_NAMED, DONE };
+struct Fiber { void *sp; unsigned tid; St st; unsigned gen; void *site; unsigned bar; };
 struct Warp { unsigned nlive, arrived; uint32_t live; int op; void *site; unsigned gen0; uint32_t snap[2]; uint64_t x[2][32]; };
 
 const size_t STACK = 256 << 10;
@@ -29,6 +29,7 @@ alignas(128) uint8_t smem[SMEM_MAX];
 void *sched_sp;
 Fiber *cur;
 unsigned cta_live, cta_arrived;
+unsigned named_arrived[16];
 const std::function<void()> *body_fn;
 unsigned long long ncoll;
 
@@ -99,6 +100,15 @@ void syncthreads()
     else { cur->st = WAIT_CTA; to_scheduler(); }
 }
 void yield_sleep() { to_scheduler(); }
+/* bar.sync id, count: `count` threads of the CTA meet at hardware barrier `id` (1..15) */
+void named_barrier(unsigned id, unsigned count)
+{
+    if (id == 0 || id > 15 || count == 0 || count % 32) die("named barrier: bad id or thread count");
+    if (++named_arrived[id] == count) {
+        named_arrived[id] = 0;
+        for (auto &f : fibers) if (f.st == WAIT_NAMED && f.bar == id) f.st = RUN;
+    } else { cur->st = WAIT_NAMED; cur->bar = id; to_scheduler(); }
+}
 
 void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &body)
 {
@@ -117,6 +127,7 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
         fibers.assign(block, Fiber());
         warps.assign((block + 31) / 32, Warp());
         cta_live = block; cta_arrived = 0;
+        memset(named_arrived, 0, sizeof named_arrived);
         for (unsigned t = 0; t < block; t++) {
             Fiber &f = fibers[t];
             f.tid = t; f.st = RUN; f.gen = 0;

@@ -51,6 +51,7 @@ const uint64_t *exchange(int op, uint64_t v, uint32_t *live);
 void syncwarp();
 void syncthreads();
 void yield_sleep();
+void named_barrier(unsigned id, unsigned count);
 uint8_t *dyn_smem();
 /* run body() once per thread of a grid x block launch with smem bytes of dynamic shared memory */
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);

@@ -123,7 +123,7 @@ def test_deflate_raw_not_last_leaves_stream_open(emu):
     blob, _ = emu.deflate(data, E.FMT_RAW, chunk=16384, last=0)
     out, eof, used = inflate_raw(blob)
     assert out == data and not eof and used == len(blob)
-    assert blob[-5:] == b"\x00\x00\x00\xff\xff"            # ends like Z_FULL_FLUSH
+    assert blob[-4:] == b"\x00\x00\xff\xff"            # ends like Z_FULL_FLUSH
 
 
 @pytest.mark.parametrize("geom", [dict(piece_log2=13, hb=11, warps=20, nbuf=17, grid=1), dict(piece_log2=13, hb=11, warps=3, nbuf=1, grid=3),
@@ -316,3 +316,82 @@ def test_lz4_decodes_oracle_frames_and_rejects_corruption(emu, port):
     members[0]["expect_cksum"] ^= 4
     _, res = emu.decode(E.FMT_LZ4, blob, members, len(data))
     assert res[0].status == E.ST_CKSUM and res[1].status == E.ST_OK
+
+
+# ------------------------------------------------------------------ group kernel: one deflate block per 8 pieces
+
+def decode_any(port, blob, fmt, n):
+    if fmt != E.FMT_ZLIB:
+        return port.decompress(blob, fmt, n + 16)
+    p, got = 0, b""
+    while p < len(blob):
+        d = zlib.decompressobj(15)
+        got += d.decompress(blob[p:])
+        assert d.eof
+        p = len(blob) - len(d.unused_data)
+    return got
+
+
+@pytest.mark.parametrize("fmt", [E.FMT_4B, E.FMT_GZIP, E.FMT_GZIP_EXT, E.FMT_RAW, E.FMT_ZLIB])
+@pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000),
+                                         ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
+                                         ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
+def test_group_deflate_round_trip(emu, port, fmt, name, make, n):
+    data = make(n)
+    blob, cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1)
+    assert decode_any(port, blob, fmt, n) == data
+    want = zlib.adler32 if fmt == E.FMT_ZLIB else zlib.crc32
+    assert cks == [want(data[i:i + 65536]) for i in range(0, n, 65536)]
+    if fmt == E.FMT_RAW:
+        out, eof, used = inflate_raw(blob)
+        assert out == data and eof and used == len(blob)
+
+
+@pytest.mark.parametrize("chunk", [65536, 131072, 524288])
+@pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=16, grid=1), dict(warps=24, nbuf=15, grid=1), dict(warps=8, nbuf=8, grid=1, hb=12)])
+def test_group_deflate_geometries_and_chunks(emu, port, chunk, geom):
+    data = sil(chunk + chunk // 2 + 4321)
+    blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, group=1, **geom)
+    assert port.decompress(blob, E.FMT_GZIP_EXT, len(data) + 16) == data
+    assert cks == [zlib.crc32(data[i:i + chunk]) for i in range(0, len(data), chunk)]
+    members = walk_gzip(blob, ext=True)
+    assert [m[4] for m in members] == [len(data[i:i + chunk]) for i in range(0, len(data), chunk)]
+
+
+def test_group_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
+    data = sil(1 << 20)
+    grouped, _ = emu.deflate(data, E.FMT_RAW, warps=8, nbuf=4, grid=2, group=1)
+    pieces, _ = emu.deflate(data, E.FMT_RAW)
+    assert inflate_raw(grouped)[0] == data
+    assert len(grouped) < len(pieces)                  # 7 of 8 block headers and flush markers are gone
+    ref = sum(len(zlib.compress(data[i:i + 65536], 1)) for i in range(0, len(data), 65536))
+    assert len(grouped) <= 1.04 * ref, (len(grouped), ref)
+    # flush markers: one per chunk boundary, not one per piece
+    assert grouped.count(b"\x00\x00\xff\xff") < pieces.count(b"\x00\x00\xff\xff") // 4
+
+
+def test_group_deflate_static_and_not_last(emu):
+    data = sil(100000)
+    blob, _ = emu.deflate(data, E.FMT_RAW, static=1, warps=8, nbuf=2, grid=1, group=1)
+    out, eof, _ = inflate_raw(blob)
+    assert out == data and eof and (blob[0] >> 1) & 3 in (0, 1)
+    blob, _ = emu.deflate(data, E.FMT_RAW, last=0, warps=8, nbuf=2, grid=1, group=1)
+    out, eof, used = inflate_raw(blob)
+    assert out == data and not eof and used == len(blob) and blob[-4:] == b"\x00\x00\xff\xff"
+
+
+def test_group_deflate_dest_too_small_keeps_whole_chunks(emu):
+    data = sil(200000)
+    full, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, group=1)
+    members = walk_gzip(full, ext=True)
+    two = members[2][0] - 24
+    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100, warps=8, nbuf=3, grid=2, group=1)
+    assert part == full[:two]
+
+
+def test_group_streams_decode_with_our_inflate(emu):
+    data = sil(200000)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, group=1)
+    members = [one_member(ln, isize, crc, src_off=off, dst_off=i * 65536) for i, (off, ln, crc, isize, _) in enumerate(walk_gzip(blob, ext=True))]
+    out, res = emu.decode(E.FMT_GZIP_EXT, blob, members, len(data))
+    assert [r.status for r in res] == [E.ST_OK] * len(members) and out == data
