@@ -10,6 +10,11 @@ Every rank owns one GPU and its own 4 GiB shard (weak scaling, no data-path coll
              point qzb200CompressDevice -> same kernels), all ranks summed, max-over-ranks time.
   e2e        the same pass through the reference-facing C ABI: qzCompress() with HOST buffers
              from qzMalloc(PINNED), host->device and device->host copies inside the timed region.
+             The 512 MiB calls are issued by --e2e-threads submitting threads, one session each (the
+             pattern of the reference's own benchmark, test/main.c:2175-2202, and of the reference arm
+             below, which uses one session per host thread): a synchronous call cannot overlap its own
+             pipeline fill and drain, a second session's call can.  e2e.one_thread is the same pass
+             issued by a single thread.
   roofline   (bytes in + bytes out) of one deflate-kernel launch / its CUDA-event duration,
              against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the reference's own software path (oracle/_ref: src/qatzip_sw.c + zlib) on the
@@ -43,7 +48,7 @@ def env_int(name, d):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed regions run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -52,7 +57,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -111,6 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-threads", type=int, default=env_int("QZ_BENCH_E2E_THREADS", 2), help="submitting threads (one session each) of the e2e pass")
     ap.add_argument("--gib", type=float, default=float(os.environ.get("QZ_BENCH_GIB", "4")), help="per-GPU workload (GiB); 4 = BASELINE config")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -193,50 +199,70 @@ def main():
     ncalls = nbytes // CALL_BYTES
 
     def device_pass():
-        made_total, codec_ms, codec_launches, launches = 0, 0.0, 0, 0
+        made_total, codec_ms, codec_launches, launches, kernel_ms = 0, 0.0, 0, 0, 0.0
         for i in range(ncalls):
             rc, used, made, _ = prod.compress_device(sess, d_in + i * CALL_BYTES, CALL_BYTES, d_out, out_cap_call, 1)
             assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
             st = prod.stats(sess)
-            made_total += made; codec_ms += st.codec_ms; codec_launches += st.codec_launches; launches += st.kernel_launches
-        return made_total, codec_ms, codec_launches, launches
+            made_total += made; codec_ms += st.codec_ms; codec_launches += st.codec_launches; launches += st.kernel_launches; kernel_ms += st.kernel_ms
+        return made_total, codec_ms, codec_launches, launches, kernel_ms
 
     host_break = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0}
+    T = max(1, min(args.e2e_threads, ncalls))
+    e2e_sess = [sess] + [prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=CHUNK) for _ in range(T - 1)]
+    e2e_out = [h_out] + [L.qzMalloc(out_cap_call, 0, q.PINNED_MEM) for _ in range(T - 1)]
+    assert all(e2e_out)
 
-    def host_pass():
-        made_total = 0
+    def host_pass(threads):
+        """every 512 MiB call of the shard through qzCompress(host -> host); thread t issues calls t, t + threads, ..."""
+        made = [0] * threads
         for k in host_break:
             host_break[k] = 0.0
-        for i in range(ncalls):
-            rc, used, made = prod.compress_call(sess, h_in + i * CALL_BYTES, CALL_BYTES, h_out, out_cap_call, 1)
-            assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
-            made_total += made
-            st = prod.stats(sess)
-            host_break["h2d_ms"] += st.h2d_ms; host_break["kernel_ms"] += st.kernel_ms; host_break["d2h_ms"] += st.d2h_ms
-        return made_total
+
+        def work(t):
+            for i in range(t, ncalls, threads):
+                rc, used, m = prod.compress_call(e2e_sess[t], h_in + i * CALL_BYTES, CALL_BYTES, e2e_out[t], out_cap_call, 1)
+                assert rc == q.QZ_OK and used == CALL_BYTES, (rc, used)
+                made[t] += m
+                if threads == 1:
+                    st = prod.stats(e2e_sess[t])
+                    host_break["h2d_ms"] += st.h2d_ms; host_break["kernel_ms"] += st.kernel_ms; host_break["d2h_ms"] += st.d2h_ms
+        if threads == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        return sum(made)
 
     for _ in range(args.warmup):
         device_pass()
     clocks = ClockSampler(local)
     barrier(); clocks.start(); t0 = time.perf_counter()
-    made = codec_ms = 0.0; codec_launches = launches = 0
+    made = codec_ms = kernel_ms = 0.0; codec_launches = launches = 0
     for _ in range(args.steps):
-        m, cm, cl, ln = device_pass()
-        made, codec_ms, codec_launches, launches = m, codec_ms + cm, codec_launches + cl, launches + ln
+        m, cm, cl, ln, km = device_pass()
+        made, codec_ms, codec_launches, launches, kernel_ms = m, codec_ms + cm, codec_launches + cl, launches + ln, kernel_ms + km
     barrier(); dt = allmax(time.perf_counter() - t0)
-    clk = clocks.stop()
     ms_per_step = dt / args.steps * 1e3
     total_in = allsum(float(nbytes))
     value = total_in / (dt / args.steps) / GB
 
     # end to end through qzCompress with host buffers
-    for _ in range(min(args.warmup, 2)):
-        host_pass()
-    barrier(); t0 = time.perf_counter()
-    for _ in range(args.steps):
-        made_h = host_pass()
-    barrier(); dt_e = allmax(time.perf_counter() - t0)
+    def timed_host(threads):
+        for _ in range(min(args.warmup, 2)):
+            host_pass(threads)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            made_h = host_pass(threads)
+        barrier(); d = allmax(time.perf_counter() - t0)
+        return d, made_h
+    dt_1, made_h = timed_host(1)
+    break_1 = dict(host_break)
+    dt_e, made_h = timed_host(T) if T > 1 else (dt_1, made_h)
+    clk = clocks.stop()
     e2e = total_in / (dt_e / args.steps) / GB
+    e2e_1 = total_in / (dt_1 / args.steps) / GB
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -261,14 +287,17 @@ def main():
         st = prod.stats(sess)
         print(json.dumps({
             "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+            "kernel_ms_per_step_cuda_events": round(kernel_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
-                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
+                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": os.environ.get("QZB200_GROUP", "default"), "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
             "ratio": round(made / nbytes, 4),
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
-                    "api": "qzCompress(host pinned -> host pinned), 512 MiB per call", "ms_per_step": round(dt_e / args.steps * 1e3, 3),
-                    "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in host_break.items()}},
+                    "api": f"qzCompress(host pinned -> host pinned), 512 MiB per call, {T} submitting thread(s) with one session each",
+                    "threads": T, "ms_per_step": round(dt_e / args.steps * 1e3, 3),
+                    "one_thread": {"value": round(e2e_1, 3), "ms_per_step": round(dt_1 / args.steps * 1e3, 3),
+                                   "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in break_1.items()}}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,

@@ -558,3 +558,22 @@ def test_async_callbacks(prod, port, data):
     assert L.qzCompress2(C.byref(sess), src, dst, CB(), C.byref(r3)) == q.QZ_OK and r3.status == q.QZ_OK and r3.src_len == n
     assert L.qzCompress2(C.byref(sess), src, dst, cb, None) == q.QZ_PARAMS
     prod.end_session(sess)          # drains and stops the completion thread
+
+
+def test_stream_config5_pattern_driven_from_c(prod, port, data):
+    """BASELINE configs[4] in small: DEFLATE_RAW, 4 KiB submissions, `last` on the final one, the loop written in C
+    (harness/stream_drive.c) exactly as the perf tool times it; the bytes must be one valid raw deflate stream."""
+    d = pick(data, 16 << 20, 15)
+    drv = C.CDLL(os.path.join(os.path.dirname(q.CORPUS_SO), "libqzdrive.so"))
+    drv.qzdrive_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint), C.POINTER(C.c_double)]
+    sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW)
+    ocap = 8 << 20
+    obuf, sink = (C.c_ubyte * ocap)(), (C.c_ubyte * len(d))()
+    outb, calls, crc, secs = C.c_uint64(0), C.c_uint64(0), C.c_uint(0), C.c_double(0)
+    rc = drv.qzdrive_stream(C.cast(prod.lib.qzCompressStream, C.c_void_p), C.cast(prod.lib.qzEndStream, C.c_void_p), C.byref(sess), d, len(d), 4096,
+                            obuf, ocap, sink, len(d), C.byref(outb), C.byref(calls), C.byref(crc), C.byref(secs))
+    prod.end_session(sess)
+    assert rc == q.QZ_OK and calls.value == len(d) // 4096 and crc.value == zlib.crc32(d)
+    z = zlib.decompressobj(-15)
+    assert z.decompress(bytes(sink[:outb.value])) == d and z.eof

@@ -85,22 +85,20 @@ if os.path.exists(q.REF_SO) and not os.environ.get("EXTRA_NOCPU"):
     ths = [threading.Thread(target=work, args=(t,)) for t in range(T)]
     [t.start() for t in ths]; bar.wait(); t0 = time.perf_counter(); bar.wait(); dt = time.perf_counter() - t0; [t.join() for t in ths]
     res["cpu_reference_decompress"] = {"GBps_out": round(CALL / dt / 1e9, 2), "threads": T, "sample_MiB_out": CALL >> 20}
-# stream API, BASELINE config 5: RAW, 4 KiB submissions (a slice of the 1 GiB stream)
+# stream API, BASELINE config 5: RAW, 4 KiB submissions (a slice of the 1 GiB stream), driven from C (harness/stream_drive.c)
 SN = int(os.environ.get("EXTRA_STREAM_MIB", "64")) << 20
+drv = C.CDLL(os.path.join(os.path.dirname(q.CORPUS_SO), "libqzdrive.so"))
+drv.qzdrive_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t,
+                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint), C.POINTER(C.c_double)]
+fn_s, fn_e = C.cast(L.qzCompressStream, C.c_void_p), C.cast(L.qzEndStream, C.c_void_p)
 for sb, batch_kb in ((65536, None), (65536, "0"), (2 * 1024 * 1024 - 5 * 1024, "0")):
     if batch_kb is None: os.environ.pop("QZB200_STREAM_BATCH_KB", None)
     else: os.environ["QZB200_STREAM_BATCH_KB"] = batch_kb
     sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW, strm_buff_sz=sb)
-    st = q.QzStream(); ocap = 4 << 20; obuf = (C.c_ubyte * ocap)()
-    consumed = outb = calls = 0
-    t0 = time.perf_counter()
-    while True:
-        left = SN - consumed; n = min(4096, left); last = 1 if left - n == 0 else 0
-        st.in_ = h_in + consumed; st.in_sz = n; st.out = C.addressof(obuf); st.out_sz = ocap
-        rc = L.qzCompressStream(C.byref(sess), C.byref(st), last); assert rc == 0, rc
-        consumed += st.in_sz; outb += st.out_sz; calls += 1
-        if last and st.pending_in == 0 and st.pending_out == 0 and consumed == SN: break
-    dt = time.perf_counter() - t0
-    L.qzEndStream(C.byref(sess), C.byref(st)); prod.end_session(sess)
-    res[f"stream_raw_4KiB_strmbuf_{sb}_{'batched4MiB' if batch_kb is None else 'per_strm_buff'}"] = {"MBps": round(SN / dt / 1e6, 1), "calls": calls, "ratio": round(outb / SN, 4), "stream_MiB": SN >> 20}
+    ocap = 8 << 20; obuf = (C.c_ubyte * ocap)()
+    outb, calls, crc, secs = C.c_uint64(0), C.c_uint64(0), C.c_uint(0), C.c_double(0)
+    rc = drv.qzdrive_stream(fn_s, fn_e, C.byref(sess), h_in, SN, 4096, obuf, ocap, None, 0, C.byref(outb), C.byref(calls), C.byref(crc), C.byref(secs))
+    assert rc == 0, rc
+    prod.end_session(sess)
+    res[f"stream_raw_4KiB_strmbuf_{sb}_{'batched4MiB' if batch_kb is None else 'per_strm_buff'}"] = {"MBps": round(SN / secs.value / 1e6, 1), "calls": calls.value, "ratio": round(outb.value / SN, 4), "stream_MiB": SN >> 20, "driver": "C"}
 print(json.dumps(res))
