@@ -235,7 +235,7 @@ struct PieceState {
 };
 
 template <int PIECE_LOG2, int HB>
-__device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, WarpPriv<HB> &ws, uint32_t *toks,
+__device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, uint16_t *table, uint32_t *toks,
                                         const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps QZ_TARG)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
@@ -266,7 +266,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
             for (uint32_t i = lane; i < n; i += 32) piece[i] = src[i];
         }
         piece[n + lane] = 0;          /* zero pad */
-        for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
+        for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
         __syncwarp();
         /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
         int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
@@ -313,9 +313,9 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
             const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
             const bool can = p + 4 <= n;
             const uint32_t h = (v * 2654435761u) >> (32 - HB);
-            uint32_t cand = can ? ws.u.table[h] : QZ_NONE16;
+            uint32_t cand = can ? table[h] : QZ_NONE16;
             __syncwarp();
-            if (can) ws.u.table[h] = (uint16_t)p;
+            if (can) table[h] = (uint16_t)p;
             __syncwarp();
             /* candidate bytes are fetched unconditionally (slot 0 when there is none): no divergent
              * verify/extend branches, all loads in flight together */
@@ -489,13 +489,9 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
 /* phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
  *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13)
  * Returns the piece's total of extra bits. */
-template <int HB>
-__device__ __forceinline__ uint32_t token_pass(WarpPriv<HB> &ws, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep)
+__device__ __forceinline__ uint32_t token_pass(uint32_t *hist, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep)
 {
-    CodeScratch &cs = ws.u.b.cs;
-    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) ws.u.b.hist[i] = 0;
-    for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
-    cs.d_len[lane] = 0;
+    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0;
     __syncwarp();
     uint32_t extra_acc = 0;
     uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;          /* one group ahead: hides the L2 round trip */
@@ -508,32 +504,32 @@ __device__ __forceinline__ uint32_t token_pass(WarpPriv<HB> &ws, uint32_t *toks,
                 const uint32_t ls = le & 31, leb = (le >> 5) & 7, lev = ((t >> 16) & 0xff) - (le >> 8);
                 uint32_t ds, de, dv;
                 qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
-                atomicAdd(&ws.u.b.hist[257 + ls], 1u);
-                atomicAdd(&ws.u.b.hist[QZ_DOFF + ds], 1u);
+                atomicAdd(&hist[257 + ls], 1u);
+                atomicAdd(&hist[QZ_DOFF + ds], 1u);
                 extra_acc += leb + de;
                 tok_st(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv, pkeep);
-            } else atomicAdd(&ws.u.b.hist[t], 1u);
+            } else atomicAdd(&hist[t], 1u);
         }
     }
     return extra_acc;
 }
 
-/* phase 3b: code construction from the histograms in ws.u.b.hist -> code lengths in cs.ll_len / cs.d_len, the planned
+/* phase 3b: code construction from the histograms in hist -> code lengths in cs.ll_len / cs.d_len, the planned
  * dynamic header in cs.hdr, and the cheapest block type for `storedb` bits of stored cost: 0 stored, 1 fixed, 2 dynamic */
-template <int HB>
-__device__ __forceinline__ int choose_block(WarpPriv<HB> &ws, uint32_t extra_total, uint32_t storedb, int static_huffman, uint32_t lane QZ_TARG)
+__device__ __forceinline__ int choose_block(CodeScratch &cs, uint32_t *hist, uint32_t extra_total, uint32_t storedb, int static_huffman, uint32_t lane QZ_TARG)
 {
-    CodeScratch &cs = ws.u.b.cs;
+    for (uint32_t i = lane; i < 288; i += 32) cs.ll_len[i] = 0;
+    cs.d_len[lane] = 0;
     if (lane == 0) {
-        ws.u.b.hist[256] = 1;
-        qz_huff_force_two(ws.u.b.hist, QZ_NUM_LL);
-        qz_huff_force_two(ws.u.b.hist + QZ_DOFF, QZ_NUM_D);
+        hist[256] = 1;
+        qz_huff_force_two(hist, QZ_NUM_LL);
+        qz_huff_force_two(hist + QZ_DOFF, QZ_NUM_D);
     }
     __syncwarp();
     /* literal/length alphabet */
     int nk = 0;
     for (uint32_t s0 = 0; s0 < 288; s0 += 32) {
-        uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? ws.u.b.hist[s] : 0;
+        uint32_t s = s0 + lane, f = s < QZ_NUM_LL ? hist[s] : 0;
         uint32_t bal = __ballot_sync(FULL, f != 0);
         if (f) cs.keys[nk + __popc(bal & lanemask_lt())] = QZ_HUFF_KEY(f, s);
         nk += __popc(bal);
@@ -547,7 +543,7 @@ __device__ __forceinline__ int choose_block(WarpPriv<HB> &ws, uint32_t extra_tot
     {
         uint32_t *dkeys = reinterpret_cast<uint32_t *>(cs.hdr.items);
         uint16_t *dids = cs.hdr.items + 64;
-        const uint32_t f = lane < QZ_NUM_D ? ws.u.b.hist[QZ_DOFF + lane] : 0;
+        const uint32_t f = lane < QZ_NUM_D ? hist[QZ_DOFF + lane] : 0;
         const int nd = __popc(__ballot_sync(FULL, f != 0));
         uint32_t x[1] = { f ? QZ_HUFF_KEY(f, lane) : 0xffffffffu };
         warp_sort_regs<1>(x, lane);
@@ -559,8 +555,8 @@ __device__ __forceinline__ int choose_block(WarpPriv<HB> &ws, uint32_t extra_tot
     }
     /* cost of each block type */
     uint32_t dynb = 0, fixb = 0;
-    for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = ws.u.b.hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
-    if (lane < QZ_NUM_D) { uint32_t f = ws.u.b.hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
+    for (uint32_t s = lane; s < QZ_NUM_LL; s += 32) { uint32_t f = hist[s]; dynb += f * cs.ll_len[s]; fixb += f * qz_fixed_ll_len(s); }
+    if (lane < QZ_NUM_D) { uint32_t f = hist[QZ_DOFF + lane]; dynb += f * cs.d_len[lane]; fixb += f * 5; }
     dynb = warp_sum(dynb) + extra_total; fixb = warp_sum(fixb) + extra_total + 3;
     /* forced dummy symbols were counted with freq 1 but are never emitted: harmless overestimate */
     warp_plan_header(cs, cs.keys, lane);
@@ -573,19 +569,17 @@ __device__ __forceinline__ int choose_block(WarpPriv<HB> &ws, uint32_t extra_tot
 /* phase 3c: open a fixed (btype 1) or dynamic (2) block at the start of slotw: code tables go where the histograms
  * were (code | len << 16 | extra-bit count << 24), the block header is written; *hb = bits written so far, *pend = the
  * partial word at that position (the first token run continues it) */
-template <int HB>
-__device__ __forceinline__ void open_block(WarpPriv<HB> &ws, int btype, bool bfinal, uint32_t *slotw, uint32_t lane, uint32_t *hb, uint32_t *pend_out QZ_TARG)
+__device__ __forceinline__ void open_block(CodeScratch &cs, uint32_t *hist, int btype, bool bfinal, uint32_t *slotw, uint32_t lane, uint32_t *hb, uint32_t *pend_out QZ_TARG)
 {
-    CodeScratch &cs = ws.u.b.cs;
-    QzBitWriter bw;
+    QzBitWriter bw; bw.acc = 0;
     EmitState es; es.bitpos = 0; es.flushed = 0;
     if (btype == 1) {
         for (uint32_t s = lane; s < 288; s += 32) cs.ll_len[s] = (uint8_t)qz_fixed_ll_len(s);
         cs.d_len[lane] = 5;
         __syncwarp();
     }
-    warp_assign_codes(cs.ll_len, 288, ws.u.b.hist, cs.keys, lane);
-    warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, ws.u.b.hist + QZ_DOFF, cs.keys, lane);
+    warp_assign_codes(cs.ll_len, 288, hist, cs.keys, lane);
+    warp_assign_codes(cs.d_len, btype == 1 ? 32 : QZ_NUM_D, hist + QZ_DOFF, cs.keys, lane);
     uint32_t *clc = cs.keys + 40;                 /* code-length alphabet codes, 19 words */
     if (btype == 2) warp_assign_codes(cs.hdr.cl_len, QZ_NUM_CL, clc, cs.keys, lane);
     if (lane == 0) {
@@ -620,9 +614,9 @@ __device__ __forceinline__ void open_block(WarpPriv<HB> &ws, int btype, bool bfi
     __syncwarp();
     *pend_out = st[0]; *hb = es.bitpos;
     /* code table entries gain their extra-bit counts: code | len << 16 | extra << 24 */
-    if (lane < 29) ws.u.b.hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
-    if (lane < QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
-    if (lane >= QZ_NUM_D) ws.u.b.hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
+    if (lane < 29) hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
+    if (lane < QZ_NUM_D) hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
+    if (lane >= QZ_NUM_D) hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
     __syncwarp();
 }
 
@@ -706,8 +700,7 @@ __device__ __forceinline__ uint32_t stored_piece(uint8_t *slot, const uint8_t *s
 }
 
 /* one piece as its own block (or run of blocks): everything after the token pass */
-template <int HB>
-__device__ __forceinline__ void finish_piece(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, uint32_t lane, const PieceState &ps,
+__device__ __forceinline__ void finish_piece(const QzbCompressJob &job, CodeScratch &cs, uint32_t *hist, uint32_t *toks, uint32_t lane, const PieceState &ps,
                                              uint32_t extra_total, uint64_t pkeep QZ_TARG)
 {
     const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
@@ -716,13 +709,13 @@ __device__ __forceinline__ void finish_piece(const QzbCompressJob &job, WarpPriv
     uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
 
     uint32_t out_bytes = 0;
-    int btype = choose_block<HB>(ws, extra_total, (5 + n) * 8, job.static_huffman, lane QZ_TPASS);
+    int btype = choose_block(cs, hist, extra_total, (5 + n) * 8, job.static_huffman, lane QZ_TPASS);
     if (n == 0) btype = 1;
 
     if (btype == 0) out_bytes = stored_piece(slot, ps.src, n, bfinal, lane);
     else {
         uint32_t hb, pend2;
-        open_block<HB>(ws, btype, bfinal, slotw, lane, &hb, &pend2 QZ_TPASS);
+        open_block(cs, hist, btype, bfinal, slotw, lane, &hb, &pend2 QZ_TPASS);
         /* ---- phase 4: emit ----
          * Every lane codes a contiguous run of tokens: pass 1 adds up the run's bit length, a warp scan
          * turns the lengths into bit offsets, pass 2 packs the run through a private 64-bit accumulator
@@ -732,7 +725,7 @@ __device__ __forceinline__ void finish_piece(const QzbCompressJob &job, WarpPriv
         const uint32_t NT = ntok + 1;
         const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
         const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-        const uint32_t mybits = count_run_bits(ws.u.b.hist, toks, beg, end, pkeep);
+        const uint32_t mybits = count_run_bits(hist, toks, beg, end, pkeep);
         uint32_t incl = mybits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -743,7 +736,7 @@ __device__ __forceinline__ void finish_piece(const QzbCompressJob &job, WarpPriv
         slotw[start >> 5] = 0;
         if (lane == 31) slotw[end_bit2 >> 5] = 0;
         __syncwarp();
-        emit_run(ws.u.b.hist, toks, beg, end, start, pend2, lane == 0, !bfinal && beg < NT && end == NT, nz, slotw, pkeep);
+        emit_run(hist, toks, beg, end, start, pend2, lane == 0, !bfinal && beg < NT && end == NT, nz, slotw, pkeep);
         out_bytes = (end_bit2 + 7) >> 3;
         __syncwarp();
     }
@@ -757,12 +750,12 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
                                         uint32_t lane, const PieceState &ps QZ_TARG)
 {
     const uint64_t pkeep = l2_policy_keep();
-    const uint32_t extra_acc = token_pass<HB>(ws, toks, ps.ntok, s_lentab, lane, pkeep);
+    const uint32_t extra_acc = token_pass(ws.u.b.hist, toks, ps.ntok, s_lentab, lane, pkeep);
     if (lane == 0) tok_st(toks + ps.ntok, 256u, pkeep);      /* end-of-block rides along as the last token */
     __syncwarp();
     const uint32_t extra_total = warp_sum(extra_acc);
     QZ_MARK(3);
-    finish_piece<HB>(job, ws, toks, lane, ps, extra_total, pkeep QZ_TPASS);
+    finish_piece(job, ws.u.b.cs, ws.u.b.hist, toks, lane, ps, extra_total, pkeep QZ_TPASS);
 }
 
 template <int PIECE_LOG2, int HB>
@@ -816,7 +809,7 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_pieces_
         b = __shfl_sync(FULL, b, 0);
         QZ_MARK(0);
         PieceState ps;
-        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
+        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
         phase34<HB>(job, ws, toks, s_lentab, lane, ps QZ_TPASS);
@@ -834,6 +827,17 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_pieces_
  * Z_FULL_FLUSH per 64 KiB would look like.  Warps of a group meet at a named barrier (bar.sync id, 256); groups of
  * one CTA are independent of each other.  Used when a chunk is a whole number of groups (hw_buff_sz >= 64 KiB). */
 #define QZ_GROUP 8
+/* Shared memory of the group kernel: a warp's private slice is its hash table during the match phase and its
+ * histogram afterwards (no code scratch: only the leader builds codes), so a 2^10-entry table makes it 2 KiB; the
+ * code scratch and the group's histogram / code tables live once per group. */
+template <int HB>
+struct GroupWarpPriv {
+    union {
+        uint16_t table[1 << HB];
+        uint32_t hist[QZ_HIST_WORDS];
+    } u;
+};
+struct GroupLead { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; };
 struct GroupShared {
     uint32_t ticket, bfinal, btype, hb, pend;
     uint32_t nbytes[QZ_GROUP], ntok[QZ_GROUP], extra[QZ_GROUP], bits[QZ_GROUP];
@@ -848,19 +852,19 @@ template <int PIECE_LOG2, int HB>
 __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
+    static_assert(sizeof(GroupWarpPriv<HB>) == (sizeof(uint16_t) << HB) && sizeof(GroupLead) % 16 == 0, "a warp's histogram must fit in its hash table");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];
     __shared__ uint16_t s_lentab[256];
     __shared__ uint32_t s_busy[1];
-    __shared__ GroupShared s_grp[QZ_DEFLATE_MAX_WARPS / QZ_GROUP];
+    __shared__ GroupShared s_grp[(QZ_DEFLATE_MAX_WARPS + QZ_GROUP - 1) / QZ_GROUP];
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     PieceBuf<PIECE_LOG2> *bufs = reinterpret_cast<PieceBuf<PIECE_LOG2> *>(smem_raw);
-    WarpPriv<HB> *wsv = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>));
-    WarpPriv<HB> &ws = wsv[warp];
+    GroupWarpPriv<HB> *wsv = reinterpret_cast<GroupWarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>));
+    GroupWarpPriv<HB> &ws = wsv[warp];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
     if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;
@@ -868,7 +872,11 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
 
     const uint32_t grp = warp / QZ_GROUP, wg = warp % QZ_GROUP, bar = 1 + grp;
     GroupShared &G = s_grp[grp];
-    WarpPriv<HB> &lead = wsv[grp * QZ_GROUP];                 /* the leader's slice: group histogram, then the code tables */
+    /* group histogram -> code tables, and the code scratch: on top of the leader's own slice when that is large enough
+     * (its own histogram sits in the part that becomes cs.keys, which is written only after the sum), else after the slices */
+    constexpr bool LEAD_OVERLAY = sizeof(GroupWarpPriv<HB>) >= sizeof(GroupLead);
+    GroupLead &lead = LEAD_OVERLAY ? *reinterpret_cast<GroupLead *>(wsv + grp * QZ_GROUP) : reinterpret_cast<GroupLead *>(wsv + nwarps)[grp];
+    static_assert(offsetof(GroupLead, hist) >= QZ_HIST_WORDS * 4, "the summed histogram must not land on the leader's own");
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
     uint32_t *toks = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
     const uint32_t gpc = job.pieces_per_chunk / QZ_GROUP;     /* groups per chunk */
@@ -913,12 +921,12 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
             }
             b = __shfl_sync(FULL, b, 0);
             QZ_MARK(0);
-            phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
+            phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
         }
         /* token pass on the private histogram; the last piece of the block carries the end-of-block token */
-        const uint32_t extra = warp_sum(token_pass<HB>(ws, toks, ps.ntok, s_lentab, lane, pkeep));
+        const uint32_t extra = warp_sum(token_pass(ws.u.hist, toks, ps.ntok, s_lentab, lane, pkeep));
         const bool last_in_group = ps.n != 0 && (wg == QZ_GROUP - 1 || chunk_end);
         if (lane == 0) {
             if (last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
@@ -937,10 +945,15 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
                 if (nb) { const uint32_t r = (G.ntok[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
             }
             if (hi > 920u && lo < 768u) {
-                if (ps.n) {
-                    if (lane == 0 && !last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
-                    __syncwarp();
-                    finish_piece<HB>(job, ws, toks, lane, ps, extra, pkeep QZ_TPASS);
+                /* rare: the pieces take turns with the group's one code scratch */
+                if (ps.n && lane == 0 && !last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
+                for (uint32_t turn = 0; turn < QZ_GROUP; turn++) {
+                    if (turn == wg && ps.n) {
+                        for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) lead.hist[s] = ws.u.hist[s];
+                        __syncwarp();
+                        finish_piece(job, lead.cs, lead.hist, toks, lane, ps, extra, pkeep QZ_TPASS);
+                    }
+                    group_bar(bar);
                 }
                 continue;
             }
@@ -950,15 +963,15 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
             uint32_t extra_total = 0, nbytes = 0, npc = 0;
             for (int i = 0; i < QZ_GROUP; i++) { extra_total += G.extra[i]; nbytes += G.nbytes[i]; npc += G.nbytes[i] ? 1u : 0u; }
             for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) {
-                uint32_t f = ws.u.b.hist[s];
+                uint32_t f = 0;
 #pragma unroll
-                for (int i = 1; i < QZ_GROUP; i++) f += wsv[grp * QZ_GROUP + i].u.b.hist[s];
-                ws.u.b.hist[s] = f;
+                for (int i = 0; i < QZ_GROUP; i++) f += wsv[grp * QZ_GROUP + i].u.hist[s];
+                lead.hist[s] = f;
             }
             __syncwarp();
-            const int btype = choose_block<HB>(ws, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
+            const int btype = choose_block(lead.cs, lead.hist, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
             uint32_t hb = 0, pend = 0;
-            if (btype) open_block<HB>(ws, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
+            if (btype) open_block(lead.cs, lead.hist, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
             if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
         }
         group_bar(bar);
@@ -974,7 +987,7 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
             const uint32_t NT = G.ntok[wg];
             const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
             const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-            const uint32_t mybits = count_run_bits(lead.u.b.hist, toks, beg, end, pkeep);
+            const uint32_t mybits = count_run_bits(lead.hist, toks, beg, end, pkeep);
             uint32_t incl = mybits;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -992,7 +1005,7 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
             group_bar(bar);
             /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
             const bool owns_eob = last_in_group && beg < NT && end == NT;
-            emit_run(lead.u.b.hist, toks, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
+            emit_run(lead.hist, toks, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
             if (lane == 0 && ps.n) job.piece_len[g] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
         }
         __syncwarp();
@@ -1191,10 +1204,19 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
     return cudaErrorInvalidValue;
 }
 
+extern "C" int qzb_deflate_max_warps(void) { return QZ_DEFLATE_MAX_WARPS; }
+
+/* shared memory of the group kernel for `warps` warps (a multiple of 8) sharing `nbuf` piece buffers */
+extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf)
+{
+    const size_t priv = (size_t)2 << hb;
+    return priv * (size_t)warps + (priv >= sizeof(GroupLead) ? 0 : sizeof(GroupLead) * (size_t)(warps / QZ_GROUP)) + sizeof(PieceBuf<13>) * (size_t)nbuf;
+}
+
 template <int P, int H>
 static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    size_t smem = sizeof(WarpPriv<H>) * (size_t)warps + sizeof(PieceBuf<P>) * (size_t)nbuf;
+    size_t smem = qzb_deflate_groups_smem_bytes(H, warps, nbuf);
     cudaError_t e = cudaFuncSetAttribute(qzb_deflate_groups_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     qzb_deflate_groups_kernel<P, H><<<grid, warps * 32, smem, st>>>(job, nbuf);
@@ -1205,6 +1227,7 @@ static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, in
 extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
     if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups) return cudaErrorInvalidValue;
+    if (job->piece_log2 == 13 && hb == 10) return launch_deflate_groups<13, 10>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 11) return launch_deflate_groups<13, 11>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 12) return launch_deflate_groups<13, 12>(*job, grid, warps, nbuf, st);
     return cudaErrorInvalidValue;

@@ -30,6 +30,7 @@ extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid,
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
+extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -53,8 +54,14 @@ extern "C" int qzb_runtime_devices(void)
     });
     return g_ndev;
 }
+/* most warps per CTA the deflate kernels were compiled for (their launch bound; qz_deflate.cu) */
+extern "C" int qzb_deflate_max_warps(void);
+#define QZB_DEFLATE_MAX_WARPS qzb_deflate_max_warps()
 #ifndef QZB200_GROUP_DEFAULT
 #define QZB200_GROUP_DEFAULT 0
+#endif
+#ifndef QZB200_GROUP_HB_DEFAULT
+#define QZB200_GROUP_HB_DEFAULT 11
 #endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
@@ -87,6 +94,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     /* deflate block granularity: 1 = one block per group of 8 pieces (group kernel, chunks that are a whole number of
      * groups, i.e. hw_buff_sz >= 64 KiB with 8 KiB pieces), 0 = one block per piece everywhere */
     t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);
+    t->group_hash_bits = env_int("QZB200_GROUP_HASH_BITS", QZB200_GROUP_HB_DEFAULT);     /* 10: 2 KiB per warp, more piece buffers; 11, 12 */
+    if (t->group_hash_bits < 10 || t->group_hash_bits > 12) t->group_hash_bits = QZB200_GROUP_HB_DEFAULT;
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -264,25 +273,28 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta;
+    int nbuf = t.buffers_per_cta, hb = t.hash_bits;
+    size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
         if (warps <= 0 || warps > 16) warps = 16;
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
     } else if (t.group && t.piece_log2 == 13 && len && job.pieces_per_chunk % 8 == 0) {
-        /* group kernel: CTAs of 2 or 3 groups of 8 warps */
+        /* group kernel: CTAs of whole groups of 8 warps; as many piece buffers as the rest of the 227 KB holds */
         const uint32_t gpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * gpc + (last_pieces + 7) / 8;
-        if (warps != 8 && warps != 16 && warps != 24) { warps = 24; if (nbuf <= 0) nbuf = 15; }
-        if (nbuf <= 0 || nbuf > warps) nbuf = (warps * 5 + 7) / 8;
-        while (nbuf > 1 && smem_for(warps, nbuf) + 3328 > smem_cap) nbuf--;
+        hb = t.group_hash_bits;
+        if (warps < 8 || warps > QZB_DEFLATE_MAX_WARPS || warps % 8) warps = 24;
+        if (nbuf <= 0 || nbuf > warps) nbuf = warps;
+        while (nbuf > 1 && qzb_deflate_groups_smem_bytes(hb, warps, nbuf) + 3328 > smem_cap) nbuf--;
+        group_smem = qzb_deflate_groups_smem_bytes(hb, warps, nbuf);
     } else {
-        if (warps <= 0 || warps > 24) { warps = 20; if (nbuf <= 0) nbuf = 17; }      /* 24 = QZ_DEFLATE_MAX_WARPS (qz_deflate.cu) */
+        if (warps <= 0 || warps > QZB_DEFLATE_MAX_WARPS) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
-    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / (smem_for(warps, nbuf) + 3328));
+    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / ((group_smem ? group_smem : smem_for(warps, nbuf)) + 3328));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
     const int need = job.ngroups ? (int)((job.ngroups + warps / 8 - 1) / (warps / 8)) : (int)((job.npieces + warps - 1) / warps);
@@ -303,7 +315,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_groups(&job, t.hash_bits, grid, warps, nbuf, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_groups(&job, hb, grid, warps, nbuf, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

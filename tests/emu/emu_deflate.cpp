@@ -80,8 +80,10 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     std::function<void()> body;
     if (group) {
         if (!job.ngroups || warps % QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || piece_log2 != 13) return -1;
-        if (hb == 11) { smem = sizeof(WarpPriv<11>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_groups_kernel<13, 11>(job, nbuf); }; }
-        else if (hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_groups_kernel<13, 12>(job, nbuf); }; }
+        smem = ((size_t)2 << hb) * warps + (((size_t)2 << hb) >= sizeof(GroupLead) ? 0 : sizeof(GroupLead) * (warps / QZ_GROUP)) + sizeof(PieceBuf<13>) * nbuf;
+        if (hb == 10) body = [&] { qzb_deflate_groups_kernel<13, 10>(job, nbuf); };
+        else if (hb == 11) body = [&] { qzb_deflate_groups_kernel<13, 11>(job, nbuf); };
+        else if (hb == 12) body = [&] { qzb_deflate_groups_kernel<13, 12>(job, nbuf); };
         else return -1;
         emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
         return emu_frame(&job, chunk_cksum_out);

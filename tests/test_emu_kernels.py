@@ -336,9 +336,10 @@ def decode_any(port, blob, fmt, n):
 @pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000),
                                          ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
                                          ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
-def test_group_deflate_round_trip(emu, port, fmt, name, make, n):
+@pytest.mark.parametrize("hb", [10, 11])
+def test_group_deflate_round_trip(emu, port, fmt, name, make, n, hb):
     data = make(n)
-    blob, cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1)
+    blob, cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1, hb=hb)
     assert decode_any(port, blob, fmt, n) == data
     want = zlib.adler32 if fmt == E.FMT_ZLIB else zlib.crc32
     assert cks == [want(data[i:i + 65536]) for i in range(0, n, 65536)]
@@ -348,7 +349,8 @@ def test_group_deflate_round_trip(emu, port, fmt, name, make, n):
 
 
 @pytest.mark.parametrize("chunk", [65536, 131072, 524288])
-@pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=16, grid=1), dict(warps=24, nbuf=15, grid=1), dict(warps=8, nbuf=8, grid=1, hb=12)])
+@pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=16, grid=1), dict(warps=24, nbuf=15, grid=1), dict(warps=8, nbuf=8, grid=1, hb=12),
+                                  dict(warps=24, nbuf=20, grid=1, hb=10), dict(warps=8, nbuf=5, grid=2, hb=10)])
 def test_group_deflate_geometries_and_chunks(emu, port, chunk, geom):
     data = sil(chunk + chunk // 2 + 4321)
     blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, group=1, **geom)
