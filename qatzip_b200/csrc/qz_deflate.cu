@@ -29,10 +29,15 @@
 #define QZ_LANE_CAP 12          /* in-lane match extension cap; longer matches are finished by the warp */
 #define QZ_MAX_MATCH 258
 #define QZ_STAGE_WORDS 64
-/* most warps a CTA of the deflate kernels may have: shared memory admits 20-24, and the bound lets the compiler use
- * up to 80 registers per thread instead of the 64 a 1024-thread bound would impose */
-#ifndef QZ_DEFLATE_MAX_WARPS
-#define QZ_DEFLATE_MAX_WARPS 24
+/* most warps a CTA may have.  Per-piece kernel: shared memory admits 20-24, and the bound lets the compiler use up to
+ * 80 registers per thread instead of the 64 a 1024-thread bound would impose.  Group kernel: 2 KiB per warp with the
+ * 2^10-entry table, so four groups of eight warps fit beside 17 piece buffers, and that measured faster than 24 warps
+ * with 80 registers. */
+#ifndef QZ_PIECES_MAX_WARPS
+#define QZ_PIECES_MAX_WARPS 24
+#endif
+#ifndef QZ_GROUPS_MAX_WARPS
+#define QZ_GROUPS_MAX_WARPS 32
 #endif
 
 /* Per-phase cycle accounting for on-box diagnosis (A/B build only: make ab ABFLAGS=-DQZ_PHASE_CLOCKS).
@@ -234,6 +239,12 @@ struct PieceState {
     const uint8_t *src;
 };
 
+#ifdef QZ_EMU_STATS
+unsigned long long qz_stat[8];      /* tiles, skipped tiles, selection iterations, long matches, long-match steps, tokens, matches */
+#define QZ_STAT(i, v) do { if (lane == 0) qz_stat[i] += (v); } while (0)
+#else
+#define QZ_STAT(i, v) do { } while (0)
+#endif
 template <int PIECE_LOG2, int HB>
 __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, uint16_t *table, uint32_t *toks,
                                         const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps QZ_TARG)
@@ -305,7 +316,8 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
         const uint32_t sh = (lane & 3) * 8;  /* base is a multiple of 32: the byte phase of p is the lane's */
         const uint32_t *piece_w = reinterpret_cast<const uint32_t *>(piece);
         for (uint32_t base = 0; base < n; base += 32) {
-            if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
+            QZ_STAT(0, 1);
+            if (entry >= 32) { entry -= 32; QZ_STAT(1, 1); continue; }      /* tile lies inside a running match: nothing to code, not indexed */
             const uint32_t p = base + lane;
             /* 12 bytes at p, straight-line: the three words every lane needs for verify + in-lane extension */
             const uint32_t *pw = piece_w + (min(p, n) >> 2);
@@ -334,13 +346,16 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
                 const uint32_t rest = M & (FULL << cur);
                 if (!rest) { cur = 32; break; }
                 const uint32_t m = __ffs(rest) - 1;
+                QZ_STAT(2, 1);
                 matchmask |= 1u << m;
                 uint32_t Lm = __shfl_sync(FULL, L, m);
                 if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
                     const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
                     const uint32_t mx = min((uint32_t)QZ_MAX_MATCH, n - pm);
                     Lm = QZ_LANE_CAP;
+                    QZ_STAT(3, 1);
                     while (Lm < mx) {
+                        QZ_STAT(4, 1);
                         uint32_t kk = Lm + lane;
                         bool eq = kk < mx && piece[pm + kk] == piece[cm + kk];
                         uint32_t bal = __ballot_sync(FULL, eq);
@@ -366,6 +381,7 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
                 tok_st(toks + ntok + __popc(tokmask & lanemask_lt()), t, pkeep);
             }
             ntok += __popc(tokmask);
+            QZ_STAT(5, __popc(tokmask)); QZ_STAT(6, __popc(matchmask));
         }
     }
     __syncwarp();
@@ -759,7 +775,7 @@ __device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> 
 }
 
 template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
+__global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
@@ -849,7 +865,7 @@ __device__ __forceinline__ void group_bar(uint32_t id) { __syncwarp(); asm volat
 #endif
 
 template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
+__global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     static_assert(sizeof(GroupWarpPriv<HB>) == (sizeof(uint16_t) << HB) && sizeof(GroupLead) % 16 == 0, "a warp's histogram must fit in its hash table");
@@ -858,7 +874,7 @@ __global__ void __launch_bounds__(QZ_DEFLATE_MAX_WARPS * 32) qzb_deflate_groups_
     __shared__ uint32_t s_xstrip[5];
     __shared__ uint16_t s_lentab[256];
     __shared__ uint32_t s_busy[1];
-    __shared__ GroupShared s_grp[(QZ_DEFLATE_MAX_WARPS + QZ_GROUP - 1) / QZ_GROUP];
+    __shared__ GroupShared s_grp[QZ_GROUPS_MAX_WARPS / QZ_GROUP];
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1196,7 +1212,7 @@ static cudaError_t launch_deflate(const QzbCompressJob &job, int grid, int warps
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    if (nbuf < 1 || nbuf > 32 || warps < 1 || warps > QZ_DEFLATE_MAX_WARPS) return cudaErrorInvalidValue;
+    if (nbuf < 1 || nbuf > 32 || warps < 1 || warps > QZ_PIECES_MAX_WARPS) return cudaErrorInvalidValue;
     if (job->piece_log2 == 13 && hb == 11) return launch_deflate<13, 11>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 12) return launch_deflate<13, 12>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 14 && hb == 12) return launch_deflate<14, 12>(*job, grid, warps, nbuf, st);
@@ -1204,7 +1220,7 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
     return cudaErrorInvalidValue;
 }
 
-extern "C" int qzb_deflate_max_warps(void) { return QZ_DEFLATE_MAX_WARPS; }
+extern "C" int qzb_deflate_max_warps(int group) { return group ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
 /* shared memory of the group kernel for `warps` warps (a multiple of 8) sharing `nbuf` piece buffers */
 extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf)
@@ -1226,7 +1242,7 @@ static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, in
 /* group kernel (one deflate block per QZ_GROUP pieces): warps must be a multiple of QZ_GROUP, job->ngroups set */
 extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups) return cudaErrorInvalidValue;
+    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups) return cudaErrorInvalidValue;
     if (job->piece_log2 == 13 && hb == 10) return launch_deflate_groups<13, 10>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 11) return launch_deflate_groups<13, 11>(*job, grid, warps, nbuf, st);
     if (job->piece_log2 == 13 && hb == 12) return launch_deflate_groups<13, 12>(*job, grid, warps, nbuf, st);

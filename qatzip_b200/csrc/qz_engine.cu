@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <vector>
 #include <thread>
@@ -55,13 +56,12 @@ extern "C" int qzb_runtime_devices(void)
     return g_ndev;
 }
 /* most warps per CTA the deflate kernels were compiled for (their launch bound; qz_deflate.cu) */
-extern "C" int qzb_deflate_max_warps(void);
-#define QZB_DEFLATE_MAX_WARPS qzb_deflate_max_warps()
+extern "C" int qzb_deflate_max_warps(int group);
 #ifndef QZB200_GROUP_DEFAULT
-#define QZB200_GROUP_DEFAULT 0
+#define QZB200_GROUP_DEFAULT 1
 #endif
 #ifndef QZB200_GROUP_HB_DEFAULT
-#define QZB200_GROUP_HB_DEFAULT 11
+#define QZB200_GROUP_HB_DEFAULT 10
 #endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
@@ -192,6 +192,8 @@ struct QzbEngine {
     QzbTuning tune;
     static constexpr int NSLOT = 4;       /* batches in flight: copy-in queued, copy-in, compute, copy-out */
     Slot slot[NSLOT];
+    cudaEvent_t ev_base = nullptr;        /* QZB200_TIMELINE=1: start of the host-buffer call, for per-batch timestamps on stderr */
+    int timeline = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -205,6 +207,8 @@ extern "C" QzbEngine *qzb_engine_create(int device)
     qzb_get_tuning(&e->tune);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+    e->timeline = env_int("QZB200_TIMELINE", 0);
+    cudaEventCreate(&e->ev_base);
     for (auto &s : e->slot) {
         if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NULL; }
         cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1); cudaEventCreate(&s.ev_h0); cudaEventCreate(&s.ev_d0); cudaEventCreate(&s.ev_d1);
@@ -217,6 +221,7 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->ev_base) cudaEventDestroy(e->ev_base);
     for (auto &s : e->slot) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -285,12 +290,12 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         const uint32_t gpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * gpc + (last_pieces + 7) / 8;
         hb = t.group_hash_bits;
-        if (warps < 8 || warps > QZB_DEFLATE_MAX_WARPS || warps % 8) warps = 24;
+        if (warps < 8 || warps > qzb_deflate_max_warps(1) || warps % 8) warps = qzb_deflate_max_warps(1);
         if (nbuf <= 0 || nbuf > warps) nbuf = warps;
         while (nbuf > 1 && qzb_deflate_groups_smem_bytes(hb, warps, nbuf) + 3328 > smem_cap) nbuf--;
         group_smem = qzb_deflate_groups_smem_bytes(hb, warps, nbuf);
     } else {
-        if (warps <= 0 || warps > QZB_DEFLATE_MAX_WARPS) { warps = 20; if (nbuf <= 0) nbuf = 17; }
+        if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
@@ -392,10 +397,15 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
     const uint64_t nb = c->src_len ? (c->src_len + batch - 1) / batch : 1;
     uint64_t out = 0, consumed = 0; int rc = RC_OK; bool stop = false;
 
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    if (e->timeline) CK(cudaEventRecord(e->ev_base, e->slot[0].st));
     auto drain = [&](Slot &s) -> int {
         if (!s.busy) return RC_OK;
         s.busy = false;
+        const double host_drain0 = e->timeline ? host_ms() : 0.0;
         CK(cudaEventSynchronize(s.ev_meta));
+        const double host_meta = e->timeline ? host_ms() : 0.0;
         if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
         float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
         cudaEventElapsedTime(&ms, s.ev_k0, s.ev_km); o->codec_ms += ms; o->codec_launches++;
@@ -416,6 +426,13 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(c->fmt, crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
         CK(cudaStreamSynchronize(s.st));
         { float t = 0; cudaEventElapsedTime(&t, s.ev_h0, s.ev_k0); o->h2d_ms += t; cudaEventElapsedTime(&t, s.ev_d0, s.ev_d1); o->d2h_ms += t; }
+        if (e->timeline) {
+            float h0 = 0, k0 = 0, km = 0, k1 = 0, d0 = 0, d1 = 0;
+            cudaEventElapsedTime(&h0, e->ev_base, s.ev_h0); cudaEventElapsedTime(&k0, e->ev_base, s.ev_k0); cudaEventElapsedTime(&km, e->ev_base, s.ev_km);
+            cudaEventElapsedTime(&k1, e->ev_base, s.ev_k1); cudaEventElapsedTime(&d0, e->ev_base, s.ev_d0); cudaEventElapsedTime(&d1, e->ev_base, s.ev_d1);
+            fprintf(stderr, "[qzb timeline] in %5.1f MiB out %5.1f MiB | dev: h2d %.2f-%.2f codec -%.2f frame -%.2f d2h %.2f-%.2f | host: drain@%.2f meta@%.2f done@%.2f\n",
+                    s.in_len / 1048576.0, bytes / 1048576.0, h0, k0, km, k1, d0, d1, host_drain0, host_meta, host_ms());
+        }
         if (bytes && !c->dst_pinned) memcpy(c->dst + out, s.h_out.p, bytes);
         out += bytes; o->nchunks += fit;
         if (fit < s.nchunks) { consumed += (uint64_t)fit * c->chunk_sz; rc = RC_BUF_ERROR; stop = true; }

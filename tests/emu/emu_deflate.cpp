@@ -79,7 +79,7 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     size_t smem;
     std::function<void()> body;
     if (group) {
-        if (!job.ngroups || warps % QZ_GROUP || warps > QZ_DEFLATE_MAX_WARPS || piece_log2 != 13) return -1;
+        if (!job.ngroups || warps % QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13) return -1;
         smem = ((size_t)2 << hb) * warps + (((size_t)2 << hb) >= sizeof(GroupLead) ? 0 : sizeof(GroupLead) * (warps / QZ_GROUP)) + sizeof(PieceBuf<13>) * nbuf;
         if (hb == 10) body = [&] { qzb_deflate_groups_kernel<13, 10>(job, nbuf); };
         else if (hb == 11) body = [&] { qzb_deflate_groups_kernel<13, 11>(job, nbuf); };
