@@ -10,11 +10,10 @@ Every rank owns one GPU and its own 4 GiB shard (weak scaling, no data-path coll
              point qzb200CompressDevice -> same kernels), all ranks summed, max-over-ranks time.
   e2e        the same pass through the reference-facing C ABI: qzCompress() with HOST buffers
              from qzMalloc(PINNED), host->device and device->host copies inside the timed region.
-             The 512 MiB calls are issued by --e2e-threads submitting threads, one session each (the
-             pattern of the reference's own benchmark, test/main.c:2175-2202, and of the reference arm
-             below, which uses one session per host thread): a synchronous call cannot overlap its own
-             pipeline fill and drain, a second session's call can.  e2e.one_thread is the same pass
-             issued by a single thread.
+             One submitting thread by default, every call synchronous.  --e2e-threads T issues the calls from
+             T threads with one session each (the pattern of the reference's own benchmark, test/main.c:2175-2202);
+             on B200 that measured the same (profiles/r01_v7_bench_2threads.json): the host link under H2D + D2H
+             traffic is what bounds a call (profiles/r01_v7_pcie_duplex.json, r01_v7_e2e_timeline.log).
   roofline   (bytes in + bytes out) of one deflate-kernel launch / its CUDA-event duration,
              against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline  the reference's own software path (oracle/_ref: src/qatzip_sw.c + zlib) on the
@@ -116,7 +115,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-threads", type=int, default=env_int("QZ_BENCH_E2E_THREADS", 2), help="submitting threads (one session each) of the e2e pass")
+    ap.add_argument("--e2e-threads", type=int, default=env_int("QZ_BENCH_E2E_THREADS", 1), help="submitting threads (one session each) of the e2e pass")
     ap.add_argument("--gib", type=float, default=float(os.environ.get("QZ_BENCH_GIB", "4")), help="per-GPU workload (GiB); 4 = BASELINE config")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -276,7 +275,8 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("deflate_pieces_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("deflate_dram_bytes_per_launch", tj.get("deflate_pieces_dram_bytes_per_launch"))
         # CPU baseline: bounded sample of the same bytes through the reference's software path
         cpu = None
         if ref_lib and not os.environ.get("QZ_BENCH_NOCPU"):
@@ -291,7 +291,7 @@ def main():
             "kernel_ms_per_step_cuda_events": round(kernel_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
-                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": os.environ.get("QZB200_GROUP", "default"), "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
+                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": "one per 64 KiB chunk (group kernel)" if st.group_blocks else "one per 8 KiB piece", "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
             "ratio": round(made / nbytes, 4),
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
                     "api": f"qzCompress(host pinned -> host pinned), 512 MiB per call, {T} submitting thread(s) with one session each",
@@ -299,7 +299,7 @@ def main():
                     "one_thread": {"value": round(e2e_1, 3), "ms_per_step": round(dt_1 / args.steps * 1e3, 3),
                                    "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in break_1.items()}}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "qzb_deflate_groups_kernel" if st.group_blocks else "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": int(per_launch_bytes), "ms_per_launch": round(per_launch_s * 1e3, 4)},
             "cpu_baseline": cpu, "clocks": clk}))

@@ -20,6 +20,7 @@ typedef struct QzB200Stats_S {
     int device;                  /* CUDA device ordinal the session runs on */
     int piece_log2, hash_bits;   /* compressor geometry in use */
     double h2d_ms, d2h_ms;       /* host-buffer compress calls: summed copy times of the last call (overlapping the kernels) */
+    int group_blocks;            /* 1: deflate sessions of this hw_buff_sz get one block per 8 pieces (group kernel), 0: one per piece */
 } QzB200Stats_T;
 
 /* qzCompress / qzDecompress with src and dest in device memory of the session's GPU.

@@ -7,11 +7,14 @@ echo "== nproc $(nproc)"; nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.m
 echo "== pytest gpu"; timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench_err.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench_err.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>>gpurun_out/bench_err.log | tee gpurun_out/bench_ref.json
+echo "== bench variants (e2e only matters): tail taper, two submitting threads"
+QZ_BENCH_NOCPU=1 QZB200_TAPER=1 timeout 300 python bench.py --steps 3 > gpurun_out/bench_taper.json 2>> gpurun_out/bench_err.log; python -c "import json; b=json.load(open('gpurun_out/bench_taper.json')); print('taper', b['value'], b['e2e']['value'])"
+QZ_BENCH_NOCPU=1 timeout 300 python bench.py --steps 3 --e2e-threads 2 > gpurun_out/bench_2thr.json 2>> gpurun_out/bench_err.log; python -c "import json; b=json.load(open('gpurun_out/bench_2thr.json')); print('2 threads', b['value'], b['e2e']['value'], 'one thread', b['e2e']['one_thread']['value'])"
 echo "== ncu launch list"
 QZ_BENCH_NOCPU=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 1 --warmup 1 --gib 0.5 > gpurun_out/ncu_launch_run.log 2>&1; tail -1 gpurun_out/ncu_launch_run.log
-echo "== ncu full: deflate piece kernel"
-QZ_BENCH_NOCPU=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qzb_deflate_pieces -s 1 -c 1 -o gpurun_out/prof_deflate -f \
+echo "== ncu full: deflate kernel"
+QZ_BENCH_NOCPU=1 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:qzb_deflate_(groups|pieces)" -s 1 -c 1 -o gpurun_out/prof_deflate -f \
    python bench.py --steps 1 --warmup 1 --gib 0.5 > gpurun_out/ncu_full_run.log 2>&1; tail -1 gpurun_out/ncu_full_run.log
 echo "== ncu full: inflate kernel"
 INFL_MIB=512 INFL_REPS=2 INFL_CASES=ours timeout 600 ncu --set full --clock-control none --import-source on -k regex:qzb_inflate_kernel -s 1 -c 1 -o gpurun_out/prof_inflate -f python tools/gpu_inflate_bench.py > gpurun_out/ncu_inflate.log 2>&1; tail -1 gpurun_out/ncu_inflate.log
