@@ -668,7 +668,7 @@ __device__ __forceinline__ void emit_run(const uint32_t *tab, const uint32_t *to
     uint64_t acc = owns_first ? (uint64_t)acc0 : 0ull;
     uint32_t nacc = start & 31, wpos = start >> 5;
     bool partial = !owns_first && nacc != 0;
-#define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slotw[wpos] = (uint32_t)acc; \
+#define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slot_st(slotw + wpos, (uint32_t)acc); \
                                                acc >>= 32; nacc -= 32; wpos++; } } while (0)
     uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);
     for (uint32_t j = beg; j < end; j += 4) {
@@ -951,6 +951,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
         }
         QZ_MARK(3);
         group_bar(bar);
+        QZ_MARK(9);                 /* waiting for the group's slowest piece */
         /* A group that mixes incompressible pieces (close to one token per byte) with compressible ones is better off
          * with a block per piece: one code table cannot serve both, and only whole blocks can fall back to stored. */
         {
@@ -989,8 +990,10 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
             uint32_t hb = 0, pend = 0;
             if (btype) open_block(lead.cs, lead.hist, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
             if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
+            QZ_MARK(11);            /* leader: block header written, tables final */
         }
         group_bar(bar);
+        QZ_MARK(10);                /* waiting for the leader */
         const uint32_t btype = G.btype;
         const bool gfinal = G.bfinal != 0;
         if (btype == 0) {
@@ -1008,7 +1011,9 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
             if (lane == 31) G.bits[wg] = incl;
+            QZ_MARK(12);            /* count pass */
             group_bar(bar);
+            QZ_MARK(13);
             uint32_t before = G.hb, total = G.hb;
 #pragma unroll
             for (int i = 0; i < QZ_GROUP; i++) { const uint32_t bi = G.bits[i]; if (i < (int)wg) before += bi; total += bi; }
@@ -1019,6 +1024,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
             slotw[start >> 5] = 0;
             if (wg == QZ_GROUP - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
             group_bar(bar);
+            QZ_MARK(14);
             /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
             const bool owns_eob = last_in_group && beg < NT && end == NT;
             emit_run(lead.hist, toks, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);

@@ -15,7 +15,17 @@ static inline uint32_t tok_ld(const uint32_t *a, uint64_t) { return *a; }
 static inline uint4 tok_ld4(const uint32_t *a, uint64_t) { return *reinterpret_cast<const uint4 *>(a); }
 static inline void tok_st(uint32_t *a, uint32_t v, uint64_t) { *a = v; }
 static inline uint4 stream_ld16(const uint4 *a, uint64_t) { return *a; }
+static inline void slot_st(uint32_t *a, uint32_t v) { *a = v; }
 #else
+/* whole words of compressed output: written once, read once by the framing kernel much later */
+__device__ __forceinline__ void slot_st(uint32_t *a, uint32_t v)
+{
+#ifdef QZ_SLOT_STREAM
+    asm volatile("st.global.cs.u32 [%0], %1;" :: "l"(a), "r"(v) : "memory");
+#else
+    *a = v;
+#endif
+}
 #define QZ_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 __device__ __forceinline__ uint32_t qz_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 

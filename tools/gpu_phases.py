@@ -1,4 +1,4 @@
-"""Per-phase cycle shares of the deflate piece kernel (needs the A/B build:
+"""Per-phase shares of warp time in the deflate kernel in use (group kernel by default, QZB200_GROUP=0: per piece) (needs the A/B build:
 make -C qatzip_b200/csrc ab ABFLAGS=-DQZ_PHASE_CLOCKS).  Prints lane-0 cycles per phase, summed over warps."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,14 +11,15 @@ cap = L.qzMaxCompressedLength(n, None)
 d_in, d_out = L.qzb200DeviceAlloc(n), L.qzb200DeviceAlloc(cap)
 assert L.qzb200CopyToDevice(d_in, h, n) == 0
 sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536)
-names = ["ticket+buffer wait", "load+crc", "match+select", "token pass", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit"]
+names = ["ticket+buffer wait", "load+crc", "match+select", "token pass", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit",
+         "wait: slowest piece of the group", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "-"]
 out = (C.c_ulonglong * 16)()
 for it in range(3):
     L.qzb_phase_cycles_read(out, 1)
     rc, used, made, _ = prod.compress_device(sess, d_in, n, d_out, cap, 1)
     st = prod.stats(sess)
     L.qzb_phase_cycles_read(out, 0)
-tot = sum(out[:9])
-res = {names[i]: round(out[i] / tot, 4) for i in range(9)}
+tot = sum(out[:16])
+res = {names[i]: round(out[i] / tot, 4) for i in range(16) if out[i]}
 res["codec_ms"] = st.codec_ms; res["ratio"] = made / n
 print(json.dumps(res))
