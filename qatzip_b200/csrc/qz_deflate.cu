@@ -156,14 +156,56 @@ __device__ __forceinline__ bool warp_leaf_depths(uint32_t *A, int n, uint32_t la
     return true;
 }
 
+/* Pass 2 of the in-place Huffman construction across the warp: A[i], i < n - 2, holds the parent of internal node i (always a
+ * higher index), node n - 2 is the root.  Pointer doubling on packed (distance so far << 16 | ancestor): every round each
+ * node adds its ancestor's distance and adopts the ancestor's ancestor, reads and writes of a round separated by a warp
+ * sync, until every node points at the root -- ceil(log2(depth)) rounds instead of n dependent double loads on one lane.
+ * On return A[0..n-1) are the depths (root 0). */
+template <int K>
+__device__ __forceinline__ void warp_depth_pass(uint32_t *A, int n, uint32_t lane)
+{
+    const int ni = n - 1, r = n - 2;
+    uint32_t x[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { const int i = (int)lane + 32 * k; x[k] = i < r ? ((1u << 16) | A[i]) : (uint32_t)r; }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) { const int i = (int)lane + 32 * k; if (i < ni) A[i] = x[k]; }
+    __syncwarp();
+    for (;;) {
+        bool more = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int i = (int)lane + 32 * k;
+            const uint32_t p = x[k] & 0xffffu;
+            if (i < r && p != (uint32_t)r) {
+                const uint32_t y = A[p];
+                x[k] = (((x[k] >> 16) + (y >> 16)) << 16) | (y & 0xffffu);
+                more |= (y & 0xffffu) != (uint32_t)r;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; k++) { const int i = (int)lane + 32 * k; if (i < r) A[i] = x[k]; }
+        __syncwarp();
+        if (__ballot_sync(FULL, more) == 0) break;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { const int i = (int)lane + 32 * k; if (i < ni) A[i] = x[k] >> 16; }
+    __syncwarp();
+}
+
 /* sorted frequencies -> code lengths per symbol, for the literal/length and the distance alphabet at once:
- * the tree passes are serial, so lane 0 walks the literal/length tree while lane 1 walks the distance
- * tree; leaf depths, and the scatter back to symbol order, run across the warp */
+ * the merge pass is serial, so lane 0 merges the literal/length tree while lane 1 merges the distance tree
+ * (branch-free code: the two lanes stay converged); node depths, leaf depths and the scatter back to symbol
+ * order run across the warp */
 __device__ __noinline__ void warp_lengths_pair(uint32_t *keys, const uint16_t *ids, int n, uint8_t *ll_len,
                                                uint32_t *dkeys, const uint16_t *dids, int nd, uint8_t *d_len, uint32_t lane)
 {
-    if (lane < 2) qz_huff_inplace_depths(lane ? dkeys : keys, lane ? nd : n);
+    if (lane < 2) qz_huff_merge_pass(lane ? dkeys : keys, lane ? nd : n);
     __syncwarp();
+    warp_depth_pass<9>(keys, n, lane);
+    warp_depth_pass<1>(dkeys, nd, lane);
     const bool ok_ll = warp_leaf_depths(keys, n, lane);
     const bool ok_d = warp_leaf_depths(dkeys, nd, lane);
     if (lane < 2) {
@@ -495,7 +537,7 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
         nitems += __shfl_sync(FULL, incl, 31);
     }
     __syncwarp();
-    if (lane == 0) { h.hlit = hlit; h.hdist = hdist; h.nitems = nitems; qz_cl_build(cf, &h); }
+    if (lane == 0) { h.hlit = hlit; h.hdist = hdist; h.nitems = nitems; qz_cl_build(cf, &h, cf + 32 /* the run-length scratch is dead by now */); }
     __syncwarp();
 }
 

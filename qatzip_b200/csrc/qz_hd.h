@@ -13,6 +13,14 @@
 #define QZ_HD_SERIAL static
 #endif
 
+/* The scalar routines take plain pointers; in the kernels those always point into shared memory.  Saying so lets the
+ * compiler use shared-memory loads and stores (LDS/STS) instead of generic ones inside out-of-line routines. */
+#if defined(__CUDA_ARCH__)
+#define QZ_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define QZ_ASSUME_SHARED(p) do { } while (0)
+#endif
+
 /* wire/data formats handled by the kernels (superset of QzDataFormat_T: LZ4 is a session type) */
 enum QzbFormat { QZB_FMT_4B = 0, QZB_FMT_GZIP = 1, QZB_FMT_GZIP_EXT = 2, QZB_FMT_RAW = 3, QZB_FMT_LZ4 = 4, QZB_FMT_ZLIB = 5 };
 

@@ -44,6 +44,7 @@ QZ_HD uint32_t qz_bw_finish(QzBitWriter *bw)
  * one-code code-length alphabet): give unused low symbols a count of 1 until two are in use. */
 QZ_HD void qz_huff_force_two(uint32_t *freq, int n)
 {
+    QZ_ASSUME_SHARED(freq);
     int used = 0;
     for (int i = 0; i < n && used < 2; i++) used += freq[i] != 0;
     for (int i = 0; used < 2 && i < n; i++) if (freq[i] == 0) { freq[i] = 1; used++; }
@@ -54,21 +55,51 @@ QZ_HD void qz_huff_force_two(uint32_t *freq, int n)
  * the n-1 internal nodes, root = node n-2 at depth 0, depths non-increasing with the index) are serial;
  * pass 3 (internal depths -> leaf depths) has a serial form here and a warp-parallel one in the kernel.
  * On return of the full routine A[i] is the code length of the i-th sorted symbol (non-increasing in i). */
+/* pass 1 alone: on return A[i], i < n - 2, is the parent of internal node i; the root is node n - 2 */
+QZ_HD_SERIAL void qz_huff_merge_pass(uint32_t *A, int n)
+{
+    /* The two-queue merge.  This loop is the longest single-lane stretch of the compressor (seven warps of a
+     * group wait for it), so it is written for its dependency chain: the weights at the heads of both queues and one
+     * element behind each head live in registers, every load is issued one consumption ahead of its use, and the
+     * choices are selects rather than branches (the literal/length and the distance tree run in two lanes of one
+     * warp and stay converged).  Same tree as the textbook form: ties go to the leaf.
+     *   ar  = weight of internal node `root`      (INF while the queue is empty, i.e. root == next)
+     *   ar2 = weight of internal node `root + 1`  (INF while that node does not exist yet)
+     *   al, al2 = weights of leaves `leaf`, `leaf + 1` (INF past the end)
+     * In-place safety: leaf + root = 2 next throughout, so writes to A[next] stay below every unread leaf. */
+    QZ_ASSUME_SHARED(A);
+    const uint32_t INF = 0xffffffffu;
+    int root = 0, leaf = 2, next;
+    uint32_t ar = A[0] + A[1], ar2 = INF;
+    uint32_t al = leaf < n ? A[leaf] : INF, al2 = leaf + 1 < n ? A[leaf + 1] : INF;
+    A[0] = ar;
+    for (next = 1; next < n - 1; next++) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int child = 0; child < 2; child++) {
+            const bool ti = ar < al;                        /* internal node is strictly lighter; an empty queue never is */
+            s += ti ? ar : al;
+            if (ti) A[root] = (uint32_t)next;               /* parent pointer */
+            root += ti ? 1 : 0; leaf += ti ? 0 : 1;
+            const int la = ti ? root + 1 : leaf + 1;        /* the element that becomes the new look-ahead */
+            const uint32_t ld = (ti ? la < next : la < n) ? A[la] : INF;
+            if (ti) { ar = ar2; ar2 = ld; } else { al = al2; al2 = ld; }
+        }
+        A[next] = s;
+        /* the node just made may be the head of the internal queue, or right behind it */
+        if (root == next) ar = s; else if (root + 1 == next) ar2 = s;
+    }
+}
 QZ_HD_SERIAL void qz_huff_inplace_depths(uint32_t *A, int n)
 {
-    int root, leaf, next;
-    A[0] += A[1]; root = 0; leaf = 2;
-    for (next = 1; next < n - 1; next++) {
-        if (leaf >= n || A[root] < A[leaf]) { A[next] = A[root]; A[root++] = (uint32_t)next; }
-        else A[next] = A[leaf++];
-        if (leaf >= n || (root < next && A[root] < A[leaf])) { A[next] += A[root]; A[root++] = (uint32_t)next; }
-        else A[next] += A[leaf++];
-    }
+    QZ_ASSUME_SHARED(A);
+    qz_huff_merge_pass(A, n);
     A[n - 2] = 0;
-    for (next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
+    for (int next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
 }
 QZ_HD_SERIAL void qz_huff_depths_to_lengths(uint32_t *A, int n)
 {
+    QZ_ASSUME_SHARED(A);
     int avbl = 1, used = 0, dpth = 0, root = n - 2, next = n - 1;
     while (avbl > 0) {
         while (root >= 0 && (int)A[root] == dpth) { used++; root--; }
@@ -88,6 +119,7 @@ QZ_HD_SERIAL void qz_huff_inplace_lengths(uint32_t *A, int n)
  * first (= least frequent first). */
 QZ_HD_SERIAL void qz_huff_limit_sorted(uint32_t *len, int n, int maxbits)
 {
+    QZ_ASSUME_SHARED(len);
     if ((int)len[0] <= maxbits) return;
     uint32_t cnt[16];
     for (int l = 0; l < 16; l++) cnt[l] = 0;
@@ -110,6 +142,7 @@ QZ_HD_SERIAL void qz_huff_limit_sorted(uint32_t *len, int n, int maxbits)
  * last loop across the warp and only the two calls in between on one lane.) */
 QZ_HD_SERIAL void qz_huff_lengths_from_sorted(uint32_t *keys, uint16_t *ids, int n_used, int maxbits, uint8_t *len_by_sym)
 {
+    QZ_ASSUME_SHARED(keys); QZ_ASSUME_SHARED(ids); QZ_ASSUME_SHARED(len_by_sym);
     for (int i = 0; i < n_used; i++) { ids[i] = (uint16_t)(keys[i] & 511u); keys[i] >>= 9; }
     qz_huff_inplace_lengths(keys, n_used);
     qz_huff_limit_sorted(keys, n_used, maxbits);
@@ -147,15 +180,17 @@ struct QzDynHeader : QzDynHeaderCore {
 QZ_HD uint16_t qz_cl_item(uint32_t sym, uint32_t eval, uint32_t ebits) { return (uint16_t)(sym | (eval << 5) | (ebits << 12)); }
 
 /* Code-length alphabet (<= 19 symbols, 7-bit cap) from its frequencies cf[]; sizes the header.
- * h->items / h->nitems / h->hlit / h->hdist must already be set. */
-QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeaderCore *h)
+ * h->items / h->nitems / h->hlit / h->hdist must already be set.  scratch: 32 words in the same memory as cf and h
+ * (shared memory in the kernels -- every pointer the device-side callers of these routines pass is). */
+QZ_HD_SERIAL void qz_cl_build(uint32_t *cf, QzDynHeaderCore *h, uint32_t *scratch)
 {
+    QZ_ASSUME_SHARED(cf); QZ_ASSUME_SHARED(h); QZ_ASSUME_SHARED(scratch);
     /* every item costs its symbol's code plus that symbol's extra bits, so the header size follows from
      * the counters alone (taken before two-code forcing adds symbols that are never written) */
     uint32_t unused = 0;
     for (int k = 0; k < QZ_NUM_CL; k++) unused |= (uint32_t)(cf[k] == 0) << k;
     qz_huff_force_two(cf, QZ_NUM_CL);
-    uint32_t keys[QZ_NUM_CL]; uint16_t ids[QZ_NUM_CL]; int nu = 0;
+    uint32_t *keys = scratch; uint16_t *ids = (uint16_t *)(scratch + 20); int nu = 0;
     for (int k = 0; k < QZ_NUM_CL; k++) {
         h->cl_len[k] = 0;
         if (cf[k]) {
@@ -204,7 +239,8 @@ QZ_HD_SERIAL void qz_dyn_header_plan(const uint8_t *ll_len, const uint8_t *d_len
         i = j;
     }
     h->nitems = n;
-    qz_cl_build(cf, h);
+    uint32_t scratch[32];
+    qz_cl_build(cf, h, scratch);
 }
 
 /* the fixed part of a dynamic block header: BFINAL/BTYPE, HLIT, HDIST, HCLEN and the 3-bit lengths */

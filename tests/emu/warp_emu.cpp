@@ -17,7 +17,7 @@ asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
 namespace emu {
 namespace {
 enum St { RUN, WAIT_WARP, WAIT_CTA, WAIT_NAMED, DONE };
-struct Fiber { void *sp; unsigned tid; St st; unsigned gen; void *site; unsigned bar; };
+struct Fiber { void *sp; unsigned tid; St st; unsigned gen; void *site; unsigned bar; bool slept; };
 struct Warp { unsigned nlive, arrived; uint32_t live; int op; void *site; unsigned gen0; uint32_t snap[2]; uint64_t x[2][32]; };
 
 const size_t STACK = 256 << 10;
@@ -30,6 +30,7 @@ void *sched_sp;
 Fiber *cur;
 unsigned cta_live, cta_arrived;
 unsigned named_arrived[16];
+bool rescan;
 const std::function<void()> *body_fn;
 unsigned long long ncoll;
 
@@ -62,8 +63,13 @@ void warp_arrive(int op, void *site)
         for (unsigned l = 0; l < 32; l++) { const Fiber &f = fibers[(cur->tid & ~31u) + l]; Dl_info d; fprintf(stderr, "  lane %2u state %d collective #%u at +0x%lx\n", l, (int)f.st, f.gen, dladdr(f.site, &d) ? (long)((char *)f.site - (char *)d.dli_fbase) : 0L); }
         die("lanes of one warp reached different collectives (divergent warp-synchronous code)");
     }
-    if (++w.arrived == w.nlive) release_warp(cur->tid >> 5);
-    else { cur->st = WAIT_WARP; to_scheduler(); }
+    if (++w.arrived == w.nlive) {
+        /* the lane that completes the rendezvous does not run on: the warp restarts from its lowest lane, so that the
+         * order of the lanes through the next stretch of code never depends on who arrived last */
+        release_warp(cur->tid >> 5);
+        rescan = true;
+        to_scheduler();
+    } else { cur->st = WAIT_WARP; to_scheduler(); }
 }
 void fiber_main()
 {
@@ -99,7 +105,7 @@ void syncthreads()
     if (++cta_arrived == cta_live) release_cta();
     else { cur->st = WAIT_CTA; to_scheduler(); }
 }
-void yield_sleep() { to_scheduler(); }
+void yield_sleep() { cur->slept = true; to_scheduler(); }
 /* bar.sync id, count: `count` threads of the CTA meet at hardware barrier `id` (1..15) */
 void named_barrier(unsigned id, unsigned count)
 {
@@ -140,16 +146,29 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
             for (int i = 0; i < 6; i++) *--sp = NULL;
             f.sp = sp;
         }
+        /* Warps take turns; inside a warp the runnable lanes always run in ascending lane order, and a warp keeps the
+         * processor until none of its lanes can run.  The order in which the lanes of a warp pass through the code between
+         * two collectives is therefore the same whatever the other warps do: results do not depend on the launch geometry
+         * (the kernels' one intended race, equal-hash insertions inside a tile, is always won by the highest lane). */
         unsigned done = 0;
+        const unsigned nw = (block + 31) / 32;
         while (done < block) {
             bool progress = false;
-            for (unsigned t = 0; t < block; t++) {
-                Fiber &f = fibers[t];
-                if (f.st != RUN) continue;
-                cur = &f; threadIdx = { t, 0, 0 };
-                emu_switch(&sched_sp, f.sp);
-                if (f.st == DONE) done++;
-                progress = true;
+            for (unsigned w = 0; w < nw; w++) {
+                for (bool ran = true; ran;) {
+                    ran = false;
+                    for (unsigned t = w * 32; t < block && t < w * 32 + 32; t++) {
+                        Fiber &f = fibers[t];
+                        if (f.st != RUN) continue;
+                        cur = &f; threadIdx = { t, 0, 0 };
+                        f.slept = false;
+                        emu_switch(&sched_sp, f.sp);
+                        if (f.st == DONE) done++;
+                        if (!f.slept) ran = true;           /* a lane that only slept (spin-wait back-off) does not hold the warp */
+                        progress = true;
+                        if (rescan) { rescan = false; break; }      /* a rendezvous completed: back to the warp's lowest lane */
+                    }
+                }
             }
             if (!progress) { cur = NULL; die("deadlock: every live thread waits at a barrier that cannot complete"); }
         }
