@@ -547,9 +547,9 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
 /* phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
  *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13)
  * Returns the piece's total of extra bits. */
-__device__ __forceinline__ uint32_t token_pass(uint32_t *hist, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep)
+__device__ __forceinline__ uint32_t token_pass(uint32_t *hist, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep, bool zero = true)
 {
-    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0;
+    if (zero) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0; }
     __syncwarp();
     uint32_t extra_acc = 0;
     uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;          /* one group ahead: hides the L2 round trip */
@@ -884,10 +884,11 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
  * and the per-block bytes (dynamic header, flush marker) by eight; the stream is what a zlib deflate with a
  * Z_FULL_FLUSH per 64 KiB would look like.  Warps of a group meet at a named barrier (bar.sync id, 256); groups of
  * one CTA are independent of each other.  Used when a chunk is a whole number of groups (hw_buff_sz >= 64 KiB). */
-#define QZ_GROUP 8
+#define QZ_GROUP 8                      /* pieces per block */
 /* Shared memory of the group kernel: a warp's private slice is its hash table during the match phase and its
- * histogram afterwards (no code scratch: only the leader builds codes), so a 2^10-entry table makes it 2 KiB; the
- * code scratch and the group's histogram / code tables live once per group. */
+ * histogram afterwards (no code scratch: only the leader builds codes), so a 2^10-entry table makes it 2 KiB.  The
+ * code scratch and the group's histogram / code tables (GroupLead, 4000 B) live in a piece buffer that the leader
+ * takes from the pool for the time the block is being coded: no shared memory is set aside for them. */
 template <int HB>
 struct GroupWarpPriv {
     union {
@@ -897,26 +898,82 @@ struct GroupWarpPriv {
 };
 struct GroupLead { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; };
 struct GroupShared {
-    uint32_t ticket, bfinal, btype, hb, pend;
-    uint32_t nbytes[QZ_GROUP], ntok[QZ_GROUP], extra[QZ_GROUP], bits[QZ_GROUP];
+    uint32_t ticket, bfinal, btype, hb, pend, lead_buf;
+    uint32_t nbytes[QZ_GROUP], ntok[QZ_GROUP], bits[QZ_GROUP], extra[QZ_GROUP];
 };
+template <int NT>
+__device__ __forceinline__ void group_bar(uint32_t id)
+{
 #ifdef QZ_WARP_EMU
-static inline void group_bar(uint32_t id) { emu::named_barrier(id, QZ_GROUP * 32); }
+    emu::named_barrier(id, NT);
 #else
-__device__ __forceinline__ void group_bar(uint32_t id) { __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(QZ_GROUP * 32) : "memory"); }
+    __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NT) : "memory");
 #endif
+}
 
-template <int PIECE_LOG2, int HB>
+/* take a free piece buffer: one bit per buffer in *busy (set = free); a warp that finds none sleeps with exponential
+ * back-off instead of spinning on the issue slots the working warps need */
+__device__ __forceinline__ uint32_t take_buffer(uint32_t *busy, uint32_t lane)
+{
+    uint32_t b = 0;
+    if (lane == 0) {
+        uint32_t ns = 128;
+        for (;;) {
+            const uint32_t m = *reinterpret_cast<volatile uint32_t *>(busy);
+            if (m) {
+                b = __ffs(m) - 1;
+                if (atomicAnd(busy, ~(1u << b)) & (1u << b)) break;
+                continue;
+            }
+            __nanosleep(ns);
+            if (ns < 4096) ns <<= 1;
+        }
+        __threadfence_block();
+    }
+    return __shfl_sync(FULL, b, 0);
+}
+__device__ __forceinline__ void give_buffer(uint32_t *busy, uint32_t b, uint32_t lane)
+{
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicOr(busy, 1u << b); }
+}
+
+/* histogram and extra-bit total of one piece from its tokens in symbol form (mixed groups: the warp's own histogram
+ * may cover two pieces) */
+__device__ __forceinline__ uint32_t hist_from_tokens(uint32_t *hist, const uint32_t *toks, uint32_t ntok, uint32_t lane, uint64_t pkeep)
+{
+    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0;
+    __syncwarp();
+    uint32_t extra = 0;
+    for (uint32_t i = lane; i < ntok; i += 32) {
+        const uint32_t t = tok_ld(toks + i, pkeep);
+        if (t & 0x80000000u) {
+            const uint32_t ls = (t >> 26) & 31, ds = (t >> 16) & 31;
+            atomicAdd(&hist[257 + ls], 1u);
+            atomicAdd(&hist[QZ_DOFF + ds], 1u);
+            extra += ((ls < 8 || ls == 28) ? 0u : (ls - 4) >> 2) + (ds < 4 ? 0u : (ds >> 1) - 1);
+        } else atomicAdd(&hist[t & 511u], 1u);
+    }
+    __syncwarp();
+    return warp_sum(extra);
+}
+
+/* GW warps per group, each with PPW = 8 / GW pieces of the block.  Only GW = 8 (one piece per warp) is instantiated: GW = 4
+ * (two pieces per warp, so that three warps instead of seven wait for the leader) did cut that wait from 16 % to 11 % of warp
+ * time on B200 but ran 30 % slower overall -- two pieces' tokens per warp no longer fit the L2 -- and is not offered. */
+template <int PIECE_LOG2, int HB, int GW>
 __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    static_assert(sizeof(GroupWarpPriv<HB>) == (sizeof(uint16_t) << HB) && sizeof(GroupLead) % 16 == 0, "a warp's histogram must fit in its hash table");
+    constexpr int PPW = QZ_GROUP / GW;
+    static_assert(sizeof(GroupWarpPriv<HB>) == (sizeof(uint16_t) << HB), "a warp's histogram must fit in its hash table");
+    static_assert(sizeof(GroupLead) <= sizeof(PieceBuf<PIECE_LOG2>) && sizeof(PieceBuf<PIECE_LOG2>) % 16 == 0, "the code scratch borrows a piece buffer");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];
     __shared__ uint16_t s_lentab[256];
     __shared__ uint32_t s_busy[1];
-    __shared__ GroupShared s_grp[QZ_GROUPS_MAX_WARPS / QZ_GROUP];
+    __shared__ GroupShared s_grp[QZ_GROUPS_MAX_WARPS / GW];
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -928,71 +985,68 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
     if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;
     __syncthreads();
 
-    const uint32_t grp = warp / QZ_GROUP, wg = warp % QZ_GROUP, bar = 1 + grp;
+    const uint32_t grp = warp / GW, wg = warp % GW, bar = 1 + grp;
     GroupShared &G = s_grp[grp];
-    /* group histogram -> code tables, and the code scratch: on top of the leader's own slice when that is large enough
-     * (its own histogram sits in the part that becomes cs.keys, which is written only after the sum), else after the slices */
-    constexpr bool LEAD_OVERLAY = sizeof(GroupWarpPriv<HB>) >= sizeof(GroupLead);
-    GroupLead &lead = LEAD_OVERLAY ? *reinterpret_cast<GroupLead *>(wsv + grp * QZ_GROUP) : reinterpret_cast<GroupLead *>(wsv + nwarps)[grp];
-    static_assert(offsetof(GroupLead, hist) >= QZ_HIST_WORDS * 4, "the summed histogram must not land on the leader's own");
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint32_t *toks = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
+    uint32_t *toks0 = job.tok_scratch + (size_t)gwarp * PPW * QZB_TOK_STRIDE(PIECE);
     const uint32_t gpc = job.pieces_per_chunk / QZ_GROUP;     /* groups per chunk */
     const uint64_t pkeep = l2_policy_keep();
+    uint32_t held = 0xffffffffu;                              /* leader: the piece buffer that serves as the block's code scratch */
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
     for (;;) {
         if (wg == 0 && lane == 0) { G.ticket = atomicAdd(job.ticket, 1u); G.bfinal = 0; }
-        group_bar(bar);
+        group_bar<GW * 32>(bar);
+        /* every warp of the group is past the previous block's emission: its code tables can go */
+        if (wg == 0 && held != 0xffffffffu) { give_buffer(&s_busy[0], held, lane); held = 0xffffffffu; }
         const uint32_t gi = G.ticket;
         if (gi >= job.ngroups) break;
         const uint32_t chunk = gi / gpc, blk = gi - chunk * gpc;
-        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_GROUP, g = g0 + wg;
-        /* this warp's piece: n = 0 for pieces behind the end of a ragged last chunk */
-        PieceState ps;
-        bool chunk_end;
-        {
+        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_GROUP;
+        /* this warp's pieces: n = 0 for pieces behind the end of a ragged last chunk */
+        PieceState ps[PPW];
+        bool last_in_group[PPW];
+#pragma unroll
+        for (int j = 0; j < PPW; j++) {
+            const uint32_t pi = wg * PPW + j;
             const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
             const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
             const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
-            const uint32_t p_off = (blk * QZ_GROUP + wg) << PIECE_LOG2;
-            ps.g = g; ps.n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u; ps.ntok = 0; ps.extra_total = 0; ps.bfinal = false;
-            ps.src = job.src + chunk_off + p_off;
-            chunk_end = ps.n != 0 && p_off + ps.n == chunk_len;
+            const uint32_t p_off = (blk * QZ_GROUP + pi) << PIECE_LOG2;
+            ps[j].g = g0 + pi; ps[j].n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u; ps[j].ntok = 0; ps[j].extra_total = 0; ps[j].bfinal = false;
+            ps[j].src = job.src + chunk_off + p_off;
+            last_in_group[j] = ps[j].n != 0 && (pi == QZ_GROUP - 1 || p_off + ps[j].n == chunk_len);
         }
-        if (ps.n) {
-            uint32_t b = 0;
-            if (lane == 0) {
-                uint32_t ns = 128;
-                for (;;) {
-                    const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&s_busy[0]);
-                    if (m) {
-                        b = __ffs(m) - 1;
-                        if (atomicAnd(&s_busy[0], ~(1u << b)) & (1u << b)) break;
-                        continue;
-                    }
-                    __nanosleep(ns);
-                    if (ns < 4096) ns <<= 1;
-                }
-                __threadfence_block();
+        /* phases 1-2 for every piece first (the hash table and the histogram share the warp's slice), then the token passes */
+#pragma unroll
+        for (int j = 0; j < PPW; j++) {
+            if (ps[j].n) {
+                const uint32_t b = take_buffer(&s_busy[0], lane);
+                QZ_MARK(0);
+                phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks0 + j * QZB_TOK_STRIDE(PIECE), s_crc_tab, s_xstrip, ps[j].g, lane, ps[j] QZ_TPASS);
+                give_buffer(&s_busy[0], b, lane);
             }
-            b = __shfl_sync(FULL, b, 0);
-            QZ_MARK(0);
-            phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
         }
-        /* token pass on the private histogram; the last piece of the block carries the end-of-block token */
-        const uint32_t extra = warp_sum(token_pass(ws.u.hist, toks, ps.ntok, s_lentab, lane, pkeep));
-        const bool last_in_group = ps.n != 0 && (wg == QZ_GROUP - 1 || chunk_end);
+        uint32_t extra = 0;
+#pragma unroll
+        for (int j = 0; j < PPW; j++) {
+            uint32_t *toks = toks0 + j * QZB_TOK_STRIDE(PIECE);
+            extra += token_pass(ws.u.hist, toks, ps[j].ntok, s_lentab, lane, pkeep, j == 0);
+            /* the last piece of the block carries the end-of-block token */
+            if (lane == 0 && last_in_group[j]) tok_st(toks + ps[j].ntok, 256u, pkeep);
+        }
+        extra = warp_sum(extra);
         if (lane == 0) {
-            if (last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
-            G.nbytes[wg] = ps.n; G.ntok[wg] = ps.ntok + (last_in_group ? 1u : 0u); G.extra[wg] = extra;
-            if (ps.bfinal) G.bfinal = 1;
+#pragma unroll
+            for (int j = 0; j < PPW; j++) {
+                G.nbytes[wg * PPW + j] = ps[j].n; G.ntok[wg * PPW + j] = ps[j].ntok + (last_in_group[j] ? 1u : 0u);
+                if (ps[j].bfinal) G.bfinal = 1;
+            }
+            G.extra[wg] = extra;
         }
         QZ_MARK(3);
-        group_bar(bar);
+        group_bar<GW * 32>(bar);
         QZ_MARK(9);                 /* waiting for the group's slowest piece */
         /* A group that mixes incompressible pieces (close to one token per byte) with compressible ones is better off
          * with a block per piece: one code table cannot serve both, and only whole blocks can fall back to stored. */
@@ -1004,73 +1058,98 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
                 if (nb) { const uint32_t r = (G.ntok[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
             }
             if (hi > 920u && lo < 768u) {
-                /* rare: the pieces take turns with the group's one code scratch */
-                if (ps.n && lane == 0 && !last_in_group) tok_st(toks + ps.ntok, 256u, pkeep);
-                for (uint32_t turn = 0; turn < QZ_GROUP; turn++) {
-                    if (turn == wg && ps.n) {
-                        for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) lead.hist[s] = ws.u.hist[s];
-                        __syncwarp();
-                        finish_piece(job, lead.cs, lead.hist, toks, lane, ps, extra, pkeep QZ_TPASS);
-                    }
-                    group_bar(bar);
+                /* rare: every piece on its own, with a piece buffer as its code scratch */
+#pragma unroll
+                for (int j = 0; j < PPW; j++) {
+                    if (!ps[j].n) continue;
+                    uint32_t *toks = toks0 + j * QZB_TOK_STRIDE(PIECE);
+                    if (lane == 0) tok_st(toks + ps[j].ntok, 256u, pkeep);
+                    const uint32_t b = take_buffer(&s_busy[0], lane);
+                    GroupLead &own = *reinterpret_cast<GroupLead *>(bufs[b].bytes);
+                    const uint32_t ex = hist_from_tokens(own.hist, toks, ps[j].ntok, lane, pkeep);
+                    finish_piece(job, own.cs, own.hist, toks, lane, ps[j], ex, pkeep QZ_TPASS);
+                    give_buffer(&s_busy[0], b, lane);
                 }
                 continue;
             }
         }
         /* leader: one histogram, one set of codes, one block header for the group */
         if (wg == 0) {
+            held = take_buffer(&s_busy[0], lane);
+            GroupLead &L = *reinterpret_cast<GroupLead *>(bufs[held].bytes);
             uint32_t extra_total = 0, nbytes = 0, npc = 0;
-            for (int i = 0; i < QZ_GROUP; i++) { extra_total += G.extra[i]; nbytes += G.nbytes[i]; npc += G.nbytes[i] ? 1u : 0u; }
+            for (int i = 0; i < GW; i++) extra_total += G.extra[i];
+            for (int i = 0; i < QZ_GROUP; i++) { nbytes += G.nbytes[i]; npc += G.nbytes[i] ? 1u : 0u; }
             for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) {
                 uint32_t f = 0;
 #pragma unroll
-                for (int i = 0; i < QZ_GROUP; i++) f += wsv[grp * QZ_GROUP + i].u.hist[s];
-                lead.hist[s] = f;
+                for (int i = 0; i < GW; i++) f += wsv[grp * GW + i].u.hist[s];
+                L.hist[s] = f;
             }
             __syncwarp();
-            const int btype = choose_block(lead.cs, lead.hist, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
+            const int btype = choose_block(L.cs, L.hist, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
             uint32_t hb = 0, pend = 0;
-            if (btype) open_block(lead.cs, lead.hist, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
-            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
+            if (btype) open_block(L.cs, L.hist, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
+            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; G.lead_buf = held; }
             QZ_MARK(11);            /* leader: block header written, tables final */
         }
-        group_bar(bar);
+        group_bar<GW * 32>(bar);
         QZ_MARK(10);                /* waiting for the leader */
         const uint32_t btype = G.btype;
         const bool gfinal = G.bfinal != 0;
         if (btype == 0) {
             /* incompressible group: every piece is its own stored block in its own slot, as in the per-piece kernel */
-            uint32_t out_bytes = 0;
-            if (ps.n) out_bytes = stored_piece(job.slots + (size_t)g * job.slot_stride, ps.src, ps.n, ps.bfinal, lane);
-            if (lane == 0 && ps.n) job.piece_len[g] = out_bytes;
+#pragma unroll
+            for (int j = 0; j < PPW; j++) {
+                if (!ps[j].n) continue;
+                const uint32_t out_bytes = stored_piece(job.slots + (size_t)ps[j].g * job.slot_stride, ps[j].src, ps[j].n, ps[j].bfinal, lane);
+                if (lane == 0) job.piece_len[ps[j].g] = out_bytes;
+            }
         } else {
+            const uint32_t *tab = reinterpret_cast<const GroupLead *>(bufs[G.lead_buf].bytes)->hist;
             uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
-            const uint32_t NT = G.ntok[wg];
-            const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
-            const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-            const uint32_t mybits = count_run_bits(lead.hist, toks, beg, end, pkeep);
-            uint32_t incl = mybits;
+            uint32_t beg[PPW], end[PPW], mybits[PPW], incl[PPW];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-            if (lane == 31) G.bits[wg] = incl;
+            for (int j = 0; j < PPW; j++) {
+                const uint32_t NT = G.ntok[wg * PPW + j];
+                const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
+                beg[j] = min(lane * R, NT); end[j] = min(beg[j] + R, NT);
+                mybits[j] = count_run_bits(tab, toks0 + j * QZB_TOK_STRIDE(PIECE), beg[j], end[j], pkeep);
+                incl[j] = mybits[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl[j], o); if (lane >= (uint32_t)o) incl[j] += y; }
+                if (lane == 31) G.bits[wg * PPW + j] = incl[j];
+            }
             QZ_MARK(12);            /* count pass */
-            group_bar(bar);
+            group_bar<GW * 32>(bar);
             QZ_MARK(13);
-            uint32_t before = G.hb, total = G.hb;
+            uint32_t before[PPW], total = G.hb;
 #pragma unroll
-            for (int i = 0; i < QZ_GROUP; i++) { const uint32_t bi = G.bits[i]; if (i < (int)wg) before += bi; total += bi; }
-            const uint32_t start = before + incl - mybits;
+            for (int j = 0; j < PPW; j++) before[j] = G.hb;
+#pragma unroll
+            for (int i = 0; i < QZ_GROUP; i++) {
+                const uint32_t bi = G.bits[i];
+#pragma unroll
+                for (int j = 0; j < PPW; j++) if (i < (int)(wg * PPW + j)) before[j] += bi;
+                total += bi;
+            }
             const uint32_t end_bit = total;
             const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);
             const uint32_t end_bit2 = gfinal ? end_bit : end_bit + nz + 32;
-            slotw[start >> 5] = 0;
-            if (wg == QZ_GROUP - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
-            group_bar(bar);
+#pragma unroll
+            for (int j = 0; j < PPW; j++) slotw[(before[j] + incl[j] - mybits[j]) >> 5] = 0;
+            if (wg == GW - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
+            group_bar<GW * 32>(bar);
             QZ_MARK(14);
-            /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
-            const bool owns_eob = last_in_group && beg < NT && end == NT;
-            emit_run(lead.hist, toks, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
-            if (lane == 0 && ps.n) job.piece_len[g] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
+#pragma unroll
+            for (int j = 0; j < PPW; j++) {
+                const uint32_t NT = G.ntok[wg * PPW + j];
+                /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
+                const bool owns_eob = last_in_group[j] && beg[j] < NT && end[j] == NT;
+                emit_run(tab, toks0 + j * QZB_TOK_STRIDE(PIECE), beg[j], end[j], before[j] + incl[j] - mybits[j], G.pend, wg == 0 && j == 0 && lane == 0,
+                         !gfinal && owns_eob, nz, slotw, pkeep);
+                if (lane == 0 && ps[j].n) job.piece_len[ps[j].g] = (wg == 0 && j == 0) ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
+            }
         }
         __syncwarp();
         QZ_MARK(8);
@@ -1270,30 +1349,30 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
 
 extern "C" int qzb_deflate_max_warps(int group) { return group ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
-/* shared memory of the group kernel for `warps` warps (a multiple of 8) sharing `nbuf` piece buffers */
+/* shared memory of the group kernel for `warps` warps sharing `nbuf` piece buffers (the code scratch borrows from the pool) */
 extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf)
 {
-    const size_t priv = (size_t)2 << hb;
-    return priv * (size_t)warps + (priv >= sizeof(GroupLead) ? 0 : sizeof(GroupLead) * (size_t)(warps / QZ_GROUP)) + sizeof(PieceBuf<13>) * (size_t)nbuf;
+    return ((size_t)2 << hb) * (size_t)warps + sizeof(PieceBuf<13>) * (size_t)nbuf;
 }
 
-template <int P, int H>
+template <int P, int H, int GW>
 static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, int warps, int nbuf, cudaStream_t st)
 {
     size_t smem = qzb_deflate_groups_smem_bytes(H, warps, nbuf);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_groups_kernel<P, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_groups_kernel<P, H, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_groups_kernel<P, H><<<grid, warps * 32, smem, st>>>(job, nbuf);
+    qzb_deflate_groups_kernel<P, H, GW><<<grid, warps * 32, smem, st>>>(job, nbuf);
     return cudaGetLastError();
 }
 
-/* group kernel (one deflate block per QZ_GROUP pieces): warps must be a multiple of QZ_GROUP, job->ngroups set */
+/* group kernel (one deflate block per QZ_GROUP pieces): warps a multiple of QZ_GROUP, job->ngroups set */
 extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
 {
-    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups) return cudaErrorInvalidValue;
-    if (job->piece_log2 == 13 && hb == 10) return launch_deflate_groups<13, 10>(*job, grid, warps, nbuf, st);
-    if (job->piece_log2 == 13 && hb == 11) return launch_deflate_groups<13, 11>(*job, grid, warps, nbuf, st);
-    if (job->piece_log2 == 13 && hb == 12) return launch_deflate_groups<13, 12>(*job, grid, warps, nbuf, st);
+    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13)
+        return cudaErrorInvalidValue;
+    if (hb == 10) return launch_deflate_groups<13, 10, 8>(*job, grid, warps, nbuf, st);
+    if (hb == 11) return launch_deflate_groups<13, 11, 8>(*job, grid, warps, nbuf, st);
+    if (hb == 12) return launch_deflate_groups<13, 12, 8>(*job, grid, warps, nbuf, st);
     return cudaErrorInvalidValue;
 }
 

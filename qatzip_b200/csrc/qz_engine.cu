@@ -278,7 +278,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, hb = t.hash_bits;
+    int nbuf = t.buffers_per_cta, hb = t.hash_bits, gw = 8;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
@@ -290,7 +290,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         const uint32_t gpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * gpc + (last_pieces + 7) / 8;
         hb = t.group_hash_bits;
-        if (warps < 8 || warps > qzb_deflate_max_warps(1) || warps % 8) warps = qzb_deflate_max_warps(1);
+        if (warps < gw || warps > qzb_deflate_max_warps(1) || warps % gw) warps = qzb_deflate_max_warps(1);
         if (nbuf <= 0 || nbuf > warps) nbuf = warps;
         while (nbuf > 1 && qzb_deflate_groups_smem_bytes(hb, warps, nbuf) + 3328 > smem_cap) nbuf--;
         group_smem = qzb_deflate_groups_smem_bytes(hb, warps, nbuf);
@@ -302,13 +302,13 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / ((group_smem ? group_smem : smem_for(warps, nbuf)) + 3328));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
-    const int need = job.ngroups ? (int)((job.ngroups + warps / 8 - 1) / (warps / 8)) : (int)((job.npieces + warps - 1) / warps);
+    const int need = job.ngroups ? (int)((job.ngroups + warps / gw - 1) / (warps / gw)) : (int)((job.npieces + warps - 1) / warps);
     if (grid > need) grid = std::max(1, need);
 
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((size_t)grid * warps * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((size_t)grid * warps * (job.ngroups ? 8 / gw : 1) * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
