@@ -894,6 +894,7 @@ struct GroupWarpPriv {
     union {
         uint16_t table[1 << HB];
         uint32_t hist[QZ_HIST_WORDS];
+        uint8_t pad[(((2 << HB) > QZ_HIST_WORDS * 4 ? (2 << HB) : QZ_HIST_WORDS * 4) + 15) & ~15];     /* 2^9 entries: the histogram (1272 B) sets the size */
     } u;
 };
 struct GroupLead { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; };
@@ -966,7 +967,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
     constexpr int PPW = QZ_GROUP / GW;
-    static_assert(sizeof(GroupWarpPriv<HB>) == (sizeof(uint16_t) << HB), "a warp's histogram must fit in its hash table");
+    static_assert(sizeof(GroupWarpPriv<HB>) % 16 == 0 && sizeof(GroupWarpPriv<HB>) >= QZ_HIST_WORDS * 4, "a warp's slice holds its hash table, then its histogram");
     static_assert(sizeof(GroupLead) <= sizeof(PieceBuf<PIECE_LOG2>) && sizeof(PieceBuf<PIECE_LOG2>) % 16 == 0, "the code scratch borrows a piece buffer");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
@@ -1352,7 +1353,8 @@ extern "C" int qzb_deflate_max_warps(int group) { return group ? QZ_GROUPS_MAX_W
 /* shared memory of the group kernel for `warps` warps sharing `nbuf` piece buffers (the code scratch borrows from the pool) */
 extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf)
 {
-    return ((size_t)2 << hb) * (size_t)warps + sizeof(PieceBuf<13>) * (size_t)nbuf;
+    const size_t priv = hb == 9 ? sizeof(GroupWarpPriv<9>) : (size_t)2 << hb;
+    return priv * (size_t)warps + sizeof(PieceBuf<13>) * (size_t)nbuf;
 }
 
 template <int P, int H, int GW>
@@ -1370,6 +1372,7 @@ extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int 
 {
     if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13)
         return cudaErrorInvalidValue;
+    if (hb == 9) return launch_deflate_groups<13, 9, 8>(*job, grid, warps, nbuf, st);
     if (hb == 10) return launch_deflate_groups<13, 10, 8>(*job, grid, warps, nbuf, st);
     if (hb == 11) return launch_deflate_groups<13, 11, 8>(*job, grid, warps, nbuf, st);
     if (hb == 12) return launch_deflate_groups<13, 12, 8>(*job, grid, warps, nbuf, st);

@@ -94,8 +94,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     /* deflate block granularity: 1 = one block per group of 8 pieces (group kernel, chunks that are a whole number of
      * groups, i.e. hw_buff_sz >= 64 KiB with 8 KiB pieces), 0 = one block per piece everywhere */
     t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);
-    t->group_hash_bits = env_int("QZB200_GROUP_HASH_BITS", QZB200_GROUP_HB_DEFAULT);     /* 10: 2 KiB per warp, more piece buffers; 11, 12 */
-    if (t->group_hash_bits < 10 || t->group_hash_bits > 12) t->group_hash_bits = QZB200_GROUP_HB_DEFAULT;
+    t->group_hash_bits = env_int("QZB200_GROUP_HASH_BITS", QZB200_GROUP_HB_DEFAULT);     /* 9: 1.25 KiB per warp (22 piece buffers, about 1 % larger output); 10: 2 KiB; 11, 12 */
+    if (t->group_hash_bits < 9 || t->group_hash_bits > 12) t->group_hash_bits = QZB200_GROUP_HB_DEFAULT;
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;

@@ -83,8 +83,9 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
         if (!job.ngroups || warps % gw || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13 || nbuf < 1) return -1;
         EmuCompressBuffers b2;
         emu_job_setup(&job, &b2, fmt, src, len, chunk_sz, last, static_huffman, piece_log2, grid * warps * (QZ_GROUP / gw), dst, cap);
-        smem = ((size_t)2 << hb) * warps + sizeof(PieceBuf<13>) * nbuf;
-        if (gw == 8 && hb == 10) body = [&] { qzb_deflate_groups_kernel<13, 10, 8>(job, nbuf); };
+        smem = (hb == 9 ? sizeof(GroupWarpPriv<9>) : ((size_t)2 << hb)) * warps + sizeof(PieceBuf<13>) * nbuf;
+        if (gw == 8 && hb == 9) body = [&] { qzb_deflate_groups_kernel<13, 9, 8>(job, nbuf); };
+        else if (gw == 8 && hb == 10) body = [&] { qzb_deflate_groups_kernel<13, 10, 8>(job, nbuf); };
         else if (gw == 8 && hb == 11) body = [&] { qzb_deflate_groups_kernel<13, 11, 8>(job, nbuf); };
         else if (gw == 8 && hb == 12) body = [&] { qzb_deflate_groups_kernel<13, 12, 8>(job, nbuf); };
         else return -1;

@@ -353,7 +353,7 @@ def test_group_deflate_round_trip(emu, port, fmt, name, make, n, hb):
 
 @pytest.mark.parametrize("chunk", [65536, 131072, 524288])
 @pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=16, grid=1), dict(warps=24, nbuf=15, grid=1), dict(warps=8, nbuf=8, grid=1, hb=12),
-                                  dict(warps=24, nbuf=20, grid=1, hb=10), dict(warps=8, nbuf=5, grid=2, hb=10), dict(warps=32, nbuf=19, grid=1, hb=10)])
+                                  dict(warps=24, nbuf=20, grid=1, hb=10), dict(warps=8, nbuf=5, grid=2, hb=10), dict(warps=32, nbuf=19, grid=1, hb=10), dict(warps=32, nbuf=22, grid=1, hb=9), dict(warps=8, nbuf=2, grid=2, hb=9)])
 def test_group_deflate_geometries_and_chunks(emu, port, chunk, geom):
     data = sil(chunk + chunk // 2 + 4321)
     blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, **dict(dict(group=1), **geom))

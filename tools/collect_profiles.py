@@ -1,13 +1,13 @@
 """Copy what a tools/gpu_final.sh visit left in gpurun_out/ into profiles/ under a round/version tag:
 bench lines, the ncu launch list, text summaries of the two full ncu captures, DRAM traffic of the deflate launch."""
 import csv, io, json, os, shutil, subprocess, sys
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01_v7"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01_v8"
 G, P = "gpurun_out", "profiles"
 def cp(src, dst):
     if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(P, dst)); print("copied", dst)
 cp("bench.json", f"{tag}_bench.json"); cp("bench_ref.json", f"{tag}_bench_ref.json"); cp("launches.csv", f"{tag}_launches_bench.csv")
 cp("extra.json", f"{tag}_extra.json"); cp("inflate_bench.json", f"{tag}_inflate_bench.json"); cp("geom.jsonl", f"{tag}_geometry_sweep.jsonl"); cp("geom41.jsonl", f"{tag}_group_ab.jsonl"); cp("pcie_duplex.json", f"{tag}_pcie_duplex.json"); cp("timeline.log", f"{tag}_e2e_timeline.log")
-cp("bench_taper.json", f"{tag}_bench_taper.json"); cp("bench_2thr.json", f"{tag}_bench_2threads.json"); cp("pytest_gpu.log", f"{tag}_pytest_gpu.log")
+cp("bench_taper.json", f"{tag}_bench_taper.json"); cp("bench_2thr.json", f"{tag}_bench_2threads.json"); cp("pytest_gpu.log", f"{tag}_pytest_gpu.log"); cp("group_hash_bits.log", f"{tag}_group_hash_bits.log")
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max",
         "sm__inst_executed.avg.per_cycle_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",

@@ -7,6 +7,8 @@ echo "== nproc $(nproc)"; nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.m
 echo "== pytest gpu"; timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench_err.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench_err.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>>gpurun_out/bench_err.log | tee gpurun_out/bench_ref.json
+echo "== hash-table sizes of the group kernel (buffers fitted to the 227 KB)"
+for hb in 10 9; do echo -n "hash bits $hb: "; QZB200_GROUP_HASH_BITS=$hb timeout 120 python tools/gpu_geom.py 2>&1 | tail -1; done | tee gpurun_out/group_hash_bits.log
 echo "== bench variants (e2e only matters): tail taper, two submitting threads"
 QZ_BENCH_NOCPU=1 QZB200_TAPER=1 timeout 300 python bench.py --steps 3 > gpurun_out/bench_taper.json 2>> gpurun_out/bench_err.log; python -c "import json; b=json.load(open('gpurun_out/bench_taper.json')); print('taper', b['value'], b['e2e']['value'])"
 QZ_BENCH_NOCPU=1 timeout 300 python bench.py --steps 3 --e2e-threads 2 > gpurun_out/bench_2thr.json 2>> gpurun_out/bench_err.log; python -c "import json; b=json.load(open('gpurun_out/bench_2thr.json')); print('2 threads', b['value'], b['e2e']['value'], 'one thread', b['e2e']['one_thread']['value'])"
