@@ -302,7 +302,9 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / ((group_smem ? group_smem : smem_for(warps, nbuf)) + 3328));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
-    const int need = job.ngroups ? (int)((job.ngroups + warps / gw - 1) / (warps / gw)) : (int)((job.npieces + warps - 1) / warps);
+    /* small batches: one unit (group or piece) per CTA spreads them over the SMs -- a group alone on an SM finishes in a
+     * fraction of the time it takes next to three others, and the surplus warps of each CTA find no ticket and leave */
+    const int need = job.ngroups ? (int)job.ngroups : (int)job.npieces;
     if (grid > need) grid = std::max(1, need);
 
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
