@@ -38,6 +38,8 @@ class Emu:
         L.emu_deflate_compress.restype = C.c_long
         L.emu_deflate_compress.argtypes = [C.c_int, V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            V, C.c_uint64, V, C.c_int]
+        L.emu_deflate_split.restype = C.c_long
+        L.emu_deflate_split.argtypes = [C.c_int, V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_lz4_compress.restype = C.c_long
         L.emu_lz4_compress.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_inflate.argtypes = [C.c_int, V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int, C.c_int]
@@ -51,6 +53,17 @@ class Emu:
         dst = C.create_string_buffer(max(cap, 1))
         ck = (C.c_uint32 * nch)()
         n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck, group)
+        assert n >= 0, "geometry not offered by the kernel"
+        return dst.raw[:n], list(ck)
+
+    def deflate_split(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, hb=10, nmatch=5, nteams=1, grid=2, cap=None):
+        """experimental matcher / coder kernel -> (stream bytes, [per-chunk checksum])"""
+        data = bytes(data)
+        nch = max(1, (len(data) + chunk - 1) // chunk)
+        cap = cap if cap is not None else len(data) + len(data) // 8 + 512 * nch + 64
+        dst = C.create_string_buffer(max(cap, 1))
+        ck = (C.c_uint32 * nch)()
+        n = self.lib.emu_deflate_split(fmt, data, len(data), chunk, last, static, hb, nmatch, nteams, grid, dst, cap, ck)
         assert n >= 0, "geometry not offered by the kernel"
         return dst.raw[:n], list(ck)
 

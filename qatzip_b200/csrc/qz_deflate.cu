@@ -1157,6 +1157,10 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_k
     }
 }
 
+#ifdef QZ_SPLIT_KERNEL
+#include "qz_deflate_split.cuh"
+#endif
+
 /* ------------------------------------------------------------------------------------------ */
 /* Framing: sizes -> exclusive scan -> headers, payload gather, footers.
  * Replaces doCompressOut's per-chunk header gen / payload memcpy / crc32_combine / footer gen
@@ -1378,6 +1382,34 @@ extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int 
     if (hb == 12) return launch_deflate_groups<13, 12, 8>(*job, grid, warps, nbuf, st);
     return cudaErrorInvalidValue;
 }
+
+/* experimental matcher / coder kernel (qz_deflate_split.cuh): present only in builds with -DQZ_SPLIT_KERNEL */
+#ifdef QZ_SPLIT_KERNEL
+extern "C" int qzb_deflate_split_compiled(void) { return 1; }
+extern "C" size_t qzb_deflate_split_smem_bytes(int hb, int nmatch, int nteams) { return qzs_smem_bytes(hb, nmatch, nteams); }
+extern "C" size_t qzb_deflate_split_tok_words(int grid) { return (size_t)grid * QZS_SLOTS * QZ_GROUP * QZB_TOK_STRIDE(1 << 13); }
+template <int H>
+static cudaError_t launch_deflate_split(const QzbCompressJob &job, int grid, int nmatch, int nteams, cudaStream_t st)
+{
+    const size_t smem = qzs_smem_bytes(H, nmatch, nteams);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_split_kernel<13, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qzb_deflate_split_kernel<13, H><<<grid, (nmatch + nteams * QZS_TEAM) * 32, smem, st>>>(job, nmatch, nteams);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *job, int hb, int grid, int nmatch, int nteams, cudaStream_t st)
+{
+    if (nmatch < 1 || nteams < 1 || nteams > 8 || nmatch + nteams * QZS_TEAM > 32 || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13) return cudaErrorInvalidValue;
+    if (hb == 10) return launch_deflate_split<10>(*job, grid, nmatch, nteams, st);
+    if (hb == 11) return launch_deflate_split<11>(*job, grid, nmatch, nteams, st);
+    return cudaErrorInvalidValue;
+}
+#else
+extern "C" int qzb_deflate_split_compiled(void) { return 0; }
+extern "C" size_t qzb_deflate_split_smem_bytes(int, int, int) { return 0; }
+extern "C" size_t qzb_deflate_split_tok_words(int) { return 0; }
+extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
 
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)
 {

@@ -26,6 +26,10 @@
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
+extern "C" int qzb_deflate_split_compiled(void);
+extern "C" size_t qzb_deflate_split_smem_bytes(int hb, int nmatch, int nteams);
+extern "C" size_t qzb_deflate_split_tok_words(int grid);
+extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *job, int hb, int grid, int nmatch, int nteams, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
@@ -93,7 +97,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->taper = env_int("QZB200_TAPER", 0);
     /* deflate block granularity: 1 = one block per group of 8 pieces (group kernel, chunks that are a whole number of
      * groups, i.e. hw_buff_sz >= 64 KiB with 8 KiB pieces), 0 = one block per piece everywhere */
-    t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);
+    t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);       /* 2: the experimental matcher / coder kernel where it is compiled in, else as 1 */
     t->group_hash_bits = env_int("QZB200_GROUP_HASH_BITS", QZB200_GROUP_HB_DEFAULT);     /* 9: 1.25 KiB per warp (22 piece buffers, about 1 % larger output); 10: 2 KiB; 11, 12 */
     if (t->group_hash_bits < 9 || t->group_hash_bits > 12) t->group_hash_bits = QZB200_GROUP_HB_DEFAULT;
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
@@ -278,7 +282,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, hb = t.hash_bits, gw = 8;
+    int nbuf = t.buffers_per_cta, hb = t.hash_bits, gw = 8, split_match = 0, split_teams = 0;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
@@ -294,6 +298,14 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         if (nbuf <= 0 || nbuf > warps) nbuf = warps;
         while (nbuf > 1 && qzb_deflate_groups_smem_bytes(hb, warps, nbuf) + 3328 > smem_cap) nbuf--;
         group_smem = qzb_deflate_groups_smem_bytes(hb, warps, nbuf);
+        if (t.group == 2 && qzb_deflate_split_compiled() && (hb == 10 || hb == 11)) {
+            /* experimental matcher / coder kernel (A/B builds only): QZB200_SPLIT_MATCHERS matcher warps + QZB200_SPLIT_TEAMS teams of 4 coder warps */
+            split_teams = std::min(8, std::max(1, env_int("QZB200_SPLIT_TEAMS", 3)));
+            split_match = std::max(1, std::min(32 - 4 * split_teams, env_int("QZB200_SPLIT_MATCHERS", 19)));
+            while (split_match > 1 && qzb_deflate_split_smem_bytes(hb, split_match, split_teams) + 4096 > smem_cap) split_match--;
+            group_smem = qzb_deflate_split_smem_bytes(hb, split_match, split_teams);
+            warps = split_match + 4 * split_teams;
+        }
     } else {
         if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
@@ -310,7 +322,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((size_t)grid * warps * (job.ngroups ? 8 / gw : 1) * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((split_match ? qzb_deflate_split_tok_words(grid) : (size_t)grid * warps * (job.ngroups ? 8 / gw : 1) * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
@@ -322,6 +334,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
+    else if (split_match) CK(qzb_launch_deflate_split(&job, hb, grid, split_match, split_teams, s.st));
     else if (job.ngroups) CK(qzb_launch_deflate_groups(&job, hb, grid, warps, nbuf, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));

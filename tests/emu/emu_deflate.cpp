@@ -101,4 +101,21 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     return emu_frame(&job, chunk_cksum_out);
 }
 
+/* experimental matcher / coder kernel (qz_deflate_split.cuh): nmatch matcher warps + nteams teams of four coder warps per CTA */
+extern "C" long emu_deflate_split(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman, int hb,
+                                  int nmatch, int nteams, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out)
+{
+    if (nmatch < 1 || nteams < 1 || nteams > 8 || nmatch + nteams * QZS_TEAM > 32 || grid < 1 || (hb != 10 && hb != 11)) return -1;
+    QzbCompressJob job; EmuCompressBuffers b;
+    emu_job_setup(&job, &b, fmt, src, len, chunk_sz, last, static_huffman, 13, 1, dst, cap);
+    if (!job.ngroups) return -1;
+    b.tok.assign((size_t)grid * QZS_SLOTS * QZ_GROUP * QZB_TOK_STRIDE(1 << 13), 0xEEEEEEEEu);
+    job.tok_scratch = b.tok.data();
+    const size_t smem = qzs_smem_bytes(hb, nmatch, nteams);
+    const unsigned block = (unsigned)(nmatch + nteams * QZS_TEAM) * 32;
+    if (hb == 10) emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 10>(job, nmatch, nteams); });
+    else emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 11>(job, nmatch, nteams); });
+    return emu_frame(&job, chunk_cksum_out);
+}
+
 extern "C" unsigned long long emu_collectives(void) { return emu::collectives(); }

@@ -117,6 +117,7 @@ static inline long long clock64() { return 0; }
 
 /* ---- atomics: fibers never run concurrently ---- */
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
 template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
 template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }

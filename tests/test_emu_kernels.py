@@ -400,3 +400,44 @@ def test_group_streams_decode_with_our_inflate(emu):
     members = [one_member(ln, isize, crc, src_off=off, dst_off=i * 65536) for i, (off, ln, crc, isize, _) in enumerate(walk_gzip(blob, ext=True))]
     out, res = emu.decode(E.FMT_GZIP_EXT, blob, members, len(data))
     assert [r.status for r in res] == [E.ST_OK] * len(members) and out == data
+
+
+# ------------------------------------------------------------------ experimental matcher / coder kernel (qz_deflate_split.cuh)
+# Compiled only into A/B builds of the product (-DQZ_SPLIT_KERNEL, QZB200_GROUP=2); the emulator library always carries it.
+
+@pytest.mark.parametrize("fmt", [E.FMT_4B, E.FMT_GZIP, E.FMT_GZIP_EXT, E.FMT_RAW, E.FMT_ZLIB])
+@pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000),
+                                         ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
+                                         ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
+def test_split_deflate_same_stream_as_group_kernel(emu, port, fmt, name, make, n):
+    data = make(n)
+    blob, cks = emu.deflate_split(data, fmt, nmatch=5, nteams=2, grid=2)
+    ref, ref_cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1, hb=10)
+    assert blob == ref and cks == ref_cks                  # same blocks, whoever matched and coded them
+    assert decode_any(port, blob, fmt, n) == data
+
+
+@pytest.mark.parametrize("chunk", [65536, 131072, 524288])
+@pytest.mark.parametrize("geom", [dict(nmatch=1, nteams=1, grid=1), dict(nmatch=19, nteams=3, grid=1), dict(nmatch=3, nteams=1, grid=4),
+                                  dict(nmatch=12, nteams=5, grid=2), dict(nmatch=7, nteams=2, grid=2, hb=11)])
+def test_split_deflate_geometries_and_chunks(emu, port, chunk, geom):
+    data = sil(chunk + chunk // 2 + 4321)
+    blob, cks = emu.deflate_split(data, E.FMT_GZIP_EXT, chunk=chunk, **geom)
+    assert port.decompress(blob, E.FMT_GZIP_EXT, len(data) + 16) == data
+    assert cks == [zlib.crc32(data[i:i + chunk]) for i in range(0, len(data), chunk)]
+    ref, _ = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, warps=8, nbuf=3, grid=2, group=1, hb=geom.get("hb", 10))
+    assert blob == ref
+
+
+def test_split_deflate_static_not_last_and_short_dest(emu):
+    data = sil(200000)
+    blob, _ = emu.deflate_split(data, E.FMT_RAW, static=1)
+    out, eof, _ = inflate_raw(blob)
+    assert out == data and eof and (blob[0] >> 1) & 3 in (0, 1)
+    blob, _ = emu.deflate_split(data, E.FMT_RAW, last=0)
+    out, eof, used = inflate_raw(blob)
+    assert out == data and not eof and used == len(blob) and blob[-4:] == b"\x00\x00\xff\xff"
+    full, _ = emu.deflate_split(data, E.FMT_GZIP_EXT)
+    two = walk_gzip(full, ext=True)[2][0] - 24
+    part, _ = emu.deflate_split(data, E.FMT_GZIP_EXT, cap=two + 100)
+    assert part == full[:two]
