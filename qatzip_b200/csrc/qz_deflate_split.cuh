@@ -26,7 +26,9 @@
 enum { QZS_FREE = 0, QZS_OPENING = 1, QZS_FILLING = 2, QZS_READY = 3, QZS_CODING = 4 };
 
 struct SplitSlot {
-    uint32_t state, gi, npieces, next, done, bfinal;
+    uint32_t state, gi, npieces, done, bfinal;
+    uint32_t next;                  /* life << 8 | next piece to hand out: a claim is a CAS on the whole word, so a matcher that looked
+                                     * at the slot in an earlier life can never take a piece of the current one by accident */
     uint32_t ntok[QZ_GROUP], nbytes[QZ_GROUP];
 };
 struct SplitTeam {
@@ -99,9 +101,9 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
                         SplitSlot &S = sh.slot[i];
                         const uint32_t st = qzs_ld(&S.state);
                         if (st == QZS_OPENING) opening = true;
-                        if (st == QZS_FILLING && qzs_ld(&S.next) < qzs_ld(&S.npieces)) {
-                            const uint32_t kk = atomicAdd(&S.next, 1u);
-                            if (kk < qzs_ld(&S.npieces)) { s = i; k = kk; }
+                        if (st == QZS_FILLING) {
+                            const uint32_t w = qzs_ld(&S.next);                 /* written last when a slot is opened: the fields below belong to life w >> 8 or later */
+                            if ((w & 0xffu) < qzs_ld(&S.npieces) && atomicCAS(&S.next, w, w + 1) == w) { s = i; k = w & 0xffu; }
                         }
                     }
                     if (s != QZS_NONE) break;
@@ -114,8 +116,15 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
                             if (gi >= job.ngroups) {
                                 sh.no_more = 1; __threadfence_block(); S.state = QZS_FREE;
                             } else {
-                                S.gi = gi; S.npieces = qzs_block_pieces(job, gi, PIECE_LOG2); S.done = 0; S.bfinal = 0; S.next = 1;
+                                /* new life: first close the hand-out word (no piece index is below 0xff), then the fields, then open it
+                                 * with piece 0 taken by this warp -- a claim prepared against the previous life fails its CAS */
+                                const uint32_t life = ((qzs_ld(&S.next) >> 8) + 1) << 8;
+                                S.next = life | 0xffu;
+                                __threadfence_block();
+                                S.gi = gi; S.npieces = qzs_block_pieces(job, gi, PIECE_LOG2); S.done = 0; S.bfinal = 0;
                                 for (int q = 0; q < QZ_GROUP; q++) { S.ntok[q] = 0; S.nbytes[q] = 0; }
+                                __threadfence_block();
+                                S.next = life | 1u;
                                 __threadfence_block();
                                 S.state = QZS_FILLING;
                                 s = i; k = 0;
