@@ -50,10 +50,12 @@ class Emu:
         data = bytes(data)
         nch = max(1, (len(data) + chunk - 1) // chunk)
         cap = cap if cap is not None else len(data) + len(data) // 8 + 512 * nch + 64
-        dst = C.create_string_buffer(max(cap, 1))
+        dst = C.create_string_buffer(max(cap, 1) + 4096)
         ck = (C.c_uint32 * nch)()
         n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck, group)
+        assert n != -2, "a kernel wrote past its scratch buffers"
         assert n >= 0, "geometry not offered by the kernel"
+        assert dst.raw[max(cap, 1):] == b"\0" * 4096, "the framing kernel wrote past the destination"
         return dst.raw[:n], list(ck)
 
     def deflate_split(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, hb=10, nmatch=5, nteams=1, grid=2, cap=None):
@@ -82,10 +84,13 @@ class Emu:
         src = bytes(src)
         arr = (Member * len(members))(*[Member(**m) for m in members])
         res = (MemberResult * len(members))()
-        dst = C.create_string_buffer(out_len + 64)
+        guard = 4096
+        dst = C.create_string_buffer(out_len + guard)
         pad = src + b"\0" * 64           # the engine over-allocates its input buffer the same way
         if fmt == FMT_LZ4:
             self.lib.emu_lz4_decompress(pad, dst, arr, res, len(members), grid)
         else:
             self.lib.emu_inflate(fmt, pad, dst, arr, res, len(members), size_only, grid)
+        if all(m["dst_off"] + m["dst_cap"] <= out_len for m in members):
+            assert dst.raw[out_len:] == b"\0" * guard, "a decoder wrote past the end of its destination"
         return dst.raw[:out_len], list(res)

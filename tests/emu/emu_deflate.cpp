@@ -9,7 +9,16 @@
 struct EmuCompressBuffers {
     std::vector<uint8_t> slots, meta;
     std::vector<uint32_t> tok;
+    size_t slots_used = 0, meta_used = 0;      /* bytes the kernels may touch; the rest is canary */
 };
+static const size_t EMU_GUARD = 4096;
+/* the canaries behind the slot and meta buffers are intact (a kernel that writes past its scratch shows up here) */
+static bool emu_canaries_ok(const EmuCompressBuffers &b)
+{
+    for (size_t i = b.slots_used; i < b.slots.size(); i++) if (b.slots[i] != 0xEE) return false;
+    for (size_t i = b.meta_used; i < b.meta.size(); i++) if (b.meta[i] != 0xEE) return false;
+    return true;
+}
 
 extern "C" EmuCompressBuffers *emu_buffers_new(void) { return new EmuCompressBuffers(); }
 extern "C" void emu_buffers_free(EmuCompressBuffers *b) { delete b; }
@@ -30,7 +39,8 @@ extern "C" void emu_job_setup(QzbCompressJob *job, EmuCompressBuffers *b, int fm
     job->npieces = (job->nchunks - 1) * job->pieces_per_chunk + last_pieces;
     job->fmt = fmt; job->last = last; job->static_huffman = static_huffman;
     job->slot_stride = PIECE + 64;
-    b->slots.assign((size_t)job->npieces * job->slot_stride + 64, 0xEE);
+    b->slots_used = (size_t)job->npieces * job->slot_stride + 64;
+    b->slots.assign(b->slots_used + EMU_GUARD, 0xEE);
     size_t o = 0;
     const size_t o_off = o; o += up16((size_t)(job->nchunks + 1) * 8);
     const size_t o_ck = o; o += up16((size_t)job->nchunks * 4);
@@ -38,7 +48,8 @@ extern "C" void emu_job_setup(QzbCompressJob *job, EmuCompressBuffers *b, int fm
     const size_t o_plen = o; o += up16((size_t)job->npieces * 4);
     const size_t o_pcrc = o; o += up16((size_t)job->npieces * 4);
     const size_t o_ticket = o; o += 16;
-    b->meta.assign(o, 0xEE);
+    b->meta_used = o;
+    b->meta.assign(o + EMU_GUARD, 0xEE);
     uint8_t *m = b->meta.data();
     memset(m + o_ticket, 0, 16);
     job->slots = b->slots.data();
@@ -90,7 +101,8 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
         else if (gw == 8 && hb == 12) body = [&] { qzb_deflate_groups_kernel<13, 12, 8>(job, nbuf); };
         else return -1;
         emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
-        return emu_frame(&job, chunk_cksum_out);
+        const long n = emu_frame(&job, chunk_cksum_out);
+        return emu_canaries_ok(b2) ? n : -2;
     }
     if (piece_log2 == 13 && hb == 11) { smem = sizeof(WarpPriv<11>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 11>(job, nbuf); }; }
     else if (piece_log2 == 13 && hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 12>(job, nbuf); }; }
@@ -98,7 +110,8 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     else if (piece_log2 == 14 && hb == 13) { smem = sizeof(WarpPriv<13>) * warps + sizeof(PieceBuf<14>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<14, 13>(job, nbuf); }; }
     else return -1;
     emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
-    return emu_frame(&job, chunk_cksum_out);
+    const long n = emu_frame(&job, chunk_cksum_out);
+    return emu_canaries_ok(b) ? n : -2;
 }
 
 /* experimental matcher / coder kernel (qz_deflate_split.cuh): nmatch matcher warps + nteams teams of four coder warps per CTA */
@@ -115,7 +128,8 @@ extern "C" long emu_deflate_split(int fmt, const uint8_t *src, uint64_t len, uin
     const unsigned block = (unsigned)(nmatch + nteams * QZS_TEAM) * 32;
     if (hb == 10) emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 10>(job, nmatch, nteams); });
     else emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 11>(job, nmatch, nteams); });
-    return emu_frame(&job, chunk_cksum_out);
+    const long n = emu_frame(&job, chunk_cksum_out);
+    return emu_canaries_ok(b) ? n : -2;
 }
 
 extern "C" unsigned long long emu_collectives(void) { return emu::collectives(); }
