@@ -279,7 +279,7 @@ def main():
             traffic = tj.get("deflate_dram_bytes_per_launch", tj.get("deflate_pieces_dram_bytes_per_launch"))
         # CPU baseline: bounded sample of the same bytes through the reference's software path
         cpu = None
-        if ref_lib and not os.environ.get("QZ_BENCH_NOCPU"):
+        if ref_lib and world == 1 and not os.environ.get("QZ_BENCH_NOCPU"):      # reported at N = 1 only
             sample = min(nbytes, max(256 << 20, ncores * (16 << 20)))
             dtc, outc, thr = cpu_reference_pass(ref_lib, h_in, sample, ncores)
             cpu = {"value": round(sample / dtc / GB, 4), "unit": "GB/s", "cores": thr, "kind": "reference",
