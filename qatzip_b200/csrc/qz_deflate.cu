@@ -1,20 +1,30 @@
-/* qz_deflate.cu -- sm_100a DEFLATE compressor: one warp per piece, everything the warp touches
- * lives in its private slice of shared memory (input piece, hash table, histograms), so HBM
- * sees each input byte once and each output byte once.
+/* qz_deflate.cu -- sm_100a DEFLATE compressor.  The device's unit is the PIECE (8 KiB of a chunk, private window): one
+ * warp matches it out of a shared-memory piece buffer with a private u16 hash table, so HBM sees each input byte once
+ * and each output byte once (tokens live in an L2-resident scratch in between).
  *
- * This kernel is the replacement for the QAT compress request submitted at reference
- * src/qatzip.c:1542 (cpaDcCompressData2, stateless deflate, CPA_DC_FLUSH_FINAL / _FULL) with the
- * session set-up of reference src/qatzip_utils.c:264-341 (dynamic or static Huffman, stored
- * fallback, CRC-32 of the input returned in res.checksum).
+ * These kernels replace the QAT compress request submitted at reference src/qatzip.c:1542 (cpaDcCompressData2, stateless
+ * deflate, CPA_DC_FLUSH_FINAL / _FULL) with the session set-up of reference src/qatzip_utils.c:264-341 (dynamic or
+ * static Huffman, stored fallback, CRC-32 of the input returned in res.checksum), and the stitching doCompressOut does
+ * afterwards (framing kernels at the end of the file).
  *
- * Per piece the warp runs four phases, all warp-synchronous (no CTA barrier):
- *   1 load    global -> shared, 16 B per lane, then CRC-32 over right-aligned per-lane strips
- *   2 match   32 positions per step: 4-byte hash probe of a u16 table, verify + extend,
- *             ballot-driven greedy selection, tokens to an L2-resident scratch, histograms
- *   3 code    sort by frequency (warp bitonic), in-place length assignment, canonical codes,
- *             dynamic header; cheapest of stored / fixed / dynamic is kept
- *   4 emit    32 tokens per step: code lookup, warp scan of bit lengths, OR into a staging
- *             window, full words flushed coalesced to the piece's slot
+ * Phases of a piece, all warp-synchronous:
+ *   1 load    global -> shared, 16 B per lane, then CRC-32 / Adler-32 over right-aligned per-lane strips
+ *   2 match   32 positions per step: 4-byte hash probe, 12-byte verify + extend with all loads in flight, ballot-driven
+ *             greedy selection, raw tokens to the scratch                                          (phase12)
+ *   3 code    token pass (symbols, histograms); sort by frequency in registers, in-place Huffman lengths (merge on one
+ *             lane, depths by pointer doubling, leaf depths across the warp), canonical codes, dynamic header plan;
+ *             cheapest of stored / fixed / dynamic                                 (token_pass, choose_block, open_block)
+ *   4 emit    every lane packs a contiguous run of tokens at a bit offset from a scan of the runs' lengths; run-boundary
+ *             words are zeroed first and joined by atomic OR                          (count_run_bits, emit_run)
+ *
+ * Two kernels string them together:
+ *   qzb_deflate_groups_kernel  (default for hw_buff_sz >= 64 KiB) eight warps = eight pieces = ONE deflate block: phases 1-2
+ *                              and the token pass per warp, the code construction once per group by its leader, emission
+ *                              at bit offsets inside the group's output; warps of a group meet at a named barrier
+ *   qzb_deflate_pieces_kernel  one block (or stored block) per piece, no cross-warp step: smaller chunks, 16 KiB pieces,
+ *                              QZB200_GROUP=0
+ * A CTA's warps share a pool of piece buffers (held only while matching, or by a group leader as code scratch); the
+ * experimental matcher / coder variant lives in qz_deflate_split.cuh.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
