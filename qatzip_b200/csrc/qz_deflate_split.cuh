@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
             T.slot = got;
         }
         group_bar<QZS_TEAM * 32>(bar);
+        QZ_MARK(15);                /* coder: waiting for a block whose pieces are all matched */
         const uint32_t s = T.slot;
         if (s == QZS_EXIT) break;
         SplitSlot &S = sh.slot[s];
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
         }
         QZ_MARK(3);
         group_bar<QZS_TEAM * 32>(bar);
+        QZ_MARK(9);                 /* waiting for the team's slowest token pass */
         /* mixed block: a block per piece (see the group kernel), the pieces take turns on the team's code scratch */
         bool mixed;
         {
@@ -259,8 +261,10 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
                 uint32_t hb = 0, pend = 0;
                 if (btype) open_block(L.cs, L.hist, btype, gfinal, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
                 if (lane == 0) { T.btype = (uint32_t)btype; T.hb = hb; T.pend = pend; }
+                QZ_MARK(11);
             }
             group_bar<QZS_TEAM * 32>(bar);
+            QZ_MARK(10);            /* waiting for the leader */
             if (T.btype == 0) {
 #pragma unroll
                 for (int j = 0; j < QZS_PPW; j++) {
@@ -283,7 +287,9 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
                     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl[j], o); if (lane >= (uint32_t)o) incl[j] += y; }
                     if (lane == 31) T.bits[tw * QZS_PPW + j] = incl[j];
                 }
+                QZ_MARK(12);
                 group_bar<QZS_TEAM * 32>(bar);
+                QZ_MARK(13);
                 uint32_t before[QZS_PPW], total = T.hb;
 #pragma unroll
                 for (int j = 0; j < QZS_PPW; j++) before[j] = T.hb;
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(1024) qzb_deflate_split_kernel(QzbCompressJob 
                 for (int j = 0; j < QZS_PPW; j++) slotw[(before[j] + incl[j] - mybits[j]) >> 5] = 0;
                 if (tw == QZS_TEAM - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
                 group_bar<QZS_TEAM * 32>(bar);
+                QZ_MARK(14);
 #pragma unroll
                 for (int j = 0; j < QZS_PPW; j++) {
                     const uint32_t NT = T.ntok[tw * QZS_PPW + j];

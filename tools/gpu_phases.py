@@ -12,7 +12,7 @@ d_in, d_out = L.qzb200DeviceAlloc(n), L.qzb200DeviceAlloc(cap)
 assert L.qzb200CopyToDevice(d_in, h, n) == 0
 sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536)
 names = ["ticket+buffer wait", "load+crc", "match+select", "token pass", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit",
-         "wait: slowest piece of the group", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "-"]
+         "wait: slowest piece of the group", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "split kernel, coders: wait for a matched block"]
 out = (C.c_ulonglong * 16)()
 for it in range(3):
     L.qzb_phase_cycles_read(out, 1)
