@@ -38,35 +38,23 @@ class Emu:
         L.emu_deflate_compress.restype = C.c_long
         L.emu_deflate_compress.argtypes = [C.c_int, V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            V, C.c_uint64, V, C.c_int]
-        L.emu_deflate_split.restype = C.c_long
-        L.emu_deflate_split.argtypes = [C.c_int, V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_lz4_compress.restype = C.c_long
         L.emu_lz4_compress.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_inflate.argtypes = [C.c_int, V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int, C.c_int]
         L.emu_lz4_decompress.argtypes = [V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int]
 
-    def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None, group=0):
-        """-> (stream bytes, [per-chunk checksum])"""
+    def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None, window=0):
+        """-> (stream bytes, [per-chunk checksum]).  window=1: the window kernel (warps / 8 groups share nbuf units; hb >= 256 is the
+        number of table entries itself, else its log2)"""
         data = bytes(data)
         nch = max(1, (len(data) + chunk - 1) // chunk)
         cap = cap if cap is not None else len(data) + len(data) // 8 + 512 * nch + 64
         dst = C.create_string_buffer(max(cap, 1) + 4096)
         ck = (C.c_uint32 * nch)()
-        n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck, group)
+        n = self.lib.emu_deflate_compress(fmt, data, len(data), chunk, last, static, piece_log2, hb, warps, nbuf, grid, dst, cap, ck, window)
         assert n != -2, "a kernel wrote past its scratch buffers"
         assert n >= 0, "geometry not offered by the kernel"
         assert dst.raw[max(cap, 1):] == b"\0" * 4096, "the framing kernel wrote past the destination"
-        return dst.raw[:n], list(ck)
-
-    def deflate_split(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, hb=10, nmatch=5, nteams=1, grid=2, cap=None):
-        """experimental matcher / coder kernel -> (stream bytes, [per-chunk checksum])"""
-        data = bytes(data)
-        nch = max(1, (len(data) + chunk - 1) // chunk)
-        cap = cap if cap is not None else len(data) + len(data) // 8 + 512 * nch + 64
-        dst = C.create_string_buffer(max(cap, 1))
-        ck = (C.c_uint32 * nch)()
-        n = self.lib.emu_deflate_split(fmt, data, len(data), chunk, last, static, hb, nmatch, nteams, grid, dst, cap, ck)
-        assert n >= 0, "geometry not offered by the kernel"
         return dst.raw[:n], list(ck)
 
     def lz4(self, data, chunk=65536, piece_log2=13, warps=4, grid=2):

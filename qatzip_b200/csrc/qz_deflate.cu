@@ -1,48 +1,45 @@
-/* qz_deflate.cu -- sm_100a DEFLATE compressor.  The device's unit is the PIECE (8 KiB of a chunk, private window): one
- * warp matches it out of a shared-memory piece buffer with a private u16 hash table, so HBM sees each input byte once
- * and each output byte once (tokens live in an L2-resident scratch in between).
+/* qz_deflate.cu -- sm_100a DEFLATE compressor.
  *
  * These kernels replace the QAT compress request submitted at reference src/qatzip.c:1542 (cpaDcCompressData2, stateless
- * deflate, CPA_DC_FLUSH_FINAL / _FULL) with the session set-up of reference src/qatzip_utils.c:264-341 (dynamic or
- * static Huffman, stored fallback, CRC-32 of the input returned in res.checksum), and the stitching doCompressOut does
- * afterwards (framing kernels at the end of the file).
+ * deflate, CPA_DC_FLUSH_FINAL / _FULL) with the session set-up of reference src/qatzip_utils.c:264-341 (32 KiB history,
+ * dynamic or static Huffman, stored fallback, CRC-32 of the input returned in res.checksum), and the stitching
+ * doCompressOut does afterwards (framing kernels at the end of the file).
  *
- * Phases of a piece, all warp-synchronous:
- *   1 load    global -> shared, 16 B per lane, then CRC-32 / Adler-32 over right-aligned per-lane strips
- *   2 match   32 positions per step: 4-byte hash probe, 12-byte verify + extend with all loads in flight, ballot-driven
- *             greedy selection, raw tokens to the scratch                                          (phase12)
- *   3 code    token pass (symbols, histograms); sort by frequency in registers, in-place Huffman lengths (merge on one
- *             lane, depths by pointer doubling, leaf depths across the warp), canonical codes, dynamic header plan;
- *             cheapest of stored / fixed / dynamic                                 (token_pass, choose_block, open_block)
- *   4 emit    every lane packs a contiguous run of tokens at a bit offset from a scan of the runs' lengths; run-boundary
+ * The device's units: a PIECE is 8 KiB of a chunk, matched by one warp; a WINDOW is 64 KiB of a chunk (eight pieces) that
+ * sits whole in shared memory while its pieces are matched, so every position sees the whole window in front of it
+ * (qz_match.cuh), and that becomes one deflate block.  HBM sees each input byte once and each output byte once; tokens
+ * live as 16-bit slots in an L2-resident scratch in between.
+ *
+ * Stages of a piece, all warp-synchronous:
+ *   1 load    global -> shared, 16 B per lane, then CRC-32 / Adler-32 over right-aligned per-lane strips   (load_and_checksum)
+ *   2 match   qz_match.cuh: 32 positions per step, single-probe 4-byte hash + in-tile candidates, 12-byte verify in the
+ *             lane, greedy parse by pointer doubling, slots to the scratch
+ *   3 code    histogram of the slots; sort by frequency in registers, in-place Huffman lengths (merge on one lane,
+ *             depths by pointer doubling, leaf depths across the warp), canonical codes, dynamic header plan; cheapest of
+ *             stored / fixed / dynamic                                       (slot_hist, choose_block, open_block)
+ *   4 emit    every lane packs a contiguous run of slots at a bit offset from a scan of the runs' lengths; run-boundary
  *             words are zeroed first and joined by atomic OR                          (count_run_bits, emit_run)
  *
  * Two kernels string them together:
- *   qzb_deflate_groups_kernel  (default for hw_buff_sz >= 64 KiB) eight warps = eight pieces = ONE deflate block: phases 1-2
- *                              and the token pass per warp, the code construction once per group by its leader, emission
- *                              at bit offsets inside the group's output; warps of a group meet at a named barrier
- *   qzb_deflate_pieces_kernel  one block (or stored block) per piece, no cross-warp step: smaller chunks, 16 KiB pieces,
- *                              QZB200_GROUP=0
- * A CTA's warps share a pool of piece buffers (held only while matching, or by a group leader as code scratch); the
- * experimental matcher / coder variant lives in qz_deflate_split.cuh.
+ *   qzb_deflate_window_kernel  (hw_buff_sz >= 64 KiB) eight warps = one window = ONE deflate block: stages 1-2 and the
+ *                              histogram per warp, the code construction once per window by the group's leader,
+ *                              emission at bit offsets inside the window's output
+ *   qzb_deflate_pieces_kernel  smaller chunks: one block per piece with a private window, no cross-warp step
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "qz_kernels.cuh"
 #include "qz_warp.cuh"
+#include "qz_match.cuh"
 #include "qz_huffman.h"
 #include "qz_crc32.h"
 #include "qz_adler32.h"
 
 #define FULL 0xffffffffu
-#define QZ_NONE16 0xffffu
-#define QZ_LANE_CAP 12          /* in-lane match extension cap; longer matches are finished by the warp */
-#define QZ_MAX_MATCH 258
 #define QZ_STAGE_WORDS 64
 /* most warps a CTA may have.  Per-piece kernel: shared memory admits 20-24, and the bound lets the compiler use up to
- * 80 registers per thread instead of the 64 a 1024-thread bound would impose.  Group kernel: 2 KiB per warp with the
- * 2^10-entry table, so four groups of eight warps fit beside 17 piece buffers, and that measured faster than 24 warps
- * with 80 registers. */
+ * 80 registers per thread instead of the 64 a 1024-thread bound would impose.  Window kernel: four groups of eight warps
+ * share two units. */
 #ifndef QZ_PIECES_MAX_WARPS
 #define QZ_PIECES_MAX_WARPS 24
 #endif
@@ -254,10 +251,9 @@ __device__ __noinline__ void warp_assign_codes(const uint8_t *len, int n, uint32
     }
 }
 
-/* Everything phases 3-4 keep in shared memory lives where the hash table was (dead after phase 2):
- * sort keys -> frequencies -> header-plan counters -> bit staging window, symbol ids, code lengths, the
- * dynamic header, and the histograms that later become the code tables.  4000 B against the 4096 B
- * of a 2^11-entry table, so a warp's private slice is exactly its hash table. */
+/* Everything the code construction and the emission keep in shared memory for one block: sort keys -> frequencies ->
+ * header-plan counters -> bit staging window -> (once the block header is out) the 256 per-length code entries; symbol
+ * ids, code lengths, the dynamic header; and the histograms that become the code tables.  4000 B. */
 struct CodeScratch {
     uint32_t keys[288];                 /* 286 sort keys at most; see above for its later lives */
     uint16_t ids[QZ_NUM_LL + 2];
@@ -266,44 +262,85 @@ struct CodeScratch {
     QzDynHeaderCore hdr;
 };
 #define QZ_HIST_WORDS (QZ_NUM_LL + 2 + QZ_NUM_D + 2)   /* [0,286) lit/len, [288,318) dist; later the code tables */
+#define QZ_DOFF 288
+struct BlockCoder { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; };
+/* code entry of length slot l (len - 3), relative to the code tables in BlockCoder::hist: it lives in cs.keys */
+#define QZ_LENVAL_OFF (-(int)(sizeof(CodeScratch) / 4))
 
-/* Shared-memory plan.  The piece buffer (8 KiB) is needed only by phases 1-2; phases 3-4 work
- * from the token scratch and the warp's private tables.  So a CTA owns NB piece buffers and
- * NW > NB warps: a warp draws a ticket, takes any free buffer, runs phases 1-2, hands the buffer
- * back and finishes phases 3-4 without it. */
+/* Per-piece kernel: a CTA owns NB piece buffers and NW > NB warps.  A warp draws a ticket, takes any free buffer, loads and
+ * matches its piece (private window: the warp's slice is the hash table), hands the buffer back and codes the piece from its
+ * slots in the L2 scratch, the slice now being the block coder. */
 template <int HB>
 struct WarpPriv {
     union {
         uint16_t table[1 << HB];
-        struct { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; } b;
+        BlockCoder b;
     } u;
 };
 template <int PIECE_LOG2>
 struct PieceBuf {
-    uint8_t bytes[(1 << PIECE_LOG2) + 32];  /* +32: zero pad so unaligned reads past n are defined */
+    uint8_t bytes[QZM_FRONT_PAD + (1 << PIECE_LOG2) + QZM_TAIL_PAD];     /* data at bytes + QZM_FRONT_PAD */
 };
-#define QZ_DOFF 288
 
-/* what phases 3-4 need to know about the piece phases 1-2 just finished */
+/* what the coding stage needs to know about a matched piece */
 struct PieceState {
-    uint32_t g, n, ntok, extra_total;
+    uint32_t g, n, nslots;
     bool bfinal;
     const uint8_t *src;
 };
 
-#ifdef QZ_EMU_STATS
-unsigned long long qz_stat[8];      /* tiles, skipped tiles, selection iterations, long matches, long-match steps, tokens, matches */
-#define QZ_STAT(i, v) do { if (lane == 0) qz_stat[i] += (v); } while (0)
-#else
-#define QZ_STAT(i, v) do { } while (0)
-#endif
-template <int PIECE_LOG2, int HB>
-__device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piece, uint16_t *table, uint32_t *toks,
-                                        const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t g, uint32_t lane, PieceState &ps QZ_TARG)
+/* ---- stage 1: global -> shared, 16 B per lane, and the checksum of the piece (CRC-32, or packed Adler sums for zlib
+ * streams) over right-aligned per-lane strips joined up a tree.  `pad`: zero the bytes behind the data. */
+template <int PIECE>
+__device__ __forceinline__ uint32_t load_and_checksum(uint8_t *piece, const uint8_t *src, uint32_t n, bool pad, int fmt,
+                                                      const uint32_t *s_crc_tab, const uint32_t *s_xstrip, uint32_t lane)
+{
+    constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
+    uint4 *d4 = reinterpret_cast<uint4 *>(piece);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        const uint32_t nv = n >> 4;
+        const uint64_t pstream = l2_policy_stream();
+        for (uint32_t i = lane; i < nv; i += 32) d4[i] = stream_ld16(s4 + i, pstream);
+        for (uint32_t i = (nv << 4) + lane; i < n; i += 32) piece[i] = src[i];
+    } else {
+        for (uint32_t i = lane; i < n; i += 32) piece[i] = src[i];
+    }
+    if (pad) { piece[n + lane] = 0; if (lane < QZM_TAIL_PAD - 32) piece[n + 32 + lane] = 0; }
+    __syncwarp();
+    /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
+    int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
+    if (lo < 0) lo = 0;
+    uint32_t c;
+    if (fmt == QZB_FMT_ZLIB) {
+        /* Adler-32 sums of the strip (STRIP < NMAX: no reduction inside), joined up the same tree */
+        uint32_t s1 = 0, s2 = 0;
+        for (int i = lo; i < hi; i++) { s1 += piece[i]; s2 += s1; }
+        s2 %= QZ_ADLER_P;
+#pragma unroll 1
+        for (int lv = 0; lv < 5; lv++) {
+            const uint32_t o1 = __shfl_down_sync(FULL, s1, 1u << lv), o2 = __shfl_down_sync(FULL, s2, 1u << lv);
+            if ((lane & ((2u << lv) - 1)) == 0) qz_adler_join(&s1, &s2, o1, o2, (uint64_t)STRIP << lv);
+        }
+        c = qz_adler_pack(s1, s2);
+    } else {
+        c = 0xffffffffu;
+        for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ piece[i]) & 0xff] ^ (c >> 8);
+        c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
+#pragma unroll
+        for (int lv = 0; lv < 5; lv++) {
+            uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
+            if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
+        }
+    }
+    return c;           /* valid in lane 0 */
+}
+
+/* geometry of piece g of the job */
+template <int PIECE_LOG2>
+__device__ __forceinline__ void piece_geometry(const QzbCompressJob &job, uint32_t g, PieceState &ps)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    constexpr uint32_t STRIP = PIECE / 32 + 4;   /* bytes per lane; /4 is odd -> conflict-free banks */
-    /* ---- which bytes ---- */
     const uint32_t chunk = g / job.pieces_per_chunk, k = g - chunk * job.pieces_per_chunk;
     const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
     const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
@@ -311,136 +348,11 @@ __device__ __forceinline__ void phase12(const QzbCompressJob &job, uint8_t *piec
     const uint32_t p_off = k << PIECE_LOG2;
     const uint32_t n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u;
     const bool last_piece = (p_off + n == chunk_len);
-    ps.g = g; ps.n = n;
+    ps.g = g; ps.n = n; ps.nslots = 0;
     ps.bfinal = last_piece && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
-    const uint8_t *src = job.src + chunk_off + p_off;
-    ps.src = src;
-
-    /* ---- phase 1: load + CRC ---- */
-    {
-        uint4 *d4 = reinterpret_cast<uint4 *>(piece);
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            uint32_t nv = n >> 4;
-            const uint64_t pstream = l2_policy_stream();
-            for (uint32_t i = lane; i < nv; i += 32) d4[i] = stream_ld16(s4 + i, pstream);
-            for (uint32_t i = (nv << 4) + lane; i < n; i += 32) piece[i] = src[i];
-        } else {
-            for (uint32_t i = lane; i < n; i += 32) piece[i] = src[i];
-        }
-        piece[n + lane] = 0;          /* zero pad */
-        for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
-        __syncwarp();
-        /* right-aligned strips: lane i owns [n-(32-i)*STRIP, n-(31-i)*STRIP) clipped at 0 */
-        int hi = (int)n - (int)((31 - lane) * STRIP), lo = hi - (int)STRIP;
-        if (lo < 0) lo = 0;
-        uint32_t c;
-        if (job.fmt == QZB_FMT_ZLIB) {
-            /* Adler-32 sums of the strip (STRIP < NMAX: no reduction inside), joined up the same tree */
-            uint32_t s1 = 0, s2 = 0;
-            for (int i = lo; i < hi; i++) { s1 += piece[i]; s2 += s1; }
-            s2 %= QZ_ADLER_P;
-#pragma unroll 1
-            for (int lv = 0; lv < 5; lv++) {
-                const uint32_t o1 = __shfl_down_sync(FULL, s1, 1u << lv), o2 = __shfl_down_sync(FULL, s2, 1u << lv);
-                if ((lane & ((2u << lv) - 1)) == 0) qz_adler_join(&s1, &s2, o1, o2, (uint64_t)STRIP << lv);
-            }
-            c = qz_adler_pack(s1, s2);
-        } else {
-            c = 0xffffffffu;
-            for (int i = lo; i < hi; i++) c = s_crc_tab[(c ^ piece[i]) & 0xff] ^ (c >> 8);
-            c = (hi > lo) ? ~c : 0u;           /* empty strip -> CRC of nothing */
-#pragma unroll
-            for (int lv = 0; lv < 5; lv++) {
-                uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
-                if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xstrip[lv]) ^ other;
-            }
-        }
-        if (lane == 0) job.piece_crc[g] = c;
-    }
-    QZ_MARK(1);
-
-    /* ---- phase 2: match + select + tokens ---- */
-    uint32_t ntok = 0;
-    const uint64_t pkeep = l2_policy_keep();
-    {
-        uint32_t entry = 0;                 /* first position of the tile not covered by a previous match */
-        const uint32_t sh = (lane & 3) * 8;  /* base is a multiple of 32: the byte phase of p is the lane's */
-        const uint32_t *piece_w = reinterpret_cast<const uint32_t *>(piece);
-        for (uint32_t base = 0; base < n; base += 32) {
-            QZ_STAT(0, 1);
-            if (entry >= 32) { entry -= 32; QZ_STAT(1, 1); continue; }      /* tile lies inside a running match: nothing to code, not indexed */
-            const uint32_t p = base + lane;
-            /* 12 bytes at p, straight-line: the three words every lane needs for verify + in-lane extension */
-            const uint32_t *pw = piece_w + (min(p, n) >> 2);
-            const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2], w3 = pw[3];
-            const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
-            const bool can = p + 4 <= n;
-            const uint32_t h = (v * 2654435761u) >> (32 - HB);
-            uint32_t cand = can ? table[h] : QZ_NONE16;
-            __syncwarp();
-            if (can) table[h] = (uint16_t)p;
-            __syncwarp();
-            /* candidate bytes are fetched unconditionally (slot 0 when there is none): no divergent
-             * verify/extend branches, all loads in flight together */
-            const bool has = cand != QZ_NONE16;
-            const uint32_t c = has ? cand : 0u, csh = (c & 3) * 8;
-            const uint32_t *cw = piece_w + (c >> 2);
-            const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
-            const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
-            uint32_t L = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : x2 ? 8 + ((__ffs(x2) - 1) >> 3) : (uint32_t)QZ_LANE_CAP;
-            L = min(L, min((uint32_t)QZ_MAX_MATCH, n - min(p, n)));
-            if (!has || x0) L = 0;
-            const uint32_t valid = __ballot_sync(FULL, p < n);
-            const uint32_t M = __ballot_sync(FULL, L >= 4);
-            uint32_t matchmask = 0, cur = entry;
-            for (;;) {
-                const uint32_t rest = M & (FULL << cur);
-                if (!rest) { cur = 32; break; }
-                const uint32_t m = __ffs(rest) - 1;
-                QZ_STAT(2, 1);
-                matchmask |= 1u << m;
-                uint32_t Lm = __shfl_sync(FULL, L, m);
-                if (Lm >= QZ_LANE_CAP) {                      /* warp finishes the long match */
-                    const uint32_t pm = base + m, cm = __shfl_sync(FULL, cand, m);
-                    const uint32_t mx = min((uint32_t)QZ_MAX_MATCH, n - pm);
-                    Lm = QZ_LANE_CAP;
-                    QZ_STAT(3, 1);
-                    while (Lm < mx) {
-                        QZ_STAT(4, 1);
-                        uint32_t kk = Lm + lane;
-                        bool eq = kk < mx && piece[pm + kk] == piece[cm + kk];
-                        uint32_t bal = __ballot_sync(FULL, eq);
-                        if (bal == FULL) { Lm += 32; continue; }
-                        Lm += __ffs(~bal) - 1; break;
-                    }
-                    Lm = min(Lm, mx);
-                    if (lane == m) L = Lm;
-                }
-                cur = m + Lm;
-                if (cur >= 32) break;
-            }
-            /* positions covered by the match running in from the previous tile or by a selected match
-             * of this one carry no token: every selected lane marks (lane, lane + L), one warp OR joins them */
-            const bool sel = (matchmask >> lane) & 1;
-            const uint32_t mycov = sel ? (((FULL << lane) << 1) & ~(lane + L >= 32 ? 0u : FULL << (lane + L))) : 0u;
-            const uint32_t tokmask = ~(__reduce_or_sync(FULL, mycov) | ~(FULL << entry)) & valid;
-            entry = cur - 32;
-            if ((tokmask >> lane) & 1) {
-                /* raw token: literal byte, or match flag | (len - 3) << 16 | (dist - 1); symbols and
-                 * histograms are derived in phase 3, off the piece buffer's critical path */
-                const uint32_t t = sel ? (0x80000000u | ((L - 3) << 16) | (p - cand - 1)) : (v & 0xff);
-                tok_st(toks + ntok + __popc(tokmask & lanemask_lt()), t, pkeep);
-            }
-            ntok += __popc(tokmask);
-            QZ_STAT(5, __popc(tokmask)); QZ_STAT(6, __popc(matchmask));
-        }
-    }
-    __syncwarp();
-    QZ_MARK(2);
-    ps.ntok = ntok;
-    ps.extra_total = 0;
+    ps.src = job.src + chunk_off + p_off;
 }
+
 
 /* ---- bit emission: 32 variable-length fields per call --------------------------------------
  * Each lane contributes `nb` bits (<= 48).  A warp scan gives every field its bit offset, the
@@ -551,38 +463,33 @@ __device__ __noinline__ void warp_plan_header(CodeScratch &cs, uint32_t *cf /* 1
     __syncwarp();
 }
 
-/* ---- phases 3-4 as building blocks (the per-piece kernel strings them together for one piece; the group
- * kernel runs the token pass and the emission per piece and the code construction once per group) ---- */
-
-/* phase 3a: token pass -- symbols, histograms, and tokens rewritten in symbol form:
- *      match flag | len symbol (5) << 26 | len extra (5) << 21 | dist symbol (5) << 16 | dist extra (13)
- * Returns the piece's total of extra bits. */
-__device__ __forceinline__ uint32_t token_pass(uint32_t *hist, uint32_t *toks, uint32_t ntok, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep, bool zero = true)
+/* ---- stage 3a: histograms of a run of slots (every slot is one code: literal / end of block, length, or distance) ----
+ * Returns the lane's share of the extra bits. */
+__device__ __forceinline__ uint32_t slot_hist(uint32_t *hist, const uint16_t *slots, uint32_t nslots, const uint16_t *s_lentab, uint32_t lane, uint64_t pkeep)
 {
-    if (zero) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0; }
-    __syncwarp();
-    uint32_t extra_acc = 0;
-    uint32_t tnext = lane < ntok ? tok_ld(toks + lane, pkeep) : 0u;          /* one group ahead: hides the L2 round trip */
-    for (uint32_t t0 = 0; t0 < ntok; t0 += 32) {
-        const uint32_t t = tnext;
-        if (t0 + 32 + lane < ntok) tnext = tok_ld(toks + t0 + 32 + lane, pkeep);
-        if (t0 + lane < ntok) {
-            if (t & 0x80000000u) {
-                const uint32_t le = s_lentab[(t >> 16) & 0xff];
-                const uint32_t ls = le & 31, leb = (le >> 5) & 7, lev = ((t >> 16) & 0xff) - (le >> 8);
-                uint32_t ds, de, dv;
-                qz_dist_code((t & 0xffff) + 1, &ds, &de, &dv);
-                atomicAdd(&hist[257 + ls], 1u);
-                atomicAdd(&hist[QZ_DOFF + ds], 1u);
-                extra_acc += leb + de;
-                tok_st(toks + t0 + lane, 0x80000000u | (ls << 26) | (lev << 21) | (ds << 16) | dv, pkeep);
-            } else atomicAdd(&hist[t], 1u);
+    uint32_t extra = 0;
+    for (uint32_t i0 = lane * 8; i0 < nslots; i0 += 256) {
+        const uint4 q = tok_ld4(reinterpret_cast<const uint32_t *>(slots + i0), pkeep);
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (i0 + k < nslots) {
+                const uint32_t s = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                if (s & QZ_SLOT_DIST) {
+                    uint32_t ds, de, dv;
+                    qz_dist_code((s & 0x7fffu) + 1, &ds, &de, &dv);
+                    atomicAdd(&hist[QZ_DOFF + ds], 1u); extra += de;
+                } else if (s & QZ_SLOT_LEN) {
+                    const uint32_t le = s_lentab[s & 0xff];
+                    atomicAdd(&hist[257 + (le & 31)], 1u); extra += (le >> 5) & 7;
+                } else atomicAdd(&hist[s], 1u);
+            }
         }
     }
-    return extra_acc;
+    return extra;
 }
 
-/* phase 3b: code construction from the histograms in hist -> code lengths in cs.ll_len / cs.d_len, the planned
+/* stage 3b: code construction from the histograms in hist -> code lengths in cs.ll_len / cs.d_len, the planned
  * dynamic header in cs.hdr, and the cheapest block type for `storedb` bits of stored cost: 0 stored, 1 fixed, 2 dynamic */
 __device__ __forceinline__ int choose_block(CodeScratch &cs, uint32_t *hist, uint32_t extra_total, uint32_t storedb, int static_huffman, uint32_t lane QZ_TARG)
 {
@@ -635,9 +542,9 @@ __device__ __forceinline__ int choose_block(CodeScratch &cs, uint32_t *hist, uin
 }
 
 /* phase 3c: open a fixed (btype 1) or dynamic (2) block at the start of slotw: code tables go where the histograms
- * were (code | len << 16 | extra-bit count << 24), the block header is written; *hb = bits written so far, *pend = the
+ * were, the block header is written; *hb = bits written so far, *pend = the
  * partial word at that position (the first token run continues it) */
-__device__ __forceinline__ void open_block(CodeScratch &cs, uint32_t *hist, int btype, bool bfinal, uint32_t *slotw, uint32_t lane, uint32_t *hb, uint32_t *pend_out QZ_TARG)
+__device__ __forceinline__ void open_block(CodeScratch &cs, uint32_t *hist, int btype, bool bfinal, uint32_t *slotw, const uint16_t *s_lentab, uint32_t lane, uint32_t *hb, uint32_t *pend_out QZ_TARG)
 {
     QzBitWriter bw; bw.acc = 0;
     EmitState es; es.bitpos = 0; es.flushed = 0;
@@ -681,40 +588,63 @@ __device__ __forceinline__ void open_block(CodeScratch &cs, uint32_t *hist, int 
     }
     __syncwarp();
     *pend_out = st[0]; *hb = es.bitpos;
-    /* code table entries gain their extra-bit counts: code | len << 16 | extra << 24 */
-    if (lane < 29) hist[257 + lane] |= ((lane < 8 || lane == 28) ? 0u : (lane - 4) >> 2) << 24;
-    if (lane < QZ_NUM_D) hist[QZ_DOFF + lane] |= (lane < 4 ? 0u : (lane >> 1) - 1) << 24;
-    if (lane >= QZ_NUM_D) hist[QZ_DOFF + lane] = 0;            /* entry 31: "no distance part" for literals */
+    /* The code tables take their final form, one entry per slot kind, value | bit count << 24:
+     *   literal / end of block  hist[s]                 code
+     *   length slot l           hist[QZ_LENVAL_OFF + l] length code with its extra bits appended (in cs.keys: the staging window is done)
+     *   distance symbol         hist[QZ_DOFF + ds]      code | code length << 16 | (code length + extra-bit count) << 24 */
+    __syncwarp();           /* every lane has read the pending word out of the staging window */
+    {
+        uint32_t *lenval = hist + QZ_LENVAL_OFF;
+        for (uint32_t l = lane; l < 256; l += 32) {
+            const uint32_t le = s_lentab[l], c = hist[257 + (le & 31)], clen = (c >> 16) & 0xff;
+            lenval[l] = (c & 0xffffu) | ((l - (le >> 8)) << clen) | ((clen + ((le >> 5) & 7)) << 24);
+        }
+        __syncwarp();
+        for (uint32_t s2 = lane; s2 < 257; s2 += 32) { const uint32_t c = hist[s2]; hist[s2] = (c & 0xffffu) | (((c >> 16) & 0xff) << 24); }
+        if (lane < QZ_NUM_D) { const uint32_t c = hist[QZ_DOFF + lane], clen = (c >> 16) & 0xff; hist[QZ_DOFF + lane] = (c & 0xffffu) | (clen << 16) | ((clen + (lane < 4 ? 0u : (lane >> 1) - 1)) << 24); }
+    }
     __syncwarp();
 }
 
-/* phase 4, pass 1: bits the tokens [beg, end) take under the code tables `tab` */
-__device__ __forceinline__ uint32_t count_run_bits(const uint32_t *tab, const uint32_t *toks, uint32_t beg, uint32_t end, uint64_t pkeep)
+/* ---- stage 4: emission.  A lane codes a contiguous run of slots ---- */
+/* slot -> (bits, bit count) under the code tables `tab` */
+__device__ __forceinline__ void slot_code(const uint32_t *tab, uint32_t s, uint32_t &val, uint32_t &nb)
+{
+    const bool isD = (s & QZ_SLOT_DIST) != 0;
+    const uint32_t x = s & 0x7fffu;                 /* distance - 1 */
+    const uint32_t lg = 31 - __clz((int)(x | 1u));
+    const uint32_t de = x < 4 ? 0u : lg - 1, ds = x < 4 ? x : 2 * lg + ((x >> de) & 1), dv = x & ((1u << de) - 1);
+    const int idx = isD ? QZ_DOFF + (int)ds : (s & QZ_SLOT_LEN) ? QZ_LENVAL_OFF + (int)(s & 0xff) : (int)s;
+    const uint32_t e = tab[idx];
+    nb = e >> 24;
+    val = isD ? (e & 0xffffu) | (dv << ((e >> 16) & 0xff)) : (e & 0xffffffu);
+}
+
+/* pass 1: bits the slots [beg, end) take (beg a multiple of 8: the slots are fetched 16 bytes at a time) */
+__device__ __forceinline__ uint32_t count_run_bits(const uint32_t *tab, const uint16_t *slots, uint32_t beg, uint32_t end, uint64_t pkeep)
 {
     uint32_t mybits = 0;
-    uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);   /* one group ahead: hides the L2 round trip */
-    for (uint32_t j = beg; j < end; j += 4) {
-        const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
-        if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+    uint4 qn = beg < end ? tok_ld4(reinterpret_cast<const uint32_t *>(slots + beg), pkeep) : make_uint4(0, 0, 0, 0);   /* one group ahead: hides the L2 round trip */
+    for (uint32_t j = beg; j < end; j += 8) {
+        const uint32_t w[4] = { qn.x, qn.y, qn.z, qn.w };
+        if (j + 8 < end) qn = tok_ld4(reinterpret_cast<const uint32_t *>(slots + j + 8), pkeep);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             if (j + k < end) {
-                const uint32_t t = tt[k];
-                const bool isM = (t >> 31) != 0;
-                const uint32_t c1 = tab[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
-                const uint32_t c2 = tab[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
-                mybits += ((c1 >> 16) & 0xff) + (c1 >> 24) + ((c2 >> 16) & 0xff) + (c2 >> 24);
+                uint32_t val, nb;
+                slot_code(tab, (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu, val, nb);
+                mybits += nb;
             }
         }
     }
     return mybits;
 }
 
-/* phase 4, pass 2: pack the tokens [beg, end) at bit `start` of slotw through a private 64-bit accumulator.  `acc0` is
- * what already sits in the first word below the start bit and `owns_first` says this lane writes that word whole (it
- * continues the block header); every other lane joins its first word by atomic OR when it starts inside one.  With
- * `trailer` the lane appends the byte-aligning empty stored block (nz zero bits, 00 00 ff ff) after its last token. */
-__device__ __forceinline__ void emit_run(const uint32_t *tab, const uint32_t *toks, uint32_t beg, uint32_t end, uint32_t start, uint32_t acc0,
+/* pass 2: pack the slots [beg, end) at bit `start` of slotw through a private 64-bit accumulator.  `acc0` is what already
+ * sits in the first word below the start bit and `owns_first` says this lane writes that word whole (it continues the block
+ * header); every other lane joins its first word by atomic OR when it starts inside one.  With `trailer` the lane appends the
+ * byte-aligning empty stored block (nz zero bits, 00 00 ff ff) after its last slot. */
+__device__ __forceinline__ void emit_run(const uint32_t *tab, const uint16_t *slots, uint32_t beg, uint32_t end, uint32_t start, uint32_t acc0,
                                          bool owns_first, bool trailer, uint32_t nz, uint32_t *slotw, uint64_t pkeep)
 {
     uint64_t acc = owns_first ? (uint64_t)acc0 : 0ull;
@@ -722,27 +652,21 @@ __device__ __forceinline__ void emit_run(const uint32_t *tab, const uint32_t *to
     bool partial = !owns_first && nacc != 0;
 #define QZ_EMIT_FLUSH() do { if (nacc >= 32) { if (partial) { atomicOr(slotw + wpos, (uint32_t)acc); partial = false; } else slot_st(slotw + wpos, (uint32_t)acc); \
                                                acc >>= 32; nacc -= 32; wpos++; } } while (0)
-    uint4 qn = beg < end ? tok_ld4(toks + beg, pkeep) : make_uint4(0, 0, 0, 0);
-    for (uint32_t j = beg; j < end; j += 4) {
-        const uint32_t tt[4] = { qn.x, qn.y, qn.z, qn.w };
-        if (j + 4 < end) qn = tok_ld4(toks + j + 4, pkeep);
+    uint4 qn = beg < end ? tok_ld4(reinterpret_cast<const uint32_t *>(slots + beg), pkeep) : make_uint4(0, 0, 0, 0);
+    for (uint32_t j = beg; j < end; j += 8) {
+        const uint32_t w[4] = { qn.x, qn.y, qn.z, qn.w };
+        if (j + 8 < end) qn = tok_ld4(reinterpret_cast<const uint32_t *>(slots + j + 8), pkeep);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             if (j + k < end) {
-                const uint32_t t = tt[k];
-                const bool isM = (t >> 31) != 0;
-                const uint32_t c1 = tab[isM ? 257 + ((t >> 26) & 31) : (t & 511)];
-                const uint32_t c2 = tab[QZ_DOFF + (isM ? (t >> 16) & 31 : 31u)];
-                const uint32_t l1 = (c1 >> 16) & 0xff, l2 = (c2 >> 16) & 0xff;
-                const uint32_t lv = isM ? (t >> 21) & 31 : 0u, dv = isM ? t & 0x1fff : 0u;
-                acc |= (uint64_t)((c1 & 0xffff) | (lv << l1)) << nacc; nacc += l1 + (c1 >> 24);
-                QZ_EMIT_FLUSH();
-                acc |= (uint64_t)((c2 & 0xffff) | (dv << l2)) << nacc; nacc += l2 + (c2 >> 24);
+                uint32_t val, nb;
+                slot_code(tab, (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu, val, nb);
+                acc |= (uint64_t)val << nacc; nacc += nb;
                 QZ_EMIT_FLUSH();
             }
         }
     }
-    if (trailer) {          /* owner of the end-of-block token: empty stored block */
+    if (trailer) {          /* owner of the end-of-block slot: empty stored block */
         nacc += nz; QZ_EMIT_FLUSH();
         nacc += 16; QZ_EMIT_FLUSH();
         acc |= (uint64_t)0xffffu << nacc; nacc += 16; QZ_EMIT_FLUSH();
@@ -750,9 +674,11 @@ __device__ __forceinline__ void emit_run(const uint32_t *tab, const uint32_t *to
     if ((uint32_t)acc) atomicOr(slotw + wpos, (uint32_t)acc);
 #undef QZ_EMIT_FLUSH
 }
+/* slots per lane for a run of NT slots: a multiple of 8 */
+__device__ __forceinline__ uint32_t run_length(uint32_t NT) { return (((NT + 31) >> 5) + 7) & ~7u; }
 
 /* stored block for one piece: the piece starts byte-aligned, so the 3 header bits + pad are one byte.
- * The bytes come from global memory again (the shared piece buffer already belongs to another warp);
+ * The bytes come from global memory again (the shared window already belongs to somebody else);
  * incompressible pieces are the only ones that pay this second read. */
 __device__ __forceinline__ uint32_t stored_piece(uint8_t *slot, const uint8_t *src, uint32_t n, bool bfinal, uint32_t lane)
 {
@@ -767,33 +693,35 @@ __device__ __forceinline__ uint32_t stored_piece(uint8_t *slot, const uint8_t *s
     return 5 + n;
 }
 
-/* one piece as its own block (or run of blocks): everything after the token pass */
-__device__ __forceinline__ void finish_piece(const QzbCompressJob &job, CodeScratch &cs, uint32_t *hist, uint32_t *toks, uint32_t lane, const PieceState &ps,
+/* one piece as its own block: everything after the histogram.  slots[0..ps.nslots) are the piece's slots; the end-of-block
+ * slot is appended here. */
+__device__ __forceinline__ void finish_piece(const QzbCompressJob &job, BlockCoder &bc, uint16_t *slots, const uint16_t *s_lentab, uint32_t lane, const PieceState &ps,
                                              uint32_t extra_total, uint64_t pkeep QZ_TARG)
 {
-    const uint32_t g = ps.g, n = ps.n, ntok = ps.ntok;
+    const uint32_t g = ps.g, n = ps.n;
     const bool bfinal = ps.bfinal;
     uint8_t *slot = job.slots + (size_t)g * job.slot_stride;
     uint32_t *slotw = reinterpret_cast<uint32_t *>(slot);
+    if (lane == 0) tok16_st(slots + ps.nslots, 256, pkeep);
+    __syncwarp();
 
     uint32_t out_bytes = 0;
-    int btype = choose_block(cs, hist, extra_total, (5 + n) * 8, job.static_huffman, lane QZ_TPASS);
+    int btype = choose_block(bc.cs, bc.hist, extra_total, (5 + n) * 8, job.static_huffman, lane QZ_TPASS);
     if (n == 0) btype = 1;
 
     if (btype == 0) out_bytes = stored_piece(slot, ps.src, n, bfinal, lane);
     else {
         uint32_t hb, pend2;
-        open_block(cs, hist, btype, bfinal, slotw, lane, &hb, &pend2 QZ_TPASS);
-        /* ---- phase 4: emit ----
-         * Every lane codes a contiguous run of tokens: pass 1 adds up the run's bit length, a warp scan
-         * turns the lengths into bit offsets, pass 2 packs the run through a private 64-bit accumulator
-         * straight into the slot.  Words that hold a run boundary are zeroed first and receive their
-         * parts by atomic OR; every other word is written whole by exactly one lane.  The end-of-block
-         * code is the last token; the lane that owns it also appends the byte-alignment trailer. */
-        const uint32_t NT = ntok + 1;
-        const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
+        open_block(bc.cs, bc.hist, btype, bfinal, slotw, s_lentab, lane, &hb, &pend2 QZ_TPASS);
+        /* Every lane codes a contiguous run of slots: pass 1 adds up the run's bit length, a warp scan turns the lengths
+         * into bit offsets, pass 2 packs the run through a private 64-bit accumulator straight into the output.  Words that
+         * hold a run boundary are zeroed first and receive their parts by atomic OR; every other word is written whole by
+         * exactly one lane.  The end-of-block code is the last slot; the lane that owns it also appends the byte-alignment
+         * trailer. */
+        const uint32_t NT = ps.nslots + 1;
+        const uint32_t R = run_length(NT);
         const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-        const uint32_t mybits = count_run_bits(hist, toks, beg, end, pkeep);
+        const uint32_t mybits = count_run_bits(bc.hist, slots, beg, end, pkeep);
         uint32_t incl = mybits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -804,7 +732,7 @@ __device__ __forceinline__ void finish_piece(const QzbCompressJob &job, CodeScra
         slotw[start >> 5] = 0;
         if (lane == 31) slotw[end_bit2 >> 5] = 0;
         __syncwarp();
-        emit_run(hist, toks, beg, end, start, pend2, lane == 0, !bfinal && beg < NT && end == NT, nz, slotw, pkeep);
+        emit_run(bc.hist, slots, beg, end, start, pend2, lane == 0, !bfinal && beg < NT && end == NT, nz, slotw, pkeep);
         out_bytes = (end_bit2 + 7) >> 3;
         __syncwarp();
     }
@@ -813,117 +741,8 @@ __device__ __forceinline__ void finish_piece(const QzbCompressJob &job, CodeScra
     QZ_MARK(8);
 }
 
-template <int HB>
-__device__ __forceinline__ void phase34(const QzbCompressJob &job, WarpPriv<HB> &ws, uint32_t *toks, const uint16_t *s_lentab,
-                                        uint32_t lane, const PieceState &ps QZ_TARG)
-{
-    const uint64_t pkeep = l2_policy_keep();
-    const uint32_t extra_acc = token_pass(ws.u.b.hist, toks, ps.ntok, s_lentab, lane, pkeep);
-    if (lane == 0) tok_st(toks + ps.ntok, 256u, pkeep);      /* end-of-block rides along as the last token */
-    __syncwarp();
-    const uint32_t extra_total = warp_sum(extra_acc);
-    QZ_MARK(3);
-    finish_piece(job, ws.u.b.cs, ws.u.b.hist, toks, lane, ps, extra_total, pkeep QZ_TPASS);
-}
-
-template <int PIECE_LOG2, int HB>
-__global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
-{
-    constexpr int PIECE = 1 << PIECE_LOG2;
-    static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "phase 3-4 scratch must fit in the hash table");
-    QZ_DYN_SMEM(smem_raw);
-    __shared__ uint32_t s_crc_tab[256];
-    __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
-    __shared__ uint16_t s_lentab[256];
-    __shared__ uint32_t s_busy[1];          /* free mask of the piece buffers */
-    constexpr uint32_t STRIP = PIECE / 32 + 4;
-
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    PieceBuf<PIECE_LOG2> *bufs = reinterpret_cast<PieceBuf<PIECE_LOG2> *>(smem_raw);
-    WarpPriv<HB> &ws = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>))[warp];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
-    if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;   /* bit b set = piece buffer b is free */
-    __syncthreads();
-
-    const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint32_t *toks = job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE);
-
-#ifdef QZ_PHASE_CLOCKS
-    long long tlast = clock64();
-#endif
-    for (;;) {
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(job.ticket, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if (g >= job.npieces) break;
-        /* take a free piece buffer: one bit per buffer in s_free; a warp that finds none sleeps with
-         * exponential back-off instead of spinning on the issue slots the working warps need */
-        uint32_t b = 0;
-        if (lane == 0) {
-            uint32_t ns = 128;
-            for (;;) {
-                const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&s_busy[0]);
-                if (m) {
-                    b = __ffs(m) - 1;
-                    if (atomicAnd(&s_busy[0], ~(1u << b)) & (1u << b)) break;
-                    continue;
-                }
-                __nanosleep(ns);
-                if (ns < 4096) ns <<= 1;
-            }
-            __threadfence_block();
-        }
-        b = __shfl_sync(FULL, b, 0);
-        QZ_MARK(0);
-        PieceState ps;
-        phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks, s_crc_tab, s_xstrip, g, lane, ps QZ_TPASS);
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); atomicOr(&s_busy[0], 1u << b); }
-        phase34<HB>(job, ws, toks, s_lentab, lane, ps QZ_TPASS);
-    }
-}
-
-/* ------------------------------------------------------------------------------------------ */
-/* Group kernel: QZ_GROUP consecutive pieces of one chunk (64 KiB with 8 KiB pieces) become ONE deflate block.
- * Eight warps take a group together.  Each runs phases 1-2 and the token pass on its own piece exactly as above
- * (private window, private token scratch), then the group's leader adds up the eight histograms and does the
- * serial work once -- sort, Huffman lengths, header plan, block type, canonical codes, block header -- and every
- * warp packs its tokens with the shared code tables at its bit offset inside the group's output, which starts at the
- * first piece's slot.  Against one block per piece this divides the per-block work (a quarter of a piece's time)
- * and the per-block bytes (dynamic header, flush marker) by eight; the stream is what a zlib deflate with a
- * Z_FULL_FLUSH per 64 KiB would look like.  Warps of a group meet at a named barrier (bar.sync id, 256); groups of
- * one CTA are independent of each other.  Used when a chunk is a whole number of groups (hw_buff_sz >= 64 KiB). */
-#define QZ_GROUP 8                      /* pieces per block */
-/* Shared memory of the group kernel: a warp's private slice is its hash table during the match phase and its
- * histogram afterwards (no code scratch: only the leader builds codes), so a 2^10-entry table makes it 2 KiB.  The
- * code scratch and the group's histogram / code tables (GroupLead, 4000 B) live in a piece buffer that the leader
- * takes from the pool for the time the block is being coded: no shared memory is set aside for them. */
-template <int HB>
-struct GroupWarpPriv {
-    union {
-        uint16_t table[1 << HB];
-        uint32_t hist[QZ_HIST_WORDS];
-        uint8_t pad[(((2 << HB) > QZ_HIST_WORDS * 4 ? (2 << HB) : QZ_HIST_WORDS * 4) + 15) & ~15];     /* 2^9 entries: the histogram (1272 B) sets the size */
-    } u;
-};
-struct GroupLead { CodeScratch cs; uint32_t hist[QZ_HIST_WORDS]; };
-struct GroupShared {
-    uint32_t ticket, bfinal, btype, hb, pend, lead_buf;
-    uint32_t nbytes[QZ_GROUP], ntok[QZ_GROUP], bits[QZ_GROUP], extra[QZ_GROUP];
-};
-template <int NT>
-__device__ __forceinline__ void group_bar(uint32_t id)
-{
-#ifdef QZ_WARP_EMU
-    emu::named_barrier(id, NT);
-#else
-    __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NT) : "memory");
-#endif
-}
-
-/* take a free piece buffer: one bit per buffer in *busy (set = free); a warp that finds none sleeps with exponential
- * back-off instead of spinning on the issue slots the working warps need */
+/* take a free buffer (piece buffer or window unit): one bit per buffer in *busy (set = free); a warp that finds none sleeps
+ * with exponential back-off instead of spinning on the issue slots the working warps need */
 __device__ __forceinline__ uint32_t take_buffer(uint32_t *busy, uint32_t lane)
 {
     uint32_t b = 0;
@@ -949,227 +768,272 @@ __device__ __forceinline__ void give_buffer(uint32_t *busy, uint32_t b, uint32_t
     if (lane == 0) { __threadfence_block(); atomicOr(busy, 1u << b); }
 }
 
-/* histogram and extra-bit total of one piece from its tokens in symbol form (mixed groups: the warp's own histogram
- * may cover two pieces) */
-__device__ __forceinline__ uint32_t hist_from_tokens(uint32_t *hist, const uint32_t *toks, uint32_t ntok, uint32_t lane, uint64_t pkeep)
-{
-    for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) hist[i] = 0;
-    __syncwarp();
-    uint32_t extra = 0;
-    for (uint32_t i = lane; i < ntok; i += 32) {
-        const uint32_t t = tok_ld(toks + i, pkeep);
-        if (t & 0x80000000u) {
-            const uint32_t ls = (t >> 26) & 31, ds = (t >> 16) & 31;
-            atomicAdd(&hist[257 + ls], 1u);
-            atomicAdd(&hist[QZ_DOFF + ds], 1u);
-            extra += ((ls < 8 || ls == 28) ? 0u : (ls - 4) >> 2) + (ds < 4 ? 0u : (ds >> 1) - 1);
-        } else atomicAdd(&hist[t & 511u], 1u);
-    }
-    __syncwarp();
-    return warp_sum(extra);
-}
-
-/* GW warps per group, each with PPW = 8 / GW pieces of the block.  Only GW = 8 (one piece per warp) is instantiated: GW = 4
- * (two pieces per warp, so that three warps instead of seven wait for the leader) did cut that wait from 16 % to 11 % of warp
- * time on B200 but ran 30 % slower overall -- two pieces' tokens per warp no longer fit the L2 -- and is not offered. */
-template <int PIECE_LOG2, int HB, int GW>
-__global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_groups_kernel(QzbCompressJob job, int nbuf)
+template <int PIECE_LOG2, int HB>
+__global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_kernel(QzbCompressJob job, int nbuf)
 {
     constexpr int PIECE = 1 << PIECE_LOG2;
-    constexpr int PPW = QZ_GROUP / GW;
-    static_assert(sizeof(GroupWarpPriv<HB>) % 16 == 0 && sizeof(GroupWarpPriv<HB>) >= QZ_HIST_WORDS * 4, "a warp's slice holds its hash table, then its histogram");
-    static_assert(sizeof(GroupLead) <= sizeof(PieceBuf<PIECE_LOG2>) && sizeof(PieceBuf<PIECE_LOG2>) % 16 == 0, "the code scratch borrows a piece buffer");
+    static_assert(sizeof(WarpPriv<HB>) == (sizeof(uint16_t) << HB), "the block coder must fit in the hash table");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
-    __shared__ uint32_t s_xstrip[5];
+    __shared__ uint32_t s_xstrip[5];        /* x^(8*STRIP*2^k) for the CRC tree */
     __shared__ uint16_t s_lentab[256];
-    __shared__ uint32_t s_busy[1];
-    __shared__ GroupShared s_grp[QZ_GROUPS_MAX_WARPS / GW];
+    __shared__ uint32_t s_busy[1];          /* free mask of the piece buffers */
     constexpr uint32_t STRIP = PIECE / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     PieceBuf<PIECE_LOG2> *bufs = reinterpret_cast<PieceBuf<PIECE_LOG2> *>(smem_raw);
-    GroupWarpPriv<HB> *wsv = reinterpret_cast<GroupWarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>));
-    GroupWarpPriv<HB> &ws = wsv[warp];
+    WarpPriv<HB> &ws = reinterpret_cast<WarpPriv<HB> *>(smem_raw + (size_t)nbuf * sizeof(PieceBuf<PIECE_LOG2>))[warp];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;
+    if (threadIdx.x == 0) s_busy[0] = nbuf >= 32 ? FULL : (1u << nbuf) - 1;   /* bit b set = piece buffer b is free */
     __syncthreads();
 
-    const uint32_t grp = warp / GW, wg = warp % GW, bar = 1 + grp;
-    GroupShared &G = s_grp[grp];
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint32_t *toks0 = job.tok_scratch + (size_t)gwarp * PPW * QZB_TOK_STRIDE(PIECE);
-    const uint32_t gpc = job.pieces_per_chunk / QZ_GROUP;     /* groups per chunk */
+    uint16_t *slots = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE));
     const uint64_t pkeep = l2_policy_keep();
-    uint32_t held = 0xffffffffu;                              /* leader: the piece buffer that serves as the block's code scratch */
+
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
     for (;;) {
-        if (wg == 0 && lane == 0) { G.ticket = atomicAdd(job.ticket, 1u); G.bfinal = 0; }
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(job.ticket, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= job.npieces) break;
+        const uint32_t b = take_buffer(&s_busy[0], lane);
+        QZ_MARK(0);
+        PieceState ps;
+        piece_geometry<PIECE_LOG2>(job, g, ps);
+        {
+            uint8_t *piece = bufs[b].bytes + QZM_FRONT_PAD;
+            const uint32_t c = load_and_checksum<PIECE>(piece, ps.src, ps.n, true, job.fmt, s_crc_tab, s_xstrip, lane);
+            if (lane == 0) job.piece_crc[g] = c;
+            for (uint32_t i = lane; i < (1u << HB) / 2; i += 32) reinterpret_cast<uint32_t *>(ws.u.table)[i] = 0xffffffffu;
+            __syncwarp();
+            QZ_MARK(1);
+            QzmDeflateSink sink = { slots, 0, pkeep };
+            qzm_match_piece(piece, ps.n, 0, ps.n, ws.u.table, 1u << HB, sink, lane);
+            ps.nslots = sink.nslots;
+            QZ_MARK(2);
+        }
+        give_buffer(&s_busy[0], b, lane);
+        BlockCoder &bc = ws.u.b;
+        for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) bc.hist[i] = 0;
+        __syncwarp();
+        const uint32_t extra_total = warp_sum(slot_hist(bc.hist, slots, ps.nslots, s_lentab, lane, pkeep));
+        __syncwarp();
+        QZ_MARK(3);
+        finish_piece(job, bc, slots, s_lentab, lane, ps, extra_total, pkeep QZ_TPASS);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Window kernel (default for hw_buff_sz >= 64 KiB): a WINDOW is 64 KiB of one chunk -- eight pieces -- and becomes ONE
+ * deflate block, what the QAT engine emits for a 64 KiB request with its 32 KiB history (reference
+ * src/qatzip_utils.c:270-291).  Eight warps take a window together.  Its bytes sit whole in a shared-memory UNIT next to
+ * the eight warps' hash tables; the stages of qz_match.cuh (prepass, seed, match) give every position the whole window in
+ * front of it as history while the eight pieces are still matched concurrently.  The unit is handed back as soon as the
+ * eighth warp has matched; the group goes on from the slots in the L2 scratch: histogram into the group's block coder,
+ * the leader builds the codes and writes the block header, every warp counts its slots' bits, the totals are scanned
+ * through shared memory, boundary words are zeroed, and every lane packs its run at its bit offset inside the group's
+ * output (the first piece's slot); the lane that codes the end-of-block slot appends the byte-aligning empty stored block
+ * unless the block is final.  A CTA has more groups than units (four and two): while two groups match, two code.
+ * Incompressible window -> every piece a stored block in its own slot; a window that mixes incompressible pieces with
+ * compressible ones -> its pieces take turns on the block coder and become blocks of their own.
+ * Warps of a group meet at a named barrier (bar.sync id, 256); groups of one CTA are independent of each other. */
+#define QZ_GROUP 8                      /* pieces per window */
+#define QZ_WINDOW (QZ_GROUP << 13)
+struct WindowShared {
+    uint32_t ticket, unit, done, btype, hb, pend;
+    uint32_t nslots[QZ_GROUP], bits[QZ_GROUP], extra[QZ_GROUP];
+};
+template <int NT>
+__device__ __forceinline__ void group_bar(uint32_t id)
+{
+#ifdef QZ_WARP_EMU
+    emu::named_barrier(id, NT);
+#else
+    __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NT) : "memory");
+#endif
+}
+/* bytes of one unit: the window with its pads, then QZ_GROUP tables of `tent` entries (rounded up to 16 bytes each) */
+__host__ __device__ __forceinline__ uint32_t window_table_stride(uint32_t tent) { return (tent + 8u) & ~7u; }       /* u16 entries */
+__host__ __device__ __forceinline__ uint32_t window_unit_bytes(uint32_t tent) { return QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD + QZ_GROUP * 2u * window_table_stride(tent); }
+
+__global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job, int nunits)
+{
+    constexpr int PIECE = 1 << 13;
+    constexpr int GW = QZ_GROUP;
+    static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
+    QZ_DYN_SMEM(smem_raw);
+    __shared__ uint32_t s_crc_tab[256];
+    __shared__ uint32_t s_xstrip[5];
+    __shared__ uint16_t s_lentab[256];
+    __shared__ uint32_t s_free[1];          /* free mask of the units */
+    __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW];
+    constexpr uint32_t STRIP = PIECE / 32 + 4;
+
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
+    if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
+    if (threadIdx.x == 0) s_free[0] = (1u << nunits) - 1;
+    __syncthreads();
+
+    const uint32_t grp = warp / GW, wg = warp % GW, bar = 1 + grp;
+    WindowShared &G = s_grp[grp];
+    BlockCoder &C = reinterpret_cast<BlockCoder *>(smem_raw + (size_t)nunits * unit_bytes)[grp];
+    const uint32_t gwarp = blockIdx.x * nwarps + warp;
+    uint16_t *slots = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE));
+    const uint32_t wpc = job.pieces_per_chunk / QZ_GROUP;     /* windows per chunk */
+    const uint64_t pkeep = l2_policy_keep();
+#ifdef QZ_PHASE_CLOCKS
+    long long tlast = clock64();
+#endif
+    for (;;) {
+        /* the leader draws the window and, if there is one, a unit for it */
+        if (wg == 0) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(job.ticket, 1u);
+            tk = __shfl_sync(FULL, tk, 0);
+            const uint32_t u = tk < job.ngroups ? take_buffer(&s_free[0], lane) : 0u;
+            if (lane == 0) { G.ticket = tk; G.unit = u; G.done = 0; }
+        }
         group_bar<GW * 32>(bar);
+        QZ_MARK(0);
         /* every warp of the group is past the previous block's emission: its code tables can go */
-        if (wg == 0 && held != 0xffffffffu) { give_buffer(&s_busy[0], held, lane); held = 0xffffffffu; }
         const uint32_t gi = G.ticket;
         if (gi >= job.ngroups) break;
-        const uint32_t chunk = gi / gpc, blk = gi - chunk * gpc;
+        if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
+        const uint32_t chunk = gi / wpc, blk = gi - chunk * wpc;
         const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_GROUP;
-        /* this warp's pieces: n = 0 for pieces behind the end of a ragged last chunk */
-        PieceState ps[PPW];
-        bool last_in_group[PPW];
-#pragma unroll
-        for (int j = 0; j < PPW; j++) {
-            const uint32_t pi = wg * PPW + j;
-            const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
-            const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
-            const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
-            const uint32_t p_off = (blk * QZ_GROUP + pi) << PIECE_LOG2;
-            ps[j].g = g0 + pi; ps[j].n = chunk_len > p_off ? min((uint32_t)PIECE, chunk_len - p_off) : 0u; ps[j].ntok = 0; ps[j].extra_total = 0; ps[j].bfinal = false;
-            ps[j].src = job.src + chunk_off + p_off;
-            last_in_group[j] = ps[j].n != 0 && (pi == QZ_GROUP - 1 || p_off + ps[j].n == chunk_len);
+        const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
+        const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
+        const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+        const uint32_t win_off = blk * QZ_WINDOW;
+        const uint32_t wlen = min((uint32_t)QZ_WINDOW, chunk_len - win_off);         /* > 0: only windows with data are counted */
+        const uint32_t npc = (wlen + PIECE - 1) >> 13;                               /* pieces with data */
+        const bool gfinal = (win_off + wlen == chunk_len) && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
+        const uint32_t p0 = wg * PIECE;
+        PieceState ps;
+        ps.g = g0 + wg; ps.n = wlen > p0 ? min((uint32_t)PIECE, wlen - p0) : 0u; ps.nslots = 0;
+        ps.src = job.src + chunk_off + win_off + p0;
+        const bool last_in_win = ps.n != 0 && p0 + ps.n == wlen;
+        ps.bfinal = last_in_win && gfinal;
+        uint8_t *unit = smem_raw + (size_t)G.unit * unit_bytes;
+        uint8_t *win = unit + QZM_FRONT_PAD;
+        uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
+        uint16_t *table = tables + (size_t)wg * tstride;
+
+        /* load + checksum + prepass of the warp's own piece */
+        if (ps.n) {
+            const uint32_t c = load_and_checksum<PIECE>(win + p0, ps.src, ps.n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
+            if (lane == 0) job.piece_crc[ps.g] = c;
         }
-        /* phases 1-2 for every piece first (the hash table and the histogram share the warp's slice), then the token passes */
-#pragma unroll
-        for (int j = 0; j < PPW; j++) {
-            if (ps[j].n) {
-                const uint32_t b = take_buffer(&s_busy[0], lane);
-                QZ_MARK(0);
-                phase12<PIECE_LOG2, HB>(job, bufs[b].bytes, ws.u.table, toks0 + j * QZB_TOK_STRIDE(PIECE), s_crc_tab, s_xstrip, ps[j].g, lane, ps[j] QZ_TPASS);
-                give_buffer(&s_busy[0], b, lane);
-            }
-        }
-        uint32_t extra = 0;
-#pragma unroll
-        for (int j = 0; j < PPW; j++) {
-            uint32_t *toks = toks0 + j * QZB_TOK_STRIDE(PIECE);
-            extra += token_pass(ws.u.hist, toks, ps[j].ntok, s_lentab, lane, pkeep, j == 0);
-            /* the last piece of the block carries the end-of-block token */
-            if (lane == 0 && last_in_group[j]) tok_st(toks + ps[j].ntok, 256u, pkeep);
-        }
-        extra = warp_sum(extra);
+        QZ_MARK(1);
+        /* (a piece's last three positions hash bytes of the next piece, which may not have arrived: they are left out) */
+        if (ps.n) qzm_prepass(win, p0 + ps.n, p0, p0 + ps.n, table, tent, lane);
+        group_bar<GW * 32>(bar);
+        qzm_seed_tables(tables, tstride, npc, tent, threadIdx.x - grp * (GW * 32), GW * 32);
+        group_bar<GW * 32>(bar);
+        QZ_MARK(4);
+        QzmDeflateSink sink = { slots, 0, pkeep };
+        if (ps.n) qzm_match_piece(win, wlen, p0, p0 + ps.n, table, tent, sink, lane);
+        ps.nslots = sink.nslots;
+        /* the eighth warp to finish hands the unit back */
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); if (atomicAdd(&G.done, 1u) == GW - 1) atomicOr(&s_free[0], 1u << G.unit); }
+        QZ_MARK(2);
+        /* histogram of the warp's slots into the group's; the last piece of the window carries the end-of-block slot */
+        uint32_t extra = warp_sum(slot_hist(C.hist, slots, ps.nslots, s_lentab, lane, pkeep));
         if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < PPW; j++) {
-                G.nbytes[wg * PPW + j] = ps[j].n; G.ntok[wg * PPW + j] = ps[j].ntok + (last_in_group[j] ? 1u : 0u);
-                if (ps[j].bfinal) G.bfinal = 1;
-            }
+            if (last_in_win) tok16_st(slots + ps.nslots, 256, pkeep);
+            G.nslots[wg] = ps.nslots + (last_in_win ? 1u : 0u);
             G.extra[wg] = extra;
         }
         QZ_MARK(3);
         group_bar<GW * 32>(bar);
         QZ_MARK(9);                 /* waiting for the group's slowest piece */
-        /* A group that mixes incompressible pieces (close to one token per byte) with compressible ones is better off
+        /* A window that mixes incompressible pieces (close to one slot per byte) with compressible ones is better off
          * with a block per piece: one code table cannot serve both, and only whole blocks can fall back to stored. */
         {
             uint32_t hi = 0, lo = 0xffffffffu;
 #pragma unroll
             for (int i = 0; i < QZ_GROUP; i++) {
-                const uint32_t nb = G.nbytes[i];
-                if (nb) { const uint32_t r = (G.ntok[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
+                const uint32_t nb = wlen > (uint32_t)i * PIECE ? min((uint32_t)PIECE, wlen - i * PIECE) : 0u;
+                if (nb) { const uint32_t r = (G.nslots[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
             }
             if (hi > 920u && lo < 768u) {
-                /* rare: every piece on its own, with a piece buffer as its code scratch */
-#pragma unroll
-                for (int j = 0; j < PPW; j++) {
-                    if (!ps[j].n) continue;
-                    uint32_t *toks = toks0 + j * QZB_TOK_STRIDE(PIECE);
-                    if (lane == 0) tok_st(toks + ps[j].ntok, 256u, pkeep);
-                    const uint32_t b = take_buffer(&s_busy[0], lane);
-                    GroupLead &own = *reinterpret_cast<GroupLead *>(bufs[b].bytes);
-                    const uint32_t ex = hist_from_tokens(own.hist, toks, ps[j].ntok, lane, pkeep);
-                    finish_piece(job, own.cs, own.hist, toks, lane, ps[j], ex, pkeep QZ_TPASS);
-                    give_buffer(&s_busy[0], b, lane);
+                /* rare: the pieces take turns on the group's block coder */
+                for (uint32_t i = 0; i < npc; i++) {
+                    if (wg == i) {
+                        for (uint32_t k = lane; k < QZ_HIST_WORDS; k += 32) C.hist[k] = 0;
+                        __syncwarp();
+                        const uint32_t ex = warp_sum(slot_hist(C.hist, slots, ps.nslots, s_lentab, lane, pkeep));
+                        __syncwarp();
+                        finish_piece(job, C, slots, s_lentab, lane, ps, ex, pkeep QZ_TPASS);
+                    }
+                    group_bar<GW * 32>(bar);
                 }
                 continue;
             }
         }
-        /* leader: one histogram, one set of codes, one block header for the group */
+        uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
+        /* leader: one set of codes, one block header for the window */
         if (wg == 0) {
-            held = take_buffer(&s_busy[0], lane);
-            GroupLead &L = *reinterpret_cast<GroupLead *>(bufs[held].bytes);
-            uint32_t extra_total = 0, nbytes = 0, npc = 0;
+            uint32_t extra_total = 0;
             for (int i = 0; i < GW; i++) extra_total += G.extra[i];
-            for (int i = 0; i < QZ_GROUP; i++) { nbytes += G.nbytes[i]; npc += G.nbytes[i] ? 1u : 0u; }
-            for (uint32_t s = lane; s < QZ_HIST_WORDS; s += 32) {
-                uint32_t f = 0;
-#pragma unroll
-                for (int i = 0; i < GW; i++) f += wsv[grp * GW + i].u.hist[s];
-                L.hist[s] = f;
-            }
-            __syncwarp();
-            const int btype = choose_block(L.cs, L.hist, extra_total, (5 * npc + nbytes) * 8, job.static_huffman, lane QZ_TPASS);
+            const int btype = choose_block(C.cs, C.hist, extra_total, (5 * npc + wlen) * 8, job.static_huffman, lane QZ_TPASS);
             uint32_t hb = 0, pend = 0;
-            if (btype) open_block(L.cs, L.hist, btype, G.bfinal != 0, reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride), lane, &hb, &pend QZ_TPASS);
-            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; G.lead_buf = held; }
+            if (btype) open_block(C.cs, C.hist, btype, gfinal, slotw, s_lentab, lane, &hb, &pend QZ_TPASS);
+            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
             QZ_MARK(11);            /* leader: block header written, tables final */
         }
         group_bar<GW * 32>(bar);
         QZ_MARK(10);                /* waiting for the leader */
-        const uint32_t btype = G.btype;
-        const bool gfinal = G.bfinal != 0;
-        if (btype == 0) {
-            /* incompressible group: every piece is its own stored block in its own slot, as in the per-piece kernel */
-#pragma unroll
-            for (int j = 0; j < PPW; j++) {
-                if (!ps[j].n) continue;
-                const uint32_t out_bytes = stored_piece(job.slots + (size_t)ps[j].g * job.slot_stride, ps[j].src, ps[j].n, ps[j].bfinal, lane);
-                if (lane == 0) job.piece_len[ps[j].g] = out_bytes;
+        if (G.btype == 0) {
+            /* incompressible window: every piece is its own stored block in its own slot */
+            if (ps.n) {
+                const uint32_t out_bytes = stored_piece(job.slots + (size_t)ps.g * job.slot_stride, ps.src, ps.n, ps.bfinal, lane);
+                if (lane == 0) job.piece_len[ps.g] = out_bytes;
             }
         } else {
-            const uint32_t *tab = reinterpret_cast<const GroupLead *>(bufs[G.lead_buf].bytes)->hist;
-            uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
-            uint32_t beg[PPW], end[PPW], mybits[PPW], incl[PPW];
+            const uint32_t *tab = C.hist;
+            const uint32_t NT = G.nslots[wg];
+            const uint32_t R = run_length(NT);
+            const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
+            const uint32_t mybits = count_run_bits(tab, slots, beg, end, pkeep);
+            uint32_t incl = mybits;
 #pragma unroll
-            for (int j = 0; j < PPW; j++) {
-                const uint32_t NT = G.ntok[wg * PPW + j];
-                const uint32_t R = (((NT + 31) >> 5) + 3) & ~3u;
-                beg[j] = min(lane * R, NT); end[j] = min(beg[j] + R, NT);
-                mybits[j] = count_run_bits(tab, toks0 + j * QZB_TOK_STRIDE(PIECE), beg[j], end[j], pkeep);
-                incl[j] = mybits[j];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl[j], o); if (lane >= (uint32_t)o) incl[j] += y; }
-                if (lane == 31) G.bits[wg * PPW + j] = incl[j];
-            }
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+            if (lane == 31) G.bits[wg] = incl;
             QZ_MARK(12);            /* count pass */
             group_bar<GW * 32>(bar);
             QZ_MARK(13);
-            uint32_t before[PPW], total = G.hb;
-#pragma unroll
-            for (int j = 0; j < PPW; j++) before[j] = G.hb;
+            uint32_t before = G.hb, total = G.hb;
 #pragma unroll
             for (int i = 0; i < QZ_GROUP; i++) {
                 const uint32_t bi = G.bits[i];
-#pragma unroll
-                for (int j = 0; j < PPW; j++) if (i < (int)(wg * PPW + j)) before[j] += bi;
+                if (i < (int)wg) before += bi;
                 total += bi;
             }
             const uint32_t end_bit = total;
             const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);
             const uint32_t end_bit2 = gfinal ? end_bit : end_bit + nz + 32;
-#pragma unroll
-            for (int j = 0; j < PPW; j++) slotw[(before[j] + incl[j] - mybits[j]) >> 5] = 0;
+            const uint32_t start = before + incl - mybits;
+            slotw[start >> 5] = 0;
             if (wg == GW - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
             group_bar<GW * 32>(bar);
             QZ_MARK(14);
-#pragma unroll
-            for (int j = 0; j < PPW; j++) {
-                const uint32_t NT = G.ntok[wg * PPW + j];
-                /* the lane that codes the end-of-block token appends the trailer; it is the last token of the group */
-                const bool owns_eob = last_in_group[j] && beg[j] < NT && end[j] == NT;
-                emit_run(tab, toks0 + j * QZB_TOK_STRIDE(PIECE), beg[j], end[j], before[j] + incl[j] - mybits[j], G.pend, wg == 0 && j == 0 && lane == 0,
-                         !gfinal && owns_eob, nz, slotw, pkeep);
-                if (lane == 0 && ps[j].n) job.piece_len[ps[j].g] = (wg == 0 && j == 0) ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
-            }
+            /* the lane that codes the end-of-block slot appends the trailer; it is the last slot of the window */
+            const bool owns_eob = last_in_win && beg < NT && end == NT;
+            emit_run(tab, slots, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
+            if (lane == 0 && ps.n) job.piece_len[ps.g] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
         }
         __syncwarp();
         QZ_MARK(8);
     }
 }
-
-#ifdef QZ_SPLIT_KERNEL
-#include "qz_deflate_split.cuh"
-#endif
 
 /* ------------------------------------------------------------------------------------------ */
 /* Framing: sizes -> exclusive scan -> headers, payload gather, footers.
@@ -1331,7 +1195,6 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
         }
     }
 }
-
 /* ------------------------------------------------------------------------------------------ */
 #ifndef QZ_WARP_EMU
 /* shared memory for `warps` warps sharing `nbuf` piece buffers */
@@ -1362,64 +1225,27 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
     return cudaErrorInvalidValue;
 }
 
-extern "C" int qzb_deflate_max_warps(int group) { return group ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
+extern "C" int qzb_deflate_max_warps(int window) { return window ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
-/* shared memory of the group kernel for `warps` warps sharing `nbuf` piece buffers (the code scratch borrows from the pool) */
-extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf)
+/* shared memory of the window kernel: `nunits` units of tables with `tent` entries, `groups` block coders */
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups, int nunits)
 {
-    const size_t priv = hb == 9 ? sizeof(GroupWarpPriv<9>) : (size_t)2 << hb;
-    return priv * (size_t)warps + sizeof(PieceBuf<13>) * (size_t)nbuf;
+    return (size_t)nunits * window_unit_bytes((uint32_t)tent) + (size_t)groups * sizeof(BlockCoder);
 }
 
-template <int P, int H, int GW>
-static cudaError_t launch_deflate_groups(const QzbCompressJob &job, int grid, int warps, int nbuf, cudaStream_t st)
+/* window kernel (one deflate block per 64 KiB window): `groups` groups of eight warps per CTA share `nunits` units;
+ * job->ngroups and job->tent set */
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, int nunits, cudaStream_t st)
 {
-    size_t smem = qzb_deflate_groups_smem_bytes(H, warps, nbuf);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_groups_kernel<P, H, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    qzb_deflate_groups_kernel<P, H, GW><<<grid, warps * 32, smem, st>>>(job, nbuf);
-    return cudaGetLastError();
-}
-
-/* group kernel (one deflate block per QZ_GROUP pieces): warps a multiple of QZ_GROUP, job->ngroups set */
-extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st)
-{
-    if (nbuf < 1 || nbuf > 32 || warps < QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || warps % QZ_GROUP || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13)
+    if (groups < 1 || groups * QZ_GROUP > QZ_GROUPS_MAX_WARPS || nunits < 1 || nunits > groups || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13 ||
+        job->tent < 256 || job->tent > 32768)
         return cudaErrorInvalidValue;
-    if (hb == 9) return launch_deflate_groups<13, 9, 8>(*job, grid, warps, nbuf, st);
-    if (hb == 10) return launch_deflate_groups<13, 10, 8>(*job, grid, warps, nbuf, st);
-    if (hb == 11) return launch_deflate_groups<13, 11, 8>(*job, grid, warps, nbuf, st);
-    if (hb == 12) return launch_deflate_groups<13, 12, 8>(*job, grid, warps, nbuf, st);
-    return cudaErrorInvalidValue;
-}
-
-/* experimental matcher / coder kernel (qz_deflate_split.cuh): present only in builds with -DQZ_SPLIT_KERNEL */
-#ifdef QZ_SPLIT_KERNEL
-extern "C" int qzb_deflate_split_compiled(void) { return 1; }
-extern "C" size_t qzb_deflate_split_smem_bytes(int hb, int nmatch, int nteams) { return qzs_smem_bytes(hb, nmatch, nteams); }
-extern "C" size_t qzb_deflate_split_tok_words(int grid) { return (size_t)grid * QZS_SLOTS * QZ_GROUP * QZB_TOK_STRIDE(1 << 13); }
-template <int H>
-static cudaError_t launch_deflate_split(const QzbCompressJob &job, int grid, int nmatch, int nteams, cudaStream_t st)
-{
-    const size_t smem = qzs_smem_bytes(H, nmatch, nteams);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_split_kernel<13, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent, groups, nunits);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_split_kernel<13, H><<<grid, (nmatch + nteams * QZS_TEAM) * 32, smem, st>>>(job, nmatch, nteams);
+    qzb_deflate_window_kernel<<<grid, groups * QZ_GROUP * 32, smem, st>>>(*job, nunits);
     return cudaGetLastError();
 }
-extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *job, int hb, int grid, int nmatch, int nteams, cudaStream_t st)
-{
-    if (nmatch < 1 || nteams < 1 || nteams > 8 || nmatch + nteams * QZS_TEAM > 32 || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13) return cudaErrorInvalidValue;
-    if (hb == 10) return launch_deflate_split<10>(*job, grid, nmatch, nteams, st);
-    if (hb == 11) return launch_deflate_split<11>(*job, grid, nmatch, nteams, st);
-    return cudaErrorInvalidValue;
-}
-#else
-extern "C" int qzb_deflate_split_compiled(void) { return 0; }
-extern "C" size_t qzb_deflate_split_smem_bytes(int, int, int) { return 0; }
-extern "C" size_t qzb_deflate_split_tok_words(int) { return 0; }
-extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
-#endif
 
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)
 {

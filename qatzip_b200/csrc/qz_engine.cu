@@ -25,17 +25,13 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_deflate_groups(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" int qzb_deflate_split_compiled(void);
-extern "C" size_t qzb_deflate_split_smem_bytes(int hb, int nmatch, int nteams);
-extern "C" size_t qzb_deflate_split_tok_words(int grid);
-extern "C" cudaError_t qzb_launch_deflate_split(const QzbCompressJob *job, int hb, int grid, int nmatch, int nteams, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, int nunits, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
-extern "C" size_t qzb_deflate_groups_smem_bytes(int hb, int warps, int nbuf);
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups, int nunits);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -61,11 +57,11 @@ extern "C" int qzb_runtime_devices(void)
 }
 /* most warps per CTA the deflate kernels were compiled for (their launch bound; qz_deflate.cu) */
 extern "C" int qzb_deflate_max_warps(int group);
-#ifndef QZB200_GROUP_DEFAULT
-#define QZB200_GROUP_DEFAULT 1
+#ifndef QZB200_WINDOW_DEFAULT
+#define QZB200_WINDOW_DEFAULT 1
 #endif
-#ifndef QZB200_GROUP_HB_DEFAULT
-#define QZB200_GROUP_HB_DEFAULT 10
+#ifndef QZB200_WINDOW_TENT_DEFAULT
+#define QZB200_WINDOW_TENT_DEFAULT 2048
 #endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
@@ -95,11 +91,13 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (fmb > mb) fmb = mb;
     t->first_batch_bytes = (size_t)fmb << 20;
     t->taper = env_int("QZB200_TAPER", 0);
-    /* deflate block granularity: 1 = one block per group of 8 pieces (group kernel, chunks that are a whole number of
-     * groups, i.e. hw_buff_sz >= 64 KiB with 8 KiB pieces), 0 = one block per piece everywhere */
-    t->group = env_int("QZB200_GROUP", QZB200_GROUP_DEFAULT);       /* 2: the experimental matcher / coder kernel where it is compiled in, else as 1 */
-    t->group_hash_bits = env_int("QZB200_GROUP_HASH_BITS", QZB200_GROUP_HB_DEFAULT);     /* 9: 1.25 KiB per warp (22 piece buffers, about 1 % larger output); 10: 2 KiB; 11, 12 */
-    if (t->group_hash_bits < 9 || t->group_hash_bits > 12) t->group_hash_bits = QZB200_GROUP_HB_DEFAULT;
+    /* deflate, hw_buff_sz >= 64 KiB: 1 = window kernel (64 KiB windows in shared memory, one block per window), 0 = one block per
+     * 8 KiB piece with a private window everywhere */
+    t->window = env_int("QZB200_WINDOW", QZB200_WINDOW_DEFAULT);
+    t->window_tent = env_int("QZB200_WINDOW_TENT", QZB200_WINDOW_TENT_DEFAULT);      /* entries of a warp's hash table (2 bytes each, eight tables per unit) */
+    if (t->window_tent < 256 || t->window_tent > 8192) t->window_tent = QZB200_WINDOW_TENT_DEFAULT;
+    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups of eight warps per CTA (0 = 4) */
+    t->window_units = env_int("QZB200_WINDOW_UNITS", 0);                              /* units per CTA (0 = as many as fit, at most the groups) */
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -282,36 +280,29 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, hb = t.hash_bits, gw = 8, split_match = 0, split_teams = 0;
+    int nbuf = t.buffers_per_cta, groups = 0, nunits = 0;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
         if (warps <= 0 || warps > 16) warps = 16;
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
-    } else if (t.group && t.piece_log2 == 13 && len && job.pieces_per_chunk % 8 == 0) {
-        /* group kernel: CTAs of whole groups of 8 warps; as many piece buffers as the rest of the 227 KB holds */
-        const uint32_t gpc = job.pieces_per_chunk / 8;
-        job.ngroups = (job.nchunks - 1) * gpc + (last_pieces + 7) / 8;
-        hb = t.group_hash_bits;
-        if (warps < gw || warps > qzb_deflate_max_warps(1) || warps % gw) warps = qzb_deflate_max_warps(1);
-        if (nbuf <= 0 || nbuf > warps) nbuf = warps;
-        while (nbuf > 1 && qzb_deflate_groups_smem_bytes(hb, warps, nbuf) + 3328 > smem_cap) nbuf--;
-        group_smem = qzb_deflate_groups_smem_bytes(hb, warps, nbuf);
-        if (t.group == 2 && qzb_deflate_split_compiled() && (hb == 10 || hb == 11)) {
-            /* experimental matcher / coder kernel (A/B builds only): QZB200_SPLIT_MATCHERS matcher warps + QZB200_SPLIT_TEAMS teams of 4 coder warps */
-            split_teams = std::min(8, std::max(1, env_int("QZB200_SPLIT_TEAMS", 3)));
-            split_match = std::max(1, std::min(32 - 4 * split_teams, env_int("QZB200_SPLIT_MATCHERS", 19)));
-            while (split_match > 1 && qzb_deflate_split_smem_bytes(hb, split_match, split_teams) + 4096 > smem_cap) split_match--;
-            group_smem = qzb_deflate_split_smem_bytes(hb, split_match, split_teams);
-            warps = split_match + 4 * split_teams;
-        }
+    } else if (t.window && t.piece_log2 == 13 && len && job.pieces_per_chunk % 8 == 0) {
+        /* window kernel: CTAs of whole groups of 8 warps; as many units as the 227 KB hold, never more than groups */
+        const uint32_t wpc = job.pieces_per_chunk / 8;
+        job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
+        job.tent = (uint32_t)t.window_tent;
+        groups = t.window_groups > 0 ? std::min(t.window_groups, qzb_deflate_max_warps(1) / 8) : qzb_deflate_max_warps(1) / 8;
+        nunits = t.window_units > 0 ? std::min(t.window_units, groups) : groups;
+        while (nunits > 1 && qzb_deflate_window_smem_bytes((int)job.tent, groups, nunits) + 3072 > smem_cap) nunits--;
+        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, groups, nunits);
+        warps = groups * 8;
     } else {
         if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
         while (warps > 2 && smem_for(warps, nbuf) + 2304 > smem_cap) { warps -= 2; nbuf = std::min(nbuf, (warps + 1) / 2); }
     }
-    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / ((group_smem ? group_smem : smem_for(warps, nbuf)) + 3328));
+    ctas_per_sm = (int)std::max<size_t>(1, (smem_cap + 1024) / ((group_smem ? group_smem : smem_for(warps, nbuf)) + 3072));
     if (ctas_per_sm * warps > 48) ctas_per_sm = std::max(1, 48 / warps);
     int grid = e->sm_count * ctas_per_sm;
     /* small batches: one unit (group or piece) per CTA spreads them over the SMs -- a group alone on an SM finishes in a
@@ -322,7 +313,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((split_match ? qzb_deflate_split_tok_words(grid) : (size_t)grid * warps * (job.ngroups ? 8 / gw : 1) * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((size_t)grid * warps * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
@@ -334,8 +325,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (split_match) CK(qzb_launch_deflate_split(&job, hb, grid, split_match, split_teams, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_groups(&job, hb, grid, warps, nbuf, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, groups, nunits, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

@@ -9,9 +9,9 @@
  * member / 4B block / LZ4 frame, reference src/qatzip.c:1513-1594).  A *piece* is the device's
  * unit: PIECE bytes of a chunk compressed by one warp into a byte-aligned run of deflate blocks
  * (or one LZ4 block).  Pieces of a chunk are laid end to end by the framing kernel. */
-/* words of token scratch per resident warp: one per input byte, the end-of-block token, and room for
- * the 16-byte loads of the emit pass to run past the last token */
-#define QZB_TOK_STRIDE(piece) ((piece) + 32)
+/* 32-bit words of token scratch per resident warp.  Deflate: 16-bit slots, at most one per input byte, the end-of-block slot,
+ * and room for the 16-byte loads of the emit pass to run past the last one.  LZ4: two words per match. */
+#define QZB_TOK_STRIDE(piece) ((piece) / 2 + 32)
 
 struct QzbCompressJob {
     const uint8_t *src;          /* device, batch input */
@@ -35,7 +35,8 @@ struct QzbCompressJob {
     uint32_t *chunk_total;       /* [nchunks] header + payload + footer bytes */
     uint64_t *chunk_off;         /* [nchunks + 1] exclusive prefix of chunk_total */
     uint32_t *chunk_cksum;       /* [nchunks] CRC-32, Adler-32 (zlib) or XXH32 of the chunk's input */
-    uint32_t ngroups;            /* group kernel only: blocks of 8 pieces over all chunks (0 = per-piece kernel) */
+    uint32_t ngroups;            /* window kernels only: windows of 8 pieces (64 KiB) over all chunks (0 = per-piece kernel) */
+    uint32_t tent;               /* window kernels: entries of a warp's hash table */
 };
 
 /* Decompress side: one unit = one gzip member / 4B block / raw stream / LZ4 frame. */

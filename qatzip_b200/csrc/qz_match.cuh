@@ -1,0 +1,203 @@
+/* qz_match.cuh -- the LZ77 match stage shared by the deflate and LZ4 compressors.
+ *
+ * What the QAT engine's history buffer does for a request (reference src/qatzip_utils.c:270-298: 32 KiB deflate window,
+ * 64 KiB LZ4 blocks) is done here on a WINDOW: up to 64 KiB of one chunk sitting whole in shared memory, matched by up
+ * to eight warps at once, each on its own PIECE (8 KiB) of it, every warp seeing everything in front of its position:
+ *
+ *   prepass   every warp records, in its own table of `tent` u16 entries, the last position of every 4-byte hash inside
+ *             its piece                                                                                   (qzm_prepass)
+ *   seed      a scan over the pieces, entry by entry: table k receives the most recent position of every hash in pieces
+ *             0..k-1 -- what a sequential compressor's hash table would hold on entering piece k         (qzm_seed_tables)
+ *   match     32 positions per step.  A position's candidate is the nearest lower lane of its tile with the same hash
+ *             (match.any), else the table entry: together exactly "the most recent earlier position with this hash" of a
+ *             sequential single-probe matcher that inserts every position.  Positions inside a byte run are not inserted
+ *             (the table keeps the run's start, which matches a later run of the same byte from ITS start).  Candidates are
+ *             verified and extended 12 bytes in the lane; the greedy parse of the tile -- which lanes start a token -- is
+ *             found by pointer doubling over next(lane) = lane + max(1, L) instead of a serial walk, matches that reach
+ *             the 12-byte cap are finished by the whole warp, a selected match takes over up to four literals in front of
+ *             it when the bytes before position and candidate agree.                                      (qzm_match_piece)
+ *
+ * With one piece and an empty table the same routine is the private-window matcher of the per-piece kernels.
+ * Tokens leave through a sink: 16-bit slots for deflate, (position, length, distance) records for LZ4.
+ */
+#ifndef QZ_MATCH_CUH
+#define QZ_MATCH_CUH
+#include <stdint.h>
+#include "qz_warp.cuh"
+
+#define QZM_FULL 0xffffffffu
+#define QZM_NONE 0xffffu
+#define QZM_LANE_CAP 12u        /* bytes verified inside the lane; longer matches are finished by the warp */
+#define QZM_FRONT_PAD 16u       /* readable bytes in front of a window (position - 1, position - 4 of its first positions) */
+#define QZM_TAIL_PAD 48u        /* zero bytes behind the window's data */
+
+__device__ __forceinline__ uint32_t qzm_hash(uint32_t v, uint32_t tent) { return __umulhi(v * 2654435761u, tent); }
+__device__ __forceinline__ uint32_t qzm_ld32u(const uint32_t *w, uint32_t off) { return __funnelshift_r(w[off >> 2], w[(off >> 2) + 1], (off & 3) * 8); }
+
+/* a position inside a byte run (the byte before it and its four bytes are all equal) is not recorded in the tables */
+__device__ __forceinline__ bool qzm_run_interior(uint32_t v, uint32_t prevb, uint32_t p) { return p != 0 && v == prevb * 0x01010101u; }
+
+/* table[h] = last position in [p0, p1) with hash h (QZM_NONE elsewhere); `win` is the window's data (4-byte aligned, p0 a
+ * multiple of 32), n its length */
+__device__ __forceinline__ void qzm_prepass(const uint8_t *win, uint32_t n, uint32_t p0, uint32_t p1, uint16_t *table, uint32_t tent, uint32_t lane)
+{
+    for (uint32_t i = lane; i < (tent + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
+    __syncwarp();
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(win);
+    const uint32_t sh = (lane & 3) * 8;
+    for (uint32_t base = p0; base < p1; base += 32) {
+        const uint32_t p = base + lane;
+        const uint32_t *pw = ww + (p >> 2);
+        const uint32_t v = __funnelshift_r(pw[0], pw[1], sh);
+        const bool ins = p < p1 && p + 4 <= n && !qzm_run_interior(v, win[(int)p - 1], p);
+        const uint32_t h = qzm_hash(v, tent);
+        const uint32_t peers = __match_any_sync(QZM_FULL, ins ? h : tent + lane);
+        if (ins && (peers >> lane) == 1u) table[h] = (uint16_t)p;      /* the highest lane of equal hashes: the most recent position */
+        __syncwarp();
+    }
+}
+
+/* tables[k] (k < npieces, `stride` u16 apart) <- the most recent position of every hash in pieces 0..k-1.  Called by all
+ * `nthreads` threads of the group between two group barriers; tables hold the prepass result on entry. */
+__device__ __forceinline__ void qzm_seed_tables(uint16_t *tables, uint32_t stride, uint32_t npieces, uint32_t tent, uint32_t tid, uint32_t nthreads)
+{
+    const uint32_t nw = (tent + 1) / 2, sw = stride / 2;
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(tables);
+    for (uint32_t i = tid; i < nw; i += nthreads) {
+        uint32_t carry = 0xffffffffu;
+        for (uint32_t k = 0; k < npieces; k++) {
+            const uint32_t w = t32[k * sw + i];
+            t32[k * sw + i] = carry;
+            const uint32_t lo = (w & 0xffffu) != 0xffffu ? w & 0xffffu : carry & 0xffffu;
+            const uint32_t hi = (w >> 16) != 0xffffu ? w & 0xffff0000u : carry & 0xffff0000u;
+            carry = lo | hi;
+        }
+    }
+}
+
+/* ---- token sinks ---- */
+/* deflate: 16-bit slots in an L2-resident scratch.  literal -> its byte; match -> 0x4000 | (len - 3), then 0x8000 | (dist - 1).
+ * Every slot is coded on its own (a length slot and a distance slot each carry one code and its extra bits), so histogram,
+ * bit count and emission run over slots, not over tokens. */
+#define QZ_SLOT_LEN 0x4000u
+#define QZ_SLOT_DIST 0x8000u
+struct QzmDeflateSink {
+    uint16_t *slots; uint32_t nslots; uint64_t pol;
+    static constexpr bool kLz4 = false;
+    static constexpr uint32_t kMinMatch = 4, kMaxMatch = 258, kMaxDist = 32768;
+    __device__ __forceinline__ void put(uint32_t tokmask, uint32_t matchmask, uint32_t lane, uint32_t lt, uint32_t p, uint32_t v, uint32_t L, uint32_t dist)
+    {
+        if ((tokmask >> lane) & 1) {
+            uint16_t *o = slots + nslots + __popc(tokmask & lt) + __popc(matchmask & lt);
+            if ((matchmask >> lane) & 1) { tok16_st(o, (uint16_t)(QZ_SLOT_LEN | (L - 3)), pol); tok16_st(o + 1, (uint16_t)(QZ_SLOT_DIST | (dist - 1)), pol); }
+            else tok16_st(o, (uint16_t)(v & 0xff), pol);
+        }
+        nslots += __popc(tokmask) + __popc(matchmask);
+    }
+};
+/* LZ4: one record of two words per match: position | length << 16, distance (positions and lengths fit 16 bits: a window is at
+ * most 64 KiB and a match ends inside its piece) */
+struct QzmLz4Sink {
+    uint32_t *recs; uint32_t nrec;
+    static constexpr bool kLz4 = true;
+    static constexpr uint32_t kMinMatch = 5, kMaxMatch = 65535, kMaxDist = 65535;
+    __device__ __forceinline__ void put(uint32_t, uint32_t matchmask, uint32_t lane, uint32_t lt, uint32_t p, uint32_t, uint32_t L, uint32_t dist)
+    {
+        if ((matchmask >> lane) & 1) {
+            uint32_t *o = recs + 2 * (nrec + __popc(matchmask & lt));
+            o[0] = p | (L << 16); o[1] = dist;
+        }
+        nrec += __popc(matchmask);
+    }
+};
+
+/* Greedy LZ77 parse of [p0, p1) of the window `win` (n bytes of data, pads as above).  `table` is seeded (or cleared, for a
+ * private window); p0 is a multiple of 32.  LZ4 sinks: matches start at or before n - 12 and end at or before n - 5
+ * (block end rules), and never inside the last piece's tail. */
+template <class Sink>
+__device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, uint32_t p0, uint32_t p1, uint16_t *table, uint32_t tent, Sink &sink, uint32_t lane)
+{
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(win);
+    const uint32_t sh = (lane & 3) * 8, lt = qz_lanemask_lt();
+    const uint32_t mstart_lim = Sink::kLz4 ? (n >= 13 ? n - 12 : 0u) : n;        /* LZ4: last position a match may start at */
+    const uint32_t mend = Sink::kLz4 ? min(p1, n >= 5 ? n - 5 : 0u) : p1;         /* matches end at or before */
+    uint32_t entry = 0;                 /* first position of the tile not covered by a match running in from the left */
+    for (uint32_t base = p0; base < p1; base += 32) {
+        if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
+        const uint32_t p = base + lane;
+        const uint32_t *pw = ww + (p >> 2);
+        const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2], w3 = pw[3];
+        const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+        const uint32_t prevb = win[(int)p - 1];
+        const bool can = p < p1 && p + 4 <= n;
+        const bool ins = can && !qzm_run_interior(v, prevb, p);
+        const uint32_t h = qzm_hash(v, tent);
+        const uint32_t peers = __match_any_sync(QZM_FULL, can ? h : tent + lane);
+        const uint32_t insmask = __ballot_sync(QZM_FULL, ins);
+        const uint32_t t = can ? table[h] : QZM_NONE;
+        __syncwarp();
+        if (ins && ((peers & insmask) >> lane) == 1u) table[h] = (uint16_t)p;
+        __syncwarp();
+        const uint32_t lower = peers & lt;
+        const uint32_t cand = lower ? base + 31 - __clz(lower) : t;
+        /* candidate bytes are fetched unconditionally (position 0 when there is none): no divergent verify branches */
+        const bool has = can && cand != QZM_NONE && p - cand <= Sink::kMaxDist && p <= mstart_lim;
+        const uint32_t c = has ? cand : 0u, csh = (c & 3) * 8;
+        const uint32_t *cw = ww + (c >> 2);
+        const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
+        const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
+        uint32_t L = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : x2 ? 8 + ((__ffs(x2) - 1) >> 3) : QZM_LANE_CAP;
+        const uint32_t room = mend > p ? mend - p : 0u;          /* bytes a match starting here may cover */
+        L = min(L, min(Sink::kMaxMatch, room));
+        if (!has || x0 || L < Sink::kMinMatch) L = 0;
+        /* bytes in front of position and candidate that agree (at most 4, never in front of the window) */
+        uint32_t back = 0;
+        if (L) { const uint32_t xb = qzm_ld32u(ww - 1, p) ^ qzm_ld32u(ww - 1, c); back = min(xb ? (uint32_t)__clz(xb) >> 3 : 4u, c); }
+
+        /* greedy parse by pointer doubling: R = lanes visited from this lane on, N = where that walk leaves the tile */
+        uint32_t R = 1u << lane, N = lane + (L ? L : 1u);
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint32_t Rn = __shfl_sync(QZM_FULL, R, N & 31), Nn = __shfl_sync(QZM_FULL, N, N & 31);
+            if (N < 32) { R |= Rn; N = Nn; }
+        }
+        const uint32_t longmask = __ballot_sync(QZM_FULL, L >= QZM_LANE_CAP && L < min(Sink::kMaxMatch, room));
+        uint32_t tokmask = 0, cur = entry, leave;
+        for (;;) {
+            const uint32_t Rc = __shfl_sync(QZM_FULL, R, cur);
+            const uint32_t U = Rc & longmask;
+            if (!U) { tokmask |= Rc; leave = __shfl_sync(QZM_FULL, N, cur); break; }
+            /* the walk is right up to its first match that reached the lane cap: the warp finishes that one */
+            const uint32_t m = __ffs(U) - 1;
+            tokmask |= Rc & (QZM_FULL >> (31 - m));
+            const uint32_t pm = base + m, cm = __shfl_sync(QZM_FULL, cand, m);
+            const uint32_t mx = min(Sink::kMaxMatch, mend - pm);
+            uint32_t Lm = QZM_LANE_CAP;
+            while (Lm < mx) {
+                const uint32_t kk = Lm + lane;
+                const bool eq = kk < mx && win[pm + kk] == win[cm + kk];
+                const uint32_t bal = __ballot_sync(QZM_FULL, eq);
+                if (bal == QZM_FULL) { Lm += 32; continue; }
+                Lm += __ffs(~bal) - 1; break;
+            }
+            Lm = min(Lm, mx);
+            if (lane == m) L = Lm;
+            cur = m + Lm;
+            if (cur >= 32) { leave = cur; break; }
+        }
+        tokmask &= __ballot_sync(QZM_FULL, p < p1);
+        uint32_t matchmask = tokmask & __ballot_sync(QZM_FULL, L != 0);
+        /* a selected match takes over the literals right in front of it while the bytes agree */
+        {
+            const uint32_t lit = tokmask & ~matchmask;
+            const uint32_t below = lane ? min(lane, (uint32_t)__clz(~lit << (32 - lane))) : 0u;     /* literal tokens directly below this lane */
+            const uint32_t ext = ((matchmask >> lane) & 1) ? min(min(back, below), Sink::kMaxMatch - L) : 0u;
+            const uint32_t kill = __reduce_or_sync(QZM_FULL, ext ? ((1u << lane) - (1u << (lane - ext))) : 0u);
+            tokmask &= ~kill;
+            sink.put(tokmask, matchmask, lane, lt, p - ext, v, L + ext, p - cand);
+        }
+        entry = leave - 32;
+    }
+    __syncwarp();
+}
+#endif

@@ -14,6 +14,7 @@ static inline uint64_t l2_policy_stream() { return 0; }
 static inline uint32_t tok_ld(const uint32_t *a, uint64_t) { return *a; }
 static inline uint4 tok_ld4(const uint32_t *a, uint64_t) { return *reinterpret_cast<const uint4 *>(a); }
 static inline void tok_st(uint32_t *a, uint32_t v, uint64_t) { *a = v; }
+static inline void tok16_st(uint16_t *a, uint16_t v, uint64_t) { *a = v; }
 static inline uint4 stream_ld16(const uint4 *a, uint64_t) { return *a; }
 static inline void slot_st(uint32_t *a, uint32_t v) { *a = v; }
 #else
@@ -48,6 +49,10 @@ __device__ __forceinline__ uint4 tok_ld4(const uint32_t *a, uint64_t pol)
 __device__ __forceinline__ void tok_st(uint32_t *a, uint32_t v, uint64_t pol)
 {
     asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tok16_st(uint16_t *a, uint16_t v, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(a), "h"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint4 stream_ld16(const uint4 *a, uint64_t pol)
 {

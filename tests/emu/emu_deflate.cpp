@@ -56,7 +56,7 @@ extern "C" void emu_job_setup(QzbCompressJob *job, EmuCompressBuffers *b, int fm
     job->piece_len = (uint32_t *)(m + o_plen); job->piece_crc = (uint32_t *)(m + o_pcrc);
     job->chunk_total = (uint32_t *)(m + o_tot); job->chunk_cksum = (uint32_t *)(m + o_ck);
     job->chunk_off = (uint64_t *)(m + o_off); job->ticket = (uint32_t *)(m + o_ticket);
-    {   /* group kernel: blocks of QZ_GROUP pieces (set for every job; the per-piece kernel ignores it) */
+    {   /* window kernel: windows of QZ_GROUP pieces (set for every job; the per-piece kernel ignores it) */
         const uint32_t gpc = job->pieces_per_chunk / QZ_GROUP;
         job->ngroups = (job->pieces_per_chunk % QZ_GROUP == 0 && len) ? (job->nchunks - 1) * gpc + (last_pieces + QZ_GROUP - 1) / QZ_GROUP : 0u;
     }
@@ -78,31 +78,28 @@ extern "C" long emu_frame(const QzbCompressJob *jobp, uint32_t *chunk_cksum_out)
     return (long)job.chunk_off[fit];
 }
 
-/* One batch through the deflate kernels.  Geometry (piece size, hash bits, warps and piece buffers per CTA, CTAs)
- * is the caller's.  Returns bytes produced, or -1 for an unsupported geometry.
- * group != 0: the group kernel (one deflate block per 8 pieces) instead of the per-piece kernel. */
+/* One batch through the deflate kernels.  Geometry is the caller's.  Returns bytes produced, -1 for an unsupported geometry,
+ * -2 when a kernel wrote past its scratch.
+ * window == 0: per-piece kernel (piece size, hash bits, warps and piece buffers per CTA, CTAs);
+ * window != 0: window kernel (one deflate block per 64 KiB window): warps / 8 groups per CTA share `nbuf` units whose
+ *              tables have `hb` entries each when hb >= 256, else 2^hb. */
 extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman,
-                                     int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int group)
+                                     int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int window)
 {
     if (warps < 1 || warps > 32 || nbuf < 1 || nbuf > warps || grid < 1) return -1;
     QzbCompressJob job; EmuCompressBuffers b;
     emu_job_setup(&job, &b, fmt, src, len, chunk_sz, last, static_huffman, piece_log2, grid * warps, dst, cap);
     size_t smem;
     std::function<void()> body;
-    if (group) {
-        const int gw = QZ_GROUP;
-        if (!job.ngroups || warps % gw || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13 || nbuf < 1) return -1;
-        EmuCompressBuffers b2;
-        emu_job_setup(&job, &b2, fmt, src, len, chunk_sz, last, static_huffman, piece_log2, grid * warps * (QZ_GROUP / gw), dst, cap);
-        smem = (hb == 9 ? sizeof(GroupWarpPriv<9>) : ((size_t)2 << hb)) * warps + sizeof(PieceBuf<13>) * nbuf;
-        if (gw == 8 && hb == 9) body = [&] { qzb_deflate_groups_kernel<13, 9, 8>(job, nbuf); };
-        else if (gw == 8 && hb == 10) body = [&] { qzb_deflate_groups_kernel<13, 10, 8>(job, nbuf); };
-        else if (gw == 8 && hb == 11) body = [&] { qzb_deflate_groups_kernel<13, 11, 8>(job, nbuf); };
-        else if (gw == 8 && hb == 12) body = [&] { qzb_deflate_groups_kernel<13, 12, 8>(job, nbuf); };
-        else return -1;
-        emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
+    if (window) {
+        const int groups = warps / QZ_GROUP, nunits = nbuf > groups ? groups : nbuf;
+        if (!job.ngroups || warps % QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13) return -1;
+        job.tent = hb >= 256 ? (uint32_t)hb : 1u << hb;
+        smem = (size_t)nunits * window_unit_bytes(job.tent) + (size_t)groups * sizeof(BlockCoder);
+        if (smem > 227 * 1024) return -1;
+        emu::launch((unsigned)grid, (unsigned)warps * 32, smem, [&] { qzb_deflate_window_kernel(job, nunits); });
         const long n = emu_frame(&job, chunk_cksum_out);
-        return emu_canaries_ok(b2) ? n : -2;
+        return emu_canaries_ok(b) ? n : -2;
     }
     if (piece_log2 == 13 && hb == 11) { smem = sizeof(WarpPriv<11>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 11>(job, nbuf); }; }
     else if (piece_log2 == 13 && hb == 12) { smem = sizeof(WarpPriv<12>) * warps + sizeof(PieceBuf<13>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<13, 12>(job, nbuf); }; }
@@ -110,24 +107,6 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     else if (piece_log2 == 14 && hb == 13) { smem = sizeof(WarpPriv<13>) * warps + sizeof(PieceBuf<14>) * nbuf; body = [&] { qzb_deflate_pieces_kernel<14, 13>(job, nbuf); }; }
     else return -1;
     emu::launch((unsigned)grid, (unsigned)warps * 32, smem, body);
-    const long n = emu_frame(&job, chunk_cksum_out);
-    return emu_canaries_ok(b) ? n : -2;
-}
-
-/* experimental matcher / coder kernel (qz_deflate_split.cuh): nmatch matcher warps + nteams teams of four coder warps per CTA */
-extern "C" long emu_deflate_split(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman, int hb,
-                                  int nmatch, int nteams, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out)
-{
-    if (nmatch < 1 || nteams < 1 || nteams > 8 || nmatch + nteams * QZS_TEAM > 32 || grid < 1 || (hb != 10 && hb != 11)) return -1;
-    QzbCompressJob job; EmuCompressBuffers b;
-    emu_job_setup(&job, &b, fmt, src, len, chunk_sz, last, static_huffman, 13, 1, dst, cap);
-    if (!job.ngroups) return -1;
-    b.tok.assign((size_t)grid * QZS_SLOTS * QZ_GROUP * QZB_TOK_STRIDE(1 << 13), 0xEEEEEEEEu);
-    job.tok_scratch = b.tok.data();
-    const size_t smem = qzs_smem_bytes(hb, nmatch, nteams);
-    const unsigned block = (unsigned)(nmatch + nteams * QZS_TEAM) * 32;
-    if (hb == 10) emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 10>(job, nmatch, nteams); });
-    else emu::launch((unsigned)grid, block, smem, [&] { qzb_deflate_split_kernel<13, 11>(job, nmatch, nteams); });
     const long n = emu_frame(&job, chunk_cksum_out);
     return emu_canaries_ok(b) ? n : -2;
 }

@@ -145,8 +145,8 @@ def test_deflate_output_does_not_depend_on_geometry(emu, port):
     b, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=7, nbuf=2, grid=1)
     c, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=20, nbuf=17, grid=3)
     assert a == b == c
-    g1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, group=1, hb=10)
-    g2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=17, grid=1, group=1, hb=10)
+    g1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=1, grid=2, window=1, hb=10)
+    g2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=2, grid=1, window=1, hb=10)
     assert g1 == g2
     assert port.decompress(g1, E.FMT_GZIP_EXT, len(data) + 16) == data
 
@@ -321,7 +321,7 @@ def test_lz4_decodes_oracle_frames_and_rejects_corruption(emu, port):
     assert res[0].status == E.ST_CKSUM and res[1].status == E.ST_OK
 
 
-# ------------------------------------------------------------------ group kernel: one deflate block per 8 pieces
+# ------------------------------------------------------------------ window kernel: 64 KiB windows in shared memory, one deflate block per window
 
 def decode_any(port, blob, fmt, n):
     if fmt != E.FMT_ZLIB:
@@ -340,9 +340,9 @@ def decode_any(port, blob, fmt, n):
                                          ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
                                          ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
 @pytest.mark.parametrize("hb", [10, 11])
-def test_group_deflate_round_trip(emu, port, fmt, name, make, n, hb):
+def test_window_deflate_round_trip(emu, port, fmt, name, make, n, hb):
     data = make(n)
-    blob, cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1, hb=hb)
+    blob, cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, window=1, hb=hb)
     assert decode_any(port, blob, fmt, n) == data
     want = zlib.adler32 if fmt == E.FMT_ZLIB else zlib.crc32
     assert cks == [want(data[i:i + 65536]) for i in range(0, n, 65536)]
@@ -352,20 +352,20 @@ def test_group_deflate_round_trip(emu, port, fmt, name, make, n, hb):
 
 
 @pytest.mark.parametrize("chunk", [65536, 131072, 524288])
-@pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=16, grid=1), dict(warps=24, nbuf=15, grid=1), dict(warps=8, nbuf=8, grid=1, hb=12),
-                                  dict(warps=24, nbuf=20, grid=1, hb=10), dict(warps=8, nbuf=5, grid=2, hb=10), dict(warps=32, nbuf=19, grid=1, hb=10), dict(warps=32, nbuf=22, grid=1, hb=9), dict(warps=8, nbuf=2, grid=2, hb=9)])
-def test_group_deflate_geometries_and_chunks(emu, port, chunk, geom):
+@pytest.mark.parametrize("geom", [dict(warps=8, nbuf=1, grid=3), dict(warps=16, nbuf=2, grid=1), dict(warps=24, nbuf=2, grid=1), dict(warps=8, nbuf=1, grid=1, hb=12),
+                                  dict(warps=24, nbuf=2, grid=1, hb=10), dict(warps=16, nbuf=1, grid=2, hb=10), dict(warps=32, nbuf=2, grid=1, hb=11), dict(warps=16, nbuf=2, grid=1, hb=2800), dict(warps=8, nbuf=1, grid=2, hb=9)])
+def test_window_deflate_geometries_and_chunks(emu, port, chunk, geom):
     data = sil(chunk + chunk // 2 + 4321)
-    blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, **dict(dict(group=1), **geom))
+    blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, **dict(dict(window=1), **geom))
     assert port.decompress(blob, E.FMT_GZIP_EXT, len(data) + 16) == data
     assert cks == [zlib.crc32(data[i:i + chunk]) for i in range(0, len(data), chunk)]
     members = walk_gzip(blob, ext=True)
     assert [m[4] for m in members] == [len(data[i:i + chunk]) for i in range(0, len(data), chunk)]
 
 
-def test_group_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
+def test_window_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
     data = sil(1 << 20)
-    grouped, _ = emu.deflate(data, E.FMT_RAW, warps=8, nbuf=4, grid=2, group=1)
+    grouped, _ = emu.deflate(data, E.FMT_RAW, warps=8, nbuf=4, grid=2, window=1)
     pieces, _ = emu.deflate(data, E.FMT_RAW)
     assert inflate_raw(grouped)[0] == data
     assert len(grouped) < len(pieces)                  # 7 of 8 block headers and flush markers are gone
@@ -375,69 +375,28 @@ def test_group_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
     assert grouped.count(b"\x00\x00\xff\xff") < pieces.count(b"\x00\x00\xff\xff") // 4
 
 
-def test_group_deflate_static_and_not_last(emu):
+def test_window_deflate_static_and_not_last(emu):
     data = sil(100000)
-    blob, _ = emu.deflate(data, E.FMT_RAW, static=1, warps=8, nbuf=2, grid=1, group=1)
+    blob, _ = emu.deflate(data, E.FMT_RAW, static=1, warps=8, nbuf=2, grid=1, window=1)
     out, eof, _ = inflate_raw(blob)
     assert out == data and eof and (blob[0] >> 1) & 3 in (0, 1)
-    blob, _ = emu.deflate(data, E.FMT_RAW, last=0, warps=8, nbuf=2, grid=1, group=1)
+    blob, _ = emu.deflate(data, E.FMT_RAW, last=0, warps=8, nbuf=2, grid=1, window=1)
     out, eof, used = inflate_raw(blob)
     assert out == data and not eof and used == len(blob) and blob[-4:] == b"\x00\x00\xff\xff"
 
 
-def test_group_deflate_dest_too_small_keeps_whole_chunks(emu):
+def test_window_deflate_dest_too_small_keeps_whole_chunks(emu):
     data = sil(200000)
-    full, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, group=1)
+    full, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, window=1)
     members = walk_gzip(full, ext=True)
     two = members[2][0] - 24
-    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100, warps=8, nbuf=3, grid=2, group=1)
+    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100, warps=8, nbuf=3, grid=2, window=1)
     assert part == full[:two]
 
 
-def test_group_streams_decode_with_our_inflate(emu):
+def test_window_streams_decode_with_our_inflate(emu):
     data = sil(200000)
-    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, group=1)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, window=1)
     members = [one_member(ln, isize, crc, src_off=off, dst_off=i * 65536) for i, (off, ln, crc, isize, _) in enumerate(walk_gzip(blob, ext=True))]
     out, res = emu.decode(E.FMT_GZIP_EXT, blob, members, len(data))
     assert [r.status for r in res] == [E.ST_OK] * len(members) and out == data
-
-
-# ------------------------------------------------------------------ experimental matcher / coder kernel (qz_deflate_split.cuh)
-# Compiled only into A/B builds of the product (-DQZ_SPLIT_KERNEL, QZB200_GROUP=2); the emulator library always carries it.
-
-@pytest.mark.parametrize("fmt", [E.FMT_4B, E.FMT_GZIP, E.FMT_GZIP_EXT, E.FMT_RAW, E.FMT_ZLIB])
-@pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000),
-                                         ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
-                                         ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
-def test_split_deflate_same_stream_as_group_kernel(emu, port, fmt, name, make, n):
-    data = make(n)
-    blob, cks = emu.deflate_split(data, fmt, nmatch=5, nteams=2, grid=2)
-    ref, ref_cks = emu.deflate(data, fmt, warps=8, nbuf=3, grid=2, group=1, hb=10)
-    assert blob == ref and cks == ref_cks                  # same blocks, whoever matched and coded them
-    assert decode_any(port, blob, fmt, n) == data
-
-
-@pytest.mark.parametrize("chunk", [65536, 131072, 524288])
-@pytest.mark.parametrize("geom", [dict(nmatch=1, nteams=1, grid=1), dict(nmatch=19, nteams=3, grid=1), dict(nmatch=3, nteams=1, grid=4),
-                                  dict(nmatch=12, nteams=5, grid=2), dict(nmatch=7, nteams=2, grid=2, hb=11)])
-def test_split_deflate_geometries_and_chunks(emu, port, chunk, geom):
-    data = sil(chunk + chunk // 2 + 4321)
-    blob, cks = emu.deflate_split(data, E.FMT_GZIP_EXT, chunk=chunk, **geom)
-    assert port.decompress(blob, E.FMT_GZIP_EXT, len(data) + 16) == data
-    assert cks == [zlib.crc32(data[i:i + chunk]) for i in range(0, len(data), chunk)]
-    ref, _ = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, warps=8, nbuf=3, grid=2, group=1, hb=geom.get("hb", 10))
-    assert blob == ref
-
-
-def test_split_deflate_static_not_last_and_short_dest(emu):
-    data = sil(200000)
-    blob, _ = emu.deflate_split(data, E.FMT_RAW, static=1)
-    out, eof, _ = inflate_raw(blob)
-    assert out == data and eof and (blob[0] >> 1) & 3 in (0, 1)
-    blob, _ = emu.deflate_split(data, E.FMT_RAW, last=0)
-    out, eof, used = inflate_raw(blob)
-    assert out == data and not eof and used == len(blob) and blob[-4:] == b"\x00\x00\xff\xff"
-    full, _ = emu.deflate_split(data, E.FMT_GZIP_EXT)
-    two = walk_gzip(full, ext=True)[2][0] - 24
-    part, _ = emu.deflate_split(data, E.FMT_GZIP_EXT, cap=two + 100)
-    assert part == full[:two]

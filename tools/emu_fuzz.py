@@ -1,5 +1,4 @@
-"""Fuzz the kernels' logic on the SIMT emulator: random structured inputs through the deflate kernels (per piece, group,
-experimental split) and LZ4, decoded by the oracle port / zlib and by our own inflate kernel.  Test infrastructure; run
+"""Fuzz the kernels' logic on the SIMT emulator: random structured inputs through the deflate kernels (per piece, window) and LZ4, decoded by the oracle port / zlib and by our own inflate kernel.  Test infrastructure; run
 by hand:  python tools/emu_fuzz.py [seconds] [seed]"""
 import os, random, struct, sys, time, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -54,12 +53,10 @@ while time.time() - t0 < budget:
     what = rng.random()
     tag = None
     try:
-        if what < 0.35 and n:
-            tag = "group"
-            blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), group=1, hb=rng.choice([9, 10, 11]), warps=rng.choice([8, 16, 32]), nbuf=rng.randint(1, 8), grid=rng.randint(1, 3))
-        elif what < 0.55 and n:
-            tag = "split"
-            blob, cks = emu.deflate_split(data, fmt, chunk=chunk, static=int(static), hb=rng.choice([10, 11]), nmatch=rng.randint(1, 12), nteams=rng.randint(1, 3), grid=rng.randint(1, 3))
+        if what < 0.55 and n:
+            tag = "window"
+            hb = rng.choice([9, 10, 11, 700, 2800])
+            blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=1, hb=hb, warps=rng.choice([8, 16] if hb == 2800 else [8, 16, 32]), nbuf=rng.randint(1, 2), grid=rng.randint(1, 3))
         elif what < 0.85:
             tag = "piece"
             chunk = rng.choice([1024, 4096, 16384, 65536, 131072])

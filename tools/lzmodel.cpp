@@ -26,6 +26,14 @@ struct Params {
     int winner = 1;        // 1: highest p in window wins table slot, 0: lowest
     int lazy = 0;
     int ways = 1;          // bucket ways
+    int scheme = 1;        // 2: chunk-wide window, per-piece tables seeded with the last occurrences in earlier pieces
+    int pp = 8192;         // scheme 2: piece (tokenised independently, matches cut at its end)
+    int tile = 1;          // scheme 2: 0 table only, 1 in-tile candidate preferred, 2 best of both
+    int maxd = 32768;
+    int lz4 = 0;
+    int tent = 0;          // scheme 2: table entries when not a power of two (multiply-shift range reduction)
+    int nir = 0;           // scheme 2: positions inside a byte run (p-1..p+3 equal) are not inserted
+    int bext = 0;          // backward extension of a selected match over the literals before it (inside the tile if 1, anywhere if 2)
 };
 
 static const uint16_t LBASE[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
@@ -127,6 +135,7 @@ static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); re
 static inline uint32_t hashf(const uint8_t *p, const Params &P)
 {
     uint32_t v = rd32(p); if (P.hbytes == 3) v &= 0xffffff;
+    if (P.tent) return (uint32_t)(((uint64_t)(v * 2654435761u) * (uint32_t)P.tent) >> 32);
     return (v * 2654435761u) >> (32 - P.hb);
 }
 static inline int mlen(const uint8_t *a, const uint8_t *b, int maxl) { int l = 0; while (l < maxl && a[l] == b[l]) l++; return l; }
@@ -179,33 +188,121 @@ static long model_piece(const uint8_t *src, int n, const Params &P, long *ntok_o
     return bits;
 }
 
+
+// scheme 2: the chunk (<= 64 KiB) sits whole in shared memory; piece k (pp bytes) has its own table of 2^hb entries, seeded
+// before matching with the most recent occurrence of every hash in pieces < k; 32 positions per step look up, then insert.
+static long lz4_size(const std::vector<Tok> &toks, int n);
+static long model_chunk2(const uint8_t *src, int n, const Params &P, long *ntok_out)
+{
+    std::vector<char> Sel(n + 1, 0);
+    const int np = (n + P.pp - 1) / P.pp, TS = P.tent ? P.tent : 1 << P.hb, WY = P.ways;
+    std::vector<int> L(n, 0), D(n, 0);
+    auto ins = [&](std::vector<int32_t> &T, uint32_t h, int p) { if (P.nir && p > 0 && rd32(src + p) == rd32(src + p - 1)) return; for (int w = WY - 1; w > 0; w--) T[h * WY + w] = T[h * WY + w - 1]; T[h * WY] = p; };
+    std::vector<int32_t> carry(TS * WY, -1);
+    for (int k = 0; k < np; k++) {
+        std::vector<int32_t> T = carry;
+        for (int p = k * P.pp; p < std::min(n, (k + 1) * P.pp); p++) if (p + 4 <= n) ins(carry, hashf(src + p, P), p);
+        const int e = std::min(n, (k + 1) * P.pp);
+        int entry = k * P.pp, anchor = k * P.pp;
+        for (int w0 = k * P.pp; w0 < e; w0 += 32) {
+            const int w1 = std::min(e, w0 + 32);
+            if (entry >= w1) continue;            // tile inside a running match: skipped, not indexed
+            for (int p = w0; p < w1; p++) {
+                const int maxl = std::min(258, e - p); int bl = 0, bd = 0;
+                if (p + 4 <= n && maxl >= P.minm) {
+                    const uint32_t h = hashf(src + p, P);
+                    int ct = -1, cq = -1;
+                    int lbest = -1; for (int w = 0; w < WY; w++) { const int c = T[h * WY + w]; if (c >= 0 && p - c <= P.maxd) { int l = mlen(src + c, src + p, maxl); if (l > lbest) { lbest = l; ct = c; } } }
+                    if (P.tile) for (int q = p - 1; q >= w0; q--) if (rd32(src + q) == rd32(src + p)) { cq = q; break; }
+                    int lt = ct >= 0 ? mlen(src + ct, src + p, maxl) : 0, lq = cq >= 0 ? mlen(src + cq, src + p, maxl) : 0;
+                    if (P.tile == 1) { if (cq >= 0) { bl = lq; bd = p - cq; } else { bl = lt; bd = p - ct; } }
+                    else { if (lq >= lt && cq >= 0) { bl = lq; bd = p - cq; } else { bl = lt; bd = p - ct; } }
+                    if (bl < P.minm) bl = 0;
+                }
+                L[p] = bl; D[p] = bd;
+            }
+            for (int p = w0; p < w1; p++) if (p + 4 <= n) ins(T, hashf(src + p, P), p);
+            // greedy selection inside the tile
+            int p = std::max(entry, w0);
+            while (p < w1) {
+                if (L[p]) {
+                    int q = p;
+                    if (P.bext) { const int lo = P.bext == 1 ? std::max(anchor, w0) : anchor; const int d = D[p];
+                        while (q > lo && L[q] < 258 && q - 1 - d >= 0 && src[q - 1] == src[q - 1 - d]) { L[q - 1] = L[q] + 1; D[q - 1] = d; L[q] = 0; q--; } }
+                    p = q + L[q]; anchor = p;
+                } else p++;
+            }
+            entry = p;
+        }
+    }
+    std::vector<Tok> toks;
+    for (int k = 0; k < np; k++) {
+        const int e = std::min(n, (k + 1) * P.pp);
+        int p = k * P.pp;
+        while (p < e) { if (L[p]) { toks.push_back({L[p], D[p], 0}); p += L[p]; } else { toks.push_back({0, 0, src[p]}); p++; } }
+    }
+    if (ntok_out) *ntok_out += toks.size();
+    if (P.lz4) return 8 * lz4_size(toks, n);
+    return encode_block_bits(toks, n);
+}
+static long lz4_size(const std::vector<Tok> &toks, int n)
+{
+    // LZ4 block: token byte, literal length ext, literals, offset(2), match length ext; last 5 bytes literal, last match starts >= 12 before end
+    std::vector<Tok> mt;
+    for (auto &t : toks) { if (t.len && !mt.empty() && mt.back().len && mt.back().dist == t.dist) mt.back().len += t.len; else mt.push_back(t); }
+    long sz = 0; int lit = 0, pos = 0;
+    for (auto &t : mt) {
+        if (t.len == 0 || t.len < 4 || pos + t.len > n - 5 || pos > n - 12) { int l = t.len ? t.len : 1; lit += l; pos += l; continue; }
+        sz += 1 + lit + (lit >= 15 ? 1 + (lit - 15) / 255 : 0) + 2 + (t.len - 4 >= 15 ? 1 + (t.len - 4 - 15) / 255 : 0);
+        lit = 0; pos += t.len;
+    }
+    sz += 1 + lit + (lit >= 15 ? 1 + (lit - 15) / 255 : 0);
+    return sz + 4;
+}
+
 int main(int argc, char **argv)
 {
-    Params P; size_t total = 24u << 20; int kind = 1; const char *only = 0;
+    Params P; size_t total = 24u << 20; int kind = 1; const char *only = 0; const char *file = 0;
     for (int i = 1; i < argc; i++) {
         auto eq = strchr(argv[i], '='); if (!eq) continue; int v = atoi(eq + 1); std::string k(argv[i], eq - argv[i]);
         if (k == "piece") P.piece = v; else if (k == "sub") P.sub = v; else if (k == "W") P.W = v; else if (k == "hb") P.hb = v;
         else if (k == "hbytes") P.hbytes = v; else if (k == "minm") P.minm = v; else if (k == "S") P.S = v; else if (k == "rle") P.rle = v;
         else if (k == "warp") P.warp = v; else if (k == "winner") P.winner = v; else if (k == "mb") total = (size_t)v << 20; else if (k == "kind") kind = v;
         else if (k == "lazy") P.lazy = v; else if (k == "ways") P.ways = v; else if (k == "only") only = eq + 1;
+        else if (k == "scheme") P.scheme = v; else if (k == "pp") P.pp = v; else if (k == "tile") P.tile = v; else if (k == "maxd") P.maxd = v;
+        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
     }
-    void *h = dlopen("harness/libqzcorpus.so", RTLD_NOW); if (!h) { fprintf(stderr, "no corpus lib\n"); return 1; }
-    auto fill = (int (*)(int, uint64_t, uint64_t, uint8_t *, size_t, int))dlsym(h, "qzcorpus_fill");
-    std::vector<uint8_t> buf(total); fill(kind, kind ? 0x51CE51A : 1, 0, buf.data(), total, 8);
+    std::vector<uint8_t> buf;
+    if (file) {
+        FILE *f = fopen(file, "rb"); if (!f) { perror(file); return 1; }
+        fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET); if ((size_t)sz < total) total = sz;
+        buf.resize(total); if (fread(buf.data(), 1, total, f) != total) return 1; fclose(f); kind = 0;
+    } else {
+        void *h = dlopen("harness/libqzcorpus.so", RTLD_NOW); if (!h) { fprintf(stderr, "no corpus lib\n"); return 1; }
+        auto fill = (int (*)(int, uint64_t, uint64_t, uint8_t *, size_t, int))dlsym(h, "qzcorpus_fill");
+        buf.resize(total); fill(kind, kind ? 0x51CE51A : 1, 0, buf.data(), total, 8);
+    }
+    int (*lz4c)(const char *, char *, int, int) = 0;
+    if (P.lz4) { void *h = dlopen("liblz4.so.1", RTLD_NOW); if (h) lz4c = (int (*)(const char *, char *, int, int))dlsym(h, "LZ4_compress_default"); if (!lz4c) { fprintf(stderr, "no liblz4\n"); return 1; } }
     const char *CYC = "TXBETXBTZTXR";
     long zl_tot = 0, my_tot = 0; long zl_c[256] = {0}, my_c[256] = {0}, nb_c[256] = {0}, ntok = 0;
     std::vector<uint8_t> tmp(80000);
     for (size_t off = 0; off < total; off += 65536) {
         int n = (int)std::min<size_t>(65536, total - off); char cls = kind ? CYC[(off >> 20) % 12] : 'r';
         if (only && !strchr(only, cls)) continue;
-        z_stream z; memset(&z, 0, sizeof z); deflateInit2(&z, 1, Z_DEFLATED, -15, 9, 0);
-        z.next_in = buf.data() + off; z.avail_in = n; z.next_out = tmp.data(); z.avail_out = tmp.size(); deflate(&z, Z_FINISH);
-        long zb = z.total_out; deflateEnd(&z);
+        long zb;
+        if (P.lz4) zb = lz4c((const char *)buf.data() + off, (char *)tmp.data(), n, (int)tmp.size()) + 4;
+        else {
+            z_stream z; memset(&z, 0, sizeof z); deflateInit2(&z, 1, Z_DEFLATED, -15, 9, 0);
+            z.next_in = buf.data() + off; z.avail_in = n; z.next_out = tmp.data(); z.avail_out = tmp.size(); deflate(&z, Z_FINISH);
+            zb = z.total_out; deflateEnd(&z);
+        }
         long mb = 0;
-        for (int q = 0; q < n; q += P.piece) mb += (model_piece(buf.data() + off + q, std::min(P.piece, n - q), P, &ntok) + 7) / 8 + (q + P.piece < n ? 5 : 0);
+        if (P.scheme == 2) mb = (model_chunk2(buf.data() + off, n, P, &ntok) + 7) / 8;
+        else for (int q = 0; q < n; q += P.piece) mb += (model_piece(buf.data() + off + q, std::min(P.piece, n - q), P, &ntok) + 7) / 8 + (q + P.piece < n ? 5 : 0);
         zl_tot += zb; my_tot += mb; zl_c[(int)cls] += zb; my_c[(int)cls] += mb; nb_c[(int)cls] += n;
     }
-    for (int c = 0; c < 256; c++) if (nb_c[c]) printf("  %c zlib %.4f model %.4f  rel %+.2f%%\n", c, (double)zl_c[c] / nb_c[c], (double)my_c[c] / nb_c[c], 100.0 * ((double)my_c[c] / zl_c[c] - 1));
-    printf("TOTAL zlib %ld model %ld rel %+.2f%%  tokens/byte %.3f\n", zl_tot, my_tot, 100.0 * ((double)my_tot / zl_tot - 1), (double)ntok / total);
+    if (kind) for (int c = 0; c < 256; c++) if (nb_c[c]) printf("  %c ref %.4f model %.4f  rel %+.2f%%\n", c, (double)zl_c[c] / nb_c[c], (double)my_c[c] / nb_c[c], 100.0 * ((double)my_c[c] / zl_c[c] - 1));
+    printf("TOTAL ref %ld (%.4f) model %ld (%.4f) rel %+.2f%%  tokens/byte %.3f\n", zl_tot, (double)zl_tot / total, my_tot, (double)my_tot / total, 100.0 * ((double)my_tot / zl_tot - 1), (double)ntok / total);
     return 0;
 }
