@@ -291,7 +291,7 @@ def main():
             "kernel_ms_per_step_cuda_events": round(kernel_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
-                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": "one per 64 KiB chunk (group kernel)" if st.group_blocks else "one per 8 KiB piece", "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
+                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": "one per 64 KiB window (window kernel)" if st.group_blocks else "one per 8 KiB piece", "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
             "ratio": round(made / nbytes, 4),
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
                     "api": f"qzCompress(host pinned -> host pinned), 512 MiB per call, {T} submitting thread(s) with one session each",
@@ -299,7 +299,7 @@ def main():
                     "one_thread": {"value": round(e2e_1, 3), "ms_per_step": round(dt_1 / args.steps * 1e3, 3),
                                    "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in break_1.items()}}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "qzb_deflate_groups_kernel" if st.group_blocks else "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "qzb_deflate_window_kernel" if st.group_blocks else "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": int(per_launch_bytes), "ms_per_launch": round(per_launch_s * 1e3, 4)},
             "cpu_baseline": cpu, "clocks": clk}))

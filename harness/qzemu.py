@@ -44,7 +44,7 @@ class Emu:
         L.emu_lz4_decompress.argtypes = [V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int]
 
     def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None, window=0):
-        """-> (stream bytes, [per-chunk checksum]).  window=1: the window kernel (warps / 8 groups share nbuf units; hb >= 256 is the
+        """-> (stream bytes, [per-chunk checksum]).  window=8 / 16: the window kernel with that many warps per 64 KiB window (the CTA's groups share nbuf units; hb >= 256 is the
         number of table entries itself, else its log2)"""
         data = bytes(data)
         nch = max(1, (len(data) + chunk - 1) // chunk)

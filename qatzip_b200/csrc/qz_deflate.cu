@@ -828,24 +828,25 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Window kernel (default for hw_buff_sz >= 64 KiB): a WINDOW is 64 KiB of one chunk -- eight pieces -- and becomes ONE
- * deflate block, what the QAT engine emits for a 64 KiB request with its 32 KiB history (reference
- * src/qatzip_utils.c:270-291).  Eight warps take a window together.  Its bytes sit whole in a shared-memory UNIT next to
- * the eight warps' hash tables; the stages of qz_match.cuh (prepass, seed, match) give every position the whole window in
- * front of it as history while the eight pieces are still matched concurrently.  The unit is handed back as soon as the
- * eighth warp has matched; the group goes on from the slots in the L2 scratch: histogram into the group's block coder,
- * the leader builds the codes and writes the block header, every warp counts its slots' bits, the totals are scanned
- * through shared memory, boundary words are zeroed, and every lane packs its run at its bit offset inside the group's
- * output (the first piece's slot); the lane that codes the end-of-block slot appends the byte-aligning empty stored block
- * unless the block is final.  A CTA has more groups than units (four and two): while two groups match, two code.
- * Incompressible window -> every piece a stored block in its own slot; a window that mixes incompressible pieces with
- * compressible ones -> its pieces take turns on the block coder and become blocks of their own.
- * Warps of a group meet at a named barrier (bar.sync id, 256); groups of one CTA are independent of each other. */
-#define QZ_GROUP 8                      /* pieces per window */
-#define QZ_WINDOW (QZ_GROUP << 13)
+/* Window kernel (default for hw_buff_sz >= 64 KiB): a WINDOW is 64 KiB of one chunk and becomes ONE deflate block, what
+ * the QAT engine emits for a 64 KiB request with its 32 KiB history (reference src/qatzip_utils.c:270-291).  GW warps (16,
+ * or 8) take a window together, each a sub-piece of 64 KiB / GW.  The window's bytes sit whole in a shared-memory UNIT next
+ * to the GW warps' hash tables; the stages of qz_match.cuh (prepass, seed, match) give every position the whole window in
+ * front of it as history while the sub-pieces are still matched concurrently.  Then the group goes on from the slots in
+ * the L2 scratch: histogram into the group's block coder, the leader builds the codes and writes the block header, every
+ * warp counts its slots' bits, the totals are scanned through shared memory, boundary words are zeroed, and every lane
+ * packs its run at its bit offset inside the window's output (the slot of its first 8 KiB piece); the lane that codes the
+ * end-of-block slot appends the byte-aligning empty stored block unless the block is final.  With GW = 16 a CTA is two
+ * groups that each own a unit; with GW = 8 four groups share two units (a unit is handed back as soon as the last warp
+ * has matched: while two groups match, two code).  Incompressible window -> every 8 KiB piece a stored block in its own
+ * slot.  Warps of a group meet at a named barrier; groups of one CTA are independent of each other.
+ * The window's checksum goes to piece_crc[] of the window's first 8 KiB piece (the framing kernel combines per window). */
+#define QZ_WINDOW 65536u
+#define QZ_WINDOW_PIECES 8u             /* 8 KiB job pieces (slots, lengths) per window */
+#define QZ_WINDOW_MAX_GW 16
 struct WindowShared {
     uint32_t ticket, unit, done, btype, hb, pend;
-    uint32_t nslots[QZ_GROUP], bits[QZ_GROUP], extra[QZ_GROUP];
+    uint32_t nslots[QZ_WINDOW_MAX_GW], bits[QZ_WINDOW_MAX_GW], extra[QZ_WINDOW_MAX_GW], cksum[QZ_WINDOW_MAX_GW];
 };
 template <int NT>
 __device__ __forceinline__ void group_bar(uint32_t id)
@@ -856,47 +857,52 @@ __device__ __forceinline__ void group_bar(uint32_t id)
     __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NT) : "memory");
 #endif
 }
-/* bytes of one unit: the window with its pads, then QZ_GROUP tables of `tent` entries (rounded up to 16 bytes each) */
+/* bytes of one unit: the window with its pads, then gw tables of `tent` entries (rounded up to 16 bytes each) */
 __host__ __device__ __forceinline__ uint32_t window_table_stride(uint32_t tent) { return (tent + 8u) & ~7u; }       /* u16 entries */
-__host__ __device__ __forceinline__ uint32_t window_unit_bytes(uint32_t tent) { return QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD + QZ_GROUP * 2u * window_table_stride(tent); }
+__host__ __device__ __forceinline__ uint32_t window_unit_bytes(uint32_t tent, uint32_t gw) { return QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD + gw * 2u * window_table_stride(tent); }
 
+template <int GW>
 __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job, int nunits)
 {
+    constexpr uint32_t SUB = QZ_WINDOW / GW;                 /* bytes of a warp's sub-piece */
+    constexpr uint32_t WPP = GW / QZ_WINDOW_PIECES;          /* warps per 8 KiB job piece */
     constexpr int PIECE = 1 << 13;
-    constexpr int GW = QZ_GROUP;
     static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];
+    __shared__ uint32_t s_xafter[GW];       /* x^(8 * bytes behind sub-piece i of a full window) */
     __shared__ uint16_t s_lentab[256];
     __shared__ uint32_t s_free[1];          /* free mask of the units */
     __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW];
-    constexpr uint32_t STRIP = PIECE / 32 + 4;
+    constexpr uint32_t STRIP = SUB / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent);
+    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent, GW);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
+    if (threadIdx.x < GW) s_xafter[threadIdx.x] = qz_crc_xpow8((uint64_t)(GW - 1 - threadIdx.x) * SUB);
     if (threadIdx.x == 0) s_free[0] = (1u << nunits) - 1;
     __syncthreads();
 
     const uint32_t grp = warp / GW, wg = warp % GW, bar = 1 + grp;
+    const bool own_unit = (uint32_t)nunits >= nwarps / GW;     /* as many units as groups: no hand-over */
     WindowShared &G = s_grp[grp];
     BlockCoder &C = reinterpret_cast<BlockCoder *>(smem_raw + (size_t)nunits * unit_bytes)[grp];
     const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint16_t *slots = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(PIECE));
-    const uint32_t wpc = job.pieces_per_chunk / QZ_GROUP;     /* windows per chunk */
+    uint16_t *slots = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(SUB));
+    const uint32_t wpc = job.pieces_per_chunk / QZ_WINDOW_PIECES;     /* windows per chunk */
     const uint64_t pkeep = l2_policy_keep();
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
     for (;;) {
-        /* the leader draws the window and, if there is one, a unit for it */
+        /* the leader draws the window and, if units are shared, one of them */
         if (wg == 0) {
             uint32_t tk = 0;
             if (lane == 0) tk = atomicAdd(job.ticket, 1u);
             tk = __shfl_sync(FULL, tk, 0);
-            const uint32_t u = tk < job.ngroups ? take_buffer(&s_free[0], lane) : 0u;
+            const uint32_t u = own_unit ? grp : (tk < job.ngroups ? take_buffer(&s_free[0], lane) : 0u);
             if (lane == 0) { G.ticket = tk; G.unit = u; G.done = 0; }
         }
         group_bar<GW * 32>(bar);
@@ -906,79 +912,71 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
         if (gi >= job.ngroups) break;
         if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
         const uint32_t chunk = gi / wpc, blk = gi - chunk * wpc;
-        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_GROUP;
+        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_WINDOW_PIECES;
         const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
         const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
         const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
         const uint32_t win_off = blk * QZ_WINDOW;
-        const uint32_t wlen = min((uint32_t)QZ_WINDOW, chunk_len - win_off);         /* > 0: only windows with data are counted */
-        const uint32_t npc = (wlen + PIECE - 1) >> 13;                               /* pieces with data */
+        const uint32_t wlen = min(QZ_WINDOW, chunk_len - win_off);                   /* > 0: only windows with data are counted */
+        const uint32_t nsub = (wlen + SUB - 1) / SUB;                                /* sub-pieces with data */
         const bool gfinal = (win_off + wlen == chunk_len) && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
-        const uint32_t p0 = wg * PIECE;
-        PieceState ps;
-        ps.g = g0 + wg; ps.n = wlen > p0 ? min((uint32_t)PIECE, wlen - p0) : 0u; ps.nslots = 0;
-        ps.src = job.src + chunk_off + win_off + p0;
-        const bool last_in_win = ps.n != 0 && p0 + ps.n == wlen;
-        ps.bfinal = last_in_win && gfinal;
+        const uint32_t p0 = wg * SUB;
+        const uint32_t n = wlen > p0 ? min(SUB, wlen - p0) : 0u;                      /* bytes of this warp's sub-piece */
+        const uint8_t *wsrc = job.src + chunk_off + win_off;
+        const bool last_in_win = n != 0 && p0 + n == wlen;
         uint8_t *unit = smem_raw + (size_t)G.unit * unit_bytes;
         uint8_t *win = unit + QZM_FRONT_PAD;
         uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
         uint16_t *table = tables + (size_t)wg * tstride;
 
-        /* load + checksum + prepass of the warp's own piece */
-        if (ps.n) {
-            const uint32_t c = load_and_checksum<PIECE>(win + p0, ps.src, ps.n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
-            if (lane == 0) job.piece_crc[ps.g] = c;
+        /* load + checksum + prepass of the warp's own sub-piece
+         * (a sub-piece's last three positions hash bytes of the next one, which may not have arrived: they are left out) */
+        if (n) {
+            const uint32_t c = load_and_checksum<SUB>(win + p0, wsrc + p0, n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
+            if (lane == 0) G.cksum[wg] = c;
+            QZ_MARK(1);
+            qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
         }
-        QZ_MARK(1);
-        /* (a piece's last three positions hash bytes of the next piece, which may not have arrived: they are left out) */
-        if (ps.n) qzm_prepass(win, p0 + ps.n, p0, p0 + ps.n, table, tent, lane);
         group_bar<GW * 32>(bar);
-        qzm_seed_tables(tables, tstride, npc, tent, threadIdx.x - grp * (GW * 32), GW * 32);
+        qzm_seed_tables(tables, tstride, nsub, tent, threadIdx.x - grp * (GW * 32), GW * 32);
+        /* the window's checksum from the sub-pieces' (CRC-32: every term times x^(8 * bytes behind it), XOR-ed) */
+        if (wg == GW - 1) {
+            uint32_t ck = 0;
+            if (job.fmt == QZB_FMT_ZLIB) {
+                if (lane == 0) {
+                    uint32_t s1 = 0, s2 = 0;
+                    for (uint32_t i = 0; i < nsub; i++) { const uint32_t w = G.cksum[i]; qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, min(SUB, wlen - i * SUB)); }
+                    ck = qz_adler_pack(s1, s2);
+                }
+            } else {
+                if (lane < nsub) ck = qz_gf2_mul(G.cksum[lane], wlen == QZ_WINDOW ? s_xafter[lane] : qz_crc_xpow8(wlen - min(wlen, (lane + 1) * SUB)));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
+            }
+            if (lane == 0) job.piece_crc[g0] = ck;
+        }
         group_bar<GW * 32>(bar);
-        QZ_MARK(4);
+        QZ_MARK(15);
         QzmDeflateSink sink = { slots, 0, pkeep };
-        if (ps.n) qzm_match_piece(win, wlen, p0, p0 + ps.n, table, tent, sink, lane);
-        ps.nslots = sink.nslots;
-        /* the eighth warp to finish hands the unit back */
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); if (atomicAdd(&G.done, 1u) == GW - 1) atomicOr(&s_free[0], 1u << G.unit); }
+        if (n) qzm_match_piece(win, wlen, p0, p0 + n, table, tent, sink, lane);
+        const uint32_t nslots = sink.nslots;
+        if (!own_unit) {        /* the last warp to finish hands the unit back */
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); if (atomicAdd(&G.done, 1u) == GW - 1) atomicOr(&s_free[0], 1u << G.unit); }
+        }
         QZ_MARK(2);
-        /* histogram of the warp's slots into the group's; the last piece of the window carries the end-of-block slot */
-        uint32_t extra = warp_sum(slot_hist(C.hist, slots, ps.nslots, s_lentab, lane, pkeep));
+        /* histogram of the warp's slots into the group's; the last sub-piece of the window carries the end-of-block slot */
+        const uint32_t extra = warp_sum(slot_hist(C.hist, slots, nslots, s_lentab, lane, pkeep));
         if (lane == 0) {
-            if (last_in_win) tok16_st(slots + ps.nslots, 256, pkeep);
-            G.nslots[wg] = ps.nslots + (last_in_win ? 1u : 0u);
+            if (last_in_win) tok16_st(slots + nslots, 256, pkeep);
+            G.nslots[wg] = nslots + (last_in_win ? 1u : 0u);
             G.extra[wg] = extra;
         }
         QZ_MARK(3);
         group_bar<GW * 32>(bar);
-        QZ_MARK(9);                 /* waiting for the group's slowest piece */
-        /* A window that mixes incompressible pieces (close to one slot per byte) with compressible ones is better off
-         * with a block per piece: one code table cannot serve both, and only whole blocks can fall back to stored. */
-        {
-            uint32_t hi = 0, lo = 0xffffffffu;
-#pragma unroll
-            for (int i = 0; i < QZ_GROUP; i++) {
-                const uint32_t nb = wlen > (uint32_t)i * PIECE ? min((uint32_t)PIECE, wlen - i * PIECE) : 0u;
-                if (nb) { const uint32_t r = (G.nslots[i] << 10) / nb; hi = max(hi, r); lo = min(lo, r); }
-            }
-            if (hi > 920u && lo < 768u) {
-                /* rare: the pieces take turns on the group's block coder */
-                for (uint32_t i = 0; i < npc; i++) {
-                    if (wg == i) {
-                        for (uint32_t k = lane; k < QZ_HIST_WORDS; k += 32) C.hist[k] = 0;
-                        __syncwarp();
-                        const uint32_t ex = warp_sum(slot_hist(C.hist, slots, ps.nslots, s_lentab, lane, pkeep));
-                        __syncwarp();
-                        finish_piece(job, C, slots, s_lentab, lane, ps, ex, pkeep QZ_TPASS);
-                    }
-                    group_bar<GW * 32>(bar);
-                }
-                continue;
-            }
-        }
+        QZ_MARK(9);                 /* waiting for the group's slowest sub-piece */
         uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
+        const uint32_t npc = (wlen + PIECE - 1) >> 13;          /* 8 KiB job pieces with data */
         /* leader: one set of codes, one block header for the window */
         if (wg == 0) {
             uint32_t extra_total = 0;
@@ -991,11 +989,14 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
         }
         group_bar<GW * 32>(bar);
         QZ_MARK(10);                /* waiting for the leader */
+        const uint32_t jp = wg / WPP;                           /* this warp's 8 KiB job piece */
+        const bool jp_owner = wg % WPP == 0 && jp < npc;
         if (G.btype == 0) {
-            /* incompressible window: every piece is its own stored block in its own slot */
-            if (ps.n) {
-                const uint32_t out_bytes = stored_piece(job.slots + (size_t)ps.g * job.slot_stride, ps.src, ps.n, ps.bfinal, lane);
-                if (lane == 0) job.piece_len[ps.g] = out_bytes;
+            /* incompressible window: every 8 KiB piece is its own stored block in its own slot */
+            if (jp_owner) {
+                const uint32_t pn = min((uint32_t)PIECE, wlen - jp * PIECE);
+                const uint32_t out_bytes = stored_piece(job.slots + (size_t)(g0 + jp) * job.slot_stride, wsrc + jp * PIECE, pn, gfinal && jp == npc - 1, lane);
+                if (lane == 0) job.piece_len[g0 + jp] = out_bytes;
             }
         } else {
             const uint32_t *tab = C.hist;
@@ -1012,7 +1013,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
             QZ_MARK(13);
             uint32_t before = G.hb, total = G.hb;
 #pragma unroll
-            for (int i = 0; i < QZ_GROUP; i++) {
+            for (int i = 0; i < GW; i++) {
                 const uint32_t bi = G.bits[i];
                 if (i < (int)wg) before += bi;
                 total += bi;
@@ -1028,7 +1029,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
             /* the lane that codes the end-of-block slot appends the trailer; it is the last slot of the window */
             const bool owns_eob = last_in_win && beg < NT && end == NT;
             emit_run(tab, slots, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
-            if (lane == 0 && ps.n) job.piece_len[ps.g] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
+            if (lane == 0 && jp_owner) job.piece_len[g0 + jp] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
         }
         __syncwarp();
         QZ_MARK(8);
@@ -1103,6 +1104,8 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
     const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
     const uint32_t hs = qzb_hdr_sz(job.fmt), fs = qzb_ftr_sz(job.fmt), payload = total - hs - fs;
     const uint32_t PIECE = 1u << job.piece_log2;
+    /* checksum units: pieces, or -- window kernels -- 64 KiB windows whose checksum sits at their first piece */
+    const uint32_t CKU = job.ngroups ? 65536u : PIECE, CKS = job.ngroups ? 8u : 1u;
     uint8_t *__restrict__ d = job.dst + off;
     __shared__ uint32_t s_poff[65];                      /* exclusive prefix of the pieces' lengths */
     if (warp == 0) {
@@ -1122,8 +1125,8 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
             ck = 0;
             if (lane == 0) {
                 uint32_t s1 = 0, s2 = 0;
-                for (uint32_t g = g0; g < g1; g++) {
-                    const uint32_t pn = min(PIECE, chunk_len - (g - g0) * PIECE), w = job.piece_crc[g];
+                for (uint32_t k = 0; k * CKU < chunk_len; k++) {
+                    const uint32_t pn = min(CKU, chunk_len - k * CKU), w = job.piece_crc[g0 + k * CKS];
                     qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, pn);
                 }
                 ck = qz_adler_finish(s1, s2, chunk_len);
@@ -1131,9 +1134,9 @@ __global__ void __launch_bounds__(QZ_FRAME_WARPS * 32) qzb_frame_kernel(QzbCompr
             ck = __shfl_sync(FULL, ck, 0);
         } else {
             ck = 0;
-            for (uint32_t k = lane; k < np; k += 32) {
-                const uint32_t after = chunk_len - min(chunk_len, (k + 1) * PIECE);      /* input bytes behind piece k */
-                ck ^= qz_gf2_mul(job.piece_crc[g0 + k], qz_crc_xpow8(after));
+            for (uint32_t k = lane; k * CKU < chunk_len; k += 32) {
+                const uint32_t after = chunk_len - min(chunk_len, (k + 1) * CKU);      /* input bytes behind checksum unit k */
+                ck ^= qz_gf2_mul(job.piece_crc[g0 + k * CKS], qz_crc_xpow8(after));
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
@@ -1228,23 +1231,28 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
 extern "C" int qzb_deflate_max_warps(int window) { return window ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
 /* shared memory of the window kernel: `nunits` units of tables with `tent` entries, `groups` block coders */
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups, int nunits)
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int gw, int groups, int nunits)
 {
-    return (size_t)nunits * window_unit_bytes((uint32_t)tent) + (size_t)groups * sizeof(BlockCoder);
+    return (size_t)nunits * window_unit_bytes((uint32_t)tent, (uint32_t)gw) + (size_t)groups * sizeof(BlockCoder);
 }
 
-/* window kernel (one deflate block per 64 KiB window): `groups` groups of eight warps per CTA share `nunits` units;
+/* window kernel (one deflate block per 64 KiB window): `groups` groups of `gw` (8 or 16) warps per CTA share `nunits` units;
  * job->ngroups and job->tent set */
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, int nunits, cudaStream_t st)
+template <int GW>
+static cudaError_t launch_window(const QzbCompressJob &job, int grid, int groups, int nunits, cudaStream_t st)
 {
-    if (groups < 1 || groups * QZ_GROUP > QZ_GROUPS_MAX_WARPS || nunits < 1 || nunits > groups || job->pieces_per_chunk % QZ_GROUP || !job->ngroups || job->piece_log2 != 13 ||
-        job->tent < 256 || job->tent > 32768)
-        return cudaErrorInvalidValue;
-    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent, groups, nunits);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = qzb_deflate_window_smem_bytes((int)job.tent, GW, groups, nunits);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_window_kernel<<<grid, groups * QZ_GROUP * 32, smem, st>>>(*job, nunits);
+    qzb_deflate_window_kernel<GW><<<grid, groups * GW * 32, smem, st>>>(job, nunits);
     return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int gw, int groups, int nunits, cudaStream_t st)
+{
+    if ((gw != 8 && gw != 16) || groups < 1 || groups * gw > QZ_GROUPS_MAX_WARPS || nunits < 1 || nunits > groups || job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups ||
+        job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768)
+        return cudaErrorInvalidValue;
+    return gw == 8 ? launch_window<8>(*job, grid, groups, nunits, st) : launch_window<16>(*job, grid, groups, nunits, st);
 }
 
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)

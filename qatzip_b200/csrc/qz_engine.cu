@@ -25,13 +25,13 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, int nunits, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int gw, int groups, int nunits, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups, int nunits);
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int gw, int groups, int nunits);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -61,7 +61,7 @@ extern "C" int qzb_deflate_max_warps(int group);
 #define QZB200_WINDOW_DEFAULT 1
 #endif
 #ifndef QZB200_WINDOW_TENT_DEFAULT
-#define QZB200_WINDOW_TENT_DEFAULT 2048
+#define QZB200_WINDOW_TENT_DEFAULT 1344
 #endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
@@ -96,7 +96,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->window = env_int("QZB200_WINDOW", QZB200_WINDOW_DEFAULT);
     t->window_tent = env_int("QZB200_WINDOW_TENT", QZB200_WINDOW_TENT_DEFAULT);      /* entries of a warp's hash table (2 bytes each, eight tables per unit) */
     if (t->window_tent < 256 || t->window_tent > 8192) t->window_tent = QZB200_WINDOW_TENT_DEFAULT;
-    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups of eight warps per CTA (0 = 4) */
+    t->window_warps = env_int("QZB200_WINDOW_WARPS", 16);                             /* warps per window: 16 (4 KiB each) or 8 (8 KiB each) */
+    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups per CTA (0 = as many as 32 warps make) */
     t->window_units = env_int("QZB200_WINDOW_UNITS", 0);                              /* units per CTA (0 = as many as fit, at most the groups) */
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
@@ -280,7 +281,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, groups = 0, nunits = 0;
+    int nbuf = t.buffers_per_cta, groups = 0, nunits = 0, gw = 16;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
@@ -292,11 +293,13 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         const uint32_t wpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
         job.tent = (uint32_t)t.window_tent;
-        groups = t.window_groups > 0 ? std::min(t.window_groups, qzb_deflate_max_warps(1) / 8) : qzb_deflate_max_warps(1) / 8;
+        gw = t.window_warps == 8 ? 8 : 16;
+        const int maxg = qzb_deflate_max_warps(1) / gw;
+        groups = t.window_groups > 0 ? std::min(t.window_groups, maxg) : maxg;
         nunits = t.window_units > 0 ? std::min(t.window_units, groups) : groups;
-        while (nunits > 1 && qzb_deflate_window_smem_bytes((int)job.tent, groups, nunits) + 3072 > smem_cap) nunits--;
-        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, groups, nunits);
-        warps = groups * 8;
+        while (nunits > 1 && qzb_deflate_window_smem_bytes((int)job.tent, gw, groups, nunits) + 3072 > smem_cap) nunits--;
+        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, gw, groups, nunits);
+        warps = groups * gw;
     } else {
         if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
@@ -325,7 +328,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, groups, nunits, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, gw, groups, nunits, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

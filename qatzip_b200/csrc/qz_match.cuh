@@ -8,10 +8,9 @@
  *             its piece                                                                                   (qzm_prepass)
  *   seed      a scan over the pieces, entry by entry: table k receives the most recent position of every hash in pieces
  *             0..k-1 -- what a sequential compressor's hash table would hold on entering piece k         (qzm_seed_tables)
- *   match     32 positions per step.  A position's candidate is the nearest lower lane of its tile with the same hash
- *             (match.any), else the table entry: together exactly "the most recent earlier position with this hash" of a
- *             sequential single-probe matcher that inserts every position.  Positions inside a byte run are not inserted
- *             (the table keeps the run's start, which matches a later run of the same byte from ITS start).  Candidates are
+ *   match     32 positions per step: all look up, then all insert.  A position inside a byte run takes the position before
+ *             it as its candidate (distance 1) and is not inserted: the table keeps the run's start, which matches a later
+ *             run of the same byte from ITS start; every other position's candidate is the table entry.  Candidates are
  *             verified and extended 12 bytes in the lane; the greedy parse of the tile -- which lanes start a token -- is
  *             found by pointer doubling over next(lane) = lane + max(1, L) instead of a serial walk, matches that reach
  *             the 12-byte cap are finished by the whole warp, a selected match takes over up to four literals in front of
@@ -49,12 +48,11 @@ __device__ __forceinline__ void qzm_prepass(const uint8_t *win, uint32_t n, uint
         const uint32_t p = base + lane;
         const uint32_t *pw = ww + (p >> 2);
         const uint32_t v = __funnelshift_r(pw[0], pw[1], sh);
-        const bool ins = p < p1 && p + 4 <= n && !qzm_run_interior(v, win[(int)p - 1], p);
-        const uint32_t h = qzm_hash(v, tent);
-        const uint32_t peers = __match_any_sync(QZM_FULL, ins ? h : tent + lane);
-        if (ins && (peers >> lane) == 1u) table[h] = (uint16_t)p;      /* the highest lane of equal hashes: the most recent position */
-        __syncwarp();
+        /* ascending tiles: a later position overwrites an earlier one.  Equal hashes inside one tile are a write/write race
+         * the hardware settles for one of the lanes -- positions less than 32 bytes apart, either will do. */
+        if (p + 4 <= n && !qzm_run_interior(v, win[(int)p - 1], p)) table[qzm_hash(v, tent)] = (uint16_t)p;
     }
+    __syncwarp();
 }
 
 /* tables[k] (k < npieces, `stride` u16 apart) <- the most recent position of every hash in pieces 0..k-1.  Called by all
@@ -130,16 +128,14 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
         const uint32_t prevb = win[(int)p - 1];
         const bool can = p < p1 && p + 4 <= n;
-        const bool ins = can && !qzm_run_interior(v, prevb, p);
+        const bool interior = qzm_run_interior(v, prevb, p);
         const uint32_t h = qzm_hash(v, tent);
-        const uint32_t peers = __match_any_sync(QZM_FULL, can ? h : tent + lane);
-        const uint32_t insmask = __ballot_sync(QZM_FULL, ins);
         const uint32_t t = can ? table[h] : QZM_NONE;
         __syncwarp();
-        if (ins && ((peers & insmask) >> lane) == 1u) table[h] = (uint16_t)p;
+        if (can && !interior) table[h] = (uint16_t)p;       /* equal hashes inside the tile: see qzm_prepass */
         __syncwarp();
-        const uint32_t lower = peers & lt;
-        const uint32_t cand = lower ? base + 31 - __clz(lower) : t;
+        /* inside a byte run the candidate is the position before (distance 1); everywhere else the table's */
+        const uint32_t cand = interior ? p - 1 : t;
         /* candidate bytes are fetched unconditionally (position 0 when there is none): no divergent verify branches */
         const bool has = can && cand != QZM_NONE && p - cand <= Sink::kMaxDist && p <= mstart_lim;
         const uint32_t c = has ? cand : 0u, csh = (c & 3) * 8;

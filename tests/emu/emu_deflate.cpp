@@ -56,10 +56,6 @@ extern "C" void emu_job_setup(QzbCompressJob *job, EmuCompressBuffers *b, int fm
     job->piece_len = (uint32_t *)(m + o_plen); job->piece_crc = (uint32_t *)(m + o_pcrc);
     job->chunk_total = (uint32_t *)(m + o_tot); job->chunk_cksum = (uint32_t *)(m + o_ck);
     job->chunk_off = (uint64_t *)(m + o_off); job->ticket = (uint32_t *)(m + o_ticket);
-    {   /* window kernel: windows of QZ_GROUP pieces (set for every job; the per-piece kernel ignores it) */
-        const uint32_t gpc = job->pieces_per_chunk / QZ_GROUP;
-        job->ngroups = (job->pieces_per_chunk % QZ_GROUP == 0 && len) ? (job->nchunks - 1) * gpc + (last_pieces + QZ_GROUP - 1) / QZ_GROUP : 0u;
-    }
     b->tok.assign((size_t)resident_warps * QZB_TOK_STRIDE(PIECE), 0xEEEEEEEEu);
     job->tok_scratch = b->tok.data();
     job->dst = dst; job->dst_cap = cap;
@@ -81,8 +77,8 @@ extern "C" long emu_frame(const QzbCompressJob *jobp, uint32_t *chunk_cksum_out)
 /* One batch through the deflate kernels.  Geometry is the caller's.  Returns bytes produced, -1 for an unsupported geometry,
  * -2 when a kernel wrote past its scratch.
  * window == 0: per-piece kernel (piece size, hash bits, warps and piece buffers per CTA, CTAs);
- * window != 0: window kernel (one deflate block per 64 KiB window): warps / 8 groups per CTA share `nbuf` units whose
- *              tables have `hb` entries each when hb >= 256, else 2^hb. */
+ * window != 0: window kernel (one deflate block per 64 KiB window), 8 (window == 8) or 16 warps per window: the groups of a CTA
+ *              share `nbuf` units whose tables have `hb` entries each when hb >= 256, else 2^hb. */
 extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman,
                                      int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int window)
 {
@@ -92,12 +88,16 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
     size_t smem;
     std::function<void()> body;
     if (window) {
-        const int groups = warps / QZ_GROUP, nunits = nbuf > groups ? groups : nbuf;
-        if (!job.ngroups || warps % QZ_GROUP || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13) return -1;
+        const int gw = window == 8 ? 8 : 16;            /* warps per window */
+        const int groups = warps / gw, nunits = nbuf > groups ? groups : nbuf;
+        if (!len || job.pieces_per_chunk % QZ_WINDOW_PIECES || warps % gw || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13) return -1;
+        const uint64_t last_len = len - (uint64_t)(job.nchunks - 1) * chunk_sz;
+        job.ngroups = (job.nchunks - 1) * (job.pieces_per_chunk / QZ_WINDOW_PIECES) + (uint32_t)((last_len + QZ_WINDOW - 1) / QZ_WINDOW);
         job.tent = hb >= 256 ? (uint32_t)hb : 1u << hb;
-        smem = (size_t)nunits * window_unit_bytes(job.tent) + (size_t)groups * sizeof(BlockCoder);
+        smem = (size_t)nunits * window_unit_bytes(job.tent, gw) + (size_t)groups * sizeof(BlockCoder);
         if (smem > 227 * 1024) return -1;
-        emu::launch((unsigned)grid, (unsigned)warps * 32, smem, [&] { qzb_deflate_window_kernel(job, nunits); });
+        if (gw == 8) emu::launch((unsigned)grid, (unsigned)warps * 32, smem, [&] { qzb_deflate_window_kernel<8>(job, nunits); });
+        else emu::launch((unsigned)grid, (unsigned)warps * 32, smem, [&] { qzb_deflate_window_kernel<16>(job, nunits); });
         const long n = emu_frame(&job, chunk_cksum_out);
         return emu_canaries_ok(b) ? n : -2;
     }

@@ -1,4 +1,4 @@
-"""Per-phase shares of warp time in the deflate kernel in use (group kernel by default, QZB200_GROUP=0: per piece) (needs the A/B build:
+"""Per-phase shares of warp time in the deflate kernel in use (window kernel by default, QZB200_WINDOW=0: per piece) (needs the A/B build:
 make -C qatzip_b200/csrc ab ABFLAGS=-DQZ_PHASE_CLOCKS).  Prints lane-0 cycles per phase, summed over warps."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,8 +11,8 @@ cap = L.qzMaxCompressedLength(n, None)
 d_in, d_out = L.qzb200DeviceAlloc(n), L.qzb200DeviceAlloc(cap)
 assert L.qzb200CopyToDevice(d_in, h, n) == 0
 sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536)
-names = ["ticket+buffer wait", "load+crc", "match+select", "token pass", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit",
-         "wait: slowest piece of the group", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "split kernel, coders: wait for a matched block"]
+names = ["ticket + unit/buffer wait", "load+crc", "match+select", "slot histogram", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit",
+         "wait: slowest piece of the window", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "prepass + seed (with their barriers)"]
 out = (C.c_ulonglong * 16)()
 for it in range(3):
     L.qzb_phase_cycles_read(out, 1)

@@ -31,6 +31,7 @@ struct Params {
     int tile = 1;          // scheme 2: 0 table only, 1 in-tile candidate preferred, 2 best of both
     int maxd = 32768;
     int lz4 = 0;
+    int dd = 4, sublanes = 16;   // tile >= 3: direct distances checked; tile >= 4: lanes per lookup/insert sub-step
     int tent = 0;          // scheme 2: table entries when not a power of two (multiply-shift range reduction)
     int nir = 0;           // scheme 2: positions inside a byte run (p-1..p+3 equal) are not inserted
     int bext = 0;          // backward extension of a selected match over the literals before it (inside the tile if 1, anywhere if 2)
@@ -213,9 +214,14 @@ static long model_chunk2(const uint8_t *src, int n, const Params &P, long *ntok_
                     const uint32_t h = hashf(src + p, P);
                     int ct = -1, cq = -1;
                     int lbest = -1; for (int w = 0; w < WY; w++) { const int c = T[h * WY + w]; if (c >= 0 && p - c <= P.maxd) { int l = mlen(src + c, src + p, maxl); if (l > lbest) { lbest = l; ct = c; } } }
-                    if (P.tile) for (int q = p - 1; q >= w0; q--) if (rd32(src + q) == rd32(src + p)) { cq = q; break; }
+                    if (P.tile == 1 || P.tile == 2) for (int q = p - 1; q >= w0; q--) if (rd32(src + q) == rd32(src + p)) { cq = q; break; }
+                    if (P.tile >= 3) {
+                        // direct short distances, then (tile >= 4) lanes of earlier sub-steps of `P.sub` lanes via the table
+                        for (int d = 1; d <= P.dd && p - d >= 0; d++) if (rd32(src + p - d) == rd32(src + p)) { cq = p - d; break; }
+                        if (cq < 0 && P.tile >= 4) { const int sb = w0 + ((p - w0) / P.sublanes) * P.sublanes; for (int q = sb - 1; q >= w0; q--) if (hashf(src + q, P) == h && !(P.nir && q > 0 && rd32(src + q) == rd32(src + q - 1))) { cq = q; break; } }
+                    }
                     int lt = ct >= 0 ? mlen(src + ct, src + p, maxl) : 0, lq = cq >= 0 ? mlen(src + cq, src + p, maxl) : 0;
-                    if (P.tile == 1) { if (cq >= 0) { bl = lq; bd = p - cq; } else { bl = lt; bd = p - ct; } }
+                    if (P.tile == 1 || P.tile >= 3) { if (cq >= 0) { bl = lq; bd = p - cq; } else { bl = lt; bd = p - ct; } }
                     else { if (lq >= lt && cq >= 0) { bl = lq; bd = p - cq; } else { bl = lt; bd = p - ct; } }
                     if (bl < P.minm) bl = 0;
                 }
@@ -270,7 +276,7 @@ int main(int argc, char **argv)
         else if (k == "warp") P.warp = v; else if (k == "winner") P.winner = v; else if (k == "mb") total = (size_t)v << 20; else if (k == "kind") kind = v;
         else if (k == "lazy") P.lazy = v; else if (k == "ways") P.ways = v; else if (k == "only") only = eq + 1;
         else if (k == "scheme") P.scheme = v; else if (k == "pp") P.pp = v; else if (k == "tile") P.tile = v; else if (k == "maxd") P.maxd = v;
-        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
+        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "dd") P.dd = v; else if (k == "sublanes") P.sublanes = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
     }
     std::vector<uint8_t> buf;
     if (file) {
