@@ -829,24 +829,30 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
 
 /* ------------------------------------------------------------------------------------------ */
 /* Window kernel (default for hw_buff_sz >= 64 KiB): a WINDOW is 64 KiB of one chunk and becomes ONE deflate block, what
- * the QAT engine emits for a 64 KiB request with its 32 KiB history (reference src/qatzip_utils.c:270-291).  GW warps (16,
- * or 8) take a window together, each a sub-piece of 64 KiB / GW.  The window's bytes sit whole in a shared-memory UNIT next
- * to the GW warps' hash tables; the stages of qz_match.cuh (prepass, seed, match) give every position the whole window in
- * front of it as history while the sub-pieces are still matched concurrently.  Then the group goes on from the slots in
- * the L2 scratch: histogram into the group's block coder, the leader builds the codes and writes the block header, every
- * warp counts its slots' bits, the totals are scanned through shared memory, boundary words are zeroed, and every lane
- * packs its run at its bit offset inside the window's output (the slot of its first 8 KiB piece); the lane that codes the
- * end-of-block slot appends the byte-aligning empty stored block unless the block is final.  With GW = 16 a CTA is two
- * groups that each own a unit; with GW = 8 four groups share two units (a unit is handed back as soon as the last warp
- * has matched: while two groups match, two code).  Incompressible window -> every 8 KiB piece a stored block in its own
- * slot.  Warps of a group meet at a named barrier; groups of one CTA are independent of each other.
+ * the QAT engine emits for a 64 KiB request with its 32 KiB history (reference src/qatzip_utils.c:270-291).
+ *
+ * A group is sixteen warps that own a shared-memory UNIT (the window's bytes and fifteen hash tables): fifteen MATCHERS,
+ * each with a sub-piece of 4384 bytes (137 tiles; the last one 4160), and one CODER.  The matchers run the stages of
+ * qz_match.cuh (load + checksum + prepass, seed, match: every position has the whole window in front of it as history
+ * while the sub-pieces are matched concurrently), leave their tokens as slots in the L2 scratch and add them to the
+ * window's histogram.  The coder turns that histogram into code tables and the block header (sort, Huffman lengths,
+ * header plan, canonical codes: a few thousand mostly serial instructions) WHILE the matchers are already matching the
+ * next window; when they are done with that, they meet the coder, and emit the window before: every warp counts its
+ * slots' bits, the totals are scanned through shared memory, boundary words are zeroed, and every lane packs its run at
+ * its bit offset inside the window's output (the slot of its first 8 KiB piece); the lane that codes the end-of-block
+ * slot appends the byte-aligning empty stored block unless the block is final.  Slots, histograms and code tables are
+ * double-buffered by window parity.  Incompressible window -> every 8 KiB piece a stored block in its own slot.
+ * Two groups per CTA, independent of each other; warps meet at named barriers (matchers only / whole group).
  * The window's checksum goes to piece_crc[] of the window's first 8 KiB piece (the framing kernel combines per window). */
 #define QZ_WINDOW 65536u
 #define QZ_WINDOW_PIECES 8u             /* 8 KiB job pieces (slots, lengths) per window */
-#define QZ_WINDOW_MAX_GW 16
-struct WindowShared {
-    uint32_t ticket, unit, done, btype, hb, pend;
-    uint32_t nslots[QZ_WINDOW_MAX_GW], bits[QZ_WINDOW_MAX_GW], extra[QZ_WINDOW_MAX_GW], cksum[QZ_WINDOW_MAX_GW];
+#define QZW_MATCHERS 15u
+#define QZW_GROUP_WARPS 16u
+#define QZW_SUB 4384u                   /* bytes of a matcher's sub-piece: 137 tiles, a multiple of 16 */
+static_assert(QZW_SUB % 32 == 0 && QZW_SUB * QZW_MATCHERS >= QZ_WINDOW && QZW_SUB * (QZW_MATCHERS - 1) < QZ_WINDOW, "sub-pieces tile the window");
+struct WindowShared {                   /* one per group and window parity */
+    uint32_t ticket, btype, hb, pend;
+    uint32_t nslots[QZW_MATCHERS + 1], bits[QZW_MATCHERS + 1], extra[QZW_MATCHERS + 1], cksum[QZW_MATCHERS + 1];
 };
 template <int NT>
 __device__ __forceinline__ void group_bar(uint32_t id)
@@ -857,182 +863,204 @@ __device__ __forceinline__ void group_bar(uint32_t id)
     __syncwarp(); asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NT) : "memory");
 #endif
 }
-/* bytes of one unit: the window with its pads, then gw tables of `tent` entries (rounded up to 16 bytes each) */
+/* bytes of one unit: the window with its pads, then the matchers' tables of `tent` entries (rounded up to 16 bytes each) */
 __host__ __device__ __forceinline__ uint32_t window_table_stride(uint32_t tent) { return (tent + 8u) & ~7u; }       /* u16 entries */
-__host__ __device__ __forceinline__ uint32_t window_unit_bytes(uint32_t tent, uint32_t gw) { return QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD + gw * 2u * window_table_stride(tent); }
+__host__ __device__ __forceinline__ uint32_t window_unit_bytes(uint32_t tent) { return QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD + QZW_MATCHERS * 2u * window_table_stride(tent); }
+/* 32-bit words of slot scratch per warp of the window kernel: two windows in flight */
+#define QZW_TOK_WORDS (2u * QZB_TOK_STRIDE(QZW_SUB))
 
-template <int GW>
-__global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job, int nunits)
+/* where window gi lies */
+struct WindowGeom {
+    uint32_t g0, wlen, nsub, npc; bool gfinal; const uint8_t *wsrc;
+};
+__device__ __forceinline__ WindowGeom window_geometry(const QzbCompressJob &job, uint32_t gi)
 {
-    constexpr uint32_t SUB = QZ_WINDOW / GW;                 /* bytes of a warp's sub-piece */
-    constexpr uint32_t WPP = GW / QZ_WINDOW_PIECES;          /* warps per 8 KiB job piece */
+    WindowGeom w;
+    const uint32_t wpc = job.pieces_per_chunk / QZ_WINDOW_PIECES;     /* windows per chunk */
+    const uint32_t chunk = gi / wpc, blk = gi - chunk * wpc;
+    w.g0 = chunk * job.pieces_per_chunk + blk * QZ_WINDOW_PIECES;
+    const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
+    const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
+    const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
+    const uint32_t win_off = blk * QZ_WINDOW;
+    w.wlen = min(QZ_WINDOW, chunk_len - win_off);                     /* > 0: only windows with data are counted */
+    w.nsub = (w.wlen + QZW_SUB - 1) / QZW_SUB;                        /* sub-pieces with data */
+    w.npc = (w.wlen + 8191u) >> 13;                                   /* 8 KiB job pieces with data */
+    w.gfinal = (win_off + w.wlen == chunk_len) && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
+    w.wsrc = job.src + chunk_off + win_off;
+    return w;
+}
+
+__global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job)
+{
+    constexpr uint32_t SUB = QZW_SUB, NM = QZW_MATCHERS, GW = QZW_GROUP_WARPS;
     constexpr int PIECE = 1 << 13;
     static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xstrip[5];
-    __shared__ uint32_t s_xafter[GW];       /* x^(8 * bytes behind sub-piece i of a full window) */
+    __shared__ uint32_t s_xafter[NM];       /* x^(8 * bytes behind sub-piece i of a full window) */
     __shared__ uint16_t s_lentab[256];
-    __shared__ uint32_t s_free[1];          /* free mask of the units */
-    __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW];
+    __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW][2];
     constexpr uint32_t STRIP = SUB / 32 + 4;
 
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent, GW);
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, ngroups_cta = nwarps / GW;
+    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (threadIdx.x < GW) s_xafter[threadIdx.x] = qz_crc_xpow8((uint64_t)(GW - 1 - threadIdx.x) * SUB);
-    if (threadIdx.x == 0) s_free[0] = (1u << nunits) - 1;
+    if (threadIdx.x < NM) s_xafter[threadIdx.x] = qz_crc_xpow8((uint64_t)(QZ_WINDOW - min(QZ_WINDOW, (threadIdx.x + 1) * SUB)));
     __syncthreads();
 
-    const uint32_t grp = warp / GW, wg = warp % GW, bar = 1 + grp;
-    const bool own_unit = (uint32_t)nunits >= nwarps / GW;     /* as many units as groups: no hand-over */
-    WindowShared &G = s_grp[grp];
-    BlockCoder &C = reinterpret_cast<BlockCoder *>(smem_raw + (size_t)nunits * unit_bytes)[grp];
-    const uint32_t gwarp = blockIdx.x * nwarps + warp;
-    uint16_t *slots = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZB_TOK_STRIDE(SUB));
-    const uint32_t wpc = job.pieces_per_chunk / QZ_WINDOW_PIECES;     /* windows per chunk */
+    const uint32_t grp = warp / GW, wg = warp % GW;
+    const uint32_t bar_m = 1 + 2 * grp, bar_f = 2 + 2 * grp;           /* matchers only / the whole group */
+    BlockCoder *coders = reinterpret_cast<BlockCoder *>(smem_raw + (size_t)ngroups_cta * unit_bytes) + 2 * grp;
+    uint8_t *unit = smem_raw + (size_t)grp * unit_bytes;
+    uint8_t *win = unit + QZM_FRONT_PAD;
+    uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
     const uint64_t pkeep = l2_policy_keep();
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
-    for (;;) {
-        /* the leader draws the window and, if units are shared, one of them */
-        if (wg == 0) {
-            uint32_t tk = 0;
-            if (lane == 0) tk = atomicAdd(job.ticket, 1u);
-            tk = __shfl_sync(FULL, tk, 0);
-            const uint32_t u = own_unit ? grp : (tk < job.ngroups ? take_buffer(&s_free[0], lane) : 0u);
-            if (lane == 0) { G.ticket = tk; G.unit = u; G.done = 0; }
-        }
-        group_bar<GW * 32>(bar);
-        QZ_MARK(0);
-        /* every warp of the group is past the previous block's emission: its code tables can go */
-        const uint32_t gi = G.ticket;
-        if (gi >= job.ngroups) break;
-        if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
-        const uint32_t chunk = gi / wpc, blk = gi - chunk * wpc;
-        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * QZ_WINDOW_PIECES;
-        const uint64_t chunk_off = (uint64_t)chunk * job.chunk_sz;
-        const uint64_t rem = job.src_len > chunk_off ? job.src_len - chunk_off : 0;
-        const uint32_t chunk_len = rem < job.chunk_sz ? (uint32_t)rem : job.chunk_sz;
-        const uint32_t win_off = blk * QZ_WINDOW;
-        const uint32_t wlen = min(QZ_WINDOW, chunk_len - win_off);                   /* > 0: only windows with data are counted */
-        const uint32_t nsub = (wlen + SUB - 1) / SUB;                                /* sub-pieces with data */
-        const bool gfinal = (win_off + wlen == chunk_len) && (job.fmt != QZB_FMT_RAW || (chunk == job.nchunks - 1 && job.last));
-        const uint32_t p0 = wg * SUB;
-        const uint32_t n = wlen > p0 ? min(SUB, wlen - p0) : 0u;                      /* bytes of this warp's sub-piece */
-        const uint8_t *wsrc = job.src + chunk_off + win_off;
-        const bool last_in_win = n != 0 && p0 + n == wlen;
-        uint8_t *unit = smem_raw + (size_t)G.unit * unit_bytes;
-        uint8_t *win = unit + QZM_FRONT_PAD;
-        uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
-        uint16_t *table = tables + (size_t)wg * tstride;
 
-        /* load + checksum + prepass of the warp's own sub-piece
-         * (a sub-piece's last three positions hash bytes of the next one, which may not have arrived: they are left out) */
-        if (n) {
-            const uint32_t c = load_and_checksum<SUB>(win + p0, wsrc + p0, n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
-            if (lane == 0) G.cksum[wg] = c;
-            QZ_MARK(1);
-            qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
+    if (wg == NM) {
+        /* ---- the coder: codes and block header of window k - 1 while the matchers work on window k ---- */
+        for (uint32_t k = 0;; k++) {
+            if (k) {
+                WindowShared &P = s_grp[grp][(k - 1) & 1];
+                BlockCoder &C = coders[(k - 1) & 1];
+                const WindowGeom w = window_geometry(job, P.ticket);
+                uint32_t extra_total = 0;
+                for (uint32_t i = 0; i < NM; i++) extra_total += P.extra[i];
+                const int btype = choose_block(C.cs, C.hist, extra_total, (5 * w.npc + w.wlen) * 8, job.static_huffman, lane QZ_TPASS);
+                uint32_t hb = 0, pend = 0;
+                if (btype) open_block(C.cs, C.hist, btype, w.gfinal, reinterpret_cast<uint32_t *>(job.slots + (size_t)w.g0 * job.slot_stride), s_lentab, lane, &hb, &pend QZ_TPASS);
+                if (lane == 0) { P.btype = (uint32_t)btype; P.hb = hb; P.pend = pend; }
+                QZ_MARK(11);
+            }
+            group_bar<GW * 32>(bar_f);
+            QZ_MARK(10);                /* coder: waiting for the matchers */
+            if (s_grp[grp][k & 1].ticket >= job.ngroups) break;
         }
-        group_bar<GW * 32>(bar);
-        qzm_seed_tables(tables, tstride, nsub, tent, threadIdx.x - grp * (GW * 32), GW * 32);
-        /* the window's checksum from the sub-pieces' (CRC-32: every term times x^(8 * bytes behind it), XOR-ed) */
-        if (wg == GW - 1) {
-            uint32_t ck = 0;
-            if (job.fmt == QZB_FMT_ZLIB) {
-                if (lane == 0) {
-                    uint32_t s1 = 0, s2 = 0;
-                    for (uint32_t i = 0; i < nsub; i++) { const uint32_t w = G.cksum[i]; qz_adler_join(&s1, &s2, w & 0xffffu, w >> 16, min(SUB, wlen - i * SUB)); }
-                    ck = qz_adler_pack(s1, s2);
+        return;
+    }
+
+    /* ---- the matchers ---- */
+    const uint32_t gwarp = blockIdx.x * nwarps + warp;
+    uint16_t *slots2 = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZW_TOK_WORDS);
+    uint16_t *table = tables + (size_t)wg * tstride;
+    const uint32_t p0 = wg * SUB;
+    uint32_t prev_gi = 0;
+    for (uint32_t k = 0;; k++) {
+        const uint32_t b = k & 1;
+        WindowShared &G = s_grp[grp][b];
+        BlockCoder &C = coders[b];
+        uint16_t *slots = slots2 + (size_t)b * 2 * QZB_TOK_STRIDE(SUB);
+        if (wg == 0 && lane == 0) G.ticket = atomicAdd(job.ticket, 1u);
+        group_bar<NM * 32>(bar_m);
+        QZ_MARK(0);
+        /* every matcher is past the emission of window k - 2: its code tables (same parity as window k) can go */
+        const uint32_t gi = G.ticket;
+        const bool have = gi < job.ngroups;
+        if (have) {
+            if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
+            const WindowGeom w = window_geometry(job, gi);
+            const uint32_t n = w.wlen > p0 ? min(SUB, w.wlen - p0) : 0u;                  /* bytes of this warp's sub-piece */
+            const bool last_in_win = n != 0 && p0 + n == w.wlen;
+            /* load + checksum + prepass of the warp's own sub-piece
+             * (a sub-piece's last three positions hash bytes of the next one, which may not have arrived: they are left out) */
+            if (n) {
+                const uint32_t c = load_and_checksum<SUB>(win + p0, w.wsrc + p0, n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
+                if (lane == 0) G.cksum[wg] = c;
+                QZ_MARK(1);
+                qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
+            }
+            group_bar<NM * 32>(bar_m);
+            qzm_seed_tables(tables, tstride, w.nsub, tent, threadIdx.x - grp * (GW * 32), NM * 32);
+            /* the window's checksum from the sub-pieces' (CRC-32: every term times x^(8 * bytes behind it), XOR-ed) */
+            if (wg == NM - 1) {
+                uint32_t ck = 0;
+                if (job.fmt == QZB_FMT_ZLIB) {
+                    if (lane == 0) {
+                        uint32_t s1 = 0, s2 = 0;
+                        for (uint32_t i = 0; i < w.nsub; i++) { const uint32_t x = G.cksum[i]; qz_adler_join(&s1, &s2, x & 0xffffu, x >> 16, min(SUB, w.wlen - i * SUB)); }
+                        ck = qz_adler_pack(s1, s2);
+                    }
+                } else {
+                    if (lane < w.nsub) ck = qz_gf2_mul(G.cksum[lane], w.wlen == QZ_WINDOW ? s_xafter[lane] : qz_crc_xpow8(w.wlen - min(w.wlen, (lane + 1) * SUB)));
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
+                }
+                if (lane == 0) job.piece_crc[w.g0] = ck;
+            }
+            group_bar<NM * 32>(bar_m);
+            QZ_MARK(15);
+            QzmDeflateSink sink = { slots, 0, pkeep };
+            if (n) qzm_match_piece(win, w.wlen, p0, p0 + n, table, tent, sink, lane);
+            QZ_MARK(2);
+            /* histogram of the warp's slots into the window's; the last sub-piece carries the end-of-block slot */
+            const uint32_t extra = warp_sum(slot_hist(C.hist, slots, sink.nslots, s_lentab, lane, pkeep));
+            if (lane == 0) {
+                if (last_in_win) tok16_st(slots + sink.nslots, 256, pkeep);
+                G.nslots[wg] = sink.nslots + (last_in_win ? 1u : 0u);
+                G.extra[wg] = extra;
+            }
+            QZ_MARK(3);
+        }
+        group_bar<GW * 32>(bar_f);
+        QZ_MARK(9);                 /* waiting for the slowest matcher and for the coder */
+        /* ---- emission of window k - 1, whose code tables the coder has just finished ---- */
+        if (k) {
+            WindowShared &P = s_grp[grp][b ^ 1];
+            const uint32_t *tab = coders[b ^ 1].hist;
+            const uint16_t *pslots = slots2 + (size_t)(b ^ 1) * 2 * QZB_TOK_STRIDE(SUB);
+            const WindowGeom w = window_geometry(job, prev_gi);      /* (P.ticket may already hold the ticket of window k + 1) */
+            const uint32_t n = w.wlen > p0 ? min(SUB, w.wlen - p0) : 0u;
+            const bool last_in_win = n != 0 && p0 + n == w.wlen;
+            uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)w.g0 * job.slot_stride);
+            if (P.btype == 0) {
+                /* incompressible window: every 8 KiB piece is its own stored block in its own slot */
+                if (wg < w.npc) {
+                    const uint32_t pn = min((uint32_t)PIECE, w.wlen - wg * PIECE);
+                    const uint32_t out_bytes = stored_piece(job.slots + (size_t)(w.g0 + wg) * job.slot_stride, w.wsrc + wg * PIECE, pn, w.gfinal && wg == w.npc - 1, lane);
+                    if (lane == 0) job.piece_len[w.g0 + wg] = out_bytes;
                 }
             } else {
-                if (lane < nsub) ck = qz_gf2_mul(G.cksum[lane], wlen == QZ_WINDOW ? s_xafter[lane] : qz_crc_xpow8(wlen - min(wlen, (lane + 1) * SUB)));
+                const uint32_t NT = P.nslots[wg];
+                const uint32_t R = run_length(NT);
+                const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
+                const uint32_t mybits = count_run_bits(tab, pslots, beg, end, pkeep);
+                uint32_t incl = mybits;
 #pragma unroll
-                for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+                if (lane == 31) P.bits[wg] = incl;
+                QZ_MARK(12);            /* count pass */
+                group_bar<NM * 32>(bar_m);
+                QZ_MARK(13);
+                uint32_t before = P.hb, total = P.hb;
+#pragma unroll
+                for (uint32_t i = 0; i < NM; i++) {
+                    const uint32_t bi = P.bits[i];
+                    if (i < wg) before += bi;
+                    total += bi;
+                }
+                const uint32_t end_bit = total;
+                const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);
+                const uint32_t end_bit2 = w.gfinal ? end_bit : end_bit + nz + 32;
+                const uint32_t start = before + incl - mybits;
+                slotw[start >> 5] = 0;
+                if (wg == NM - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
+                group_bar<NM * 32>(bar_m);
+                QZ_MARK(14);
+                /* the lane that codes the end-of-block slot appends the trailer; it is the last slot of the window */
+                const bool owns_eob = last_in_win && beg < NT && end == NT;
+                emit_run(tab, pslots, beg, end, start, P.pend, wg == 0 && lane == 0, !w.gfinal && owns_eob, nz, slotw, pkeep);
+                if (lane == 0 && wg < w.npc) job.piece_len[w.g0 + wg] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
             }
-            if (lane == 0) job.piece_crc[g0] = ck;
-        }
-        group_bar<GW * 32>(bar);
-        QZ_MARK(15);
-        QzmDeflateSink sink = { slots, 0, pkeep };
-        if (n) qzm_match_piece(win, wlen, p0, p0 + n, table, tent, sink, lane);
-        const uint32_t nslots = sink.nslots;
-        if (!own_unit) {        /* the last warp to finish hands the unit back */
             __syncwarp();
-            if (lane == 0) { __threadfence_block(); if (atomicAdd(&G.done, 1u) == GW - 1) atomicOr(&s_free[0], 1u << G.unit); }
+            QZ_MARK(8);
         }
-        QZ_MARK(2);
-        /* histogram of the warp's slots into the group's; the last sub-piece of the window carries the end-of-block slot */
-        const uint32_t extra = warp_sum(slot_hist(C.hist, slots, nslots, s_lentab, lane, pkeep));
-        if (lane == 0) {
-            if (last_in_win) tok16_st(slots + nslots, 256, pkeep);
-            G.nslots[wg] = nslots + (last_in_win ? 1u : 0u);
-            G.extra[wg] = extra;
-        }
-        QZ_MARK(3);
-        group_bar<GW * 32>(bar);
-        QZ_MARK(9);                 /* waiting for the group's slowest sub-piece */
-        uint32_t *slotw = reinterpret_cast<uint32_t *>(job.slots + (size_t)g0 * job.slot_stride);
-        const uint32_t npc = (wlen + PIECE - 1) >> 13;          /* 8 KiB job pieces with data */
-        /* leader: one set of codes, one block header for the window */
-        if (wg == 0) {
-            uint32_t extra_total = 0;
-            for (int i = 0; i < GW; i++) extra_total += G.extra[i];
-            const int btype = choose_block(C.cs, C.hist, extra_total, (5 * npc + wlen) * 8, job.static_huffman, lane QZ_TPASS);
-            uint32_t hb = 0, pend = 0;
-            if (btype) open_block(C.cs, C.hist, btype, gfinal, slotw, s_lentab, lane, &hb, &pend QZ_TPASS);
-            if (lane == 0) { G.btype = (uint32_t)btype; G.hb = hb; G.pend = pend; }
-            QZ_MARK(11);            /* leader: block header written, tables final */
-        }
-        group_bar<GW * 32>(bar);
-        QZ_MARK(10);                /* waiting for the leader */
-        const uint32_t jp = wg / WPP;                           /* this warp's 8 KiB job piece */
-        const bool jp_owner = wg % WPP == 0 && jp < npc;
-        if (G.btype == 0) {
-            /* incompressible window: every 8 KiB piece is its own stored block in its own slot */
-            if (jp_owner) {
-                const uint32_t pn = min((uint32_t)PIECE, wlen - jp * PIECE);
-                const uint32_t out_bytes = stored_piece(job.slots + (size_t)(g0 + jp) * job.slot_stride, wsrc + jp * PIECE, pn, gfinal && jp == npc - 1, lane);
-                if (lane == 0) job.piece_len[g0 + jp] = out_bytes;
-            }
-        } else {
-            const uint32_t *tab = C.hist;
-            const uint32_t NT = G.nslots[wg];
-            const uint32_t R = run_length(NT);
-            const uint32_t beg = min(lane * R, NT), end = min(beg + R, NT);
-            const uint32_t mybits = count_run_bits(tab, slots, beg, end, pkeep);
-            uint32_t incl = mybits;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-            if (lane == 31) G.bits[wg] = incl;
-            QZ_MARK(12);            /* count pass */
-            group_bar<GW * 32>(bar);
-            QZ_MARK(13);
-            uint32_t before = G.hb, total = G.hb;
-#pragma unroll
-            for (int i = 0; i < GW; i++) {
-                const uint32_t bi = G.bits[i];
-                if (i < (int)wg) before += bi;
-                total += bi;
-            }
-            const uint32_t end_bit = total;
-            const uint32_t nz = 3 + ((0u - (end_bit + 3)) & 7);
-            const uint32_t end_bit2 = gfinal ? end_bit : end_bit + nz + 32;
-            const uint32_t start = before + incl - mybits;
-            slotw[start >> 5] = 0;
-            if (wg == GW - 1 && lane == 31) slotw[end_bit2 >> 5] = 0;
-            group_bar<GW * 32>(bar);
-            QZ_MARK(14);
-            /* the lane that codes the end-of-block slot appends the trailer; it is the last slot of the window */
-            const bool owns_eob = last_in_win && beg < NT && end == NT;
-            emit_run(tab, slots, beg, end, start, G.pend, wg == 0 && lane == 0, !gfinal && owns_eob, nz, slotw, pkeep);
-            if (lane == 0 && jp_owner) job.piece_len[g0 + jp] = wg == 0 ? (end_bit2 + 7) >> 3 : 0u;        /* pieces behind a ragged end have no entry */
-        }
-        __syncwarp();
-        QZ_MARK(8);
+        if (!have) break;
+        prev_gi = gi;
     }
 }
 
@@ -1230,29 +1258,25 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
 
 extern "C" int qzb_deflate_max_warps(int window) { return window ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
-/* shared memory of the window kernel: `nunits` units of tables with `tent` entries, `groups` block coders */
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int gw, int groups, int nunits)
+/* shared memory of the window kernel with `groups` groups (a unit and two block coders each) of tables with `tent` entries */
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups)
 {
-    return (size_t)nunits * window_unit_bytes((uint32_t)tent, (uint32_t)gw) + (size_t)groups * sizeof(BlockCoder);
+    return (size_t)groups * (window_unit_bytes((uint32_t)tent) + 2 * sizeof(BlockCoder));
 }
+/* 32-bit words of slot scratch the window kernel needs for a grid of CTAs with `groups` groups */
+extern "C" size_t qzb_deflate_window_tok_words(int grid, int groups) { return (size_t)grid * groups * QZW_GROUP_WARPS * QZW_TOK_WORDS; }
 
-/* window kernel (one deflate block per 64 KiB window): `groups` groups of `gw` (8 or 16) warps per CTA share `nunits` units;
- * job->ngroups and job->tent set */
-template <int GW>
-static cudaError_t launch_window(const QzbCompressJob &job, int grid, int groups, int nunits, cudaStream_t st)
+/* window kernel (one deflate block per 64 KiB window): `groups` groups of sixteen warps per CTA; job->ngroups and job->tent set */
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, cudaStream_t st)
 {
-    const size_t smem = qzb_deflate_window_smem_bytes((int)job.tent, GW, groups, nunits);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    qzb_deflate_window_kernel<GW><<<grid, groups * GW * 32, smem, st>>>(job, nunits);
-    return cudaGetLastError();
-}
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int gw, int groups, int nunits, cudaStream_t st)
-{
-    if ((gw != 8 && gw != 16) || groups < 1 || groups * gw > QZ_GROUPS_MAX_WARPS || nunits < 1 || nunits > groups || job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups ||
+    if (groups < 1 || groups * (int)QZW_GROUP_WARPS > QZ_GROUPS_MAX_WARPS || job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups ||
         job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768)
         return cudaErrorInvalidValue;
-    return gw == 8 ? launch_window<8>(*job, grid, groups, nunits, st) : launch_window<16>(*job, grid, groups, nunits, st);
+    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent, groups);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qzb_deflate_window_kernel<<<grid, groups * QZW_GROUP_WARPS * 32, smem, st>>>(*job);
+    return cudaGetLastError();
 }
 
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)

@@ -25,13 +25,14 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int gw, int groups, int nunits, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, cudaStream_t st);
+extern "C" size_t qzb_deflate_window_tok_words(int grid, int groups);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int gw, int groups, int nunits);
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -94,11 +95,9 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     /* deflate, hw_buff_sz >= 64 KiB: 1 = window kernel (64 KiB windows in shared memory, one block per window), 0 = one block per
      * 8 KiB piece with a private window everywhere */
     t->window = env_int("QZB200_WINDOW", QZB200_WINDOW_DEFAULT);
-    t->window_tent = env_int("QZB200_WINDOW_TENT", QZB200_WINDOW_TENT_DEFAULT);      /* entries of a warp's hash table (2 bytes each, eight tables per unit) */
+    t->window_tent = env_int("QZB200_WINDOW_TENT", QZB200_WINDOW_TENT_DEFAULT);      /* entries of a matcher's hash table (2 bytes each, fifteen tables per unit) */
     if (t->window_tent < 256 || t->window_tent > 8192) t->window_tent = QZB200_WINDOW_TENT_DEFAULT;
-    t->window_warps = env_int("QZB200_WINDOW_WARPS", 16);                             /* warps per window: 16 (4 KiB each) or 8 (8 KiB each) */
-    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups per CTA (0 = as many as 32 warps make) */
-    t->window_units = env_int("QZB200_WINDOW_UNITS", 0);                              /* units per CTA (0 = as many as fit, at most the groups) */
+    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups of sixteen warps per CTA (0 = 2) */
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -281,7 +280,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, groups = 0, nunits = 0, gw = 16;
+    int nbuf = t.buffers_per_cta, groups = 0;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
@@ -293,13 +292,11 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         const uint32_t wpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
         job.tent = (uint32_t)t.window_tent;
-        gw = t.window_warps == 8 ? 8 : 16;
-        const int maxg = qzb_deflate_max_warps(1) / gw;
+        const int maxg = qzb_deflate_max_warps(1) / 16;
         groups = t.window_groups > 0 ? std::min(t.window_groups, maxg) : maxg;
-        nunits = t.window_units > 0 ? std::min(t.window_units, groups) : groups;
-        while (nunits > 1 && qzb_deflate_window_smem_bytes((int)job.tent, gw, groups, nunits) + 3072 > smem_cap) nunits--;
-        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, gw, groups, nunits);
-        warps = groups * gw;
+        while (groups > 1 && qzb_deflate_window_smem_bytes((int)job.tent, groups) + 3072 > smem_cap) groups--;
+        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, groups);
+        warps = groups * 16;
     } else {
         if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
@@ -316,7 +313,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((size_t)grid * warps * QZB_TOK_STRIDE(PIECE) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((job.ngroups ? qzb_deflate_window_tok_words(grid, groups) : (size_t)grid * warps * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
@@ -328,7 +325,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, gw, groups, nunits, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, groups, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

@@ -13,8 +13,8 @@
  *             run of the same byte from ITS start; every other position's candidate is the table entry.  Candidates are
  *             verified and extended 12 bytes in the lane; the greedy parse of the tile -- which lanes start a token -- is
  *             found by pointer doubling over next(lane) = lane + max(1, L) instead of a serial walk, matches that reach
- *             the 12-byte cap are finished by the whole warp, a selected match takes over up to four literals in front of
- *             it when the bytes before position and candidate agree.                                      (qzm_match_piece)
+ *             the 12-byte cap are finished by the whole warp, a selected match takes over the literal in front of it when
+ *             the byte before position and candidate agrees.                                      (qzm_match_piece)
  *
  * With one piece and an empty table the same routine is the private-window matcher of the per-piece kernels.
  * Tokens leave through a sink: 16-bit slots for deflate, (position, length, distance) records for LZ4.
@@ -44,6 +44,7 @@ __device__ __forceinline__ void qzm_prepass(const uint8_t *win, uint32_t n, uint
     __syncwarp();
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(win);
     const uint32_t sh = (lane & 3) * 8;
+#pragma unroll 4
     for (uint32_t base = p0; base < p1; base += 32) {
         const uint32_t p = base + lane;
         const uint32_t *pw = ww + (p >> 2);
@@ -142,13 +143,13 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         const uint32_t *cw = ww + (c >> 2);
         const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
         const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
-        uint32_t L = x1 ? 4 + ((__ffs(x1) - 1) >> 3) : x2 ? 8 + ((__ffs(x2) - 1) >> 3) : QZM_LANE_CAP;
+        const uint32_t xx = x1 ? x1 : x2;
+        uint32_t L = (x1 ? 4u : 8u) + (xx ? (uint32_t)(__ffs(xx) - 1) >> 3 : 4u);     /* 4..12 = QZM_LANE_CAP */
         const uint32_t room = mend > p ? mend - p : 0u;          /* bytes a match starting here may cover */
         L = min(L, min(Sink::kMaxMatch, room));
         if (!has || x0 || L < Sink::kMinMatch) L = 0;
-        /* bytes in front of position and candidate that agree (at most 4, never in front of the window) */
-        uint32_t back = 0;
-        if (L) { const uint32_t xb = qzm_ld32u(ww - 1, p) ^ qzm_ld32u(ww - 1, c); back = min(xb ? (uint32_t)__clz(xb) >> 3 : 4u, c); }
+        /* the byte in front of position and candidate agrees (and the candidate is not the window's first byte) */
+        const bool back = L != 0 && c != 0 && prevb == win[(int)c - 1];
 
         /* greedy parse by pointer doubling: R = lanes visited from this lane on, N = where that walk leaves the tile */
         uint32_t R = 1u << lane, N = lane + (L ? L : 1u);
@@ -183,14 +184,12 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         }
         tokmask &= __ballot_sync(QZM_FULL, p < p1);
         uint32_t matchmask = tokmask & __ballot_sync(QZM_FULL, L != 0);
-        /* a selected match takes over the literals right in front of it while the bytes agree */
+        /* a selected match takes over the literal right in front of it when that byte agrees too */
         {
             const uint32_t lit = tokmask & ~matchmask;
-            const uint32_t below = lane ? min(lane, (uint32_t)__clz(~lit << (32 - lane))) : 0u;     /* literal tokens directly below this lane */
-            const uint32_t ext = ((matchmask >> lane) & 1) ? min(min(back, below), Sink::kMaxMatch - L) : 0u;
-            const uint32_t kill = __reduce_or_sync(QZM_FULL, ext ? ((1u << lane) - (1u << (lane - ext))) : 0u);
-            tokmask &= ~kill;
-            sink.put(tokmask, matchmask, lane, lt, p - ext, v, L + ext, p - cand);
+            const bool ext = back && lane != 0 && ((matchmask >> lane) & (lit >> (lane - 1)) & 1) && L < Sink::kMaxMatch;
+            tokmask &= ~(__ballot_sync(QZM_FULL, ext) >> 1);
+            sink.put(tokmask, matchmask, lane, lt, p - (ext ? 1u : 0u), v, L + (ext ? 1u : 0u), p - cand);
         }
         entry = leave - 32;
     }

@@ -145,11 +145,11 @@ def test_deflate_output_does_not_depend_on_geometry(emu, port):
     b, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=7, nbuf=2, grid=1)
     c, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=20, nbuf=17, grid=3)
     assert a == b == c
-    g1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=1, grid=2, window=8, hb=10)
-    g2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=2, grid=1, window=8, hb=10)
+    g1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=16, nbuf=1, grid=2, window=1, hb=10)
+    g2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=2, grid=1, window=1, hb=10)
     assert g1 == g2
-    h1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=16, nbuf=1, grid=2, window=16, hb=1344)
-    h2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=2, grid=1, window=16, hb=1344)
+    h1, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=16, nbuf=1, grid=2, window=1, hb=1344)
+    h2, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=32, nbuf=2, grid=1, window=1, hb=1344)
     assert h1 == h2 and port.decompress(h1, E.FMT_GZIP_EXT, len(data) + 16) == data
     assert port.decompress(g1, E.FMT_GZIP_EXT, len(data) + 16) == data
 
@@ -342,10 +342,10 @@ def decode_any(port, blob, fmt, n):
 @pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000),
                                          ("zeros", lambda n: b"\0" * n, 100000), ("tiny", sil, 37), ("one_byte", sil, 1),
                                          ("piece_edge", sil, 65536 + 8192), ("mixed", lambda n: sil(30000) + noise(40000) + sil(n - 70000), 170000)])
-@pytest.mark.parametrize("gw,hb", [(8, 11), (16, 1344)])
-def test_window_deflate_round_trip(emu, port, fmt, name, make, n, gw, hb):
+@pytest.mark.parametrize("hb", [11, 1344])
+def test_window_deflate_round_trip(emu, port, fmt, name, make, n, hb):
     data = make(n)
-    blob, cks = emu.deflate(data, fmt, warps=gw, nbuf=1, grid=2, window=gw, hb=hb)
+    blob, cks = emu.deflate(data, fmt, warps=16, grid=2, window=1, hb=hb)
     assert decode_any(port, blob, fmt, n) == data
     want = zlib.adler32 if fmt == E.FMT_ZLIB else zlib.crc32
     assert cks == [want(data[i:i + 65536]) for i in range(0, n, 65536)]
@@ -355,9 +355,8 @@ def test_window_deflate_round_trip(emu, port, fmt, name, make, n, gw, hb):
 
 
 @pytest.mark.parametrize("chunk", [65536, 131072, 524288])
-@pytest.mark.parametrize("geom", [dict(window=8, warps=8, nbuf=1, grid=3), dict(window=8, warps=16, nbuf=2, grid=1), dict(window=8, warps=24, nbuf=2, grid=1), dict(window=8, warps=8, nbuf=1, grid=1, hb=12),
-                                  dict(window=8, warps=32, nbuf=2, grid=1, hb=11), dict(window=8, warps=16, nbuf=2, grid=1, hb=2800), dict(window=16, warps=16, nbuf=1, grid=2, hb=10),
-                                  dict(window=16, warps=32, nbuf=2, grid=1, hb=1344), dict(window=16, warps=32, nbuf=1, grid=2, hb=9), dict(window=16, warps=16, nbuf=1, grid=3, hb=11)])
+@pytest.mark.parametrize("geom", [dict(window=1, warps=16, grid=3), dict(window=1, warps=32, grid=1, hb=10), dict(window=1, warps=16, grid=1, hb=12), dict(window=1, warps=32, grid=2, hb=1344),
+                                  dict(window=1, warps=32, grid=1, hb=9), dict(window=1, warps=16, grid=2, hb=700)])
 def test_window_deflate_geometries_and_chunks(emu, port, chunk, geom):
     data = sil(chunk + chunk // 2 + 4321)
     blob, cks = emu.deflate(data, E.FMT_GZIP_EXT, chunk=chunk, **geom)
@@ -369,7 +368,7 @@ def test_window_deflate_geometries_and_chunks(emu, port, chunk, geom):
 
 def test_window_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
     data = sil(1 << 20)
-    grouped, _ = emu.deflate(data, E.FMT_RAW, warps=8, nbuf=4, grid=2, window=8)
+    grouped, _ = emu.deflate(data, E.FMT_RAW, warps=16, nbuf=4, grid=2, window=1)
     pieces, _ = emu.deflate(data, E.FMT_RAW)
     assert inflate_raw(grouped)[0] == data
     assert len(grouped) < len(pieces)                  # 7 of 8 block headers and flush markers are gone
@@ -381,26 +380,26 @@ def test_window_deflate_one_block_per_64k_and_smaller_than_per_piece(emu):
 
 def test_window_deflate_static_and_not_last(emu):
     data = sil(100000)
-    blob, _ = emu.deflate(data, E.FMT_RAW, static=1, warps=8, nbuf=2, grid=1, window=8)
+    blob, _ = emu.deflate(data, E.FMT_RAW, static=1, warps=16, nbuf=2, grid=1, window=1)
     out, eof, _ = inflate_raw(blob)
     assert out == data and eof and (blob[0] >> 1) & 3 in (0, 1)
-    blob, _ = emu.deflate(data, E.FMT_RAW, last=0, warps=8, nbuf=2, grid=1, window=8)
+    blob, _ = emu.deflate(data, E.FMT_RAW, last=0, warps=16, nbuf=2, grid=1, window=1)
     out, eof, used = inflate_raw(blob)
     assert out == data and not eof and used == len(blob) and blob[-4:] == b"\x00\x00\xff\xff"
 
 
 def test_window_deflate_dest_too_small_keeps_whole_chunks(emu):
     data = sil(200000)
-    full, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, window=8)
+    full, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=16, nbuf=3, grid=2, window=1)
     members = walk_gzip(full, ext=True)
     two = members[2][0] - 24
-    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100, warps=8, nbuf=3, grid=2, window=8)
+    part, _ = emu.deflate(data, E.FMT_GZIP_EXT, cap=two + 100, warps=16, nbuf=3, grid=2, window=1)
     assert part == full[:two]
 
 
 def test_window_streams_decode_with_our_inflate(emu):
     data = sil(200000)
-    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=8, nbuf=3, grid=2, window=8)
+    blob, _ = emu.deflate(data, E.FMT_GZIP_EXT, warps=16, nbuf=3, grid=2, window=1)
     members = [one_member(ln, isize, crc, src_off=off, dst_off=i * 65536) for i, (off, ln, crc, isize, _) in enumerate(walk_gzip(blob, ext=True))]
     out, res = emu.decode(E.FMT_GZIP_EXT, blob, members, len(data))
     assert [r.status for r in res] == [E.ST_OK] * len(members) and out == data

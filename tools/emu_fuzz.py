@@ -55,11 +55,7 @@ while time.time() - t0 < budget:
     try:
         if what < 0.55 and n:
             tag = "window"
-            if rng.random() < 0.5:
-                blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=16, hb=rng.choice([9, 10, 700, 1344]), warps=rng.choice([16, 32]), nbuf=rng.randint(1, 2), grid=rng.randint(1, 3))
-            else:
-              hb = rng.choice([9, 10, 11, 700, 2800])
-              blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=8, hb=hb, warps=rng.choice([8, 16] if hb == 2800 else [8, 16, 32]), nbuf=rng.randint(1, 2), grid=rng.randint(1, 3))
+            blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=1, hb=rng.choice([9, 10, 700, 1344]), warps=rng.choice([16, 32]), grid=rng.randint(1, 3))
         elif what < 0.85:
             tag = "piece"
             chunk = rng.choice([1024, 4096, 16384, 65536, 131072])

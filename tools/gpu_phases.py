@@ -12,7 +12,7 @@ d_in, d_out = L.qzb200DeviceAlloc(n), L.qzb200DeviceAlloc(cap)
 assert L.qzb200CopyToDevice(d_in, h, n) == 0
 sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536)
 names = ["ticket + unit/buffer wait", "load+crc", "match+select", "slot histogram", "sort", "huffman lengths", "header plan+cost", "codes+prefix", "emit",
-         "wait: slowest piece of the window", "wait: leader", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "prepass + seed (with their barriers)"]
+         "wait: slowest matcher / coder", "coder: waiting for the matchers", "leader: header emit + tables", "count pass", "wait: bit totals", "wait: zeroed words", "prepass + seed (with their barriers)"]
 out = (C.c_ulonglong * 16)()
 for it in range(3):
     L.qzb_phase_cycles_read(out, 1)

@@ -31,6 +31,7 @@ struct Params {
     int tile = 1;          // scheme 2: 0 table only, 1 in-tile candidate preferred, 2 best of both
     int maxd = 32768;
     int lz4 = 0;
+    int bcap = 4;          // most bytes a match is extended backwards
     int dd = 4, sublanes = 16;   // tile >= 3: direct distances checked; tile >= 4: lanes per lookup/insert sub-step
     int tent = 0;          // scheme 2: table entries when not a power of two (multiply-shift range reduction)
     int nir = 0;           // scheme 2: positions inside a byte run (p-1..p+3 equal) are not inserted
@@ -234,7 +235,7 @@ static long model_chunk2(const uint8_t *src, int n, const Params &P, long *ntok_
                 if (L[p]) {
                     int q = p;
                     if (P.bext) { const int lo = P.bext == 1 ? std::max(anchor, w0) : anchor; const int d = D[p];
-                        while (q > lo && L[q] < 258 && q - 1 - d >= 0 && src[q - 1] == src[q - 1 - d]) { L[q - 1] = L[q] + 1; D[q - 1] = d; L[q] = 0; q--; } }
+                        while (q > lo && p - q < P.bcap && L[q] < 258 && q - 1 - d >= 0 && src[q - 1] == src[q - 1 - d]) { L[q - 1] = L[q] + 1; D[q - 1] = d; L[q] = 0; q--; } }
                     p = q + L[q]; anchor = p;
                 } else p++;
             }
@@ -276,7 +277,7 @@ int main(int argc, char **argv)
         else if (k == "warp") P.warp = v; else if (k == "winner") P.winner = v; else if (k == "mb") total = (size_t)v << 20; else if (k == "kind") kind = v;
         else if (k == "lazy") P.lazy = v; else if (k == "ways") P.ways = v; else if (k == "only") only = eq + 1;
         else if (k == "scheme") P.scheme = v; else if (k == "pp") P.pp = v; else if (k == "tile") P.tile = v; else if (k == "maxd") P.maxd = v;
-        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "dd") P.dd = v; else if (k == "sublanes") P.sublanes = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
+        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "dd") P.dd = v; else if (k == "bcap") P.bcap = v; else if (k == "sublanes") P.sublanes = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
     }
     std::vector<uint8_t> buf;
     if (file) {
