@@ -832,10 +832,12 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
  * the QAT engine emits for a 64 KiB request with its 32 KiB history (reference src/qatzip_utils.c:270-291).
  *
  * A group is sixteen warps that own a shared-memory UNIT (the window's bytes and fifteen hash tables): fifteen MATCHERS,
- * each with a sub-piece of 4384 bytes (137 tiles; the last one 4160), and one CODER.  The matchers run the stages of
- * qz_match.cuh (load + checksum + prepass, seed, match: every position has the whole window in front of it as history
- * while the sub-pieces are matched concurrently), leave their tokens as slots in the L2 scratch and add them to the
- * window's histogram.  The coder turns that histogram into code tables and the block header (sort, Huffman lengths,
+ * each with a sub-piece of 4384 bytes (137 tiles; the last one 4160), and one CODER.  The coder draws the window and has it
+ * copied into the unit by one TMA bulk copy (cp.async.bulk, completion on the group's mbarrier) that is issued the moment
+ * the matchers have finished with the window before and runs while they emit; it also takes the window's checksum.  The
+ * matchers run the stages of qz_match.cuh (prepass, seed, match: every position has the whole window in front of it as
+ * history while the sub-pieces are matched concurrently), leave their tokens as slots in the L2 scratch and add them to
+ * the window's histogram.  The coder turns that histogram into code tables and the block header (sort, Huffman lengths,
  * header plan, canonical codes: a few thousand mostly serial instructions) WHILE the matchers are already matching the
  * next window; when they are done with that, they meet the coder, and emit the window before: every warp counts its
  * slots' bits, the totals are scanned through shared memory, boundary words are zeroed, and every lane packs its run at
@@ -891,6 +893,49 @@ __device__ __forceinline__ WindowGeom window_geometry(const QzbCompressJob &job,
     return w;
 }
 
+/* Checksum of the window in shared memory by one warp (the coder): CRC-32, or packed Adler-32 sums for zlib streams.
+ * Lane i owns the strip [n - (32 - i) S, n - (31 - i) S) with S = 2052 bytes (513 words: the lanes' byte loads fall into
+ * different banks), as four quarters of 513 bytes with independent dependency chains.  The strips' remainders are "pure"
+ * (no initial value, no final inversion): positions in front of the window count as zero bytes and leave a pure remainder
+ * untouched, so short windows take the same code; crc32(M) = pure(M) ^ crc32(|M| zero bytes).
+ * s_xw[0] = x^(8 * 513), s_xw[1 + k] = x^(8 * 2052 * 2^k), s_xw[6] = crc32 of 65536 zero bytes. */
+#define QZW_CK_STRIP 2052
+#define QZW_CK_QUARTER 513
+__device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n, int fmt, const uint32_t *s_crc_tab, const uint32_t *s_xw, uint32_t lane)
+{
+    const int hi = (int)n - (int)((31 - lane) * QZW_CK_STRIP), lo = hi - QZW_CK_STRIP;
+    if (fmt == QZB_FMT_ZLIB) {
+        /* Adler-32 sums of the strip (2052 < NMAX: no reduction inside), joined up a tree like the CRC terms */
+        uint32_t s1 = 0, s2 = 0;
+        for (int i = lo < 0 ? 0 : lo; i < hi; i++) { s1 += win[i]; s2 += s1; }
+        s2 %= QZ_ADLER_P;
+        uint64_t len = (uint64_t)(hi > 0 ? hi - (lo < 0 ? 0 : lo) : 0);
+#pragma unroll 1
+        for (int lv = 0; lv < 5; lv++) {
+            const uint32_t o1 = __shfl_down_sync(FULL, s1, 1u << lv), o2 = __shfl_down_sync(FULL, s2, 1u << lv);
+            const uint64_t olen = __shfl_down_sync(FULL, len, 1u << lv);
+            if ((lane & ((2u << lv) - 1)) == 0) { qz_adler_join(&s1, &s2, o1, o2, olen); len += olen; }
+        }
+        return __shfl_sync(FULL, qz_adler_pack(s1, s2), 0);
+    }
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 1
+    for (int j = 0; j < QZW_CK_QUARTER; j++) {
+        const int q0 = lo + j, q1 = q0 + QZW_CK_QUARTER, q2 = q1 + QZW_CK_QUARTER, q3 = q2 + QZW_CK_QUARTER;
+        const uint32_t b0 = q0 >= 0 ? win[q0] : 0u, b1 = q1 >= 0 ? win[q1] : 0u, b2 = q2 >= 0 ? win[q2] : 0u, b3 = q3 >= 0 ? win[q3] : 0u;
+        c0 = s_crc_tab[(c0 ^ b0) & 0xff] ^ (c0 >> 8); c1 = s_crc_tab[(c1 ^ b1) & 0xff] ^ (c1 >> 8);
+        c2 = s_crc_tab[(c2 ^ b2) & 0xff] ^ (c2 >> 8); c3 = s_crc_tab[(c3 ^ b3) & 0xff] ^ (c3 >> 8);
+    }
+    uint32_t c = qz_gf2_mul(qz_gf2_mul(qz_gf2_mul(c0, s_xw[0]) ^ c1, s_xw[0]) ^ c2, s_xw[0]) ^ c3;
+#pragma unroll 1
+    for (int lv = 0; lv < 5; lv++) {
+        const uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
+        if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xw[1 + lv]) ^ other;
+    }
+    c = __shfl_sync(FULL, c, 0);
+    return c ^ (n == QZ_WINDOW ? s_xw[6] : ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(n)));
+}
+
 __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job)
 {
     constexpr uint32_t SUB = QZW_SUB, NM = QZW_MATCHERS, GW = QZW_GROUP_WARPS;
@@ -898,17 +943,18 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
     static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
-    __shared__ uint32_t s_xstrip[5];
-    __shared__ uint32_t s_xafter[NM];       /* x^(8 * bytes behind sub-piece i of a full window) */
+    __shared__ uint32_t s_xw[7];
     __shared__ uint16_t s_lentab[256];
+    __shared__ uint64_t s_mbar[QZ_GROUPS_MAX_WARPS / GW];       /* "window k is in the unit", one phase per window */
     __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW][2];
-    constexpr uint32_t STRIP = SUB / 32 + 4;
 
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, ngroups_cta = nwarps / GW;
     const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
-    if (threadIdx.x < 5) s_xstrip[threadIdx.x] = qz_crc_xpow8((uint64_t)STRIP << threadIdx.x);
-    if (threadIdx.x < NM) s_xafter[threadIdx.x] = qz_crc_xpow8((uint64_t)(QZ_WINDOW - min(QZ_WINDOW, (threadIdx.x + 1) * SUB)));
+    if (threadIdx.x == 0) s_xw[0] = qz_crc_xpow8(QZW_CK_QUARTER);
+    if (threadIdx.x >= 1 && threadIdx.x < 6) s_xw[threadIdx.x] = qz_crc_xpow8((uint64_t)QZW_CK_STRIP << (threadIdx.x - 1));
+    if (threadIdx.x == 6) s_xw[6] = ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(QZ_WINDOW));
+    if (threadIdx.x < ngroups_cta) qz_mbar_init(&s_mbar[threadIdx.x]);
     __syncthreads();
 
     const uint32_t grp = warp / GW, wg = warp % GW;
@@ -917,13 +963,33 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
     uint8_t *unit = smem_raw + (size_t)grp * unit_bytes;
     uint8_t *win = unit + QZM_FRONT_PAD;
     uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
+    uint64_t *mbar = &s_mbar[grp];
     const uint64_t pkeep = l2_policy_keep();
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
 
     if (wg == NM) {
-        /* ---- the coder: codes and block header of window k - 1 while the matchers work on window k ---- */
+        /* ---- the coder: draws the windows, has them copied into the unit (TMA bulk copy, completion on the group's
+         * mbarrier), checksums them, and builds codes and block header of window k - 1 while the matchers work on window k ---- */
+        auto fetch = [&](uint32_t k) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(job.ticket, 1u);
+            tk = __shfl_sync(FULL, tk, 0);
+            uint32_t bulk = 0;
+            const uint8_t *src = job.src;
+            if (tk < job.ngroups) {
+                const WindowGeom w = window_geometry(job, tk);
+                src = w.wsrc;
+                bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? w.wlen & ~15u : 0u;       /* the rest by hand: a ragged tail, or everything from an unaligned source */
+                for (uint32_t i = bulk + lane; i < w.wlen; i += 32) win[i] = src[i];
+                for (uint32_t i = lane; i < QZM_TAIL_PAD; i += 32) win[w.wlen + i] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) { s_grp[grp][k & 1].ticket = tk; qz_bulk_load_arrive(win, src, bulk, mbar); }
+            __syncwarp();
+        };
+        fetch(0);
         for (uint32_t k = 0;; k++) {
             if (k) {
                 WindowShared &P = s_grp[grp][(k - 1) & 1];
@@ -937,9 +1003,19 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
                 if (lane == 0) { P.btype = (uint32_t)btype; P.hb = hb; P.pend = pend; }
                 QZ_MARK(11);
             }
+            const uint32_t gi = s_grp[grp][k & 1].ticket;
+            const bool have = gi < job.ngroups;
+            if (have) {
+                const WindowGeom w = window_geometry(job, gi);
+                qz_mbar_wait(mbar, k);
+                const uint32_t ck = window_checksum(win, w.wlen, job.fmt, s_crc_tab, s_xw, lane);
+                if (lane == 0) job.piece_crc[w.g0] = ck;
+                QZ_MARK(1);
+            }
             group_bar<GW * 32>(bar_f);
             QZ_MARK(10);                /* coder: waiting for the matchers */
-            if (s_grp[grp][k & 1].ticket >= job.ngroups) break;
+            if (!have) break;
+            fetch(k + 1);               /* every matcher is done reading window k */
         }
         return;
     }
@@ -955,43 +1031,20 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
         WindowShared &G = s_grp[grp][b];
         BlockCoder &C = coders[b];
         uint16_t *slots = slots2 + (size_t)b * 2 * QZB_TOK_STRIDE(SUB);
-        if (wg == 0 && lane == 0) G.ticket = atomicAdd(job.ticket, 1u);
-        group_bar<NM * 32>(bar_m);
+        qz_mbar_wait(mbar, k);
         QZ_MARK(0);
-        /* every matcher is past the emission of window k - 2: its code tables (same parity as window k) can go */
         const uint32_t gi = G.ticket;
         const bool have = gi < job.ngroups;
         if (have) {
-            if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
             const WindowGeom w = window_geometry(job, gi);
             const uint32_t n = w.wlen > p0 ? min(SUB, w.wlen - p0) : 0u;                  /* bytes of this warp's sub-piece */
             const bool last_in_win = n != 0 && p0 + n == w.wlen;
-            /* load + checksum + prepass of the warp's own sub-piece
-             * (a sub-piece's last three positions hash bytes of the next one, which may not have arrived: they are left out) */
-            if (n) {
-                const uint32_t c = load_and_checksum<SUB>(win + p0, w.wsrc + p0, n, last_in_win, job.fmt, s_crc_tab, s_xstrip, lane);
-                if (lane == 0) G.cksum[wg] = c;
-                QZ_MARK(1);
-                qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
-            }
+            /* (a sub-piece's last three positions hash bytes of the next one: they are left to the match stage) */
+            if (n) qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
             group_bar<NM * 32>(bar_m);
+            /* every matcher is past the emission of window k - 2: its code tables (same parity as window k) can go */
+            if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
             qzm_seed_tables(tables, tstride, w.nsub, tent, threadIdx.x - grp * (GW * 32), NM * 32);
-            /* the window's checksum from the sub-pieces' (CRC-32: every term times x^(8 * bytes behind it), XOR-ed) */
-            if (wg == NM - 1) {
-                uint32_t ck = 0;
-                if (job.fmt == QZB_FMT_ZLIB) {
-                    if (lane == 0) {
-                        uint32_t s1 = 0, s2 = 0;
-                        for (uint32_t i = 0; i < w.nsub; i++) { const uint32_t x = G.cksum[i]; qz_adler_join(&s1, &s2, x & 0xffffu, x >> 16, min(SUB, w.wlen - i * SUB)); }
-                        ck = qz_adler_pack(s1, s2);
-                    }
-                } else {
-                    if (lane < w.nsub) ck = qz_gf2_mul(G.cksum[lane], w.wlen == QZ_WINDOW ? s_xafter[lane] : qz_crc_xpow8(w.wlen - min(w.wlen, (lane + 1) * SUB)));
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) ck ^= __shfl_xor_sync(FULL, ck, o);
-                }
-                if (lane == 0) job.piece_crc[w.g0] = ck;
-            }
             group_bar<NM * 32>(bar_m);
             QZ_MARK(15);
             QzmDeflateSink sink = { slots, 0, pkeep };

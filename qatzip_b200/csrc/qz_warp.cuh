@@ -17,6 +17,10 @@ static inline void tok_st(uint32_t *a, uint32_t v, uint64_t) { *a = v; }
 static inline void tok16_st(uint16_t *a, uint16_t v, uint64_t) { *a = v; }
 static inline uint4 stream_ld16(const uint4 *a, uint64_t) { return *a; }
 static inline void slot_st(uint32_t *a, uint32_t v) { *a = v; }
+/* bulk copy + mbarrier: the copy is synchronous here, the barrier a count of completed phases */
+static inline void qz_mbar_init(uint64_t *mb) { *mb = 0; }
+static inline void qz_mbar_wait(uint64_t *mb, uint32_t k) { while (*reinterpret_cast<volatile uint64_t *>(mb) <= k) __nanosleep(0); }
+static inline void qz_bulk_load_arrive(void *dst, const void *src, uint32_t bytes, uint64_t *mb) { memcpy(dst, src, bytes); *mb += 1; }
 #else
 /* whole words of compressed output: written once, read once by the framing kernel much later */
 __device__ __forceinline__ void slot_st(uint32_t *a, uint32_t v)
@@ -28,6 +32,32 @@ __device__ __forceinline__ void slot_st(uint32_t *a, uint32_t v)
 #endif
 }
 #define QZ_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+/* ---- TMA bulk copy global -> shared, completion on an mbarrier (one arrival + the copy's bytes per phase) ----
+ * qz_mbar_init: one thread, before a CTA barrier.  qz_bulk_load_arrive: one thread; `bytes` a multiple of 16 (0: arrival
+ * only), both addresses 16-byte aligned; everything that thread (and, after a __syncwarp, its warp) wrote before is visible
+ * to whoever passes qz_mbar_wait for that phase.  qz_mbar_wait(mb, k): blocks until phase k (0, 1, 2 ...) is complete. */
+__device__ __forceinline__ void qz_mbar_init(uint64_t *mb)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mb);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void qz_mbar_wait(uint64_t *mb, uint32_t k)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mb), parity = k & 1u;
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void qz_bulk_load_arrive(void *dst, const void *src, uint32_t bytes, uint64_t *mb)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mb), d = (uint32_t)__cvta_generic_to_shared(dst);
+    if (bytes) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
+    } else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(a) : "memory");
+}
 __device__ __forceinline__ uint32_t qz_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 /* L2 residency control.  The token scratch is written once and read twice by the same SM within
