@@ -769,7 +769,7 @@ extern "C" int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *st)
     *st = s->stats; st->device = qzb_runtime_default_device(); st->piece_log2 = t.piece_log2;
     st->group_blocks = (t.window && t.piece_log2 == 13 && s->p.hw_buff_sz % (8u << 13) == 0) ? 1 : 0;
     st->hash_bits = t.hash_bits;
-    if (st->group_blocks) { st->hash_bits = 0; while ((2 << st->hash_bits) <= t.window_tent) st->hash_bits++; }
+    if (st->group_blocks) st->hash_bits = 11;        /* about 2600 entries per table: whatever the shared memory holds */
     return QZ_OK;
 }
 extern "C" void *qzb200DeviceAlloc(uint64_t n) { int d = qzb_runtime_default_device(); return d < 0 ? NULL : qzb_device_alloc(d, (size_t)n); }

@@ -831,30 +831,33 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
 /* Window kernel (default for hw_buff_sz >= 64 KiB): a WINDOW is 64 KiB of one chunk and becomes ONE deflate block, what
  * the QAT engine emits for a 64 KiB request with its 32 KiB history (reference src/qatzip_utils.c:270-291).
  *
- * A group is sixteen warps that own a shared-memory UNIT (the window's bytes and fifteen hash tables): fifteen MATCHERS,
- * each with a sub-piece of 4384 bytes (137 tiles; the last one 4160), and one CODER.  The coder draws the window and has it
- * copied into the unit by one TMA bulk copy (cp.async.bulk, completion on the group's mbarrier) that is issued the moment
- * the matchers have finished with the window before and runs while they emit; it also takes the window's checksum.  The
- * matchers run the stages of qz_match.cuh (prepass, seed, match: every position has the whole window in front of it as
- * history while the sub-pieces are matched concurrently), leave their tokens as slots in the L2 scratch and add them to
- * the window's histogram.  The coder turns that histogram into code tables and the block header (sort, Huffman lengths,
- * header plan, canonical codes: a few thousand mostly serial instructions) WHILE the matchers are already matching the
- * next window; when they are done with that, they meet the coder, and emit the window before: every warp counts its
- * slots' bits, the totals are scanned through shared memory, boundary words are zeroed, and every lane packs its run at
- * its bit offset inside the window's output (the slot of its first 8 KiB piece); the lane that codes the end-of-block
- * slot appends the byte-aligning empty stored block unless the block is final.  Slots, histograms and code tables are
- * double-buffered by window parity.  Incompressible window -> every 8 KiB piece a stored block in its own slot.
- * Two groups per CTA, independent of each other; warps meet at named barriers (matchers only / whole group).
+ * A CTA (one per SM, 32 warps) holds ONE window at a time in shared memory, next to thirty hash tables that take all the
+ * shared memory there is (about 2600 entries each): thirty MATCHERS, each with a sub-piece of 2208 bytes (69 tiles; the
+ * last one 1504), and two CODERS that take turns, window by window.  The coder of window k draws it and has it copied in
+ * by one TMA bulk copy (cp.async.bulk, completion on an mbarrier) that is issued the moment the matchers have finished
+ * with window k - 1 and runs while they emit window k - 2; it takes the window's checksum while the matchers match it.
+ * The matchers run the stages of qz_match.cuh (prepass, seed, match: every position has the whole window in front of it
+ * as history while the sub-pieces are matched concurrently), leave their tokens as slots in the L2 scratch and add them
+ * to the window's histogram.  The same coder then turns that histogram into code tables and the block header (sort,
+ * Huffman lengths, header plan, canonical codes: several thousand mostly serial instructions) WHILE the matchers are
+ * already matching window k + 1 (fetched and checksummed by the other coder); when they are done with that, they meet
+ * the coders, and emit window k: every warp counts its slots' bits, the totals are scanned through shared memory,
+ * boundary words are zeroed, and every lane packs its run at its bit offset inside the window's output (the slot of its
+ * first 8 KiB piece); the lane that codes the end-of-block slot appends the byte-aligning empty stored block unless the
+ * block is final.  Slots, histograms and code tables are double-buffered by window parity.  Incompressible window ->
+ * every 8 KiB piece a stored block in its own slot.  Warps meet at named barriers (matchers only / everybody).
  * The window's checksum goes to piece_crc[] of the window's first 8 KiB piece (the framing kernel combines per window). */
 #define QZ_WINDOW 65536u
 #define QZ_WINDOW_PIECES 8u             /* 8 KiB job pieces (slots, lengths) per window */
-#define QZW_MATCHERS 15u
-#define QZW_GROUP_WARPS 16u
-#define QZW_SUB 4384u                   /* bytes of a matcher's sub-piece: 137 tiles, a multiple of 16 */
+#define QZW_MATCHERS 30u
+#define QZW_CODERS 2u
+#define QZW_WARPS (QZW_MATCHERS + QZW_CODERS)
+#define QZW_SUB 2208u                   /* bytes of a matcher's sub-piece: 69 tiles, a multiple of 16 */
 static_assert(QZW_SUB % 32 == 0 && QZW_SUB * QZW_MATCHERS >= QZ_WINDOW && QZW_SUB * (QZW_MATCHERS - 1) < QZ_WINDOW, "sub-pieces tile the window");
-struct WindowShared {                   /* one per group and window parity */
+static_assert(QZW_WARPS == QZ_GROUPS_MAX_WARPS, "the kernel's launch bound");
+struct WindowShared {                   /* one per window parity */
     uint32_t ticket, btype, hb, pend;
-    uint32_t nslots[QZW_MATCHERS + 1], bits[QZW_MATCHERS + 1], extra[QZW_MATCHERS + 1], cksum[QZW_MATCHERS + 1];
+    uint32_t nslots[QZW_WARPS], bits[QZW_WARPS], extra[QZW_WARPS];
 };
 template <int NT>
 __device__ __forceinline__ void group_bar(uint32_t id)
@@ -938,61 +941,69 @@ __device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n,
 
 __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job)
 {
-    constexpr uint32_t SUB = QZW_SUB, NM = QZW_MATCHERS, GW = QZW_GROUP_WARPS;
+    constexpr uint32_t SUB = QZW_SUB, NM = QZW_MATCHERS, NW = QZW_WARPS;
     constexpr int PIECE = 1 << 13;
     static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
     QZ_DYN_SMEM(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     __shared__ uint32_t s_xw[7];
     __shared__ uint16_t s_lentab[256];
-    __shared__ uint64_t s_mbar[QZ_GROUPS_MAX_WARPS / GW];       /* "window k is in the unit", one phase per window */
-    __shared__ WindowShared s_grp[QZ_GROUPS_MAX_WARPS / GW][2];
+    __shared__ uint64_t s_mbar[1];          /* "window k is in shared memory", one phase per window */
+    __shared__ WindowShared s_win[2];
 
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, ngroups_cta = nwarps / GW;
-    const uint32_t tent = job.tent, tstride = window_table_stride(tent), unit_bytes = window_unit_bytes(tent);
+    const uint32_t lane = lane_id(), wg = threadIdx.x >> 5;
+    const uint32_t tent = job.tent, tstride = window_table_stride(tent);
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
     if (threadIdx.x == 0) s_xw[0] = qz_crc_xpow8(QZW_CK_QUARTER);
     if (threadIdx.x >= 1 && threadIdx.x < 6) s_xw[threadIdx.x] = qz_crc_xpow8((uint64_t)QZW_CK_STRIP << (threadIdx.x - 1));
     if (threadIdx.x == 6) s_xw[6] = ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(QZ_WINDOW));
-    if (threadIdx.x < ngroups_cta) qz_mbar_init(&s_mbar[threadIdx.x]);
+    if (threadIdx.x == 0) qz_mbar_init(&s_mbar[0]);
     __syncthreads();
 
-    const uint32_t grp = warp / GW, wg = warp % GW;
-    const uint32_t bar_m = 1 + 2 * grp, bar_f = 2 + 2 * grp;           /* matchers only / the whole group */
-    BlockCoder *coders = reinterpret_cast<BlockCoder *>(smem_raw + (size_t)ngroups_cta * unit_bytes) + 2 * grp;
-    uint8_t *unit = smem_raw + (size_t)grp * unit_bytes;
-    uint8_t *win = unit + QZM_FRONT_PAD;
-    uint16_t *tables = reinterpret_cast<uint16_t *>(unit + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
-    uint64_t *mbar = &s_mbar[grp];
+    constexpr uint32_t bar_m = 1, bar_f = 2;                           /* matchers only / everybody */
+    BlockCoder *coders = reinterpret_cast<BlockCoder *>(smem_raw + window_unit_bytes(tent));
+    uint8_t *win = smem_raw + QZM_FRONT_PAD;
+    uint16_t *tables = reinterpret_cast<uint16_t *>(smem_raw + QZM_FRONT_PAD + QZ_WINDOW + QZM_TAIL_PAD);
+    uint64_t *mbar = &s_mbar[0];
     const uint64_t pkeep = l2_policy_keep();
 #ifdef QZ_PHASE_CLOCKS
     long long tlast = clock64();
 #endif
 
-    if (wg == NM) {
-        /* ---- the coder: draws the windows, has them copied into the unit (TMA bulk copy, completion on the group's
-         * mbarrier), checksums them, and builds codes and block header of window k - 1 while the matchers work on window k ---- */
-        auto fetch = [&](uint32_t k) {
-            uint32_t tk = 0;
-            if (lane == 0) tk = atomicAdd(job.ticket, 1u);
-            tk = __shfl_sync(FULL, tk, 0);
-            uint32_t bulk = 0;
-            const uint8_t *src = job.src;
-            if (tk < job.ngroups) {
-                const WindowGeom w = window_geometry(job, tk);
-                src = w.wsrc;
-                bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? w.wlen & ~15u : 0u;       /* the rest by hand: a ragged tail, or everything from an unaligned source */
-                for (uint32_t i = bulk + lane; i < w.wlen; i += 32) win[i] = src[i];
-                for (uint32_t i = lane; i < QZM_TAIL_PAD; i += 32) win[w.wlen + i] = 0;
-            }
-            __syncwarp();
-            if (lane == 0) { s_grp[grp][k & 1].ticket = tk; qz_bulk_load_arrive(win, src, bulk, mbar); }
-            __syncwarp();
-        };
-        fetch(0);
+    if (wg >= NM) {
+        /* ---- the coders.  Coder c owns the windows k with k & 1 == c: it draws window k and has it copied in (TMA bulk
+         * copy, completion on the mbarrier) once the matchers are done with window k - 1, checksums it while the matchers
+         * match it, and builds its codes and block header while they match window k + 1. ---- */
+        const uint32_t me = wg - NM;
         for (uint32_t k = 0;; k++) {
-            if (k) {
-                WindowShared &P = s_grp[grp][(k - 1) & 1];
+            WindowShared &G = s_win[k & 1];
+            if ((k & 1) == me) {
+                /* fetch window k (every matcher is done reading window k - 1) */
+                uint32_t tk = 0;
+                if (lane == 0) tk = atomicAdd(job.ticket, 1u);
+                tk = __shfl_sync(FULL, tk, 0);
+                uint32_t bulk = 0, wlen = 0, g0 = 0;
+                const uint8_t *src = job.src;
+                if (tk < job.ngroups) {
+                    const WindowGeom w = window_geometry(job, tk);
+                    src = w.wsrc; wlen = w.wlen; g0 = w.g0;
+                    bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? w.wlen & ~15u : 0u;       /* the rest by hand: a ragged tail, or everything from an unaligned source */
+                    for (uint32_t i = bulk + lane; i < w.wlen; i += 32) win[i] = src[i];
+                    for (uint32_t i = lane; i < QZM_TAIL_PAD; i += 32) win[w.wlen + i] = 0;
+                }
+                __syncwarp();
+                if (lane == 0) { G.ticket = tk; qz_bulk_load_arrive(win, src, bulk, mbar); }
+                __syncwarp();
+                QZ_MARK(0);
+                if (tk < job.ngroups) {
+                    qz_mbar_wait(mbar, k);
+                    const uint32_t ck = window_checksum(win, wlen, job.fmt, s_crc_tab, s_xw, lane);
+                    if (lane == 0) job.piece_crc[g0] = ck;
+                }
+                QZ_MARK(1);
+            } else if (k) {
+                /* codes and block header of window k - 1 */
+                WindowShared &P = s_win[(k - 1) & 1];
                 BlockCoder &C = coders[(k - 1) & 1];
                 const WindowGeom w = window_geometry(job, P.ticket);
                 uint32_t extra_total = 0;
@@ -1003,32 +1014,22 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
                 if (lane == 0) { P.btype = (uint32_t)btype; P.hb = hb; P.pend = pend; }
                 QZ_MARK(11);
             }
-            const uint32_t gi = s_grp[grp][k & 1].ticket;
-            const bool have = gi < job.ngroups;
-            if (have) {
-                const WindowGeom w = window_geometry(job, gi);
-                qz_mbar_wait(mbar, k);
-                const uint32_t ck = window_checksum(win, w.wlen, job.fmt, s_crc_tab, s_xw, lane);
-                if (lane == 0) job.piece_crc[w.g0] = ck;
-                QZ_MARK(1);
-            }
-            group_bar<GW * 32>(bar_f);
-            QZ_MARK(10);                /* coder: waiting for the matchers */
-            if (!have) break;
-            fetch(k + 1);               /* every matcher is done reading window k */
+            group_bar<NW * 32>(bar_f);
+            QZ_MARK(10);                /* coders: waiting for the matchers */
+            if (G.ticket >= job.ngroups) break;
         }
         return;
     }
 
     /* ---- the matchers ---- */
-    const uint32_t gwarp = blockIdx.x * nwarps + warp;
+    const uint32_t gwarp = blockIdx.x * NM + wg;
     uint16_t *slots2 = reinterpret_cast<uint16_t *>(job.tok_scratch + (size_t)gwarp * QZW_TOK_WORDS);
     uint16_t *table = tables + (size_t)wg * tstride;
     const uint32_t p0 = wg * SUB;
     uint32_t prev_gi = 0;
     for (uint32_t k = 0;; k++) {
         const uint32_t b = k & 1;
-        WindowShared &G = s_grp[grp][b];
+        WindowShared &G = s_win[b];
         BlockCoder &C = coders[b];
         uint16_t *slots = slots2 + (size_t)b * 2 * QZB_TOK_STRIDE(SUB);
         qz_mbar_wait(mbar, k);
@@ -1044,7 +1045,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
             group_bar<NM * 32>(bar_m);
             /* every matcher is past the emission of window k - 2: its code tables (same parity as window k) can go */
             if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
-            qzm_seed_tables(tables, tstride, w.nsub, tent, threadIdx.x - grp * (GW * 32), NM * 32);
+            qzm_seed_tables(tables, tstride, w.nsub, tent, threadIdx.x, NM * 32);
             group_bar<NM * 32>(bar_m);
             QZ_MARK(15);
             QzmDeflateSink sink = { slots, 0, pkeep };
@@ -1059,11 +1060,11 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
             }
             QZ_MARK(3);
         }
-        group_bar<GW * 32>(bar_f);
-        QZ_MARK(9);                 /* waiting for the slowest matcher and for the coder */
-        /* ---- emission of window k - 1, whose code tables the coder has just finished ---- */
+        group_bar<NW * 32>(bar_f);
+        QZ_MARK(9);                 /* waiting for the slowest matcher and for the coders */
+        /* ---- emission of window k - 1, whose code tables its coder has just finished ---- */
         if (k) {
-            WindowShared &P = s_grp[grp][b ^ 1];
+            WindowShared &P = s_win[b ^ 1];
             const uint32_t *tab = coders[b ^ 1].hist;
             const uint16_t *pslots = slots2 + (size_t)(b ^ 1) * 2 * QZB_TOK_STRIDE(SUB);
             const WindowGeom w = window_geometry(job, prev_gi);      /* (P.ticket may already hold the ticket of window k + 1) */
@@ -1311,24 +1312,26 @@ extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int
 
 extern "C" int qzb_deflate_max_warps(int window) { return window ? QZ_GROUPS_MAX_WARPS : QZ_PIECES_MAX_WARPS; }
 
-/* shared memory of the window kernel with `groups` groups (a unit and two block coders each) of tables with `tent` entries */
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups)
+/* shared memory of the window kernel: the window, thirty tables of `tent` entries, two block coders */
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent) { return (size_t)window_unit_bytes((uint32_t)tent) + 2 * sizeof(BlockCoder); }
+/* the most entries a table can have with `cap` bytes of dynamic shared memory */
+extern "C" int qzb_deflate_window_max_tent(size_t cap)
 {
-    return (size_t)groups * (window_unit_bytes((uint32_t)tent) + 2 * sizeof(BlockCoder));
+    int tent = 256;
+    while (tent + 8 <= 32768 && qzb_deflate_window_smem_bytes(tent + 8) <= cap) tent += 8;
+    return tent;
 }
-/* 32-bit words of slot scratch the window kernel needs for a grid of CTAs with `groups` groups */
-extern "C" size_t qzb_deflate_window_tok_words(int grid, int groups) { return (size_t)grid * groups * QZW_GROUP_WARPS * QZW_TOK_WORDS; }
+/* 32-bit words of slot scratch the window kernel needs for a grid of CTAs */
+extern "C" size_t qzb_deflate_window_tok_words(int grid) { return (size_t)grid * QZW_MATCHERS * QZW_TOK_WORDS; }
 
-/* window kernel (one deflate block per 64 KiB window): `groups` groups of sixteen warps per CTA; job->ngroups and job->tent set */
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, cudaStream_t st)
+/* window kernel (one deflate block per 64 KiB window), one CTA of 32 warps per SM; job->ngroups and job->tent set */
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, cudaStream_t st)
 {
-    if (groups < 1 || groups * (int)QZW_GROUP_WARPS > QZ_GROUPS_MAX_WARPS || job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups ||
-        job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768)
-        return cudaErrorInvalidValue;
-    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent, groups);
+    if (job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups || job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768) return cudaErrorInvalidValue;
+    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent);
     cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_window_kernel<<<grid, groups * QZW_GROUP_WARPS * 32, smem, st>>>(*job);
+    qzb_deflate_window_kernel<<<grid, QZW_WARPS * 32, smem, st>>>(*job);
     return cudaGetLastError();
 }
 

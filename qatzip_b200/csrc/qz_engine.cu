@@ -25,14 +25,15 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int groups, cudaStream_t st);
-extern "C" size_t qzb_deflate_window_tok_words(int grid, int groups);
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, cudaStream_t st);
+extern "C" size_t qzb_deflate_window_tok_words(int grid);
+extern "C" int qzb_deflate_window_max_tent(size_t cap);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
-extern "C" size_t qzb_deflate_window_smem_bytes(int tent, int groups);
+extern "C" size_t qzb_deflate_window_smem_bytes(int tent);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
@@ -60,9 +61,6 @@ extern "C" int qzb_runtime_devices(void)
 extern "C" int qzb_deflate_max_warps(int group);
 #ifndef QZB200_WINDOW_DEFAULT
 #define QZB200_WINDOW_DEFAULT 1
-#endif
-#ifndef QZB200_WINDOW_TENT_DEFAULT
-#define QZB200_WINDOW_TENT_DEFAULT 1344
 #endif
 static int env_int(const char *name, int dflt) { const char *v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 extern "C" int qzb_runtime_default_device(void)
@@ -95,9 +93,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     /* deflate, hw_buff_sz >= 64 KiB: 1 = window kernel (64 KiB windows in shared memory, one block per window), 0 = one block per
      * 8 KiB piece with a private window everywhere */
     t->window = env_int("QZB200_WINDOW", QZB200_WINDOW_DEFAULT);
-    t->window_tent = env_int("QZB200_WINDOW_TENT", QZB200_WINDOW_TENT_DEFAULT);      /* entries of a matcher's hash table (2 bytes each, fifteen tables per unit) */
-    if (t->window_tent < 256 || t->window_tent > 8192) t->window_tent = QZB200_WINDOW_TENT_DEFAULT;
-    t->window_groups = env_int("QZB200_WINDOW_GROUPS", 0);                            /* groups of sixteen warps per CTA (0 = 2) */
+    t->window_tent = env_int("QZB200_WINDOW_TENT", 0);      /* entries of a matcher's hash table (2 bytes each, thirty tables); 0 = as many as fit */
+    if (t->window_tent && (t->window_tent < 256 || t->window_tent > 8192)) t->window_tent = 0;
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -280,7 +277,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     const size_t smem_cap = 227 * 1024;
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
     /* deflate: NW warps share NB piece buffers (NW ~ 2 NB, see qz_deflate.cu); LZ4 warps each own one */
-    int nbuf = t.buffers_per_cta, groups = 0;
+    int nbuf = t.buffers_per_cta;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
     if (lz4) {
@@ -291,12 +288,11 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         /* window kernel: CTAs of whole groups of 8 warps; as many units as the 227 KB hold, never more than groups */
         const uint32_t wpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
-        job.tent = (uint32_t)t.window_tent;
-        const int maxg = qzb_deflate_max_warps(1) / 16;
-        groups = t.window_groups > 0 ? std::min(t.window_groups, maxg) : maxg;
-        while (groups > 1 && qzb_deflate_window_smem_bytes((int)job.tent, groups) + 3072 > smem_cap) groups--;
-        group_smem = qzb_deflate_window_smem_bytes((int)job.tent, groups);
-        warps = groups * 16;
+        /* the thirty tables take what the window and the block coders leave of the 227 KB (QZB200_WINDOW_TENT: fewer entries) */
+        const int fit = qzb_deflate_window_max_tent(smem_cap - 3072);
+        job.tent = (uint32_t)(t.window_tent > 0 ? std::min(t.window_tent, fit) : fit);
+        group_smem = qzb_deflate_window_smem_bytes((int)job.tent);
+        warps = 32;
     } else {
         if (warps <= 0 || warps > qzb_deflate_max_warps(0)) { warps = 20; if (nbuf <= 0) nbuf = 17; }
         if (nbuf <= 0 || nbuf > warps) nbuf = (warps + 1) / 2;
@@ -313,7 +309,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((job.ngroups ? qzb_deflate_window_tok_words(grid, groups) : (size_t)grid * warps * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((job.ngroups ? qzb_deflate_window_tok_words(grid) : (size_t)grid * warps * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
@@ -325,7 +321,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, groups, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

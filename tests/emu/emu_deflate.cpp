@@ -77,27 +77,26 @@ extern "C" long emu_frame(const QzbCompressJob *jobp, uint32_t *chunk_cksum_out)
 /* One batch through the deflate kernels.  Geometry is the caller's.  Returns bytes produced, -1 for an unsupported geometry,
  * -2 when a kernel wrote past its scratch.
  * window == 0: per-piece kernel (piece size, hash bits, warps and piece buffers per CTA, CTAs);
- * window != 0: window kernel (one deflate block per 64 KiB window): warps / 16 groups per CTA, tables of `hb` entries each when
- *              hb >= 256, else 2^hb (nbuf is ignored). */
+ * window != 0: window kernel (one deflate block per 64 KiB window): CTAs of 32 warps, tables of `hb` entries each when
+ *              hb >= 256, else 2^hb (warps and nbuf are ignored). */
 extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman,
                                      int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int window)
 {
-    if (warps < 1 || warps > 32 || nbuf < 1 || nbuf > warps || grid < 1) return -1;
+    if (grid < 1 || (!window && (warps < 1 || warps > 32 || nbuf < 1 || nbuf > warps))) return -1;
     QzbCompressJob job; EmuCompressBuffers b;
     emu_job_setup(&job, &b, fmt, src, len, chunk_sz, last, static_huffman, piece_log2, grid * warps, dst, cap);
     size_t smem;
     std::function<void()> body;
     if (window) {
-        const int groups = warps / (int)QZW_GROUP_WARPS;
-        if (!len || job.pieces_per_chunk % QZ_WINDOW_PIECES || warps % (int)QZW_GROUP_WARPS || warps > QZ_GROUPS_MAX_WARPS || piece_log2 != 13) return -1;
+        if (!len || job.pieces_per_chunk % QZ_WINDOW_PIECES || piece_log2 != 13) return -1;
         const uint64_t last_len = len - (uint64_t)(job.nchunks - 1) * chunk_sz;
         job.ngroups = (job.nchunks - 1) * (job.pieces_per_chunk / QZ_WINDOW_PIECES) + (uint32_t)((last_len + QZ_WINDOW - 1) / QZ_WINDOW);
         job.tent = hb >= 256 ? (uint32_t)hb : 1u << hb;
-        smem = (size_t)groups * (window_unit_bytes(job.tent) + 2 * sizeof(BlockCoder));
+        smem = (size_t)window_unit_bytes(job.tent) + 2 * sizeof(BlockCoder);
         if (smem > 227 * 1024) return -1;
-        b.tok.assign((size_t)grid * groups * QZW_GROUP_WARPS * QZW_TOK_WORDS, 0xEEEEEEEEu);
+        b.tok.assign((size_t)grid * QZW_MATCHERS * QZW_TOK_WORDS, 0xEEEEEEEEu);
         job.tok_scratch = b.tok.data();
-        emu::launch((unsigned)grid, (unsigned)warps * 32, smem, [&] { qzb_deflate_window_kernel(job); });
+        emu::launch((unsigned)grid, QZW_WARPS * 32, smem, [&] { qzb_deflate_window_kernel(job); });
         const long n = emu_frame(&job, chunk_cksum_out);
         return emu_canaries_ok(b) ? n : -2;
     }

@@ -55,7 +55,7 @@ while time.time() - t0 < budget:
     try:
         if what < 0.55 and n:
             tag = "window"
-            blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=1, hb=rng.choice([9, 10, 700, 1344]), warps=rng.choice([16, 32]), grid=rng.randint(1, 3))
+            blob, cks = emu.deflate(data, fmt, chunk=chunk, static=int(static), window=1, hb=rng.choice([9, 10, 700, 2584]), grid=rng.randint(1, 3))
         elif what < 0.85:
             tag = "piece"
             chunk = rng.choice([1024, 4096, 16384, 65536, 131072])

@@ -31,6 +31,7 @@ struct Params {
     int tile = 1;          // scheme 2: 0 table only, 1 in-tile candidate preferred, 2 best of both
     int maxd = 32768;
     int lz4 = 0;
+    int psamp = 1;         // scheme 2: the prepass (history for later pieces) records every psamp-th position only
     int bcap = 4;          // most bytes a match is extended backwards
     int dd = 4, sublanes = 16;   // tile >= 3: direct distances checked; tile >= 4: lanes per lookup/insert sub-step
     int tent = 0;          // scheme 2: table entries when not a power of two (multiply-shift range reduction)
@@ -203,7 +204,7 @@ static long model_chunk2(const uint8_t *src, int n, const Params &P, long *ntok_
     std::vector<int32_t> carry(TS * WY, -1);
     for (int k = 0; k < np; k++) {
         std::vector<int32_t> T = carry;
-        for (int p = k * P.pp; p < std::min(n, (k + 1) * P.pp); p++) if (p + 4 <= n) ins(carry, hashf(src + p, P), p);
+        for (int p = k * P.pp; p < std::min(n, (k + 1) * P.pp); p++) if (p + 4 <= n && (p % P.psamp) == 0) ins(carry, hashf(src + p, P), p);
         const int e = std::min(n, (k + 1) * P.pp);
         int entry = k * P.pp, anchor = k * P.pp;
         for (int w0 = k * P.pp; w0 < e; w0 += 32) {
@@ -277,7 +278,7 @@ int main(int argc, char **argv)
         else if (k == "warp") P.warp = v; else if (k == "winner") P.winner = v; else if (k == "mb") total = (size_t)v << 20; else if (k == "kind") kind = v;
         else if (k == "lazy") P.lazy = v; else if (k == "ways") P.ways = v; else if (k == "only") only = eq + 1;
         else if (k == "scheme") P.scheme = v; else if (k == "pp") P.pp = v; else if (k == "tile") P.tile = v; else if (k == "maxd") P.maxd = v;
-        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "dd") P.dd = v; else if (k == "bcap") P.bcap = v; else if (k == "sublanes") P.sublanes = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
+        else if (k == "lz4") P.lz4 = v; else if (k == "bext") P.bext = v; else if (k == "dd") P.dd = v; else if (k == "bcap") P.bcap = v; else if (k == "psamp") P.psamp = v; else if (k == "sublanes") P.sublanes = v; else if (k == "tent") P.tent = v; else if (k == "nir") P.nir = v; else if (k == "file") file = eq + 1;
     }
     std::vector<uint8_t> buf;
     if (file) {
