@@ -896,19 +896,20 @@ __device__ __forceinline__ WindowGeom window_geometry(const QzbCompressJob &job,
     return w;
 }
 
-/* Checksum of the window in shared memory by one warp (the coder): CRC-32, or packed Adler-32 sums for zlib streams.
- * Lane i owns the strip [n - (32 - i) S, n - (31 - i) S) with S = 2052 bytes (513 words: the lanes' byte loads fall into
- * different banks), as four quarters of 513 bytes with independent dependency chains.  The strips' remainders are "pure"
- * (no initial value, no final inversion): positions in front of the window count as zero bytes and leave a pure remainder
- * untouched, so short windows take the same code; crc32(M) = pure(M) ^ crc32(|M| zero bytes).
- * s_xw[0] = x^(8 * 513), s_xw[1 + k] = x^(8 * 2052 * 2^k), s_xw[6] = crc32 of 65536 zero bytes. */
+/* Checksum of the window in shared memory by one warp (a coder): CRC-32, or packed Adler-32 sums for zlib streams.
+ * Lane i owns the strip [m - (32 - i) S, m - (31 - i) S) of the window's whole words (m = n & ~3) with S = 2052 bytes (513
+ * words: the lanes' loads fall into different banks), as three thirds of 684 bytes with independent dependency chains,
+ * four bytes per step through four tables (slicing by 4).  The strips' remainders are "pure" (no initial value, no final
+ * inversion): positions in front of the window count as zero bytes and leave a pure remainder untouched, so short windows
+ * take the same code; the up to three bytes behind m continue the joined remainder; crc32(M) = pure(M) ^ crc32(|M| zero bytes).
+ * s_xw[0] = x^(8 * 684), s_xw[1 + k] = x^(8 * 2052 * 2^k), s_xw[6] = crc32 of 65536 zero bytes. */
 #define QZW_CK_STRIP 2052
-#define QZW_CK_QUARTER 513
-__device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n, int fmt, const uint32_t *s_crc_tab, const uint32_t *s_xw, uint32_t lane)
+#define QZW_CK_THIRD 684
+__device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n, int fmt, const uint32_t *s_crc_tab /* [4][256] */, const uint32_t *s_xw, uint32_t lane)
 {
-    const int hi = (int)n - (int)((31 - lane) * QZW_CK_STRIP), lo = hi - QZW_CK_STRIP;
     if (fmt == QZB_FMT_ZLIB) {
         /* Adler-32 sums of the strip (2052 < NMAX: no reduction inside), joined up a tree like the CRC terms */
+        const int hi = (int)n - (int)((31 - lane) * QZW_CK_STRIP), lo = hi - QZW_CK_STRIP;
         uint32_t s1 = 0, s2 = 0;
         for (int i = lo < 0 ? 0 : lo; i < hi; i++) { s1 += win[i]; s2 += s1; }
         s2 %= QZ_ADLER_P;
@@ -921,21 +922,28 @@ __device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n,
         }
         return __shfl_sync(FULL, qz_adler_pack(s1, s2), 0);
     }
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const uint32_t m = n & ~3u;
+    const int lo = (int)m - (int)((32 - lane) * QZW_CK_STRIP);
+    const uint32_t *T0 = s_crc_tab, *T1 = s_crc_tab + 256, *T2 = s_crc_tab + 512, *T3 = s_crc_tab + 768;
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+#define QZ_CRC_STEP4(c, w) do { c ^= (w); c = T3[c & 0xff] ^ T2[(c >> 8) & 0xff] ^ T1[(c >> 16) & 0xff] ^ T0[c >> 24]; } while (0)
 #pragma unroll 1
-    for (int j = 0; j < QZW_CK_QUARTER; j++) {
-        const int q0 = lo + j, q1 = q0 + QZW_CK_QUARTER, q2 = q1 + QZW_CK_QUARTER, q3 = q2 + QZW_CK_QUARTER;
-        const uint32_t b0 = q0 >= 0 ? win[q0] : 0u, b1 = q1 >= 0 ? win[q1] : 0u, b2 = q2 >= 0 ? win[q2] : 0u, b3 = q3 >= 0 ? win[q3] : 0u;
-        c0 = s_crc_tab[(c0 ^ b0) & 0xff] ^ (c0 >> 8); c1 = s_crc_tab[(c1 ^ b1) & 0xff] ^ (c1 >> 8);
-        c2 = s_crc_tab[(c2 ^ b2) & 0xff] ^ (c2 >> 8); c3 = s_crc_tab[(c3 ^ b3) & 0xff] ^ (c3 >> 8);
+    for (int j = 0; j < QZW_CK_THIRD; j += 4) {
+        const int q0 = lo + j, q1 = q0 + QZW_CK_THIRD, q2 = q1 + QZW_CK_THIRD;
+        const uint32_t w0 = q0 >= 0 ? *reinterpret_cast<const uint32_t *>(win + q0) : 0u;
+        const uint32_t w1 = q1 >= 0 ? *reinterpret_cast<const uint32_t *>(win + q1) : 0u;
+        const uint32_t w2 = q2 >= 0 ? *reinterpret_cast<const uint32_t *>(win + q2) : 0u;
+        QZ_CRC_STEP4(c0, w0); QZ_CRC_STEP4(c1, w1); QZ_CRC_STEP4(c2, w2);
     }
-    uint32_t c = qz_gf2_mul(qz_gf2_mul(qz_gf2_mul(c0, s_xw[0]) ^ c1, s_xw[0]) ^ c2, s_xw[0]) ^ c3;
+#undef QZ_CRC_STEP4
+    uint32_t c = qz_gf2_mul(qz_gf2_mul(c0, s_xw[0]) ^ c1, s_xw[0]) ^ c2;
 #pragma unroll 1
     for (int lv = 0; lv < 5; lv++) {
         const uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);   /* right neighbour block */
         if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, s_xw[1 + lv]) ^ other;
     }
     c = __shfl_sync(FULL, c, 0);
+    for (uint32_t i = m; i < n; i++) c = T0[(c ^ win[i]) & 0xff] ^ (c >> 8);
     return c ^ (n == QZ_WINDOW ? s_xw[6] : ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(n)));
 }
 
@@ -945,7 +953,7 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
     constexpr int PIECE = 1 << 13;
     static_assert(sizeof(BlockCoder) % 16 == 0, "block coders are laid end to end");
     QZ_DYN_SMEM(smem_raw);
-    __shared__ uint32_t s_crc_tab[256];
+    __shared__ uint32_t s_crc_tab[4 * 256];         /* slicing by 4 */
     __shared__ uint32_t s_xw[7];
     __shared__ uint16_t s_lentab[256];
     __shared__ uint64_t s_mbar[1];          /* "window k is in shared memory", one phase per window */
@@ -953,8 +961,13 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
 
     const uint32_t lane = lane_id(), wg = threadIdx.x >> 5;
     const uint32_t tent = job.tent, tstride = window_table_stride(tent);
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) { s_crc_tab[i] = qz_crc_table_entry(i); s_lentab[i] = len_table_entry(i); }
-    if (threadIdx.x == 0) s_xw[0] = qz_crc_xpow8(QZW_CK_QUARTER);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t e = qz_crc_table_entry(i);
+        s_lentab[i] = len_table_entry(i);
+        s_crc_tab[i] = e;
+        for (int t = 1; t < 4; t++) { e = (e >> 8) ^ qz_crc_table_entry(e & 0xff); s_crc_tab[t * 256 + i] = e; }
+    }
+    if (threadIdx.x == 0) s_xw[0] = qz_crc_xpow8(QZW_CK_THIRD);
     if (threadIdx.x >= 1 && threadIdx.x < 6) s_xw[threadIdx.x] = qz_crc_xpow8((uint64_t)QZW_CK_STRIP << (threadIdx.x - 1));
     if (threadIdx.x == 6) s_xw[6] = ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(QZ_WINDOW));
     if (threadIdx.x == 0) qz_mbar_init(&s_mbar[0]);

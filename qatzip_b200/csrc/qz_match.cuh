@@ -151,19 +151,18 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         /* the byte in front of position and candidate agrees (and the candidate is not the window's first byte) */
         const bool back = L != 0 && c != 0 && prevb == win[(int)c - 1];
 
-        /* greedy parse by pointer doubling: R = lanes visited from this lane on, N = where that walk leaves the tile */
-        uint32_t R = 1u << lane, N = lane + (L ? L : 1u);
+        /* greedy parse by pointer doubling: R = lanes visited from this lane on, N = the lane that walk has reached (a lane
+         * whose token leaves the tile points at itself), E = where this lane's token ends */
+        const uint32_t E = lane + (L ? L : 1u);
+        uint32_t R = 1u << lane, N = E < 32 ? E : lane;
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const uint32_t Rn = __shfl_sync(QZM_FULL, R, N & 31), Nn = __shfl_sync(QZM_FULL, N, N & 31);
-            if (N < 32) { R |= Rn; N = Nn; }
-        }
+        for (int r = 0; r < 5; r++) { R |= __shfl_sync(QZM_FULL, R, N); N = __shfl_sync(QZM_FULL, N, N); }
         const uint32_t longmask = __ballot_sync(QZM_FULL, L >= QZM_LANE_CAP && L < min(Sink::kMaxMatch, room));
         uint32_t tokmask = 0, cur = entry, leave;
         for (;;) {
             const uint32_t Rc = __shfl_sync(QZM_FULL, R, cur);
             const uint32_t U = Rc & longmask;
-            if (!U) { tokmask |= Rc; leave = __shfl_sync(QZM_FULL, N, cur); break; }
+            if (!U) { tokmask |= Rc; leave = __shfl_sync(QZM_FULL, E, 31 - __clz(Rc)); break; }
             /* the walk is right up to its first match that reached the lane cap: the warp finishes that one */
             const uint32_t m = __ffs(U) - 1;
             tokmask |= Rc & (QZM_FULL >> (31 - m));
