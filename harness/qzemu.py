@@ -40,6 +40,8 @@ class Emu:
                                            V, C.c_uint64, V, C.c_int]
         L.emu_lz4_compress.restype = C.c_long
         L.emu_lz4_compress.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
+        L.emu_lz4_window.restype = C.c_long
+        L.emu_lz4_window.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_inflate.argtypes = [C.c_int, V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int, C.c_int]
         L.emu_lz4_decompress.argtypes = [V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int]
 
@@ -64,6 +66,17 @@ class Emu:
         dst = C.create_string_buffer(cap)
         ck = (C.c_uint32 * nch)()
         n = self.lib.emu_lz4_compress(data, len(data), chunk, piece_log2, warps, grid, dst, cap, ck)
+        assert n >= 0
+        return dst.raw[:n], list(ck)
+
+    def lz4_window(self, data, chunk=65536, tent=6900, nw=12, grid=2):
+        """window kernel: one LZ4 block per 64 KiB -> (frames, [XXH32 per chunk])"""
+        data = bytes(data)
+        nch = max(1, (len(data) + chunk - 1) // chunk)
+        cap = len(data) + len(data) // 8 + 512 * nch + 64
+        dst = C.create_string_buffer(cap)
+        ck = (C.c_uint32 * nch)()
+        n = self.lib.emu_lz4_window(data, len(data), chunk, tent, nw, grid, dst, cap, ck)
         assert n >= 0
         return dst.raw[:n], list(ck)
 

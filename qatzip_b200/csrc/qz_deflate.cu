@@ -1327,9 +1327,13 @@ extern "C" int qzb_deflate_max_warps(int window) { return window ? QZ_GROUPS_MAX
 
 /* shared memory of the window kernel: the window, thirty tables of `tent` entries, two block coders */
 extern "C" size_t qzb_deflate_window_smem_bytes(int tent) { return (size_t)window_unit_bytes((uint32_t)tent) + 2 * sizeof(BlockCoder); }
-/* the most entries a table can have with `cap` bytes of dynamic shared memory */
-extern "C" int qzb_deflate_window_max_tent(size_t cap)
+/* the most entries a table can have: what the 227 KB per CTA leave after the kernel's static shared memory, the window and the
+ * block coders */
+extern "C" int qzb_deflate_window_max_tent(void)
 {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, qzb_deflate_window_kernel) != cudaSuccess) { (void)cudaGetLastError(); return 256; }
+    const size_t cap = 227 * 1024 - a.sharedSizeBytes - 64;
     int tent = 256;
     while (tent + 8 <= 32768 && qzb_deflate_window_smem_bytes(tent + 8) <= cap) tent += 8;
     return tent;

@@ -27,7 +27,7 @@
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_window_tok_words(int grid);
-extern "C" int qzb_deflate_window_max_tent(size_t cap);
+extern "C" int qzb_deflate_window_max_tent(void);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
@@ -35,6 +35,10 @@ extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, in
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
 extern "C" size_t qzb_deflate_window_smem_bytes(int tent);
 extern "C" size_t qzb_lz4_smem_bytes(int piece_log2, int warps);
+extern "C" cudaError_t qzb_launch_lz4_window(const QzbCompressJob *job, int grid, int nw, cudaStream_t st);
+extern "C" size_t qzb_lz4_window_smem_bytes(int tent, int nw);
+extern "C" int qzb_lz4_window_max_tent(int nw);
+extern "C" size_t qzb_lz4_window_tok_words(int grid, int nw);
 
 /* qatzip.h return codes used here (kept numeric so this file does not depend on the public header) */
 enum { RC_OK = 0, RC_PARAMS = -1, RC_FAIL = -2, RC_BUF_ERROR = -3, RC_DATA_ERROR = -4 };
@@ -95,6 +99,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->window = env_int("QZB200_WINDOW", QZB200_WINDOW_DEFAULT);
     t->window_tent = env_int("QZB200_WINDOW_TENT", 0);      /* entries of a matcher's hash table (2 bytes each, thirty tables); 0 = as many as fit */
     if (t->window_tent && (t->window_tent < 256 || t->window_tent > 8192)) t->window_tent = 0;
+    t->lz4_warps = env_int("QZB200_LZ4_WARPS", 12);         /* LZ4 window kernel: 12 warps (tables of ~6900 entries) or 16 (~5200) */
     int wmb = env_int("QZB200_ZLIB_WINDOW_MB", 128);
     if (wmb < 1) wmb = 1;
     if (wmb > 2048) wmb = 2048;
@@ -280,7 +285,17 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     int nbuf = t.buffers_per_cta;
     size_t group_smem = 0;
     auto smem_for = [&](int w, int nb) { return lz4 ? qzb_lz4_smem_bytes(t.piece_log2, w) : qzb_deflate_smem_bytes(t.piece_log2, t.hash_bits, w, nb); };
-    if (lz4) {
+    int lz4_nw = 0;
+    if (lz4 && t.window && t.piece_log2 == 13 && len && job.pieces_per_chunk % 8 == 0) {
+        /* LZ4 window kernel: one block per 64 KiB window, one CTA per SM, tables as large as the shared memory allows */
+        const uint32_t wpc = job.pieces_per_chunk / 8;
+        job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
+        lz4_nw = t.lz4_warps == 16 ? 16 : 12;
+        const int fit = qzb_lz4_window_max_tent(lz4_nw);
+        job.tent = (uint32_t)(t.window_tent > 0 ? std::min(t.window_tent, fit) : fit);
+        group_smem = qzb_lz4_window_smem_bytes((int)job.tent, lz4_nw);
+        warps = lz4_nw; nbuf = 0;
+    } else if (lz4) {
         if (warps <= 0 || warps > 16) warps = 16;
         while (warps > 1 && smem_for(warps, 0) + 2304 > smem_cap) warps--;
         nbuf = 0;
@@ -289,7 +304,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
         const uint32_t wpc = job.pieces_per_chunk / 8;
         job.ngroups = (job.nchunks - 1) * wpc + (last_pieces + 7) / 8;
         /* the thirty tables take what the window and the block coders leave of the 227 KB (QZB200_WINDOW_TENT: fewer entries) */
-        const int fit = qzb_deflate_window_max_tent(smem_cap - 3072);
+        const int fit = qzb_deflate_window_max_tent();
         job.tent = (uint32_t)(t.window_tent > 0 ? std::min(t.window_tent, fit) : fit);
         group_smem = qzb_deflate_window_smem_bytes((int)job.tent);
         warps = 32;
@@ -309,7 +324,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     if (s.d_slots.ensure((size_t)job.npieces * job.slot_stride + 64) != RC_OK) return RC_FAIL;
     MetaLayout ml = meta_layout(job.npieces, job.nchunks);
     if (s.d_meta.ensure(ml.total) != RC_OK || s.h_meta.ensure(ml.piece_len) != RC_OK) return RC_FAIL;
-    if (s.d_tok.ensure((job.ngroups ? qzb_deflate_window_tok_words(grid) : (size_t)grid * warps * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
+    if (s.d_tok.ensure((lz4_nw ? qzb_lz4_window_tok_words(grid, lz4_nw) : job.ngroups ? qzb_deflate_window_tok_words(grid) : (size_t)grid * warps * QZB_TOK_STRIDE(PIECE)) * 4) != RC_OK) return RC_FAIL;
     uint8_t *dm = (uint8_t *)s.d_meta.p;
     job.slots = (uint8_t *)s.d_slots.p;
     job.piece_len = (uint32_t *)(dm + ml.piece_len); job.piece_crc = (uint32_t *)(dm + ml.piece_crc);
@@ -320,7 +335,8 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
 
     CK(cudaMemsetAsync(job.ticket, 0, 16, s.st));
     CK(cudaEventRecord(s.ev_k0, s.st));
-    if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
+    if (lz4_nw) CK(qzb_launch_lz4_window(&job, grid, lz4_nw, s.st));
+    else if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
     else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, s.st));
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));

@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include "qz_kernels.cuh"
 #include "qz_warp.cuh"
+#include "qz_match.cuh"
 #include "qz_xxh32.h"
 
 #define FULL 0xffffffffu
@@ -193,6 +194,161 @@ __global__ void __launch_bounds__(512) qzb_lz4_pieces_kernel(QzbCompressJob job)
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Window kernel (hw_buff_sz >= 64 KiB): 64 KiB of a chunk become ONE LZ4 block, as in the reference's sessions
+ * (lz4BlockMaxSize = 64 KiB, reference src/qatzip_utils.c:292-298, src/qatzip_sw.c:443-471).  A CTA holds one window in
+ * shared memory next to its warps' hash tables that take the rest of it (about 5000 entries each); sixteen warps match a
+ * sub-piece of 4 KiB each with the stages of qz_match.cuh (every position has the whole window in front of it as history),
+ * leave (position, length, distance) records in the L2 scratch, size their sequences, scan the sizes through shared
+ * memory and write the block at byte offsets; literals are read from global memory again, so the next window's TMA bulk
+ * copy (issued by warp 0 as soon as everybody has matched) overlaps the encoding.  A block that would not be smaller than
+ * its input is stored. */
+#define QZL_MAX_WARPS 16u
+struct Lz4WindowShared { uint32_t ticket[2]; uint32_t nrec[QZL_MAX_WARPS], last_end[QZL_MAX_WARPS], bytes[QZL_MAX_WARPS]; };
+/* bytes of a warp's sub-piece when `nw` warps share the window: whole tiles, a multiple of 16 (16 warps: 4096, 12 warps: 5504) */
+__host__ __device__ __forceinline__ uint32_t lz4_sub_bytes(uint32_t nw) { return ((65536u + nw - 1) / nw + 31u) & ~31u; }
+__host__ __device__ __forceinline__ uint32_t lz4_table_stride(uint32_t tent) { return (tent + 8u) & ~7u; }
+__host__ __device__ __forceinline__ uint32_t lz4_window_smem(uint32_t tent, uint32_t nw) { return QZM_FRONT_PAD + 65536u + QZM_TAIL_PAD + nw * 2u * lz4_table_stride(tent); }
+
+/* Sequences of the records [0, nrec): sizes, and with `out` their bytes at out[0...).  prev_end = where the literals of the
+ * first sequence start.  Returns the bytes of all sequences; *last_end = end of the last match (prev_end if there is none). */
+__device__ __forceinline__ uint32_t lz4_encode_records(const uint32_t *recs, uint32_t nrec, uint32_t prev_end, uint8_t *out, const uint8_t *src, uint32_t lane, uint32_t *last_end)
+{
+    uint32_t total = 0, carry = prev_end;
+    for (uint32_t r0 = 0; r0 < nrec; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        uint32_t pos = 0, len = 0, dist = 0, sz = 0, lit = 0, lit_start = 0;
+        const bool have = r < nrec;
+        if (have) { const uint32_t a = __ldcg(recs + 2 * r); dist = __ldcg(recs + 2 * r + 1); pos = a & 0xffff; len = a >> 16; }
+        const uint32_t my_end = have ? pos + len : 0;
+        uint32_t before = __shfl_up_sync(FULL, my_end, 1);
+        if (lane == 0) before = carry;
+        if (have) { lit_start = before; lit = pos - lit_start; sz = 1 + lz4_ext(lit) + lit + 2 + lz4_ext(len - 4); }
+        uint32_t incl = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        if (out) {
+            uint8_t *o = out + total + incl - sz;
+            if (have) {
+                *o++ = (uint8_t)((lit >= 15 ? 15u : lit) << 4 | (len - 4 >= 15 ? 15u : len - 4));
+                o = lz4_put_ext(o, lit);
+                if (lit <= 16) for (uint32_t i = 0; i < lit; i++) o[i] = src[lit_start + i];
+                uint8_t *q = o + lit;
+                *q++ = (uint8_t)dist; *q++ = (uint8_t)(dist >> 8);
+                lz4_put_ext(q, len - 4);
+            }
+            /* long literal runs are copied by the whole warp */
+            uint32_t big = __ballot_sync(FULL, have && lit > 16);
+            while (big) {
+                const uint32_t l = __ffs(big) - 1; big &= big - 1;
+                const uint32_t n = __shfl_sync(FULL, lit, l), from = __shfl_sync(FULL, lit_start, l);
+                uint8_t *to = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(o), l));
+                for (uint32_t i = lane; i < n; i += 32) to[i] = src[from + i];
+            }
+        }
+        total += __shfl_sync(FULL, incl, 31);
+        carry = __shfl_sync(FULL, my_end, min(31u, nrec - r0 - 1));
+    }
+    *last_end = carry;
+    return total;
+}
+
+template <int QZL_WARPS>
+__global__ void __launch_bounds__(QZL_WARPS * 32) qzb_lz4_window_kernel(QzbCompressJob job)
+{
+    constexpr uint32_t QZL_SUB = ((65536u + QZL_WARPS - 1) / QZL_WARPS + 31u) & ~31u;
+    QZ_DYN_SMEM(smem_raw);
+    __shared__ uint64_t s_mbar[1];
+    __shared__ Lz4WindowShared G;
+    const uint32_t lane = lz_lane(), wg = threadIdx.x >> 5;
+    const uint32_t tent = job.tent, tstride = lz4_table_stride(tent);
+    uint8_t *win = smem_raw + QZM_FRONT_PAD;
+    uint16_t *tables = reinterpret_cast<uint16_t *>(smem_raw + QZM_FRONT_PAD + 65536u + QZM_TAIL_PAD);
+    uint16_t *table = tables + (size_t)wg * tstride;
+    uint32_t *recs = job.tok_scratch + (size_t)(blockIdx.x * QZL_WARPS + wg) * QZB_TOK_STRIDE(QZL_SUB);
+    const uint32_t wpc = job.pieces_per_chunk / 8;          /* windows per chunk */
+    if (threadIdx.x == 0) qz_mbar_init(&s_mbar[0]);
+    __syncthreads();
+
+    /* warp 0: draw window k and have it copied in (everything behind the 16-byte-aligned part by hand) */
+    auto fetch = [&](uint32_t k) {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(job.ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        uint32_t bulk = 0;
+        const uint8_t *src = job.src;
+        if (tk < job.ngroups) {
+            const uint32_t chunk = tk / wpc, blk = tk - chunk * wpc;
+            const uint64_t off = (uint64_t)chunk * job.chunk_sz + (uint64_t)blk * 65536u;
+            const uint32_t wlen = (uint32_t)min((uint64_t)65536u, min((uint64_t)chunk * job.chunk_sz + job.chunk_sz, job.src_len) - off);
+            src = job.src + off;
+            bulk = (reinterpret_cast<uintptr_t>(src) & 15) == 0 ? wlen & ~15u : 0u;
+            for (uint32_t i = bulk + lane; i < wlen; i += 32) win[i] = src[i];
+            for (uint32_t i = lane; i < QZM_TAIL_PAD; i += 32) win[wlen + i] = 0;
+        }
+        __syncwarp();
+        if (lane == 0) { G.ticket[k & 1] = tk; qz_bulk_load_arrive(win, src, bulk, &s_mbar[0]); }
+        __syncwarp();
+    };
+    if (wg == 0) fetch(0);
+    for (uint32_t k = 0;; k++) {
+        qz_mbar_wait(&s_mbar[0], k);
+        const uint32_t gi = G.ticket[k & 1];
+        if (gi >= job.ngroups) break;
+        const uint32_t chunk = gi / wpc, blk = gi - chunk * wpc;
+        const uint32_t g0 = chunk * job.pieces_per_chunk + blk * 8;
+        const uint64_t off = (uint64_t)chunk * job.chunk_sz + (uint64_t)blk * 65536u;
+        const uint32_t wlen = (uint32_t)min((uint64_t)65536u, min((uint64_t)chunk * job.chunk_sz + job.chunk_sz, job.src_len) - off);
+        const uint8_t *src = job.src + off;
+        const uint32_t nsub = (wlen + QZL_SUB - 1) / QZL_SUB, npc = (wlen + 8191u) >> 13;
+        const uint32_t p0 = wg * QZL_SUB, n = wlen > p0 ? min(QZL_SUB, wlen - p0) : 0u;
+        if (n) qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
+        __syncthreads();
+        qzm_seed_tables(tables, tstride, nsub, tent, threadIdx.x, QZL_WARPS * 32);
+        __syncthreads();
+        QzmLz4Sink sink = { recs, 0 };
+        if (n) qzm_match_piece(win, wlen, p0, p0 + n, table, tent, sink, lane);
+        uint32_t my_last = 0;
+        if (sink.nrec) { const uint32_t a = __ldcg(recs + 2 * (sink.nrec - 1)); my_last = (a & 0xffff) + (a >> 16); }
+        if (lane == 0) { G.nrec[wg] = sink.nrec; G.last_end[wg] = my_last; }
+        __syncthreads();
+        /* everybody has matched: the next window may come in while this one is encoded */
+        if (wg == 0) fetch(k + 1);
+        /* where this warp's first literal run starts: the end of the last match in front of its records */
+        uint32_t prev_end = 0, lastw = 0;
+        for (uint32_t i = 0; i < QZL_WARPS; i++) { if (G.nrec[i]) { lastw = i; if (i < wg) prev_end = G.last_end[i]; } }
+        uint32_t dummy;
+        uint32_t bytes = lz4_encode_records(recs, sink.nrec, prev_end, nullptr, src, lane, &dummy);
+        const uint32_t final_end = G.last_end[lastw];            /* 0 when the window has no match at all */
+        const uint32_t tail = wlen - final_end, tail_sz = 1 + lz4_ext(tail) + tail;
+        if (wg == lastw) bytes += tail_sz;
+        if (lane == 0) G.bytes[wg] = bytes;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t i = 0; i < QZL_WARPS; i++) { const uint32_t bi = G.bytes[i]; if (i < wg) before += bi; total += bi; }
+        uint8_t *slot = job.slots + (size_t)g0 * job.slot_stride, *out = slot + 4;
+        uint32_t blk_bytes;
+        if (total < wlen) {
+            uint32_t le;
+            const uint32_t mine = lz4_encode_records(recs, sink.nrec, prev_end, out + before, src, lane, &le);
+            if (wg == lastw) {
+                uint8_t *o = out + before + mine;
+                if (lane == 0) { *o = (uint8_t)((tail >= 15 ? 15u : tail) << 4); lz4_put_ext(o + 1, tail); }
+                o += 1 + lz4_ext(tail);
+                for (uint32_t i = lane; i < tail; i += 32) o[i] = src[final_end + i];
+            }
+            blk_bytes = total;
+            if (threadIdx.x == 0) { slot[0] = (uint8_t)total; slot[1] = (uint8_t)(total >> 8); slot[2] = (uint8_t)(total >> 16); slot[3] = 0; }
+        } else {
+            for (uint32_t i = threadIdx.x; i < wlen; i += QZL_WARPS * 32) out[i] = src[i];
+            blk_bytes = wlen;
+            if (threadIdx.x == 0) { slot[0] = (uint8_t)wlen; slot[1] = (uint8_t)(wlen >> 8); slot[2] = (uint8_t)(wlen >> 16); slot[3] = 0x80; }
+        }
+        if (lane == 0 && wg < npc) job.piece_len[g0 + wg] = wg == 0 ? blk_bytes + 4 : 0u;
+        __syncthreads();            /* G is reused by the next window */
+    }
+}
+
 /* ---- XXH32 of every chunk: 4 lanes per chunk (one per accumulator), 8 chunks per warp ----
  * reference src/xxhash.c:404-437 (stripe loop) / :328-400 (finalize) */
 __global__ void __launch_bounds__(256) qzb_xxh32_chunks_kernel(QzbCompressJob job)
@@ -341,6 +497,35 @@ static cudaError_t launch_lz4(const QzbCompressJob &job, int grid, int warps, cu
     cudaError_t e = cudaFuncSetAttribute(qzb_lz4_pieces_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     qzb_lz4_pieces_kernel<P><<<grid, warps * 32, smem, st>>>(job);
+    return cudaGetLastError();
+}
+/* window kernel with `nw` (12 or 16) warps: the most entries a table can have, shared memory for them, slot scratch for a grid */
+extern "C" size_t qzb_lz4_window_smem_bytes(int tent, int nw) { return lz4_window_smem((uint32_t)tent, (uint32_t)nw); }
+extern "C" int qzb_lz4_window_max_tent(int nw)
+{
+    cudaFuncAttributes a;
+    if ((nw == 12 ? cudaFuncGetAttributes(&a, qzb_lz4_window_kernel<12>) : cudaFuncGetAttributes(&a, qzb_lz4_window_kernel<16>)) != cudaSuccess) { (void)cudaGetLastError(); return 256; }
+    const size_t cap = 227 * 1024 - a.sharedSizeBytes - 64;
+    int tent = 256;
+    while (tent + 8 <= 32760 && lz4_window_smem((uint32_t)tent + 8, (uint32_t)nw) <= cap) tent += 8;
+    return tent;
+}
+extern "C" size_t qzb_lz4_window_tok_words(int grid, int nw) { return (size_t)grid * nw * QZB_TOK_STRIDE(lz4_sub_bytes((uint32_t)nw)); }
+template <int NW>
+static cudaError_t launch_lz4_window(const QzbCompressJob &job, int grid, cudaStream_t st)
+{
+    const size_t smem = lz4_window_smem(job.tent, NW);
+    cudaError_t e = cudaFuncSetAttribute(qzb_lz4_window_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    qzb_lz4_window_kernel<NW><<<grid, NW * 32, smem, st>>>(job);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_lz4_window(const QzbCompressJob *job, int grid, int nw, cudaStream_t st)
+{
+    if ((nw != 12 && nw != 16) || job->pieces_per_chunk % 8 || !job->ngroups || job->piece_log2 != 13 || job->tent < 256 || job->tent > 32760) return cudaErrorInvalidValue;
+    cudaError_t e = nw == 12 ? launch_lz4_window<12>(*job, grid, st) : launch_lz4_window<16>(*job, grid, st);
+    if (e != cudaSuccess) return e;
+    qzb_xxh32_chunks_kernel<<<(job->nchunks * 4 + 255) / 256, 256, 0, st>>>(*job);
     return cudaGetLastError();
 }
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st)

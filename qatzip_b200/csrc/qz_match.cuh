@@ -99,7 +99,7 @@ struct QzmDeflateSink {
 struct QzmLz4Sink {
     uint32_t *recs; uint32_t nrec;
     static constexpr bool kLz4 = true;
-    static constexpr uint32_t kMinMatch = 5, kMaxMatch = 65535, kMaxDist = 65535;
+    static constexpr uint32_t kMinMatch = 4, kMaxMatch = 65535, kMaxDist = 65535;
     __device__ __forceinline__ void put(uint32_t, uint32_t matchmask, uint32_t lane, uint32_t lt, uint32_t p, uint32_t, uint32_t L, uint32_t dist)
     {
         if ((matchmask >> lane) & 1) {

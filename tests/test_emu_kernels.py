@@ -415,3 +415,31 @@ def test_window_ratio_gate(emu):
         ref = sum(len(zlib.compress(data[i:i + 65536], 1)) - 6 for i in range(0, len(data), 65536))
         assert inflate_raw(ours)[0] == data
         assert len(ours) <= 1.05 * ref, (name, len(ours), ref)
+
+
+# ------------------------------------------------------------------ LZ4 window kernel: one 64 KiB block per chunk
+
+@pytest.mark.parametrize("nw,tent", [(12, 6900), (16, 5200), (12, 300)])
+@pytest.mark.parametrize("name,make,n", [("sil", sil, 300000), ("one_chunk", sil, 65536), ("rle", rle, 150000), ("noise", noise, 70000), ("zeros", lambda n: b"\0" * n, 200000),
+                                         ("tiny", sil, 11), ("twelve", sil, 12), ("thirteen", lambda n: b"a" * n, 13), ("edge", sil, 65536 + 4097)])
+def test_lz4_window_round_trip(emu, port, name, make, n, nw, tent):
+    data = make(n)
+    blob, cks = emu.lz4_window(data, tent=tent, nw=nw)
+    assert port.decompress(blob, E.FMT_LZ4, n + 16) == data
+    assert cks == [port.xxh32(data[i:i + 65536]) for i in range(0, n, 65536)]
+    frames = walk_lz4(blob)
+    assert len(frames) == (n + 65535) // 65536                 # one frame per chunk ...
+    members = [dict(src_off=off, src_len=ln, exact_len=1, dst_off=i * 65536, dst_cap=size, exact_out=1, expect_cksum=ck, check_cksum=1) for i, (off, ln, size, ck) in enumerate(frames)]
+    out, res = emu.decode(E.FMT_LZ4, blob, members, n)          # ... that our own decoder takes back
+    assert [r.status for r in res] == [E.ST_OK] * len(frames) and out == data
+
+
+def test_lz4_window_larger_chunks_and_ratio(emu, port):
+    data = sil(400000)
+    blob, _ = emu.lz4_window(data, chunk=131072)
+    assert port.decompress(blob, E.FMT_LZ4, len(data) + 16) == data
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_sample.txt"), "rb").read()
+    for name, d in (("sil", sil(1 << 20)), ("rle", rle(1 << 19)), ("text", text)):
+        ours, _ = emu.lz4_window(d)
+        ref = sum(len(port.compress(d[i:i + 65536], E.FMT_LZ4)) for i in range(0, len(d), 65536))
+        assert len(ours) <= 1.05 * ref, (name, len(ours), ref)

@@ -150,6 +150,17 @@ def test_ratio_within_5_percent_of_reference(prod, ref, corpus):
         assert ours <= theirs * 1.05, name
 
 
+def test_lz4_ratio_within_5_percent_of_reference(prod, ref, corpus):
+    """LZ4 at the same granularity as the hardware path: one frame with one 64 KiB block per chunk (reference session:
+    lz4BlockMaxSize = 64 KiB, src/qatzip_utils.c:292-298), against the reference's LZ4F per 64 KiB chunk: <= 1.05"""
+    for name, d in ratio_corpora(corpus):
+        d = d[:8 << 20]
+        ours = len(prod.compress(d, fmt=q.FMT_LZ4))
+        theirs = sum(len(ref.compress(d[i:i + 65536], fmt=q.FMT_LZ4)) for i in range(0, len(d), 65536))
+        print(f"LZ4 {name}: ours {ours / len(d):.4f} reference {theirs / len(d):.4f} rel {ours / theirs - 1:+.2%}")
+        assert ours <= theirs * 1.05, name
+
+
 # ---------------------------------------------------------------------------- error semantics
 def test_buf_error_partial_progress_compress(prod, port, data):
     """reference mode 17 (:4212-4271): small dest -> QZ_BUF_ERROR, whole chunks only"""

@@ -17,7 +17,9 @@ res = {}
 # raw PCIe copy bandwidth with the same pinned pages (what bounds the end-to-end number)
 for nm, fn, a, b in (("h2d", L.qzb200CopyToDevice, d_in, h_in), ("d2h", L.qzb200CopyToHost, h_back, d_in)):
     fn(a, b, N); t0 = time.perf_counter(); fn(a, b, N); res["pcie_" + nm + "_GBps"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
+ONLY = os.environ.get("EXTRA_ONLY")
 for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4), ("zlib", q.FMT_ZLIB)):
+    if ONLY and name != ONLY: continue
     sess = prod.new_session(fmt=fmt)
     # compress each 512 MiB call into consecutive regions; remember sizes
     sizes, kms = [], 0.0
@@ -56,7 +58,7 @@ for name, fmt in (("gzip_ext", q.QZ_DEFLATE_GZIP_EXT), ("lz4", q.FMT_LZ4), ("zli
         res[name + "_decompress"]["GBps_out_e2e_host"] = round(N / (time.perf_counter() - t0) / 1e9, 2)
     prod.end_session(sess)
 # the reference's software inflate on all host threads over the same gzip-ext members (CPU baseline of decompress)
-if os.path.exists(q.REF_SO) and not os.environ.get("EXTRA_NOCPU"):
+if os.path.exists(q.REF_SO) and not os.environ.get("EXTRA_NOCPU") and not ONLY:
     import threading
     ref = q.QzLib(q.REF_SO)
     sess0 = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT)
@@ -91,7 +93,7 @@ drv = C.CDLL(os.path.join(os.path.dirname(q.CORPUS_SO), "libqzdrive.so"))
 drv.qzdrive_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t,
                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint), C.POINTER(C.c_double)]
 fn_s, fn_e = C.cast(L.qzCompressStream, C.c_void_p), C.cast(L.qzEndStream, C.c_void_p)
-for sb, batch_kb in ((65536, None), (65536, "0"), (2 * 1024 * 1024 - 5 * 1024, "0")):
+for sb, batch_kb in ((65536, None), (65536, "0"), (2 * 1024 * 1024 - 5 * 1024, "0")) if SN and not ONLY else ():
     if batch_kb is None: os.environ.pop("QZB200_STREAM_BATCH_KB", None)
     else: os.environ["QZB200_STREAM_BATCH_KB"] = batch_kb
     sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW, strm_buff_sz=sb)
