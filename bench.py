@@ -76,6 +76,15 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def kernel_source_sha():
+    """identifies the deflate kernel sources an ncu capture belongs to"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("qz_deflate.cu", "qz_match.cuh", "qz_warp.cuh", "qz_huffman.h"):
+        h.update(open(os.path.join(ROOT, "qatzip_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def cpu_reference_pass(lib_path, host_addr, nbytes, threads):
     """The reference's software path over host_addr[0:nbytes): one session per thread, contiguous
     slices, simultaneous start (pattern of reference test/main.c:2175-2202).  Returns (seconds, out_bytes)."""
@@ -123,6 +132,9 @@ def main():
     ncores = os.cpu_count() or 1
     ref_lib = q.REF_SO if os.path.exists(q.REF_SO) else None
     workload = f"qzCompress QZ_DEFLATE_GZIP_EXT L1 hw_buff_sz=64KiB, {nbytes / (1 << 30):g} GiB SILESIA-LIKE per GPU in 512 MiB calls"
+    # the same dictionary in both arms (the reference arm times a bounded sample of this workload per step: cpu_baseline.sample)
+    config = {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
+              "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"}
 
     import __graft_entry__ as ge
     if not (os.path.exists(q.CORPUS_SO) and os.path.exists(q.PORT_SO)):
@@ -148,7 +160,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(v, 4), "unit": "GB/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": workload, "l2": "inputs larger than L2"},
+                          "config": config,
                           "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": thr, "kind": "reference",
                                            "sample": f"{sample >> 20} MiB of the workload per step, one slice per thread"},
                           "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -272,11 +284,16 @@ def main():
         per_launch_bytes = (nbytes + made) / (codec_launches / args.steps)
         per_launch_s = codec_ms / 1e3 / codec_launches
         achieved = per_launch_bytes / per_launch_s / GB
-        traffic = None
+        # DRAM bytes per launch come from an ncu capture (profiles/traffic.json, written by tools/collect_profiles.py); they are
+        # reported only while the kernel sources are the ones that were captured
+        traffic, traffic_note = None, "no capture"
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = tj.get("deflate_dram_bytes_per_launch", tj.get("deflate_pieces_dram_bytes_per_launch"))
+            if tj.get("source_sha") == kernel_source_sha():
+                traffic, traffic_note = tj.get("deflate_dram_bytes_per_launch"), f"ncu capture {tj.get('capture')} of these kernel sources ({tj.get('source_sha', '')[:12]})"
+            else:
+                traffic_note = f"capture {tj.get('capture')} is of other kernel sources ({str(tj.get('source_sha'))[:12]}): not reported"
         # CPU baseline: bounded sample of the same bytes through the reference's software path
         cpu = None
         if ref_lib and world == 1 and not os.environ.get("QZ_BENCH_NOCPU"):      # reported at N = 1 only
@@ -285,13 +302,13 @@ def main():
             cpu = {"value": round(sample / dtc / GB, 4), "unit": "GB/s", "cores": thr, "kind": "reference",
                    "sample": f"first {sample >> 20} MiB of rank 0's shard, one pass, {thr} threads", "ratio": round(outc / sample, 4)}
         st = prod.stats(sess)
-        print(json.dumps({
+        line = {
             "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
             "kernel_ms_per_step_cuda_events": round(kernel_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload, "format": "QZ_DEFLATE_GZIP_EXT", "level": 1, "hw_buff_sz": CHUNK, "per_gpu_bytes": nbytes,
-                       "piece_log2": st.piece_log2, "hash_bits": st.hash_bits, "deflate_blocks": "one per 64 KiB window (window kernel)" if st.group_blocks else "one per 8 KiB piece", "l2": "inputs larger than L2 (4 GiB per GPU vs 126 MB)"},
+            "config": config,
+            "kernel": {"deflate_blocks": "one per 64 KiB window (window kernel)" if st.group_blocks else "one per 8 KiB piece", "piece_log2": st.piece_log2},
             "ratio": round(made / nbytes, 4),
             "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made_h),
                     "api": f"qzCompress(host pinned -> host pinned), 512 MiB per call, {T} submitting thread(s) with one session each",
@@ -300,9 +317,32 @@ def main():
                                    "stage_ms_per_step_summed_overlapping": {k: round(v, 2) for k, v in break_1.items()}}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "qzb_deflate_window_kernel" if st.group_blocks else "qzb_deflate_pieces_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "bytes_per_launch": int(per_launch_bytes), "ms_per_launch": round(per_launch_s * 1e3, 4)},
-            "cpu_baseline": cpu, "clocks": clk}))
+            "cpu_baseline": cpu, "clocks": clk}
+    # ---------------------------------------------------------------- secondary legs (BASELINE configs[2..4]), after the timed headline
+    secondary = {}
+    if os.environ.get("QZ_BENCH_SECONDARY", "1") != "0":
+        from harness import bench_secondary as bs
+        for p in (h_in, h_out, *e2e_out[1:]):
+            L.qzFree(p)
+        L.qzb200DeviceFree(d_in); L.qzb200DeviceFree(d_out)
+        peak2 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        sec_steps = max(1, min(args.steps, 3))
+        try:
+            secondary["lz4_config3"] = bs.lz4_leg(prod, ref_lib, cor, peak2, ncores, sec_steps, rank, world, barrier, allmax, allsum)
+        except Exception as e:          # a secondary leg never takes the headline down
+            secondary["lz4_config3"] = {"error": repr(e)}
+        if rank == 0 and world == 1:
+            for name, fn in (("inflate_config2", lambda: bs.inflate_leg(prod, ref_lib, cor, peak2, ncores, sec_steps) if ref_lib else {"unavailable": "oracle/_ref missing"}),
+                             ("stream_config4", lambda: bs.stream_leg(prod, ref_lib, cor, peak2, ncores))):
+                try:
+                    secondary[name] = fn()
+                except Exception as e:
+                    secondary[name] = {"error": repr(e)}
+    if rank == 0:
+        line["secondary"] = secondary
+        print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
     return 0
