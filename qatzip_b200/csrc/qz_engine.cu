@@ -29,7 +29,9 @@ extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int 
 extern "C" size_t qzb_deflate_window_tok_words(int grid);
 extern "C" int qzb_deflate_window_max_tent(void);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, int grid, cudaStream_t st);
+extern "C" size_t qzb_inflate_smem_bytes(int dpw);
+extern "C" int qzb_inflate_cta_threads(int dpw);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
@@ -84,7 +86,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
-    t->inflate_lane_min = 0;                              /* (unused: the lane-per-member decoder was measured slower and removed) */
+    t->inflate_dpw = env_int("QZB200_INFLATE_DPW", 4);      /* members decoded at once by one warp: 1, 2, 4 or 8 */
+    if (t->inflate_dpw != 1 && t->inflate_dpw != 2 && t->inflate_dpw != 8) t->inflate_dpw = 4;
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
@@ -599,7 +602,9 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             d_src = (const uint8_t *)s.d_in.p;
         }
         if (!d_dst) { if (s.d_out.ensure(out_len + 64) != RC_OK) return RC_FAIL; d_dst = (uint8_t *)s.d_out.p; }
-        if (s.h_members.ensure(count * sizeof(QzbMember)) != RC_OK || s.d_members.ensure(count * sizeof(QzbMember)) != RC_OK) return RC_FAIL;
+        /* the member table, and behind it the order the members are handed out in (largest payload first) */
+        const size_t order_off = align_up(count * sizeof(QzbMember), 16);
+        if (s.h_members.ensure(order_off + count * 4) != RC_OK || s.d_members.ensure(order_off + count * 4) != RC_OK) return RC_FAIL;
         if (s.h_results.ensure(count * sizeof(QzbMemberResult)) != RC_OK || s.d_results.ensure(count * sizeof(QzbMemberResult) + 16) != RC_OK) return RC_FAIL;
         QzbMember *hm = (QzbMember *)s.h_members.p;
         uint64_t stage_off = 0;
@@ -610,16 +615,31 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             else if (staged_out) { hm[i].dst_off = stage_off; stage_off += align_up(hm[i].dst_cap, 16); }
             else hm[i].dst_off -= out_base;
         }
-        CK(cudaMemcpyAsync(s.d_members.p, hm, count * sizeof(QzbMember), cudaMemcpyHostToDevice, s.st));
+        bool ordered = false;
+        if (!lz4 && count > 64) {
+            uint32_t lo = 0xffffffffu, hi = 0;
+            for (size_t i = 0; i < count; i++) { lo = std::min(lo, hm[i].src_len); hi = std::max(hi, hm[i].src_len); }
+            if (hi > 2 * (uint64_t)lo) {
+                uint32_t *ord = (uint32_t *)((uint8_t *)s.h_members.p + order_off);
+                for (size_t i = 0; i < count; i++) ord[i] = (uint32_t)i;
+                std::stable_sort(ord, ord + count, [&](uint32_t a, uint32_t b) { return hm[a].src_len > hm[b].src_len; });
+                ordered = true;
+            }
+        }
+        CK(cudaMemcpyAsync(s.d_members.p, hm, ordered ? order_off + count * 4 : count * sizeof(QzbMember), cudaMemcpyHostToDevice, s.st));
         uint32_t *ticket = (uint32_t *)((uint8_t *)s.d_results.p + count * sizeof(QzbMemberResult));
         CK(cudaMemsetAsync(ticket, 0, 16, s.st));
         QzbDecompressJob job; memset(&job, 0, sizeof job);
         job.src = d_src; job.dst = d_dst; job.members = (const QzbMember *)s.d_members.p; job.results = (QzbMemberResult *)s.d_results.p;
         job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket; job.size_only = size_only ? 1 : 0;
-        const int grid = (int)std::min<size_t>((count + 7) / 8, (size_t)grid_cap);
+        if (ordered) job.order = (const uint32_t *)((const uint8_t *)s.d_members.p + order_off);
+        const int dpw = e->tune.inflate_dpw;
+        const size_t slots_per_cta = lz4 ? 8 : (size_t)(qzb_inflate_cta_threads(dpw) / 32) * dpw;
+        const int ctas_per_sm = lz4 ? 8 : (int)std::max<size_t>(1, std::min<size_t>(2048 / qzb_inflate_cta_threads(dpw), (227 * 1024) / (qzb_inflate_smem_bytes(dpw) + 2048)));
+        const int grid = (int)std::min<size_t>((count + slots_per_cta - 1) / slots_per_cta, (size_t)e->sm_count * ctas_per_sm);
         CK(cudaEventRecord(s.ev_k0, s.st));
         if (lz4) CK(qzb_launch_lz4_decompress(&job, grid, s.st));
-        else CK(qzb_launch_inflate(&job, grid, s.st));
+        else CK(qzb_launch_inflate(&job, dpw, grid, s.st));
         CK(cudaEventRecord(s.ev_k1, s.st));
         o->kernel_launches += 1;
         CK(cudaMemcpyAsync(s.h_results.p, s.d_results.p, count * sizeof(QzbMemberResult), cudaMemcpyDeviceToHost, s.st));

@@ -1,12 +1,12 @@
-/* qz_inflate.cu -- sm_100a DEFLATE decoder: one warp per member.
+/* qz_inflate.cu -- sm_100a DEFLATE decoder: several members per warp.
  *
  * Replaces the QAT decompress request at reference src/qatzip.c:2191 (cpaDcDecompressData,
  * stateless, FLUSH_FINAL) and folds in the checks doDecompressOut performs afterwards
  * (reference src/qatzip_utils.c:1483-1532 decompOutCheckSum: checksum vs footer, produced vs
- * ISIZE).  Lane 0 is the bit-serial Huffman decoder (tables in the warp's shared-memory
- * slice, built by all lanes); literals are stored as they are decoded and every
- * back-reference / stored block is copied by the whole warp.  Output and history live in
- * the caller's destination buffer (HBM / L2), so there is no separate window. */
+ * ISIZE).  A warp decodes several members at once: one lane per member is its bit-serial Huffman
+ * decoder (tables in shared memory, built by all lanes), the whole warp places the decoded
+ * tokens.  Output and history live in the caller's destination buffer (HBM / L2), so there is no
+ * separate window. */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "qz_kernels.cuh"
@@ -108,162 +108,213 @@ __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t l
     return __shfl_sync(FULL, qz_adler_finish(s1, s2, n), 0);
 }
 
-__global__ void __launch_bounds__(256, 4) qzb_inflate_kernel(QzbDecompressJob job)
+/* The kernel.  A warp works on DPW members at once, one per SLOT: lane s * (32 / DPW) is slot s's DECODER and keeps the
+ * member's bit reader, output position and state in its registers; every slot has its own tables and token buffer in
+ * shared memory.  The serial part -- turning the bit stream into tokens, and reading a dynamic block's code lengths --
+ * is the same instruction stream for all decoders, so DPW members share every one of its issue slots (with one decoder
+ * per warp the kernel was bound by exactly those: 22 warp instructions per output byte at 4 of 32 lanes active).  The
+ * parallel parts -- building a block's tables, placing a batch of tokens, stored blocks, the checksum -- are done by the
+ * whole warp, slot after slot.  One round: free slots draw members; slots between blocks read their block header; all
+ * decoders fill their token buffers; the batches are placed; finished members are checked and reported. */
+template <int DPW>
+__global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
 {
+    constexpr uint32_t TL = 32 / DPW;               /* lanes per slot */
     QZ_DYN_SMEM(smem_raw);
     InflWarpSmem *s_w = reinterpret_cast<InflWarpSmem *>(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
     __syncthreads();
-    InflWarpSmem &ws = s_w[warp];
-    QzInflTables &T = ws.t;
+    InflWarpSmem *slots = s_w + (size_t)warp * DPW;
+    const uint32_t myslot = lane / TL;
+    const bool is_dec = (lane % TL) == 0;
+    const bool wr = !job.size_only;
+
+    /* slot state, meaningful in the slot's decoder lane */
+    bool active = false, exhausted = false, in_block = false;
+    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0;
+    const uint8_t *src = job.src; uint8_t *dst = job.dst;
+    QzbMember m; m.src_off = 0; m.src_len = 0; m.exact_len = 0; m.dst_off = 0; m.dst_cap = 0; m.exact_out = 0; m.expect_cksum = 0; m.check_cksum = 0;
+    QzBitReader br; qz_br_init(&br, job.src, 0);
 
     for (;;) {
-        uint32_t mi = 0;
-        if (lane == 0) mi = atomicAdd(job.ticket, 1u);
-        mi = bcast(mi);
-        if (mi >= job.nmembers) break;
-        const QzbMember m = job.members[mi];
-        const uint8_t *src = job.src + m.src_off;
-        uint8_t *dst = job.dst + m.dst_off;
-        const uint32_t cap = m.dst_cap;
-        QzBitReader br;
-        qz_br_init(&br, src, m.src_len);
-        uint32_t out = 0, status = QZB_ST_OK, bfinal = 0;
-        const bool wr = !job.size_only;
+        /* ---- free slots draw members ---- */
+        if (is_dec && !active && !exhausted) {
+            mi = atomicAdd(job.ticket, 1u);
+            if (mi >= job.nmembers) exhausted = true;
+            else {
+                if (job.order) mi = job.order[mi];       /* the longest members first: the last round of a launch is short ones */
+                m = job.members[mi];
+                src = job.src + m.src_off; dst = job.dst + m.dst_off; cap = m.dst_cap;
+                qz_br_init(&br, src, m.src_len);
+                out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; active = true;
+            }
+        }
+        if (__ballot_sync(FULL, is_dec && active) == 0) break;
+        bool done = false;                       /* this slot's member ends in this round */
 
-        while (!bfinal && status == QZB_ST_OK) {
-            uint32_t type = 0;
-            if (lane == 0) {
-                qz_br_refill(&br);
-                /* QZ_DEFLATE_RAW chunks that are not the last of the stream end without BFINAL:
-                 * stop cleanly when nothing but padding is left */
-                if (job.fmt == QZB_FMT_RAW && qz_br_exhausted(&br)) type = 4;
-                else { bfinal = qz_br_bits(&br, 1); type = qz_br_bits(&br, 2); }
+        /* ---- block headers of the slots that are between blocks ---- */
+        uint32_t type = 7;
+        if (is_dec && active && !in_block) {
+            qz_br_refill(&br);
+            /* QZ_DEFLATE_RAW chunks that are not the last of the stream end without BFINAL: stop cleanly when nothing
+             * but padding is left */
+            if (job.fmt == QZB_FMT_RAW && qz_br_exhausted(&br)) { type = 4; done = true; }
+            else {
+                bfinal = qz_br_bits(&br, 1); type = qz_br_bits(&br, 2);
+                if (type == 3) { status = QZB_ST_DATA_ERROR; done = true; }
             }
-            type = bcast(type); bfinal = bcast(bfinal);
-            if (type == 4) break;
-            if (type == 3) { status = QZB_ST_DATA_ERROR; break; }
-            if (type == 0) {
-                uint32_t len = 0, start = 0, st = QZB_ST_OK;
-                if (lane == 0) {
-                    uint32_t drop = br.nacc & 7; br.acc >>= drop; br.nacc -= drop;
-                    qz_br_refill(&br);
-                    len = qz_br_bits(&br, 16);
-                    uint32_t nlen = qz_br_bits(&br, 16);
-                    start = qz_br_consumed(&br);
-                    if ((len ^ 0xffffu) != nlen) st = QZB_ST_DATA_ERROR;
-                    else if (start + len > br.n) st = QZB_ST_IN_TRUNC;
-                    else if (out + len > cap) st = QZB_ST_OUT_FULL;
-                    else qz_br_seek(&br, start + len);
-                }
-                st = bcast(st); len = bcast(len); start = bcast(start);
-                if (st != QZB_ST_OK) { status = st; break; }
-                if (wr) for (uint32_t i = lane; i < len; i += 32) dst[out + i] = src[start + i];
-                out += len;
-                __syncwarp();
-                continue;
-            }
-            /* Huffman block: lane 0 reads the code lengths, the warp builds the tables */
-            uint32_t st = QZB_ST_OK, hlit = 288, hdist = 30;
-            if (lane == 0) {
-                if (type == 1) qz_inflate_fixed_lens(&T);
-                else if (qz_inflate_read_dynamic(&br, &T, &hlit, &hdist) != 0) st = QZB_ST_DATA_ERROR;
-            }
-            st = bcast(st); hlit = bcast(hlit); hdist = bcast(hdist);
-            if (st != QZB_ST_OK) { status = st; break; }
-            __syncwarp();
-            /* the whole warp builds the tables (the literal/length table's tail doubles as scratch until it is cleared) */
-            if (warp_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut + 512, lane) < 0 ||
-                warp_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.ll_lut + 512, lane) < 0) { status = QZB_ST_DATA_ERROR; break; }
+        }
+        /* stored blocks: the decoder checks the lengths, the warp copies */
+        uint32_t slen = 0, sstart = 0;
+        if (type == 0) {
+            const uint32_t drop = br.nacc & 7; br.acc >>= drop; br.nacc -= drop;
+            qz_br_refill(&br);
+            slen = qz_br_bits(&br, 16);
+            const uint32_t nlen = qz_br_bits(&br, 16);
+            sstart = qz_br_consumed(&br);
+            if ((slen ^ 0xffffu) != nlen) status = QZB_ST_DATA_ERROR;
+            else if (slen > br.n || sstart > br.n - slen) status = QZB_ST_IN_TRUNC;
+            else if (slen > cap - out) status = QZB_ST_OUT_FULL;
+            else qz_br_seek(&br, sstart + slen);
+            if (status != QZB_ST_OK) { done = true; slen = 0; }
+        }
+        uint32_t smask = __ballot_sync(FULL, type == 0 && slen != 0);
+        while (smask) {
+            const uint32_t j = __ffs(smask) - 1; smask &= smask - 1;
+            const uint32_t n = __shfl_sync(FULL, slen, j), st = __shfl_sync(FULL, sstart, j), o = __shfl_sync(FULL, out, j);
+            const uint8_t *from = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(src), j)) + st;
+            uint8_t *to = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j)) + o;
+            if (wr) for (uint32_t i = lane; i < n; i += 32) to[i] = from[i];
+        }
+        if (type == 0) { out += slen; if (bfinal && status == QZB_ST_OK) done = true; }
+        __syncwarp();
+        /* Huffman blocks: every decoder reads its code lengths (dynamic) or fills in the fixed ones ... */
+        uint32_t hlit = 288, hdist = 30;
+        if (type == 1) qz_inflate_fixed_lens(&slots[myslot].t);
+        else if (type == 2 && qz_inflate_read_dynamic(&br, &slots[myslot].t, &hlit, &hdist) != 0) { status = QZB_ST_DATA_ERROR; done = true; type = 7; }
+        __syncwarp();
+        /* ... and the whole warp builds the tables, slot after slot (the literal/length table's tail doubles as scratch
+         * until it is cleared) */
+        uint32_t hmask = __ballot_sync(FULL, type == 1 || type == 2);
+        while (hmask) {
+            const uint32_t j = __ffs(hmask) - 1; hmask &= hmask - 1;
+            QzInflTables &T = slots[j / TL].t;
+            const uint32_t hl = __shfl_sync(FULL, hlit, j), hd = __shfl_sync(FULL, hdist, j);
+            const bool bad = warp_infl_prepare(T.lens, (int)hl, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut + 512, lane) < 0 ||
+                             warp_infl_prepare(T.lens + hl, (int)hd, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.ll_lut + 512, lane) < 0;
+            if (bad) { if (lane == j) { status = QZB_ST_DATA_ERROR; done = true; } continue; }
             __syncwarp();
             for (uint32_t i = lane; i < (1u << QZ_LL_LUT_BITS); i += 32) T.ll_lut[i] = 0;
             for (uint32_t i = lane; i < (1u << QZ_D_LUT_BITS); i += 32) T.d_lut[i] = 0;
             __syncwarp();
             qz_infl_fill_lut(T.lens, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut, QZ_LL_LUT_BITS, 0, (int)lane, 32);
-            qz_infl_fill_lut(T.lens + hlit, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut, QZ_D_LUT_BITS, 1, (int)lane, 32);
+            qz_infl_fill_lut(T.lens + hl, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut, QZ_D_LUT_BITS, 1, (int)lane, 32);
             __syncwarp();
-            /* lane 0 decodes a batch of tokens (no output touched); then every lane places one:
-             * literals and matches whose source lies wholly before the batch go out at once, matches
-             * that read bytes produced inside the batch follow in order, copied by the whole warp */
-            for (;;) {
-                int ev = 0; uint32_t ntk = 0, pos = out;
-                if (lane == 0) ev = qz_inflate_tokens(&br, &T, ws.tok, QZ_INFL_BATCH, &ntk, &pos, cap);
-                __syncwarp();
-                ev = (int)bcast((uint32_t)ev); ntk = bcast(ntk);
-                const uint32_t t = lane < ntk ? ws.tok[lane] : 0u;
-                const bool is_match = lane < ntk && !qz_tok_is_literal(t);
-                const uint32_t len = lane < ntk ? (is_match ? qz_tok_len(t) : 1u) : 0u;
-                const uint32_t dist = qz_tok_dist(t);
-                uint32_t incl = len;
+            if (lane == j) in_block = true;
+        }
+
+        /* ---- every decoder inside a block fills its token buffer (no output touched) ---- */
+        int ev = QZI_MATCH; uint32_t ntk = 0, pos = out;
+        if (is_dec && active && in_block && !done) ev = qz_inflate_tokens(&br, &slots[myslot].t, slots[myslot].tok, QZ_INFL_BATCH, &ntk, &pos, cap);
+        __syncwarp();
+        /* ---- the batches are placed, slot after slot, by the whole warp: literals and matches whose source lies wholly
+         * before the batch go out at once, matches that read bytes produced inside the batch follow in order ---- */
+        uint32_t pmask = __ballot_sync(FULL, ntk != 0);
+        while (pmask) {
+            const uint32_t j = __ffs(pmask) - 1; pmask &= pmask - 1;
+            const uint32_t n = __shfl_sync(FULL, ntk, j), o0 = __shfl_sync(FULL, out, j);
+            uint8_t *d = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
+            const uint32_t t = lane < n ? slots[j / TL].tok[lane] : 0u;
+            const bool is_match = lane < n && !qz_tok_is_literal(t);
+            const uint32_t len = lane < n ? (is_match ? qz_tok_len(t) : 1u) : 0u;
+            const uint32_t dist = qz_tok_dist(t);
+            uint32_t incl = len;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-                const uint32_t o = out + incl - len;                       /* where this lane's token lands */
-                const uint32_t span = dist < len ? dist : len;               /* distinct source bytes actually read */
-                const bool dep = is_match && (o - dist + span > out);        /* reads output of this very batch */
-                /* short matches that neither overlap themselves nor read this batch: the owning lane copies,
-                 * all loads first (ordinary cached loads: what this warp wrote is in this SM's L1 or in L2) */
-                const bool lane_copy = is_match && !dep && len <= QZ_INFL_LANE_COPY && dist >= len;
-                if (lane < ntk && wr) {
-                    if (!is_match) dst[o] = (uint8_t)qz_tok_byte(t);
-                    else if (lane_copy) {
-                        const uint8_t *from = dst + o - dist;
-                        uint8_t v[QZ_INFL_LANE_COPY];
+            for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, k); if (lane >= (uint32_t)k) incl += y; }
+            const uint32_t o = o0 + incl - len;                          /* where this lane's token lands */
+            const uint32_t span = dist < len ? dist : len;               /* distinct source bytes actually read */
+            const bool dep = is_match && (o - dist + span > o0);         /* reads output of this very batch */
+            /* short matches that neither overlap themselves nor read this batch: the owning lane copies, all loads first */
+            const bool lane_copy = is_match && !dep && len <= QZ_INFL_LANE_COPY && dist >= len;
+            if (lane < n && wr) {
+                if (!is_match) d[o] = (uint8_t)qz_tok_byte(t);
+                else if (lane_copy) {
+                    const uint8_t *from = d + o - dist;
+                    uint8_t v[QZ_INFL_LANE_COPY];
 #pragma unroll
-                        for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) v[k] = k < len ? from[k] : (uint8_t)0;
+                    for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) v[k] = k < len ? from[k] : (uint8_t)0;
 #pragma unroll
-                        for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) if (k < len) dst[o + k] = v[k];
-                    }
+                    for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) if (k < len) d[o + k] = v[k];
                 }
-                /* the rest (long, self-overlapping, or fed by this batch) go in order, copied by the whole warp */
-                uint32_t depmask = wr ? __ballot_sync(FULL, is_match && !lane_copy) : 0u;
+            }
+            /* the rest (long, self-overlapping, or fed by this batch) go in order, copied by the whole warp */
+            uint32_t depmask = wr ? __ballot_sync(FULL, is_match && !lane_copy) : 0u;
+            __syncwarp();
+            while (depmask) {
+                const uint32_t q = __ffs(depmask) - 1; depmask &= depmask - 1;
+                const uint32_t oj = __shfl_sync(FULL, o, q), lj = __shfl_sync(FULL, len, q), dj = __shfl_sync(FULL, dist, q);
+                const uint8_t *from = d + oj - dj;
+                /* dj < lj: every output byte repeats one of the dj bytes before oj, all already final */
+                if (dj >= lj) { for (uint32_t k = lane; k < lj; k += 32) d[oj + k] = from[k]; }
+                else { for (uint32_t k = lane; k < lj; k += 32) d[oj + k] = from[k % dj]; }
                 __syncwarp();
-                while (depmask) {
-                    const uint32_t j = __ffs(depmask) - 1; depmask &= depmask - 1;
-                    const uint32_t oj = __shfl_sync(FULL, o, j), lj = __shfl_sync(FULL, len, j), dj = __shfl_sync(FULL, dist, j);
-                    const uint8_t *from = dst + oj - dj;
-                    /* dj < lj: every output byte repeats one of the dj bytes before oj, all already final */
-                    if (dj >= lj) { for (uint32_t k = lane; k < lj; k += 32) dst[oj + k] = from[k]; }
-                    else { for (uint32_t k = lane; k < lj; k += 32) dst[oj + k] = from[k % dj]; }
-                    __syncwarp();
-                }
-                out += __shfl_sync(FULL, incl, 31);
-                if (ev == QZI_END_BLOCK) break;
-                if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; break; }
-                if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; break; }
-                if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; break; }
             }
         }
-        /* verdict */
-        uint32_t consumed = bcast(lane == 0 ? qz_br_consumed(&br) : 0u);
-        uint32_t over = bcast(lane == 0 ? (uint32_t)qz_br_overrun(&br) : 0u);
-        if (status == QZB_ST_OK && over) status = QZB_ST_IN_TRUNC;
-        if (status == QZB_ST_OK && m.exact_len && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
-        if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
-        uint32_t crc = 0;
-        if (status == QZB_ST_OK && wr) {
-            __syncwarp();
-            crc = (job.fmt == QZB_FMT_ZLIB) ? warp_adler32_global(dst, out, lane) : warp_crc32_global(dst, out, s_crc_tab, lane);
-            if (m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
+        if (is_dec && active && in_block && !done) {
+            out = pos;
+            if (ev == QZI_END_BLOCK) { in_block = false; if (bfinal) done = true; }
+            else if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; done = true; }
+            else if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; done = true; }
+            else if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; done = true; }
         }
-        if (lane == 0) {
-            QzbMemberResult r;
-            r.status = status; r.consumed = consumed; r.produced = out; r.cksum = crc; r.saw_final = bfinal;
-            r.pad[0] = r.pad[1] = r.pad[2] = 0;
-            job.results[mi] = r;
+
+        /* ---- finished members: verdict, checksum by the whole warp, result ---- */
+        uint32_t consumed = 0;
+        if (done) {
+            consumed = qz_br_consumed(&br);
+            if (status == QZB_ST_OK && qz_br_overrun(&br)) status = QZB_ST_IN_TRUNC;
+            if (status == QZB_ST_OK && m.exact_len && consumed != m.src_len) status = QZB_ST_DATA_ERROR;
+            if (status == QZB_ST_OK && m.exact_out && out != cap) status = QZB_ST_SIZE;
+        }
+        uint32_t dmask = __ballot_sync(FULL, done);
+        __syncwarp();
+        while (dmask) {
+            const uint32_t j = __ffs(dmask) - 1; dmask &= dmask - 1;
+            const uint32_t stj = __shfl_sync(FULL, status, j), n = __shfl_sync(FULL, out, j);
+            const uint8_t *d = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
+            uint32_t crc = 0;
+            if (stj == QZB_ST_OK && wr) crc = (job.fmt == QZB_FMT_ZLIB) ? warp_adler32_global(d, n, lane) : warp_crc32_global(d, n, s_crc_tab, lane);
+            if (lane == j) {
+                if (status == QZB_ST_OK && wr && m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
+                QzbMemberResult r;
+                r.status = status; r.consumed = consumed; r.produced = out; r.cksum = crc; r.saw_final = bfinal;
+                r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                job.results[mi] = r;
+                active = false;
+            }
         }
         __syncwarp();
     }
 }
 
 #ifndef QZ_WARP_EMU
-extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int grid, cudaStream_t st)
+/* decoders per warp (1, 2, 4 or 8); a CTA is 8 warps (4 with eight decoders per warp: 32 slots fill the shared memory) */
+static int inflate_cta_warps(int dpw) { return dpw == 8 ? 4 : 8; }
+extern "C" size_t qzb_inflate_smem_bytes(int dpw) { return sizeof(InflWarpSmem) * (size_t)inflate_cta_warps(dpw) * (size_t)dpw; }
+extern "C" int qzb_inflate_cta_threads(int dpw) { return inflate_cta_warps(dpw) * 32; }
+template <int DPW>
+static cudaError_t launch_inflate(const QzbDecompressJob &job, int grid, cudaStream_t st)
 {
-    const size_t smem = sizeof(InflWarpSmem) * 8;          /* 8 warps per CTA, 4 CTAs per SM */
-    cudaError_t e = cudaFuncSetAttribute(qzb_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = qzb_inflate_smem_bytes(DPW);
+    cudaError_t e = cudaFuncSetAttribute(qzb_inflate_kernel<DPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_inflate_kernel<<<grid, 256, smem, st>>>(*job);
+    qzb_inflate_kernel<DPW><<<grid, inflate_cta_warps(DPW) * 32, smem, st>>>(job);
     return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, int grid, cudaStream_t st)
+{
+    return dpw == 1 ? launch_inflate<1>(*job, grid, st) : dpw == 2 ? launch_inflate<2>(*job, grid, st) : dpw == 8 ? launch_inflate<8>(*job, grid, st) : launch_inflate<4>(*job, grid, st);
 }
 #endif

@@ -67,5 +67,6 @@ struct QzbDecompressJob {
     int32_t fmt;
     uint32_t *ticket;
     int32_t size_only;           /* deflate: decode lengths only -- no output written, no checksum (member discovery) */
+    const uint32_t *order;       /* deflate: ticket -> member index, largest payload first (NULL: in index order) */
 };
 #endif
