@@ -333,6 +333,15 @@ def main():
             secondary["lz4_config3"] = bs.lz4_leg(prod, ref_lib, cor, peak2, ncores, sec_steps, rank, world, barrier, allmax, allsum)
         except Exception as e:          # a secondary leg never takes the headline down
             secondary["lz4_config3"] = {"error": repr(e)}
+        # one process driving every visible GPU (the other ranks of a torchrun launch sit at the barrier meanwhile)
+        barrier()
+        if rank == 0 and L.qzb200DeviceCount() > 1:
+            try:
+                secondary["one_process_all_gpus"] = bs.one_process_leg(prod, cor, ncores, sec_steps, nbytes)
+                secondary["one_process_all_gpus_lz4"] = bs.one_process_leg(prod, cor, ncores, sec_steps, min(nbytes, 2 << 30), fmt=q.FMT_LZ4)
+            except Exception as e:
+                secondary["one_process_all_gpus"] = {"error": repr(e)}
+        barrier()
         if rank == 0 and world == 1:
             for name, fn in (("inflate_config2", lambda: bs.inflate_leg(prod, ref_lib, cor, peak2, ncores, sec_steps) if ref_lib else {"unavailable": "oracle/_ref missing"}),
                              ("stream_config4", lambda: bs.stream_leg(prod, ref_lib, cor, peak2, ncores))):

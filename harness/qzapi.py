@@ -77,7 +77,7 @@ class QzB200Stats(C.Structure):  # include/qatzip_b200.h
     _fields_ = [("kernel_ms", C.c_double), ("codec_ms", C.c_double), ("codec_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("units", C.c_uint64), ("device", C.c_int),
                 ("piece_log2", C.c_int), ("hash_bits", C.c_int), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("group_blocks", C.c_int)]
+                ("group_blocks", C.c_int), ("devices", C.c_int)]
 
 
 def _addr(buf):

@@ -20,7 +20,8 @@ typedef struct QzB200Stats_S {
     int device;                  /* CUDA device ordinal the session runs on */
     int piece_log2, hash_bits;   /* compressor geometry in use */
     double h2d_ms, d2h_ms;       /* host-buffer compress calls: summed copy times of the last call (overlapping the kernels) */
-    int group_blocks;            /* 1: deflate sessions of this hw_buff_sz get one block per 8 pieces (group kernel), 0: one per piece */
+    int group_blocks;            /* 1: deflate sessions of this hw_buff_sz get one block per 64 KiB window (window kernel), 0: one per 8 KiB piece */
+    int devices;                 /* GPUs a host-buffer compress call of this session is spread over (QZB200_DEVICES; 1 by default) */
 } QzB200Stats_T;
 
 /* qzCompress / qzDecompress with src and dest in device memory of the session's GPU.
@@ -33,14 +34,15 @@ int qzb200DecompressDevice(QzSession_T *sess, const void *d_src, const void *h_s
                            void *d_dest, uint64_t dest_cap, uint64_t *consumed, uint64_t *produced);
 /* statistics of the most recent data call on this session (host or device entry point) */
 int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *stats);
-/* number of CUDA devices the library can use, and the one this process would pick
- * (QZB200_DEVICE, else LOCAL_RANK, else 0) */
 /* plain device-memory helpers (cudaMalloc / cudaFree / cudaMemcpy on the session's GPU) so that a
  * C caller or a ctypes harness can stage data in HBM without linking the CUDA runtime itself */
 void *qzb200DeviceAlloc(uint64_t bytes);
 void qzb200DeviceFree(void *d_ptr);
 int qzb200CopyToDevice(void *d_dst, const void *h_src, uint64_t bytes);
 int qzb200CopyToHost(void *h_dst, const void *d_src, uint64_t bytes);
+/* number of CUDA devices the library can use, and the one this process would pick (QZB200_DEVICE, else LOCAL_RANK, else 0).
+ * QZB200_DEVICES = "all" | count | list makes one process use several: sessions take them in turn as their primary device,
+ * and every host-buffer qzCompress call deals its batches over all of them (output and checksums stitched in order). */
 int qzb200DeviceCount(void);
 int qzb200DefaultDevice(void);
 

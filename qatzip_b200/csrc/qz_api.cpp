@@ -20,6 +20,7 @@
 #include <thread>
 #include "../../include/qatzip.h"
 #include "../../include/qatzip_b200.h"
+#include <atomic>
 #include "qz_engine.h"
 
 #define QZB_NUM_BUFF 32                 /* reference src/qatzip_internal.h:65 (req_cnt_thrshold ceiling) */
@@ -377,7 +378,13 @@ static int ready_session(QzSession_T *sess, QzbSess **out)
     }
     QzbSess *s = (QzbSess *)sess->internal;
     if (!s->engine) {
-        s->engine = qzb_engine_create(qzb_runtime_default_device());
+        /* sessions take the configured devices in turn as their primary one (the reference hands its instances out
+         * interleaved across devices, src/qatzip.c:795-808, qzGrabInstance :363); with one device that is the default device */
+        static std::atomic<unsigned> g_next_device{0};
+        int devs[16];
+        const int nd = qzb_runtime_device_list(devs, 16);
+        const int primary = nd > 1 ? devs[g_next_device.fetch_add(1) % (unsigned)nd] : qzb_runtime_default_device();
+        s->engine = qzb_engine_create(primary);
         if (!s->engine) { sess->hw_session_stat = QZ_NOSW_NO_INST_ATTACH; return QZ_NOSW_NO_INST_ATTACH; }
     }
     *out = s;
@@ -766,7 +773,7 @@ extern "C" int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *st)
     if (!sess || !st || !sess->internal) return QZ_PARAMS;
     QzbSess *s = (QzbSess *)sess->internal;
     QzbTuning t; qzb_get_tuning(&t);
-    *st = s->stats; st->device = qzb_runtime_default_device(); st->piece_log2 = t.piece_log2;
+    *st = s->stats; st->device = qzb_runtime_default_device(); st->devices = s->engine ? qzb_engine_device_count(s->engine) : 1; st->piece_log2 = t.piece_log2;
     st->group_blocks = (t.window && t.piece_log2 == 13 && s->p.hw_buff_sz % (8u << 13) == 0) ? 1 : 0;
     st->hash_bits = t.hash_bits;
     if (st->group_blocks) st->hash_bits = 11;        /* about 2600 entries per table: whatever the shared memory holds */

@@ -77,6 +77,28 @@ extern "C" int qzb_runtime_default_device(void)
     if (d < 0) d = env_int("LOCAL_RANK", 0);
     return d % n;
 }
+/* Devices one engine may spread a host-buffer compress call over (the reference interleaves its instances across the QAT
+ * devices of a process, src/qatzip.c:795-808 and qzGrabInstance :363): QZB200_DEVICES = "all", a count, or a comma-separated
+ * list; unset = the one default device (one process per GPU, as under torchrun). */
+static std::vector<int> configured_devices(void)
+{
+    std::vector<int> d;
+    const int n = qzb_runtime_devices();
+    const char *v = getenv("QZB200_DEVICES");
+    if (n <= 0) return d;
+    if (!v || !*v) { d.push_back(qzb_runtime_default_device()); return d; }
+    if (!strcmp(v, "all")) { for (int i = 0; i < n; i++) d.push_back(i); return d; }
+    if (!strchr(v, ',')) { const int k = std::max(1, std::min(n, atoi(v))); const int first = qzb_runtime_default_device(); for (int i = 0; i < k; i++) d.push_back((first + i) % n); return d; }
+    for (const char *p = v; *p;) { const int x = atoi(p); if (x >= 0 && x < n && std::find(d.begin(), d.end(), x) == d.end()) d.push_back(x); p = strchr(p, ','); if (!p) break; p++; }
+    if (d.empty()) d.push_back(qzb_runtime_default_device());
+    return d;
+}
+extern "C" int qzb_runtime_device_list(int *out, int cap)
+{
+    const std::vector<int> d = configured_devices();
+    for (int i = 0; i < (int)d.size() && i < cap; i++) out[i] = d[i];
+    return (int)d.size();
+}
 extern "C" void qzb_get_tuning(QzbTuning *t)
 {
     t->piece_log2 = env_int("QZB200_PIECE_LOG2", 13);
@@ -86,8 +108,8 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (t->piece_log2 == 14 && t->hash_bits != 12 && t->hash_bits != 13) t->hash_bits = 12;
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
-    t->inflate_dpw = env_int("QZB200_INFLATE_DPW", 4);      /* members decoded at once by one warp: 1, 2, 4 or 8 */
-    if (t->inflate_dpw != 1 && t->inflate_dpw != 2 && t->inflate_dpw != 8) t->inflate_dpw = 4;
+    t->inflate_dpw = env_int("QZB200_INFLATE_DPW", 1);      /* members decoded at once by one warp: 1 (measured fastest on B200), 2, 4 or 8 */
+    if (t->inflate_dpw != 2 && t->inflate_dpw != 4 && t->inflate_dpw != 8) t->inflate_dpw = 1;
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
@@ -181,6 +203,7 @@ struct HostBuf {
 };
 
 struct Slot {
+    int device = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_meta = nullptr, ev_done = nullptr, ev_h0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
     DevBuf d_in, d_slots, d_out, d_meta, d_tok, d_members, d_results;
@@ -194,34 +217,53 @@ struct Slot {
 };
 
 struct QzbEngine {
-    int device = 0;
+    int device = 0;                       /* primary device: decompress, device-resident calls */
+    std::vector<int> devices;             /* devices[0] == device; host-buffer compress calls deal their batches over all of them */
     int sm_count = 148;
     QzbTuning tune;
-    static constexpr int NSLOT = 4;       /* batches in flight: copy-in queued, copy-in, compute, copy-out */
-    Slot slot[NSLOT];
+    static constexpr int NSLOT = 4;       /* batches in flight per device: copy-in queued, copy-in, compute, copy-out */
+    static constexpr int MAX_DEV = 16;
+    Slot slot[NSLOT * MAX_DEV];           /* slot[d * NSLOT + k]: k-th slot of devices[d] */
     cudaEvent_t ev_base = nullptr;        /* QZB200_TIMELINE=1: start of the host-buffer call, for per-batch timestamps on stderr */
     int timeline = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int slot_setup(Slot &s, int device)
+{
+    s.device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return RC_FAIL;
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return RC_FAIL;
+    cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1); cudaEventCreate(&s.ev_h0); cudaEventCreate(&s.ev_d0); cudaEventCreate(&s.ev_d1);
+    cudaEventCreateWithFlags(&s.ev_meta, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
+    return RC_OK;
+}
+/* `device`: the engine's primary device.  With QZB200_DEVICES naming several, the engine also gets slots on the others
+ * (in list order, starting behind the primary) for host-buffer compress calls. */
 extern "C" QzbEngine *qzb_engine_create(int device)
 {
     if (device < 0 || device >= qzb_runtime_devices()) return NULL;
     if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
     QzbEngine *e = new QzbEngine();
     e->device = device;
+    e->devices.push_back(device);
+    {
+        const std::vector<int> all = configured_devices();
+        const auto it = std::find(all.begin(), all.end(), device);
+        if (it != all.end())
+            for (size_t k = 1; k < all.size() && (int)e->devices.size() < QzbEngine::MAX_DEV; k++) e->devices.push_back(all[((it - all.begin()) + k) % all.size()]);
+    }
     qzb_get_tuning(&e->tune);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
     e->timeline = env_int("QZB200_TIMELINE", 0);
     cudaEventCreate(&e->ev_base);
-    for (auto &s : e->slot) {
-        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) { delete e; return NULL; }
-        cudaEventCreate(&s.ev_k0); cudaEventCreate(&s.ev_km); cudaEventCreate(&s.ev_k1); cudaEventCreate(&s.ev_h0); cudaEventCreate(&s.ev_d0); cudaEventCreate(&s.ev_d1);
-        cudaEventCreateWithFlags(&s.ev_meta, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming);
-    }
+    for (size_t d = 0; d < e->devices.size(); d++)
+        for (int k = 0; k < QzbEngine::NSLOT; k++)
+            if (slot_setup(e->slot[d * QzbEngine::NSLOT + k], e->devices[d]) != RC_OK) { (void)cudaGetLastError(); qzb_engine_destroy(e); return NULL; }
+    cudaSetDevice(device);
     return e;
 }
 extern "C" void qzb_engine_destroy(QzbEngine *e)
@@ -230,7 +272,9 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
     cudaSetDevice(e->device);
     if (e->ev_base) cudaEventDestroy(e->ev_base);
     for (auto &s : e->slot) {
-        if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+        if (!s.st) continue;
+        cudaSetDevice(s.device);
+        cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_km) cudaEventDestroy(s.ev_km);
         if (s.ev_h0) cudaEventDestroy(s.ev_h0);
@@ -245,6 +289,16 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
     }
     delete e;
 }
+extern "C" int qzb_engine_device_count(const QzbEngine *e) { return e ? (int)e->devices.size() : 0; }
+
+/* Whatever way an engine call ends, no slot is left with work in flight or marked busy: a later call on the session
+ * would otherwise drain a stale batch into its own output (and copies into the caller's buffers would still be running). */
+struct SlotGuard {
+    QzbEngine *e;
+    explicit SlotGuard(QzbEngine *e_) : e(e_) { settle(); }
+    ~SlotGuard() { settle(); cudaSetDevice(e->device); }
+    void settle() { for (auto &s : e->slot) if (s.st && s.busy) { cudaSetDevice(s.device); cudaStreamSynchronize(s.st); (void)cudaGetLastError(); s.busy = false; } }
+};
 
 /* ------------------------------------------------------------------ compress */
 static uint32_t hdr_sz(int fmt) { return fmt == QZB_FMT_GZIP_EXT ? 24u : fmt == QZB_FMT_GZIP ? 10u : fmt == QZB_FMT_4B ? 4u : fmt == QZB_FMT_LZ4 ? 15u : fmt == QZB_FMT_ZLIB ? 2u : 0u; }
@@ -271,6 +325,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
 {
     const QzbTuning &t = e->tune;
     const uint32_t PIECE = 1u << t.piece_log2;
+    CK(cudaSetDevice(s.device));
     QzbCompressJob job; memset(&job, 0, sizeof job);
     job.src = d_src; job.src_len = len; job.chunk_sz = c->chunk_sz; job.piece_log2 = (uint32_t)t.piece_log2;
     job.pieces_per_chunk = (c->chunk_sz + PIECE - 1) / PIECE;
@@ -380,6 +435,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
 {
     memset(o, 0, sizeof *o);
     if (!e || !c || c->chunk_sz < 1024 || (c->chunk_sz & (c->chunk_sz - 1))) return RC_PARAMS;
+    SlotGuard guard(e);
     CK(cudaSetDevice(e->device));
     uint32_t crc = c->crc_in;
     const uint32_t xchunk = c->want_crc ? qz_crc_xpow8(c->chunk_sz) : 0;
@@ -422,9 +478,10 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
     if (e->timeline) CK(cudaEventRecord(e->ev_base, e->slot[0].st));
     auto drain = [&](Slot &s) -> int {
         if (!s.busy) return RC_OK;
-        s.busy = false;
+        CK(cudaSetDevice(s.device));
         const double host_drain0 = e->timeline ? host_ms() : 0.0;
         CK(cudaEventSynchronize(s.ev_meta));
+        s.busy = false;
         const double host_meta = e->timeline ? host_ms() : 0.0;
         if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
         float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
@@ -446,7 +503,7 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         if (c->want_crc && c->fmt != QZB_FMT_LZ4) crc = fold_chunk_crcs(c->fmt, crc, ck, fit, c->chunk_sz, s.in_len, xchunk);
         CK(cudaStreamSynchronize(s.st));
         { float t = 0; cudaEventElapsedTime(&t, s.ev_h0, s.ev_k0); o->h2d_ms += t; cudaEventElapsedTime(&t, s.ev_d0, s.ev_d1); o->d2h_ms += t; }
-        if (e->timeline) {
+        if (e->timeline && s.device == e->device) {
             float h0 = 0, k0 = 0, km = 0, k1 = 0, d0 = 0, d1 = 0;
             cudaEventElapsedTime(&h0, e->ev_base, s.ev_h0); cudaEventElapsedTime(&k0, e->ev_base, s.ev_k0); cudaEventElapsedTime(&km, e->ev_base, s.ev_km);
             cudaEventElapsedTime(&k1, e->ev_base, s.ev_k1); cudaEventElapsedTime(&d0, e->ev_base, s.ev_d0); cudaEventElapsedTime(&d1, e->ev_base, s.ev_d1);
@@ -460,20 +517,24 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
         return RC_OK;
     };
 
-    /* Ring of NSLOT slots.  Batch b is issued on slot b % NSLOT as soon as that slot's previous
-     * tenant (batch b - NSLOT) has been drained; after issuing b the oldest undrained batch is
-     * drained, so that while the host waits for it two younger batches are already queued. */
-    constexpr int NS = QzbEngine::NSLOT;
+    /* Ring of NS slots, NSLOT on each of the engine's devices, dealt device by device: batch b goes to device b % G.  It is
+     * issued as soon as that slot's previous tenant (batch b - NS) has been drained; after issuing b the oldest undrained
+     * batch is drained, so that while the host waits for it younger batches are already queued on every device.  Draining
+     * in batch order is what lays the output end to end and folds the checksums in order, whichever GPU made them. */
+    const int G = (int)e->devices.size();
+    const int NS = QzbEngine::NSLOT * G;
+    auto slot_of = [&](uint64_t b) -> Slot & { return e->slot[(b % G) * QzbEngine::NSLOT + ((b / G) % QzbEngine::NSLOT)]; };
     uint64_t next_drain = 0;
     /* batch sizes ramp up 16, 32, 64 ... MiB (QZB200_FIRST_MB, QZB200_BATCH_MB): the first kernel starts after a short copy, and a call's
      * unavoidable fill/drain tail (calls are synchronous) stays small against its steady state */
-    uint64_t in_off_next = 0;
+    uint64_t in_off_next = 0, issued = 0;
     for (uint64_t b = 0; (in_off_next < c->src_len || b == 0) && !stop; b++) {
-        Slot &s = e->slot[b % NS];
-        while (next_drain + NS <= b) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
+        while (next_drain + NS <= b) { if (drain(slot_of(next_drain)) != RC_OK) return RC_FAIL; next_drain++; }
         if (stop) break;
+        Slot &s = slot_of(b);
+        CK(cudaSetDevice(s.device));
         const uint64_t first = std::max<uint64_t>(c->chunk_sz, e->tune.first_batch_bytes / c->chunk_sz * c->chunk_sz);
-        const uint64_t ramp = first << std::min<uint64_t>(b, 10);
+        const uint64_t ramp = first << std::min<uint64_t>(b / G, 10);
         const uint64_t in_off = in_off_next, left = c->src_len - in_off;
         uint64_t len = std::min<uint64_t>(std::min(batch, ramp), left);
         /* optional taper (QZB200_TAPER=1): no batch takes more than half of what is left, so the last
@@ -493,13 +554,14 @@ extern "C" int qzb_engine_compress(QzbEngine *e, const QzbCompressCall *c, QzbCo
             }
         }
         const int last = (in_off + len == c->src_len) ? c->last : 0;
-        if (enqueue_compress(e, s, c, (const uint8_t *)s.d_in.p, len, (uint8_t *)s.d_out.p, s.d_out.cap, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
         s.busy = true; s.in_off = in_off; s.in_len = len;
-        if (b + 1 - next_drain >= (uint64_t)NS) {       /* ring full: retire the oldest while NS-1 younger ones are queued */
-            if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++;
+        if (enqueue_compress(e, s, c, (const uint8_t *)s.d_in.p, len, (uint8_t *)s.d_out.p, s.d_out.cap, last, &o->kernel_launches) != RC_OK) return RC_FAIL;
+        issued = b + 1;
+        if (issued - next_drain >= (uint64_t)NS) {       /* ring full: retire the oldest while NS-1 younger ones are queued */
+            if (drain(slot_of(next_drain)) != RC_OK) return RC_FAIL; next_drain++;
         }
     }
-    for (int k = 0; k < NS; k++, next_drain++) if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL;
+    for (; next_drain < issued; next_drain++) if (drain(slot_of(next_drain)) != RC_OK) return RC_FAIL;
     o->consumed = consumed; o->produced = out; o->crc = crc;
     return rc;
 }
@@ -581,8 +643,8 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
     const uint8_t *hsrc = c->src_device ? c->src_host_view : c->src;
     if (!hsrc) return RC_PARAMS;
     if (c->src_device != c->dst_device) return RC_PARAMS;
+    SlotGuard guard(e);
     const bool lz4 = (c->fmt == QZB_FMT_LZ4);
-    const int grid_cap = e->sm_count * 8;
     uint64_t cur_in = 0, cur_out = 0;      /* everything before these offsets is decoded and delivered */
     uint64_t zlib_window = e->tune.zlib_window_bytes;       /* span searched for zlib stream starts per round */
 

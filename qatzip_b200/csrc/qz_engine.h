@@ -19,7 +19,10 @@ int qzb_runtime_devices(void);
 /* which device this process uses by default: QZB200_DEVICE, else LOCAL_RANK, else 0 */
 int qzb_runtime_default_device(void);
 
+/* devices host-buffer compress calls may be spread over (QZB200_DEVICES; default: the one default device) */
+int qzb_runtime_device_list(int *out, int cap);
 QzbEngine *qzb_engine_create(int device);
+int qzb_engine_device_count(const QzbEngine *e);
 void qzb_engine_destroy(QzbEngine *e);
 
 typedef struct QzbCompressCall {

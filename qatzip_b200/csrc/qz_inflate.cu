@@ -116,8 +116,11 @@ __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t l
  * parallel parts -- building a block's tables, placing a batch of tokens, stored blocks, the checksum -- are done by the
  * whole warp, slot after slot.  One round: free slots draw members; slots between blocks read their block header; all
  * decoders fill their token buffers; the batches are placed; finished members are checked and reported. */
+#ifndef QZ_INFL_MIN_CTAS
+#define QZ_INFL_MIN_CTAS(dpw) ((dpw) == 1 ? 3 : (dpw) == 2 ? 2 : 1)
+#endif
 template <int DPW>
-__global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
+__global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel(QzbDecompressJob job)
 {
     constexpr uint32_t TL = 32 / DPW;               /* lanes per slot */
     QZ_DYN_SMEM(smem_raw);
@@ -195,15 +198,15 @@ __global__ void __launch_bounds__(256) qzb_inflate_kernel(QzbDecompressJob job)
         if (type == 1) qz_inflate_fixed_lens(&slots[myslot].t);
         else if (type == 2 && qz_inflate_read_dynamic(&br, &slots[myslot].t, &hlit, &hdist) != 0) { status = QZB_ST_DATA_ERROR; done = true; type = 7; }
         __syncwarp();
-        /* ... and the whole warp builds the tables, slot after slot (the literal/length table's tail doubles as scratch
-         * until it is cleared) */
+        /* ... and the whole warp builds the tables, slot after slot (the distance table doubles as scratch until it is
+         * cleared) */
         uint32_t hmask = __ballot_sync(FULL, type == 1 || type == 2);
         while (hmask) {
             const uint32_t j = __ffs(hmask) - 1; hmask &= hmask - 1;
             QzInflTables &T = slots[j / TL].t;
             const uint32_t hl = __shfl_sync(FULL, hlit, j), hd = __shfl_sync(FULL, hdist, j);
-            const bool bad = warp_infl_prepare(T.lens, (int)hl, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut + 512, lane) < 0 ||
-                             warp_infl_prepare(T.lens + hl, (int)hd, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.ll_lut + 512, lane) < 0;
+            const bool bad = warp_infl_prepare(T.lens, (int)hl, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.d_lut + 64, lane) < 0 ||
+                             warp_infl_prepare(T.lens + hl, (int)hd, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut + 64, lane) < 0;
             if (bad) { if (lane == j) { status = QZB_ST_DATA_ERROR; done = true; } continue; }
             __syncwarp();
             for (uint32_t i = lane; i < (1u << QZ_LL_LUT_BITS); i += 32) T.ll_lut[i] = 0;

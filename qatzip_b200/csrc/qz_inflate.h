@@ -12,8 +12,12 @@
 #include "qz_hd.h"
 #include "qz_deflate_tables.h"
 
-#define QZ_LL_LUT_BITS 10    /* 4 KiB of 32-bit entries per warp */
-#define QZ_D_LUT_BITS 8
+#ifndef QZ_LL_LUT_BITS
+#define QZ_LL_LUT_BITS 10    /* 4 KiB of 32-bit entries per member being decoded */
+#endif
+#ifndef QZ_D_LUT_BITS
+#define QZ_D_LUT_BITS 8      /* at least 7: the code-length alphabet's table borrows 128 entries */
+#endif
 
 /* Decode-table entry:
  *   bits 0..3   code length (1..15); an all-zero entry = code longer than the table, or unused
@@ -134,16 +138,15 @@ QZ_HD void qz_infl_fill_lut(const uint8_t *len, const uint16_t *count, const uin
         for (uint32_t k = r; k < (1u << lut_bits); k += (1u << l)) lut[k] = e;
     }
 }
-/* canonical bit-by-bit decode for codes longer than the table.  Returns the symbol and its code length
- * in *len_out, or -1. */
-QZ_HD int qz_infl_slow(uint64_t acc, const uint16_t *count, const uint16_t *sorted, uint32_t *len_out)
+/* Canonical decode for codes longer than the table's `lut_bits` (the table has already ruled out every shorter code): the
+ * next 15 bits as an MSB-first number; its l-bit prefix is a code of length l exactly when it falls into that length's range
+ * of consecutive codes.  Returns the symbol and its code length in *len_out, or -1. */
+QZ_HD int qz_infl_slow(uint64_t acc, const uint16_t *count, const uint16_t *first, const uint16_t *offs, const uint16_t *sorted, int lut_bits, uint32_t *len_out)
 {
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l < 16; l++) {
-        code |= (int)(acc & 1); acc >>= 1;
-        int c = count[l];
-        if (code - c < first) { *len_out = (uint32_t)l; return sorted[index + (code - first)]; }
-        index += c; first += c; first <<= 1; code <<= 1;
+    const uint32_t rev = qz_bitrev((uint32_t)acc & 0x7fffu, 15);
+    for (int l = lut_bits + 1; l < 16; l++) {
+        const uint32_t idx = (rev >> (15 - l)) - first[l];
+        if (idx < count[l]) { *len_out = (uint32_t)l; return sorted[offs[l] + idx]; }
     }
     return -1;
 }
@@ -187,7 +190,7 @@ lit:
             continue;
         }
         if (e == 0) {
-            uint32_t l; const int sym = qz_infl_slow(acc, t->ll_count, t->ll_sorted, &l);
+            uint32_t l; const int sym = qz_infl_slow(acc, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
             if (sym < 0) { ev = QZI_ERR_DATA; goto done; }
             e = qz_infl_ll_entry((uint32_t)sym, l);
             if ((int32_t)e < 0) goto lit;
@@ -204,7 +207,7 @@ lit:
             QZI_REFILL();
             uint32_t de = d_lut[(uint32_t)acc & ((1u << QZ_D_LUT_BITS) - 1)];
             if (de == 0) {
-                uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_sorted, &l);
+                uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_first, t->d_offs, t->d_sorted, QZ_D_LUT_BITS, &l);
                 if (ds < 0) { ev = QZI_ERR_DATA; goto done; }
                 de = qz_infl_d_entry((uint32_t)ds, l);
             }
