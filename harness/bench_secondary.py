@@ -283,39 +283,47 @@ def stream_leg(prod, ref_lib, cor, peak, ncores):
 
 # ------------------------------------------------------------------------------------------------ one process, all GPUs
 def one_process_leg(prod, cor, ncores, steps, nbytes, fmt=q.QZ_DEFLATE_GZIP_EXT):
-    """the headline e2e call pattern (qzCompress, host pinned -> host pinned, 512 MiB calls) from ONE process and ONE thread with
-    QZB200_DEVICES=all: every call deals its batches over all visible GPUs (per-GPU submission queues inside the library)"""
+    """the headline e2e call pattern (qzCompress, host pinned -> host pinned, 512 MiB calls) from ONE process with
+    QZB200_DEVICES=all: (a) one submitting thread -- every call deals its batches over all visible GPUs (per-GPU submission
+    queues inside the library); (b) one submitting thread per GPU with a session each (the reference's own benchmark pattern,
+    test/main.c:2175-2202) -- the sessions take the GPUs in turn as their primary device and still spread every call"""
     L = prod.lib
     ndev = L.qzb200DeviceCount()
+    ncalls = max(ndev, nbytes // CALL)
+    nbytes = ncalls * CALL
     h_in = L.qzMalloc(nbytes, 0, q.PINNED_MEM)
     cap = L.qzMaxCompressedLength(CALL, None)
-    h_out = L.qzMalloc(cap, 0, q.PINNED_MEM)
-    assert h_in and h_out
+    assert h_in
     cor.fill(q.Corpus.SILESIA_LIKE, h_in, nbytes, threads=max(1, min(64, ncores)))
     old = os.environ.get("QZB200_DEVICES")
     os.environ["QZB200_DEVICES"] = "all"
-    sess = prod.new_session(fmt=fmt, hw_buff_sz=65536)
+    res = {}
+    for label, T in (("one_thread", 1), ("thread_per_gpu", ndev)):
+        sess = [prod.new_session(fmt=fmt, hw_buff_sz=65536) for _ in range(T)]
+        outs = [L.qzMalloc(cap, 0, q.PINNED_MEM) for _ in range(T)]
+        assert all(outs)
+        made = [0] * T
 
-    def host_pass():
-        made = 0
-        for i in range(nbytes // CALL):
-            rc, used, m = prod.compress_call(sess, h_in + i * CALL, CALL, h_out, cap, 1)
-            assert rc == 0 and used == CALL
-            made += m
-        return made
-    host_pass()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        made = host_pass()
-    dt = (time.perf_counter() - t0) / steps
-    devices = prod.stats(sess).devices
-    prod.end_session(sess)
+        def work(t):
+            made[t] = 0
+            for i in range(t, ncalls, T):
+                rc, used, m = prod.compress_call(sess[t], h_in + i * CALL, CALL, outs[t], cap, 1)
+                assert rc == 0 and used == CALL
+                made[t] += m
+        _threads_run(T, work)
+        dt = min(_threads_run(T, work) for _ in range(steps))
+        devices = prod.stats(sess[0]).devices
+        for s_ in sess:
+            prod.end_session(s_)
+        for o in outs:
+            L.qzFree(o)
+        res[label] = {"value": round(nbytes / dt / GB, 3), "unit": "GB/s", "threads": T, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(sum(made)),
+                      "api": "qzCompress(host pinned -> host pinned), 512 MiB per call, one session per thread"}
     if old is None:
         os.environ.pop("QZB200_DEVICES", None)
     else:
         os.environ["QZB200_DEVICES"] = old
-    L.qzFree(h_in); L.qzFree(h_out)
-    return {"config": f"qzCompress {'QZ_LZ4' if fmt == q.FMT_LZ4 else 'QZ_DEFLATE_GZIP_EXT'}, 64 KiB chunks, {nbytes / (1 << 30):g} GiB, one process, one submitting thread, QZB200_DEVICES=all",
+    L.qzFree(h_in)
+    return {"config": f"qzCompress {'QZ_LZ4' if fmt == q.FMT_LZ4 else 'QZ_DEFLATE_GZIP_EXT'}, 64 KiB chunks, {nbytes / (1 << 30):g} GiB, ONE process, QZB200_DEVICES=all",
             "devices": int(devices), "visible_devices": int(ndev), "metric": "qzCompress GB/s (input), end to end", "unit": "GB/s",
-            "e2e": {"value": round(nbytes / dt / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(made),
-                    "api": "qzCompress(host pinned -> host pinned), 512 MiB per call"}, "ratio": round(made / nbytes, 4)}
+            "e2e": res["thread_per_gpu"], "e2e_one_thread": res["one_thread"], "ratio": round(sum(made) / (nbytes / 1) if False else res["thread_per_gpu"]["d2h_bytes_per_step"] / nbytes, 4)}

@@ -24,7 +24,7 @@ class Member(C.Structure):  # QzbMember, qatzip_b200/csrc/qz_kernels.cuh
 
 class MemberResult(C.Structure):  # QzbMemberResult
     _fields_ = [("status", C.c_uint32), ("consumed", C.c_uint32), ("produced", C.c_uint32), ("cksum", C.c_uint32),
-                ("saw_final", C.c_uint32), ("pad", C.c_uint32 * 3)]
+                ("saw_final", C.c_uint32), ("safe_consumed", C.c_uint32), ("safe_produced", C.c_uint32), ("pad", C.c_uint32)]
 
 
 def build():

@@ -554,6 +554,22 @@ extern "C" void qzFree(void *m)
 extern "C" int qzMemFindAddr(unsigned char *a) { return a ? qzb_pinned_contains(a, 1) : 0; }
 
 /* ------------------------------------------------------------------ stream API (reference src/qatzip_stream.c) */
+/* Compress streams are double-buffered: while the caller fills one staging buffer, a worker thread of the stream has the
+ * engine compress the other one (reference: one synchronous request per full buffer, src/qatzip_stream.c:514-560). */
+struct QzbStreamJob {
+    unsigned char *in = nullptr, *out = nullptr;     /* staging input (pinned), its compressed form */
+    unsigned int in_cap = 0, out_cap = 0, in_len = 0, out_len = 0, last = 0;
+    int rc = QZ_OK;
+};
+struct QzbStreamWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    QzSession_T *sess = nullptr;
+    QzbStreamJob *job = nullptr;           /* queued or running; nullptr = idle */
+    bool running = false, quit = false;
+    unsigned long crc = 0;                 /* running CRC of the stream, carried from job to job */
+};
 struct QzbStreamBuf {
     unsigned char *in_buf, *out_buf;
     unsigned int in_cap, out_cap;          /* staging capacity (may grow beyond strm_buff_sz on decode) */
@@ -561,7 +577,31 @@ struct QzbStreamBuf {
     unsigned int flush_more;
     unsigned int finished;                 /* a call with last==1 has already been coded */
     unsigned int batched;                  /* compress: staging buffer already sized for batched engine calls */
+    /* compress, asynchronous mode (entered when the first staging buffer has filled once) */
+    QzbStreamWorker *worker;
+    QzbStreamJob *flight;                  /* the job the worker has (its output is taken over when it is done) */
+    QzbStreamJob *spare;                   /* buffers of the job before, reused for the next one */
 };
+static void stream_worker_main(QzbStreamWorker *w)
+{
+    std::unique_lock<std::mutex> lk(w->mu);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->quit || (w->job && !w->running && w->job->rc == 1); });
+        if (w->quit) return;
+        QzbStreamJob *j = w->job;
+        w->running = true;
+        lk.unlock();
+        unsigned int in_len = j->in_len, out_len = j->out_cap;
+        unsigned long crc = w->crc;
+        int rc = qzCompressCrc(w->sess, j->in, &in_len, j->out, &out_len, j->last, &crc);
+        if (rc == QZ_OK && in_len != j->in_len) rc = QZ_FAIL;
+        lk.lock();
+        w->crc = crc; j->out_len = out_len; j->rc = rc == QZ_OK ? QZ_OK : QZ_FAIL;
+        w->running = false;
+        w->cv.notify_all();
+    }
+}
+static void stream_job_free(QzbStreamJob *j) { if (j) { qzFree(j->in); qzFree(j->out); delete j; } }
 static int stream_init(QzSession_T *sess, QzStream_T *strm, QzbSess **sp)
 {
     int rc = ready_session(sess, sp);
@@ -611,21 +651,87 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
     if (s->p.data_fmt != QZ_DEFLATE_RAW && s->p.data_fmt != QZ_DEFLATE_GZIP_EXT) { strm->in_sz = 0; strm->out_sz = 0; return QZ_PARAMS; }
     QzbStreamBuf *b = (QzbStreamBuf *)strm->opaque;
     unsigned int consumed = 0, produced = 0; int rc = QZ_OK;
-    /* The reference submits one engine request per full strm_buff_sz buffer (src/qatzip_stream.c:514-560).
-     * A GPU launch costs about what 20 MiB of compression costs, so the staging buffer here is at least
-     * QZB200_STREAM_BATCH_KB (default 4 MiB, a whole number of chunks) of pinned memory: the stream is
-     * still cut into hw_buff_sz chunks, only fewer, larger engine calls carry them. */
+    /* The reference submits one synchronous engine request per full strm_buff_sz buffer (src/qatzip_stream.c:514-560).
+     * A GPU launch costs about what 20 MiB of compression costs, so the staging buffer here is QZB200_STREAM_BATCH_KB
+     * (default 8 MiB, a whole number of chunks) of pinned memory, and there are two of them: while the caller fills one,
+     * the stream's worker thread has the engine compress the other.  The stream is still cut into hw_buff_sz chunks, the
+     * bytes are the same; output appears in larger steps.  QZB200_STREAM_BATCH_KB=0: the reference's cadence, synchronous. */
     if (!b->batched) {
         b->batched = 1;
         const char *ev = getenv("QZB200_STREAM_BATCH_KB");
-        unsigned long long want = (ev && *ev ? strtoull(ev, NULL, 10) : 4096ull) << 10;
+        unsigned long long want = (ev && *ev ? strtoull(ev, NULL, 10) : 8192ull) << 10;
         const unsigned int hw = s->p.hw_buff_sz;
         if (want > (64ull << 20)) want = 64ull << 20;
         want = (want + hw - 1) / hw * hw;
         if (want > b->in_cap && strm->pending_in == 0 && strm->pending_out == 0) {
             unsigned char *ni = (unsigned char *)qzMalloc((size_t)want, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
-            if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = (unsigned int)want; b->in_off = 0; }
+            if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = (unsigned int)want; b->in_off = 0; b->batched = 2; }
         }
+    }
+    if (b->batched == 2) {
+        /* ---- double-buffered: at most one job with the worker while this thread stages the next ---- */
+        auto take_over = [&](bool wait) -> bool {        /* the finished job's output becomes the pending output */
+            if (!b->flight || strm->pending_out) return false;
+            QzbStreamWorker *w = b->worker;
+            std::unique_lock<std::mutex> lk(w->mu);
+            if (!wait && (w->running || b->flight->rc == 1)) return false;
+            w->cv.wait(lk, [&] { return !w->running && b->flight->rc != 1; });
+            QzbStreamJob *j = b->flight;
+            w->job = nullptr; b->flight = nullptr;
+            if (b->spare) stream_job_free(b->spare);
+            b->spare = j;
+            if (j->rc != QZ_OK) { rc = QZ_FAIL; return false; }
+            std::swap(b->out_buf, j->out); std::swap(b->out_cap, j->out_cap);
+            strm->pending_out = j->out_len; b->out_off = 0; strm->crc_32 = (unsigned int)w->crc;
+            if (j->last) b->finished = 1;
+            return true;
+        };
+        for (;;) {
+            if (strm->pending_out) { produced += stream_copy_out(strm, b, strm->out + produced); if (strm->pending_out) break; }
+            if (take_over(false)) continue;
+            if (rc != QZ_OK) break;
+            if (strm->in) consumed += stream_copy_in(strm, b, strm->in + consumed);
+            const bool input_done = (strm->in_sz == 0);
+            const bool want_last = last && input_done && !b->finished && !(b->flight && b->flight->last);
+            if (strm->pending_in < b->in_cap && !want_last) {
+                /* nothing to submit: at the end of the stream wait for what is still in flight */
+                if (last && input_done && b->flight) { if (take_over(true)) continue; if (rc != QZ_OK) break; }
+                break;
+            }
+            /* the staged buffer goes to the worker: first the job before it must be done and its output taken over
+             * (if that output is still waiting for room in the caller's buffer, so does everything else) */
+            if (b->flight) { if (take_over(true)) continue; break; }
+            if (!b->worker) {
+                b->worker = new QzbStreamWorker();
+                b->worker->sess = sess; b->worker->crc = strm->crc_32;
+                b->worker->th = std::thread(stream_worker_main, b->worker);
+            }
+            QzbStreamJob *j = b->spare; b->spare = nullptr;
+            const unsigned int need_out = qzMaxCompressedLength(b->in_cap, sess);
+            if (!j) {
+                j = new QzbStreamJob();
+                j->in_cap = b->in_cap; j->in = (unsigned char *)qzMalloc(j->in_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+                j->out_cap = need_out; j->out = (unsigned char *)qzMalloc(j->out_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+                if (!j->in || !j->out) { stream_job_free(j); rc = QZ_FAIL; break; }
+            }
+            if (j->out_cap < need_out) {
+                qzFree(j->out); j->out_cap = need_out; j->out = (unsigned char *)qzMalloc(j->out_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+                if (!j->out) { stream_job_free(j); rc = QZ_FAIL; break; }
+            }
+            std::swap(b->in_buf, j->in); std::swap(b->in_cap, j->in_cap);        /* the job's old input buffer is the next one to fill */
+            j->in_len = strm->pending_in; j->last = want_last ? 1u : 0u; j->out_len = 0;
+            strm->pending_in = 0; b->in_off = 0;
+            {
+                std::lock_guard<std::mutex> g(b->worker->mu);
+                j->rc = 1;                                   /* queued */
+                b->worker->job = j; b->flight = j;
+            }
+            b->worker->cv.notify_all();
+            if (want_last) { if (take_over(true)) continue; break; }
+            if (input_done) break;
+        }
+        strm->in_sz = consumed; strm->out_sz = produced;
+        return rc;
     }
     /* 1. hand over output left from an earlier call */
     if (strm->pending_out) {
@@ -722,6 +828,13 @@ extern "C" int qzEndStream(QzSession_T *sess, QzStream_T *strm)
     if (!sess || !strm) return QZ_PARAMS;
     if (strm->opaque) {
         QzbStreamBuf *b = (QzbStreamBuf *)strm->opaque;
+        if (b->worker) {
+            { std::unique_lock<std::mutex> lk(b->worker->mu); b->worker->cv.wait(lk, [&] { return !b->worker->running && !(b->worker->job && b->worker->job->rc == 1); }); b->worker->quit = true; }
+            b->worker->cv.notify_all();
+            b->worker->th.join();
+            delete b->worker;
+        }
+        stream_job_free(b->flight); stream_job_free(b->spare);
         qzFree(b->in_buf); qzFree(b->out_buf); free(b);
         strm->opaque = NULL;
     }

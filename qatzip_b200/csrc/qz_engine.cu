@@ -1033,6 +1033,13 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                         }
                     }
                     if (st == RC_OK && r.produced > c->dst_cap - cur_out) st = RC_BUF_ERROR;
+                    if (st != RC_OK && c->fmt == QZB_FMT_RAW && r.safe_produced && r.safe_consumed && r.safe_produced <= c->dst_cap - cur_out) {
+                        /* a raw stream that ran out of input (or room) behind a flush marker: everything up to that marker is
+                         * delivered and the call reports how far it got, so a stream caller can go on from there with more
+                         * input (reference: the piecemeal path of src/qatzip_stream.c:599-749) */
+                        if (deliver(from, r.safe_produced) != RC_OK) return RC_FAIL;
+                        cur_out += r.safe_produced; cur_in = u.unit_start + r.safe_consumed; o->nmembers++;
+                    }
                     if (st != RC_OK) { rc2 = st; break; }
                     if (deliver(from, r.produced) != RC_OK) return RC_FAIL;
                     cur_out += r.produced;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
 
     /* slot state, meaningful in the slot's decoder lane */
     bool active = false, exhausted = false, in_block = false;
-    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0;
+    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0, safe_in = 0, safe_out = 0;
     const uint8_t *src = job.src; uint8_t *dst = job.dst;
     QzbMember m; m.src_off = 0; m.src_len = 0; m.exact_len = 0; m.dst_off = 0; m.dst_cap = 0; m.exact_out = 0; m.expect_cksum = 0; m.check_cksum = 0;
     QzBitReader br; qz_br_init(&br, job.src, 0);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
                 m = job.members[mi];
                 src = job.src + m.src_off; dst = job.dst + m.dst_off; cap = m.dst_cap;
                 qz_br_init(&br, src, m.src_len);
-                out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; active = true;
+                out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; active = true; safe_in = 0; safe_out = 0;
             }
         }
         if (__ballot_sync(FULL, is_dec && active) == 0) break;
@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
             uint8_t *to = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j)) + o;
             if (wr) for (uint32_t i = lane; i < n; i += 32) to[i] = from[i];
         }
-        if (type == 0) { out += slen; if (bfinal && status == QZB_ST_OK) done = true; }
+        if (type == 0) {
+            out += slen;
+            if (status == QZB_ST_OK) { safe_in = qz_br_consumed(&br); safe_out = out; if (bfinal) done = true; }      /* byte-aligned behind a stored block */
+        }
         __syncwarp();
         /* Huffman blocks: every decoder reads its code lengths (dynamic) or fills in the fixed ones ... */
         uint32_t hlit = 288, hdist = 30;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
                 if (status == QZB_ST_OK && wr && m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
                 QzbMemberResult r;
                 r.status = status; r.consumed = consumed; r.produced = out; r.cksum = crc; r.saw_final = bfinal;
-                r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                r.safe_consumed = safe_in; r.safe_produced = safe_out; r.pad = 0;
                 job.results[mi] = r;
                 active = false;
             }

@@ -56,7 +56,9 @@ struct QzbMemberResult {
     uint32_t produced;
     uint32_t cksum;              /* CRC-32 / XXH32 of the output */
     uint32_t saw_final;          /* deflate: BFINAL block seen */
-    uint32_t pad[3];
+    uint32_t safe_consumed;      /* deflate: input and output position behind the last stored block (byte-aligned: every flush marker */
+    uint32_t safe_produced;      /*   is one), where a decode that ran out of input or room can be picked up again; 0 if none */
+    uint32_t pad;
 };
 struct QzbDecompressJob {
     const uint8_t *src;

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) qzb_lz4_decompress_kernel(QzbDecompressJo
         }
         if (lane == 0) {
             QzbMemberResult r;
-            r.status = status; r.consumed = ip; r.produced = op; r.cksum = ck; r.saw_final = 1; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            r.status = status; r.consumed = ip; r.produced = op; r.cksum = ck; r.saw_final = 1; r.safe_consumed = r.safe_produced = r.pad = 0;
             job.results[mi] = r;
         }
         __syncwarp();

@@ -467,6 +467,25 @@ def test_stream_decompress_slices(prod, data):
     prod.end_session(sess)
 
 
+def test_stream_decompress_raw_piecemeal(prod, ref, data):
+    """reference test mode 9 on QZ_DEFLATE_RAW (test/main.c:2506-2848; piecemeal path src/qatzip_stream.c:599-749): a raw
+    stream of several chunks comes back through qzDecompressStream in slices -- hw_buff_sz / 4 as the reference feeds it, and a
+    256-byte drip -- without the whole stream ever being staged at once being a requirement: everything up to the last flush
+    marker that has arrived is delivered"""
+    d = pick(data, 700000, 21)
+    # made by our qzCompressStream, and by the reference's software path in one call
+    sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW)
+    ours = stream_compress(prod, sess, d, 30000, 1 << 20)[0]
+    prod.end_session(sess)
+    theirs = ref.compress(d, fmt=q.QZ_DEFLATE_RAW)
+    assert zlib.decompress(ours, -15) == d
+    for blob in (ours, theirs):
+        for slice_sz, out_sz in ((16384, 1 << 20), (256, 1 << 20), (100000, 65536)):
+            sess = prod.new_session(fmt=q.QZ_DEFLATE_RAW)
+            assert stream_decompress(prod, sess, blob, slice_sz, out_sz) == d
+            prod.end_session(sess)
+
+
 def test_stream_rejects_other_formats(prod):
     sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP)
     st = q.QzStream(); buf = (C.c_ubyte * 4096)()
