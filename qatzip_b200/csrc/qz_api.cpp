@@ -270,7 +270,8 @@ extern "C" int qzSetupSession(QzSession_T *sess, QzSessionParams_T *params)
     QzSessionParams_T tmp;
     if (!params) { qzGetDefaults(&tmp); params = &tmp; }
     if (check_params_v1(params) != QZ_OK) return QZ_PARAMS;
-    QzbParams p = g_defaults;
+    QzbParams p;
+    { std::lock_guard<std::mutex> g(g_defaults_lock); p = g_defaults; }
     p.huffman_hdr = params->huffman_hdr; p.direction = params->direction; p.data_fmt = fmt_to_internal(params->data_fmt);
     p.comp_lvl = params->comp_lvl; p.comp_algorithm = params->comp_algorithm; p.max_forks = params->max_forks;
     p.sw_backup = params->sw_backup; p.hw_buff_sz = params->hw_buff_sz; p.strm_buff_sz = params->strm_buff_sz;
@@ -284,7 +285,8 @@ extern "C" int qzSetupSessionDeflate(QzSession_T *sess, QzSessionParamsDeflate_T
     QzSessionParamsDeflate_T tmp;
     if (!params) { qzGetDefaultsDeflate(&tmp); params = &tmp; }
     if (check_params_deflate(params) != QZ_OK) return QZ_PARAMS;
-    QzbParams p = g_defaults;
+    QzbParams p;
+    { std::lock_guard<std::mutex> g(g_defaults_lock); p = g_defaults; }
     internal_from_common(&p, &params->common_params);
     p.huffman_hdr = params->huffman_hdr; p.data_fmt = fmt_to_internal(params->data_fmt);
     p.stop_decompression_stream_end = 0; p.zlib_format = 0;
@@ -297,7 +299,8 @@ extern "C" int qzSetupSessionDeflateExt(QzSession_T *sess, QzSessionParamsDeflat
     if (!params) { qzGetDefaultsDeflateExt(&tmp); params = &tmp; }
     if (check_params_deflate(&params->deflate_params) != QZ_OK) return QZ_PARAMS;
     if (params->zlib_format > 1) return QZ_PARAMS;
-    QzbParams p = g_defaults;
+    QzbParams p;
+    { std::lock_guard<std::mutex> g(g_defaults_lock); p = g_defaults; }
     internal_from_common(&p, &params->deflate_params.common_params);
     p.huffman_hdr = params->deflate_params.huffman_hdr; p.data_fmt = fmt_to_internal(params->deflate_params.data_fmt);
     p.stop_decompression_stream_end = params->stop_decompression_stream_end; p.zlib_format = params->zlib_format;
@@ -310,7 +313,8 @@ extern "C" int qzSetupSessionLZ4(QzSession_T *sess, QzSessionParamsLZ4_T *params
     QzSessionParamsLZ4_T tmp;
     if (!params) { qzGetDefaultsLZ4(&tmp); params = &tmp; }
     if (check_params_lz4(params) != QZ_OK) return QZ_PARAMS;
-    QzbParams p = g_defaults;
+    QzbParams p;
+    { std::lock_guard<std::mutex> g(g_defaults_lock); p = g_defaults; }
     internal_from_common(&p, &params->common_params);
     p.data_fmt = QZB_FMT_INTERNAL_LZ4; p.stop_decompression_stream_end = 0; p.zlib_format = 0;
     return attach_session(sess, &p);
@@ -342,7 +346,10 @@ extern "C" int qzTeardownSession(QzSession_T *sess)
 extern "C" int qzClose(QzSession_T *sess)
 {
     if (!sess) return QZ_PARAMS;
-    /* device context is process-wide and released at unload; nothing per-session to stop */
+    /* the device context is process-wide and released at unload; what qzClose undoes is qzInit, so that a later qzInit
+     * answers QZ_OK again like the reference's (src/qatzip.c:1084-1116 stops the service qzInit started) */
+    std::lock_guard<std::mutex> g(g_lock);
+    g_init_done = 0; g_init_rc = QZ_NONE;
     return QZ_OK;
 }
 extern "C" int qzGetStatus(QzSession_T *sess, QzStatus_T *status)
@@ -454,8 +461,9 @@ extern "C" int qzDecompressCrcExt(QzSession_T *sess, const unsigned char *src, u
         s->end_of_stream = 0;
         rc = qzb_engine_decompress(s->engine, &c, &o);
         s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.kernel_ms; s->stats.codec_launches = o.kernel_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
-        if (rc != QZ_OK && rc != QZ_BUF_ERROR && rc != QZ_DATA_ERROR) goto err;
-        if (rc == QZ_DATA_ERROR && o.consumed == 0) goto err;
+        /* an error behind members that did decode: their lengths are reported together with the code, like the reference does
+         * (src/qatzip.c:2640-2650), so a stream caller can deliver them */
+        if (rc != QZ_OK && rc != QZ_BUF_ERROR && o.consumed == 0) goto err;
         if (o.nmembers > 0) s->end_of_stream = 1;                        /* reference src/qatzip_utils.c:1534-1554 */
         *src_len = (unsigned int)o.consumed; *dest_len = (unsigned int)o.produced;
         sess->total_in += o.consumed; sess->total_out += o.produced;
@@ -541,9 +549,14 @@ extern "C" unsigned int qzMaxCompressedLength(unsigned int src_sz, QzSession_T *
 extern "C" void *qzMalloc(size_t sz, int numa, int force_pinned)
 {
     (void)numa;
-    void *p = qzb_pinned_alloc(sz);
-    if (p) return p;
-    if (force_pinned == PINNED_MEM) return NULL;       /* reference src/qatzip_mem.c:211-215 */
+    /* page-locked memory for PINNED_MEM requests and for anything large enough to be worth DMA-ing from directly;
+     * small COMMON_MEM requests (stream bookkeeping, tests) come from the heap: cudaHostAlloc costs a system call and
+     * locks pages (reference src/qatzip_mem.c:199-215: pinned first, heap as the COMMON_MEM fallback) */
+    if (force_pinned == PINNED_MEM || sz >= (256u << 10)) {
+        void *p = qzb_pinned_alloc(sz);
+        if (p) return p;
+        if (force_pinned == PINNED_MEM) return NULL;       /* reference src/qatzip_mem.c:211-215 */
+    }
     return malloc(sz ? sz : 1);
 }
 extern "C" void qzFree(void *m)
@@ -879,6 +892,7 @@ extern "C" int qzb200DecompressDevice(QzSession_T *sess, const void *d_src, cons
     rc = qzb_engine_decompress(s->engine, &c, &o);
     s->stats.kernel_ms = o.kernel_ms; s->stats.codec_ms = o.kernel_ms; s->stats.codec_launches = o.kernel_launches; s->stats.kernel_launches = o.kernel_launches; s->stats.units = o.nmembers;
     *consumed = o.consumed; *produced = o.produced;
+    if (rc == QZ_OK || rc == QZ_BUF_ERROR) { sess->total_in += o.consumed; sess->total_out += o.produced; }
     return rc;
 }
 extern "C" int qzb200GetStats(QzSession_T *sess, QzB200Stats_T *st)

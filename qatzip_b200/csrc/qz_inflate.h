@@ -216,7 +216,7 @@ lit:
             const uint32_t dist = ((de >> 8) & 0xffff) + (((uint32_t)(acc >> dcl)) & ~(0xffffffffu << deb));
             acc >>= (dcl + deb); nacc -= (dcl + deb);
             if (dist > o) { ev = QZI_ERR_DATA; goto done; }
-            if (o + len > cap) { ev = QZI_ERR_FULL; goto done; }
+            if (len > cap - o) { ev = QZI_ERR_FULL; goto done; }      /* (o <= cap always; no 32-bit wrap) */
             *tp++ = ((len - 3) << 16) | (dist - 1);
             o += len;
         }

@@ -467,6 +467,25 @@ def test_stream_decompress_slices(prod, data):
     prod.end_session(sess)
 
 
+def test_golden_streams_through_the_gpu_decoder(prod):
+    """the committed fixtures (streams the compiled reference made, tests/golden/make_golden.py) through the product's
+    qzDecompress at the hw_buff_sz they were made with, and through qzDecompressStream in 100-byte slices"""
+    import hashlib
+    import json
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    man = json.load(open(os.path.join(gold, "manifest.json")))
+    assert man["cases"]
+    for case in man["cases"]:
+        raw = open(os.path.join(gold, case["input"]), "rb").read()
+        blob = open(os.path.join(gold, case["stream"]), "rb").read()
+        assert hashlib.sha256(raw).hexdigest() == case["input_sha256"]
+        assert prod.decompress(blob, len(raw) + 8, fmt=case["fmt"], hw_buff_sz=case["hw_buff_sz"]) == raw, case["stream"]
+        if case["fmt"] in (q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW) and len(raw) > 1:
+            sess = prod.new_session(fmt=case["fmt"], hw_buff_sz=case["hw_buff_sz"])
+            assert stream_decompress(prod, sess, blob, 100, 1 << 16) == raw, case["stream"]
+            prod.end_session(sess)
+
+
 def test_stream_decompress_raw_piecemeal(prod, ref, data):
     """reference test mode 9 on QZ_DEFLATE_RAW (test/main.c:2506-2848; piecemeal path src/qatzip_stream.c:599-749): a raw
     stream of several chunks comes back through qzDecompressStream in slices -- hw_buff_sz / 4 as the reference feeds it, and a
