@@ -86,16 +86,17 @@ def inflate_leg(prod, ref_lib, cor, peak, ncores, steps):
     h_c = L.qzMalloc(total_c, 0, q.PINNED_MEM)
     h_back = L.qzMalloc(n_out, 0, q.PINNED_MEM)
     assert h_c and h_back
-    # calls of at most 512 MiB of output (the API's lengths are 32-bit): [(c_off, c_len, out_off, out_len)]
+    # calls of at most 3.5 GiB of output (the API's lengths are 32-bit): [(c_off, c_len, out_off, out_len)]
+    OUT_CALL = 3584 << 20
     calls, c_off, o_off, cl, ol = [], 0, 0, 0, 0
     off = 0
     for m, (_, n) in zip(members, cuts):
         C.memmove(h_c + off, m, len(m)); off += len(m)
-        if ol + n > CALL:
+        if ol + n > OUT_CALL:
             calls.append((c_off, cl, o_off, ol)); c_off += cl; o_off += ol; cl = ol = 0
         cl += len(m); ol += n
     calls.append((c_off, cl, o_off, ol))
-    d_c, d_out = L.qzb200DeviceAlloc(max(c[1] for c in calls)), L.qzb200DeviceAlloc(CALL)
+    d_c, d_out = L.qzb200DeviceAlloc(max(c[1] for c in calls)), L.qzb200DeviceAlloc(max(c[3] for c in calls))
     assert d_c and d_out
     sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP, hw_buff_sz=262144)
 
@@ -157,7 +158,7 @@ def inflate_leg(prod, ref_lib, cor, peak, ncores, steps):
             "metric": "qzDecompress GB/s (output)", "unit": "GB/s", "members": len(members), "compressed_ratio": round(total_c / n_out, 4),
             "value": round(n_out / wall / GB, 3), "value_kernels_only": round(n_out / (kms / 1e3) / GB, 3),
             "e2e": {"value": round(n_out / e2e_s / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": total_c, "d2h_bytes_per_step": n_out,
-                    "api": "qzDecompress(host pinned -> host pinned), calls of <= 512 MiB of output"},
+                    "api": "qzDecompress(host pinned -> host pinned), calls of <= 3.5 GiB of output"},
             "bit_exact": exact, "roofline": dict(_roof(total_c + n_out, kms, launches, peak) or {}, kernel="qzb_inflate_kernel"),
             "cpu_baseline": {"value": round(sample_out / ref_s / GB, 3), "unit": "GB/s", "cores": T, "kind": "reference",
                              "sample": f"the first {sample_members} members ({sample_out >> 20} MiB of output), one slice per thread"},

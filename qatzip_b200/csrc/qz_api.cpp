@@ -552,7 +552,7 @@ extern "C" void *qzMalloc(size_t sz, int numa, int force_pinned)
     /* page-locked memory for PINNED_MEM requests and for anything large enough to be worth DMA-ing from directly;
      * small COMMON_MEM requests (stream bookkeeping, tests) come from the heap: cudaHostAlloc costs a system call and
      * locks pages (reference src/qatzip_mem.c:199-215: pinned first, heap as the COMMON_MEM fallback) */
-    if (force_pinned == PINNED_MEM || sz >= (256u << 10)) {
+    if (force_pinned == PINNED_MEM || sz >= (96u << 10)) {
         void *p = qzb_pinned_alloc(sz);
         if (p) return p;
         if (force_pinned == PINNED_MEM) return NULL;       /* reference src/qatzip_mem.c:211-215 */

@@ -1,13 +1,13 @@
 """Copy what a tools/gpu_final.sh visit left in gpurun_out/ into profiles/ under a round/version tag:
 bench lines, the ncu launch list, text summaries of the two full ncu captures, DRAM traffic of the deflate launch."""
 import csv, io, json, os, shutil, subprocess, sys
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01_v8"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 G, P = "gpurun_out", "profiles"
 def cp(src, dst):
     if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(P, dst)); print("copied", dst)
 cp("bench.json", f"{tag}_bench.json"); cp("bench_ref.json", f"{tag}_bench_ref.json"); cp("launches.csv", f"{tag}_launches_bench.csv")
 cp("extra.json", f"{tag}_extra.json"); cp("inflate_bench.json", f"{tag}_inflate_bench.json"); cp("geom.jsonl", f"{tag}_geometry_sweep.jsonl"); cp("geom41.jsonl", f"{tag}_group_ab.jsonl"); cp("pcie_duplex.json", f"{tag}_pcie_duplex.json"); cp("timeline.log", f"{tag}_e2e_timeline.log")
-cp("bench_taper.json", f"{tag}_bench_taper.json"); cp("bench_2thr.json", f"{tag}_bench_2threads.json"); cp("pytest_gpu.log", f"{tag}_pytest_gpu.log"); cp("group_hash_bits.log", f"{tag}_group_hash_bits.log")
+cp("pytest_gpu.log", f"{tag}_pytest_gpu.log"); cp("phases_window.json", f"{tag}_phases_window_kernel.json")
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max",
         "sm__inst_executed.avg.per_cycle_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -30,7 +30,9 @@ def summarize(rep, out, title):
     print("wrote", out)
     return d
 d = summarize("prof_deflate.ncu-rep", f"{tag}_ncu_deflate_summary.txt",
-              "ncu --set full --clock-control none --import-source on; one launch over a 512 MiB device-resident call of `bench.py --gib 0.5` (65536 pieces in 8192 groups)")
+              "ncu --set full --clock-control none --import-source on; one launch over a 512 MiB device-resident call of `bench.py --gib 0.5` (8192 windows of 64 KiB)")
+summarize("prof_lz4.ncu-rep", f"{tag}_ncu_lz4_summary.txt",
+          "ncu --set full --clock-control none --import-source on; one launch of the LZ4 window kernel over 512 MiB (tools/gpu_perf_extra.py, EXTRA_ONLY=lz4)")
 summarize("prof_inflate.ncu-rep", f"{tag}_ncu_inflate_summary.txt",
           "ncu --set full --clock-control none --import-source on; one launch of tools/gpu_inflate_bench.py (8192 gzip-ext members of 64 KiB made by our compressor, 512 MiB out)")
 if d:
@@ -39,7 +41,10 @@ if d:
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
     rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
     b = json.load(open(os.path.join(G, "bench.json"))) if os.path.exists(os.path.join(G, "bench.json")) else {}
+    sys.path.insert(0, os.getcwd())
+    import bench
     json.dump({"deflate_dram_bytes_per_launch": int(rd + wr), "kernel": d.get("Kernel Name", ("", ""))[0], "dram_read": int(rd), "dram_write": int(wr),
-               "launch": "512 MiB device-resident call, 65536 pieces in 8192 groups", "source": f"ncu --set full capture summarised in profiles/{tag}_ncu_deflate_summary.txt",
+               "launch": "512 MiB device-resident call, 8192 windows of 64 KiB", "capture": f"profiles/{tag}_ncu_deflate_summary.txt", "source_sha": bench.kernel_source_sha(),
+               "source": f"ncu --set full capture summarised in profiles/{tag}_ncu_deflate_summary.txt",
                "algorithmic_bytes": b.get("roofline", {}).get("bytes_per_launch")}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print("traffic", int(rd + wr))
