@@ -91,6 +91,36 @@ __device__ uint32_t warp_crc32_global(const uint8_t *p, uint32_t n, const uint32
     return __shfl_sync(FULL, c, 0);
 }
 
+/* CRC-32 of the 4 KiB at p by the whole warp: 128 bytes per lane, the tree's multipliers x^(8 * 128 * 2^k) in xk[0..5) */
+#define QZ_INFL_CRC_BLOCK 4096u
+__device__ __forceinline__ uint32_t warp_crc32_block(const uint8_t *p, const uint32_t *crc_tab, const uint32_t *xk, uint32_t lane)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(p + lane * 128);
+    uint32_t c = 0xffffffffu;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll 2
+        for (int i = 0; i < 8; i++) {
+            const uint4 v = q[i];
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                c = crc_tab[(c ^ w[k]) & 0xff] ^ (c >> 8); c = crc_tab[(c ^ (w[k] >> 8)) & 0xff] ^ (c >> 8);
+                c = crc_tab[(c ^ (w[k] >> 16)) & 0xff] ^ (c >> 8); c = crc_tab[(c ^ (w[k] >> 24)) & 0xff] ^ (c >> 8);
+            }
+        }
+    } else {
+        const uint8_t *b = p + lane * 128;
+        for (int i = 0; i < 128; i++) c = crc_tab[(c ^ b[i]) & 0xff] ^ (c >> 8);
+    }
+    c = ~c;
+#pragma unroll 1
+    for (int lv = 0; lv < 5; lv++) {
+        const uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);
+        if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, xk[lv]) ^ other;
+    }
+    return __shfl_sync(FULL, c, 0);
+}
+
 /* Adler-32 of dst[0..n) by the whole warp: same strips, sums joined as in qz_adler32.h */
 __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t lane)
 {
@@ -126,17 +156,20 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
     QZ_DYN_SMEM(smem_raw);
     InflWarpSmem *s_w = reinterpret_cast<InflWarpSmem *>(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
+    __shared__ uint32_t s_xk[6];            /* x^(8 * 128 * 2^k), k < 5: the block checksum's tree; [5] = x^(8 * 4096): the fold */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
+    if (threadIdx.x < 6) s_xk[threadIdx.x] = qz_crc_xpow8((uint64_t)128 << threadIdx.x);
     __syncthreads();
     InflWarpSmem *slots = s_w + (size_t)warp * DPW;
+    const bool crc_blocks = !job.size_only && job.fmt != QZB_FMT_ZLIB;       /* CRC-32 taken 4 KiB at a time while the output is still in cache */
     const uint32_t myslot = lane / TL;
     const bool is_dec = (lane % TL) == 0;
     const bool wr = !job.size_only;
 
     /* slot state, meaningful in the slot's decoder lane */
     bool active = false, exhausted = false, in_block = false;
-    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0, safe_in = 0, safe_out = 0;
+    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0, safe_in = 0, safe_out = 0, crc_run = 0, crc_done = 0;
     const uint8_t *src = job.src; uint8_t *dst = job.dst;
     QzbMember m; m.src_off = 0; m.src_len = 0; m.exact_len = 0; m.dst_off = 0; m.dst_cap = 0; m.exact_out = 0; m.expect_cksum = 0; m.check_cksum = 0;
     QzBitReader br; qz_br_init(&br, job.src, 0);
@@ -151,7 +184,7 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
                 m = job.members[mi];
                 src = job.src + m.src_off; dst = job.dst + m.dst_off; cap = m.dst_cap;
                 qz_br_init(&br, src, m.src_len);
-                out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; active = true; safe_in = 0; safe_out = 0;
+                out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; active = true; safe_in = 0; safe_out = 0; crc_run = 0; crc_done = 0;
             }
         }
         if (__ballot_sync(FULL, is_dec && active) == 0) break;
@@ -276,6 +309,21 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
             else if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; done = true; }
         }
 
+        /* ---- checksum of the 4 KiB blocks that have become complete, while they are still in L1 / L2: the running CRC-32
+         * of everything before is multiplied by x^(8 * 4096) and the block's added (zlib's crc32_combine) ---- */
+        if (crc_blocks) {
+            uint32_t cmask = __ballot_sync(FULL, is_dec && active && status == QZB_ST_OK && out - crc_done >= QZ_INFL_CRC_BLOCK);
+            while (cmask) {
+                const uint32_t j = __ffs(cmask) - 1;
+                const uint32_t from = __shfl_sync(FULL, crc_done, j);
+                const uint8_t *d = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
+                __syncwarp();
+                const uint32_t cb = warp_crc32_block(d + from, s_crc_tab, s_xk, lane);
+                if (lane == j) { crc_run = qz_gf2_mul(crc_run, s_xk[5]) ^ cb; crc_done += QZ_INFL_CRC_BLOCK; }
+                if (__shfl_sync(FULL, out - crc_done, j) < QZ_INFL_CRC_BLOCK) cmask &= cmask - 1;
+            }
+        }
+
         /* ---- finished members: verdict, checksum by the whole warp, result ---- */
         uint32_t consumed = 0;
         if (done) {
@@ -291,7 +339,15 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
             const uint32_t stj = __shfl_sync(FULL, status, j), n = __shfl_sync(FULL, out, j);
             const uint8_t *d = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
             uint32_t crc = 0;
-            if (stj == QZB_ST_OK && wr) crc = (job.fmt == QZB_FMT_ZLIB) ? warp_adler32_global(d, n, lane) : warp_crc32_global(d, n, s_crc_tab, lane);
+            if (stj == QZB_ST_OK && wr) {
+                if (job.fmt == QZB_FMT_ZLIB) crc = warp_adler32_global(d, n, lane);
+                else {
+                    /* what the block-wise pass has not covered yet, joined to the running value */
+                    const uint32_t done_j = __shfl_sync(FULL, crc_done, j), run_j = __shfl_sync(FULL, crc_run, j);
+                    const uint32_t tail = warp_crc32_global(d + done_j, n - done_j, s_crc_tab, lane);
+                    crc = done_j ? (n - done_j ? qz_gf2_mul(run_j, __shfl_sync(FULL, lane == 0 ? qz_crc_xpow8(n - done_j) : 0u, 0)) ^ tail : run_j) : tail;
+                }
+            }
             if (lane == j) {
                 if (status == QZB_ST_OK && wr && m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
                 QzbMemberResult r;
