@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(QZ_PIECES_MAX_WARPS * 32) qzb_deflate_pieces_k
             __syncwarp();
             QZ_MARK(1);
             QzmDeflateSink sink = { slots, 0, pkeep };
-            qzm_match_piece(piece, ps.n, 0, ps.n, ws.u.table, 1u << HB, sink, lane);
+            qzm_match_piece<1>(piece, ps.n, 0, ps.n, ws.u.table, 1u << HB, sink, lane);
             ps.nslots = sink.nslots;
             QZ_MARK(2);
         }
@@ -947,6 +947,8 @@ __device__ __noinline__ uint32_t window_checksum(const uint8_t *win, uint32_t n,
     return c ^ (n == QZ_WINDOW ? s_xw[6] : ~qz_gf2_mul(0xffffffffu, qz_crc_xpow8(n)));
 }
 
+/* WAYS: entries of a hash bucket the match stage looks at: 1 (levels 1-5), 2 (levels 6 and up) */
+template <int WAYS>
 __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_kernel(QzbCompressJob job)
 {
     constexpr uint32_t SUB = QZW_SUB, NM = QZW_MATCHERS, NW = QZW_WARPS;
@@ -1054,15 +1056,15 @@ __global__ void __launch_bounds__(QZ_GROUPS_MAX_WARPS * 32) qzb_deflate_window_k
             const uint32_t n = w.wlen > p0 ? min(SUB, w.wlen - p0) : 0u;                  /* bytes of this warp's sub-piece */
             const bool last_in_win = n != 0 && p0 + n == w.wlen;
             /* (a sub-piece's last three positions hash bytes of the next one: they are left to the match stage) */
-            if (n) qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
+            if (n) qzm_prepass<WAYS>(win, p0 + n, p0, p0 + n, table, tent, lane);
             group_bar<NM * 32>(bar_m);
             /* every matcher is past the emission of window k - 2: its code tables (same parity as window k) can go */
             if (wg == 0) { for (uint32_t i = lane; i < QZ_HIST_WORDS; i += 32) C.hist[i] = 0; }
-            qzm_seed_tables(tables, tstride, w.nsub, tent, threadIdx.x, NM * 32);
+            qzm_seed_tables<WAYS>(tables, tstride, w.nsub, tent, threadIdx.x, NM * 32);
             group_bar<NM * 32>(bar_m);
             QZ_MARK(15);
             QzmDeflateSink sink = { slots, 0, pkeep };
-            if (n) qzm_match_piece(win, w.wlen, p0, p0 + n, table, tent, sink, lane);
+            if (n) qzm_match_piece<WAYS>(win, w.wlen, p0, p0 + n, table, tent, sink, lane);
             QZ_MARK(2);
             /* histogram of the warp's slots into the window's; the last sub-piece carries the end-of-block slot */
             const uint32_t extra = warp_sum(slot_hist(C.hist, slots, sink.nslots, s_lentab, lane, pkeep));
@@ -1332,7 +1334,7 @@ extern "C" size_t qzb_deflate_window_smem_bytes(int tent) { return (size_t)windo
 extern "C" int qzb_deflate_window_max_tent(void)
 {
     cudaFuncAttributes a;
-    if (cudaFuncGetAttributes(&a, qzb_deflate_window_kernel) != cudaSuccess) { (void)cudaGetLastError(); return 256; }
+    if (cudaFuncGetAttributes(&a, qzb_deflate_window_kernel<1>) != cudaSuccess) { (void)cudaGetLastError(); return 256; }
     const size_t cap = 227 * 1024 - a.sharedSizeBytes - 64;
     int tent = 256;
     while (tent + 8 <= 32768 && qzb_deflate_window_smem_bytes(tent + 8) <= cap) tent += 8;
@@ -1341,15 +1343,21 @@ extern "C" int qzb_deflate_window_max_tent(void)
 /* 32-bit words of slot scratch the window kernel needs for a grid of CTAs */
 extern "C" size_t qzb_deflate_window_tok_words(int grid) { return (size_t)grid * QZW_MATCHERS * QZW_TOK_WORDS; }
 
-/* window kernel (one deflate block per 64 KiB window), one CTA of 32 warps per SM; job->ngroups and job->tent set */
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, cudaStream_t st)
+/* window kernel (one deflate block per 64 KiB window), one CTA of 32 warps per SM; job->ngroups and job->tent set;
+ * ways: 1, or 2 for the deeper search of compression levels 6 and up */
+template <int WAYS>
+static cudaError_t launch_window(const QzbCompressJob &job, int grid, cudaStream_t st)
 {
-    if (job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups || job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768) return cudaErrorInvalidValue;
-    const size_t smem = qzb_deflate_window_smem_bytes((int)job->tent);
-    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = qzb_deflate_window_smem_bytes((int)job.tent);
+    cudaError_t e = cudaFuncSetAttribute(qzb_deflate_window_kernel<WAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    qzb_deflate_window_kernel<<<grid, QZW_WARPS * 32, smem, st>>>(*job);
+    qzb_deflate_window_kernel<WAYS><<<grid, QZW_WARPS * 32, smem, st>>>(job);
     return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int ways, cudaStream_t st)
+{
+    if (job->pieces_per_chunk % QZ_WINDOW_PIECES || !job->ngroups || job->piece_log2 != 13 || job->tent < 256 || job->tent > 32768 || (job->tent & 1)) return cudaErrorInvalidValue;
+    return ways == 2 ? launch_window<2>(*job, grid, st) : launch_window<1>(*job, grid, st);
 }
 
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st)

@@ -25,7 +25,7 @@
 #include "qz_xxh32.h"
 
 extern "C" cudaError_t qzb_launch_deflate(const QzbCompressJob *job, int hb, int grid, int warps, int nbuf, cudaStream_t st);
-extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, cudaStream_t st);
+extern "C" cudaError_t qzb_launch_deflate_window(const QzbCompressJob *job, int grid, int ways, cudaStream_t st);
 extern "C" size_t qzb_deflate_window_tok_words(int grid);
 extern "C" int qzb_deflate_window_max_tent(void);
 extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t st);
@@ -395,7 +395,7 @@ static int enqueue_compress(QzbEngine *e, Slot &s, const QzbCompressCall *c, con
     CK(cudaEventRecord(s.ev_k0, s.st));
     if (lz4_nw) CK(qzb_launch_lz4_window(&job, grid, lz4_nw, s.st));
     else if (lz4) CK(qzb_launch_lz4_compress(&job, grid, warps, s.st));
-    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, s.st));
+    else if (job.ngroups) CK(qzb_launch_deflate_window(&job, grid, c->level >= 6 ? 2 : 1, s.st));      /* levels 6 and up: two-entry buckets (QAT 2.0 maps 1-5 / 6-8 / 9-12 to three search depths, reference README.md:133-148) */
     else CK(qzb_launch_deflate(&job, t.hash_bits, grid, warps, nbuf, s.st));
     CK(cudaEventRecord(s.ev_km, s.st));
     CK(qzb_launch_frame(&job, s.st));

@@ -302,12 +302,12 @@ __global__ void __launch_bounds__(QZL_WARPS * 32) qzb_lz4_window_kernel(QzbCompr
         const uint8_t *src = job.src + off;
         const uint32_t nsub = (wlen + QZL_SUB - 1) / QZL_SUB, npc = (wlen + 8191u) >> 13;
         const uint32_t p0 = wg * QZL_SUB, n = wlen > p0 ? min(QZL_SUB, wlen - p0) : 0u;
-        if (n) qzm_prepass(win, p0 + n, p0, p0 + n, table, tent, lane);
+        if (n) qzm_prepass<1>(win, p0 + n, p0, p0 + n, table, tent, lane);
         __syncthreads();
-        qzm_seed_tables(tables, tstride, nsub, tent, threadIdx.x, QZL_WARPS * 32);
+        qzm_seed_tables<1>(tables, tstride, nsub, tent, threadIdx.x, QZL_WARPS * 32);
         __syncthreads();
         QzmLz4Sink sink = { recs, 0 };
-        if (n) qzm_match_piece(win, wlen, p0, p0 + n, table, tent, sink, lane);
+        if (n) qzm_match_piece<1>(win, wlen, p0, p0 + n, table, tent, sink, lane);
         uint32_t my_last = 0;
         if (sink.nrec) { const uint32_t a = __ldcg(recs + 2 * (sink.nrec - 1)); my_last = (a & 0xffff) + (a >> 16); }
         if (lane == 0) { G.nrec[wg] = sink.nrec; G.last_end[wg] = my_last; }

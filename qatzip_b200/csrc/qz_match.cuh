@@ -36,13 +36,16 @@ __device__ __forceinline__ uint32_t qzm_ld32u(const uint32_t *w, uint32_t off) {
 /* a position inside a byte run (the byte before it and its four bytes are all equal) is not recorded in the tables */
 __device__ __forceinline__ bool qzm_run_interior(uint32_t v, uint32_t prevb, uint32_t p) { return p != 0 && v == prevb * 0x01010101u; }
 
-/* table[h] = last position in [p0, p1) with hash h (QZM_NONE elsewhere); `win` is the window's data (4-byte aligned, p0 a
- * multiple of 32), n its length */
+/* WAYS = 1: table[h] = last position in [p0, p1) with hash h (QZM_NONE elsewhere).  WAYS = 2 (the deeper search of the higher
+ * compression levels): the table is tent / 2 buckets of two entries, low half = the last position, high half = the one before.
+ * `win` is the window's data (4-byte aligned, p0 a multiple of 32), n its length */
+template <int WAYS>
 __device__ __forceinline__ void qzm_prepass(const uint8_t *win, uint32_t n, uint32_t p0, uint32_t p1, uint16_t *table, uint32_t tent, uint32_t lane)
 {
     for (uint32_t i = lane; i < (tent + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(table)[i] = 0xffffffffu;
     __syncwarp();
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(win);
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(table);
     const uint32_t sh = (lane & 3) * 8;
 #pragma unroll 4
     for (uint32_t base = p0; base < p1; base += 32) {
@@ -51,13 +54,22 @@ __device__ __forceinline__ void qzm_prepass(const uint8_t *win, uint32_t n, uint
         const uint32_t v = __funnelshift_r(pw[0], pw[1], sh);
         /* ascending tiles: a later position overwrites an earlier one.  Equal hashes inside one tile are a write/write race
          * the hardware settles for one of the lanes -- positions less than 32 bytes apart, either will do. */
-        if (p + 4 <= n && !qzm_run_interior(v, win[(int)p - 1], p)) table[qzm_hash(v, tent)] = (uint16_t)p;
+        const bool ins = p + 4 <= n && !qzm_run_interior(v, win[(int)p - 1], p);
+        if (WAYS == 1) { if (ins) table[qzm_hash(v, tent)] = (uint16_t)p; }
+        else {
+            const uint32_t h = qzm_hash(v, tent / 2);
+            const uint32_t w = ins ? t32[h] : 0u;
+            __syncwarp();
+            if (ins) t32[h] = (w << 16) | p;
+            __syncwarp();
+        }
     }
     __syncwarp();
 }
 
-/* tables[k] (k < npieces, `stride` u16 apart) <- the most recent position of every hash in pieces 0..k-1.  Called by all
+/* tables[k] (k < npieces, `stride` u16 apart) <- the most recent position(s) of every hash in pieces 0..k-1.  Called by all
  * `nthreads` threads of the group between two group barriers; tables hold the prepass result on entry. */
+template <int WAYS>
 __device__ __forceinline__ void qzm_seed_tables(uint16_t *tables, uint32_t stride, uint32_t npieces, uint32_t tent, uint32_t tid, uint32_t nthreads)
 {
     const uint32_t nw = (tent + 1) / 2, sw = stride / 2;
@@ -67,9 +79,15 @@ __device__ __forceinline__ void qzm_seed_tables(uint16_t *tables, uint32_t strid
         for (uint32_t k = 0; k < npieces; k++) {
             const uint32_t w = t32[k * sw + i];
             t32[k * sw + i] = carry;
-            const uint32_t lo = (w & 0xffffu) != 0xffffu ? w & 0xffffu : carry & 0xffffu;
-            const uint32_t hi = (w >> 16) != 0xffffu ? w & 0xffff0000u : carry & 0xffff0000u;
-            carry = lo | hi;
+            if (WAYS == 1) {
+                /* two independent entries per word */
+                const uint32_t lo = (w & 0xffffu) != 0xffffu ? w & 0xffffu : carry & 0xffffu;
+                const uint32_t hi = (w >> 16) != 0xffffu ? w & 0xffff0000u : carry & 0xffff0000u;
+                carry = lo | hi;
+            } else {
+                /* one bucket per word: the piece's two most recent positions, filled up from what was carried */
+                if ((w & 0xffffu) != 0xffffu) carry = (w >> 16) != 0xffffu ? w : (carry << 16) | (w & 0xffffu);
+            }
         }
     }
 }
@@ -113,10 +131,11 @@ struct QzmLz4Sink {
 /* Greedy LZ77 parse of [p0, p1) of the window `win` (n bytes of data, pads as above).  `table` is seeded (or cleared, for a
  * private window); p0 is a multiple of 32.  LZ4 sinks: matches start at or before n - 12 and end at or before n - 5
  * (block end rules), and never inside the last piece's tail. */
-template <class Sink>
+template <int WAYS, class Sink>
 __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, uint32_t p0, uint32_t p1, uint16_t *table, uint32_t tent, Sink &sink, uint32_t lane)
 {
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(win);
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(table);
     const uint32_t sh = (lane & 3) * 8, lt = qz_lanemask_lt();
     const uint32_t mstart_lim = Sink::kLz4 ? (n >= 13 ? n - 12 : 0u) : n;        /* LZ4: last position a match may start at */
     const uint32_t mend = Sink::kLz4 ? min(p1, n >= 5 ? n - 5 : 0u) : p1;         /* matches end at or before */
@@ -130,24 +149,52 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         const uint32_t prevb = win[(int)p - 1];
         const bool can = p < p1 && p + 4 <= n;
         const bool interior = qzm_run_interior(v, prevb, p);
-        const uint32_t h = qzm_hash(v, tent);
-        const uint32_t t = can ? table[h] : QZM_NONE;
-        __syncwarp();
-        if (can && !interior) table[h] = (uint16_t)p;       /* equal hashes inside the tile: see qzm_prepass */
-        __syncwarp();
+        uint32_t t, t2 = QZM_NONE;
+        if (WAYS == 1) {
+            const uint32_t h = qzm_hash(v, tent);
+            t = can ? table[h] : QZM_NONE;
+            __syncwarp();
+            if (can && !interior) table[h] = (uint16_t)p;       /* equal hashes inside the tile: see qzm_prepass */
+            __syncwarp();
+        } else {
+            const uint32_t h = qzm_hash(v, tent / 2);
+            const uint32_t w = can ? t32[h] : 0xffffffffu;
+            __syncwarp();
+            if (can && !interior) t32[h] = (w << 16) | p;
+            __syncwarp();
+            t = w & 0xffffu; t2 = w >> 16;
+        }
         /* inside a byte run the candidate is the position before (distance 1); everywhere else the table's */
-        const uint32_t cand = interior ? p - 1 : t;
+        const uint32_t cand1 = interior ? p - 1 : t;
         /* candidate bytes are fetched unconditionally (position 0 when there is none): no divergent verify branches */
-        const bool has = can && cand != QZM_NONE && p - cand <= Sink::kMaxDist && p <= mstart_lim;
-        const uint32_t c = has ? cand : 0u, csh = (c & 3) * 8;
-        const uint32_t *cw = ww + (c >> 2);
-        const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
-        const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
-        const uint32_t xx = x1 ? x1 : x2;
-        uint32_t L = (x1 ? 4u : 8u) + (xx ? (uint32_t)(__ffs(xx) - 1) >> 3 : 4u);     /* 4..12 = QZM_LANE_CAP */
+        const bool has1 = can && cand1 != QZM_NONE && p - cand1 <= Sink::kMaxDist && p <= mstart_lim;
+        uint32_t cand = cand1, L;
+        bool has = has1;
+        {
+            const uint32_t c = has1 ? cand1 : 0u, csh = (c & 3) * 8;
+            const uint32_t *cw = ww + (c >> 2);
+            const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
+            const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
+            const uint32_t xx = x1 ? x1 : x2;
+            L = (x1 ? 4u : 8u) + (xx ? (uint32_t)(__ffs(xx) - 1) >> 3 : 4u);     /* 4..12 = QZM_LANE_CAP */
+            if (!has1 || x0) L = 0;
+        }
+        if (WAYS == 2) {
+            /* the bucket's older entry: taken when it verifies longer (both reach the cap: the nearer one stays) */
+            const bool has2 = can && !interior && t2 != QZM_NONE && p - t2 <= Sink::kMaxDist && p <= mstart_lim;
+            const uint32_t c = has2 ? t2 : 0u, csh = (c & 3) * 8;
+            const uint32_t *cw = ww + (c >> 2);
+            const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
+            const uint32_t x0 = __funnelshift_r(c0, c1, csh) ^ v, x1 = __funnelshift_r(c1, c2, csh) ^ v1, x2 = __funnelshift_r(c2, c3, csh) ^ v2;
+            const uint32_t xx = x1 ? x1 : x2;
+            uint32_t L2 = (x1 ? 4u : 8u) + (xx ? (uint32_t)(__ffs(xx) - 1) >> 3 : 4u);
+            if (!has2 || x0) L2 = 0;
+            if (L2 > L) { L = L2; cand = t2; has = true; }
+        }
+        const uint32_t c = has ? cand : 0u;
         const uint32_t room = mend > p ? mend - p : 0u;          /* bytes a match starting here may cover */
         L = min(L, min(Sink::kMaxMatch, room));
-        if (!has || x0 || L < Sink::kMinMatch) L = 0;
+        if (L < Sink::kMinMatch) L = 0;
         /* the byte in front of position and candidate agrees (and the candidate is not the window's first byte) */
         const bool back = L != 0 && c != 0 && prevb == win[(int)c - 1];
 

@@ -77,7 +77,7 @@ extern "C" long emu_frame(const QzbCompressJob *jobp, uint32_t *chunk_cksum_out)
 /* One batch through the deflate kernels.  Geometry is the caller's.  Returns bytes produced, -1 for an unsupported geometry,
  * -2 when a kernel wrote past its scratch.
  * window == 0: per-piece kernel (piece size, hash bits, warps and piece buffers per CTA, CTAs);
- * window != 0: window kernel (one deflate block per 64 KiB window): CTAs of 32 warps, tables of `hb` entries each when
+ * window != 0: window kernel (one deflate block per 64 KiB window; window == 2: two-entry hash buckets): CTAs of 32 warps, tables of `hb` entries each when
  *              hb >= 256, else 2^hb (warps and nbuf are ignored). */
 extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, uint32_t chunk_sz, int last, int static_huffman,
                                      int piece_log2, int hb, int warps, int nbuf, int grid, uint8_t *dst, uint64_t cap, uint32_t *chunk_cksum_out, int window)
@@ -96,7 +96,8 @@ extern "C" long emu_deflate_compress(int fmt, const uint8_t *src, uint64_t len, 
         if (smem > 227 * 1024) return -1;
         b.tok.assign((size_t)grid * QZW_MATCHERS * QZW_TOK_WORDS, 0xEEEEEEEEu);
         job.tok_scratch = b.tok.data();
-        emu::launch((unsigned)grid, QZW_WARPS * 32, smem, [&] { qzb_deflate_window_kernel(job); });
+        if (window == 2) emu::launch((unsigned)grid, QZW_WARPS * 32, smem, [&] { qzb_deflate_window_kernel<2>(job); });
+        else emu::launch((unsigned)grid, QZW_WARPS * 32, smem, [&] { qzb_deflate_window_kernel<1>(job); });
         const long n = emu_frame(&job, chunk_cksum_out);
         return emu_canaries_ok(b) ? n : -2;
     }

@@ -443,3 +443,15 @@ def test_lz4_window_larger_chunks_and_ratio(emu, port):
         ours, _ = emu.lz4_window(d)
         ref = sum(len(port.compress(d[i:i + 65536], E.FMT_LZ4)) for i in range(0, len(d), 65536))
         assert len(ours) <= 1.05 * ref, (name, len(ours), ref)
+
+
+def test_window_deeper_search_for_higher_levels(emu, port):
+    """compression levels 6 and up look at two entries per hash bucket (window=2): same decoder, smaller output on text"""
+    text = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_sample.txt"), "rb").read()
+    for data in (text, sil(300000), rle(100000), noise(70000), b"x" * 5, sil(65536 + 77)):
+        one, _ = emu.deflate(data, E.FMT_GZIP_EXT, grid=2, window=1, hb=2584)
+        two, cks = emu.deflate(data, E.FMT_GZIP_EXT, grid=2, window=2, hb=2584)
+        assert port.decompress(two, E.FMT_GZIP_EXT, len(data) + 16) == data
+        assert cks == [zlib.crc32(data[i:i + 65536]) for i in range(0, len(data), 65536)]
+        if data is text:
+            assert len(two) < len(one)

@@ -150,6 +150,21 @@ def test_ratio_within_5_percent_of_reference(prod, ref, corpus):
         assert ours <= theirs * 1.05, name
 
 
+def test_compression_levels(prod, ref):
+    """comp_lvl is honoured the way QAT 2.0 does it (reference README.md:133-148: levels 1-5, 6-8 and 9-12 are three search depths):
+    levels 6 and up search two entries per hash bucket.  Every level decodes with the reference; on text the deeper search
+    is smaller."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    d = open(os.path.join(here, "golden", "text_sample.txt"), "rb").read()
+    sizes = {}
+    for lvl in (1, 5, 6, 9):
+        blob = prod.compress(d, fmt=q.QZ_DEFLATE_GZIP_EXT, level=lvl)
+        assert ref.decompress(blob, len(d) + 8, fmt=q.QZ_DEFLATE_GZIP_EXT) == d
+        sizes[lvl] = len(blob)
+    print("levels", sizes)
+    assert sizes[1] == sizes[5] and sizes[6] == sizes[9] and sizes[6] < sizes[1]
+
+
 def test_lz4_ratio_within_5_percent_of_reference(prod, ref, corpus):
     """LZ4 at the same granularity as the hardware path: one frame with one 64 KiB block per chunk (reference session:
     lz4BlockMaxSize = 64 KiB, src/qatzip_utils.c:292-298), against the reference's LZ4F per 64 KiB chunk: <= 1.05"""
