@@ -474,15 +474,15 @@ __device__ __forceinline__ uint32_t slot_hist(uint32_t *hist, const uint16_t *sl
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (i0 + k < nslots) {
+                /* one path for the three slot kinds (no divergence): symbol index and extra-bit count by selects */
                 const uint32_t s = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                if (s & QZ_SLOT_DIST) {
-                    uint32_t ds, de, dv;
-                    qz_dist_code((s & 0x7fffu) + 1, &ds, &de, &dv);
-                    atomicAdd(&hist[QZ_DOFF + ds], 1u); extra += de;
-                } else if (s & QZ_SLOT_LEN) {
-                    const uint32_t le = s_lentab[s & 0xff];
-                    atomicAdd(&hist[257 + (le & 31)], 1u); extra += (le >> 5) & 7;
-                } else atomicAdd(&hist[s], 1u);
+                const bool isD = (s & QZ_SLOT_DIST) != 0, isL = !isD && (s & QZ_SLOT_LEN) != 0;
+                const uint32_t x = s & 0x7fffu;                 /* distance - 1 */
+                const uint32_t lg = 31 - __clz((int)(x | 1u));
+                const uint32_t de = x < 4 ? 0u : lg - 1, ds = x < 4 ? x : 2 * lg + ((x >> de) & 1);
+                const uint32_t le = s_lentab[s & 0xff];
+                atomicAdd(&hist[isD ? QZ_DOFF + ds : isL ? 257 + (le & 31) : s], 1u);
+                extra += isD ? de : isL ? (le >> 5) & 7 : 0u;
             }
         }
     }

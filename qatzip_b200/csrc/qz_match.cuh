@@ -22,6 +22,7 @@
 #ifndef QZ_MATCH_CUH
 #define QZ_MATCH_CUH
 #include <stdint.h>
+#include <type_traits>
 #include "qz_warp.cuh"
 
 #define QZM_FULL 0xffffffffu
@@ -140,14 +141,16 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
     const uint32_t mstart_lim = Sink::kLz4 ? (n >= 13 ? n - 12 : 0u) : n;        /* LZ4: last position a match may start at */
     const uint32_t mend = Sink::kLz4 ? min(p1, n >= 5 ? n - 5 : 0u) : p1;         /* matches end at or before */
     uint32_t entry = 0;                 /* first position of the tile not covered by a match running in from the left */
-    for (uint32_t base = p0; base < p1; base += 32) {
-        if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
+    /* One tile.  EDGE = false is the copy for tiles well inside the sub-piece, where every bounds test is known to pass:
+     * all 32 positions exist and have four bytes, a 12-byte match fits, (LZ4) matches may start. */
+    auto tile = [&](const uint32_t base, auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
         const uint32_t p = base + lane;
         const uint32_t *pw = ww + (p >> 2);
         const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2], w3 = pw[3];
         const uint32_t v = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
         const uint32_t prevb = win[(int)p - 1];
-        const bool can = p < p1 && p + 4 <= n;
+        const bool can = EDGE ? (p < p1 && p + 4 <= n) : true;
         const bool interior = qzm_run_interior(v, prevb, p);
         uint32_t t, t2 = QZM_NONE;
         if (WAYS == 1) {
@@ -167,7 +170,7 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         /* inside a byte run the candidate is the position before (distance 1); everywhere else the table's */
         const uint32_t cand1 = interior ? p - 1 : t;
         /* candidate bytes are fetched unconditionally (position 0 when there is none): no divergent verify branches */
-        const bool has1 = can && cand1 != QZM_NONE && p - cand1 <= Sink::kMaxDist && p <= mstart_lim;
+        const bool has1 = can && cand1 != QZM_NONE && p - cand1 <= Sink::kMaxDist && (!EDGE || p <= mstart_lim);
         uint32_t cand = cand1, L;
         bool has = has1;
         {
@@ -181,7 +184,7 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         }
         if (WAYS == 2) {
             /* the bucket's older entry: taken when it verifies longer (both reach the cap: the nearer one stays) */
-            const bool has2 = can && !interior && t2 != QZM_NONE && p - t2 <= Sink::kMaxDist && p <= mstart_lim;
+            const bool has2 = can && !interior && t2 != QZM_NONE && p - t2 <= Sink::kMaxDist && (!EDGE || p <= mstart_lim);
             const uint32_t c = has2 ? t2 : 0u, csh = (c & 3) * 8;
             const uint32_t *cw = ww + (c >> 2);
             const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2], c3 = cw[3];
@@ -192,8 +195,8 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
             if (L2 > L) { L = L2; cand = t2; has = true; }
         }
         const uint32_t c = has ? cand : 0u;
-        const uint32_t room = mend > p ? mend - p : 0u;          /* bytes a match starting here may cover */
-        L = min(L, min(Sink::kMaxMatch, room));
+        const uint32_t room = EDGE ? (mend > p ? mend - p : 0u) : 0xffffu;          /* bytes a match starting here may cover */
+        if (EDGE) L = min(L, min(Sink::kMaxMatch, room));
         if (L < Sink::kMinMatch) L = 0;
         /* the byte in front of position and candidate agrees (and the candidate is not the window's first byte) */
         const bool back = L != 0 && c != 0 && prevb == win[(int)c - 1];
@@ -204,7 +207,7 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         uint32_t R = 1u << lane, N = E < 32 ? E : lane;
 #pragma unroll
         for (int r = 0; r < 5; r++) { R |= __shfl_sync(QZM_FULL, R, N); N = __shfl_sync(QZM_FULL, N, N); }
-        const uint32_t longmask = __ballot_sync(QZM_FULL, L >= QZM_LANE_CAP && L < min(Sink::kMaxMatch, room));
+        const uint32_t longmask = __ballot_sync(QZM_FULL, L >= QZM_LANE_CAP && (!EDGE || L < min(Sink::kMaxMatch, room)));
         uint32_t tokmask = 0, cur = entry, leave;
         for (;;) {
             const uint32_t Rc = __shfl_sync(QZM_FULL, R, cur);
@@ -228,7 +231,7 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
             cur = m + Lm;
             if (cur >= 32) { leave = cur; break; }
         }
-        tokmask &= __ballot_sync(QZM_FULL, p < p1);
+        if (EDGE) tokmask &= __ballot_sync(QZM_FULL, p < p1);
         uint32_t matchmask = tokmask & __ballot_sync(QZM_FULL, L != 0);
         /* a selected match takes over the literal right in front of it when that byte agrees too */
         {
@@ -238,6 +241,11 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
             sink.put(tokmask, matchmask, lane, lt, p - (ext ? 1u : 0u), v, L + (ext ? 1u : 0u), p - cand);
         }
         entry = leave - 32;
+    };
+    for (uint32_t base = p0; base < p1; base += 32) {
+        if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
+        if (base + 32 + QZM_LANE_CAP <= mend && base + 35 <= n && base + 31 <= mstart_lim) tile(base, std::false_type());
+        else tile(base, std::true_type());
     }
     __syncwarp();
 }

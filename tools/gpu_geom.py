@@ -8,7 +8,7 @@ h = L.qzMalloc(n, 0, q.PINNED_MEM); q.Corpus().fill(q.Corpus.SILESIA_LIKE, h, n,
 cap = L.qzMaxCompressedLength(n, None)
 d_in, d_out = L.qzb200DeviceAlloc(n), L.qzb200DeviceAlloc(cap)
 assert L.qzb200CopyToDevice(d_in, h, n) == 0
-sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=1, hw_buff_sz=65536)
+sess = prod.new_session(fmt=q.QZ_DEFLATE_GZIP_EXT, level=int(os.environ.get("GEOM_LEVEL", "1")), hw_buff_sz=65536)
 ms = []
 for it in range(6):
     rc, used, made, _ = prod.compress_device(sess, d_in, n, d_out, cap, 1)
