@@ -362,6 +362,31 @@ def test_device_resident_entry_points(prod, port, data, fmt):
     prod.end_session(sess)
 
 
+@pytest.mark.parametrize("fmt", [q.QZ_DEFLATE_GZIP_EXT, q.FMT_LZ4])
+def test_device_resident_unaligned_source(prod, port, data, fmt):
+    """the window kernels copy a window in by one TMA bulk copy when its address is 16-byte aligned; any other source (here:
+    device pointer + 3, ragged length) is copied by hand.  Same stream either way."""
+    L = prod.lib
+    n = (2 << 20) + 4321
+    d = data[:n]
+    sess = prod.new_session(fmt=fmt)
+    cap = n + n // 4 + 65536
+    d_in, d_out = L.qzb200DeviceAlloc(n + 16), L.qzb200DeviceAlloc(cap)
+    assert d_in and d_out
+    blobs = []
+    for skew in (0, 3):
+        assert L.qzb200CopyToDevice(d_in + skew, d, n) == 0
+        rc, used, made, crc = prod.compress_device(sess, d_in + skew, n, d_out, cap)
+        assert rc == q.QZ_OK and used == n
+        blob = bytearray(made)
+        assert L.qzb200CopyToHost(q._addr(blob), d_out, made) == 0
+        assert port.decompress(bytes(blob), fmt, n + 8) == d
+        blobs.append(bytes(blob))
+    assert blobs[0] == blobs[1]
+    L.qzb200DeviceFree(d_in); L.qzb200DeviceFree(d_out)
+    prod.end_session(sess)
+
+
 def test_large_roundtrip_properties(prod, corpus):
     """256 MiB per call (BASELINE-size pieces): GPU compress -> GPU decompress identity and CRC of CRCs."""
     L = prod.lib
