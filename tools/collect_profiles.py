@@ -6,7 +6,7 @@ G, P = "gpurun_out", "profiles"
 def cp(src, dst):
     if os.path.exists(os.path.join(G, src)): shutil.copy(os.path.join(G, src), os.path.join(P, dst)); print("copied", dst)
 cp("bench.json", f"{tag}_bench.json"); cp("bench_ref.json", f"{tag}_bench_ref.json"); cp("launches.csv", f"{tag}_launches_bench.csv")
-cp("extra.json", f"{tag}_extra.json"); cp("inflate_bench.json", f"{tag}_inflate_bench.json"); cp("geom.jsonl", f"{tag}_geometry_sweep.jsonl"); cp("geom41.jsonl", f"{tag}_group_ab.jsonl"); cp("pcie_duplex.json", f"{tag}_pcie_duplex.json"); cp("timeline.log", f"{tag}_e2e_timeline.log")
+cp("extra.json", f"{tag}_extra.json"); cp("pcie_duplex.json", f"{tag}_pcie_duplex.json")
 cp("pytest_gpu.log", f"{tag}_pytest_gpu.log"); cp("phases_window.json", f"{tag}_phases_window_kernel.json")
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max",
