@@ -272,6 +272,21 @@ def stream_leg(prod, ref_lib, cor, peak, ncores):
            "e2e": {"value": round(n / secs / GB, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(outb),
                    "api": "qzCompressStream(host memory in, host memory out): the value IS the end-to-end number"},
            "roofline": None}
+    if hasattr(drv, "qzdrive_copy_ceiling"):
+        # the same loop with no compressor behind it: 4 KiB copies into a pinned staging buffer, the compressed share copied out
+        drv.qzdrive_copy_ceiling.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.POINTER(C.c_double)]
+        cap = 8 << 20
+        s_in, s_out = L.qzMalloc(cap, 0, q.PINNED_MEM), L.qzMalloc(cap, 0, q.PINNED_MEM)
+        obuf = (C.c_ubyte * cap)()
+        cs = C.c_double(0)
+        best = None
+        for _ in range(3):
+            drv.qzdrive_copy_ceiling(h_in, n, 4096, s_in, s_out, cap, int(cap * outb / n), obuf, C.byref(cs))
+            best = cs.value if best is None else min(best, cs.value)
+        L.qzFree(s_in); L.qzFree(s_out)
+        out["host_copy_ceiling"] = {"value": round(n / best / GB, 3), "unit": "GB/s",
+                                    "what": "the submission loop with memcpy only (4 KiB in to pinned staging, compressed share out), one thread: bounds any stream API here"}
+        out["frac_of_host_copy_ceiling"] = round(out["value"] / out["host_copy_ceiling"]["value"], 3)
     if ref_lib:
         ref = q.QzLib(ref_lib)
         sample = min(n, 64 << 20)

@@ -41,3 +41,26 @@ int qzdrive_stream(void *fn_, void *end_, QzSession_T *sess, const unsigned char
     end(sess, &st);
     return rc;
 }
+
+/* What the submission loop above costs with no compressor behind it: every in_step bytes are copied into a staging buffer
+ * (the caller may reuse its own buffer after the call, so a stream API has to), and for every full staging buffer
+ * out_per_stage bytes are copied out of a second one into out.  One thread, like the loop above; the seconds this takes
+ * bound what any qzCompressStream can reach on this host. */
+#include <string.h>
+int qzdrive_copy_ceiling(const unsigned char *src, size_t n, unsigned in_step, unsigned char *stage_in, unsigned char *stage_out,
+                         unsigned stage_cap, unsigned out_per_stage, unsigned char *out, double *seconds)
+{
+    size_t consumed = 0; unsigned fill = 0;
+    if (out_per_stage > stage_cap) return -1;
+    const double t0 = now_s();
+    while (consumed < n) {
+        const size_t left = n - consumed;
+        unsigned step = left < in_step ? (unsigned)left : in_step;
+        if (step > stage_cap - fill) step = stage_cap - fill;
+        memcpy(stage_in + fill, src + consumed, step);
+        consumed += step; fill += step;
+        if (fill == stage_cap) { memcpy(out, stage_out, out_per_stage); fill = 0; }
+    }
+    *seconds = now_s() - t0;
+    return 0;
+}

@@ -18,10 +18,12 @@
 #include <condition_variable>
 #include <deque>
 #include <thread>
+#include <vector>
 #include "../../include/qatzip.h"
 #include "../../include/qatzip_b200.h"
 #include <atomic>
 #include "qz_engine.h"
+#include "qz_crc32.h"
 
 #define QZB_NUM_BUFF 32                 /* reference src/qatzip_internal.h:65 (req_cnt_thrshold ceiling) */
 #define QZB_FMT_INTERNAL_LZ4 4          /* internal data_fmt value for LZ4 frames (QzbFormat) */
@@ -343,11 +345,13 @@ extern "C" int qzTeardownSession(QzSession_T *sess)
     }
     return QZ_OK;
 }
+static void stream_pool_release();
 extern "C" int qzClose(QzSession_T *sess)
 {
     if (!sess) return QZ_PARAMS;
     /* the device context is process-wide and released at unload; what qzClose undoes is qzInit, so that a later qzInit
      * answers QZ_OK again like the reference's (src/qatzip.c:1084-1116 stops the service qzInit started) */
+    stream_pool_release();
     std::lock_guard<std::mutex> g(g_lock);
     g_init_done = 0; g_init_rc = QZ_NONE;
     return QZ_OK;
@@ -567,21 +571,27 @@ extern "C" void qzFree(void *m)
 extern "C" int qzMemFindAddr(unsigned char *a) { return a ? qzb_pinned_contains(a, 1) : 0; }
 
 /* ------------------------------------------------------------------ stream API (reference src/qatzip_stream.c) */
-/* Compress streams are double-buffered: while the caller fills one staging buffer, a worker thread of the stream has the
- * engine compress the other one (reference: one synchronous request per full buffer, src/qatzip_stream.c:514-560). */
+/* Compress streams are buffered three deep: while the caller fills one staging buffer, two worker threads of the stream
+ * (each with an engine of its own, so their copies and kernels overlap) compress the two before it (reference: one synchronous
+ * request per full buffer, src/qatzip_stream.c:514-560).  Jobs finish in any order and are taken over in stream order; each
+ * job's CRC-32 is of its own bytes and is joined to the stream's by crc32_combine (the reference does the same per request,
+ * src/qatzip.c:1707-1714). */
+#define QZB_STREAM_WORKERS 2
 struct QzbStreamJob {
     unsigned char *in = nullptr, *out = nullptr;     /* staging input (pinned), its compressed form */
-    unsigned int in_cap = 0, out_cap = 0, in_len = 0, out_len = 0, last = 0;
-    int rc = QZ_OK;
+    unsigned int in_cap = 0, out_cap = 0, in_len = 0, out_len = 0, last = 0, crc = 0;
+    int rc = QZ_OK;                                  /* 1 = queued or running */
+    int worker = 0;
 };
 struct QzbStreamWorker {
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
-    QzSession_T *sess = nullptr;
+    QzbSess *s = nullptr;
+    QzbEngine *engine = nullptr;           /* worker 0: the session's; the others: their own, on the same device */
+    bool own_engine = false;
     QzbStreamJob *job = nullptr;           /* queued or running; nullptr = idle */
     bool running = false, quit = false;
-    unsigned long crc = 0;                 /* running CRC of the stream, carried from job to job */
 };
 struct QzbStreamBuf {
     unsigned char *in_buf, *out_buf;
@@ -590,11 +600,67 @@ struct QzbStreamBuf {
     unsigned int flush_more;
     unsigned int finished;                 /* a call with last==1 has already been coded */
     unsigned int batched;                  /* compress: staging buffer already sized for batched engine calls */
-    /* compress, asynchronous mode (entered when the first staging buffer has filled once) */
-    QzbStreamWorker *worker;
-    QzbStreamJob *flight;                  /* the job the worker has (its output is taken over when it is done) */
-    QzbStreamJob *spare;                   /* buffers of the job before, reused for the next one */
+    /* compress, asynchronous mode */
+    QzbStreamWorker *worker[QZB_STREAM_WORKERS];
+    QzbStreamJob *flight[QZB_STREAM_WORKERS];      /* jobs with the workers, oldest first */
+    unsigned int nflight, last_queued, any_taken;
+    QzbStreamJob *spare;                   /* buffers of a finished job, reused for the next one */
 };
+/* What a stream sets up beyond its session -- the second worker's engine and the pinned staging buffers -- costs more than
+ * compressing a gigabyte does, so qzEndStream parks them here for the next stream of the process (the reference sizes its
+ * pinned pools once, in qzSetupSession: src/qatzip.c:1318-1400).  qzClose releases them. */
+static std::mutex g_stream_pool_lock;
+static std::vector<QzbEngine *> g_stream_engines;
+struct QzbParkedBuf { unsigned char *p; unsigned int cap; };
+static std::vector<QzbParkedBuf> g_stream_bufs;
+static const size_t QZB_STREAM_POOL_BUFS = 12, QZB_STREAM_POOL_ENGINES = 4;
+static QzbEngine *stream_engine_get(int device)
+{
+    {
+        std::lock_guard<std::mutex> g(g_stream_pool_lock);
+        for (size_t i = 0; i < g_stream_engines.size(); i++)
+            if (qzb_engine_primary_device(g_stream_engines[i]) == device) {
+                QzbEngine *e = g_stream_engines[i]; g_stream_engines.erase(g_stream_engines.begin() + (long)i); return e;
+            }
+    }
+    return qzb_engine_create(device);
+}
+static void stream_engine_put(QzbEngine *e)
+{
+    {
+        std::lock_guard<std::mutex> g(g_stream_pool_lock);
+        if (g_stream_engines.size() < QZB_STREAM_POOL_ENGINES) { g_stream_engines.push_back(e); return; }
+    }
+    qzb_engine_destroy(e);
+}
+static unsigned char *stream_buf_get(unsigned int want, unsigned int *cap, bool exact = false)
+{
+    {
+        std::lock_guard<std::mutex> g(g_stream_pool_lock);
+        for (size_t i = 0; i < g_stream_bufs.size(); i++)
+            if (exact ? g_stream_bufs[i].cap == want : (g_stream_bufs[i].cap >= want && g_stream_bufs[i].cap / 2 <= want)) {
+                QzbParkedBuf b = g_stream_bufs[i]; g_stream_bufs.erase(g_stream_bufs.begin() + (long)i); *cap = b.cap; return b.p;
+            }
+    }
+    *cap = want;
+    return (unsigned char *)qzMalloc(want, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+}
+static void stream_buf_put(unsigned char *p, unsigned int cap)
+{
+    if (!p) return;
+    if (cap >= (1u << 20) && qzb_pinned_contains(p, cap)) {
+        std::lock_guard<std::mutex> g(g_stream_pool_lock);
+        if (g_stream_bufs.size() < QZB_STREAM_POOL_BUFS) { g_stream_bufs.push_back({p, cap}); return; }
+    }
+    qzFree(p);
+}
+static void stream_pool_release()
+{
+    std::vector<QzbEngine *> es; std::vector<QzbParkedBuf> bs;
+    { std::lock_guard<std::mutex> g(g_stream_pool_lock); es.swap(g_stream_engines); bs.swap(g_stream_bufs); }
+    for (QzbEngine *e : es) qzb_engine_destroy(e);
+    for (QzbParkedBuf &b : bs) qzFree(b.p);
+}
 static void stream_worker_main(QzbStreamWorker *w)
 {
     std::unique_lock<std::mutex> lk(w->mu);
@@ -604,17 +670,22 @@ static void stream_worker_main(QzbStreamWorker *w)
         QzbStreamJob *j = w->job;
         w->running = true;
         lk.unlock();
-        unsigned int in_len = j->in_len, out_len = j->out_cap;
-        unsigned long crc = w->crc;
-        int rc = qzCompressCrc(w->sess, j->in, &in_len, j->out, &out_len, j->last, &crc);
-        if (rc == QZ_OK && in_len != j->in_len) rc = QZ_FAIL;
+        QzbCompressCall c; QzbCompressOut o;
+        memset(&c, 0, sizeof c);
+        c.fmt = w->s->p.data_fmt; c.level = (int)w->s->p.comp_lvl; c.static_huffman = (w->s->p.huffman_hdr == QZ_STATIC_HDR);
+        c.last = (int)j->last; c.chunk_sz = w->s->p.hw_buff_sz;
+        c.src = j->in; c.src_len = j->in_len; c.dst = j->out; c.dst_cap = j->out_cap;
+        c.src_pinned = qzb_pinned_contains(j->in, j->in_len); c.dst_pinned = qzb_pinned_contains(j->out, j->out_cap);
+        c.want_crc = 1; c.crc_in = 0;
+        int rc = qzb_engine_compress(w->engine, &c, &o);
+        if (rc == QZ_OK && o.consumed != j->in_len) rc = QZ_FAIL;
         lk.lock();
-        w->crc = crc; j->out_len = out_len; j->rc = rc == QZ_OK ? QZ_OK : QZ_FAIL;
+        j->out_len = (unsigned int)o.produced; j->crc = o.crc; j->rc = rc == QZ_OK ? QZ_OK : QZ_FAIL;
         w->running = false;
         w->cv.notify_all();
     }
 }
-static void stream_job_free(QzbStreamJob *j) { if (j) { qzFree(j->in); qzFree(j->out); delete j; } }
+static void stream_job_free(QzbStreamJob *j) { if (j) { stream_buf_put(j->in, j->in_cap); stream_buf_put(j->out, j->out_cap); delete j; } }
 static int stream_init(QzSession_T *sess, QzStream_T *strm, QzbSess **sp)
 {
     int rc = ready_session(sess, sp);
@@ -666,8 +737,8 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
     unsigned int consumed = 0, produced = 0; int rc = QZ_OK;
     /* The reference submits one synchronous engine request per full strm_buff_sz buffer (src/qatzip_stream.c:514-560).
      * A GPU launch costs about what 20 MiB of compression costs, so the staging buffer here is QZB200_STREAM_BATCH_KB
-     * (default 8 MiB, a whole number of chunks) of pinned memory, and there are two of them: while the caller fills one,
-     * the stream's worker thread has the engine compress the other.  The stream is still cut into hw_buff_sz chunks, the
+     * (default 8 MiB, a whole number of chunks) of pinned memory, and there are three of them: while the caller fills one,
+     * the stream's two worker threads have their engines compress the others.  The stream is still cut into hw_buff_sz chunks, the
      * bytes are the same; output appears in larger steps.  QZB200_STREAM_BATCH_KB=0: the reference's cadence, synchronous. */
     if (!b->batched) {
         b->batched = 1;
@@ -677,25 +748,38 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
         if (want > (64ull << 20)) want = 64ull << 20;
         want = (want + hw - 1) / hw * hw;
         if (want > b->in_cap && strm->pending_in == 0 && strm->pending_out == 0) {
-            unsigned char *ni = (unsigned char *)qzMalloc((size_t)want, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
-            if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = (unsigned int)want; b->in_off = 0; b->batched = 2; }
+            unsigned int got = 0;
+            unsigned char *ni = stream_buf_get((unsigned int)want, &got, true);     /* jobs are cut at the capacity: exactly this size */
+            if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = got; b->in_off = 0; b->batched = 2; }
         }
     }
     if (b->batched == 2) {
-        /* ---- double-buffered: at most one job with the worker while this thread stages the next ---- */
-        auto take_over = [&](bool wait) -> bool {        /* the finished job's output becomes the pending output */
-            if (!b->flight || strm->pending_out) return false;
-            QzbStreamWorker *w = b->worker;
-            std::unique_lock<std::mutex> lk(w->mu);
-            if (!wait && (w->running || b->flight->rc == 1)) return false;
-            w->cv.wait(lk, [&] { return !w->running && b->flight->rc != 1; });
-            QzbStreamJob *j = b->flight;
-            w->job = nullptr; b->flight = nullptr;
+        static const unsigned int nworkers = [] {       /* QZB200_STREAM_WORKERS=1: one job in flight (A/B) */
+            const char *ev = getenv("QZB200_STREAM_WORKERS");
+            long v = ev && *ev ? strtol(ev, NULL, 10) : QZB_STREAM_WORKERS;
+            return (unsigned int)(v < 1 ? 1 : v > QZB_STREAM_WORKERS ? QZB_STREAM_WORKERS : v);
+        }();
+        /* ---- asynchronous: up to QZB_STREAM_WORKERS jobs with the workers while this thread stages the next ---- */
+        auto take_over = [&](bool wait) -> bool {        /* the oldest job's output becomes the pending output */
+            if (!b->nflight || strm->pending_out) return false;
+            QzbStreamJob *j = b->flight[0];
+            QzbStreamWorker *w = b->worker[j->worker];
+            {
+                std::unique_lock<std::mutex> lk(w->mu);
+                if (!wait && (w->running || j->rc == 1)) return false;
+                w->cv.wait(lk, [&] { return !w->running && j->rc != 1; });
+                w->job = nullptr;
+            }
+            for (unsigned int i = 1; i < b->nflight; i++) b->flight[i - 1] = b->flight[i];
+            b->nflight--;
             if (b->spare) stream_job_free(b->spare);
             b->spare = j;
             if (j->rc != QZ_OK) { rc = QZ_FAIL; return false; }
             std::swap(b->out_buf, j->out); std::swap(b->out_cap, j->out_cap);
-            strm->pending_out = j->out_len; b->out_off = 0; strm->crc_32 = (unsigned int)w->crc;
+            strm->pending_out = j->out_len; b->out_off = 0;
+            strm->crc_32 = b->any_taken ? qz_crc32_combine(strm->crc_32, j->crc, j->in_len) : j->crc;
+            b->any_taken = 1;
+            sess->total_in += j->in_len; sess->total_out += j->out_len;
             if (j->last) b->finished = 1;
             return true;
         };
@@ -705,41 +789,53 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
             if (rc != QZ_OK) break;
             if (strm->in) consumed += stream_copy_in(strm, b, strm->in + consumed);
             const bool input_done = (strm->in_sz == 0);
-            const bool want_last = last && input_done && !b->finished && !(b->flight && b->flight->last);
+            const bool want_last = last && input_done && !b->finished && !b->last_queued;
             if (strm->pending_in < b->in_cap && !want_last) {
                 /* nothing to submit: at the end of the stream wait for what is still in flight */
-                if (last && input_done && b->flight) { if (take_over(true)) continue; if (rc != QZ_OK) break; }
+                if (last && input_done && b->nflight) { if (take_over(true)) continue; if (rc != QZ_OK) break; }
                 break;
             }
-            /* the staged buffer goes to the worker: first the job before it must be done and its output taken over
-             * (if that output is still waiting for room in the caller's buffer, so does everything else) */
-            if (b->flight) { if (take_over(true)) continue; break; }
-            if (!b->worker) {
-                b->worker = new QzbStreamWorker();
-                b->worker->sess = sess; b->worker->crc = strm->crc_32;
-                b->worker->th = std::thread(stream_worker_main, b->worker);
+            /* the staged buffer goes to a worker: with all of them busy the oldest job must be done and its output taken over
+             * first (if that output is still waiting for room in the caller's buffer, so does everything else) */
+            if (b->nflight >= nworkers) { if (take_over(true)) continue; break; }
+            int wi = -1;
+            for (int i = 0; i < (int)nworkers && wi < 0; i++) {
+                bool busy = false;
+                for (unsigned int k = 0; k < b->nflight; k++) busy |= b->flight[k]->worker == i;
+                if (!busy) wi = i;
+            }
+            if (!b->worker[wi]) {
+                QzbStreamWorker *w = new QzbStreamWorker();
+                w->s = s;
+                if (wi == 0) w->engine = s->engine;
+                else { w->engine = stream_engine_get(qzb_engine_primary_device(s->engine)); w->own_engine = true; }
+                if (!w->engine) { delete w; rc = QZ_FAIL; break; }
+                w->th = std::thread(stream_worker_main, w);
+                b->worker[wi] = w;
             }
             QzbStreamJob *j = b->spare; b->spare = nullptr;
             const unsigned int need_out = qzMaxCompressedLength(b->in_cap, sess);
             if (!j) {
                 j = new QzbStreamJob();
-                j->in_cap = b->in_cap; j->in = (unsigned char *)qzMalloc(j->in_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
-                j->out_cap = need_out; j->out = (unsigned char *)qzMalloc(j->out_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+                j->in = stream_buf_get(b->in_cap, &j->in_cap, true);
+                j->out = stream_buf_get(need_out, &j->out_cap);
                 if (!j->in || !j->out) { stream_job_free(j); rc = QZ_FAIL; break; }
             }
             if (j->out_cap < need_out) {
-                qzFree(j->out); j->out_cap = need_out; j->out = (unsigned char *)qzMalloc(j->out_cap, QZ_AUTO_SELECT_NUMA_NODE, PINNED_MEM);
+                stream_buf_put(j->out, j->out_cap); j->out = stream_buf_get(need_out, &j->out_cap);
                 if (!j->out) { stream_job_free(j); rc = QZ_FAIL; break; }
             }
             std::swap(b->in_buf, j->in); std::swap(b->in_cap, j->in_cap);        /* the job's old input buffer is the next one to fill */
-            j->in_len = strm->pending_in; j->last = want_last ? 1u : 0u; j->out_len = 0;
+            j->in_len = strm->pending_in; j->last = want_last ? 1u : 0u; j->out_len = 0; j->worker = wi;
             strm->pending_in = 0; b->in_off = 0;
+            if (want_last) b->last_queued = 1;
             {
-                std::lock_guard<std::mutex> g(b->worker->mu);
+                std::lock_guard<std::mutex> g(b->worker[wi]->mu);
                 j->rc = 1;                                   /* queued */
-                b->worker->job = j; b->flight = j;
+                b->worker[wi]->job = j;
             }
-            b->worker->cv.notify_all();
+            b->flight[b->nflight++] = j;
+            b->worker[wi]->cv.notify_all();
             if (want_last) { if (take_over(true)) continue; break; }
             if (input_done) break;
         }
@@ -841,14 +937,20 @@ extern "C" int qzEndStream(QzSession_T *sess, QzStream_T *strm)
     if (!sess || !strm) return QZ_PARAMS;
     if (strm->opaque) {
         QzbStreamBuf *b = (QzbStreamBuf *)strm->opaque;
-        if (b->worker) {
-            { std::unique_lock<std::mutex> lk(b->worker->mu); b->worker->cv.wait(lk, [&] { return !b->worker->running && !(b->worker->job && b->worker->job->rc == 1); }); b->worker->quit = true; }
-            b->worker->cv.notify_all();
-            b->worker->th.join();
-            delete b->worker;
+        for (int i = 0; i < QZB_STREAM_WORKERS; i++) {
+            QzbStreamWorker *w = b->worker[i];
+            if (!w) continue;
+            { std::unique_lock<std::mutex> lk(w->mu); w->cv.wait(lk, [&] { return !w->running && !(w->job && w->job->rc == 1); }); w->quit = true; }
+            w->cv.notify_all();
+            w->th.join();
+            if (w->own_engine) stream_engine_put(w->engine);
+            delete w;
         }
-        stream_job_free(b->flight); stream_job_free(b->spare);
-        qzFree(b->in_buf); qzFree(b->out_buf); free(b);
+        for (unsigned int i = 0; i < b->nflight; i++) stream_job_free(b->flight[i]);
+        stream_job_free(b->spare);
+        if (b->batched == 2) { stream_buf_put(b->in_buf, b->in_cap); stream_buf_put(b->out_buf, b->out_cap); }
+        else { qzFree(b->in_buf); qzFree(b->out_buf); }
+        free(b);
         strm->opaque = NULL;
     }
     strm->pending_in = 0; strm->pending_out = 0; strm->in_sz = 0; strm->out_sz = 0;

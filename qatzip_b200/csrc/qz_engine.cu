@@ -290,6 +290,7 @@ extern "C" void qzb_engine_destroy(QzbEngine *e)
     delete e;
 }
 extern "C" int qzb_engine_device_count(const QzbEngine *e) { return e ? (int)e->devices.size() : 0; }
+extern "C" int qzb_engine_primary_device(const QzbEngine *e) { return e ? e->device : -1; }
 
 /* Whatever way an engine call ends, no slot is left with work in flight or marked busy: a later call on the session
  * would otherwise drain a stale batch into its own output (and copies into the caller's buffers would still be running). */

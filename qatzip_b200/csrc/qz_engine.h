@@ -23,6 +23,7 @@ int qzb_runtime_default_device(void);
 int qzb_runtime_device_list(int *out, int cap);
 QzbEngine *qzb_engine_create(int device);
 int qzb_engine_device_count(const QzbEngine *e);
+int qzb_engine_primary_device(const QzbEngine *e);
 void qzb_engine_destroy(QzbEngine *e);
 
 typedef struct QzbCompressCall {
