@@ -32,6 +32,7 @@ extern "C" cudaError_t qzb_launch_frame(const QzbCompressJob *job, cudaStream_t 
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, int grid, cudaStream_t st);
 extern "C" size_t qzb_inflate_smem_bytes(int dpw);
 extern "C" int qzb_inflate_cta_threads(int dpw);
+extern "C" int qzb_inflate_cta_slots(int dpw);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
@@ -109,7 +110,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
     t->inflate_dpw = env_int("QZB200_INFLATE_DPW", 1);      /* members decoded at once by one warp: 1 (measured fastest on B200), 2, 4 or 8 */
-    if (t->inflate_dpw != 2 && t->inflate_dpw != 4 && t->inflate_dpw != 8) t->inflate_dpw = 1;
+    if (t->inflate_dpw != 2 && t->inflate_dpw != 4 && t->inflate_dpw != 8 && t->inflate_dpw != 16 && t->inflate_dpw != 31) t->inflate_dpw = 1;
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
@@ -697,8 +698,8 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         job.nmembers = (uint32_t)count; job.fmt = c->fmt; job.ticket = ticket; job.size_only = size_only ? 1 : 0;
         if (ordered) job.order = (const uint32_t *)((const uint8_t *)s.d_members.p + order_off);
         const int dpw = e->tune.inflate_dpw;
-        const size_t slots_per_cta = lz4 ? 8 : (size_t)(qzb_inflate_cta_threads(dpw) / 32) * dpw;
-        const int ctas_per_sm = lz4 ? 8 : (int)std::max<size_t>(1, std::min<size_t>(2048 / qzb_inflate_cta_threads(dpw), (227 * 1024) / (qzb_inflate_smem_bytes(dpw) + 2048)));
+        const size_t slots_per_cta = lz4 ? 8 : (size_t)qzb_inflate_cta_slots(dpw);
+        const int ctas_per_sm = lz4 ? 8 : (int)std::max<size_t>(1, std::min<size_t>(2048 / qzb_inflate_cta_threads(dpw), (228 * 1024) / (qzb_inflate_smem_bytes(dpw) + 1024 + 1200)));
         const int grid = (int)std::min<size_t>((count + slots_per_cta - 1) / slots_per_cta, (size_t)e->sm_count * ctas_per_sm);
         CK(cudaEventRecord(s.ev_k0, s.st));
         if (lz4) CK(qzb_launch_lz4_decompress(&job, grid, s.st));

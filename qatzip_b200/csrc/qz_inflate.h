@@ -161,74 +161,118 @@ QZ_HD uint32_t qz_tok_byte(uint32_t t) { return (t >> 8) & 0xff; }
 QZ_HD uint32_t qz_tok_len(uint32_t t) { return ((t >> 16) & 0xff) + 3; }
 QZ_HD uint32_t qz_tok_dist(uint32_t t) { return (t & 0x7fff) + 1; }
 
+/* the 32 bits that start `sh` (0..31) bits into lo, continuing in hi: one SHF on the device */
+QZ_HD uint32_t qz_funnel(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31));
+#endif
+}
+
 /* Turn the next symbols of the current Huffman block into at most `max_tok` tokens WITHOUT touching
  * the output; *pos is the output position before the batch and is advanced by the bytes the tokens
  * stand for.  Returns QZI_MATCH (= 0: buffer full, more to come), QZI_END_BLOCK, or an error.
  * This loop is the serial heart of inflate (one lane per member runs it), so it is written for
- * instruction count: reader state in locals, one pointer for input words and one for tokens, the
- * literal case first and exits by goto. */
-QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
-                            uint32_t *pos, uint32_t cap)
+ * instruction count.  Inside it the reader is three consecutive input words (the third fetched one
+ * word ahead of need) and a bit offset into the first: a symbol's bits are one funnel shift away and
+ * consuming them is one add.  The output position is not stepped per literal: every token stands for
+ * at least one byte, so the batch is cut at the room left and the position follows from the token
+ * count plus what the matches added. */
+/* Token i is stored at tok[i * tstride + ((i + tskew) & tmask)]: (1, 0, 0) is a plain array; (32, lane, 31) is the layout
+ * the lanes of one warp use when each decodes a member of its own (qz_inflate.cu: consecutive tokens of a lane and equal
+ * token numbers of different lanes both fall into different shared-memory banks). */
+QZ_HD int qz_inflate_tokens_at(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t tstride, uint32_t tskew, uint32_t tmask,
+                               uint32_t max_tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
 {
-    uint32_t o = *pos;
+#define QZI_TOK(i) tok[(i) * tstride + (((i) + tskew) & tmask)]
     int ev = QZI_MATCH;
-    uint64_t acc = b->acc; uint32_t nacc = b->nacc, wnext = b->wnext;
-    const uint32_t *wp = (const uint32_t *)(b->base + b->pos);              /* address wnext came from */
-    const uint32_t *const wlast = (const uint32_t *)(b->base + (b->end & ~3u)) - 1;   /* last word wholly inside the input */
-    uint32_t *tp = tok, *const tend = tok + max_tok;
+    const uint32_t held = (b->nacc + 31) >> 5;                               /* words the accumulator reaches back over */
+    uint32_t sh = held * 32 - b->nacc;                                       /* bit offset of the next symbol in w0 */
+    const uint8_t *const base = b->base;
+    uint32_t woff = b->pos - 4 * held;                                       /* offset of the word being fetched */
+    const uint32_t endw = b->end & ~3u;                                      /* words below this offset lie wholly inside the input */
+#define QZI_WORD(off) ((off) < endw ? *(const uint32_t *)(base + (off)) : qz_br_word(b, (off)))
+#define QZI_ADVANCE() do { sh -= 32; w0 = w1; w1 = w2; woff += 4; w2 = QZI_WORD(woff); } while (0)
+    uint32_t w0 = QZI_WORD(woff), w1 = QZI_WORD(woff + 4), w2 = QZI_WORD(woff + 8);
+    woff += 8;                                                               /* offset w2 came from */
+    const uint32_t room = cap - *pos;
+    uint32_t nt = 0, nmax = max_tok < room ? max_tok : room;
+    uint32_t adj = *pos;                                                     /* output position = adj + nt */
     const uint32_t *const ll_lut = t->ll_lut, *const d_lut = t->d_lut;
-#define QZI_REFILL() do { if (nacc <= 32) { acc |= (uint64_t)wnext << nacc; nacc += 32; wp++; \
-                          wnext = wp <= wlast ? *wp : qz_br_word(b, (uint32_t)((const uint8_t *)wp - b->base)); } } while (0)
-    while (tp != tend) {
-        QZI_REFILL();
-        uint32_t e = ll_lut[(uint32_t)acc & ((1u << QZ_LL_LUT_BITS) - 1)];
+    if (room == 0) {
+        /* the output is full: the block may still end here, anything else does not fit */
+        const uint32_t bits = qz_funnel(w0, w1, sh);
+        uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
+        if (e == 0) {
+            uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
+            e = sym < 0 ? QZE_BAD : qz_infl_ll_entry((uint32_t)sym, l);
+        }
+        if (e & QZE_EOB) { sh += e & 15; if (sh >= 32) QZI_ADVANCE(); ev = QZI_END_BLOCK; }
+        else ev = (e & (QZE_LIT | QZE_LEN)) ? QZI_ERR_FULL : QZI_ERR_DATA;
+        goto done;
+    }
+    while (nt != nmax) {
+        uint32_t bits = qz_funnel(w0, w1, sh);
+        uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
         if ((int32_t)e < 0) {                                /* literal */
 lit:
-            if (o >= cap) { ev = QZI_ERR_FULL; goto done; }
-            acc >>= (e & 15); nacc -= (e & 15);
-            *tp++ = e; o++;
+            sh += e & 15;
+            QZI_TOK(nt) = e; nt++;
+            if (sh >= 32) QZI_ADVANCE();
             continue;
         }
         if (e == 0) {
-            uint32_t l; const int sym = qz_infl_slow(acc, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
+            uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
             if (sym < 0) { ev = QZI_ERR_DATA; goto done; }
             e = qz_infl_ll_entry((uint32_t)sym, l);
             if ((int32_t)e < 0) goto lit;
         }
         if (!(e & QZE_LEN)) {
-            if (e & QZE_EOB) { acc >>= (e & 15); nacc -= (e & 15); ev = QZI_END_BLOCK; }
+            if (e & QZE_EOB) { sh += e & 15; if (sh >= 32) QZI_ADVANCE(); ev = QZI_END_BLOCK; }
             else ev = QZI_ERR_DATA;
             goto done;
         }
-        {   /* length: code + extra bits, at most 20 of the >= 33 buffered */
+        {   /* length: code + extra bits, at most 20 of the 32 in hand; distance: at most 28 */
             const uint32_t cl = e & 15, eb = (e >> 4) & 15;
-            const uint32_t len = ((e >> 8) & 0xffff) + (((uint32_t)(acc >> cl)) & ~(0xffffffffu << eb));
-            acc >>= (cl + eb); nacc -= (cl + eb);
-            QZI_REFILL();
-            uint32_t de = d_lut[(uint32_t)acc & ((1u << QZ_D_LUT_BITS) - 1)];
+            const uint32_t len = ((e >> 8) & 0xffff) + ((bits >> cl) & ~(0xffffffffu << eb));
+            sh += cl + eb; if (sh >= 32) QZI_ADVANCE();
+            bits = qz_funnel(w0, w1, sh);
+            uint32_t de = d_lut[bits & ((1u << QZ_D_LUT_BITS) - 1)];
             if (de == 0) {
-                uint32_t l; const int ds = qz_infl_slow(acc, t->d_count, t->d_first, t->d_offs, t->d_sorted, QZ_D_LUT_BITS, &l);
+                uint32_t l; const int ds = qz_infl_slow(bits, t->d_count, t->d_first, t->d_offs, t->d_sorted, QZ_D_LUT_BITS, &l);
                 if (ds < 0) { ev = QZI_ERR_DATA; goto done; }
                 de = qz_infl_d_entry((uint32_t)ds, l);
             }
             if (de & QZE_BAD) { ev = QZI_ERR_DATA; goto done; }
             const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
-            const uint32_t dist = ((de >> 8) & 0xffff) + (((uint32_t)(acc >> dcl)) & ~(0xffffffffu << deb));
-            acc >>= (dcl + deb); nacc -= (dcl + deb);
+            const uint32_t dist = ((de >> 8) & 0xffff) + ((bits >> dcl) & ~(0xffffffffu << deb));
+            sh += dcl + deb; if (sh >= 32) QZI_ADVANCE();
+            const uint32_t o = adj + nt;
             if (dist > o) { ev = QZI_ERR_DATA; goto done; }
             if (len > cap - o) { ev = QZI_ERR_FULL; goto done; }      /* (o <= cap always; no 32-bit wrap) */
-            *tp++ = ((len - 3) << 16) | (dist - 1);
-            o += len;
+            QZI_TOK(nt) = ((len - 3) << 16) | (dist - 1); nt++;
+            adj += len - 1;
+            const uint32_t left = cap - o - len;                     /* tokens still to come each need a byte of it */
+            if (nmax - nt > left) nmax = nt + left;
         }
     }
 done:
-#undef QZI_REFILL
-    b->acc = acc; b->nacc = nacc; b->pos = (uint32_t)((const uint8_t *)wp - b->base); b->wnext = wnext;
+#undef QZI_ADVANCE
+#undef QZI_WORD
+#undef QZI_TOK
+    b->acc = (uint64_t)(w0 >> sh); b->nacc = 32 - sh; b->pos = woff - 4; b->wnext = w1;
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
     if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
-    *ntok = (uint32_t)(tp - tok); *pos = o;
+    *ntok = nt; *pos = adj + nt;
     return ev;
+}
+QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
+                            uint32_t *pos, uint32_t cap)
+{
+    return qz_inflate_tokens_at(b, t, tok, 1, 0, 0, max_tok, ntok, pos, cap);
 }
 
 /* Read the code lengths of a dynamic block header into t->lens (hlit lengths then hdist).  The
