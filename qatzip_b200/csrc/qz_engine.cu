@@ -110,7 +110,7 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     t->warps_per_cta = env_int("QZB200_WARPS", 0);       /* 0 = default geometry */
     t->buffers_per_cta = env_int("QZB200_BUFFERS", 0);
     t->inflate_dpw = env_int("QZB200_INFLATE_DPW", 1);      /* members decoded at once by one warp: 1 (measured fastest on B200), 2, 4 or 8 */
-    if (t->inflate_dpw != 2 && t->inflate_dpw != 4 && t->inflate_dpw != 8 && t->inflate_dpw != 16 && t->inflate_dpw != 31) t->inflate_dpw = 1;
+    if (t->inflate_dpw != 2 && t->inflate_dpw != 4 && t->inflate_dpw != 8) t->inflate_dpw = 1;
     int mb = env_int("QZB200_BATCH_MB", 64);
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;

@@ -380,227 +380,12 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
     }
 }
 
-/* ---------------------------------------------------------------------------------------------------------------------
- * The rounds kernel: decoding and placing in different warps.
- *
- * In the kernel above a warp alternates between its serial part (one lane turns bits into tokens, 31 idle) and its parallel
- * part (32 lanes place them), and the time of a round is the sum of both dependency chains.  Here a CTA has S members in
- * flight, one per SLOT, and S + 1 warps: the lanes of warp 0 are the S DECODERS -- lane i runs the token loop of slot i's
- * member, so the serial instruction stream is shared by S members -- and warp 1 + i is slot i's OWNER: it draws the
- * member, reads block headers and builds the tables, copies stored blocks, places the decoded batches, takes the checksum
- * and reports the result.  The CTA moves in rounds separated by one barrier: in round r the decoders fill token buffer
- * r & 1 of their slots while every owner places the batch its decoder left in buffer (r - 1) & 1, so both chains run at
- * the same time and a round lasts as long as the longer one.  A decoder that reaches the end of a block parks the bit
- * reader in the slot and pauses; its owner (next round, after placing that last batch) prepares the next block or the
- * next member and hands the reader back (`fresh`); the decoder resumes the round after.  Shared memory per slot: the tables;
- * per CTA: two token buffers of 32 tokens for each of 32 lanes, laid out so that neither the decoders' stores nor an
- * owner's 32 loads collide in a bank. */
-struct InflSlot {
-    QzInflTables t;
-    QzBitReader br;                      /* the member's bit reader while the decoder lane does not hold it */
-    uint32_t out, cap, fresh, pad;       /* owner -> decoder when a block is ready: output position and capacity */
-    uint32_t ntok[2], pos0[2], pos1[2];  /* decoder -> owner, per token buffer: tokens, output position before and after */
-    int32_t ev[2];
-};
-#define QZ_INFL_RING_WORDS (2 * 32 * QZ_INFL_BATCH)
-
-template <int S>
-__global__ void __launch_bounds__(32 * (S + 1), S > 16 ? 1 : 2) qzb_inflate_rounds_kernel(QzbDecompressJob job)
-{
-    QZ_DYN_SMEM(smem_raw);
-    InflSlot *slots = reinterpret_cast<InflSlot *>(smem_raw);
-    uint32_t *ring = reinterpret_cast<uint32_t *>(slots + S);
-    __shared__ uint32_t s_crc_tab[256];
-    __shared__ uint32_t s_xk[6];
-    __shared__ uint32_t s_alive[2][32];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
-    if (threadIdx.x < 6) s_xk[threadIdx.x] = qz_crc_xpow8((uint64_t)128 << threadIdx.x);
-    if (threadIdx.x < 64) s_alive[threadIdx.x >> 5][threadIdx.x & 31] = 0;
-    if (warp == 0 && lane < S) {
-        InflSlot &sl = slots[lane];
-        sl.fresh = 0; sl.ntok[0] = 0; sl.ntok[1] = 0; sl.ev[0] = QZI_MATCH; sl.ev[1] = QZI_MATCH;
-    }
-    __syncthreads();
-    const bool crc_blocks = !job.size_only && job.fmt != QZB_FMT_ZLIB;
-    const bool wr = !job.size_only;
-
-    /* decoder lane (warp 0) */
-    bool running = false;
-    QzBitReader br; qz_br_init(&br, job.src, 0);
-    uint32_t pos = 0, dcap = 0;
-    /* owner warp (1 + slot); everything warp-uniform */
-    const uint32_t slot = warp ? warp - 1 : 0;
-    InflSlot &sl = slots[slot];
-    bool active = false, exhausted = false, in_block = false, done = false;
-    uint32_t mi = 0, out = 0, status = QZB_ST_OK, bfinal = 0, cap = 0, safe_in = 0, safe_out = 0, crc_run = 0, crc_done = 0;
-    const uint8_t *src = job.src; uint8_t *dst = job.dst;
-    QzbMember m; m.src_off = 0; m.src_len = 0; m.exact_len = 0; m.dst_off = 0; m.dst_cap = 0; m.exact_out = 0; m.expect_cksum = 0; m.check_cksum = 0;
-
-    for (uint32_t r = 0;; r++) {
-        if (warp == 0) {
-            /* ---------------- decoders: the next batch of every running slot ---------------- */
-            if (lane < S) {
-                InflSlot &ds = slots[lane];
-                const uint32_t buf = r & 1;
-                if (!running && ds.fresh) { br = ds.br; pos = ds.out; dcap = ds.cap; ds.fresh = 0; running = true; }
-                uint32_t ntk = 0; const uint32_t p0 = pos; int ev = QZI_MATCH;
-                if (running) {
-                    ev = qz_inflate_tokens_at(&br, &ds.t, ring + buf * (32 * QZ_INFL_BATCH), 32, lane, 31, QZ_INFL_BATCH, &ntk, &pos, dcap);
-                    if (ev != QZI_MATCH) { ds.br = br; running = false; }
-                }
-                ds.ntok[buf] = ntk; ds.ev[buf] = ev; ds.pos0[buf] = p0; ds.pos1[buf] = pos;
-            }
-        } else {
-            /* ---------------- owner: place what the decoder left in the last round ---------------- */
-            if (active && in_block) {
-                const uint32_t buf = (r - 1) & 1;
-                const uint32_t n = sl.ntok[buf], o0 = sl.pos0[buf]; const int ev = sl.ev[buf];
-                if (n) {
-                    const uint32_t t = lane < n ? ring[buf * (32 * QZ_INFL_BATCH) + lane * 32 + ((lane + slot) & 31)] : 0u;
-                    infl_place(dst, o0, n, t, wr, lane);
-                    out = sl.pos1[buf];
-                }
-                if (ev == QZI_END_BLOCK) { in_block = false; if (bfinal) done = true; }
-                else if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; done = true; in_block = false; }
-                else if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; done = true; in_block = false; }
-                else if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; done = true; in_block = false; }
-                /* checksum of the 4 KiB blocks that have become complete, while they are still in L2 */
-                if (crc_blocks && status == QZB_ST_OK) {
-                    __syncwarp();
-                    while (out - crc_done >= QZ_INFL_CRC_BLOCK) {
-                        const uint32_t cb = warp_crc32_block(dst + crc_done, s_crc_tab, s_xk, lane);
-                        crc_run = qz_gf2_mul(crc_run, s_xk[5]) ^ cb; crc_done += QZ_INFL_CRC_BLOCK;
-                    }
-                }
-            }
-            /* ---------------- owner: until a Huffman block is ready for the decoder, or nothing is left ---------------- */
-            while (!(active && in_block)) {
-                if (!active) {
-                    if (exhausted) break;
-                    uint32_t tk = 0;
-                    if (lane == 0) tk = atomicAdd(job.ticket, 1u);
-                    tk = bcast(tk);
-                    if (tk >= job.nmembers) { exhausted = true; break; }
-                    mi = job.order ? job.order[tk] : tk;       /* the longest members first: the last round of a launch is short ones */
-                    m = job.members[mi];
-                    src = job.src + m.src_off; dst = job.dst + m.dst_off; cap = m.dst_cap;
-                    if (lane == 0) qz_br_init(&sl.br, src, m.src_len);
-                    out = 0; status = QZB_ST_OK; bfinal = 0; in_block = false; done = false; active = true;
-                    safe_in = 0; safe_out = 0; crc_run = 0; crc_done = 0;
-                    __syncwarp();
-                }
-                if (!done) {
-                    /* block header: lane 0 reads, everybody learns */
-                    uint32_t type = 7, slen = 0, sstart = 0, st = status, bf = bfinal;
-                    if (lane == 0) {
-                        QzBitReader *B = &sl.br;
-                        qz_br_refill(B);
-                        /* QZ_DEFLATE_RAW chunks that are not the last of the stream end without BFINAL: stop cleanly when
-                         * nothing but padding is left */
-                        if (job.fmt == QZB_FMT_RAW && qz_br_exhausted(B)) type = 4;
-                        else { bf = qz_br_bits(B, 1); type = qz_br_bits(B, 2); }
-                        if (type == 0) {
-                            const uint32_t drop = B->nacc & 7; B->acc >>= drop; B->nacc -= drop;
-                            qz_br_refill(B);
-                            slen = qz_br_bits(B, 16);
-                            const uint32_t nlen = qz_br_bits(B, 16);
-                            sstart = qz_br_consumed(B);
-                            if ((slen ^ 0xffffu) != nlen) st = QZB_ST_DATA_ERROR;
-                            else if (slen > B->n || sstart > B->n - slen) st = QZB_ST_IN_TRUNC;
-                            else if (slen > cap - out) st = QZB_ST_OUT_FULL;
-                            else qz_br_seek(B, sstart + slen);
-                        }
-                    }
-                    type = bcast(type); bfinal = bcast(bf); status = bcast(st);
-                    if (type == 4) done = true;
-                    else if (type == 3) { status = QZB_ST_DATA_ERROR; done = true; }
-                    else if (type == 0) {
-                        if (status != QZB_ST_OK) done = true;
-                        else {
-                            slen = bcast(slen); sstart = bcast(sstart);
-                            if (wr) for (uint32_t i = lane; i < slen; i += 32) dst[out + i] = src[sstart + i];
-                            out += slen;
-                            safe_in = sstart + slen; safe_out = out;       /* byte-aligned behind a stored block */
-                            if (bfinal) done = true;
-                            __syncwarp();
-                        }
-                    } else {
-                        /* Huffman block: lane 0 reads the code lengths (dynamic) or all lanes fill in the fixed ones, the
-                         * warp builds the tables (the distance table doubles as scratch until it is cleared) */
-                        uint32_t hlit = 288, hdist = 30, bad = 0;
-                        QzInflTables &T = sl.t;
-                        if (type == 1) {
-                            for (uint32_t sy = lane; sy < 288; sy += 32) T.lens[sy] = (uint8_t)qz_fixed_ll_len(sy);
-                            if (lane < 30) T.lens[288 + lane] = 5;
-                        } else if (lane == 0) bad = qz_inflate_read_dynamic(&sl.br, &T, &hlit, &hdist) != 0;
-                        bad = bcast(bad); hlit = bcast(hlit); hdist = bcast(hdist);
-                        __syncwarp();
-                        if (!bad) bad = warp_infl_prepare(T.lens, (int)hlit, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.d_lut + 64, lane) < 0 ||
-                                        warp_infl_prepare(T.lens + hlit, (int)hdist, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut + 64, lane) < 0;
-                        if (bad) { status = QZB_ST_DATA_ERROR; done = true; }
-                        else {
-                            __syncwarp();
-                            for (uint32_t i = lane; i < (1u << QZ_LL_LUT_BITS); i += 32) T.ll_lut[i] = 0;
-                            for (uint32_t i = lane; i < (1u << QZ_D_LUT_BITS); i += 32) T.d_lut[i] = 0;
-                            __syncwarp();
-                            qz_infl_fill_lut(T.lens, T.ll_count, T.ll_first, T.ll_offs, T.ll_sorted, T.ll_lut, QZ_LL_LUT_BITS, 0, (int)lane, 32);
-                            qz_infl_fill_lut(T.lens + hlit, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut, QZ_D_LUT_BITS, 1, (int)lane, 32);
-                            if (lane == 0) { sl.out = out; sl.cap = cap; sl.fresh = 1; }
-                            __syncwarp();
-                            in_block = true;
-                        }
-                    }
-                }
-                if (done) {
-                    /* ---- the member ends here: verdict, the rest of the checksum, result ---- */
-                    uint32_t consumed = 0, st = status;
-                    if (lane == 0) {
-                        consumed = qz_br_consumed(&sl.br);
-                        if (st == QZB_ST_OK && qz_br_overrun(&sl.br)) st = QZB_ST_IN_TRUNC;
-                        if (st == QZB_ST_OK && m.exact_len && consumed != m.src_len) st = QZB_ST_DATA_ERROR;
-                        if (st == QZB_ST_OK && m.exact_out && out != cap) st = QZB_ST_SIZE;
-                    }
-                    consumed = bcast(consumed); status = bcast(st);
-                    uint32_t crc = 0;
-                    __syncwarp();
-                    if (status == QZB_ST_OK && wr) {
-                        if (job.fmt == QZB_FMT_ZLIB) crc = warp_adler32_global(dst, out, lane);
-                        else {
-                            /* what the block-wise pass has not covered yet, joined to the running value */
-                            const uint32_t tail = warp_crc32_global(dst + crc_done, out - crc_done, s_crc_tab, lane);
-                            crc = crc_done ? (out - crc_done ? qz_gf2_mul(crc_run, bcast(lane == 0 ? qz_crc_xpow8(out - crc_done) : 0u)) ^ tail : crc_run) : tail;
-                        }
-                    }
-                    if (lane == 0) {
-                        if (status == QZB_ST_OK && wr && m.check_cksum && crc != m.expect_cksum) status = QZB_ST_CKSUM;
-                        QzbMemberResult res;
-                        res.status = status; res.consumed = consumed; res.produced = out; res.cksum = crc; res.saw_final = bfinal;
-                        res.safe_consumed = safe_in; res.safe_produced = safe_out; res.pad = 0;
-                        job.results[mi] = res;
-                    }
-                    active = false; done = false; in_block = false;
-                }
-            }
-            if (lane == 0) s_alive[r & 1][slot] = active ? 1u : 0u;
-        }
-        __syncthreads();
-        const uint32_t a = lane < S ? s_alive[r & 1][lane] : 0u;
-        if (__ballot_sync(FULL, a != 0) == 0) break;
-    }
-}
-
 #ifndef QZ_WARP_EMU
 /* decoders per warp (1, 2, 4 or 8); a CTA is 8 warps (4 with eight decoders per warp: 32 slots fill the shared memory) */
-static int inflate_cta_warps(int dpw) { return dpw >= 16 ? (dpw >= 31 ? 32 : 17) : dpw == 8 ? 4 : 8; }
-/* dpw 16 and 31 name the rounds kernel with that many slots per CTA */
-extern "C" size_t qzb_inflate_smem_bytes(int dpw)
-{
-    if (dpw >= 16) return sizeof(InflSlot) * (size_t)(dpw >= 31 ? 31 : 16) + QZ_INFL_RING_WORDS * sizeof(uint32_t);
-    return sizeof(InflWarpSmem) * (size_t)inflate_cta_warps(dpw) * (size_t)dpw;
-}
+static int inflate_cta_warps(int dpw) { return dpw == 8 ? 4 : 8; }
+extern "C" size_t qzb_inflate_smem_bytes(int dpw) { return sizeof(InflWarpSmem) * (size_t)inflate_cta_warps(dpw) * (size_t)dpw; }
 extern "C" int qzb_inflate_cta_threads(int dpw) { return inflate_cta_warps(dpw) * 32; }
-extern "C" int qzb_inflate_cta_slots(int dpw) { return dpw >= 16 ? (dpw >= 31 ? 31 : 16) : inflate_cta_warps(dpw) * dpw; }
+extern "C" int qzb_inflate_cta_slots(int dpw) { return inflate_cta_warps(dpw) * dpw; }
 template <int DPW>
 static cudaError_t launch_inflate(const QzbDecompressJob &job, int grid, cudaStream_t st)
 {
@@ -610,19 +395,8 @@ static cudaError_t launch_inflate(const QzbDecompressJob &job, int grid, cudaStr
     qzb_inflate_kernel<DPW><<<grid, inflate_cta_warps(DPW) * 32, smem, st>>>(job);
     return cudaGetLastError();
 }
-template <int S>
-static cudaError_t launch_inflate_rounds(const QzbDecompressJob &job, int grid, cudaStream_t st)
-{
-    const size_t smem = qzb_inflate_smem_bytes(S);
-    cudaError_t e = cudaFuncSetAttribute(qzb_inflate_rounds_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    qzb_inflate_rounds_kernel<S><<<grid, 32 * (S + 1), smem, st>>>(job);
-    return cudaGetLastError();
-}
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, int grid, cudaStream_t st)
 {
-    if (dpw >= 31) return launch_inflate_rounds<31>(*job, grid, st);
-    if (dpw >= 16) return launch_inflate_rounds<16>(*job, grid, st);
     return dpw == 1 ? launch_inflate<1>(*job, grid, st) : dpw == 2 ? launch_inflate<2>(*job, grid, st) : dpw == 8 ? launch_inflate<8>(*job, grid, st) : launch_inflate<4>(*job, grid, st);
 }
 #endif

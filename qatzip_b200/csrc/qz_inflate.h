@@ -180,13 +180,9 @@ QZ_HD uint32_t qz_funnel(uint32_t lo, uint32_t hi, uint32_t sh)
  * consuming them is one add.  The output position is not stepped per literal: every token stands for
  * at least one byte, so the batch is cut at the room left and the position follows from the token
  * count plus what the matches added. */
-/* Token i is stored at tok[i * tstride + ((i + tskew) & tmask)]: (1, 0, 0) is a plain array; (32, lane, 31) is the layout
- * the lanes of one warp use when each decodes a member of its own (qz_inflate.cu: consecutive tokens of a lane and equal
- * token numbers of different lanes both fall into different shared-memory banks). */
-QZ_HD int qz_inflate_tokens_at(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t tstride, uint32_t tskew, uint32_t tmask,
-                               uint32_t max_tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
+QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
+                            uint32_t *pos, uint32_t cap)
 {
-#define QZI_TOK(i) tok[(i) * tstride + (((i) + tskew) & tmask)]
     int ev = QZI_MATCH;
     const uint32_t held = (b->nacc + 31) >> 5;                               /* words the accumulator reaches back over */
     uint32_t sh = held * 32 - b->nacc;                                       /* bit offset of the next symbol in w0 */
@@ -219,7 +215,7 @@ QZ_HD int qz_inflate_tokens_at(QzBitReader *b, const QzInflTables *t, uint32_t *
         if ((int32_t)e < 0) {                                /* literal */
 lit:
             sh += e & 15;
-            QZI_TOK(nt) = e; nt++;
+            tok[nt++] = e;
             if (sh >= 32) QZI_ADVANCE();
             continue;
         }
@@ -252,7 +248,7 @@ lit:
             const uint32_t o = adj + nt;
             if (dist > o) { ev = QZI_ERR_DATA; goto done; }
             if (len > cap - o) { ev = QZI_ERR_FULL; goto done; }      /* (o <= cap always; no 32-bit wrap) */
-            QZI_TOK(nt) = ((len - 3) << 16) | (dist - 1); nt++;
+            tok[nt++] = ((len - 3) << 16) | (dist - 1);
             adj += len - 1;
             const uint32_t left = cap - o - len;                     /* tokens still to come each need a byte of it */
             if (nmax - nt > left) nmax = nt + left;
@@ -261,18 +257,12 @@ lit:
 done:
 #undef QZI_ADVANCE
 #undef QZI_WORD
-#undef QZI_TOK
     b->acc = (uint64_t)(w0 >> sh); b->nacc = 32 - sh; b->pos = woff - 4; b->wnext = w1;
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
     if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
     *ntok = nt; *pos = adj + nt;
     return ev;
-}
-QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
-                            uint32_t *pos, uint32_t cap)
-{
-    return qz_inflate_tokens_at(b, t, tok, 1, 0, 0, max_tok, ntok, pos, cap);
 }
 
 /* Read the code lengths of a dynamic block header into t->lens (hlit lengths then hdist).  The

@@ -10,13 +10,11 @@ extern "C" int emu_inflate(int fmt, const uint8_t *src, uint8_t *dst, const QzbM
     QzbDecompressJob job; memset(&job, 0, sizeof job);
     job.src = src; job.dst = dst; job.members = members; job.results = results; job.nmembers = nmembers; job.fmt = fmt;
     job.ticket = ticket; job.size_only = size_only;
-    /* decoders per warp: QZ_EMU_INFLATE_DPW (1, 2, 4, 8; 16 and 31: the rounds kernel), default 4 as in the product */
+    /* decoders per warp: QZ_EMU_INFLATE_DPW (1, 2, 4, 8), default 4 as in the product */
     const char *e = getenv("QZ_EMU_INFLATE_DPW");
     const int dpw = e ? atoi(e) : 4;
     const unsigned g = (unsigned)(grid < 1 ? 1 : grid);
-    if (dpw == 31) emu::launch(g, 1024, sizeof(InflSlot) * 31 + QZ_INFL_RING_WORDS * 4, [&] { qzb_inflate_rounds_kernel<31>(job); });
-    else if (dpw == 16) emu::launch(g, 544, sizeof(InflSlot) * 16 + QZ_INFL_RING_WORDS * 4, [&] { qzb_inflate_rounds_kernel<16>(job); });
-    else if (dpw == 1) emu::launch(g, 256, sizeof(InflWarpSmem) * 8, [&] { qzb_inflate_kernel<1>(job); });
+    if (dpw == 1) emu::launch(g, 256, sizeof(InflWarpSmem) * 8, [&] { qzb_inflate_kernel<1>(job); });
     else if (dpw == 2) emu::launch(g, 256, sizeof(InflWarpSmem) * 16, [&] { qzb_inflate_kernel<2>(job); });
     else if (dpw == 8) emu::launch(g, 128, sizeof(InflWarpSmem) * 32, [&] { qzb_inflate_kernel<8>(job); });
     else emu::launch(g, 256, sizeof(InflWarpSmem) * 32, [&] { qzb_inflate_kernel<4>(job); });
