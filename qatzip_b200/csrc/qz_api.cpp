@@ -603,7 +603,7 @@ struct QzbStreamBuf {
     /* compress, asynchronous mode */
     QzbStreamWorker *worker[QZB_STREAM_WORKERS];
     QzbStreamJob *flight[QZB_STREAM_WORKERS];      /* jobs with the workers, oldest first */
-    unsigned int nflight, last_queued, any_taken;
+    unsigned int nflight, last_queued, any_taken, nworkers;
     QzbStreamJob *spare;                   /* buffers of a finished job, reused for the next one */
 };
 /* What a stream sets up beyond its session -- the second worker's engine and the pinned staging buffers -- costs more than
@@ -751,14 +751,13 @@ extern "C" int qzCompressStream(QzSession_T *sess, QzStream_T *strm, unsigned in
             unsigned int got = 0;
             unsigned char *ni = stream_buf_get((unsigned int)want, &got, true);     /* jobs are cut at the capacity: exactly this size */
             if (ni) { qzFree(b->in_buf); b->in_buf = ni; b->in_cap = got; b->in_off = 0; b->batched = 2; }
+            const char *wv = getenv("QZB200_STREAM_WORKERS");        /* 1: one job in flight (A/B) */
+            const long nw = wv && *wv ? strtol(wv, NULL, 10) : QZB_STREAM_WORKERS;
+            b->nworkers = (unsigned int)(nw < 1 ? 1 : nw > QZB_STREAM_WORKERS ? QZB_STREAM_WORKERS : nw);
         }
     }
     if (b->batched == 2) {
-        static const unsigned int nworkers = [] {       /* QZB200_STREAM_WORKERS=1: one job in flight (A/B) */
-            const char *ev = getenv("QZB200_STREAM_WORKERS");
-            long v = ev && *ev ? strtol(ev, NULL, 10) : QZB_STREAM_WORKERS;
-            return (unsigned int)(v < 1 ? 1 : v > QZB_STREAM_WORKERS ? QZB_STREAM_WORKERS : v);
-        }();
+        const unsigned int nworkers = b->nworkers;
         /* ---- asynchronous: up to QZB_STREAM_WORKERS jobs with the workers while this thread stages the next ---- */
         auto take_over = [&](bool wait) -> bool {        /* the oldest job's output becomes the pending output */
             if (!b->nflight || strm->pending_out) return false;

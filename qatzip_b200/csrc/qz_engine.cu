@@ -617,8 +617,9 @@ static void gzip_scan_candidates(const uint8_t *p, uint64_t lo, uint64_t n, std:
     out.clear();
     if (n < lo + 10) return;
     const uint64_t span = n - lo;
-    unsigned T = std::thread::hardware_concurrency(); if (T == 0) T = 4; if (T > 16) T = 16;
-    if (span < (8u << 20)) T = 1;
+    /* one slice of at least 8 MiB per thread, at most 64 threads (a 1.5 GiB call: 3 ms instead of 18 with sixteen) */
+    unsigned T = std::thread::hardware_concurrency(); if (T == 0) T = 4; if (T > 64) T = 64;
+    if (span / (8u << 20) < T) T = (unsigned)std::max<uint64_t>(1, span / (8u << 20));
     std::vector<std::vector<uint64_t>> part(T);
     auto work = [&](unsigned t) {
         const uint64_t a = lo + span * t / T, b = lo + span * (t + 1) / T;

@@ -483,6 +483,27 @@ def test_stream_compress_slices(prod, port, ref, data, fmt, batch_kb, monkeypatc
     prod.end_session(sess)
 
 
+@pytest.mark.parametrize("workers", ["1", "2"])
+@pytest.mark.parametrize("fmt", [q.QZ_DEFLATE_GZIP_EXT, q.QZ_DEFLATE_RAW])
+def test_stream_many_jobs_in_flight(prod, port, data, fmt, workers, monkeypatch):
+    """Staging of 256 KiB (four chunks a job) over 6 MiB: two dozen jobs go through the stream's worker threads, with an
+    output buffer small enough that finished jobs wait for room while the next ones are already being compressed.
+    Output order, the combined CRC-32 and the bytes must not depend on the number of workers or on the buffer sizes."""
+    monkeypatch.setenv("QZB200_STREAM_BATCH_KB", "256")
+    monkeypatch.setenv("QZB200_STREAM_WORKERS", workers)
+    d = pick(data, 6 << 20, 41)
+    sess = prod.new_session(fmt=fmt)
+    blobs = []
+    for slice_sz, out_sz in ((50000, 8192), (4096, 1 << 20), (700000, 300000)):
+        blob, crc, _, _ = stream_compress(prod, sess, d, slice_sz, out_sz=out_sz)
+        assert crc == zlib.crc32(d)
+        blobs.append(blob)
+    assert all(b == blobs[0] for b in blobs)
+    assert port.decompress(blobs[0], fmt, len(d) + 8) == d
+    assert blobs[0] == prod.compress(d, fmt=fmt)              # the same chunks as one qzCompress call makes
+    prod.end_session(sess)
+
+
 def test_stream_small_output_pending(prod, port, data):
     """mode 20: 8 KiB out_sz with pending_out draining"""
     d = pick(data, 300000, 13)
