@@ -115,6 +115,14 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (mb < 1) mb = 1;
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
+    /* Decompress batches (compressed bytes per launch, host-memory calls).  A launch lasts at least as long as its longest
+     * member takes one warp (a 256 KiB member: ~30 ms), so the bytes in flight -- four batches -- have to cover that time at
+     * the kernel's rate: 4 x 128 MiB of input is ~1.2 GiB of output (measured: 12.5 GB/s with 64 MiB batches on mixed
+     * 4-256 KiB members) */
+    int imb = env_int("QZB200_INFLATE_BATCH_MB", 128);
+    if (imb < 1) imb = 1;
+    if (imb > 1024) imb = 1024;
+    t->inflate_batch_bytes = (size_t)imb << 20;
     int fmb = env_int("QZB200_FIRST_MB", 16);
     if (fmb < 1) fmb = 1;
     if (fmb > mb) fmb = mb;
@@ -640,6 +648,8 @@ static void gzip_scan_candidates(const uint8_t *p, uint64_t lo, uint64_t n, std:
 extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, QzbDecompressOut *o)
 {
     std::vector<uint64_t> gz_cand; bool gz_scanned = false;       /* absolute offsets of plausible gzip member starts */
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     memset(o, 0, sizeof *o);
     if (!e || !c) return RC_PARAMS;
     CK(cudaSetDevice(e->device));
@@ -925,7 +935,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             /* one warp per member: a launch needs ~7000 members in flight to fill 148 SMs, so batches are
              * cut by member count first and by bytes second */
             /* host buffers: batches small enough to pipeline copies; device-resident: one launch as wide as possible */
-            const uint64_t bin = c->src_device ? ((uint64_t)1 << 30) : e->tune.batch_bytes, bout = bin * 4;
+            const uint64_t bin = c->src_device ? ((uint64_t)1 << 40) : e->tune.inflate_batch_bytes, bout = bin * 4;      /* device-resident: one launch per call */
             size_t i = 0, issued = 0; bool stop = false;
             long seq_unit = -1;
             size_t nsized = units.size();
@@ -933,9 +943,13 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             auto drain = [&](Slot &s) -> int {
                 if (!s.busy) return RC_OK;
                 s.busy = false;
+                const double t_drain = e->timeline ? host_ms() : 0.0;
                 CK(cudaEventSynchronize(s.ev_meta));
                 if (stop) { CK(cudaStreamSynchronize(s.st)); return RC_OK; }
                 float ms = 0; cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); o->kernel_ms += ms;
+                const double t_meta = e->timeline ? host_ms() : 0.0;
+                auto tl_print = [&]() { if (e->timeline) fprintf(stderr, "[qzb timeline] inflate batch: %zu members, out %.1f MiB | kernel %.2f ms | host: drain@%.2f results@%.2f delivered@%.2f\n",
+                                                                s.nmembers, (double)s.out_len / 1048576.0, ms, t_drain, t_meta, host_ms()); };
                 const QzbMemberResult *r = (const QzbMemberResult *)s.h_results.p;
                 size_t good = 0;
                 while (good < s.nmembers && r[good].status == QZB_ST_OK) good++;
@@ -953,6 +967,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     if (getenv("QZB200_DEBUG")) fprintf(stderr, "[qatzip_b200] member %ld failed: status %u consumed %u/%u produced %u/%u cksum %08x/%08x\n", failed_unit, r[good].status,
                                                         r[good].consumed, units[(size_t)failed_unit].m.src_len, r[good].produced, units[(size_t)failed_unit].m.dst_cap, r[good].cksum, units[(size_t)failed_unit].m.expect_cksum);
                 }
+                tl_print();
                 return RC_OK;
             };
             constexpr int NS = QzbEngine::NSLOT;

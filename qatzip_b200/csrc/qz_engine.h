@@ -76,7 +76,7 @@ int qzb_pinned_free(void *p);          /* 1 if p was one of ours */
 int qzb_pinned_contains(const void *p, size_t len);
 
 /* tuning knobs (environment: QZB200_PIECE_LOG2, QZB200_HASH_BITS, QZB200_BATCH_MB, QZB200_WARPS) */
-typedef struct QzbTuning { int piece_log2, hash_bits, warps_per_cta, buffers_per_cta, inflate_dpw; size_t batch_bytes, first_batch_bytes, zlib_window_bytes; int taper; int window, window_tent, lz4_warps; } QzbTuning;
+typedef struct QzbTuning { int piece_log2, hash_bits, warps_per_cta, buffers_per_cta, inflate_dpw; size_t batch_bytes, first_batch_bytes, zlib_window_bytes, inflate_batch_bytes; int taper; int window, window_tent, lz4_warps; } QzbTuning;
 void qzb_get_tuning(QzbTuning *t);
 
 /* raw device memory helpers for callers that keep data in HBM (bench, tests) */
