@@ -163,6 +163,14 @@ def test_compression_levels(prod, ref):
         sizes[lvl] = len(blob)
     print("levels", sizes)
     assert sizes[1] == sizes[5] and sizes[6] == sizes[9] and sizes[6] < sizes[1]
+    # LZ4: levels below 6 use sixteen matchers with smaller tables, 6 and up twelve with larger ones
+    lz = {}
+    for lvl in (1, 9):
+        blob = prod.compress(d, fmt=q.FMT_LZ4, level=lvl)
+        assert ref.decompress(blob, len(d) + 8, fmt=q.FMT_LZ4) == d
+        lz[lvl] = len(blob)
+    print("LZ4 levels", lz)
+    assert lz[9] < lz[1]
 
 
 def test_lz4_ratio_within_5_percent_of_reference(prod, ref, corpus):
