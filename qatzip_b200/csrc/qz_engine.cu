@@ -17,6 +17,9 @@
 #include <mutex>
 #include <vector>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include "qz_engine.h"
 #include "qz_kernels.cuh"
@@ -633,6 +636,16 @@ static void gzip_scan_candidates(const uint8_t *p, uint64_t lo, uint64_t n, std:
     auto work = [&](unsigned t) {
         const uint64_t a = lo + span * t / T, b = lo + span * (t + 1) / T;
         uint64_t q = a;
+#if defined(__SSE2__)
+        /* 16 positions a step: 1f at q and 8b at q + 1 (one in 65 536 positions of compressed data passes) */
+        const __m128i c1f = _mm_set1_epi8(0x1f), c8b = _mm_set1_epi8((char)0x8b);
+        while (q + 17 <= b && q + 17 <= n) {
+            const __m128i x = _mm_loadu_si128((const __m128i *)(p + q)), y = _mm_loadu_si128((const __m128i *)(p + q + 1));
+            unsigned m = (unsigned)_mm_movemask_epi8(_mm_and_si128(_mm_cmpeq_epi8(x, c1f), _mm_cmpeq_epi8(y, c8b)));
+            while (m) { const unsigned k = (unsigned)__builtin_ctz(m); m &= m - 1; if (gzip_member_start(p, q + k, n)) part[t].push_back(q + k); }
+            q += 16;
+        }
+#endif
         while (q < b) {
             const uint8_t *f = (const uint8_t *)memchr(p + q, 0x1f, b - q);
             if (!f) break;
@@ -769,7 +782,20 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             std::vector<uint64_t> cand;
             if (win >= 2 && hdr_ok(0)) {
                 cand.push_back(0);
-                if (!c->stop_at_first) for (uint64_t q = 1; q + 6 <= win; q++) if (hdr_ok(q)) cand.push_back(q);
+                if (!c->stop_at_first && win >= 7) {
+                    /* every offset is tested (one in ~2000 passes): sliced over host threads like the gzip member scan */
+                    const uint64_t lo = 1, hi = win - 5;
+                    unsigned T = std::thread::hardware_concurrency(); if (T == 0) T = 4; if (T > 64) T = 64;
+                    if ((hi - lo) / (4u << 20) < T) T = (unsigned)std::max<uint64_t>(1, (hi - lo) / (4u << 20));
+                    std::vector<std::vector<uint64_t>> part(T);
+                    auto work = [&](unsigned t) {
+                        const uint64_t a = lo + (hi - lo) * t / T, b = lo + (hi - lo) * (t + 1) / T;
+                        for (uint64_t q = a; q < b; q++) if (hdr_ok(q)) part[t].push_back(q);
+                    };
+                    if (T == 1) work(0);
+                    else { std::vector<std::thread> th; for (unsigned t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+                    for (auto &v : part) cand.insert(cand.end(), v.begin(), v.end());
+                }
             }
             if (cand.empty()) { final_rc = (win < 2) ? RC_DATA_ERROR : RC_FAIL; break; }
             for (uint64_t q : cand) {
