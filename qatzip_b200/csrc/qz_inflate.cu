@@ -17,11 +17,11 @@
 
 #define FULL 0xffffffffu
 
-#define QZ_INFL_BATCH 32
 #define QZ_INFL_LANE_COPY 16          /* matches up to this long are copied by the lane that owns the token */
 struct InflWarpSmem {
     QzInflTables t;
     uint32_t tok[QZ_INFL_BATCH];     /* one decoded batch: lane 0 fills it, every lane places one token */
+    uint32_t inw[QZ_INFL_INW];       /* the compressed words the next batch can reach, staged by the whole warp */
 };
 
 __device__ __forceinline__ uint32_t bcast(uint32_t v) { return __shfl_sync(FULL, v, 0); }
@@ -154,16 +154,12 @@ __device__ __forceinline__ void infl_place(uint8_t *d, uint32_t o0, uint32_t n, 
     const bool dep = is_match && (o - dist + span > o0);         /* reads output of this very batch */
     /* short matches that neither overlap themselves nor read this batch: the owning lane copies, all loads first */
     const bool lane_copy = is_match && !dep && len <= QZ_INFL_LANE_COPY && dist >= len;
-    if (lane < n && wr) {
-        if (!is_match) d[o] = (uint8_t)qz_tok_byte(t);
-        else if (lane_copy) {
-            const uint8_t *from = d + o - dist;
-            uint8_t v[QZ_INFL_LANE_COPY];
-#pragma unroll
-            for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) v[k] = k < len ? from[k] : (uint8_t)0;
-#pragma unroll
-            for (uint32_t k = 0; k < QZ_INFL_LANE_COPY; k++) if (k < len) d[o + k] = v[k];
-        }
+    if (wr) {
+        /* (their sources lie before the batch, so nothing written here is read here: as many steps as the longest of them) */
+        const uint32_t steps = __reduce_max_sync(FULL, lane_copy ? len : 0u);
+        if (lane < n && !is_match) d[o] = (uint8_t)qz_tok_byte(t);
+        const uint8_t *from = d + o - dist;
+        for (uint32_t k = 0; k < steps; k++) if (lane_copy && k < len) d[o + k] = from[k];
     }
     /* the rest (long, self-overlapping, or fed by this batch) go in order, copied by the whole warp */
     uint32_t depmask = wr ? __ballot_sync(FULL, is_match && !lane_copy) : 0u;
@@ -191,15 +187,16 @@ __device__ __forceinline__ void infl_place(uint8_t *d, uint32_t o0, uint32_t n, 
 #define QZ_INFL_MIN_CTAS(dpw) ((dpw) == 1 ? 3 : (dpw) == 2 ? 2 : 1)
 #endif
 /* The token loop as a function of its own: the compiler then allocates registers for the loop alone instead of sharing them
- * with the kernel's member state (inlined, it rebuilt shared-memory addresses in every iteration).  Tables and token buffer
- * are in shared memory, which is said so that the loads stay LDS. */
-__device__ __noinline__ int infl_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
+ * with the kernel's member state.  Window, tables and token buffer are in shared memory, which is said so that the loads stay LDS. */
+__device__ __noinline__ int infl_tokens(const uint32_t *inw, uint32_t *lp, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
 {
 #ifndef QZ_WARP_EMU
+    __builtin_assume(__isShared(inw));
     __builtin_assume(__isShared(t));
     __builtin_assume(__isShared(tok));
 #endif
-    return qz_inflate_tokens(b, t, tok, QZ_INFL_BATCH, ntok, pos, cap);
+    return cap - *pos < QZ_INFL_ROOMY ? qz_inflate_tokens_core<true>(inw, lp, t, tok, ntok, pos, cap)
+                                      : qz_inflate_tokens_core<false>(inw, lp, t, tok, ntok, pos, cap);
 }
 
 template <int DPW>
@@ -309,7 +306,28 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
 
         /* ---- every decoder inside a block fills its token buffer (no output touched) ---- */
         int ev = QZI_MATCH; uint32_t ntk = 0, pos = out;
-        if (is_dec && active && in_block && !done) ev = infl_tokens(&br, &slots[myslot].t, slots[myslot].tok, &ntk, &pos, cap);
+        {
+            /* the compressed words the batch can reach go to shared memory first, fetched by the whole warp, slot after slot */
+            const bool dec_now = is_dec && active && in_block && !done;
+            uint32_t woff = 0, lp = 0;
+            if (dec_now) qz_br_where(&br, &woff, &lp);
+            uint32_t fmask = __ballot_sync(FULL, dec_now);
+            while (fmask) {
+                const uint32_t j = __ffs(fmask) - 1; fmask &= fmask - 1;
+                const uint8_t *base_j = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(br.base), j));
+                const uint32_t end_j = __shfl_sync(FULL, br.end, j), woff_j = __shfl_sync(FULL, woff, j);
+                uint32_t *w = slots[j / TL].inw;
+#pragma unroll
+                for (uint32_t i = lane; i < QZ_INFL_INW; i += 32) w[i] = qz_word_at(base_j, end_j, woff_j + 4 * i);
+            }
+            __syncwarp();
+            if (dec_now) {
+                ev = infl_tokens(slots[myslot].inw, &lp, &slots[myslot].t, slots[myslot].tok, &ntk, &pos, cap);
+                qz_br_resume(&br, woff, slots[myslot].inw, lp);
+                /* past the end of the input the window holds zero bits: see qz_inflate_tokens */
+                if (ev == QZI_MATCH && qz_br_overrun(&br)) ev = QZI_ERR_TRUNC;
+            }
+        }
         __syncwarp();
         /* ---- the batches are placed, slot after slot, by the whole warp: literals and matches whose source lies wholly
          * before the batch go out at once, matches that read bytes produced inside the batch follow in order ---- */

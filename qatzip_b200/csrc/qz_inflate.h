@@ -20,14 +20,15 @@
 #endif
 
 /* Decode-table entry:
- *   bits 0..3   code length (1..15); an all-zero entry = code longer than the table, or unused
+ *   bits 0..3   code length (1..15); an all-zero entry = code longer than the table, unused, or a symbol that must not occur
  *   bits 4..7   number of extra bits that follow the code
  *   bits 8..23  literal byte, or length base 3..258, or distance base 1..24577
- *   bits 28..31 kind */
+ *   bits 29..31 kind; an entry function's answer with no kind bit set = symbol that must not occur (lit/len 286, 287;
+ *               distance 30, 31): such symbols are left out of the table, so the decode loop meets them on its slow path only */
 #define QZE_LIT 0x80000000u
 #define QZE_LEN 0x40000000u      /* also marks a valid distance entry */
 #define QZE_EOB 0x20000000u
-#define QZE_BAD 0x10000000u      /* symbol that must not occur (lit/len 286, 287; distance 30, 31) */
+#define QZE_KIND (QZE_LIT | QZE_LEN | QZE_EOB)
 
 struct QzInflTables {
     uint32_t ll_lut[1 << QZ_LL_LUT_BITS];
@@ -43,13 +44,13 @@ QZ_HD uint32_t qz_infl_ll_entry(uint32_t s, uint32_t l)
 {
     if (s < 256) return QZE_LIT | (s << 8) | l;
     if (s == 256) return QZE_EOB | l;
-    if (s > 285) return QZE_BAD | l;
+    if (s > 285) return l;
     uint32_t eb, base = qz_len_base(s - 257, &eb);
     return QZE_LEN | (base << 8) | (eb << 4) | l;
 }
 QZ_HD uint32_t qz_infl_d_entry(uint32_t s, uint32_t l)
 {
-    if (s > 29) return QZE_BAD | l;
+    if (s > 29) return l;
     uint32_t eb, base = qz_dist_base(s, &eb);
     return QZE_LEN | (base << 8) | (eb << 4) | l;
 }
@@ -135,6 +136,7 @@ QZ_HD void qz_infl_fill_lut(const uint8_t *len, const uint16_t *count, const uin
         if (l > (uint32_t)lut_bits) continue;
         const uint32_t r = qz_bitrev((uint32_t)first[l] + (uint32_t)(i - offs[l]), l);
         const uint32_t e = is_dist ? qz_infl_d_entry(s, l) : qz_infl_ll_entry(s, l);
+        if (!(e & QZE_KIND)) continue;
         for (uint32_t k = r; k < (1u << lut_bits); k += (1u << l)) lut[k] = e;
     }
 }
@@ -155,13 +157,45 @@ QZ_HD int qz_infl_slow(uint64_t acc, const uint16_t *count, const uint16_t *firs
 enum { QZI_MATCH = 0, QZI_END_BLOCK = 1, QZI_ERR_DATA = -1, QZI_ERR_FULL = -2, QZI_ERR_TRUNC = -3 };
 
 /* Token produced by the decode loop: a literal is its table entry as is (QZE_LIT set, byte in bits 8..15),
- * a match is (len - 3) << 16 | (dist - 1) with bit 31 clear. */
+ * a match is len << 16 | dist (len 3..258, dist 1..32768) with bit 31 clear. */
 QZ_HD int qz_tok_is_literal(uint32_t t) { return (t >> 31) != 0; }
 QZ_HD uint32_t qz_tok_byte(uint32_t t) { return (t >> 8) & 0xff; }
-QZ_HD uint32_t qz_tok_len(uint32_t t) { return ((t >> 16) & 0xff) + 3; }
-QZ_HD uint32_t qz_tok_dist(uint32_t t) { return (t & 0x7fff) + 1; }
+QZ_HD uint32_t qz_tok_len(uint32_t t) { return (t >> 16) & 0x1ff; }
+QZ_HD uint32_t qz_tok_dist(uint32_t t) { return t & 0xffff; }
 
-/* the 32 bits that start `sh` (0..31) bits into lo, continuing in hi: one SHF on the device */
+/* ---- the token loop ----
+ * Turns the next symbols of the current Huffman block into at most QZ_INFL_BATCH tokens WITHOUT touching the output.  This is
+ * the serial heart of inflate (one lane per member runs it) and it is bound by instruction issue, so it is written for
+ * instruction count: the compressed words a batch can reach (32 tokens of at most 48 bits, starting less than 32 bits into
+ * the first word) are STAGED in a small window beforehand (by the whole warp on the device), and inside the loop the reader is
+ * nothing but a bit offset into that window -- a symbol's bits are two loads and a funnel shift away, consuming them is one
+ * add, and there is no refill code at all.  The output position is not stepped per literal (every token stands for at least
+ * one byte: position = adj + token count), and away from the end of the destination the room checks are compiled out. */
+#define QZ_INFL_BATCH 32
+#define QZ_INFL_INW 64                      /* staged words: bits 0 .. 31 + 32 * 48 and the word after, rounded up to two per lane */
+#define QZ_INFL_ROOMY (QZ_INFL_BATCH * 258u) /* with this much room left no batch can overflow the destination */
+
+/* where the reader stands: byte offset (from b->base) of the word that holds the next bit, and the bit's offset in that word */
+QZ_HD void qz_br_where(const QzBitReader *b, uint32_t *woff, uint32_t *sh)
+{
+    const uint32_t held = (b->nacc + 31) >> 5;                               /* words the accumulator reaches back over */
+    *sh = held * 32 - b->nacc; *woff = b->pos - 4 * held;
+}
+/* the stream's word at byte offset off from base (bytes past `end` read as zero) */
+QZ_HD uint32_t qz_word_at(const uint8_t *base, uint32_t end, uint32_t off)
+{
+    if (off + 4 <= end) return *(const uint32_t *)(base + off);
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < 4; k++) if (off + k < end) w |= (uint32_t)base[off + k] << (8 * k);
+    return w;
+}
+/* put the reader at bit lp of the window that was staged from byte offset woff */
+QZ_HD void qz_br_resume(QzBitReader *b, uint32_t woff, const uint32_t *inw, uint32_t lp)
+{
+    const uint32_t wi = lp >> 5, s = lp & 31;
+    b->acc = (uint64_t)(inw[wi] >> s); b->nacc = 32 - s; b->pos = woff + 4 * wi + 4; b->wnext = inw[wi + 1];
+}
+/* the 32 bits that start `sh` (low five bits used) bits into lo, continuing in hi: one SHF on the device */
 QZ_HD uint32_t qz_funnel(uint32_t lo, uint32_t hi, uint32_t sh)
 {
 #ifdef __CUDA_ARCH__
@@ -171,97 +205,98 @@ QZ_HD uint32_t qz_funnel(uint32_t lo, uint32_t hi, uint32_t sh)
 #endif
 }
 
-/* Turn the next symbols of the current Huffman block into at most `max_tok` tokens WITHOUT touching
- * the output; *pos is the output position before the batch and is advanced by the bytes the tokens
- * stand for.  Returns QZI_MATCH (= 0: buffer full, more to come), QZI_END_BLOCK, or an error.
- * This loop is the serial heart of inflate (one lane per member runs it), so it is written for
- * instruction count.  Inside it the reader is three consecutive input words (the third fetched one
- * word ahead of need) and a bit offset into the first: a symbol's bits are one funnel shift away and
- * consuming them is one add.  The output position is not stepped per literal: every token stands for
- * at least one byte, so the batch is cut at the room left and the position follows from the token
- * count plus what the matches added. */
-QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t max_tok, uint32_t *ntok,
-                            uint32_t *pos, uint32_t cap)
+/* CAREFUL = false needs cap - *pos >= QZ_INFL_ROOMY.  *lp: bit offset into inw, in and out.  Returns QZI_MATCH (= 0: batch
+ * full, more to come), QZI_END_BLOCK, or an error; *pos is advanced by the bytes the tokens stand for. */
+template <bool CAREFUL>
+QZ_HD int qz_inflate_tokens_core(const uint32_t *inw, uint32_t *lp_io, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
 {
     int ev = QZI_MATCH;
-    const uint32_t held = (b->nacc + 31) >> 5;                               /* words the accumulator reaches back over */
-    uint32_t sh = held * 32 - b->nacc;                                       /* bit offset of the next symbol in w0 */
-    const uint8_t *const base = b->base;
-    uint32_t woff = b->pos - 4 * held;                                       /* offset of the word being fetched */
-    const uint32_t endw = b->end & ~3u;                                      /* words below this offset lie wholly inside the input */
-#define QZI_WORD(off) ((off) < endw ? *(const uint32_t *)(base + (off)) : qz_br_word(b, (off)))
-#define QZI_ADVANCE() do { sh -= 32; w0 = w1; w1 = w2; woff += 4; w2 = QZI_WORD(woff); } while (0)
-    uint32_t w0 = QZI_WORD(woff), w1 = QZI_WORD(woff + 4), w2 = QZI_WORD(woff + 8);
-    woff += 8;                                                               /* offset w2 came from */
-    const uint32_t room = cap - *pos;
-    uint32_t nt = 0, nmax = max_tok < room ? max_tok : room;
-    uint32_t adj = *pos;                                                     /* output position = adj + nt */
+    uint32_t lp = *lp_io, nt = 0, adj = *pos, nmax = QZ_INFL_BATCH;          /* output position = adj + nt */
     const uint32_t *const ll_lut = t->ll_lut, *const d_lut = t->d_lut;
-    if (room == 0) {
-        /* the output is full: the block may still end here, anything else does not fit */
-        const uint32_t bits = qz_funnel(w0, w1, sh);
-        uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
-        if (e == 0) {
-            uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
-            e = sym < 0 ? QZE_BAD : qz_infl_ll_entry((uint32_t)sym, l);
+    if (CAREFUL) {
+        const uint32_t room = cap - adj;
+        if (room < nmax) nmax = room;
+        if (room == 0) {
+            /* the output is full: the block may still end here, anything else does not fit */
+            const uint32_t bits = qz_funnel(inw[lp >> 5], inw[(lp >> 5) + 1], lp);
+            uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
+            if (e == 0) {
+                uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
+                e = sym < 0 ? 0u : qz_infl_ll_entry((uint32_t)sym, l);
+            }
+            if (e & QZE_EOB) { lp += e & 15; ev = QZI_END_BLOCK; }
+            else ev = (e & (QZE_LIT | QZE_LEN)) ? QZI_ERR_FULL : QZI_ERR_DATA;
+            goto done;
         }
-        if (e & QZE_EOB) { sh += e & 15; if (sh >= 32) QZI_ADVANCE(); ev = QZI_END_BLOCK; }
-        else ev = (e & (QZE_LIT | QZE_LEN)) ? QZI_ERR_FULL : QZI_ERR_DATA;
-        goto done;
     }
     while (nt != nmax) {
-        uint32_t bits = qz_funnel(w0, w1, sh);
+        uint32_t wi = lp >> 5;
+        uint32_t bits = qz_funnel(inw[wi], inw[wi + 1], lp);
         uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
         if ((int32_t)e < 0) {                                /* literal */
 lit:
-            sh += e & 15;
+            lp += e & 15;
             tok[nt++] = e;
-            if (sh >= 32) QZI_ADVANCE();
             continue;
         }
-        if (e == 0) {
-            uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
-            if (sym < 0) { ev = QZI_ERR_DATA; goto done; }
-            e = qz_infl_ll_entry((uint32_t)sym, l);
-            if ((int32_t)e < 0) goto lit;
-        }
         if (!(e & QZE_LEN)) {
-            if (e & QZE_EOB) { sh += e & 15; if (sh >= 32) QZI_ADVANCE(); ev = QZI_END_BLOCK; }
-            else ev = QZI_ERR_DATA;
-            goto done;
+            /* off the fast path: a code longer than the table, the end of the block, or a symbol that must not occur */
+            if (e == 0) {
+                uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
+                if (sym < 0) { ev = QZI_ERR_DATA; goto done; }
+                e = qz_infl_ll_entry((uint32_t)sym, l);
+                if ((int32_t)e < 0) goto lit;
+            }
+            if (!(e & QZE_LEN)) {
+                if (e & QZE_EOB) { lp += e & 15; ev = QZI_END_BLOCK; }
+                else ev = QZI_ERR_DATA;
+                goto done;
+            }
         }
         {   /* length: code + extra bits, at most 20 of the 32 in hand; distance: at most 28 */
             const uint32_t cl = e & 15, eb = (e >> 4) & 15;
             const uint32_t len = ((e >> 8) & 0xffff) + ((bits >> cl) & ~(0xffffffffu << eb));
-            sh += cl + eb; if (sh >= 32) QZI_ADVANCE();
-            bits = qz_funnel(w0, w1, sh);
+            lp += cl + eb;
+            wi = lp >> 5;
+            bits = qz_funnel(inw[wi], inw[wi + 1], lp);
             uint32_t de = d_lut[bits & ((1u << QZ_D_LUT_BITS) - 1)];
-            if (de == 0) {
-                uint32_t l; const int ds = qz_infl_slow(bits, t->d_count, t->d_first, t->d_offs, t->d_sorted, QZ_D_LUT_BITS, &l);
+            if (!(de & QZE_LEN)) {
+                uint32_t l = 0; const int ds = qz_infl_slow(bits, t->d_count, t->d_first, t->d_offs, t->d_sorted, QZ_D_LUT_BITS, &l);
                 if (ds < 0) { ev = QZI_ERR_DATA; goto done; }
                 de = qz_infl_d_entry((uint32_t)ds, l);
+                if (!(de & QZE_LEN)) { ev = QZI_ERR_DATA; goto done; }
             }
-            if (de & QZE_BAD) { ev = QZI_ERR_DATA; goto done; }
             const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
             const uint32_t dist = ((de >> 8) & 0xffff) + ((bits >> dcl) & ~(0xffffffffu << deb));
-            sh += dcl + deb; if (sh >= 32) QZI_ADVANCE();
+            lp += dcl + deb;
             const uint32_t o = adj + nt;
             if (dist > o) { ev = QZI_ERR_DATA; goto done; }
-            if (len > cap - o) { ev = QZI_ERR_FULL; goto done; }      /* (o <= cap always; no 32-bit wrap) */
-            tok[nt++] = ((len - 3) << 16) | (dist - 1);
+            if (CAREFUL) { if (len > cap - o) { ev = QZI_ERR_FULL; goto done; } }      /* (o <= cap always; no 32-bit wrap) */
+            tok[nt++] = (len << 16) | dist;
             adj += len - 1;
-            const uint32_t left = cap - o - len;                     /* tokens still to come each need a byte of it */
-            if (nmax - nt > left) nmax = nt + left;
+            if (CAREFUL) {
+                const uint32_t left = cap - o - len;                 /* tokens still to come each need a byte of it */
+                if (nmax - nt > left) nmax = nt + left;
+            }
         }
     }
 done:
-#undef QZI_ADVANCE
-#undef QZI_WORD
-    b->acc = (uint64_t)(w0 >> sh); b->nacc = 32 - sh; b->pos = woff - 4; b->wnext = w1;
+    *lp_io = lp; *ntok = nt; *pos = adj + nt;
+    return ev;
+}
+
+/* the whole step on one thread (host tests; the kernel stages with all lanes and calls the core itself) */
+QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
+{
+    uint32_t inw[QZ_INFL_INW], woff, lp;
+    qz_br_where(b, &woff, &lp);
+    for (uint32_t i = 0; i < QZ_INFL_INW; i++) inw[i] = qz_word_at(b->base, b->end, woff + 4 * i);
+    int ev = cap - *pos < QZ_INFL_ROOMY ? qz_inflate_tokens_core<true>(inw, &lp, t, tok, ntok, pos, cap)
+                                        : qz_inflate_tokens_core<false>(inw, &lp, t, tok, ntok, pos, cap);
+    qz_br_resume(b, woff, inw, lp);
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
     if (ev == QZI_MATCH && qz_br_overrun(b)) ev = QZI_ERR_TRUNC;
-    *ntok = nt; *pos = adj + nt;
     return ev;
 }
 

@@ -136,7 +136,7 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
         }
         for (;;) {   // the kernel's batch loop: 32 tokens decoded without touching the output, then placed
             uint32_t tok[32], ntk = 0, pos = out;
-            int ev = qz_inflate_tokens(&br, &T, tok, 32, &ntk, &pos, cap);
+            int ev = qz_inflate_tokens(&br, &T, tok, &ntk, &pos, cap);
             for (uint32_t k = 0; k < ntk; k++) {
                 if (!qz_tok_is_literal(tok[k])) { uint32_t ml = qz_tok_len(tok[k]), md = qz_tok_dist(tok[k]);
                     for (uint32_t q = 0; q < ml; q++) dst[out + q] = dst[out - md + (md >= ml ? q : q % md)]; out += ml; }
