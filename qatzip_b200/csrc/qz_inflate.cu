@@ -21,7 +21,6 @@
 struct InflWarpSmem {
     QzInflTables t;
     uint32_t tok[QZ_INFL_BATCH];     /* one decoded batch: lane 0 fills it, every lane places one token */
-    uint32_t inw[QZ_INFL_INW];       /* the compressed words the next batch can reach, staged by the whole warp */
 };
 
 __device__ __forceinline__ uint32_t bcast(uint32_t v) { return __shfl_sync(FULL, v, 0); }
@@ -141,7 +140,7 @@ __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t l
 /* One batch of tokens goes to the output, one token per lane (t: this lane's, lanes >= n idle), the batch starting at
  * d[o0]: literals and matches whose source lies wholly before the batch go out at once, matches that read bytes produced
  * inside the batch follow in order. */
-__device__ __forceinline__ void infl_place(uint8_t *d, uint32_t o0, uint32_t n, uint32_t t, bool wr, uint32_t lane)
+__device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t n, uint32_t t, bool wr, uint32_t lane)
 {
     const bool is_match = lane < n && !qz_tok_is_literal(t);
     const uint32_t len = lane < n ? (is_match ? qz_tok_len(t) : 1u) : 0u;
@@ -173,6 +172,7 @@ __device__ __forceinline__ void infl_place(uint8_t *d, uint32_t o0, uint32_t n, 
         else { for (uint32_t k = lane; k < lj; k += 32) d[oj + k] = from[k % dj]; }
         __syncwarp();
     }
+    return __shfl_sync(FULL, incl, 31);          /* bytes the batch stands for */
 }
 
 /* The kernel.  A warp works on DPW members at once, one per SLOT: lane s * (32 / DPW) is slot s's DECODER and keeps the
@@ -184,7 +184,7 @@ __device__ __forceinline__ void infl_place(uint8_t *d, uint32_t o0, uint32_t n, 
  * whole warp, slot after slot.  One round: free slots draw members; slots between blocks read their block header; all
  * decoders fill their token buffers; the batches are placed; finished members are checked and reported. */
 #ifndef QZ_INFL_MIN_CTAS
-#define QZ_INFL_MIN_CTAS(dpw) ((dpw) == 1 ? 3 : (dpw) == 2 ? 2 : 1)
+#define QZ_INFL_MIN_CTAS(dpw) ((dpw) == 1 ? 4 : (dpw) == 2 ? 2 : 1)
 #endif
 /* The token loop as a function of its own: the compiler then allocates registers for the loop alone instead of sharing them
  * with the kernel's member state.  Window, tables and token buffer are in shared memory, which is said so that the loads stay LDS. */
@@ -316,14 +316,14 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
                 const uint32_t j = __ffs(fmask) - 1; fmask &= fmask - 1;
                 const uint8_t *base_j = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(br.base), j));
                 const uint32_t end_j = __shfl_sync(FULL, br.end, j), woff_j = __shfl_sync(FULL, woff, j);
-                uint32_t *w = slots[j / TL].inw;
+                uint32_t *w = slots[j / TL].t.stage;
 #pragma unroll
                 for (uint32_t i = lane; i < QZ_INFL_INW; i += 32) w[i] = qz_word_at(base_j, end_j, woff_j + 4 * i);
             }
             __syncwarp();
             if (dec_now) {
-                ev = infl_tokens(slots[myslot].inw, &lp, &slots[myslot].t, slots[myslot].tok, &ntk, &pos, cap);
-                qz_br_resume(&br, woff, slots[myslot].inw, lp);
+                ev = infl_tokens(slots[myslot].t.stage, &lp, &slots[myslot].t, slots[myslot].tok, &ntk, &pos, cap);
+                qz_br_resume(&br, woff, slots[myslot].t.stage, lp);
                 /* past the end of the input the window holds zero bits: see qz_inflate_tokens */
                 if (ev == QZI_MATCH && qz_br_overrun(&br)) ev = QZI_ERR_TRUNC;
             }
@@ -336,7 +336,13 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
             const uint32_t j = __ffs(pmask) - 1; pmask &= pmask - 1;
             const uint32_t n = __shfl_sync(FULL, ntk, j), o0 = __shfl_sync(FULL, out, j);
             uint8_t *d = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
-            infl_place(d, o0, n, lane < n ? slots[j / TL].tok[lane] : 0u, wr, lane);
+            uint32_t o = o0;
+#pragma unroll 1
+            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                const uint32_t n32 = min(32u, n - i0);
+                o += infl_place(d, o, n32, lane < n32 ? slots[j / TL].tok[i0 + lane] : 0u, wr, lane);
+                __syncwarp();
+            }
         }
         if (is_dec && active && in_block && !done) {
             out = pos;

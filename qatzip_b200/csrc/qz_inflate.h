@@ -30,6 +30,12 @@
 #define QZE_EOB 0x20000000u
 #define QZE_KIND (QZE_LIT | QZE_LEN | QZE_EOB)
 
+/* tokens per batch of the decode loop, and the compressed words staged for one batch (see the token loop below) */
+#ifndef QZ_INFL_BATCH
+#define QZ_INFL_BATCH 64                    /* tokens per batch: a multiple of 32 (the warp places 32 at a time) */
+#endif
+#define QZ_INFL_INW (2 * QZ_INFL_BATCH)     /* staged words: bits 0 .. 31 + BATCH * 48 and the word after, rounded up to whole lanes */
+
 struct QzInflTables {
     uint32_t ll_lut[1 << QZ_LL_LUT_BITS];
     uint32_t d_lut[1 << QZ_D_LUT_BITS];
@@ -37,7 +43,10 @@ struct QzInflTables {
     uint16_t ll_first[16], d_first[16];      /* canonical first code of each length */
     uint16_t ll_offs[16], d_offs[16];        /* index in sorted[] of the first symbol of each length */
     uint16_t ll_sorted[288], d_sorted[32];   /* symbols ordered by (length, symbol) */
-    uint8_t lens[320];                       /* code lengths read from a dynamic header (hlit, then hdist) */
+    union {
+        uint8_t lens[320];                   /* while a block's tables are built: code lengths read from its header (hlit, then hdist) */
+        uint32_t stage[QZ_INFL_INW];         /* while the block is decoded: the compressed words the next batch can reach */
+    };
 };
 
 QZ_HD uint32_t qz_infl_ll_entry(uint32_t s, uint32_t l)
@@ -171,8 +180,6 @@ QZ_HD uint32_t qz_tok_dist(uint32_t t) { return t & 0xffff; }
  * nothing but a bit offset into that window -- a symbol's bits are two loads and a funnel shift away, consuming them is one
  * add, and there is no refill code at all.  The output position is not stepped per literal (every token stands for at least
  * one byte: position = adj + token count), and away from the end of the destination the room checks are compiled out. */
-#define QZ_INFL_BATCH 32
-#define QZ_INFL_INW 64                      /* staged words: bits 0 .. 31 + 32 * 48 and the word after, rounded up to two per lane */
 #define QZ_INFL_ROOMY (QZ_INFL_BATCH * 258u) /* with this much room left no batch can overflow the destination */
 
 /* where the reader stands: byte offset (from b->base) of the word that holds the next bit, and the bit's offset in that word */

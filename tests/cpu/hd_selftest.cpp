@@ -135,7 +135,7 @@ static int inflate_all(const uint8_t *src, uint32_t n, std::vector<uint8_t> &dst
             qz_infl_fill_lut(T.lens + hlit, T.d_count, T.d_first, T.d_offs, T.d_sorted, T.d_lut, QZ_D_LUT_BITS, 1, lane, 32);
         }
         for (;;) {   // the kernel's batch loop: 32 tokens decoded without touching the output, then placed
-            uint32_t tok[32], ntk = 0, pos = out;
+            uint32_t tok[QZ_INFL_BATCH], ntk = 0, pos = out;
             int ev = qz_inflate_tokens(&br, &T, tok, &ntk, &pos, cap);
             for (uint32_t k = 0; k < ntk; k++) {
                 if (!qz_tok_is_literal(tok[k])) { uint32_t ml = qz_tok_len(tok[k]), md = qz_tok_dist(tok[k]);
