@@ -176,13 +176,16 @@ __device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t
 }
 
 /* The kernel.  A warp works on DPW members at once, one per SLOT: lane s * (32 / DPW) is slot s's DECODER and keeps the
- * member's bit reader, output position and state in its registers; every slot has its own tables and token buffer in
- * shared memory.  The serial part -- turning the bit stream into tokens, and reading a dynamic block's code lengths --
- * is the same instruction stream for all decoders, so DPW members share every one of its issue slots (with one decoder
- * per warp the kernel was bound by exactly those: 22 warp instructions per output byte at 4 of 32 lanes active).  The
- * parallel parts -- building a block's tables, placing a batch of tokens, stored blocks, the checksum -- are done by the
- * whole warp, slot after slot.  One round: free slots draw members; slots between blocks read their block header; all
- * decoders fill their token buffers; the batches are placed; finished members are checked and reported. */
+ * member's bit reader, output position and state in its registers; every slot has its own tables, staged input window
+ * and token buffer in shared memory.  One round: free slots draw members (largest first); slots between blocks read their
+ * block header (the decoder lane reads the code lengths, the warp builds the tables); the warp stages the compressed words
+ * the next batch can reach; every decoder turns them into up to 64 tokens (qz_inflate.h: the serial part, one lane);
+ * the warp places the tokens 32 at a time, checksums the 4 KiB blocks that have become complete while they are still in
+ * cache, and reports finished members.
+ * DPW = 1 is what runs (measured: the decode is bound by instruction issue and by the members in flight per SM, which the
+ * shared-memory tables fix, so several decoders per warp -- the same instruction stream for all of them, each path of a
+ * divergent step paid by everybody -- only trade warps for lanes: 53 / 45 / 29 / 20 GB/s for DPW 1 / 2 / 4 / 8; DESIGN.md
+ * section 5).  Four CTAs of eight warps per SM: 64 registers, 6.7 KB of shared memory per member. */
 #ifndef QZ_INFL_MIN_CTAS
 #define QZ_INFL_MIN_CTAS(dpw) ((dpw) == 1 ? 4 : (dpw) == 2 ? 2 : 1)
 #endif
