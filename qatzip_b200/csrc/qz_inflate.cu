@@ -137,18 +137,28 @@ __device__ uint32_t warp_adler32_global(const uint8_t *p, uint32_t n, uint32_t l
     return __shfl_sync(FULL, qz_adler_finish(s1, s2, n), 0);
 }
 
-/* One batch of tokens goes to the output, one token per lane (t: this lane's, lanes >= n idle), the batch starting at
- * d[o0]: literals and matches whose source lies wholly before the batch go out at once, matches that read bytes produced
- * inside the batch follow in order. */
-__device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t n, uint32_t t, bool wr, uint32_t lane)
+/* Thirty-two tokens go to the output, one token per lane (t: this lane's, lanes >= n idle), starting at d[o0]: literals and
+ * matches whose source lies wholly before these tokens go out at once, matches that read bytes produced by them follow in
+ * order.  Returns the bytes placed.  A distance that reaches before the start of the member's output (d[0]) ends the
+ * placing in front of its token and sets *bad_dist: the decode loop leaves that check to this side, which knows every
+ * token's position anyway. */
+__device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t n, uint32_t t, bool wr, uint32_t lane, bool *bad_dist)
 {
-    const bool is_match = lane < n && !qz_tok_is_literal(t);
-    const uint32_t len = lane < n ? (is_match ? qz_tok_len(t) : 1u) : 0u;
+    bool is_match = lane < n && !qz_tok_is_literal(t);
+    uint32_t len = lane < n ? (is_match ? qz_tok_len(t) : 1u) : 0u;
     const uint32_t dist = qz_tok_dist(t);
     uint32_t incl = len;
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, k); if (lane >= (uint32_t)k) incl += y; }
     const uint32_t o = o0 + incl - len;                          /* where this lane's token lands */
+    uint32_t placed = __shfl_sync(FULL, incl, 31);
+    const uint32_t badmask = __ballot_sync(FULL, is_match && dist > o);
+    if (badmask) {
+        const uint32_t first = __ffs(badmask) - 1;
+        placed = __shfl_sync(FULL, o, first) - o0;
+        n = first; *bad_dist = true;
+        if (lane >= first) { is_match = false; len = 0; }
+    }
     const uint32_t span = dist < len ? dist : len;               /* distinct source bytes actually read */
     const bool dep = is_match && (o - dist + span > o0);         /* reads output of this very batch */
     /* short matches that neither overlap themselves nor read this batch: the owning lane copies, all loads first */
@@ -172,7 +182,7 @@ __device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t
         else { for (uint32_t k = lane; k < lj; k += 32) d[oj + k] = from[k % dj]; }
         __syncwarp();
     }
-    return __shfl_sync(FULL, incl, 31);          /* bytes the batch stands for */
+    return placed;
 }
 
 /* The kernel.  A warp works on DPW members at once, one per SLOT: lane s * (32 / DPW) is slot s's DECODER and keeps the
@@ -335,21 +345,24 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
         /* ---- the batches are placed, slot after slot, by the whole warp: literals and matches whose source lies wholly
          * before the batch go out at once, matches that read bytes produced inside the batch follow in order ---- */
         uint32_t pmask = __ballot_sync(FULL, ntk != 0);
+        bool bad_dist = false;
         while (pmask) {
             const uint32_t j = __ffs(pmask) - 1; pmask &= pmask - 1;
             const uint32_t n = __shfl_sync(FULL, ntk, j), o0 = __shfl_sync(FULL, out, j);
             uint8_t *d = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
-            uint32_t o = o0;
+            uint32_t o = o0; bool bad = false;
 #pragma unroll 1
-            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            for (uint32_t i0 = 0; i0 < n && !bad; i0 += 32) {
                 const uint32_t n32 = min(32u, n - i0);
-                o += infl_place(d, o, n32, lane < n32 ? slots[j / TL].tok[i0 + lane] : 0u, wr, lane);
+                o += infl_place(d, o, n32, lane < n32 ? slots[j / TL].tok[i0 + lane] : 0u, wr, lane, &bad);
                 __syncwarp();
             }
+            if (lane == j) { pos = o; bad_dist = bad; }          /* the output position after the batch, whichever loop decoded it */
         }
         if (is_dec && active && in_block && !done) {
             out = pos;
-            if (ev == QZI_END_BLOCK) { in_block = false; if (bfinal) done = true; }
+            if (bad_dist) { status = QZB_ST_DATA_ERROR; done = true; }
+            else if (ev == QZI_END_BLOCK) { in_block = false; if (bfinal) done = true; }
             else if (ev == QZI_ERR_DATA) { status = QZB_ST_DATA_ERROR; done = true; }
             else if (ev == QZI_ERR_FULL) { status = QZB_ST_OUT_FULL; done = true; }
             else if (ev == QZI_ERR_TRUNC) { status = QZB_ST_IN_TRUNC; done = true; }

@@ -19,16 +19,23 @@
 #define QZ_D_LUT_BITS 8      /* at least 7: the code-length alphabet's table borrows 128 entries */
 #endif
 
-/* Decode-table entry:
- *   bits 0..3   code length (1..15); an all-zero entry = code longer than the table, unused, or a symbol that must not occur
- *   bits 4..7   number of extra bits that follow the code
- *   bits 8..23  literal byte, or length base 3..258, or distance base 1..24577
- *   bits 29..31 kind; an entry function's answer with no kind bit set = symbol that must not occur (lit/len 286, 287;
- *               distance 30, 31): such symbols are left out of the table, so the decode loop meets them on its slow path only */
+/* Decode-table entry, laid out for the token loop's instruction count:
+ *   bits 0..4   code length (1..15): a shift by the whole entry (funnel shift: low five bits) skips the code
+ *   bit  5      QZE_LEN: a length or a distance symbol;  bit 6  QZE_EOB: end of block
+ *   bits 8..12  code length + number of extra bits (lengths, distances): what the symbol consumes in all, a byte of its own;
+ *               bits 8..15 of a literal entry hold the literal byte instead
+ *   bits 16..30 length base 3..258 or distance base 1..24577: entry >> 16
+ *   bit  31     QZE_LIT: a literal (the sign bit)
+ * An all-zero table entry = code longer than the table, or unused.  An entry function's answer with no kind bit set = a symbol
+ * that must not occur (lit/len 286, 287; distance 30, 31): such symbols are left out of the table, so the decode loop meets
+ * them on its slow path only. */
 #define QZE_LIT 0x80000000u
-#define QZE_LEN 0x40000000u      /* also marks a valid distance entry */
-#define QZE_EOB 0x20000000u
+#define QZE_LEN 0x00000020u      /* also marks a valid distance entry */
+#define QZE_EOB 0x00000040u
 #define QZE_KIND (QZE_LIT | QZE_LEN | QZE_EOB)
+#define QZE_CODE_BITS(e) ((e) & 31u)
+#define QZE_ALL_BITS(e) (((e) >> 8) & 0xffu)
+#define QZE_BASE(e) ((e) >> 16)
 
 /* tokens per batch of the decode loop, and the compressed words staged for one batch (see the token loop below) */
 #ifndef QZ_INFL_BATCH
@@ -55,13 +62,13 @@ QZ_HD uint32_t qz_infl_ll_entry(uint32_t s, uint32_t l)
     if (s == 256) return QZE_EOB | l;
     if (s > 285) return l;
     uint32_t eb, base = qz_len_base(s - 257, &eb);
-    return QZE_LEN | (base << 8) | (eb << 4) | l;
+    return QZE_LEN | (base << 16) | ((l + eb) << 8) | l;
 }
 QZ_HD uint32_t qz_infl_d_entry(uint32_t s, uint32_t l)
 {
     if (s > 29) return l;
     uint32_t eb, base = qz_dist_base(s, &eb);
-    return QZE_LEN | (base << 8) | (eb << 4) | l;
+    return QZE_LEN | (base << 16) | ((l + eb) << 8) | l;
 }
 
 /* LSB-first bit reader.  Input is fetched as aligned 32-bit words, one word ahead of need (wnext),
@@ -212,13 +219,28 @@ QZ_HD uint32_t qz_funnel(uint32_t lo, uint32_t hi, uint32_t sh)
 #endif
 }
 
-/* CAREFUL = false needs cap - *pos >= QZ_INFL_ROOMY.  *lp: bit offset into inw, in and out.  Returns QZI_MATCH (= 0: batch
- * full, more to come), QZI_END_BLOCK, or an error; *pos is advanced by the bytes the tokens stand for. */
+/* the value of a length or distance symbol: base + the extra bits that follow its code in `bits` */
+QZ_HD uint32_t qz_sym_value(uint32_t e, uint32_t bits, uint32_t all)
+{
+    const uint32_t field = bits & ~(0xffffffffu << all);         /* code and extra bits (all <= 28) */
+#ifdef __CUDA_ARCH__
+    return QZE_BASE(e) + __funnelshift_r(field, 0u, e);          /* the shift takes the entry's low five bits: the code length */
+#else
+    return QZE_BASE(e) + (field >> QZE_CODE_BITS(e));
+#endif
+}
+
+/* CAREFUL = true: the destination may fill up in this batch -- every token is checked against the room left and against the
+ * output position (a distance must not reach before the start), *pos is advanced by the bytes the tokens stand for.
+ * CAREFUL = false needs cap - *pos >= QZ_INFL_ROOMY: no batch can overflow, so the loop does not follow the output position at
+ * all; *pos is left alone, and the distances are checked against the positions when the tokens are placed (the placing side
+ * computes every token's position anyway).  *lp: bit offset into inw, in and out.  Returns QZI_MATCH (= 0: batch full, more
+ * to come), QZI_END_BLOCK, or an error. */
 template <bool CAREFUL>
 QZ_HD int qz_inflate_tokens_core(const uint32_t *inw, uint32_t *lp_io, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
 {
     int ev = QZI_MATCH;
-    uint32_t lp = *lp_io, nt = 0, adj = *pos, nmax = QZ_INFL_BATCH;          /* output position = adj + nt */
+    uint32_t lp = *lp_io, nt = 0, adj = *pos, nmax = QZ_INFL_BATCH;          /* CAREFUL: output position = adj + nt */
     const uint32_t *const ll_lut = t->ll_lut, *const d_lut = t->d_lut;
     if (CAREFUL) {
         const uint32_t room = cap - adj;
@@ -231,8 +253,8 @@ QZ_HD int qz_inflate_tokens_core(const uint32_t *inw, uint32_t *lp_io, const QzI
                 uint32_t l; const int sym = qz_infl_slow(bits, t->ll_count, t->ll_first, t->ll_offs, t->ll_sorted, QZ_LL_LUT_BITS, &l);
                 e = sym < 0 ? 0u : qz_infl_ll_entry((uint32_t)sym, l);
             }
-            if (e & QZE_EOB) { lp += e & 15; ev = QZI_END_BLOCK; }
-            else ev = (e & (QZE_LIT | QZE_LEN)) ? QZI_ERR_FULL : QZI_ERR_DATA;
+            if ((int32_t)e >= 0 && (e & QZE_EOB)) { lp += QZE_CODE_BITS(e); ev = QZI_END_BLOCK; }
+            else ev = ((int32_t)e < 0 || (e & QZE_LEN)) ? QZI_ERR_FULL : QZI_ERR_DATA;
             goto done;
         }
     }
@@ -242,7 +264,7 @@ QZ_HD int qz_inflate_tokens_core(const uint32_t *inw, uint32_t *lp_io, const QzI
         uint32_t e = ll_lut[bits & ((1u << QZ_LL_LUT_BITS) - 1)];
         if ((int32_t)e < 0) {                                /* literal */
 lit:
-            lp += e & 15;
+            lp += QZE_CODE_BITS(e);
             tok[nt++] = e;
             continue;
         }
@@ -255,15 +277,15 @@ lit:
                 if ((int32_t)e < 0) goto lit;
             }
             if (!(e & QZE_LEN)) {
-                if (e & QZE_EOB) { lp += e & 15; ev = QZI_END_BLOCK; }
+                if (e & QZE_EOB) { lp += QZE_CODE_BITS(e); ev = QZI_END_BLOCK; }
                 else ev = QZI_ERR_DATA;
                 goto done;
             }
         }
         {   /* length: code + extra bits, at most 20 of the 32 in hand; distance: at most 28 */
-            const uint32_t cl = e & 15, eb = (e >> 4) & 15;
-            const uint32_t len = ((e >> 8) & 0xffff) + ((bits >> cl) & ~(0xffffffffu << eb));
-            lp += cl + eb;
+            const uint32_t all = QZE_ALL_BITS(e);
+            const uint32_t len = qz_sym_value(e, bits, all);
+            lp += all;
             wi = lp >> 5;
             bits = qz_funnel(inw[wi], inw[wi + 1], lp);
             uint32_t de = d_lut[bits & ((1u << QZ_D_LUT_BITS) - 1)];
@@ -273,33 +295,44 @@ lit:
                 de = qz_infl_d_entry((uint32_t)ds, l);
                 if (!(de & QZE_LEN)) { ev = QZI_ERR_DATA; goto done; }
             }
-            const uint32_t dcl = de & 15, deb = (de >> 4) & 15;
-            const uint32_t dist = ((de >> 8) & 0xffff) + ((bits >> dcl) & ~(0xffffffffu << deb));
-            lp += dcl + deb;
-            const uint32_t o = adj + nt;
-            if (dist > o) { ev = QZI_ERR_DATA; goto done; }
-            if (CAREFUL) { if (len > cap - o) { ev = QZI_ERR_FULL; goto done; } }      /* (o <= cap always; no 32-bit wrap) */
-            tok[nt++] = (len << 16) | dist;
-            adj += len - 1;
+            const uint32_t dall = QZE_ALL_BITS(de);
+            const uint32_t dist = qz_sym_value(de, bits, dall);
+            lp += dall;
             if (CAREFUL) {
+                const uint32_t o = adj + nt;
+                if (dist > o) { ev = QZI_ERR_DATA; goto done; }
+                if (len > cap - o) { ev = QZI_ERR_FULL; goto done; }      /* (o <= cap always; no 32-bit wrap) */
+                adj += len - 1;
                 const uint32_t left = cap - o - len;                 /* tokens still to come each need a byte of it */
-                if (nmax - nt > left) nmax = nt + left;
+                if (nmax - (nt + 1) > left) nmax = nt + 1 + left;
             }
+            tok[nt++] = (len << 16) | dist;
         }
     }
 done:
-    *lp_io = lp; *ntok = nt; *pos = adj + nt;
+    *lp_io = lp; *ntok = nt;
+    if (CAREFUL) *pos = adj + nt;
     return ev;
 }
 
-/* the whole step on one thread (host tests; the kernel stages with all lanes and calls the core itself) */
+/* the whole step on one thread (host tests; the kernel stages with all lanes, calls the core itself and learns the new
+ * output position from placing the tokens) */
 QZ_HD int qz_inflate_tokens(QzBitReader *b, const QzInflTables *t, uint32_t *tok, uint32_t *ntok, uint32_t *pos, uint32_t cap)
 {
     uint32_t inw[QZ_INFL_INW], woff, lp;
     qz_br_where(b, &woff, &lp);
     for (uint32_t i = 0; i < QZ_INFL_INW; i++) inw[i] = qz_word_at(b->base, b->end, woff + 4 * i);
-    int ev = cap - *pos < QZ_INFL_ROOMY ? qz_inflate_tokens_core<true>(inw, &lp, t, tok, ntok, pos, cap)
-                                        : qz_inflate_tokens_core<false>(inw, &lp, t, tok, ntok, pos, cap);
+    int ev;
+    if (cap - *pos < QZ_INFL_ROOMY) ev = qz_inflate_tokens_core<true>(inw, &lp, t, tok, ntok, pos, cap);
+    else {
+        ev = qz_inflate_tokens_core<false>(inw, &lp, t, tok, ntok, pos, cap);
+        uint32_t o = *pos;
+        for (uint32_t k = 0; k < *ntok; k++) {
+            if (qz_tok_is_literal(tok[k])) o++;
+            else { if (qz_tok_dist(tok[k]) > o) { *ntok = k; ev = QZI_ERR_DATA; break; } o += qz_tok_len(tok[k]); }
+        }
+        *pos = o;
+    }
     qz_br_resume(b, woff, inw, lp);
     /* Past the end of the input the reader supplies zero bits; a code table in which the all-zero
      * code is a length symbol would turn those into tokens for ever.  Once per batch is enough. */
