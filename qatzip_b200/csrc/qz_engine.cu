@@ -36,6 +36,7 @@ extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, 
 extern "C" size_t qzb_inflate_smem_bytes(int dpw);
 extern "C" int qzb_inflate_cta_threads(int dpw);
 extern "C" int qzb_inflate_cta_slots(int dpw);
+extern "C" cudaError_t qzb_launch_gzip_scan(const uint8_t *p, uint64_t lo, uint64_t n, uint32_t *list, uint32_t cap, uint32_t *count, int grid, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_compress(const QzbCompressJob *job, int grid, int warps, cudaStream_t st);
 extern "C" cudaError_t qzb_launch_lz4_decompress(const QzbDecompressJob *job, int grid, cudaStream_t st);
 extern "C" size_t qzb_deflate_smem_bytes(int piece_log2, int hb, int warps, int nbuf);
@@ -875,7 +876,37 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     /* next member by magic scan, footer right before it: reference src/qatzip_gzip.c:244-261.
                      * The guess is verified by the decode (exact length, ISIZE, CRC) and replaced by a
                      * sequential decode of this member if it does not hold. */
-                    if (!gz_scanned) { gzip_scan_candidates(hsrc, in, c->src_len, gz_cand); gz_scanned = true; }
+                    if (!gz_scanned) {
+                        const double t0 = e->timeline ? host_ms() : 0.0;
+                        bool on_device = false;
+                        if (c->src_device && c->src_len - in < 0xffffffffull) {
+                            /* the compressed bytes are in device memory: scan them there (a gigabyte in well under a
+                             * millisecond; the host needs ~10 ms on sixteen threads), bring the offsets back and sort them */
+                            Slot &s0 = e->slot[0];
+                            const uint64_t span = c->src_len - in;
+                            const uint32_t lcap = (uint32_t)std::min<uint64_t>(span / 256 + 65536, 0x3fffffffu);
+                            if (s0.d_meta.ensure(16 + (size_t)lcap * 4) == RC_OK && s0.h_meta.ensure(16) == RC_OK) {
+                                uint32_t *d_count = (uint32_t *)s0.d_meta.p, *d_list = d_count + 4;
+                                CK(cudaMemsetAsync(d_count, 0, 16, s0.st));
+                                CK(qzb_launch_gzip_scan(c->src, in, c->src_len, d_list, lcap, d_count, e->sm_count * 8, s0.st));
+                                CK(cudaMemcpyAsync(s0.h_meta.p, d_count, 4, cudaMemcpyDeviceToHost, s0.st));
+                                CK(cudaStreamSynchronize(s0.st));
+                                const uint32_t found = *(const uint32_t *)s0.h_meta.p;
+                                if (found <= lcap && s0.h_meta.ensure(16 + (size_t)found * 4) == RC_OK) {
+                                    if (found) { CK(cudaMemcpyAsync((uint8_t *)s0.h_meta.p + 16, d_list, (size_t)found * 4, cudaMemcpyDeviceToHost, s0.st)); CK(cudaStreamSynchronize(s0.st)); }
+                                    const uint32_t *hl = (const uint32_t *)((const uint8_t *)s0.h_meta.p + 16);
+                                    gz_cand.resize(found);
+                                    for (uint32_t i = 0; i < found; i++) gz_cand[i] = in + hl[i];
+                                    std::sort(gz_cand.begin(), gz_cand.end());
+                                    on_device = true;
+                                }
+                            }
+                        }
+                        if (!on_device) gzip_scan_candidates(hsrc, in, c->src_len, gz_cand);
+                        gz_scanned = true;
+                        if (e->timeline) fprintf(stderr, "[qzb timeline] inflate: member scan of %.1f MiB (%s): %.2f ms, %zu candidates\n", (double)(c->src_len - in) / 1048576.0,
+                                                 on_device ? "device" : "host", host_ms() - t0, gz_cand.size());
+                    }
                     /* first candidate that leaves room for this member's footer and has a believable ISIZE in front */
                     uint64_t q = 0; bool found = false;
                     for (auto it = std::lower_bound(gz_cand.begin(), gz_cand.end(), in + (uint64_t)h + 8); it != gz_cand.end(); ++it) {
@@ -954,6 +985,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
         }
         if (units.empty()) { final_rc = parse_rc; break; }
 
+        if (e->timeline) fprintf(stderr, "[qzb timeline] inflate: %zu units parsed @%.2f ms\n", units.size(), host_ms());
         /* ---- pass 2 (device) ---- */
         const bool all_sized = std::all_of(units.begin(), units.end(), [](const ParsedMember &u) { return u.sized; });
         int rc2 = RC_OK; long failed_unit = -1;
@@ -1010,6 +1042,7 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                 if (stop) break;
                 Slot &s = e->slot[issued % NS];
                 if (run(s, i, j - i, units[i].unit_start, sin, units[i].m.dst_off, sout, false) != RC_OK) return RC_FAIL;
+                if (e->timeline) fprintf(stderr, "[qzb timeline] inflate: batch of %zu issued @%.2f ms\n", j - i, host_ms());
                 issued++; i = j;
                 if (issued - next_drain >= (size_t)NS) { if (drain(e->slot[next_drain % NS]) != RC_OK) return RC_FAIL; next_drain++; }
             }

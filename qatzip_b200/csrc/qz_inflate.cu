@@ -420,6 +420,21 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
     }
 }
 
+/* Positions in p[lo, n) that look like the start of a gzip member -- the same test as the host's gzip_member_start()
+ * (qz_engine.cu; reference: one linear scan per member, src/qatzip_gzip.c:244-261) -- for calls whose compressed bytes are
+ * already in device memory: the whole input at HBM speed instead of at the host's.  Offsets relative to lo, unordered. */
+__global__ void qzb_gzip_scan_kernel(const uint8_t *p, uint64_t lo, uint64_t n, uint32_t *list, uint32_t cap, uint32_t *count)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q + 10 <= n; q += stride) {
+        if (p[q] != 0x1f || p[q + 1] != 0x8b) continue;
+        if (p[q + 2] == 8 && (p[q + 3] & 0xe0) == 0 && (p[q + 8] == 0 || p[q + 8] == 2 || p[q + 8] == 4) && (p[q + 9] <= 13 || p[q + 9] == 255)) {
+            const uint32_t i = atomicAdd(count, 1u);
+            if (i < cap) list[i] = (uint32_t)(q - lo);
+        }
+    }
+}
+
 #ifndef QZ_WARP_EMU
 /* decoders per warp (1, 2, 4 or 8); a CTA is 8 warps (4 with eight decoders per warp: 32 slots fill the shared memory) */
 static int inflate_cta_warps(int dpw) { return dpw == 8 ? 4 : 8; }
@@ -433,6 +448,11 @@ static cudaError_t launch_inflate(const QzbDecompressJob &job, int grid, cudaStr
     cudaError_t e = cudaFuncSetAttribute(qzb_inflate_kernel<DPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     qzb_inflate_kernel<DPW><<<grid, inflate_cta_warps(DPW) * 32, smem, st>>>(job);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t qzb_launch_gzip_scan(const uint8_t *p, uint64_t lo, uint64_t n, uint32_t *list, uint32_t cap, uint32_t *count, int grid, cudaStream_t st)
+{
+    qzb_gzip_scan_kernel<<<grid, 256, 0, st>>>(p, lo, n, list, cap, count);
     return cudaGetLastError();
 }
 extern "C" cudaError_t qzb_launch_inflate(const QzbDecompressJob *job, int dpw, int grid, cudaStream_t st)
