@@ -711,8 +711,11 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
             for (size_t i = 0; i < count; i++) { lo = std::min(lo, hm[i].src_len); hi = std::max(hi, hm[i].src_len); }
             if (hi > 2 * (uint64_t)lo) {
                 uint32_t *ord = (uint32_t *)((uint8_t *)s.h_members.p + order_off);
-                for (size_t i = 0; i < count; i++) ord[i] = (uint32_t)i;
-                std::stable_sort(ord, ord + count, [&](uint32_t a, uint32_t b) { return hm[a].src_len > hm[b].src_len; });
+                /* longest payload first, equal lengths in member order: one sort over (inverted length, index) keys */
+                std::vector<uint64_t> keys(count);
+                for (size_t i = 0; i < count; i++) keys[i] = (uint64_t)(0xffffffffu - hm[i].src_len) << 32 | (uint32_t)i;
+                std::sort(keys.begin(), keys.end());
+                for (size_t i = 0; i < count; i++) ord[i] = (uint32_t)keys[i];
                 ordered = true;
             }
         }
@@ -894,10 +897,10 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                                 const uint32_t found = *(const uint32_t *)s0.h_meta.p;
                                 if (found <= lcap && s0.h_meta.ensure(16 + (size_t)found * 4) == RC_OK) {
                                     if (found) { CK(cudaMemcpyAsync((uint8_t *)s0.h_meta.p + 16, d_list, (size_t)found * 4, cudaMemcpyDeviceToHost, s0.st)); CK(cudaStreamSynchronize(s0.st)); }
-                                    const uint32_t *hl = (const uint32_t *)((const uint8_t *)s0.h_meta.p + 16);
+                                    uint32_t *hl = (uint32_t *)((uint8_t *)s0.h_meta.p + 16);
+                                    std::sort(hl, hl + found);
                                     gz_cand.resize(found);
                                     for (uint32_t i = 0; i < found; i++) gz_cand[i] = in + hl[i];
-                                    std::sort(gz_cand.begin(), gz_cand.end());
                                     on_device = true;
                                 }
                             }
@@ -909,7 +912,11 @@ extern "C" int qzb_engine_decompress(QzbEngine *e, const QzbDecompressCall *c, Q
                     }
                     /* first candidate that leaves room for this member's footer and has a believable ISIZE in front */
                     uint64_t q = 0; bool found = false;
-                    for (auto it = std::lower_bound(gz_cand.begin(), gz_cand.end(), in + (uint64_t)h + 8); it != gz_cand.end(); ++it) {
+                    auto it0 = std::lower_bound(gz_cand.begin(), gz_cand.end(), in + (uint64_t)h + 8);
+                    /* the walk reads one header and one footer per member, each a cache miss on the host view: ask for the
+                     * ones a few members ahead now */
+                    if (gz_cand.end() - it0 > 6) { const uint8_t *pf = hsrc + *(it0 + 6); __builtin_prefetch(pf - 8); __builtin_prefetch(pf + 24); }
+                    for (auto it = it0; it != gz_cand.end(); ++it) {
                         q = *it - in;
                         if ((uint64_t)rd32(p + q - 4) <= (q - h - 8) * 1032 + 64) { found = true; break; }
                     }
