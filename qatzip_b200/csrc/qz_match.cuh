@@ -242,9 +242,11 @@ __device__ __forceinline__ void qzm_match_piece(const uint8_t *win, uint32_t n, 
         }
         entry = leave - 32;
     };
+    /* tiles at or below this base are interior: no match of theirs can reach a limit (one compare per tile instead of three) */
+    const int interior = min(min((int)mend - 32 - (int)QZM_LANE_CAP, (int)n - 35), (int)mstart_lim - 31);
     for (uint32_t base = p0; base < p1; base += 32) {
         if (entry >= 32) { entry -= 32; continue; }      /* tile lies inside a running match: nothing to code, not indexed */
-        if (base + 32 + QZM_LANE_CAP <= mend && base + 35 <= n && base + 31 <= mstart_lim) tile(base, std::false_type());
+        if ((int)base <= interior) tile(base, std::false_type());
         else tile(base, std::true_type());
     }
     __syncwarp();
