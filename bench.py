@@ -118,7 +118,30 @@ def cpu_reference_pass(lib_path, host_addr, nbytes, threads):
     return dt, sum(outs), threads
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line: whatever libraries print there meanwhile (NCCL's version banner at the first
+    collective, for one) goes to stderr instead"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -157,7 +180,7 @@ def main():
                 times.append(dt)
         dt = sum(times) / len(times)
         v = sample / dt / GB
-        print(json.dumps({"impl": "reference", "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(v, 4), "unit": "GB/s",
+        _emit(({"impl": "reference", "metric": "qzCompress GB/s (input) at 64 KiB chunks", "value": round(v, 4), "unit": "GB/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                           "config": config,
@@ -351,7 +374,7 @@ def main():
                     secondary[name] = {"error": repr(e)}
     if rank == 0:
         line["secondary"] = secondary
-        print(json.dumps(line))
+        _emit(line)
     if dist:
         dist.destroy_process_group()
     return 0
