@@ -120,10 +120,11 @@ extern "C" void qzb_get_tuning(QzbTuning *t)
     if (mb > 1024) mb = 1024;
     t->batch_bytes = (size_t)mb << 20;
     /* Decompress batches (compressed bytes per launch, host-memory calls).  A launch lasts at least as long as its longest
-     * member takes one warp (a 256 KiB member: ~30 ms), so the bytes in flight -- four batches -- have to cover that time at
-     * the kernel's rate: 4 x 128 MiB of input is ~1.2 GiB of output (measured: 12.5 GB/s with 64 MiB batches on mixed
-     * 4-256 KiB members) */
-    int imb = env_int("QZB200_INFLATE_BATCH_MB", 128);
+     * member takes one warp (a 256 KiB member: ~25 ms), so the bytes in flight -- four batches -- have to cover that time at
+     * the kernel's rate.  Measured on mixed 4-256 KiB members, a 4 GiB call: 64 MiB batches 12.5 GB/s, 128 MiB 23-24,
+     * 256 MiB 28.1, 512 MiB 28.6 (device buffers grow with the batch: 256 MiB in + up to 1 GiB out per slot, only for calls
+     * that large) */
+    int imb = env_int("QZB200_INFLATE_BATCH_MB", 256);
     if (imb < 1) imb = 1;
     if (imb > 1024) imb = 1024;
     t->inflate_batch_bytes = (size_t)imb << 20;
