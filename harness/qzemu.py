@@ -43,6 +43,7 @@ class Emu:
         L.emu_lz4_window.restype = C.c_long
         L.emu_lz4_window.argtypes = [V, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, V, C.c_uint64, V]
         L.emu_inflate.argtypes = [C.c_int, V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int, C.c_int]
+        L.emu_gzip_scan.argtypes = [V, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.c_int]
         L.emu_lz4_decompress.argtypes = [V, V, C.POINTER(Member), C.POINTER(MemberResult), C.c_uint32, C.c_int]
 
     def deflate(self, data, fmt=FMT_GZIP_EXT, chunk=65536, last=1, static=0, piece_log2=13, hb=11, warps=4, nbuf=3, grid=2, cap=None, window=0):
@@ -79,6 +80,13 @@ class Emu:
         n = self.lib.emu_lz4_window(data, len(data), chunk, tent, nw, grid, dst, cap, ck)
         assert n >= 0
         return dst.raw[:n], list(ck)
+
+    def gzip_scan(self, src, lo=0, cap=4096, grid=3):
+        """offsets (absolute, sorted) of plausible gzip member starts in src[lo:], and the number found"""
+        src = bytes(src)
+        lst = (C.c_uint32 * cap)()
+        found = self.lib.emu_gzip_scan(src + b"\0" * 16, lo, len(src), lst, cap, grid)
+        return sorted(lo + lst[i] for i in range(min(found, cap))), found
 
     def decode(self, fmt, src, members, out_len, size_only=0, grid=2):
         """members: list of dicts with Member's fields -> (output bytes, [MemberResult])"""

@@ -20,3 +20,12 @@ extern "C" int emu_inflate(int fmt, const uint8_t *src, uint8_t *dst, const QzbM
     else emu::launch(g, 256, sizeof(InflWarpSmem) * 32, [&] { qzb_inflate_kernel<4>(job); });
     return 0;
 }
+
+/* qzb_gzip_scan_kernel over src[lo, n): offsets (relative to lo) of plausible gzip member starts, unordered; returns how many
+ * were found (more than cap: the list is cut, the count is not) */
+extern "C" int emu_gzip_scan(const uint8_t *src, uint64_t lo, uint64_t n, uint32_t *list, uint32_t cap, int grid)
+{
+    uint32_t count = 0;
+    emu::launch((unsigned)(grid < 1 ? 1 : grid), 256, 0, [&] { qzb_gzip_scan_kernel(src, lo, n, list, cap, &count); });
+    return (int)count;
+}

@@ -455,3 +455,23 @@ def test_window_deeper_search_for_higher_levels(emu, port):
         assert cks == [zlib.crc32(data[i:i + 65536]) for i in range(0, len(data), 65536)]
         if data is text:
             assert len(two) < len(one)
+
+
+def test_gzip_member_scan_kernel(emu):
+    """the device-side scan for member starts (device-resident decompress of plain gzip) against the host's predicate
+    (qz_engine.cu gzip_member_start): magic, method, reserved flag bits clear, XFL in {0, 2, 4}, OS <= 13 or 255"""
+    import gzip, random
+    rng = random.Random(5)
+    def plausible(p, q):
+        return (q + 10 <= len(p) and p[q] == 0x1f and p[q + 1] == 0x8b and p[q + 2] == 8 and (p[q + 3] & 0xe0) == 0 and
+                p[q + 8] in (0, 2, 4) and (p[q + 9] <= 13 or p[q + 9] == 255))
+    members = [gzip.compress(sil(rng.randrange(1, 40000)), 1) for _ in range(9)]
+    decoys = [bytes([0x1f, 0x8b, 8, 0xe0, 0, 0, 0, 0, 0, 3]), bytes([0x1f, 0x8b, 9, 0, 0, 0, 0, 0, 0, 3]), bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 1, 3]),
+              bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 4, 255]), bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 14]), bytes([0x1f, 0x8b, 8])]
+    blob = b"".join(m + rng.choice(decoys) for m in members) + bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0])      # a header cut short at the end
+    for lo in (0, 1, len(members[0]) + 3):
+        want = [q for q in range(lo, len(blob)) if plausible(blob, q)]
+        got, found = emu.gzip_scan(blob, lo=lo)
+        assert found == len(want) and got == want
+    got, found = emu.gzip_scan(blob, cap=2)          # a list that is too short is cut, the count still says so
+    assert found == len([q for q in range(len(blob)) if plausible(blob, q)]) and len(got) == 2
