@@ -90,9 +90,9 @@ __device__ uint32_t warp_crc32_global(const uint8_t *p, uint32_t n, const uint32
     return __shfl_sync(FULL, c, 0);
 }
 
-/* CRC-32 of the 4 KiB at p by the whole warp: 128 bytes per lane, the tree's multipliers x^(8 * 128 * 2^k) in xk[0..5) */
+/* CRC-32 of the 4 KiB at p by the whole warp: 128 bytes per lane; xl[lane] = x^(8 * 128 * (31 - lane)) */
 #define QZ_INFL_CRC_BLOCK 4096u
-__device__ __forceinline__ uint32_t warp_crc32_block(const uint8_t *p, const uint32_t *crc_tab, const uint32_t *xk, uint32_t lane)
+__device__ __forceinline__ uint32_t warp_crc32_block(const uint8_t *p, const uint32_t *crc_tab, const uint32_t *xl, uint32_t lane)
 {
     const uint4 *q = reinterpret_cast<const uint4 *>(p + lane * 128);
     uint32_t c = 0xffffffffu;
@@ -112,12 +112,8 @@ __device__ __forceinline__ uint32_t warp_crc32_block(const uint8_t *p, const uin
         for (int i = 0; i < 128; i++) c = crc_tab[(c ^ b[i]) & 0xff] ^ (c >> 8);
     }
     c = ~c;
-#pragma unroll 1
-    for (int lv = 0; lv < 5; lv++) {
-        const uint32_t other = __shfl_down_sync(FULL, c, 1u << lv);
-        if ((lane & ((2u << lv) - 1)) == 0) c = qz_gf2_mul(c, xk[lv]) ^ other;
-    }
-    return __shfl_sync(FULL, c, 0);
+    /* crc(block) = xor over lanes of crc(lane's 128 bytes) * x^(8 * 128 * (31 - lane)): one multiply per lane, all at once */
+    return __reduce_xor_sync(FULL, lane == 31 ? c : qz_gf2_mul(c, xl[lane]));
 }
 
 /* Adler-32 of dst[0..n) by the whole warp: same strips, sums joined as in qz_adler32.h */
@@ -168,7 +164,14 @@ __device__ __forceinline__ uint32_t infl_place(uint8_t *d, uint32_t o0, uint32_t
         const uint32_t steps = __reduce_max_sync(FULL, lane_copy ? len : 0u);
         if (lane < n && !is_match) d[o] = (uint8_t)qz_tok_byte(t);
         const uint8_t *from = d + o - dist;
-        for (uint32_t k = 0; k < steps; k++) if (lane_copy && k < len) d[o + k] = from[k];
+        for (uint32_t k = 0; k < steps; k += 2) {                /* two bytes a step: half the loop's own instructions */
+            const bool c0 = lane_copy && k < len, c1 = lane_copy && k + 1 < len;
+            uint8_t v0 = 0, v1 = 0;
+            if (c0) v0 = from[k];
+            if (c1) v1 = from[k + 1];
+            if (c0) d[o + k] = v0;
+            if (c1) d[o + k + 1] = v1;
+        }
     }
     /* the rest (long, self-overlapping, or fed by this batch) go in order, copied by the whole warp */
     uint32_t depmask = wr ? __ballot_sync(FULL, is_match && !lane_copy) : 0u;
@@ -219,10 +222,10 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
     QZ_DYN_SMEM(smem_raw);
     InflWarpSmem *s_w = reinterpret_cast<InflWarpSmem *>(smem_raw);
     __shared__ uint32_t s_crc_tab[256];
-    __shared__ uint32_t s_xk[6];            /* x^(8 * 128 * 2^k), k < 5: the block checksum's tree; [5] = x^(8 * 4096): the fold */
+    __shared__ uint32_t s_xl[33];           /* [lane] = x^(8 * 128 * (31 - lane)): the block checksum's lane multipliers; [32] = x^(8 * 4096): the fold */
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_crc_tab[i] = qz_crc_table_entry(i);
-    if (threadIdx.x < 6) s_xk[threadIdx.x] = qz_crc_xpow8((uint64_t)128 << threadIdx.x);
+    if (threadIdx.x < 33) s_xl[threadIdx.x] = qz_crc_xpow8(threadIdx.x == 32 ? 4096u : 128u * (31u - threadIdx.x));
     __syncthreads();
     InflWarpSmem *slots = s_w + (size_t)warp * DPW;
     const bool crc_blocks = !job.size_only && job.fmt != QZB_FMT_ZLIB;       /* CRC-32 taken 4 KiB at a time while the output is still in cache */
@@ -377,8 +380,8 @@ __global__ void __launch_bounds__(256, QZ_INFL_MIN_CTAS(DPW)) qzb_inflate_kernel
                 const uint32_t from = __shfl_sync(FULL, crc_done, j);
                 const uint8_t *d = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, reinterpret_cast<uintptr_t>(dst), j));
                 __syncwarp();
-                const uint32_t cb = warp_crc32_block(d + from, s_crc_tab, s_xk, lane);
-                if (lane == j) { crc_run = qz_gf2_mul(crc_run, s_xk[5]) ^ cb; crc_done += QZ_INFL_CRC_BLOCK; }
+                const uint32_t cb = warp_crc32_block(d + from, s_crc_tab, s_xl, lane);
+                if (lane == j) { crc_run = qz_gf2_mul(crc_run, s_xl[32]) ^ cb; crc_done += QZ_INFL_CRC_BLOCK; }
                 if (__shfl_sync(FULL, out - crc_done, j) < QZ_INFL_CRC_BLOCK) cmask &= cmask - 1;
             }
         }

@@ -108,6 +108,13 @@ static inline uint32_t __reduce_or_sync(uint32_t, uint32_t v)
     for (int i = 0; i < 32; i++) if ((live >> i) & 1u) r |= (uint32_t)x[i];
     return r;
 }
+static inline uint32_t __reduce_xor_sync(uint32_t, uint32_t v)
+{
+    uint32_t live; const uint64_t *x = emu::exchange(emu::OP_REDUCE, v, &live);
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) if ((live >> i) & 1u) r ^= (uint32_t)x[i];
+    return r;
+}
 static inline uint32_t __reduce_max_sync(uint32_t, uint32_t v)
 {
     uint32_t live; const uint64_t *x = emu::exchange(emu::OP_REDUCE, v, &live);
